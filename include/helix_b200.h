@@ -1,0 +1,243 @@
+/*
+ * helix_b200.h — C ABI of the B200-native vector-search inner loop for HelixDB.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain
+ * pointers and sizes, returns an `hx_status` (0 = OK) and never throws or aborts.
+ * The reference (HelixDB, 100 % Rust) exposes no FFI for this path; the natural
+ * seam is the pair of methods every production vector query funnels through:
+ *
+ *   ValidatedVectorReadIndex::<D>::search             crates/db/src/search/vector/read_index.rs:81-90
+ *   ValidatedVectorReadIndex::<D>::search_restricted  crates/db/src/search/vector/read_index.rs:92-101
+ *     -> VectorIndex::<D>::search                     crates/db/src/search/vector/index.rs:1578-1587
+ *     -> VectorIndex::<D>::search_restricted          crates/db/src/search/vector/restricted.rs:466-479
+ *
+ * reached from the planner operators ExecNodeAccessPlan::VectorSearch
+ * (crates/planner/src/exec/access/node.rs:69-78) and ExecOp::VectorSearch
+ * (crates/planner/src/exec/op/operation.rs:26-29).  INTEGRATION.md shows the
+ * Rust `extern "C"` block a maintainer would add on the reference side.
+ *
+ * The device index is a *disposable mirror* of the reference's KV rows (like its
+ * resident VectorMemoryStore, memory_store.rs:97-130): vectors, per-row headers
+ * (cosine norm), the layer-0 and upper-layer neighbour rows, entry point and
+ * max layer are uploaded once and searched many times.
+ *
+ * Threading: an `hx_index*` may be searched concurrently from several host
+ * threads (each call takes a private stream + scratch block from a pool);
+ * load/build calls must not overlap searches on the same handle.
+ */
+#ifndef HELIX_B200_H
+#define HELIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+/* Mirrors the HelixDbError variants the reference can return on this path
+ * (crates/db/src/error.rs:379,415,433,467,631-661).  Query validation happens
+ * before any traversal and in this order: dimension -> finiteness -> cosine
+ * zero norm -> component magnitude (domain.rs:113-154). */
+typedef int32_t hx_status;
+enum {
+  HX_OK = 0,
+  HX_ERR_INDEX_NOT_FOUND = 1,          /* HelixDbError::IndexNotFound (null / destroyed handle)        */
+  HX_ERR_INVALID_DIMENSION = 2,        /* HelixDbError::InvalidDimension{expected,got}                  */
+  HX_ERR_INVALID_VECTOR_COMPONENT = 3, /* HelixDbError::InvalidVectorComponent{index} (NaN / Inf)       */
+  HX_ERR_ZERO_NORM_COSINE = 4,         /* HelixDbError::ZeroNormCosineVector                             */
+  HX_ERR_MAGNITUDE_EXCEEDED = 5,       /* HelixDbError::VectorComponentMagnitudeExceeded{..}             */
+  HX_ERR_INVALID_VECTOR_CONFIG = 6,    /* HelixDbError::InvalidVectorConfig                              */
+  HX_ERR_QUERY = 7,                    /* HelixDbError::Query(String): >1e6 candidates, restricted k>800 */
+  HX_ERR_INVARIANT_VIOLATION = 8,      /* HelixDbError::InvariantViolation: NaN/negative score, bad rows */
+  HX_ERR_INVALID_PARAMETER = 9,        /* VectorParameterError: k == 0, ef < k, null pointer             */
+  HX_ERR_CUDA = 10,                    /* a CUDA runtime call failed (see hx_last_error)                 */
+  HX_ERR_OUT_OF_MEMORY = 11,
+  HX_ERR_UNSUPPORTED = 12              /* e.g. SimHash Adaptive mode (parity unpinned)       */
+};
+
+/* ---- metrics -------------------------------------------------------------- */
+/* D in {Euclidean, Cosine, Manhattan} (search/dispatch.rs:127-188).
+ * Scores: Euclidean = squared L2 (spaces/simple.rs:204-218),
+ *         Cosine    = (1 - cos)/2 in [0,1] (distance/cosine.rs:96-118),
+ *         Manhattan = L1 (spaces/simple.rs:186-202).  All f32. */
+typedef enum {
+  HX_METRIC_EUCLIDEAN = 0,
+  HX_METRIC_COSINE = 1,
+  HX_METRIC_MANHATTAN = 2
+} hx_metric;
+
+/* ---- index configuration --------------------------------------------------- */
+/* Mirrors VectorIndexDefinition / VectorIndexConfig defaults
+ * (crates/db/src/config/indexes.rs:374-408): m=16, m0=32, ef_construction=200. */
+typedef struct {
+  uint32_t dimension;       /* > 0                                                     */
+  int32_t  metric;          /* hx_metric                                               */
+  uint32_t m;               /* upper-layer degree limit                                */
+  uint32_t m0;              /* configured layer-0 degree; effective = max(m0, 2m)      */
+  uint32_t ef_construction; /* used by hx_index_build                                  */
+  int32_t  device;          /* CUDA device ordinal (one process per GPU: LOCAL_RANK)   */
+  uint32_t storage;         /* 0 = f32 rows (parity path), 1 = also keep a bf16 copy
+                               for the tensor-core batched path (hx_search_dense)     */
+  uint32_t reserved;
+} hx_index_config;
+
+/* ---- per-query parameters ---------------------------------------------------- */
+/* Mirrors SearchParams (search/vector/mod.rs:411-621).  SearchParams::new(k):
+ * ef = max(k, 100).  mode HX_SIMHASH_OFF + pre_sampling_ratio 1.0 is the
+ * reference's strict-exhaustive specialisation (STRICT_EXHAUSTIVE, search.rs:
+ * 296-304,595-596) — the only mode whose results are pinned. */
+typedef enum { HX_SIMHASH_OFF = 0, HX_SIMHASH_ADAPTIVE = 1, HX_SIMHASH_ALWAYS = 2 } hx_simhash_mode;
+
+typedef struct {
+  uint32_t k;                  /* results per query, > 0                                */
+  uint32_t ef;                 /* beam width, >= k; 0 => max(k,100)                    */
+  int32_t  simhash_mode;       /* hx_simhash_mode; only HX_SIMHASH_OFF is executed      */
+  float    pre_sampling_ratio; /* must be 1.0 (strict exhaustive)                       */
+  uint32_t collect_stats;      /* fill hx_stats (per-call sums)                         */
+  uint32_t reserved;
+} hx_search_params;
+
+/* Counter semantics mirror SearchStats (search/vector/mod.rs:668-679):
+ * expansion_steps counts every candidate pop including the one that triggers the
+ * stop test (search.rs:538-551); neighbors_examined sums full row lengths before
+ * the visited filter (:579-581); distance_computations includes the entry point
+ * (:511-513).  Sums over the B queries of the call. */
+typedef struct {
+  uint64_t expansion_steps;
+  uint64_t neighbors_examined;
+  uint64_t distance_computations;
+  uint64_t vectors_loaded;
+  uint64_t upper_layer_steps;   /* greedy moves above layer 0 (not in the reference's stats) */
+  uint64_t algorithmic_bytes;   /* E*(5+8*deg) + Dc*(4+4d), SURVEY §8(d)                    */
+  uint64_t kernel_launches;     /* launches of OUR kernels issued by the call               */
+  uint64_t reserved;
+} hx_stats;
+
+typedef struct hx_index hx_index;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+hx_status hx_index_create(const hx_index_config* cfg, hx_index** out);
+void      hx_index_destroy(hx_index* idx);
+
+/* Upload n rows.  `ids` need not be sorted; rows are re-ordered so that device slot
+ * order == ascending id order (the reference canonicalises neighbour rows to
+ * ascending node id, encoding/v1/values/vectors.rs:67-110, so slot order makes the
+ * (score, id) tie rule a single 64-bit compare).  Every row is validated like
+ * decode_item_borrowed (mod.rs:889-949): finite, magnitude bound, non-zero for
+ * cosine.  Replaces any previous contents. */
+hx_status hx_index_load_vectors(hx_index* idx, const uint64_t* ids, const float* rows, size_t n);
+
+/* Generate vectors on the device instead (bench only; no PCIe copy):
+ * kind 0 = unit-normalised Gaussian mixture, ids = first_id..first_id+n-1.
+ * Queries for the same mixture: hx_generate_queries. */
+hx_status hx_index_generate_vectors(hx_index* idx, uint64_t first_id, size_t n, uint64_t seed,
+                                    uint32_t n_centroids, float sigma);
+hx_status hx_generate_queries(hx_index* idx, uint64_t seed, uint32_t n_centroids, float sigma,
+                              uint64_t first_query, size_t n_queries, float* out_host);
+/* Copy rows [first_slot, first_slot+n) (slot order) back to the host (f32, n*dimension). */
+hx_status hx_index_download_vectors(hx_index* idx, size_t first_slot, size_t n, float* out_rows,
+                                    uint64_t* out_ids);
+
+/* Mirror one HNSW layer.  layer 0 rows = layer-0 neighbour rows
+ * `[0x12][count u32 BE][id u64 BE x <= m0]`, layers >= 1 = upper rows
+ * (encoding/v1/values/vectors/neighbors.rs:57-76) — passed here decoded, CSR style:
+ * node_ids[i] owns neighbors[offsets[i] .. offsets[i+1]).  Neighbour ids without a
+ * vector row are kept out of the device rows but still counted in
+ * neighbors_examined (the reference skips them at fetch time, search.rs:909-913). */
+hx_status hx_index_load_graph(hx_index* idx, uint16_t layer, const uint64_t* node_ids,
+                              const uint32_t* offsets, const uint64_t* neighbors, size_t n_nodes);
+/* VectorIndexState::Populated{entry_point,max_layer} (configuration.rs). */
+hx_status hx_index_set_entry(hx_index* idx, uint64_t entry_point, uint16_t max_layer);
+
+/* Build the HNSW graph on the device from the loaded vectors (SURVEY §8(f).1:
+ * insert_hnsw / search_layer_beam / select_diverse / add_bidirectional_link,
+ * mutation.rs:787-1005,1498-1591, restated as batched concurrent insertion).
+ * `levels` (n entries, slot order of ascending id) may be NULL => drawn from `seed`
+ * with select_layer's law floor(-ln(U)*ml), ml = 1/ln(m) (mod.rs:769-796). */
+hx_status hx_index_build(hx_index* idx, const uint16_t* levels, uint64_t seed);
+
+/* Download the graph (for the CPU oracle to traverse the identical adjacency). */
+hx_status hx_index_graph_info(hx_index* idx, uint64_t* n_nodes, uint64_t* entry_point,
+                              uint16_t* max_layer, uint32_t* layer0_stride, uint32_t* upper_stride);
+hx_status hx_index_download_graph(hx_index* idx, uint16_t* levels /*n*/, uint32_t* deg0 /*n*/,
+                                  uint32_t* nbr0 /*n*layer0_stride, slot numbers*/,
+                                  uint64_t* n_upper_rows, uint32_t* upper_node /*cap*/,
+                                  uint16_t* upper_layer /*cap*/, uint32_t* upper_deg /*cap*/,
+                                  uint32_t* upper_nbr /*cap*upper_stride*/, size_t upper_cap);
+
+/* ---- search (host buffers: the reference-facing call) ------------------------------ */
+/* VectorIndex::search (index.rs:1578) -> SearchSession::run (search.rs:1101-1230):
+ * validate query, greedy descent layers max_layer..1 (search.rs:169-224), layer-0
+ * beam (search.rs:267-1067, strict-exhaustive), results sorted by (score,id),
+ * truncated to k.  B independent queries, no cross-query sharing.
+ * out_ids/out_scores are B*k; out_counts[b] <= k.  Empty index => counts 0, HX_OK. */
+hx_status hx_search(hx_index* idx, const float* queries, size_t B, const hx_search_params* p,
+                    uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats);
+
+/* VectorIndex::search_restricted (restricted.rs:466-613), exact branch
+ * restricted_exact_scan (restricted.rs:753-835) executed for ANY |C| <= 1e6.
+ * cand_ids: ascending unique u64 (RoaringTreemap iteration order), shared by the B
+ * queries.  k is clamped to |C| and must then be <= 800 (restricted.rs:200-213).
+ * Empty candidate set => counts 0 before any device work (restricted.rs:539-541). */
+hx_status hx_search_restricted(hx_index* idx, const float* queries, size_t B,
+                               const hx_search_params* p, const uint64_t* cand_ids, size_t n_cand,
+                               uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
+                               hx_stats* stats);
+/* Same, one candidate set per query: query b owns cand_ids[cand_offsets[b]..cand_offsets[b+1]). */
+hx_status hx_search_restricted_multi(hx_index* idx, const float* queries, size_t B,
+                                     const hx_search_params* p, const uint64_t* cand_ids,
+                                     const uint64_t* cand_offsets, uint64_t* out_ids,
+                                     float* out_scores, uint32_t* out_counts, hx_stats* stats);
+
+/* RestrictedExecutionPlan chosen by the reference for this |C| and dimension
+ * (restricted.rs:40-42,426-453): 0 = Exact, 1 = FilteredGraph.  Informational: the
+ * device path always answers exactly. */
+int32_t hx_restricted_plan(uint64_t n_candidates, uint32_t dimension);
+
+/* ---- search (device buffers: inputs already resident in HBM) ------------------------- */
+/* Same semantics, no validation copy, no host sync: everything is enqueued on
+ * `cuda_stream` (a cudaStream_t, 0 = legacy default stream).  d_queries must have been
+ * validated by the caller.  Used by bench.py for `value`, and by the sharded path. */
+hx_status hx_search_device(hx_index* idx, const float* d_queries, size_t B,
+                           const hx_search_params* p, uint64_t* d_out_ids, float* d_out_scores,
+                           uint32_t* d_out_counts, void* cuda_stream, hx_stats* stats_or_null);
+/* Candidates as device slot numbers (ascending), per query CSR. */
+hx_status hx_search_restricted_device(hx_index* idx, const float* d_queries, size_t B,
+                                      const hx_search_params* p, const uint32_t* d_cand_slots,
+                                      const uint64_t* d_cand_offsets, uint64_t total_cands,
+                                      uint64_t* d_out_ids, float* d_out_scores,
+                                      uint32_t* d_out_counts, void* cuda_stream);
+/* Map ascending candidate ids to device slots (absent ids dropped, restricted.rs:615-659). */
+hx_status hx_map_candidates_device(hx_index* idx, const uint64_t* d_cand_ids, uint64_t n,
+                                   uint32_t* d_out_slots, uint64_t* d_out_count, void* cuda_stream);
+
+/* ---- sharded path: merge of per-shard top-k ------------------------------ */
+/* After ONE all-gather of per-shard (score,id,count) blocks over NCCL, every rank selects
+ * the k smallest by (score,id) per query.  d_all_* are [n_shards][B][k] / [n_shards][B]. */
+hx_status hx_merge_topk_device(int32_t device, const uint64_t* d_all_ids, const float* d_all_scores,
+                               const uint32_t* d_all_counts, uint32_t n_shards, size_t B, uint32_t k,
+                               uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts,
+                               void* cuda_stream);
+
+/* ---- dense batched path (tensor cores; configs C4/C5) ---------------------------------- */
+/* Exhaustive top-k of B queries against all rows through the bf16 copy:
+ * tcgen05 MMA for the B x N contraction, per-tile candidate filter, fp32 re-rank of
+ * survivors with the exact kernel.  Requires cfg.storage == 1. */
+hx_status hx_search_dense(hx_index* idx, const float* queries, size_t B, const hx_search_params* p,
+                          uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
+                          hx_stats* stats);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+const char* hx_last_error(void);          /* thread-local, valid until the next failing call     */
+uint32_t    hx_last_error_index(void);    /* component index for HX_ERR_INVALID_VECTOR_COMPONENT */
+const char* hx_version(void);
+/* Launch duration (ms, CUDA events on the launch stream) of the dominant kernel of the most
+ * recent search call on this handle, and the number of launches it covered. */
+hx_status hx_last_kernel_ms(hx_index* idx, float* ms, uint32_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HELIX_B200_H */

@@ -1,0 +1,1432 @@
+/*
+ * hx_oracle.c — CPU restatement of HelixDB's vector-search hot path (see hx_oracle.h).
+ *
+ * TEST INFRASTRUCTURE ONLY — never linked into the product library.
+ *
+ * Build with -ffp-contract=off and without -ffast-math: the reference is Rust, which
+ * never contracts a*b+c and never re-associates float sums; the only fused operations
+ * are the explicit _mm256_fmadd_ps calls of spaces/simple_avx.rs.
+ *
+ * All "V/" paths are /root/reference/crates/db/src/search/vector/.
+ */
+#define _GNU_SOURCE
+#include "hx_oracle.h"
+
+#include <float.h>
+#include <immintrin.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------------------------------
+ * Distance kernels
+ * ------------------------------------------------------------------------------------------ */
+
+/* V/spaces/simple.rs:204-218 — `distance += (l - r) * (l - r)`, strictly sequential, no FMA. */
+float hxo_euclid_scalar(const float* u, const float* v, size_t d) {
+  float distance = 0.0f;
+  for (size_t i = 0; i < d; ++i) {
+    float diff = u[i] - v[i];
+    float sq = diff * diff;
+    distance = distance + sq;
+  }
+  return distance;
+}
+
+/* V/spaces/simple.rs:220-234 */
+float hxo_dot_scalar(const float* u, const float* v, size_t d) {
+  float product = 0.0f;
+  for (size_t i = 0; i < d; ++i) {
+    float p = u[i] * v[i];
+    product = product + p;
+  }
+  return product;
+}
+
+/* V/spaces/simple.rs:186-202 — `distance += (l - r).abs()`, sequential; the reference has no SIMD path. */
+float hxo_manhattan(const float* u, const float* v, size_t d) {
+  float distance = 0.0f;
+  for (size_t i = 0; i < d; ++i) {
+    float diff = u[i] - v[i];
+    distance = distance + fabsf(diff);
+  }
+  return distance;
+}
+
+int hxo_has_avx_fma(void) {
+  return __builtin_cpu_supports("avx") && __builtin_cpu_supports("fma");
+}
+
+/* V/spaces/simple_avx.rs:6-12 hsum256_ps_avx */
+__attribute__((target("avx,fma"))) static float hsum256(__m256 x) {
+  __m128 x128 = _mm_add_ps(_mm256_extractf128_ps(x, 1), _mm256_castps256_ps128(x));
+  __m128 x64 = _mm_add_ps(x128, _mm_movehl_ps(x128, x128));
+  __m128 x32 = _mm_add_ss(x64, _mm_shuffle_ps(x64, x64, 0x55));
+  return _mm_cvtss_f32(x32);
+}
+
+/* V/spaces/simple_avx.rs:128-180 euclid_similarity_avx_fma */
+__attribute__((target("avx,fma"))) float hxo_euclid_avx_fma(const float* p1, const float* p2, size_t n) {
+  size_t m = n - (n % 32);
+  __m256 s1 = _mm256_setzero_ps(), s2 = _mm256_setzero_ps(), s3 = _mm256_setzero_ps(), s4 = _mm256_setzero_ps();
+  size_t i = 0;
+  while (i < m) {
+    __m256 d1 = _mm256_sub_ps(_mm256_loadu_ps(p1), _mm256_loadu_ps(p2));
+    s1 = _mm256_fmadd_ps(d1, d1, s1);
+    __m256 d2 = _mm256_sub_ps(_mm256_loadu_ps(p1 + 8), _mm256_loadu_ps(p2 + 8));
+    s2 = _mm256_fmadd_ps(d2, d2, s2);
+    __m256 d3 = _mm256_sub_ps(_mm256_loadu_ps(p1 + 16), _mm256_loadu_ps(p2 + 16));
+    s3 = _mm256_fmadd_ps(d3, d3, s3);
+    __m256 d4 = _mm256_sub_ps(_mm256_loadu_ps(p1 + 24), _mm256_loadu_ps(p2 + 24));
+    s4 = _mm256_fmadd_ps(d4, d4, s4);
+    p1 += 32;
+    p2 += 32;
+    i += 32;
+  }
+  __m256 sum = _mm256_add_ps(_mm256_add_ps(s1, s2), _mm256_add_ps(s3, s4));
+  float result = hsum256(sum);
+  for (size_t t = 0; t < n - m; ++t) {
+    float a = p1[t], b = p2[t];
+    float d = a - b;
+    float sq = d * d;
+    result = result + sq;
+  }
+  return result;
+}
+
+/* V/spaces/simple_avx.rs:184-238 dot_similarity_avx_fma */
+__attribute__((target("avx,fma"))) float hxo_dot_avx_fma(const float* p1, const float* p2, size_t n) {
+  size_t m = n - (n % 32);
+  __m256 s1 = _mm256_setzero_ps(), s2 = _mm256_setzero_ps(), s3 = _mm256_setzero_ps(), s4 = _mm256_setzero_ps();
+  size_t i = 0;
+  while (i < m) {
+    s1 = _mm256_fmadd_ps(_mm256_loadu_ps(p1), _mm256_loadu_ps(p2), s1);
+    s2 = _mm256_fmadd_ps(_mm256_loadu_ps(p1 + 8), _mm256_loadu_ps(p2 + 8), s2);
+    s3 = _mm256_fmadd_ps(_mm256_loadu_ps(p1 + 16), _mm256_loadu_ps(p2 + 16), s3);
+    s4 = _mm256_fmadd_ps(_mm256_loadu_ps(p1 + 24), _mm256_loadu_ps(p2 + 24), s4);
+    p1 += 32;
+    p2 += 32;
+    i += 32;
+  }
+  __m256 sum = _mm256_add_ps(_mm256_add_ps(s1, s2), _mm256_add_ps(s3, s4));
+  float result = hsum256(sum);
+  for (size_t t = 0; t < n - m; ++t) {
+    float p = p1[t] * p2[t];
+    result = result + p;
+  }
+  return result;
+}
+
+/* The same accumulation order spelled with scalar fmaf(): 32 independent accumulators
+ * (accumulator a, lane j  <->  element index i with i mod 32 == 8a + j), then
+ * (s1+s2)+(s3+s4) per lane, then hsum256's tree, then the scalar tail.  This is the form
+ * the CUDA kernels implement; it must equal the intrinsic version bit for bit. */
+static float avx_order_reduce(const float acc[32]) {
+  float lane[8];
+  for (int j = 0; j < 8; ++j) {
+    float a = acc[j] + acc[8 + j];
+    float b = acc[16 + j] + acc[24 + j];
+    lane[j] = a + b;
+  }
+  float x128[4];
+  for (int j = 0; j < 4; ++j) x128[j] = lane[4 + j] + lane[j];
+  float x64_0 = x128[0] + x128[2];
+  float x64_1 = x128[1] + x128[3];
+  return x64_0 + x64_1;
+}
+
+float hxo_euclid_avx_fma_portable(const float* u, const float* v, size_t n) {
+  size_t m = n - (n % 32);
+  float acc[32];
+  for (int l = 0; l < 32; ++l) acc[l] = 0.0f;
+  for (size_t i = 0; i < m; i += 32)
+    for (int l = 0; l < 32; ++l) {
+      float d = u[i + l] - v[i + l];
+      acc[l] = fmaf(d, d, acc[l]);
+    }
+  float result = avx_order_reduce(acc);
+  for (size_t i = m; i < n; ++i) {
+    float d = u[i] - v[i];
+    float sq = d * d;
+    result = result + sq;
+  }
+  return result;
+}
+
+float hxo_dot_avx_fma_portable(const float* u, const float* v, size_t n) {
+  size_t m = n - (n % 32);
+  float acc[32];
+  for (int l = 0; l < 32; ++l) acc[l] = 0.0f;
+  for (size_t i = 0; i < m; i += 32)
+    for (int l = 0; l < 32; ++l) acc[l] = fmaf(u[i + l], v[i + l], acc[l]);
+  float result = avx_order_reduce(acc);
+  for (size_t i = m; i < n; ++i) {
+    float p = u[i] * v[i];
+    result = result + p;
+  }
+  return result;
+}
+
+/* V/spaces/simple.rs:120-144: on x86_64 with avx+fma detected, AvxFma is used iff len >= 32
+ * (MIN_DIM_SIZE_AVX, simple.rs:32); because float_simd() then returns AvxFma, the Sse arm never
+ * matches, so every len < 32 takes the scalar loop.  The oracle always models that machine
+ * (the reference's CI kernel-equivalence matrix and this container's host both have avx+fma). */
+float hxo_euclidean_distance(const float* u, const float* v, size_t d) {
+  if (d >= 32) return hxo_has_avx_fma() ? hxo_euclid_avx_fma(u, v, d) : hxo_euclid_avx_fma_portable(u, v, d);
+  return hxo_euclid_scalar(u, v, d);
+}
+/* V/spaces/simple.rs:155-177 */
+float hxo_dot_product(const float* u, const float* v, size_t d) {
+  if (d >= 32) return hxo_has_avx_fma() ? hxo_dot_avx_fma(u, v, d) : hxo_dot_avx_fma_portable(u, v, d);
+  return hxo_dot_scalar(u, v, d);
+}
+
+/* V/distance/cosine.rs:12-36 scaled_l2_norm */
+double hxo_scaled_l2_norm(const float* v, size_t d) {
+  double scale = 0.0, scaled_sum = 1.0;
+  for (size_t i = 0; i < d; ++i) {
+    double magnitude = (double)fabsf(v[i]);
+    if (magnitude == 0.0) continue;
+    if (scale < magnitude) {
+      double ratio = scale / magnitude;
+      scaled_sum = 1.0 + scaled_sum * ratio * ratio;
+      scale = magnitude;
+    } else {
+      double ratio = magnitude / scale;
+      scaled_sum += ratio * ratio;
+    }
+  }
+  if (scale == 0.0) return 0.0;
+  return scale * sqrt(scaled_sum);
+}
+
+/* V/distance/cosine.rs:120-122 norm_no_header: `scaled_l2_norm(v).min(f32::MAX as f64) as f32` */
+float hxo_cosine_norm(const float* v, size_t d) {
+  double n = hxo_scaled_l2_norm(v, d);
+  double mx = (double)FLT_MAX;
+  if (n > mx) n = mx;
+  return (float)n;
+}
+
+/* new_header: Cosine -> norm (cosine.rs:89-93); Euclidean/Manhattan -> bias 0.0 (euclidean.rs:42-44) */
+float hxo_header(int metric, const float* v, size_t d) {
+  return metric == HXO_COSINE ? hxo_cosine_norm(v, d) : 0.0f;
+}
+
+/* V/distance/cosine.rs:39-59 stable_half_cosine */
+static float stable_half_cosine(const float* p, const float* q, size_t d) {
+  double pn = hxo_scaled_l2_norm(p, d), qn = hxo_scaled_l2_norm(q, d);
+  if (pn == 0.0 || qn == 0.0) return NAN;
+  double dot = 0.0;
+  for (size_t i = 0; i < d; ++i) dot += (double)p[i] * (double)q[i];
+  double c = dot / (pn * qn);
+  if (c < -1.0) c = -1.0;
+  if (c > 1.0) c = 1.0;
+  return (float)((1.0 - c) * 0.5);
+}
+
+/* V/distance/cosine.rs:96-118 */
+float hxo_cosine_distance(const float* p, float pn, const float* q, float qn, size_t d) {
+  float pq = hxo_dot_product(p, q, d);
+  float pnqn = pn * qn;
+  if (pn > 0.0f && qn > 0.0f && pn != FLT_MAX && qn != FLT_MAX && isnormal(pnqn) && isfinite(pq)) {
+    float c = pq / pnqn;
+    if (c < -1.0f) c = -1.0f;
+    if (c > 1.0f) c = 1.0f;
+    float one_minus = 1.0f - c;
+    return one_minus / 2.0f;
+  }
+  return stable_half_cosine(p, q, d);
+}
+
+float hxo_distance(int metric, const float* p, float p_hdr, const float* q, float q_hdr, size_t d) {
+  switch (metric) {
+    case HXO_EUCLIDEAN: return hxo_euclidean_distance(p, q, d);
+    case HXO_COSINE: return hxo_cosine_distance(p, p_hdr, q, q_hdr, d);
+    default: return hxo_manhattan(p, q, d);
+  }
+}
+
+/* V/parameters.rs:241-258 + V/model.rs:21-28: NaN / Inf / negative => InvariantViolation; -0 -> +0 */
+int hxo_score_validate(float* score) {
+  if (!isfinite(*score)) return HXO_ERR_INVARIANT_VIOLATION;
+  if (*score < 0.0f) return HXO_ERR_INVARIANT_VIOLATION;
+  if (*score == 0.0f) *score = 0.0f; /* normalize_zero */
+  return HXO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Input domain  V/domain.rs:15-160
+ * ------------------------------------------------------------------------------------------ */
+int hxo_component_limit(int metric, size_t d, float* limit) {
+  double factor;
+  if (metric == HXO_COSINE) return 0;
+  factor = metric == HXO_EUCLIDEAN ? 8.0 : 4.0;
+  double divisor = (double)((uint64_t)d * (uint64_t)factor);
+  double exact = metric == HXO_EUCLIDEAN ? sqrt((double)FLT_MAX / divisor) : (double)FLT_MAX / divisor;
+  float rounded = (float)exact;
+  if ((double)rounded > exact) {
+    uint32_t bits;
+    memcpy(&bits, &rounded, 4);
+    bits -= 1;
+    memcpy(&rounded, &bits, 4);
+  }
+  *limit = rounded;
+  return 1;
+}
+
+int hxo_validate_vector(int metric, size_t expected_d, const float* v, size_t actual_d, uint32_t* bad_index) {
+  if (bad_index) *bad_index = 0;
+  if (actual_d != expected_d) return HXO_ERR_INVALID_DIMENSION;
+  for (size_t i = 0; i < actual_d; ++i)
+    if (!isfinite(v[i])) {
+      if (bad_index) *bad_index = (uint32_t)i;
+      return HXO_ERR_INVALID_VECTOR_COMPONENT;
+    }
+  if (metric == HXO_COSINE) {
+    int all_zero = 1;
+    for (size_t i = 0; i < actual_d; ++i)
+      if (!(v[i] == 0.0f)) {
+        all_zero = 0;
+        break;
+      }
+    if (all_zero) return HXO_ERR_ZERO_NORM_COSINE;
+  }
+  float limit;
+  if (hxo_component_limit(metric, expected_d, &limit)) {
+    for (size_t i = 0; i < actual_d; ++i)
+      if (fabsf(v[i]) > limit) {
+        if (bad_index) *bad_index = (uint32_t)i;
+        return HXO_ERR_MAGNITUDE_EXCEEDED;
+      }
+  }
+  return HXO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Layer selection  V/mod.rs:705-709,769-796
+ * ------------------------------------------------------------------------------------------ */
+float hxo_default_ml_for_m(uint32_t m) {
+  float effective_m = (float)(m < 2 ? 2 : m);
+  return 1.0f / logf(effective_m);
+}
+
+uint16_t hxo_select_layer_from_uniform(float ml, float uniform) {
+  if (!(isfinite(ml) && ml > 0.0f)) ml = hxo_default_ml_for_m(16);
+  if (isfinite(uniform)) {
+    float lo = FLT_MIN, hi = 1.0f - FLT_EPSILON;
+    if (uniform < lo) uniform = lo;
+    if (uniform > hi) uniform = hi;
+  } else {
+    uniform = 0.5f;
+  }
+  float neg_ln = -logf(uniform);
+  float sampled = floorf(neg_ln * ml);
+  if (!isfinite(sampled) || sampled <= 0.0f) return 0;
+  if (sampled > 63.0f) sampled = 63.0f;
+  return (uint16_t)sampled;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Restricted planning  V/restricted.rs
+ * ------------------------------------------------------------------------------------------ */
+int hxo_restricted_plan(uint64_t n_candidates, uint32_t dimension) {
+  /* restricted.rs:40-42 thresholds, :426-453 plan */
+  uint64_t bytes = n_candidates * (uint64_t)dimension * 4u;
+  return (n_candidates <= 256 && bytes <= 4u * 1024u * 1024u) ? 0 : 1;
+}
+
+int hxo_restricted_result_count(uint32_t k, uint64_t n_candidates, uint32_t* out_k) {
+  /* restricted.rs:200-213; ResultCount::try_new rejects 0 */
+  uint64_t c = k < n_candidates ? k : n_candidates;
+  if (c == 0) return HXO_ERR_INVALID_PARAMETER;
+  if (c > 800) return HXO_ERR_QUERY;
+  *out_k = (uint32_t)c;
+  return HXO_OK;
+}
+
+size_t hxo_deterministic_sample_ids(const uint64_t* ids, size_t n, size_t limit, uint64_t* out) {
+  /* restricted.rs:321-342 */
+  size_t sample_count = limit < n ? limit : n;
+  if (sample_count == n) {
+    memcpy(out, ids, n * sizeof(uint64_t));
+    return n;
+  }
+  if (sample_count == 1) {
+    out[0] = ids[0];
+    return 1;
+  }
+  uint64_t last_rank = (uint64_t)n - 1;
+  for (size_t s = 0; s < sample_count; ++s) {
+    unsigned __int128 r = (unsigned __int128)s * last_rank / (unsigned __int128)(sample_count - 1);
+    out[s] = ids[(size_t)r];
+  }
+  return sample_count;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Fixtures
+ * ------------------------------------------------------------------------------------------ */
+void hxo_fixture_xorshift_vector(uint64_t entity_id, uint32_t d, float* out) {
+  uint64_t state = entity_id + 0x9e3779b97f4a7c15ULL;
+  for (uint32_t i = 0; i < d; ++i) {
+    state ^= state << 13;
+    state ^= state >> 7;
+    state ^= state << 17;
+    int32_t centered = (int32_t)(uint16_t)(state & 0xffff) - 32768;
+    out[i] = (float)centered / 32768.0f;
+  }
+}
+
+void hxo_fixture_circle_vector(uint64_t entity_id, uint64_t entity_count, float* out2) {
+  double angle = 6.283185307179586 /* std::f64::consts::TAU */ * (double)entity_id / (double)entity_count;
+  out2[0] = (float)cos(angle);
+  out2[1] = (float)sin(angle);
+}
+
+static int cmp_u64(const void* a, const void* b) {
+  uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+size_t hxo_fixture_skip_neighbors(uint64_t entity_id, uint64_t entity_count, uint64_t* out, size_t cap) {
+  uint64_t tmp[160];
+  size_t n = 0;
+  uint64_t offset = 1;
+  while (offset < entity_count) {
+    uint64_t forward = (entity_id - 1 + offset) % entity_count + 1;
+    uint64_t backward = (entity_id - 1 + entity_count - offset % entity_count) % entity_count + 1;
+    if (forward != entity_id && n < 160) tmp[n++] = forward;
+    if (backward != entity_id && n < 160) tmp[n++] = backward;
+    if (offset > UINT64_MAX / 2) break;
+    offset *= 2;
+  }
+  qsort(tmp, n, sizeof(uint64_t), cmp_u64);
+  size_t w = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (w == 0 || tmp[w - 1] != tmp[i]) tmp[w++] = tmp[i];
+  if (w > cap) w = cap;
+  memcpy(out, tmp, w * sizeof(uint64_t));
+  return w;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * In-memory index
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  uint16_t nlayers; /* rows for layers 1..nlayers (some may be absent => present[l]=0) */
+  uint8_t* present; /* [nlayers] */
+  uint32_t* deg;    /* [nlayers] */
+  uint32_t* raw;    /* [nlayers] row length including ids without vectors */
+  uint32_t* nbr;    /* [nlayers * capu_alloc] */
+  uint32_t cap;     /* per-row capacity */
+} upper_rows;
+
+struct hxo_index {
+  int metric;
+  uint32_t dim, m, m0, efc;
+  uint32_t lim_upper, lim0; /* MutationDegreeLimits: upper = m, layer0 = max(m0, 2m) (mutation.rs:179-199) */
+  uint32_t stride0;         /* storage stride for layer-0 rows (>= lim0 + 1, and >= any imported row) */
+  size_t n, cap;
+  uint64_t* ids;
+  float* vecs;
+  float* hdr;
+  uint8_t* has_vec;
+  uint8_t* has_row0;
+  uint32_t* nbr0;
+  uint32_t* deg0;
+  upper_rows** up;
+  int32_t* level; /* highest layer with a row, -1 none */
+  /* id -> slot */
+  uint64_t* hk;
+  uint32_t* hv;
+  size_t hcap, hcount;
+  int populated;
+  uint64_t entry_id;
+  uint16_t max_layer;
+  uint64_t count;
+};
+
+static uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+static void hash_grow(hxo_index* ix) {
+  size_t ncap = ix->hcap ? ix->hcap * 2 : 1024;
+  uint64_t* nk = (uint64_t*)malloc(ncap * sizeof(uint64_t));
+  uint32_t* nv = (uint32_t*)malloc(ncap * sizeof(uint32_t));
+  for (size_t i = 0; i < ncap; ++i) nv[i] = UINT32_MAX;
+  for (size_t i = 0; i < ix->hcap; ++i)
+    if (ix->hv[i] != UINT32_MAX) {
+      size_t p = mix64(ix->hk[i]) & (ncap - 1);
+      while (nv[p] != UINT32_MAX) p = (p + 1) & (ncap - 1);
+      nk[p] = ix->hk[i];
+      nv[p] = ix->hv[i];
+    }
+  free(ix->hk);
+  free(ix->hv);
+  ix->hk = nk;
+  ix->hv = nv;
+  ix->hcap = ncap;
+}
+
+static uint32_t slot_of(const hxo_index* ix, uint64_t id) {
+  if (!ix->hcap) return UINT32_MAX;
+  size_t p = mix64(id) & (ix->hcap - 1);
+  while (ix->hv[p] != UINT32_MAX) {
+    if (ix->hk[p] == id) return ix->hv[p];
+    p = (p + 1) & (ix->hcap - 1);
+  }
+  return UINT32_MAX;
+}
+
+static void reserve_nodes(hxo_index* ix, size_t want) {
+  if (want <= ix->cap) return;
+  size_t ncap = ix->cap ? ix->cap : 1024;
+  while (ncap < want) ncap *= 2;
+  ix->ids = (uint64_t*)realloc(ix->ids, ncap * sizeof(uint64_t));
+  ix->vecs = (float*)realloc(ix->vecs, ncap * (size_t)ix->dim * sizeof(float));
+  ix->hdr = (float*)realloc(ix->hdr, ncap * sizeof(float));
+  ix->has_vec = (uint8_t*)realloc(ix->has_vec, ncap);
+  ix->has_row0 = (uint8_t*)realloc(ix->has_row0, ncap);
+  ix->nbr0 = (uint32_t*)realloc(ix->nbr0, ncap * (size_t)ix->stride0 * sizeof(uint32_t));
+  ix->deg0 = (uint32_t*)realloc(ix->deg0, ncap * sizeof(uint32_t));
+  ix->up = (upper_rows**)realloc(ix->up, ncap * sizeof(upper_rows*));
+  ix->level = (int32_t*)realloc(ix->level, ncap * sizeof(int32_t));
+  ix->cap = ncap;
+}
+
+static uint32_t slot_get_or_create(hxo_index* ix, uint64_t id) {
+  uint32_t s = slot_of(ix, id);
+  if (s != UINT32_MAX) return s;
+  if ((ix->hcount + 1) * 2 > ix->hcap) hash_grow(ix);
+  reserve_nodes(ix, ix->n + 1);
+  s = (uint32_t)ix->n++;
+  ix->ids[s] = id;
+  ix->hdr[s] = 0.0f;
+  ix->has_vec[s] = 0;
+  ix->has_row0[s] = 0;
+  ix->deg0[s] = 0;
+  ix->up[s] = NULL;
+  ix->level[s] = -1;
+  size_t p = mix64(id) & (ix->hcap - 1);
+  while (ix->hv[p] != UINT32_MAX) p = (p + 1) & (ix->hcap - 1);
+  ix->hk[p] = id;
+  ix->hv[p] = s;
+  ix->hcount++;
+  return s;
+}
+
+hxo_index* hxo_index_new(int metric, uint32_t dim, uint32_t m, uint32_t m0, uint32_t ef_construction) {
+  if (dim == 0 || m == 0 || metric < 0 || metric > 2) return NULL;
+  hxo_index* ix = (hxo_index*)calloc(1, sizeof(hxo_index));
+  ix->metric = metric;
+  ix->dim = dim;
+  ix->m = m;
+  ix->m0 = m0;
+  ix->efc = ef_construction;
+  ix->lim_upper = m;
+  ix->lim0 = m0 >= 2 * m ? m0 : 2 * m;
+  ix->stride0 = ix->lim0 + 1;
+  return ix;
+}
+
+void hxo_index_free(hxo_index* ix) {
+  if (!ix) return;
+  for (size_t i = 0; i < ix->n; ++i)
+    if (ix->up[i]) {
+      free(ix->up[i]->present);
+      free(ix->up[i]->deg);
+      free(ix->up[i]->raw);
+      free(ix->up[i]->nbr);
+      free(ix->up[i]);
+    }
+  free(ix->ids);
+  free(ix->vecs);
+  free(ix->hdr);
+  free(ix->has_vec);
+  free(ix->has_row0);
+  free(ix->nbr0);
+  free(ix->deg0);
+  free(ix->up);
+  free(ix->level);
+  free(ix->hk);
+  free(ix->hv);
+  free(ix);
+}
+
+size_t hxo_index_len(const hxo_index* ix) { return (size_t)ix->count; }
+uint32_t hxo_index_layer0_limit(const hxo_index* ix) { return ix->lim0; }
+
+int hxo_index_state(const hxo_index* ix, uint64_t* entry_point, uint16_t* max_layer) {
+  if (!ix->populated) return 0;
+  if (entry_point) *entry_point = ix->entry_id;
+  if (max_layer) *max_layer = ix->max_layer;
+  return 1;
+}
+
+static void ensure_stride0(hxo_index* ix, uint32_t need) {
+  if (need <= ix->stride0) return;
+  uint32_t ns = ix->stride0;
+  while (ns < need) ns *= 2;
+  uint32_t* nn = (uint32_t*)malloc(ix->cap * (size_t)ns * sizeof(uint32_t));
+  for (size_t s = 0; s < ix->n; ++s)
+    memcpy(nn + s * (size_t)ns, ix->nbr0 + s * (size_t)ix->stride0, ix->deg0[s] * sizeof(uint32_t));
+  free(ix->nbr0);
+  ix->nbr0 = nn;
+  ix->stride0 = ns;
+}
+
+static upper_rows* upper_ensure(hxo_index* ix, uint32_t slot, uint16_t layer, uint32_t need_cap) {
+  upper_rows* u = ix->up[slot];
+  uint32_t cap = ix->lim_upper + 1;
+  if (need_cap > cap) cap = need_cap;
+  if (!u) {
+    u = (upper_rows*)calloc(1, sizeof(upper_rows));
+    u->cap = cap;
+    ix->up[slot] = u;
+  }
+  if (cap > u->cap) {
+    uint32_t* nn = (uint32_t*)calloc((size_t)u->nlayers * cap + 1, sizeof(uint32_t));
+    for (uint16_t l = 0; l < u->nlayers; ++l)
+      memcpy(nn + (size_t)l * cap, u->nbr + (size_t)l * u->cap, u->deg[l] * sizeof(uint32_t));
+    free(u->nbr);
+    u->nbr = nn;
+    u->cap = cap;
+  }
+  if (layer > u->nlayers) {
+    u->present = (uint8_t*)realloc(u->present, layer);
+    u->deg = (uint32_t*)realloc(u->deg, layer * sizeof(uint32_t));
+    u->raw = (uint32_t*)realloc(u->raw, layer * sizeof(uint32_t));
+    u->nbr = (uint32_t*)realloc(u->nbr, (size_t)layer * u->cap * sizeof(uint32_t));
+    for (uint16_t l = u->nlayers; l < layer; ++l) {
+      u->present[l] = 0;
+      u->deg[l] = 0;
+      u->raw[l] = 0;
+    }
+    u->nlayers = layer;
+  }
+  return u;
+}
+
+/* neighbour-row accessors: a missing row is the deployed empty-neighbour state
+ * (search.rs:152-153 `unwrap_or_default`, :201-203) */
+static const uint32_t* row_get(const hxo_index* ix, uint16_t layer, uint32_t slot, uint32_t* deg) {
+  if (layer == 0) {
+    *deg = ix->has_row0[slot] ? ix->deg0[slot] : 0;
+    return ix->nbr0 + (size_t)slot * ix->stride0;
+  }
+  const upper_rows* u = ix->up[slot];
+  if (!u || layer > u->nlayers || !u->present[layer - 1]) {
+    *deg = 0;
+    return NULL;
+  }
+  *deg = u->deg[layer - 1];
+  return u->nbr + (size_t)(layer - 1) * u->cap;
+}
+
+static int cmp_slot_by_id_ctx(const void* a, const void* b, void* ctx) {
+  const hxo_index* ix = (const hxo_index*)ctx;
+  uint64_t x = ix->ids[*(const uint32_t*)a], y = ix->ids[*(const uint32_t*)b];
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* stage_neighbors_vec_for_mutation (mutation.rs:1291-1307): canonical ascending node-id order */
+static void row_set(hxo_index* ix, uint16_t layer, uint32_t slot, const uint32_t* nbrs, uint32_t n) {
+  uint32_t* dst;
+  if (layer == 0) {
+    ensure_stride0(ix, n);
+    dst = ix->nbr0 + (size_t)slot * ix->stride0;
+    ix->has_row0[slot] = 1;
+    ix->deg0[slot] = n;
+  } else {
+    upper_rows* u = upper_ensure(ix, slot, layer, n);
+    dst = u->nbr + (size_t)(layer - 1) * u->cap;
+    u->present[layer - 1] = 1;
+    u->deg[layer - 1] = n;
+    u->raw[layer - 1] = n;
+  }
+  if (n) memmove(dst, nbrs, n * sizeof(uint32_t));
+  qsort_r(dst, n, sizeof(uint32_t), cmp_slot_by_id_ctx, ix);
+  if ((int32_t)layer > ix->level[slot]) ix->level[slot] = layer;
+}
+
+int hxo_index_put_vector(hxo_index* ix, uint64_t id, const float* v) {
+  uint32_t bad;
+  int rc = hxo_validate_vector(ix->metric, ix->dim, v, ix->dim, &bad);
+  if (rc) return rc;
+  uint32_t s = slot_get_or_create(ix, id);
+  memcpy(ix->vecs + (size_t)s * ix->dim, v, ix->dim * sizeof(float));
+  ix->hdr[s] = hxo_header(ix->metric, v, ix->dim);
+  if (!ix->has_vec[s]) ix->count++;
+  ix->has_vec[s] = 1;
+  return HXO_OK;
+}
+
+int hxo_index_put_vectors(hxo_index* ix, const uint64_t* ids, const float* rows, size_t n) {
+  reserve_nodes(ix, ix->n + n);
+  for (size_t i = 0; i < n; ++i) {
+    int rc = hxo_index_put_vector(ix, ids[i], rows + i * (size_t)ix->dim);
+    if (rc) return rc;
+  }
+  return HXO_OK;
+}
+
+int hxo_index_put_neighbors(hxo_index* ix, uint16_t layer, uint64_t id, const uint64_t* nbrs, size_t n) {
+  uint32_t s = slot_get_or_create(ix, id);
+  uint32_t* tmp = (uint32_t*)malloc((n + 1) * sizeof(uint32_t));
+  for (size_t i = 0; i < n; ++i) tmp[i] = slot_get_or_create(ix, nbrs[i]);
+  row_set(ix, layer, s, tmp, (uint32_t)n);
+  free(tmp);
+  return HXO_OK;
+}
+
+int hxo_index_set_entry(hxo_index* ix, uint64_t entry_point, uint16_t max_layer) {
+  ix->populated = 1;
+  ix->entry_id = entry_point;
+  ix->max_layer = max_layer;
+  return HXO_OK;
+}
+
+size_t hxo_index_node_ids(const hxo_index* ix, uint64_t* out, size_t cap) {
+  size_t w = 0;
+  for (size_t s = 0; s < ix->n && w < cap; ++s)
+    if (ix->has_vec[s]) out[w++] = ix->ids[s];
+  qsort(out, w, sizeof(uint64_t), cmp_u64);
+  return w;
+}
+
+int hxo_index_node_level(const hxo_index* ix, uint64_t id) {
+  uint32_t s = slot_of(ix, id);
+  return s == UINT32_MAX ? -1 : ix->level[s];
+}
+
+size_t hxo_index_get_neighbors(const hxo_index* ix, uint16_t layer, uint64_t id, uint64_t* out, size_t cap) {
+  uint32_t s = slot_of(ix, id);
+  if (s == UINT32_MAX) return 0;
+  uint32_t deg;
+  const uint32_t* r = row_get(ix, layer, s, &deg);
+  size_t w = 0;
+  for (uint32_t i = 0; i < deg && w < cap; ++i) out[w++] = ix->ids[r[i]];
+  return w;
+}
+
+int hxo_index_get_vector(const hxo_index* ix, uint64_t id, float* out) {
+  uint32_t s = slot_of(ix, id);
+  if (s == UINT32_MAX || !ix->has_vec[s]) return HXO_ERR_INDEX_NOT_FOUND;
+  memcpy(out, ix->vecs + (size_t)s * ix->dim, ix->dim * sizeof(float));
+  return HXO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Candidate ordering  V/model.rs:41-61: (score, then node_id)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float score;
+  uint32_t slot;
+} cand;
+
+static inline int cand_less(const hxo_index* ix, cand a, cand b) {
+  if (a.score < b.score) return 1;
+  if (a.score > b.score) return 0;
+  return ix->ids[a.slot] < ix->ids[b.slot];
+}
+
+typedef struct {
+  cand* a;
+  size_t n, cap;
+} heap;
+
+static void heap_reserve(heap* h, size_t want) {
+  if (want <= h->cap) return;
+  size_t nc = h->cap ? h->cap * 2 : 256;
+  while (nc < want) nc *= 2;
+  h->a = (cand*)realloc(h->a, nc * sizeof(cand));
+  h->cap = nc;
+}
+/* max==0: min-heap (BinaryHeap<Reverse<Candidate>>); max==1: max-heap (BinaryHeap<Candidate>) */
+static inline int heap_before(const hxo_index* ix, int max, cand a, cand b) {
+  return max ? cand_less(ix, b, a) : cand_less(ix, a, b);
+}
+static void heap_push(const hxo_index* ix, heap* h, int max, cand c) {
+  heap_reserve(h, h->n + 1);
+  size_t i = h->n++;
+  while (i > 0) {
+    size_t p = (i - 1) / 2;
+    if (!heap_before(ix, max, c, h->a[p])) break;
+    h->a[i] = h->a[p];
+    i = p;
+  }
+  h->a[i] = c;
+}
+static cand heap_pop(const hxo_index* ix, heap* h, int max) {
+  cand top = h->a[0];
+  cand last = h->a[--h->n];
+  size_t i = 0;
+  for (;;) {
+    size_t l = 2 * i + 1, r = l + 1;
+    if (l >= h->n) break;
+    size_t c = (r < h->n && heap_before(ix, max, h->a[r], h->a[l])) ? r : l;
+    if (!heap_before(ix, max, h->a[c], last)) break;
+    h->a[i] = h->a[c];
+    i = c;
+  }
+  if (h->n) h->a[i] = last;
+  return top;
+}
+
+static int cmp_cand_ctx(const void* a, const void* b, void* ctx) {
+  const hxo_index* ix = (const hxo_index*)ctx;
+  cand x = *(const cand*)a, y = *(const cand*)b;
+  if (cand_less(ix, x, y)) return -1;
+  if (cand_less(ix, y, x)) return 1;
+  return 0;
+}
+
+/* per-thread scratch */
+typedef struct {
+  uint32_t* stamp;
+  size_t stamp_n;
+  uint32_t epoch;
+  heap cands, w;
+  uint32_t* frontier;
+  size_t frontier_cap;
+} scratch;
+
+static void scratch_begin(scratch* sc, size_t n) {
+  if (sc->stamp_n < n) {
+    free(sc->stamp);
+    sc->stamp = (uint32_t*)calloc(n, sizeof(uint32_t));
+    sc->stamp_n = n;
+    sc->epoch = 0;
+  }
+  if (++sc->epoch == 0) {
+    memset(sc->stamp, 0, sc->stamp_n * sizeof(uint32_t));
+    sc->epoch = 1;
+  }
+  sc->cands.n = 0;
+  sc->w.n = 0;
+}
+static void scratch_free(scratch* sc) {
+  free(sc->stamp);
+  free(sc->cands.a);
+  free(sc->w.a);
+  free(sc->frontier);
+  memset(sc, 0, sizeof(*sc));
+}
+static inline int visited_insert(scratch* sc, uint32_t slot) { /* HashSet::insert: 1 if newly inserted */
+  if (sc->stamp[slot] == sc->epoch) return 0;
+  sc->stamp[slot] = sc->epoch;
+  return 1;
+}
+static inline int visited_contains(const scratch* sc, uint32_t slot) { return sc->stamp[slot] == sc->epoch; }
+
+static inline float dist_q(const hxo_index* ix, const float* q, float q_hdr, uint32_t slot) {
+  return hxo_distance(ix->metric, q, q_hdr, ix->vecs + (size_t)slot * ix->dim, ix->hdr[slot], ix->dim);
+}
+
+/* V/search.rs:169-224 search_layer_greedy (and its mutation twin mutation.rs:1008-1064) */
+static int greedy_slot(const hxo_index* ix, scratch* sc, const float* q, float q_hdr, uint32_t entry_slot,
+                       uint16_t layer, uint32_t* out_slot, hxo_stats* st) {
+  scratch_begin(sc, ix->n);
+  uint32_t current = entry_slot;
+  if (entry_slot == UINT32_MAX || !ix->has_vec[entry_slot]) { /* missing entry item: return entry unchanged */
+    *out_slot = entry_slot;
+    return HXO_OK;
+  }
+  float current_dist = dist_q(ix, q, q_hdr, current);
+  int rc = hxo_score_validate(&current_dist);
+  if (rc) return rc;
+  visited_insert(sc, current);
+  for (;;) {
+    uint32_t deg;
+    const uint32_t* nbrs = row_get(ix, layer, current, &deg);
+    int changed = 0;
+    for (uint32_t i = 0; i < deg; ++i) {
+      uint32_t nb = nbrs[i];
+      if (!visited_insert(sc, nb)) continue;
+      if (!ix->has_vec[nb]) continue;
+      float d = dist_q(ix, q, q_hdr, nb);
+      rc = hxo_score_validate(&d);
+      if (rc) return rc;
+      if (d < current_dist) {
+        current = nb;
+        current_dist = d;
+        changed = 1;
+      }
+    }
+    if (!changed) break;
+    if (st) st->upper_layer_steps++;
+  }
+  *out_slot = current;
+  return HXO_OK;
+}
+
+static __thread scratch tls_scratch;
+
+int hxo_search_layer_greedy(const hxo_index* ix, const float* query, uint64_t entry, uint16_t layer,
+                            uint64_t* out_node) {
+  uint32_t es = slot_of(ix, entry);
+  if (es == UINT32_MAX) { /* unknown entry is returned unchanged (tests/.../search.rs:268-274) */
+    *out_node = entry;
+    return HXO_OK;
+  }
+  float qh = hxo_header(ix->metric, query, ix->dim);
+  uint32_t out;
+  int rc = greedy_slot(ix, &tls_scratch, query, qh, es, layer, &out, NULL);
+  if (rc) return rc;
+  *out_node = ix->ids[out];
+  return HXO_OK;
+}
+
+/* V/search.rs:267-1067 with STRICT_EXHAUSTIVE = true: SimHashDecision::exhaustive() (:595-596), no
+ * pre-sampling, no filter, every unvisited neighbour admitted to scoring and marked visited
+ * (:830-831, mark_sampled_neighbors_visited :89-97), simhash_fill_slots stays 0. */
+static int layer0_strict(const hxo_index* ix, scratch* sc, const float* q, float q_hdr, uint32_t entry_slot,
+                         uint32_t ef, hxo_stats* st) {
+  scratch_begin(sc, ix->n);
+  if (entry_slot == UINT32_MAX || !ix->has_vec[entry_slot]) return HXO_OK; /* :463-499 empty results */
+  float entry_dist = dist_q(ix, q, q_hdr, entry_slot);
+  if (st) st->distance_computations++;
+  int rc = hxo_score_validate(&entry_dist);
+  if (rc) return rc;
+  cand e = {entry_dist, entry_slot};
+  heap_push(ix, &sc->cands, 0, e);
+  heap_push(ix, &sc->w, 1, e);
+  visited_insert(sc, entry_slot);
+
+  while (sc->cands.n) {
+    if (st) st->expansion_steps++;
+    cand current = heap_pop(ix, &sc->cands, 0);
+    if (sc->w.n >= ef && current.score > sc->w.a[0].score) break; /* :549 */
+
+    uint32_t deg;
+    const uint32_t* nbrs = row_get(ix, 0, current.slot, &deg);
+    if (st) st->neighbors_examined += deg;
+    if (sc->frontier_cap < deg) {
+      sc->frontier = (uint32_t*)realloc(sc->frontier, (deg + 64) * sizeof(uint32_t));
+      sc->frontier_cap = deg + 64;
+    }
+    uint32_t nf = 0;
+    for (uint32_t i = 0; i < deg; ++i)
+      if (!visited_contains(sc, nbrs[i])) sc->frontier[nf++] = nbrs[i]; /* :583-589 */
+    if (!nf) continue;
+    for (uint32_t i = 0; i < nf; ++i) visited_insert(sc, sc->frontier[i]); /* :830-831 */
+    for (uint32_t i = 0; i < nf; ++i) {                                     /* :909-953, neighbour-id order */
+      uint32_t nb = sc->frontier[i];
+      if (!ix->has_vec[nb]) continue; /* :910-912 */
+      if (st) st->vectors_loaded++;
+      float d = dist_q(ix, q, q_hdr, nb);
+      if (st) st->distance_computations++;
+      rc = hxo_score_validate(&d);
+      if (rc) return rc;
+      if (d < sc->w.a[0].score || sc->w.n < ef) { /* :935 */
+        cand c = {d, nb};
+        heap_push(ix, &sc->cands, 0, c);
+        heap_push(ix, &sc->w, 1, c);
+        while (sc->w.n > ef) heap_pop(ix, &sc->w, 1); /* :947-952 */
+      }
+    }
+  }
+  return HXO_OK;
+}
+
+static int search_impl(const hxo_index* ix, scratch* sc, const float* query, uint32_t query_dim, uint32_t k,
+                       uint32_t ef, uint64_t* out_ids, float* out_scores, uint32_t* out_count, hxo_stats* st) {
+  *out_count = 0;
+  if (k == 0) return HXO_ERR_INVALID_PARAMETER;      /* ResultCount::try_new */
+  if (ef == 0) ef = k > 100 ? k : 100;               /* SearchParams::new mod.rs:482-487 */
+  if (ef < k) return HXO_ERR_INVALID_PARAMETER;      /* SearchBeamWidth::try_new */
+  uint32_t bad;
+  int rc = hxo_validate_vector(ix->metric, ix->dim, query, query_dim, &bad); /* search.rs:1120-1125 */
+  if (rc) return rc;
+  if (!ix->populated) return HXO_OK;                 /* search.rs:1127-1128 */
+  float qh = hxo_header(ix->metric, query, ix->dim); /* search.rs:1135-1138 */
+  uint32_t entry = slot_of(ix, ix->entry_id);
+  for (int layer = ix->max_layer; layer >= 1; --layer) { /* search.rs:1150-1156 */
+    if (entry == UINT32_MAX) break;
+    rc = greedy_slot(ix, sc, query, qh, entry, (uint16_t)layer, &entry, st);
+    if (rc) return rc;
+  }
+  rc = layer0_strict(ix, sc, query, qh, entry, ef, st);
+  if (rc) return rc;
+  /* search.rs:994-1004 sort by (score,id); :1229 take(k) */
+  qsort_r(sc->w.a, sc->w.n, sizeof(cand), cmp_cand_ctx, (void*)ix);
+  uint32_t n = sc->w.n < k ? (uint32_t)sc->w.n : k;
+  for (uint32_t i = 0; i < n; ++i) {
+    out_ids[i] = ix->ids[sc->w.a[i].slot];
+    out_scores[i] = sc->w.a[i].score;
+  }
+  *out_count = n;
+  return HXO_OK;
+}
+
+int hxo_search(const hxo_index* ix, const float* query, uint32_t query_dim, uint32_t k, uint32_t ef,
+               uint64_t* out_ids, float* out_scores, uint32_t* out_count, hxo_stats* stats) {
+  if (stats) memset(stats, 0, sizeof(*stats));
+  return search_impl(ix, &tls_scratch, query, query_dim, k, ef, out_ids, out_scores, out_count, stats);
+}
+
+/* V/restricted.rs:753-835 restricted_exact_scan (+ :661-704 restricted_score_keys): iterate the bitmap
+ * ascending, skip ids without a vector row (:615-659 — an id present in the graph but lacking its
+ * SimHash row is an error there; the flat image has no SimHash rows), keep the k smallest by
+ * (score,id) in a max-heap, sort. */
+static int restricted_impl(const hxo_index* ix, scratch* sc, const float* query, uint32_t query_dim, uint32_t k,
+                           const uint64_t* cand_ids, size_t n_cand, uint64_t* out_ids, float* out_scores,
+                           uint32_t* out_count, uint64_t* ndist) {
+  *out_count = 0;
+  if (ndist) *ndist = 0;
+  if (n_cand == 0) return HXO_OK; /* RestrictedVectorCandidates::Empty, restricted.rs:539-541 */
+  if (n_cand > 1000000) return HXO_ERR_QUERY; /* restricted.rs:40,356-371 */
+  uint32_t kk;
+  int rc = hxo_restricted_result_count(k, n_cand, &kk);
+  if (rc) return rc;
+  uint32_t bad;
+  rc = hxo_validate_vector(ix->metric, ix->dim, query, query_dim, &bad);
+  if (rc) return rc;
+  if (!ix->populated) return HXO_OK; /* restricted.rs:563-566 */
+  float qh = hxo_header(ix->metric, query, ix->dim);
+  sc->w.n = 0;
+  for (size_t i = 0; i < n_cand; ++i) {
+    uint32_t s = slot_of(ix, cand_ids[i]);
+    if (s == UINT32_MAX || !ix->has_vec[s]) continue;
+    float d = dist_q(ix, query, qh, s);
+    if (ndist) (*ndist)++;
+    rc = hxo_score_validate(&d);
+    if (rc) return rc;
+    cand c = {d, s};
+    heap_push(ix, &sc->w, 1, c);
+    if (sc->w.n > kk) heap_pop(ix, &sc->w, 1);
+  }
+  qsort_r(sc->w.a, sc->w.n, sizeof(cand), cmp_cand_ctx, (void*)ix);
+  for (size_t i = 0; i < sc->w.n; ++i) {
+    out_ids[i] = ix->ids[sc->w.a[i].slot];
+    out_scores[i] = sc->w.a[i].score;
+  }
+  *out_count = (uint32_t)sc->w.n;
+  return HXO_OK;
+}
+
+int hxo_search_restricted(const hxo_index* ix, const float* query, uint32_t query_dim, uint32_t k,
+                          const uint64_t* cand_ids, size_t n_cand, uint64_t* out_ids, float* out_scores,
+                          uint32_t* out_count, uint64_t* distance_computations) {
+  return restricted_impl(ix, &tls_scratch, query, query_dim, k, cand_ids, n_cand, out_ids, out_scores,
+                         out_count, distance_computations);
+}
+
+static int exact_impl(const hxo_index* ix, scratch* sc, const float* query, uint32_t k, uint64_t* out_ids,
+                      float* out_scores, uint32_t* out_count) {
+  *out_count = 0;
+  if (k == 0) return HXO_ERR_INVALID_PARAMETER;
+  float qh = hxo_header(ix->metric, query, ix->dim);
+  sc->w.n = 0;
+  for (size_t s = 0; s < ix->n; ++s) {
+    if (!ix->has_vec[s]) continue;
+    float d = dist_q(ix, query, qh, (uint32_t)s);
+    int rc = hxo_score_validate(&d);
+    if (rc) return rc;
+    if (sc->w.n == k && !(d < sc->w.a[0].score || (d == sc->w.a[0].score && ix->ids[s] < ix->ids[sc->w.a[0].slot])))
+      continue;
+    cand c = {d, (uint32_t)s};
+    heap_push(ix, &sc->w, 1, c);
+    if (sc->w.n > k) heap_pop(ix, &sc->w, 1);
+  }
+  qsort_r(sc->w.a, sc->w.n, sizeof(cand), cmp_cand_ctx, (void*)ix);
+  for (size_t i = 0; i < sc->w.n; ++i) {
+    out_ids[i] = ix->ids[sc->w.a[i].slot];
+    out_scores[i] = sc->w.a[i].score;
+  }
+  *out_count = (uint32_t)sc->w.n;
+  return HXO_OK;
+}
+
+int hxo_search_exact(const hxo_index* ix, const float* query, uint32_t k, uint64_t* out_ids, float* out_scores,
+                     uint32_t* out_count) {
+  return exact_impl(ix, &tls_scratch, query, k, out_ids, out_scores, out_count);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Build: V/mutation.rs:642-1005,1498-1591 + V/mod.rs:809-856
+ * ------------------------------------------------------------------------------------------ */
+
+/* search_layer_beam (mutation.rs:904-1005): visited on discovery; admit `w.len() < ef || d < w.max`;
+ * result sorted ascending by (score,id). Output in sc->w.a[0..sc->w.n). */
+static int beam_for_insert(const hxo_index* ix, scratch* sc, const float* q, float q_hdr, uint32_t entry_slot,
+                           uint16_t layer, uint32_t ef) {
+  scratch_begin(sc, ix->n);
+  if (entry_slot == UINT32_MAX || !ix->has_vec[entry_slot]) return HXO_OK;
+  float ed = dist_q(ix, q, q_hdr, entry_slot);
+  int rc = hxo_score_validate(&ed);
+  if (rc) return rc;
+  cand e = {ed, entry_slot};
+  heap_push(ix, &sc->cands, 0, e);
+  heap_push(ix, &sc->w, 1, e);
+  visited_insert(sc, entry_slot);
+  while (sc->cands.n) {
+    cand current = heap_pop(ix, &sc->cands, 0);
+    if (sc->w.n >= ef && current.score > sc->w.a[0].score) break;
+    uint32_t deg;
+    const uint32_t* nbrs = row_get(ix, layer, current.slot, &deg);
+    if (sc->frontier_cap < deg) {
+      sc->frontier = (uint32_t*)realloc(sc->frontier, (deg + 64) * sizeof(uint32_t));
+      sc->frontier_cap = deg + 64;
+    }
+    uint32_t nf = 0;
+    for (uint32_t i = 0; i < deg; ++i)
+      if (visited_insert(sc, nbrs[i])) sc->frontier[nf++] = nbrs[i];
+    for (uint32_t i = 0; i < nf; ++i) {
+      uint32_t nb = sc->frontier[i];
+      if (!ix->has_vec[nb]) continue;
+      float d = dist_q(ix, q, q_hdr, nb);
+      rc = hxo_score_validate(&d);
+      if (rc) return rc;
+      if (sc->w.n < ef || d < sc->w.a[0].score) {
+        cand c = {d, nb};
+        heap_push(ix, &sc->cands, 0, c);
+        heap_push(ix, &sc->w, 1, c);
+        if (sc->w.n > ef) heap_pop(ix, &sc->w, 1);
+      }
+    }
+  }
+  qsort_r(sc->w.a, sc->w.n, sizeof(cand), cmp_cand_ctx, (void*)ix);
+  return HXO_OK;
+}
+
+/* select_diverse (mod.rs:809-856).  `resolvable[i]` = get_item(candidates[i]) is Some.
+ * Returns number selected into out (selection order). */
+static int select_diverse(const hxo_index* ix, const cand* candidates, size_t nc, const uint8_t* resolvable,
+                          uint32_t m, uint32_t* out, uint32_t* out_n) {
+  uint32_t ns = 0;
+  uint8_t* taken = (uint8_t*)calloc(nc + 1, 1);
+  for (size_t i = 0; i < nc && ns < m; ++i) {
+    if (!resolvable[i]) continue;
+    uint32_t c = candidates[i].slot;
+    int diverse = 1;
+    for (uint32_t s = 0; s < ns; ++s) {
+      float pd = hxo_distance(ix->metric, ix->vecs + (size_t)c * ix->dim, ix->hdr[c],
+                              ix->vecs + (size_t)out[s] * ix->dim, ix->hdr[out[s]], ix->dim);
+      int rc = hxo_score_validate(&pd);
+      if (rc) {
+        free(taken);
+        return rc;
+      }
+      if (pd < candidates[i].score) {
+        diverse = 0;
+        break;
+      }
+    }
+    if (diverse) {
+      out[ns++] = c;
+      taken[i] = 1;
+    }
+  }
+  if (ns < m) { /* backfill with closest remaining resolvable */
+    for (size_t i = 0; i < nc && ns < m; ++i) {
+      if (!resolvable[i] || taken[i]) continue;
+      /* selected_ids.insert(c.node_id): candidates are unique per list */
+      out[ns++] = candidates[i].slot;
+      taken[i] = 1;
+    }
+  }
+  free(taken);
+  *out_n = ns;
+  return HXO_OK;
+}
+
+static int row_contains(const uint32_t* r, uint32_t n, uint32_t x) {
+  for (uint32_t i = 0; i < n; ++i)
+    if (r[i] == x) return 1;
+  return 0;
+}
+
+/* remove_edge_from_neighbor (mutation.rs:1890-1908) */
+static void remove_edge(hxo_index* ix, uint16_t layer, uint32_t neighbor, uint32_t node_to_remove) {
+  uint32_t deg;
+  const uint32_t* r = row_get(ix, layer, neighbor, &deg);
+  if (!row_contains(r, deg, node_to_remove)) return;
+  uint32_t* tmp = (uint32_t*)malloc((deg + 1) * sizeof(uint32_t));
+  uint32_t w = 0;
+  for (uint32_t i = 0; i < deg; ++i)
+    if (r[i] != node_to_remove) tmp[w++] = r[i];
+  row_set(ix, layer, neighbor, tmp, w);
+  free(tmp);
+}
+
+/* add_bidirectional_link (mutation.rs:1498-1591) */
+static int add_bidirectional_link(hxo_index* ix, uint16_t layer, uint32_t from, uint32_t to, uint32_t max_nbrs) {
+  uint32_t deg;
+  const uint32_t* r = row_get(ix, layer, to, &deg);
+  uint32_t n = deg;
+  uint32_t* to_nbrs = (uint32_t*)malloc((deg + 2) * sizeof(uint32_t));
+  memcpy(to_nbrs, r, deg * sizeof(uint32_t));
+  if (!row_contains(to_nbrs, n, from)) to_nbrs[n++] = from;
+  uint32_t ncand = n;
+  uint32_t* candidate_nbrs = (uint32_t*)malloc((ncand + 1) * sizeof(uint32_t));
+  memcpy(candidate_nbrs, to_nbrs, ncand * sizeof(uint32_t));
+  int rc = HXO_OK;
+  if (n > max_nbrs) {
+    if (ix->has_vec[to]) {
+      cand* distances = (cand*)malloc(n * sizeof(cand));
+      uint8_t* resolvable = (uint8_t*)malloc(n);
+      uint32_t nd = 0;
+      const float* tv = ix->vecs + (size_t)to * ix->dim;
+      for (uint32_t i = 0; i < n; ++i) {
+        uint32_t nb = to_nbrs[i];
+        if (!ix->has_vec[nb]) continue;
+        float d = hxo_distance(ix->metric, tv, ix->hdr[to], ix->vecs + (size_t)nb * ix->dim, ix->hdr[nb], ix->dim);
+        rc = hxo_score_validate(&d);
+        if (rc) break;
+        distances[nd].score = d;
+        distances[nd].slot = nb;
+        resolvable[nd] = 1;
+        nd++;
+      }
+      if (!rc) {
+        qsort_r(distances, nd, sizeof(cand), cmp_cand_ctx, ix);
+        uint32_t ns;
+        rc = select_diverse(ix, distances, nd, resolvable, max_nbrs, to_nbrs, &ns);
+        n = ns;
+      }
+      free(distances);
+      free(resolvable);
+    } else {
+      n = max_nbrs; /* truncate */
+    }
+  }
+  if (!rc) {
+    row_set(ix, layer, to, to_nbrs, n);
+    uint32_t rdeg;
+    const uint32_t* retained = row_get(ix, layer, to, &rdeg);
+    /* copy retained since remove_edge may realloc rows */
+    uint32_t* ret = (uint32_t*)malloc((rdeg + 1) * sizeof(uint32_t));
+    memcpy(ret, retained, rdeg * sizeof(uint32_t));
+    for (uint32_t i = 0; i < ncand; ++i)
+      if (!row_contains(ret, rdeg, candidate_nbrs[i])) remove_edge(ix, layer, candidate_nbrs[i], to);
+    free(ret);
+  }
+  free(to_nbrs);
+  free(candidate_nbrs);
+  return rc;
+}
+
+/* insert_with_mutation_cache (mutation.rs:642-780) + insert_hnsw (:787-895) */
+int hxo_index_insert(hxo_index* ix, uint64_t id, const float* v, uint16_t node_layer) {
+  if (slot_of(ix, id) != UINT32_MAX && ix->has_vec[slot_of(ix, id)]) return HXO_ERR_INVALID_PARAMETER; /* fresh build only */
+  int rc = hxo_index_put_vector(ix, id, v);
+  if (rc) return rc;
+  uint32_t node = slot_of(ix, id);
+  scratch* sc = &tls_scratch;
+  const float* q = ix->vecs + (size_t)node * ix->dim;
+  float qh = ix->hdr[node];
+
+  if (!ix->populated) { /* mutation.rs:706-739 */
+    ix->populated = 1;
+    ix->entry_id = id;
+    ix->max_layer = node_layer;
+    for (uint16_t l = 0; l <= node_layer; ++l) row_set(ix, l, node, NULL, 0);
+    return HXO_OK;
+  }
+  uint16_t old_max = ix->max_layer;
+  uint32_t cur = slot_of(ix, ix->entry_id);
+  if (node_layer < old_max) {
+    for (int layer = old_max; layer >= (int)node_layer + 1; --layer) {
+      rc = greedy_slot(ix, sc, q, qh, cur, (uint16_t)layer, &cur, NULL);
+      if (rc) return rc;
+    }
+  }
+  uint16_t top = old_max < node_layer ? old_max : node_layer;
+  for (int layer = top; layer >= 0; --layer) {
+    uint32_t ef = layer == 0 ? (ix->efc > ix->lim0 ? ix->efc : ix->lim0)
+                             : (ix->efc > 2 * ix->lim_upper ? ix->efc : 2 * ix->lim_upper);
+    rc = beam_for_insert(ix, sc, q, qh, cur, (uint16_t)layer, ef);
+    if (rc) return rc;
+    size_t nc = sc->w.n;
+    cand* candidates = (cand*)malloc((nc + 1) * sizeof(cand));
+    memcpy(candidates, sc->w.a, nc * sizeof(cand));
+    uint32_t max_nbrs = layer == 0 ? ix->lim0 : ix->lim_upper;
+    /* select_neighbors_heuristic (mutation.rs:1072-1098): items only for the first 2*max candidates */
+    uint8_t* resolvable = (uint8_t*)calloc(nc + 1, 1);
+    for (size_t i = 0; i < nc && i < (size_t)max_nbrs * 2; ++i) resolvable[i] = ix->has_vec[candidates[i].slot];
+    uint32_t* nbrs = (uint32_t*)malloc((max_nbrs + 1) * sizeof(uint32_t));
+    uint32_t nn;
+    rc = select_diverse(ix, candidates, nc, resolvable, max_nbrs, nbrs, &nn);
+    if (!rc) {
+      row_set(ix, (uint16_t)layer, node, nbrs, nn); /* stage_new_neighbors_for_mutation */
+      for (uint32_t i = 0; i < nn && !rc; ++i) rc = add_bidirectional_link(ix, (uint16_t)layer, node, nbrs[i], max_nbrs);
+      if (nc) cur = candidates[0].slot; /* mutation.rs:876-878 */
+    }
+    free(candidates);
+    free(resolvable);
+    free(nbrs);
+    if (rc) return rc;
+  }
+  if (node_layer > old_max) {
+    for (uint16_t l = old_max + 1; l <= node_layer; ++l) row_set(ix, l, node, NULL, 0);
+    ix->entry_id = id; /* mutation.rs:769-772 */
+    ix->max_layer = node_layer;
+  }
+  return HXO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Bulk graph import (slot space = rank of ascending id), as downloaded from the device
+ * ------------------------------------------------------------------------------------------ */
+int hxo_index_import_graph(hxo_index* ix, const uint16_t* levels, const uint32_t* deg0, const uint32_t* nbr0,
+                           uint32_t layer0_stride, size_t n_upper_rows, const uint32_t* upper_node,
+                           const uint16_t* upper_layer, const uint32_t* upper_deg, const uint32_t* upper_nbr,
+                           uint32_t upper_stride, uint64_t entry_point, uint16_t max_layer) {
+  /* rank -> oracle slot */
+  size_t n = 0;
+  uint64_t* sorted = (uint64_t*)malloc(ix->n * sizeof(uint64_t) + 8);
+  n = hxo_index_node_ids(ix, sorted, ix->n);
+  uint32_t* rank2slot = (uint32_t*)malloc((n + 1) * sizeof(uint32_t));
+  for (size_t r = 0; r < n; ++r) rank2slot[r] = slot_of(ix, sorted[r]);
+  free(sorted);
+  uint32_t* tmp = (uint32_t*)malloc(((size_t)layer0_stride + upper_stride + 2) * sizeof(uint32_t));
+  for (size_t r = 0; r < n; ++r) {
+    uint32_t d = deg0[r];
+    for (uint32_t j = 0; j < d; ++j) tmp[j] = rank2slot[nbr0[r * (size_t)layer0_stride + j]];
+    row_set(ix, 0, rank2slot[r], tmp, d);
+    (void)levels;
+  }
+  for (size_t u = 0; u < n_upper_rows; ++u) {
+    uint32_t d = upper_deg[u];
+    for (uint32_t j = 0; j < d; ++j) tmp[j] = rank2slot[upper_nbr[u * (size_t)upper_stride + j]];
+    row_set(ix, upper_layer[u], rank2slot[upper_node[u]], tmp, d);
+  }
+  free(tmp);
+  free(rank2slot);
+  return hxo_index_set_entry(ix, entry_point, max_layer);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Threaded drivers (one query per thread at a time; no intra-query parallelism, like the reference)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const hxo_index* ix;
+  const float* queries;
+  size_t nq;
+  uint32_t k, ef;
+  const uint64_t* cand_ids;
+  const uint64_t* cand_offsets;
+  uint64_t* out_ids;
+  float* out_scores;
+  uint32_t* out_counts;
+  hxo_stats* stats_sum;
+  int mode; /* 0 hnsw, 1 restricted, 2 exact */
+  size_t next;
+  pthread_mutex_t mu;
+  int rc;
+} batch_job;
+
+static void* batch_worker(void* arg) {
+  batch_job* job = (batch_job*)arg;
+  scratch sc;
+  memset(&sc, 0, sizeof(sc));
+  hxo_stats local;
+  memset(&local, 0, sizeof(local));
+  for (;;) {
+    size_t i = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
+    if (i >= job->nq) break;
+    const float* q = job->queries + i * (size_t)job->ix->dim;
+    uint64_t* oi = job->out_ids + i * (size_t)job->k;
+    float* os = job->out_scores + i * (size_t)job->k;
+    int rc;
+    if (job->mode == 0) {
+      rc = search_impl(job->ix, &sc, q, job->ix->dim, job->k, job->ef, oi, os, &job->out_counts[i], &local);
+    } else if (job->mode == 1) {
+      size_t b = job->cand_offsets[i], e = job->cand_offsets[i + 1];
+      rc = restricted_impl(job->ix, &sc, q, job->ix->dim, job->k, job->cand_ids + b, e - b, oi, os,
+                           &job->out_counts[i], NULL);
+    } else {
+      rc = exact_impl(job->ix, &sc, q, job->k, oi, os, &job->out_counts[i]);
+    }
+    if (rc) job->rc = rc;
+  }
+  if (job->stats_sum) {
+    pthread_mutex_lock(&job->mu);
+    job->stats_sum->expansion_steps += local.expansion_steps;
+    job->stats_sum->neighbors_examined += local.neighbors_examined;
+    job->stats_sum->distance_computations += local.distance_computations;
+    job->stats_sum->vectors_loaded += local.vectors_loaded;
+    job->stats_sum->upper_layer_steps += local.upper_layer_steps;
+    pthread_mutex_unlock(&job->mu);
+  }
+  scratch_free(&sc);
+  return NULL;
+}
+
+static double run_batch(batch_job* job, int threads) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  pthread_mutex_init(&job->mu, NULL);
+  job->next = 0;
+  job->rc = 0;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_t th[256];
+  for (int t = 0; t < threads; ++t) pthread_create(&th[t], NULL, batch_worker, job);
+  for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  pthread_mutex_destroy(&job->mu);
+  double s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return job->rc ? -1.0 : s;
+}
+
+double hxo_search_batch(const hxo_index* ix, const float* queries, size_t nq, uint32_t k, uint32_t ef, int threads,
+                        uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hxo_stats* stats_sum) {
+  batch_job job;
+  memset(&job, 0, sizeof(job));
+  if (stats_sum) memset(stats_sum, 0, sizeof(*stats_sum));
+  job.ix = ix;
+  job.queries = queries;
+  job.nq = nq;
+  job.k = k;
+  job.ef = ef;
+  job.out_ids = out_ids;
+  job.out_scores = out_scores;
+  job.out_counts = out_counts;
+  job.stats_sum = stats_sum;
+  job.mode = 0;
+  return run_batch(&job, threads);
+}
+
+double hxo_search_restricted_batch(const hxo_index* ix, const float* queries, size_t nq, uint32_t k,
+                                   const uint64_t* cand_ids, const uint64_t* cand_offsets, int threads,
+                                   uint64_t* out_ids, float* out_scores, uint32_t* out_counts) {
+  batch_job job;
+  memset(&job, 0, sizeof(job));
+  job.ix = ix;
+  job.queries = queries;
+  job.nq = nq;
+  job.k = k;
+  job.cand_ids = cand_ids;
+  job.cand_offsets = cand_offsets;
+  job.out_ids = out_ids;
+  job.out_scores = out_scores;
+  job.out_counts = out_counts;
+  job.mode = 1;
+  return run_batch(&job, threads);
+}
+
+double hxo_search_exact_batch(const hxo_index* ix, const float* queries, size_t nq, uint32_t k, int threads,
+                              uint64_t* out_ids, float* out_scores, uint32_t* out_counts) {
+  batch_job job;
+  memset(&job, 0, sizeof(job));
+  job.ix = ix;
+  job.queries = queries;
+  job.nq = nq;
+  job.k = k;
+  job.out_ids = out_ids;
+  job.out_scores = out_scores;
+  job.out_counts = out_counts;
+  job.mode = 2;
+  return run_batch(&job, threads);
+}

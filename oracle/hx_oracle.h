@@ -1,0 +1,152 @@
+/*
+ * hx_oracle.h — CPU restatement of HelixDB's vector-search hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is the parity oracle and the CPU baseline of
+ * bench.py; nothing in the product path (helix-db_b200/) may include, link or
+ * call it.  Every function cites the reference file:line it restates (paths are
+ * relative to /root/reference/crates/db/src/search/vector/).
+ *
+ * Pinning: checked against the reference's own known-answer tests (SURVEY §8c,
+ * tests/test_oracle_kat.py).  NOT pinned: SimHash bit values and Adaptive-mode
+ * sampling (they live in rand 0.10.2 / chacha20 0.10.1, absent from the tree and
+ * pinned by no committed value) — only strict-exhaustive search is restated.
+ */
+#ifndef HX_ORACLE_H
+#define HX_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { HXO_EUCLIDEAN = 0, HXO_COSINE = 1, HXO_MANHATTAN = 2 };
+
+/* same numeric values as hx_status in include/helix_b200.h */
+enum {
+  HXO_OK = 0,
+  HXO_ERR_INDEX_NOT_FOUND = 1,
+  HXO_ERR_INVALID_DIMENSION = 2,
+  HXO_ERR_INVALID_VECTOR_COMPONENT = 3,
+  HXO_ERR_ZERO_NORM_COSINE = 4,
+  HXO_ERR_MAGNITUDE_EXCEEDED = 5,
+  HXO_ERR_INVALID_VECTOR_CONFIG = 6,
+  HXO_ERR_QUERY = 7,
+  HXO_ERR_INVARIANT_VIOLATION = 8,
+  HXO_ERR_INVALID_PARAMETER = 9
+};
+
+/* ---- distance kernels (spaces/simple.rs, spaces/simple_avx.rs) ---- */
+float hxo_euclid_scalar(const float* u, const float* v, size_t d);      /* simple.rs:204-218 */
+float hxo_dot_scalar(const float* u, const float* v, size_t d);         /* simple.rs:220-234 */
+float hxo_manhattan(const float* u, const float* v, size_t d);          /* simple.rs:186-202 */
+float hxo_euclid_avx_fma(const float* u, const float* v, size_t d);     /* simple_avx.rs:128-180 (intrinsics) */
+float hxo_dot_avx_fma(const float* u, const float* v, size_t d);        /* simple_avx.rs:184-238 (intrinsics) */
+float hxo_euclid_avx_fma_portable(const float* u, const float* v, size_t d); /* same order, fmaf() only */
+float hxo_dot_avx_fma_portable(const float* u, const float* v, size_t d);
+float hxo_euclidean_distance(const float* u, const float* v, size_t d); /* simple.rs:120-144 dispatch: AvxFma iff d>=32 */
+float hxo_dot_product(const float* u, const float* v, size_t d);        /* simple.rs:155-177 */
+int   hxo_has_avx_fma(void);
+
+/* ---- metric headers and scores (distance/{cosine,euclidean,manhattan}.rs) ---- */
+double hxo_scaled_l2_norm(const float* v, size_t d);                    /* cosine.rs:12-36 */
+float  hxo_cosine_norm(const float* v, size_t d);                       /* cosine.rs:120-122 */
+float  hxo_header(int metric, const float* v, size_t d);                /* new_header: cosine norm, else 0.0 bias */
+float  hxo_cosine_distance(const float* p, float pn, const float* q, float qn, size_t d); /* cosine.rs:96-118 */
+float  hxo_distance(int metric, const float* p, float p_hdr, const float* q, float q_hdr, size_t d);
+/* DistanceScore::try_new (parameters.rs:241-258): finite, >= 0, -0 -> +0. Returns 0 if valid. */
+int    hxo_score_validate(float* score);
+
+/* ---- input domain (domain.rs:15-160) ---- */
+/* Returns 1 and the limit if the metric has one (Euclidean sqrt(MAX/(8d)), Manhattan MAX/(4d)); 0 for cosine. */
+int hxo_component_limit(int metric, size_t d, float* limit);
+/* ValidatedMetricVector::try_new order: dimension -> finiteness -> cosine zero -> magnitude. */
+int hxo_validate_vector(int metric, size_t expected_d, const float* v, size_t actual_d, uint32_t* bad_index);
+
+/* ---- layer selection (mod.rs:769-796) ---- */
+uint16_t hxo_select_layer_from_uniform(float ml, float uniform);
+float    hxo_default_ml_for_m(uint32_t m);                               /* mod.rs:705-709 */
+
+/* ---- restricted planning (restricted.rs:40-56,200-213,321-342,426-453) ---- */
+int  hxo_restricted_plan(uint64_t n_candidates, uint32_t dimension);     /* 0 Exact, 1 FilteredGraph */
+/* RestrictedResultCount::try_new: min(k,|C|), error if > 800 or == 0 */
+int  hxo_restricted_result_count(uint32_t k, uint64_t n_candidates, uint32_t* out_k);
+/* NonEmptyCandidateSet::deterministic_sample_ids over a sorted id array */
+size_t hxo_deterministic_sample_ids(const uint64_t* sorted_ids, size_t n, size_t limit, uint64_t* out);
+
+/* ---- deterministic fixtures from the reference's tests ---- */
+/* tests/production_support/index_lifecycle_scale.rs:410-422 (xorshift, d values in [-1,1)) */
+void hxo_fixture_xorshift_vector(uint64_t entity_id, uint32_t d, float* out);
+/* scale_contracts.rs:44-48 */
+void hxo_fixture_circle_vector(uint64_t entity_id, uint64_t entity_count, float* out2);
+/* scale_contracts.rs:50-71; returns count written (sorted, unique, self-free) */
+size_t hxo_fixture_skip_neighbors(uint64_t entity_id, uint64_t entity_count, uint64_t* out, size_t cap);
+
+/* ---- in-memory index (flat arrays: the reference's algorithm without its KV layer) ---- */
+typedef struct hxo_index hxo_index;
+
+typedef struct {
+  uint64_t expansion_steps;       /* search.rs:538-541 */
+  uint64_t neighbors_examined;    /* search.rs:579-581 */
+  uint64_t distance_computations; /* search.rs:511-513,931-933 */
+  uint64_t vectors_loaded;        /* search.rs:893-896 (rows fetched, entry excluded) */
+  uint64_t upper_layer_steps;
+} hxo_stats;
+
+hxo_index* hxo_index_new(int metric, uint32_t dim, uint32_t m, uint32_t m0, uint32_t ef_construction);
+void       hxo_index_free(hxo_index* idx);
+size_t     hxo_index_len(const hxo_index* idx);
+int        hxo_index_state(const hxo_index* idx, uint64_t* entry_point, uint16_t* max_layer); /* 1 populated */
+uint32_t   hxo_index_layer0_limit(const hxo_index* idx);                  /* max(m0, 2m) mutation.rs:179-199 */
+
+/* Raw row mirroring (fixtures that seed rows directly, like scale_contracts.rs:96-150). */
+int hxo_index_put_vector(hxo_index* idx, uint64_t id, const float* v);    /* validated */
+int hxo_index_put_neighbors(hxo_index* idx, uint16_t layer, uint64_t id, const uint64_t* nbrs, size_t n);
+int hxo_index_set_entry(hxo_index* idx, uint64_t entry_point, uint16_t max_layer);
+/* Bulk: n rows at once (ids ascending or not). */
+int hxo_index_put_vectors(hxo_index* idx, const uint64_t* ids, const float* rows, size_t n);
+
+/* insert_with_mutation_cache + insert_hnsw (mutation.rs:642-895) with the layer given by the caller. */
+int hxo_index_insert(hxo_index* idx, uint64_t id, const float* v, uint16_t layer);
+
+/* Row export (for mirroring into the device index). */
+size_t hxo_index_node_ids(const hxo_index* idx, uint64_t* out, size_t cap);            /* ascending */
+int    hxo_index_node_level(const hxo_index* idx, uint64_t id);                        /* -1 = no rows */
+size_t hxo_index_get_neighbors(const hxo_index* idx, uint16_t layer, uint64_t id, uint64_t* out, size_t cap);
+int    hxo_index_get_vector(const hxo_index* idx, uint64_t id, float* out);
+
+/* search_layer_greedy (search.rs:169-224). */
+int hxo_search_layer_greedy(const hxo_index* idx, const float* query, uint64_t entry, uint16_t layer,
+                            uint64_t* out_node);
+/* SearchSession::run, strict-exhaustive (search.rs:1101-1230 + :267-1067 STRICT_EXHAUSTIVE). */
+int hxo_search(const hxo_index* idx, const float* query, uint32_t query_dim, uint32_t k, uint32_t ef,
+               uint64_t* out_ids, float* out_scores, uint32_t* out_count, hxo_stats* stats);
+/* restricted_exact_scan (restricted.rs:753-835) for any |C| (ids ascending unique). */
+int hxo_search_restricted(const hxo_index* idx, const float* query, uint32_t query_dim, uint32_t k,
+                          const uint64_t* cand_ids, size_t n_cand, uint64_t* out_ids, float* out_scores,
+                          uint32_t* out_count, uint64_t* distance_computations);
+/* exact top-k over the whole index (ground truth for recall), same (score,id) rule. */
+int hxo_search_exact(const hxo_index* idx, const float* query, uint32_t k, uint64_t* out_ids,
+                     float* out_scores, uint32_t* out_count);
+
+/* Threaded drivers: one query per thread at a time (the reference's one-query-per-tokio-task model).
+ * Return wall seconds spent in the parallel region. */
+double hxo_search_batch(const hxo_index* idx, const float* queries, size_t nq, uint32_t k, uint32_t ef,
+                        int threads, uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
+                        hxo_stats* stats_sum);
+double hxo_search_restricted_batch(const hxo_index* idx, const float* queries, size_t nq, uint32_t k,
+                                   const uint64_t* cand_ids, const uint64_t* cand_offsets, int threads,
+                                   uint64_t* out_ids, float* out_scores, uint32_t* out_counts);
+double hxo_search_exact_batch(const hxo_index* idx, const float* queries, size_t nq, uint32_t k, int threads,
+                              uint64_t* out_ids, float* out_scores, uint32_t* out_counts);
+
+/* Bulk graph import in slot space (slot = rank of id ascending), as downloaded from the device. */
+int hxo_index_import_graph(hxo_index* idx, const uint16_t* levels, const uint32_t* deg0, const uint32_t* nbr0,
+                           uint32_t layer0_stride, size_t n_upper_rows, const uint32_t* upper_node,
+                           const uint16_t* upper_layer, const uint32_t* upper_deg, const uint32_t* upper_nbr,
+                           uint32_t upper_stride, uint64_t entry_point, uint16_t max_layer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,307 @@
+"""Pins the CPU oracle against the reference's own known-answer tests.
+
+Paths: V/ = /root/reference/crates/db/src/search/vector/, T/ = /root/reference/crates/db/tests/production_support/.
+Nothing here reads /root/reference at run time: the expected values are the literals the reference's tests assert.
+"""
+import math
+import struct
+
+import numpy as np
+import pytest
+
+
+def bits(x):
+    return struct.unpack("<I", struct.pack("<f", float(x)))[0]
+
+
+# --- item 2: distance KATs (V/distance/mod.rs:112-137, T/vector/distance_neighbors.rs:79-110) -------------
+def test_distance_kats(hxo):
+    assert hxo.distance(hxo.COSINE, [1.0, 0.0], [0.0, 1.0]) == 0.5
+    assert math.isnan(hxo.distance(hxo.COSINE, [1.0, 0.0], [0.0, 0.0]))
+    assert math.isnan(hxo.distance(hxo.COSINE, [0.0, 0.0], [0.0, 0.0]))
+    assert hxo.header(hxo.COSINE, [1.0, 0.0]) == 1.0
+    assert hxo.distance(hxo.EUCLIDEAN, [1.0, 2.0], [4.0, 6.0]) == 25.0
+    assert hxo.distance(hxo.MANHATTAN, [1.0, -2.0, 3.0], [-1.0, 2.0, 1.0]) == 8.0
+    # Euclidean/Manhattan norm_no_header = sqrt(dot(v,v)) (euclidean.rs:50-52)
+    assert math.sqrt(hxo.pair("hxo_dot_product", [3.0, 4.0], [3.0, 4.0])) == 5.0
+    # header of Euclidean rows is the 0.0 bias (magnitude_regressions.rs:333-338)
+    assert hxo.header(hxo.EUCLIDEAN, [1.0, -2.0]) == 0.0
+
+
+# --- cosine extremes (V/distance/cosine.rs:130-149) ---------------------------------------------------------
+def test_cosine_extremes(hxo):
+    fmax = np.finfo(np.float32).max
+    assert hxo.header(hxo.COSINE, [fmax, fmax]) == fmax
+    assert hxo.distance(hxo.COSINE, [fmax, fmax], [fmax, fmax]) <= np.finfo(np.float32).eps
+    tiny = np.frombuffer(struct.pack("<I", 1), dtype=np.float32)[0]
+    assert hxo.header(hxo.COSINE, [tiny, tiny]) > 0.0
+    assert hxo.distance(hxo.COSINE, [tiny, tiny], [tiny, tiny]) <= np.finfo(np.float32).eps
+
+
+# --- AVX vs scalar exact equality on the 70-float vector (V/spaces/simple_avx.rs:248-286) ------------------
+def test_avx_equals_scalar_on_reference_vector(hxo):
+    blk = [float(x) for x in range(10, 26)]
+    v1 = np.array(blk * 4 + [26.0, 27.0, 28.0, 29.0, 30.0, 31.0], dtype=np.float32)
+    v2 = np.array([float(x) for x in range(40, 56)] + blk * 3 + [56.0, 57.0, 58.0, 59.0, 60.0, 61.0],
+                  dtype=np.float32)
+    assert v1.size == 70 and v2.size == 70
+    assert hxo.lib().hxo_has_avx_fma() == 1
+    assert hxo.pair("hxo_euclid_avx_fma", v1, v2) == hxo.pair("hxo_euclid_scalar", v1, v2)
+    assert hxo.pair("hxo_dot_avx_fma", v1, v2) == hxo.pair("hxo_dot_scalar", v1, v2)
+    # dispatch takes the AvxFma arm for d >= 32 and the scalar loop below (simple.rs:32,120-144)
+    assert hxo.pair("hxo_euclidean_distance", v1, v2) == hxo.pair("hxo_euclid_avx_fma", v1, v2)
+    assert hxo.pair("hxo_euclidean_distance", v1[:31], v2[:31]) == hxo.pair("hxo_euclid_scalar", v1[:31], v2[:31])
+
+
+def test_portable_avx_order_is_bit_identical_to_intrinsics(hxo):
+    rng = np.random.default_rng(7)
+    for d in (32, 33, 63, 64, 65, 70, 128, 768, 769, 1536, 1567):
+        for _ in range(8):
+            u = rng.standard_normal(d).astype(np.float32)
+            v = rng.standard_normal(d).astype(np.float32)
+            assert bits(hxo.pair("hxo_euclid_avx_fma", u, v)) == bits(hxo.pair("hxo_euclid_avx_fma_portable", u, v))
+            assert bits(hxo.pair("hxo_dot_avx_fma", u, v)) == bits(hxo.pair("hxo_dot_avx_fma_portable", u, v))
+
+
+# --- item 4: f32 kernels vs f64 oracle, LCG vectors (T/vector/magnitude_regressions.rs:268-328) ------------
+def test_magnitude_regression_tolerance(hxo):
+    domains = [(hxo.EUCLIDEAN, d) for d in (1, 15, 16, 17, 31, 32, 33, 1536)] + \
+              [(hxo.MANHATTAN, d) for d in (1, 15, 16, 17, 31, 32, 33, 1536)]
+    state = 0x5EED5AFECAFEBABE
+    mask = (1 << 64) - 1
+    for case in range(128):
+        metric, d = domains[case % len(domains)]
+        limit = hxo.component_limit(metric, d)
+
+        def gen():
+            nonlocal state
+            out = np.empty(d, dtype=np.float32)
+            for i in range(d):
+                state = (state * 6364136223846793005 + 1442695040888963407) & mask
+                unit = float((state >> 32) & 0xFFFFFFFF) / float(0xFFFFFFFF)
+                out[i] = np.float32(((unit * 2.0) - 1.0) * float(limit))
+            return out
+
+        left, right = gen(), gen()
+        assert hxo.validate_vector(metric, d, left)[0] == hxo.OK
+        assert hxo.validate_vector(metric, d, right)[0] == hxo.OK
+        score = hxo.distance(metric, left, right)
+        reverse = hxo.distance(metric, right, left)
+        l64, r64 = left.astype(np.float64), right.astype(np.float64)
+        oracle = float(((l64 - r64) ** 2).sum()) if metric == hxo.EUCLIDEAN else float(np.abs(l64 - r64).sum())
+        tol = max(d * float(np.finfo(np.float32).eps), 1.0e-5)
+        assert math.isfinite(score) and score >= 0.0
+        assert score == reverse
+        assert abs(score - oracle) <= max(abs(oracle), 1.0) * tol
+
+
+# --- component limits (V/domain.rs:15-90, docs/VECTOR_MAGNITUDE_VALIDATION.md) -----------------------------
+def test_component_limits(hxo):
+    fmax = float(np.finfo(np.float32).max)
+    for d in (1, 2, 128, 768, 1536):
+        le = hxo.component_limit(hxo.EUCLIDEAN, d)
+        lm = hxo.component_limit(hxo.MANHATTAN, d)
+        assert hxo.component_limit(hxo.COSINE, d) is None
+        assert float(le) <= math.sqrt(fmax / (8 * d)) < float(np.nextafter(np.float32(le), np.float32(np.inf)))
+        assert float(lm) <= fmax / (4 * d) < float(np.nextafter(np.float32(lm), np.float32(np.inf)))
+        v = np.zeros(d, dtype=np.float32)
+        v[-1] = np.nextafter(np.float32(le), np.float32(np.inf))
+        rc, idx = hxo.validate_vector(hxo.EUCLIDEAN, d, v)
+        assert rc == hxo.ERR_MAGNITUDE_EXCEEDED and idx == d - 1
+        v[-1] = le
+        assert hxo.validate_vector(hxo.EUCLIDEAN, d, v)[0] == hxo.OK
+
+
+# --- validation order (T/vector/search.rs:160-183) ---------------------------------------------------------
+def test_validation_order(hxo):
+    assert hxo.validate_vector(hxo.COSINE, 3, [1.0, 0.0])[0] == hxo.ERR_INVALID_DIMENSION
+    assert hxo.validate_vector(hxo.COSINE, 3, [1.0, float("nan"), 0.0]) == (hxo.ERR_INVALID_VECTOR_COMPONENT, 1)
+    assert hxo.validate_vector(hxo.COSINE, 3, [0.0, 0.0, 0.0])[0] == hxo.ERR_ZERO_NORM_COSINE
+    assert hxo.validate_vector(hxo.COSINE, 3, [1.0, 0.0, 0.0])[0] == hxo.OK
+    # a NaN wins over the zero-norm and magnitude checks; a dimension error wins over everything
+    assert hxo.validate_vector(hxo.EUCLIDEAN, 2, [float("inf"), 1e38]) == (hxo.ERR_INVALID_VECTOR_COMPONENT, 0)
+    assert hxo.validate_vector(hxo.EUCLIDEAN, 2, [float("nan")])[0] == hxo.ERR_INVALID_DIMENSION
+    ix = hxo.Index(hxo.COSINE, 3)
+    ids, sc = ix.search([1.0, 0.0, 0.0], 1)       # empty index -> Ok([])
+    assert len(ids) == 0
+    with pytest.raises(hxo.OracleError) as e:
+        ix.search([1.0, 0.0, 0.0], 0)              # SearchParams::new(0) is an error
+    assert e.value.code == hxo.ERR_INVALID_PARAMETER
+
+
+# --- item 1: phase-0 public result baseline (V/index.rs:2318-2411) -----------------------------------------
+def test_phase0_public_result_and_io_baseline(hxo):
+    ix = hxo.Index(hxo.COSINE, 2, m=4, m0=8, ef_construction=16)
+    for node_id, vec, layer in [(1, [1.0, 0.0], 0), (2, [0.0, 1.0], 1), (3, [-1.0, 0.0], 2), (4, [0.0, -1.0], 0)]:
+        ix.insert(node_id, vec, layer)             # scripted layers [0,1,2,0]
+    ids, scores, st = ix.search([1.0, 0.0], 4, ef=16, with_stats=True)
+    assert [(int(i), bits(s)) for i, s in zip(ids, scores)] == [
+        (1, bits(0.0)), (2, bits(0.5)), (4, bits(0.5)), (3, bits(1.0))]
+    assert st["expansion_steps"] == 4
+    assert st["neighbors_examined"] == 12
+    assert st["vectors_loaded"] == 3
+    assert st["distance_computations"] == 4
+    assert ix.state() == (3, 2)
+
+
+# --- scripted-layer KAT: layers [0,1,3] for ids 10,11,12 (V/index.rs:1919-1973) ----------------------------
+def test_scripted_layers_entry_point(hxo):
+    ix = hxo.Index(hxo.EUCLIDEAN, 2)
+    for node_id, vec, layer in [(10, [0.0, 0.0], 0), (11, [1.0, 0.0], 1), (12, [0.0, 1.0], 3)]:
+        ix.insert(node_id, vec, layer)
+    assert ix.state() == (12, 3)
+    assert ix.node_level(10) == 0 and ix.node_level(11) == 1 and ix.node_level(12) == 3
+
+
+# --- item 7: explicit upper-layer greedy KAT (T/vector/search.rs:231-291) ----------------------------------
+def test_search_layer_greedy_kat(hxo):
+    ix = hxo.Index(hxo.COSINE, 3)
+    ix.put_vector(100, [0.0, 1.0, 0.0])
+    ix.put_vector(101, [1.0, 0.0, 0.0])
+    ix.put_neighbors(1, 100, [99, 101])            # 99 has no vector row
+    ix.put_neighbors(1, 101, [100])
+    q = [1.0, 0.0, 0.0]
+    assert ix.search_layer_greedy(q, 100, 1) == 101
+    umax = (1 << 64) - 1
+    assert ix.search_layer_greedy(q, umax, 0) == umax      # unknown entry returned unchanged
+    assert ix.search_layer_greedy(q, 99, 1) == 99          # entry without a vector returns itself
+
+
+# --- item 5: tie stability, ids {2,1,3} (T/vector/restricted.rs:710-786) -----------------------------------
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "manhattan"])
+def test_tie_stability(hxo, metric):
+    m = hxo.METRICS[metric]
+    ix = hxo.Index(m, 2, m=4, m0=8, ef_construction=16)
+    for node_id in (2, 1, 3):
+        ix.insert(node_id, [1.0, 0.0], 0)
+    ids, scores = ix.search_restricted([1.0, 0.0], 3, [1, 2, 3])
+    assert ids.tolist() == [1, 2, 3] and scores.tolist() == [0.0, 0.0, 0.0]
+    ids, _ = ix.search([1.0, 0.0], 3, ef=16)
+    assert ids.tolist() == [1, 2, 3]
+
+
+# --- restricted planning (V/restricted.rs:40-56,200-213,321-342,426-453; T/vector/restricted.rs:532-551) ---
+def test_restricted_admission_and_sampling(hxo):
+    L = hxo.lib()
+    assert L.hxo_restricted_plan(256, 128) == 0
+    assert L.hxo_restricted_plan(257, 128) == 1
+    assert L.hxo_restricted_plan(256, 4096) == 0            # 256*4096*4 = 4 MiB exactly
+    assert L.hxo_restricted_plan(256, 4097) == 1
+    assert hxo.restricted_result_count(10, 3) == (hxo.OK, 3)
+    assert hxo.restricted_result_count(801, 10**6)[0] == hxo.ERR_QUERY
+    assert hxo.restricted_result_count(800, 10**6) == (hxo.OK, 800)
+    assert hxo.deterministic_sample_ids([7], 64).tolist() == [7]
+    assert hxo.deterministic_sample_ids([3, 7], 64).tolist() == [3, 7]
+    ids = np.arange(1, 100001, dtype=np.uint64)
+    s = hxo.deterministic_sample_ids(ids, 64)
+    assert len(s) == 64 and s[0] == 1 and s[-1] == 100000
+    assert all(s[i] < s[i + 1] for i in range(63))
+    assert s.tolist() == [1 + (i * 99999) // 63 for i in range(64)]
+    assert hxo.deterministic_sample_ids(ids, 1).tolist() == [1]
+
+
+# --- layer selection (V/mod.rs:769-796) --------------------------------------------------------------------
+def test_select_layer(hxo):
+    L = hxo.lib()
+    ml = L.hxo_default_ml_for_m(16)
+    assert abs(ml - 1.0 / math.log(16.0)) < 1e-7
+    assert L.hxo_select_layer_from_uniform(ml, 0.99) == 0
+    assert L.hxo_select_layer_from_uniform(ml, 1.0 / 16.0 - 1e-4) == 1
+    assert L.hxo_select_layer_from_uniform(ml, 1.0 / 256.0 - 1e-5) == 2
+    assert L.hxo_select_layer_from_uniform(ml, 0.0) == 31          # clamp to MIN_POSITIVE: floor(87.3*0.3607)
+    assert L.hxo_select_layer_from_uniform(ml, float("nan")) == 0  # 0.5
+    assert L.hxo_select_layer_from_uniform(np.finfo(np.float32).tiny, 0.001) == 0  # ml=MIN_POSITIVE => layer 0
+    assert L.hxo_select_layer_from_uniform(100.0, 1e-30) == 63     # cap
+
+
+# --- item 6: circle fixtures (V/scale_contracts.rs:44-93,161-270) -----------------------------------------
+def _circle_index(hxo, n):
+    ix = hxo.Index(hxo.COSINE, 2, m=32, m0=64, ef_construction=200)
+    for e in range(1, n + 1):
+        ix.put_vector(e, hxo.circle_vector(e, n))
+    for e in range(1, n + 1):
+        ix.put_neighbors(0, e, hxo.skip_neighbors(e, n))
+    ix.set_entry(1, 0)
+    return ix
+
+
+def test_circle_fixture_24_recall_is_one(hxo):
+    n = 24
+    nb = hxo.skip_neighbors(1, n)
+    assert 1 not in nb.tolist() and all(nb[i] < nb[i + 1] for i in range(len(nb) - 1))
+    ix = _circle_index(hxo, n)
+    matched = 0
+    for qi in range(24):
+        e = 1 + qi * (n // 24)
+        q = hxo.circle_vector(e, n)
+        got, _ = ix.search(q, 10, ef=64)
+        exact, _ = ix.search_exact(q, 10)
+        if qi == 0:
+            assert exact[0] == 1
+        matched += len(set(got.tolist()) & set(exact.tolist()))
+    assert matched == 240
+
+
+def test_circle_fixture_10k_recall(hxo):
+    n = 10_000
+    ix = _circle_index(hxo, n)
+    matched = 0
+    for qi in range(24):
+        e = 1 + qi * (n // 24)
+        q = hxo.circle_vector(e, n)
+        got, _ = ix.search(q, 10, ef=64)
+        exact, _ = ix.search_exact(q, 10)
+        matched += len(set(got.tolist()) & set(exact.tolist()))
+    assert matched / 240.0 >= 0.995
+
+
+# --- item 8: build invariants (V/index.rs:3605-3701) -------------------------------------------------------
+def _invariant_matrix_vector(i, d=8):
+    # any deterministic spread works for the structural invariants; mirror a cheap integer recipe
+    return np.array([math.sin(0.37 * (i + 1) * (j + 1)) + 0.01 * j for j in range(d)], dtype=np.float32)
+
+
+@pytest.mark.parametrize("m,efc", [(16, 64), (16, 200), (32, 64), (64, 512)])
+def test_build_invariants(hxo, m, efc):
+    ix = hxo.Index(hxo.EUCLIDEAN, 8, m=m, m0=2 * m, ef_construction=efc)
+    n = 160
+    for i in range(n):
+        ix.insert(i + 1, _invariant_matrix_vector(i), 0)   # ml = MIN_POSITIVE => every node on layer 0
+    lim0 = ix.layer0_limit
+    rows = {i: ix.neighbors(0, i).tolist() for i in range(1, n + 1)}
+    for i, r in rows.items():
+        assert len(r) <= lim0
+        assert i not in r
+        assert all(r[j] < r[j + 1] for j in range(len(r) - 1))
+        for nb in r:
+            assert i in rows[nb], f"edge {i}->{nb} is not bidirectional"
+    assert ix.state() == (1, 0)
+
+
+# --- item 9: xorshift generator, C1's shape (T/index_lifecycle_scale.rs:410-422,1332-1359) ----------------
+def test_xorshift_fixture_and_top1(hxo):
+    v = hxo.xorshift_vectors(0, 3, 128)
+    assert v.shape == (3, 128) and v.min() >= -1.0 and v.max() < 1.0
+    # first component of entity 0, computed by hand from the recipe
+    state = (0 + 0x9E3779B97F4A7C15) & ((1 << 64) - 1)
+    state ^= (state << 13) & ((1 << 64) - 1)
+    state ^= state >> 7
+    state ^= (state << 17) & ((1 << 64) - 1)
+    assert v[0, 0] == np.float32(((state & 0xFFFF) - 32768) / 32768.0)
+    n = 2000
+    rows = hxo.xorshift_vectors(0, n, 128)
+    ix = hxo.Index(hxo.EUCLIDEAN, 128)
+    rng = np.random.default_rng(1234)
+    ml = hxo.lib().hxo_default_ml_for_m(16)
+    for i in range(n):
+        ix.insert(i, rows[i], int(hxo.lib().hxo_select_layer_from_uniform(ml, float(rng.random(dtype=np.float32)))))
+    ids, sc = ix.search(rows[0], 1)
+    assert ids.tolist() == [0] and sc[0] == 0.0      # brute-force top-1 of vector(0) is entity 0
+    # recall@10 of the restated build+search vs exact on held-out queries
+    q = hxo.xorshift_vectors(n, 32, 128)
+    hit = 0
+    for i in range(32):
+        got, _ = ix.search(q[i], 10)
+        ex, _ = ix.search_exact(q[i], 10)
+        hit += len(set(got.tolist()) & set(ex.tolist()))
+    assert hit / 320.0 >= 0.95

@@ -1,0 +1,559 @@
+"""helix-db_b200 — host-side mirror of HelixDB's vector-index read API over the B200 C ABI.
+
+The reference's production vector queries funnel through
+``ValidatedVectorReadIndex::<D>::{search, search_restricted}``
+(crates/db/src/search/vector/read_index.rs:81-101) with ``SearchParams``
+(search/vector/mod.rs:411-621), ``RestrictedVectorCandidates`` (restricted.rs:344-389),
+``SearchResult`` (result.rs:20-40) and ``HelixDbError`` (crates/db/src/error.rs).  This module
+gives the same names, argument meaning and error behaviour on top of ``libhelix_b200.so``
+(include/helix_b200.h) through ctypes, so the parity tests read like the reference's own tests.
+
+There is no CPU fallback: if the CUDA library is missing or no device is present, every search raises.
+Import it as ``helix_db_b200`` (see the shim at the repository root; the directory name is not a Python
+identifier).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libhelix_b200.so"
+
+# ---- status codes (include/helix_b200.h) ------------------------------------------------------------------
+HX_OK = 0
+HX_ERR_INDEX_NOT_FOUND = 1
+HX_ERR_INVALID_DIMENSION = 2
+HX_ERR_INVALID_VECTOR_COMPONENT = 3
+HX_ERR_ZERO_NORM_COSINE = 4
+HX_ERR_MAGNITUDE_EXCEEDED = 5
+HX_ERR_INVALID_VECTOR_CONFIG = 6
+HX_ERR_QUERY = 7
+HX_ERR_INVARIANT_VIOLATION = 8
+HX_ERR_INVALID_PARAMETER = 9
+HX_ERR_CUDA = 10
+HX_ERR_OUT_OF_MEMORY = 11
+HX_ERR_UNSUPPORTED = 12
+
+_VARIANT = {
+    HX_ERR_INDEX_NOT_FOUND: "IndexNotFound",
+    HX_ERR_INVALID_DIMENSION: "InvalidDimension",
+    HX_ERR_INVALID_VECTOR_COMPONENT: "InvalidVectorComponent",
+    HX_ERR_ZERO_NORM_COSINE: "ZeroNormCosineVector",
+    HX_ERR_MAGNITUDE_EXCEEDED: "VectorComponentMagnitudeExceeded",
+    HX_ERR_INVALID_VECTOR_CONFIG: "InvalidVectorConfig",
+    HX_ERR_QUERY: "Query",
+    HX_ERR_INVARIANT_VIOLATION: "InvariantViolation",
+    HX_ERR_INVALID_PARAMETER: "VectorParameterError",
+    HX_ERR_CUDA: "Cuda",
+    HX_ERR_OUT_OF_MEMORY: "OutOfMemory",
+    HX_ERR_UNSUPPORTED: "Unsupported",
+}
+
+
+class HelixDbError(Exception):
+    """Mirror of the HelixDbError variants reachable on this path (crates/db/src/error.rs:379-661)."""
+
+    def __init__(self, code: int, message: str = "", index: int = 0):
+        self.code = code
+        self.variant = _VARIANT.get(code, f"Status{code}")
+        self.index = index
+        super().__init__(f"{self.variant}: {message}")
+
+
+class VectorParameterError(HelixDbError):
+    pass
+
+
+class Metric(enum.IntEnum):
+    Euclidean = 0
+    Cosine = 1
+    Manhattan = 2
+
+
+class SimHashMode(enum.IntEnum):
+    Off = 0
+    Adaptive = 1
+    Always = 2
+
+
+class _Config(C.Structure):
+    _fields_ = [("dimension", C.c_uint32), ("metric", C.c_int32), ("m", C.c_uint32), ("m0", C.c_uint32),
+                ("ef_construction", C.c_uint32), ("device", C.c_int32), ("storage", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class _Params(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("ef", C.c_uint32), ("simhash_mode", C.c_int32), ("pre_sampling_ratio", C.c_float),
+                ("collect_stats", C.c_uint32), ("query_dimension", C.c_uint32)]
+
+
+class SearchStats(C.Structure):
+    """Subset of SearchStats (search/vector/mod.rs:668-679) the device path reports."""
+    _fields_ = [("expansion_steps", C.c_uint64), ("neighbors_examined", C.c_uint64),
+                ("distance_computations", C.c_uint64), ("vectors_loaded", C.c_uint64),
+                ("upper_layer_steps", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("reserved", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_ if f != "reserved"}
+
+
+# every symbol include/helix_b200.h declares (checked by tests/test_abi_surface.py)
+ABI_SYMBOLS = [
+    "hx_index_create", "hx_index_destroy", "hx_index_load_vectors", "hx_index_generate_vectors",
+    "hx_generate_queries", "hx_index_download_vectors", "hx_index_load_graph", "hx_index_set_entry",
+    "hx_index_build", "hx_index_graph_info", "hx_index_download_graph", "hx_search", "hx_search_restricted",
+    "hx_search_restricted_multi", "hx_restricted_plan", "hx_search_device", "hx_search_restricted_device",
+    "hx_map_candidates_device", "hx_merge_topk_device", "hx_search_dense", "hx_last_error", "hx_last_error_index",
+    "hx_version", "hx_last_kernel_ms",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libhelix_b200.so.  Raises (never falls back) when the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise HelixDbError(HX_ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
+                                        f"g.build()'` (there is no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, sz = C.c_void_p, C.c_size_t
+    u64p, u32p, u16p, fp = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint16), C.POINTER(C.c_float)
+    L.hx_index_create.restype = C.c_int32
+    L.hx_index_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    L.hx_index_destroy.restype = None
+    L.hx_index_destroy.argtypes = [vp]
+    L.hx_index_load_vectors.restype = C.c_int32
+    L.hx_index_load_vectors.argtypes = [vp, u64p, fp, sz]
+    L.hx_index_generate_vectors.restype = C.c_int32
+    L.hx_index_generate_vectors.argtypes = [vp, C.c_uint64, sz, C.c_uint64, C.c_uint32, C.c_float]
+    L.hx_generate_queries.restype = C.c_int32
+    L.hx_generate_queries.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_float, C.c_uint64, sz, fp]
+    L.hx_index_download_vectors.restype = C.c_int32
+    L.hx_index_download_vectors.argtypes = [vp, sz, sz, fp, u64p]
+    L.hx_index_load_graph.restype = C.c_int32
+    L.hx_index_load_graph.argtypes = [vp, C.c_uint16, u64p, u32p, u64p, sz]
+    L.hx_index_set_entry.restype = C.c_int32
+    L.hx_index_set_entry.argtypes = [vp, C.c_uint64, C.c_uint16]
+    L.hx_index_build.restype = C.c_int32
+    L.hx_index_build.argtypes = [vp, u16p, C.c_uint64]
+    L.hx_index_graph_info.restype = C.c_int32
+    L.hx_index_graph_info.argtypes = [vp, u64p, u64p, u16p, u32p, u32p]
+    L.hx_index_download_graph.restype = C.c_int32
+    L.hx_index_download_graph.argtypes = [vp, u16p, u32p, u32p, u64p, u32p, u16p, u32p, u32p, sz]
+    L.hx_search.restype = C.c_int32
+    L.hx_search.argtypes = [vp, fp, sz, C.POINTER(_Params), u64p, fp, u32p, C.POINTER(SearchStats)]
+    L.hx_search_restricted.restype = C.c_int32
+    L.hx_search_restricted.argtypes = [vp, fp, sz, C.POINTER(_Params), u64p, sz, u64p, fp, u32p,
+                                       C.POINTER(SearchStats)]
+    L.hx_search_restricted_multi.restype = C.c_int32
+    L.hx_search_restricted_multi.argtypes = [vp, fp, sz, C.POINTER(_Params), u64p, u64p, u64p, fp, u32p,
+                                             C.POINTER(SearchStats)]
+    L.hx_restricted_plan.restype = C.c_int32
+    L.hx_restricted_plan.argtypes = [C.c_uint64, C.c_uint32]
+    L.hx_search_device.restype = C.c_int32
+    L.hx_search_device.argtypes = [vp, vp, sz, C.POINTER(_Params), vp, vp, vp, vp, C.POINTER(SearchStats)]
+    L.hx_search_restricted_device.restype = C.c_int32
+    L.hx_search_restricted_device.argtypes = [vp, vp, sz, C.POINTER(_Params), vp, vp, C.c_uint64, C.c_uint64, vp, vp,
+                                              vp, vp]
+    L.hx_map_candidates_device.restype = C.c_int32
+    L.hx_map_candidates_device.argtypes = [vp, vp, C.c_uint64, vp, vp, vp]
+    L.hx_merge_topk_device.restype = C.c_int32
+    L.hx_merge_topk_device.argtypes = [C.c_int32, vp, vp, vp, C.c_uint32, sz, C.c_uint32, vp, vp, vp, vp]
+    L.hx_search_dense.restype = C.c_int32
+    L.hx_search_dense.argtypes = [vp, fp, sz, C.POINTER(_Params), u64p, fp, u32p, C.POINTER(SearchStats)]
+    L.hx_last_error.restype = C.c_char_p
+    L.hx_last_error_index.restype = C.c_uint32
+    L.hx_version.restype = C.c_char_p
+    L.hx_last_kernel_ms.restype = C.c_int32
+    L.hx_last_kernel_ms.argtypes = [vp, fp, u32p]
+    _lib = L
+    return L
+
+
+def _raise(code: int):
+    L = load_library()
+    msg = (L.hx_last_error() or b"").decode("utf-8", "replace")
+    idx = int(L.hx_last_error_index())
+    cls = VectorParameterError if code == HX_ERR_INVALID_PARAMETER else HelixDbError
+    raise cls(code, msg, idx)
+
+
+def _ck(code: int):
+    if code != HX_OK:
+        _raise(code)
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u64(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _u32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+# ---- reference-shaped value types -------------------------------------------------------------------------
+class SearchResult:
+    """SearchResult{entity_id, score} (search/vector/result.rs:20-40)."""
+    __slots__ = ("_id", "_score")
+
+    def __init__(self, entity_id: int, score: float):
+        self._id, self._score = int(entity_id), np.float32(score)
+
+    def entity_id(self) -> int:
+        return self._id
+
+    def score(self) -> np.float32:
+        return self._score
+
+    def __repr__(self):
+        return f"SearchResult(entity_id={self._id}, score={float(self._score)!r})"
+
+    def __eq__(self, o):
+        return isinstance(o, SearchResult) and self._id == o._id and self._score.tobytes() == o._score.tobytes()
+
+
+class SearchParams:
+    """SearchParams builder (search/vector/mod.rs:480-621).  ``SearchParams.new(k)``: ef = max(k,100),
+    SimHashMode.Adaptive.  Only ``Off`` + pre-sampling 1.0 (strict exhaustive) executes on the device."""
+
+    def __init__(self, k: int):
+        if k <= 0:
+            raise VectorParameterError(HX_ERR_INVALID_PARAMETER, "result count must be non-zero")
+        self._k = int(k)
+        self._ef = max(self._k, 100)
+        self._mode = SimHashMode.Adaptive
+        self._pre_ratio = None
+        self.collect_stats = False
+        self.query_dimension = 0
+
+    @classmethod
+    def new(cls, k: int) -> "SearchParams":
+        return cls(k)
+
+    def k(self):
+        return self._k
+
+    def ef(self):
+        return self._ef
+
+    def with_ef(self, ef: int) -> "SearchParams":
+        if ef < self._k:
+            raise VectorParameterError(HX_ERR_INVALID_PARAMETER,
+                                       f"search beam width must be at least {self._k}, got {ef}")
+        self._ef = int(ef)
+        return self
+
+    def with_simhash_mode(self, mode: SimHashMode) -> "SearchParams":
+        self._mode = SimHashMode(mode)
+        return self
+
+    def with_pre_simhash_sampling_ratio(self, ratio: float) -> "SearchParams":
+        if not (0.0 <= ratio <= 1.0):
+            raise VectorParameterError(HX_ERR_INVALID_PARAMETER, "ratio must be in the unit interval")
+        self._pre_ratio = float(ratio)
+        return self
+
+    @classmethod
+    def strict(cls, k: int, ef: int | None = None) -> "SearchParams":
+        """The reference's strict baseline: Off + pre-sampling 1.0 (mod.rs:518-554)."""
+        p = cls(k).with_simhash_mode(SimHashMode.Off).with_pre_simhash_sampling_ratio(1.0)
+        return p.with_ef(ef) if ef is not None else p
+
+    def requires_query_simhash(self) -> bool:   # mod.rs:556-561
+        return self._mode != SimHashMode.Off or (self._pre_ratio is not None and self._pre_ratio < 1.0)
+
+    def _c(self) -> _Params:
+        ratio = 1.0 if self._pre_ratio is None and self._mode == SimHashMode.Off else \
+            (self._pre_ratio if self._pre_ratio is not None else 0.8)
+        return _Params(self._k, self._ef, int(self._mode), ratio, 1 if self.collect_stats else 0,
+                       int(self.query_dimension))
+
+
+class RestrictedVectorCandidates:
+    """RestrictedVectorCandidates::from_ids (restricted.rs:356-371): unique ascending ids, at most 1e6."""
+    MAX = 1_000_000
+
+    def __init__(self, ids: np.ndarray):
+        self.ids = ids
+
+    @classmethod
+    def from_ids(cls, ids) -> "RestrictedVectorCandidates":
+        a = np.unique(np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids, dtype=np.uint64))
+        if a.size > cls.MAX:
+            raise HelixDbError(HX_ERR_QUERY, f"restricted vector search accepts at most {cls.MAX} unique candidates")
+        return cls(a)
+
+    def is_empty(self):
+        return self.ids.size == 0
+
+    def contains(self, node_id: int) -> bool:
+        i = np.searchsorted(self.ids, np.uint64(node_id))
+        return bool(i < self.ids.size and self.ids[i] == node_id)
+
+    def __len__(self):
+        return int(self.ids.size)
+
+
+class VectorIndexConfig:
+    """VectorIndexConfig::new(name, property, dimension).with_m(..) (defaults config/indexes.rs:374-408)."""
+
+    def __init__(self, name: str, prop: str, dimension: int):
+        self.name, self.property, self.dimension = name, prop, int(dimension)
+        self.m, self.m0, self.ef_construction = 16, 32, 200
+
+    def with_m(self, m):
+        self.m = int(m)
+        return self
+
+    def with_m0(self, m0):
+        self.m0 = int(m0)
+        return self
+
+    def with_ef_construction(self, e):
+        self.ef_construction = int(e)
+        return self
+
+
+class VectorIndex:
+    """Device-resident stand-in for ``VectorIndex::<D>`` (search/vector/index.rs).
+
+    The reference reads rows through SlateDB; here the rows are mirrored once into HBM
+    (``load_vectors`` / ``load_graph`` / ``set_entry`` or ``build``) and then searched."""
+
+    def __init__(self, metric: Metric, config: VectorIndexConfig, device: int = 0, storage: int = 0):
+        self.L = load_library()
+        self.metric, self.config, self.device = Metric(metric), config, device
+        cfg = _Config(config.dimension, int(self.metric), config.m, config.m0, config.ef_construction, device,
+                      storage, 0)
+        h = C.c_void_p()
+        _ck(self.L.hx_index_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.dim = config.dimension
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hx_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mirror management ----
+    def load_vectors(self, ids, rows):
+        ia, ip = _u64(ids)
+        ra, rp = _f32(rows)
+        if ra.size != ia.size * self.dim:
+            raise HelixDbError(HX_ERR_INVALID_DIMENSION, f"expected {ia.size}x{self.dim} floats, got {ra.size}")
+        _ck(self.L.hx_index_load_vectors(self.h, ip, rp, ia.size))
+
+    def generate_vectors(self, first_id, n, seed, n_centroids=1024, sigma=0.3):
+        _ck(self.L.hx_index_generate_vectors(self.h, first_id, n, seed, n_centroids, sigma))
+
+    def generate_queries(self, seed, n, first_query=0, n_centroids=1024, sigma=0.3):
+        out = np.empty((n, self.dim), dtype=np.float32)
+        _ck(self.L.hx_generate_queries(self.h, seed, n_centroids, sigma, first_query, n,
+                                       out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def download_vectors(self, first_slot, n):
+        rows = np.empty((n, self.dim), dtype=np.float32)
+        ids = np.empty(n, dtype=np.uint64)
+        _ck(self.L.hx_index_download_vectors(self.h, first_slot, n, rows.ctypes.data_as(C.POINTER(C.c_float)),
+                                             ids.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return ids, rows
+
+    def load_graph(self, layer, node_ids, offsets, neighbors):
+        na, np_ = _u64(node_ids)
+        oa, op = _u32(offsets)
+        nb, nbp = _u64(neighbors)
+        _ck(self.L.hx_index_load_graph(self.h, layer, np_, op, nbp, na.size))
+
+    def set_entry(self, entry_point, max_layer):
+        _ck(self.L.hx_index_set_entry(self.h, entry_point, max_layer))
+
+    def build(self, levels=None, seed=0):
+        if levels is None:
+            _ck(self.L.hx_index_build(self.h, None, seed))
+        else:
+            la = np.ascontiguousarray(levels, dtype=np.uint16)
+            _ck(self.L.hx_index_build(self.h, la.ctypes.data_as(C.POINTER(C.c_uint16)), seed))
+
+    def graph_info(self):
+        n, e, ml, s0, su = C.c_uint64(0), C.c_uint64(0), C.c_uint16(0), C.c_uint32(0), C.c_uint32(0)
+        _ck(self.L.hx_index_graph_info(self.h, C.byref(n), C.byref(e), C.byref(ml), C.byref(s0), C.byref(su)))
+        return dict(n=int(n.value), entry_point=int(e.value), max_layer=int(ml.value), layer0_stride=int(s0.value),
+                    upper_stride=int(su.value))
+
+    def download_graph(self):
+        gi = self.graph_info()
+        n, s0, su = gi["n"], gi["layer0_stride"], gi["upper_stride"]
+        nup = C.c_uint64(0)
+        _ck(self.L.hx_index_download_graph(self.h, None, None, None, C.byref(nup), None, None, None, None, 0))
+        rows = int(nup.value)
+        levels = np.zeros(max(n, 1), dtype=np.uint16)
+        deg0 = np.zeros(max(n, 1), dtype=np.uint32)
+        nbr0 = np.zeros(max(n * s0, 1), dtype=np.uint32)
+        un = np.zeros(max(rows, 1), dtype=np.uint32)
+        ul = np.zeros(max(rows, 1), dtype=np.uint16)
+        ud = np.zeros(max(rows, 1), dtype=np.uint32)
+        unb = np.zeros(max(rows * su, 1), dtype=np.uint32)
+        _ck(self.L.hx_index_download_graph(
+            self.h, levels.ctypes.data_as(C.POINTER(C.c_uint16)), deg0.ctypes.data_as(C.POINTER(C.c_uint32)),
+            nbr0.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(nup), un.ctypes.data_as(C.POINTER(C.c_uint32)),
+            ul.ctypes.data_as(C.POINTER(C.c_uint16)), ud.ctypes.data_as(C.POINTER(C.c_uint32)),
+            unb.ctypes.data_as(C.POINTER(C.c_uint32)), rows))
+        gi.update(levels=levels[:n], deg0=deg0[:n], nbr0=nbr0[:n * s0], upper_node=un[:rows], upper_layer=ul[:rows],
+                  upper_deg=ud[:rows], upper_nbr=unb[:rows * su])
+        return gi
+
+    def mirror_from_oracle(self, oracle_index):
+        """Upload the rows of an oracle.hxo.Index (tests only; the oracle object is passed in by the test)."""
+        ids = oracle_index.node_ids()
+        rows = np.stack([oracle_index.vector(int(i)) for i in ids]) if len(ids) else np.zeros((0, self.dim), np.float32)
+        self.load_vectors(ids, rows)
+        graph, state = oracle_index.export_graph()
+        for layer, (nodes, offs, nbrs) in graph.items():
+            self.load_graph(layer, nodes, offs, nbrs)
+        if state is not None:
+            self.set_entry(state[0], state[1])
+
+    # ---- search ----
+    def _search_raw(self, queries, params: SearchParams, stats=None):
+        qa, qp = _f32(queries)
+        qd = params.query_dimension or self.dim
+        B = qa.size // qd if qa.ndim != 1 or qa.size != qd else 1
+        cp = params._c()
+        k = cp.k
+        ids = np.zeros((B, k), dtype=np.uint64)
+        sc = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        st = stats if stats is not None else SearchStats()
+        _ck(self.L.hx_search(self.h, qp, B, C.byref(cp), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                             sc.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_uint32)),
+                             C.byref(st)))
+        return ids, sc, cnt
+
+    def search(self, query, params: SearchParams):
+        """VectorIndex::search (index.rs:1578): one query -> Vec<SearchResult> sorted by (score, id)."""
+        ids, sc, cnt = self._search_raw(np.asarray(query, dtype=np.float32).reshape(1, -1), params)
+        return [SearchResult(ids[0, i], sc[0, i]) for i in range(int(cnt[0]))]
+
+    def search_with_stats(self, query, params: SearchParams):
+        params.collect_stats = True
+        st = SearchStats()
+        ids, sc, cnt = self._search_raw(np.asarray(query, dtype=np.float32).reshape(1, -1), params, st)
+        return [SearchResult(ids[0, i], sc[0, i]) for i in range(int(cnt[0]))], st
+
+    def search_batch(self, queries, params: SearchParams, stats=None):
+        return self._search_raw(np.asarray(queries, dtype=np.float32), params, stats)
+
+    def search_restricted(self, query, params: SearchParams, allowed: RestrictedVectorCandidates):
+        """VectorIndex::search_restricted (restricted.rs:466-479); exact for every |C| <= 1e6."""
+        ids, sc, cnt = self.search_restricted_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), params,
+                                                    allowed)
+        return [SearchResult(ids[0, i], sc[0, i]) for i in range(int(cnt[0]))]
+
+    def search_restricted_batch(self, queries, params: SearchParams, allowed: RestrictedVectorCandidates, stats=None):
+        qa, qp = _f32(queries)
+        qd = params.query_dimension or self.dim
+        B = qa.size // qd
+        cp = params._c()
+        k = cp.k
+        ca, cpnt = _u64(allowed.ids)
+        ids = np.zeros((B, k), dtype=np.uint64)
+        sc = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        st = stats if stats is not None else SearchStats()
+        _ck(self.L.hx_search_restricted(self.h, qp, B, C.byref(cp), cpnt, ca.size,
+                                        ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                        cnt.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(st)))
+        return ids, sc, cnt
+
+    def search_restricted_multi(self, queries, params: SearchParams, cand_ids, cand_offsets, stats=None):
+        qa, qp = _f32(queries)
+        B = qa.size // self.dim
+        cp = params._c()
+        k = cp.k
+        ca, cpnt = _u64(cand_ids)
+        oa, op = _u64(cand_offsets)
+        assert oa.size == B + 1
+        ids = np.zeros((B, k), dtype=np.uint64)
+        sc = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        st = stats if stats is not None else SearchStats()
+        _ck(self.L.hx_search_restricted_multi(self.h, qp, B, C.byref(cp), cpnt, op,
+                                              ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                              cnt.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(st)))
+        return ids, sc, cnt
+
+    def search_dense_batch(self, queries, params: SearchParams, stats=None):
+        qa, qp = _f32(queries)
+        B = qa.size // self.dim
+        cp = params._c()
+        k = cp.k
+        ids = np.zeros((B, k), dtype=np.uint64)
+        sc = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        st = stats if stats is not None else SearchStats()
+        _ck(self.L.hx_search_dense(self.h, qp, B, C.byref(cp), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                   sc.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                   C.byref(st)))
+        return ids, sc, cnt
+
+    # ---- device-buffer path (raw pointers, e.g. torch tensors' data_ptr()) ----
+    def search_device(self, d_queries_ptr, B, params: SearchParams, d_ids_ptr, d_scores_ptr, d_counts_ptr,
+                      stream_ptr=0, stats=None):
+        cp = params._c()
+        _ck(self.L.hx_search_device(self.h, d_queries_ptr, B, C.byref(cp), d_ids_ptr, d_scores_ptr, d_counts_ptr,
+                                    stream_ptr, C.byref(stats) if stats is not None else None))
+
+    def search_restricted_device(self, d_queries_ptr, B, params, d_slots_ptr, d_offsets_ptr, total, max_per_query,
+                                 d_ids_ptr, d_scores_ptr, d_counts_ptr, stream_ptr=0):
+        cp = params._c()
+        _ck(self.L.hx_search_restricted_device(self.h, d_queries_ptr, B, C.byref(cp), d_slots_ptr, d_offsets_ptr,
+                                               total, max_per_query, d_ids_ptr, d_scores_ptr, d_counts_ptr,
+                                               stream_ptr))
+
+    def map_candidates_device(self, d_ids_ptr, n, d_slots_ptr, stream_ptr=0):
+        _ck(self.L.hx_map_candidates_device(self.h, d_ids_ptr, n, d_slots_ptr, None, stream_ptr))
+
+    def last_kernel_ms(self):
+        ms, n = C.c_float(0), C.c_uint32(0)
+        _ck(self.L.hx_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+
+def merge_topk_device(device, d_all_ids, d_all_scores, d_all_counts, n_shards, B, k, d_out_ids, d_out_scores,
+                      d_out_counts, stream_ptr=0):
+    _ck(load_library().hx_merge_topk_device(device, d_all_ids, d_all_scores, d_all_counts, n_shards, B, k, d_out_ids,
+                                            d_out_scores, d_out_counts, stream_ptr))
+
+
+def restricted_plan(n_candidates: int, dimension: int) -> str:
+    """RestrictedExecutionPlan the reference would choose (restricted.rs:426-453)."""
+    return "Exact" if load_library().hx_restricted_plan(n_candidates, dimension) == 0 else "FilteredGraph"
+
+
+def version() -> str:
+    return load_library().hx_version().decode()

@@ -1,0 +1,1276 @@
+// hx_api.cu — C ABI of libhelix_b200 (include/helix_b200.h): index mirror management and the
+// search entry points that stand in for VectorIndex::search / search_restricted
+// (crates/db/src/search/vector/index.rs:1578-1587, restricted.rs:466-613).
+//
+// There is deliberately NO CPU fallback in this file: every search runs the CUDA kernels or fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "hx_index.hpp"
+#include "k_hnsw.cuh"
+#include "k_scan.cuh"
+#include "k_util.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local uint32_t g_err_index = 0;
+
+void hx_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void hx_set_error_index(uint32_t idx) { g_err_index = idx; }
+
+extern "C" const char* hx_last_error(void) { return g_err; }
+extern "C" uint32_t hx_last_error_index(void) { return g_err_index; }
+extern "C" const char* hx_version(void) { return "helix_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+// VectorComponentLimit::try_new (domain.rs:24-79)
+static bool component_limit(int metric, uint32_t dim, float* limit) {
+  if (metric == HX_METRIC_COSINE) return false;
+  const double factor = metric == HX_METRIC_EUCLIDEAN ? 8.0 : 4.0;
+  const double divisor = (double)dim * factor;
+  const double exact =
+      metric == HX_METRIC_EUCLIDEAN ? std::sqrt((double)FLT_MAX / divisor) : (double)FLT_MAX / divisor;
+  float rounded = (float)exact;
+  if ((double)rounded > exact) {
+    uint32_t bits;
+    memcpy(&bits, &rounded, 4);
+    bits -= 1;
+    memcpy(&rounded, &bits, 4);
+  }
+  *limit = rounded;
+  return true;
+}
+
+// scaled_l2_norm / norm_no_header on the host (cosine.rs:12-36,120-122) for the small-batch path.
+static float host_cosine_norm(const float* v, uint32_t d) {
+  double scale = 0.0, scaled_sum = 1.0;
+  for (uint32_t i = 0; i < d; ++i) {
+    double magnitude = (double)std::fabs(v[i]);
+    if (magnitude == 0.0) continue;
+    if (scale < magnitude) {
+      double ratio = scale / magnitude;
+      double t = scaled_sum * ratio;
+      t = t * ratio;
+      scaled_sum = 1.0 + t;
+      scale = magnitude;
+    } else {
+      double ratio = magnitude / scale;
+      double t = ratio * ratio;
+      scaled_sum = scaled_sum + t;
+    }
+  }
+  double n = scale == 0.0 ? 0.0 : scale * std::sqrt(scaled_sum);
+  if (n > (double)FLT_MAX) n = (double)FLT_MAX;
+  return (float)n;
+}
+
+// ValidatedMetricVector::try_new on the host; returns status word like k_validate_and_header
+static uint32_t host_validate(const float* v, uint32_t dim, int metric, bool has_limit, float limit) {
+  for (uint32_t i = 0; i < dim; ++i)
+    if (!std::isfinite(v[i])) return (HX_ST_COMPONENT << 24) | (i & 0xffffffu);
+  if (metric == HX_METRIC_COSINE) {
+    bool nz = false;
+    for (uint32_t i = 0; i < dim; ++i)
+      if (!(v[i] == 0.0f)) { nz = true; break; }
+    if (!nz) return HX_ST_ZERO_NORM << 24;
+  }
+  if (has_limit)
+    for (uint32_t i = 0; i < dim; ++i)
+      if (std::fabs(v[i]) > limit) return (HX_ST_MAGNITUDE << 24) | (i & 0xffffffu);
+  return HX_ST_OK;
+}
+
+static hx_status status_from_word(uint32_t w, size_t which, const char* what) {
+  const uint32_t code = w >> 24, idx = w & 0xffffffu;
+  hx_set_error_index(idx);
+  switch (code) {
+    case HX_ST_COMPONENT:
+      hx_set_error("%s %zu: component %u is not finite", what, which, idx);
+      return HX_ERR_INVALID_VECTOR_COMPONENT;
+    case HX_ST_ZERO_NORM:
+      hx_set_error("%s %zu: zero-norm vector under the cosine metric", what, which);
+      return HX_ERR_ZERO_NORM_COSINE;
+    case HX_ST_MAGNITUDE:
+      hx_set_error("%s %zu: component %u exceeds the metric magnitude limit", what, which, idx);
+      return HX_ERR_MAGNITUDE_EXCEEDED;
+    default:
+      return HX_OK;
+  }
+}
+
+HxDev hx_index::dev() const {
+  HxDev d{};
+  d.vec = d_vec;
+  d.hdr = d_hdr;
+  d.ids = d_ids;
+  d.nbr0 = d_nbr0;
+  d.deg0 = d_deg0;
+  d.raw0 = d_raw0;
+  d.upper_off = d_upper_off;
+  d.upper_nbr = d_upper_nbr;
+  d.upper_deg = d_upper_deg;
+  d.level = d_level;
+  d.n = (uint32_t)n;
+  d.dim = cfg.dimension;
+  d.ld = ld;
+  d.stride0 = stride0;
+  d.stride_u = stride_u;
+  d.metric = cfg.metric;
+  d.entry_slot = entry_slot;
+  d.max_layer = max_layer;
+  d.populated = populated ? 1 : 0;
+  return d;
+}
+
+void hx_index::free_vectors() {
+  if (d_vec) cudaFree(d_vec);
+  if (d_hdr) cudaFree(d_hdr);
+  if (d_ids) cudaFree(d_ids);
+  if (d_vec_bf16) cudaFree(d_vec_bf16);
+  if (d_sqnorm) cudaFree(d_sqnorm);
+  d_vec = nullptr; d_hdr = nullptr; d_ids = nullptr; d_vec_bf16 = nullptr; d_sqnorm = nullptr;
+  n = 0;
+  ids_sorted.clear();
+}
+
+void hx_index::free_graph() {
+  if (d_nbr0) cudaFree(d_nbr0);
+  if (d_deg0) cudaFree(d_deg0);
+  if (d_raw0) cudaFree(d_raw0);
+  if (d_upper_off) cudaFree(d_upper_off);
+  if (d_upper_nbr) cudaFree(d_upper_nbr);
+  if (d_upper_deg) cudaFree(d_upper_deg);
+  if (d_level) cudaFree(d_level);
+  d_nbr0 = nullptr; d_deg0 = nullptr; d_raw0 = nullptr; d_upper_off = nullptr;
+  d_upper_nbr = nullptr; d_upper_deg = nullptr; d_level = nullptr;
+  stride0 = 0; stride_u = 0; n_upper_rows = 0;
+  staged.clear();
+  graph_dirty = false;
+  populated = false;
+}
+
+hx_status HxScratch::ring_next(cudaEvent_t* e0, cudaEvent_t* e1) {
+  const size_t cap = 512;
+  if (ring0.size() < cap) {
+    cudaEvent_t a, b;
+    HX_CUDA(cudaEventCreate(&a));
+    HX_CUDA(cudaEventCreate(&b));
+    ring0.push_back(a);
+    ring1.push_back(b);
+    *e0 = a;
+    *e1 = b;
+    ring_pos = ring0.size() % cap;
+  } else {
+    *e0 = ring0[ring_pos];
+    *e1 = ring1[ring_pos];
+    ring_pos = (ring_pos + 1) % cap;
+  }
+  if (ring_pending < cap) ring_pending++;
+  return HX_OK;
+}
+
+void HxScratch::destroy() {
+  for (cudaEvent_t e : ring0) cudaEventDestroy(e);
+  for (cudaEvent_t e : ring1) cudaEventDestroy(e);
+  ring0.clear();
+  ring1.clear();
+  if (stream) cudaStreamDestroy(stream);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  d_queries.release(); d_qhdr.release(); d_out_scores.release();
+  d_qstatus.release(); d_out_counts.release(); d_qstats.release(); d_err.release(); d_epochs.release();
+  d_cand_slots.release(); d_out_ids.release(); d_cand_ids.release(); d_cand_offsets.release(); d_keys.release();
+  d_stamps.release();
+  h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
+  h_counts.release(); h_qstats.release(); h_status.release(); h_err.release();
+}
+
+hx_status hx_acquire_scratch(hx_index* ix, HxScratch** out) {
+  std::unique_lock<std::mutex> lk(ix->mu);
+  for (;;) {
+    for (HxScratch* s : ix->pool)
+      if (!s->busy) {
+        s->busy = true;
+        *out = s;
+        return HX_OK;
+      }
+    if (ix->pool.size() < 4) {
+      HxScratch* s = new HxScratch();
+      cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+      if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+      if (e != cudaSuccess) {
+        hx_set_error("scratch creation failed: %s", cudaGetErrorString(e));
+        s->destroy();
+        delete s;
+        return HX_ERR_CUDA;
+      }
+      s->busy = true;
+      ix->pool.push_back(s);
+      *out = s;
+      return HX_OK;
+    }
+    ix->cv.wait(lk);
+  }
+}
+
+void hx_release_scratch(hx_index* ix, HxScratch* s) {
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    s->busy = false;
+  }
+  ix->cv.notify_one();
+}
+
+// Device-buffer calls are ordered by the caller's stream and share one dedicated scratch set.
+static hx_status dev_scratch(hx_index* ix, HxScratch** out) {
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!ix->dev_scratch) ix->dev_scratch = new HxScratch();
+  *out = ix->dev_scratch;
+  return HX_OK;
+}
+
+struct ScratchGuard {
+  hx_index* ix;
+  HxScratch* s;
+  ~ScratchGuard() {
+    if (s) hx_release_scratch(ix, s);
+  }
+};
+
+bool hx_slot_of(const hx_index* ix, uint64_t id, uint32_t* slot) {
+  if (ix->n == 0) return false;
+  if (ix->contiguous) {
+    if (id < ix->first_id || id - ix->first_id >= ix->n) return false;
+    *slot = (uint32_t)(id - ix->first_id);
+    return true;
+  }
+  auto it = std::lower_bound(ix->ids_sorted.begin(), ix->ids_sorted.end(), id);
+  if (it == ix->ids_sorted.end() || *it != id) return false;
+  *slot = (uint32_t)(it - ix->ids_sorted.begin());
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" hx_status hx_index_create(const hx_index_config* cfg, hx_index** out) {
+  if (!cfg || !out) {
+    hx_set_error("hx_index_create: null argument");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  *out = nullptr;
+  if (cfg->dimension == 0 || cfg->m == 0 || cfg->metric < 0 || cfg->metric > 2) {
+    hx_set_error("invalid vector index config: dimension=%u m=%u metric=%d", cfg->dimension, cfg->m, cfg->metric);
+    return HX_ERR_INVALID_VECTOR_CONFIG;
+  }
+  if (cfg->dimension > 65536) {
+    hx_set_error("dimension %u above the supported maximum 65536", cfg->dimension);
+    return HX_ERR_INVALID_VECTOR_CONFIG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    hx_set_error("no CUDA device available (%s): libhelix_b200 has no CPU fallback", cudaGetErrorString(e));
+    return HX_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    hx_set_error("device ordinal %d out of range (%d devices)", cfg->device, ndev);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  HX_CUDA(cudaSetDevice(cfg->device));
+  hx_index* ix = new hx_index();
+  ix->cfg = *cfg;
+  ix->device = cfg->device;
+  ix->lim0 = std::max(cfg->m0, 2 * cfg->m);
+  ix->ld = round_up(cfg->dimension, 32);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
+  *out = ix;
+  return HX_OK;
+}
+
+extern "C" void hx_index_destroy(hx_index* ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  cudaDeviceSynchronize();
+  for (HxScratch* s : ix->pool) {
+    s->destroy();
+    delete s;
+  }
+  if (ix->dev_scratch) {
+    ix->dev_scratch->destroy();
+    delete ix->dev_scratch;
+  }
+  ix->free_graph();
+  ix->free_vectors();
+  delete ix;
+}
+
+static hx_status alloc_vectors(hx_index* ix, size_t n) {
+  ix->free_graph();
+  ix->free_vectors();
+  if (n >= (1ull << 31)) {
+    hx_set_error("a shard holds at most 2^31-1 rows (got %zu)", n);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (n == 0) return HX_OK;
+  HX_CUDA(cudaMalloc((void**)&ix->d_vec, n * (size_t)ix->ld * sizeof(float)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_hdr, n * sizeof(float)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_ids, n * sizeof(uint64_t)));
+  ix->n = n;
+  return HX_OK;
+}
+
+// validate rows on the device like decode_item_borrowed (mod.rs:889-949) and compute row headers
+static hx_status validate_rows_device(hx_index* ix) {
+  const size_t n = ix->n;
+  uint32_t* d_status = nullptr;
+  HX_CUDA(cudaMalloc((void**)&d_status, n * sizeof(uint32_t)));
+  float limit = 0.f;
+  const bool has_limit = component_limit(ix->cfg.metric, ix->cfg.dimension, &limit);
+  const size_t threads = 256, warps_per_block = threads / 32;
+  const size_t blocks = (n + warps_per_block - 1) / warps_per_block;
+  k_validate_and_header<<<(unsigned)blocks, (unsigned)threads>>>(ix->d_vec, n, ix->cfg.dimension, ix->ld,
+                                                               ix->cfg.metric, limit, has_limit ? 1 : 0, ix->d_hdr,
+                                                               d_status);
+  cudaError_t e = cudaGetLastError();
+  std::vector<uint32_t> st(n);
+  if (e == cudaSuccess) e = cudaMemcpy(st.data(), d_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_status);
+  if (e != cudaSuccess) {
+    hx_set_error("row validation failed: %s", cudaGetErrorString(e));
+    return HX_ERR_CUDA;
+  }
+  for (size_t i = 0; i < n; ++i)
+    if (st[i] != HX_ST_OK) return status_from_word(st[i], i, "row (slot)");
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_load_vectors(hx_index* ix, const uint64_t* ids, const float* rows, size_t n) {
+  if (!ix) {
+    hx_set_error("null index handle");
+    return HX_ERR_INDEX_NOT_FOUND;
+  }
+  if (n && (!ids || !rows)) {
+    hx_set_error("hx_index_load_vectors: null pointer");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  HX_CUDA(cudaSetDevice(ix->device));
+  hx_status rc = alloc_vectors(ix, n);
+  if (rc) return rc;
+  if (n == 0) return HX_OK;
+  const uint32_t dim = ix->cfg.dimension;
+  // slot order = ascending id
+  std::vector<uint32_t> order(n);
+  std::iota(order.begin(), order.end(), 0u);
+  bool sorted = true;
+  for (size_t i = 1; i < n; ++i)
+    if (ids[i - 1] >= ids[i]) { sorted = false; break; }
+  if (!sorted) {
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b]; });
+    for (size_t i = 1; i < n; ++i)
+      if (ids[order[i - 1]] == ids[order[i]]) {
+        hx_set_error("duplicate node id %llu", (unsigned long long)ids[order[i]]);
+        ix->free_vectors();
+        return HX_ERR_INVARIANT_VIOLATION;
+      }
+  }
+  ix->ids_sorted.resize(n);
+  for (size_t i = 0; i < n; ++i) ix->ids_sorted[i] = ids[order[i]];
+  ix->first_id = ix->ids_sorted[0];
+  ix->contiguous = (ix->ids_sorted[n - 1] - ix->ids_sorted[0] == (uint64_t)(n - 1));
+  HX_CUDA(cudaMemcpy(ix->d_ids, ix->ids_sorted.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  if (sorted && ix->ld == dim) {
+    HX_CUDA(cudaMemcpy(ix->d_vec, rows, n * (size_t)dim * sizeof(float), cudaMemcpyHostToDevice));
+  } else if (sorted) {
+    HX_CUDA(cudaMemset(ix->d_vec, 0, n * (size_t)ix->ld * sizeof(float)));
+    HX_CUDA(cudaMemcpy2D(ix->d_vec, (size_t)ix->ld * sizeof(float), rows, (size_t)dim * sizeof(float),
+                         (size_t)dim * sizeof(float), n, cudaMemcpyHostToDevice));
+  } else {
+    const size_t chunk = std::max<size_t>(1, (64u << 20) / ((size_t)ix->ld * sizeof(float)));
+    std::vector<float> stage(chunk * (size_t)ix->ld, 0.f);
+    for (size_t b = 0; b < n; b += chunk) {
+      const size_t c = std::min(chunk, n - b);
+      for (size_t i = 0; i < c; ++i)
+        memcpy(stage.data() + i * (size_t)ix->ld, rows + (size_t)order[b + i] * dim, dim * sizeof(float));
+      HX_CUDA(cudaMemcpy(ix->d_vec + b * (size_t)ix->ld, stage.data(), c * (size_t)ix->ld * sizeof(float),
+                         cudaMemcpyHostToDevice));
+    }
+  }
+  rc = validate_rows_device(ix);
+  if (rc) {
+    ix->free_vectors();
+    return rc;
+  }
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_generate_vectors(hx_index* ix, uint64_t first_id, size_t n, uint64_t seed,
+                                               uint32_t n_centroids, float sigma) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (n_centroids == 0) return HX_ERR_INVALID_PARAMETER;
+  HX_CUDA(cudaSetDevice(ix->device));
+  hx_status rc = alloc_vectors(ix, n);
+  if (rc || n == 0) return rc;
+  const size_t blocks = (n + 7) / 8;
+  k_generate_mixture<<<(unsigned)blocks, 256>>>(ix->d_vec, n, ix->cfg.dimension, ix->ld, seed, n_centroids, sigma, 0,
+                                               0x1111ull);
+  k_iota_ids<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_ids, n, first_id);
+  HX_CUDA(cudaGetLastError());
+  ix->ids_sorted.resize(n);
+  for (size_t i = 0; i < n; ++i) ix->ids_sorted[i] = first_id + i;
+  ix->first_id = first_id;
+  ix->contiguous = true;
+  rc = validate_rows_device(ix);
+  if (rc) ix->free_vectors();
+  return rc;
+}
+
+extern "C" hx_status hx_generate_queries(hx_index* ix, uint64_t seed, uint32_t n_centroids, float sigma,
+                                         uint64_t first_query, size_t n_queries, float* out_host) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (!out_host || n_centroids == 0) return HX_ERR_INVALID_PARAMETER;
+  if (n_queries == 0) return HX_OK;
+  HX_CUDA(cudaSetDevice(ix->device));
+  float* d = nullptr;
+  const uint32_t dim = ix->cfg.dimension;
+  HX_CUDA(cudaMalloc((void**)&d, n_queries * (size_t)ix->ld * sizeof(float)));
+  k_generate_mixture<<<(unsigned)((n_queries + 7) / 8), 256>>>(d, n_queries, dim, ix->ld, seed, n_centroids, sigma,
+                                                              first_query, 0x2222ull);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpy2D(out_host, (size_t)dim * sizeof(float), d, (size_t)ix->ld * sizeof(float),
+                     (size_t)dim * sizeof(float), n_queries, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    hx_set_error("query generation failed: %s", cudaGetErrorString(e));
+    return HX_ERR_CUDA;
+  }
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_download_vectors(hx_index* ix, size_t first_slot, size_t n, float* out_rows,
+                                               uint64_t* out_ids) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (first_slot + n > ix->n) {
+    hx_set_error("slot range [%zu,%zu) outside the index (%zu rows)", first_slot, first_slot + n, ix->n);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (n == 0) return HX_OK;
+  HX_CUDA(cudaSetDevice(ix->device));
+  const uint32_t dim = ix->cfg.dimension;
+  if (out_rows)
+    HX_CUDA(cudaMemcpy2D(out_rows, (size_t)dim * sizeof(float), ix->d_vec + first_slot * (size_t)ix->ld,
+                         (size_t)ix->ld * sizeof(float), (size_t)dim * sizeof(float), n, cudaMemcpyDeviceToHost));
+  if (out_ids) memcpy(out_ids, ix->ids_sorted.data() + first_slot, n * sizeof(uint64_t));
+  return HX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph mirror
+// ------------------------------------------------------------------------------------------------
+extern "C" hx_status hx_index_load_graph(hx_index* ix, uint16_t layer, const uint64_t* node_ids,
+                                         const uint32_t* offsets, const uint64_t* neighbors, size_t n_nodes) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (n_nodes && (!node_ids || !offsets)) return HX_ERR_INVALID_PARAMETER;
+  if (layer > 63) {   // MAX_SELECTED_LAYER (mod.rs:772)
+    hx_set_error("layer %u above the maximum 63", layer);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (ix->staged.size() <= layer) ix->staged.resize((size_t)layer + 1);
+  HxLayerRows& L = ix->staged[layer];
+  L = HxLayerRows();
+  L.offsets.push_back(0);
+  for (size_t i = 0; i < n_nodes; ++i) {
+    uint32_t slot;
+    if (!hx_slot_of(ix, node_ids[i], &slot)) continue;   // a row whose owner has no vector is unreachable
+    const uint32_t b = offsets[i], e = offsets[i + 1];
+    uint32_t kept = 0;
+    uint64_t prev = 0;
+    for (uint32_t j = b; j < e; ++j) {
+      if (j > b && neighbors[j] <= prev) {
+        hx_set_error("layer %u row of node %llu is not strictly ascending", layer, (unsigned long long)node_ids[i]);
+        return HX_ERR_INVARIANT_VIOLATION;   // canonical rows are ascending & unique (values/vectors.rs:67-110)
+      }
+      prev = neighbors[j];
+      uint32_t ns;
+      if (neighbors[j] == node_ids[i]) {
+        hx_set_error("layer %u row of node %llu links to itself", layer, (unsigned long long)node_ids[i]);
+        return HX_ERR_INVARIANT_VIOLATION;
+      }
+      if (hx_slot_of(ix, neighbors[j], &ns)) {
+        L.nbr.push_back(ns);
+        kept++;
+      }
+    }
+    (void)kept;
+    L.node.push_back(slot);
+    L.offsets.push_back((uint32_t)L.nbr.size());
+    L.raw_len.push_back(e - b);
+  }
+  ix->graph_dirty = true;
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_set_entry(hx_index* ix, uint64_t entry_point, uint16_t max_layer) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  uint32_t slot;
+  if (!hx_slot_of(ix, entry_point, &slot)) {
+    hx_set_error("entry point %llu has no vector row in the device mirror", (unsigned long long)entry_point);
+    return HX_ERR_INVARIANT_VIOLATION;
+  }
+  ix->entry_id = entry_point;
+  ix->entry_slot = slot;
+  ix->max_layer = max_layer;
+  ix->populated = true;
+  return HX_OK;
+}
+
+// Turn the staged per-layer CSR rows into the fixed-stride device image.
+hx_status hx_finalize_graph(hx_index* ix) {
+  if (!ix->graph_dirty) return HX_OK;
+  HX_CUDA(cudaSetDevice(ix->device));
+  const size_t n = ix->n;
+  // free previous device graph but keep staging
+  std::vector<HxLayerRows> staged;
+  staged.swap(ix->staged);
+  const bool pop = ix->populated;
+  ix->free_graph();
+  ix->populated = pop;
+  ix->staged.swap(staged);
+  if (n == 0) {
+    ix->graph_dirty = false;
+    return HX_OK;
+  }
+  uint32_t max0 = ix->lim0, maxu = ix->cfg.m;
+  for (size_t l = 0; l < ix->staged.size(); ++l) {
+    const HxLayerRows& L = ix->staged[l];
+    for (size_t i = 0; i + 1 < L.offsets.size(); ++i) {
+      const uint32_t len = L.offsets[i + 1] - L.offsets[i];
+      if (l == 0) max0 = std::max(max0, len); else maxu = std::max(maxu, len);
+    }
+  }
+  if (max0 > 4096 || maxu > 4096) {
+    hx_set_error("neighbour rows longer than 4096 are not supported");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  ix->stride0 = round_up(max0, 32);
+  ix->stride_u = round_up(maxu, 16);
+  std::vector<uint8_t> level(n, 0);
+  std::vector<uint32_t> nbr0(n * (size_t)ix->stride0, 0);
+  std::vector<uint16_t> deg0(n, 0), raw0(n, 0);
+  if (!ix->staged.empty()) {
+    const HxLayerRows& L = ix->staged[0];
+    for (size_t i = 0; i < L.node.size(); ++i) {
+      const uint32_t s = L.node[i], b = L.offsets[i], e = L.offsets[i + 1];
+      memcpy(nbr0.data() + (size_t)s * ix->stride0, L.nbr.data() + b, (size_t)(e - b) * sizeof(uint32_t));
+      deg0[s] = (uint16_t)(e - b);
+      raw0[s] = (uint16_t)std::min<uint32_t>(L.raw_len[i], 65535);
+    }
+  }
+  for (size_t l = 1; l < ix->staged.size(); ++l)
+    for (uint32_t s : ix->staged[l].node) level[s] = std::max<uint8_t>(level[s], (uint8_t)l);
+  std::vector<uint32_t> upper_off(n, HX_ABSENT);
+  size_t rows = 0;
+  for (size_t s = 0; s < n; ++s)
+    if (level[s] > 0) {
+      upper_off[s] = (uint32_t)rows;
+      rows += level[s];
+    }
+  ix->n_upper_rows = rows;
+  std::vector<uint32_t> upper_nbr(std::max<size_t>(rows, 1) * ix->stride_u, 0);
+  std::vector<uint16_t> upper_deg(std::max<size_t>(rows, 1), 0);
+  for (size_t l = 1; l < ix->staged.size(); ++l) {
+    const HxLayerRows& L = ix->staged[l];
+    for (size_t i = 0; i < L.node.size(); ++i) {
+      const uint32_t s = L.node[i], b = L.offsets[i], e = L.offsets[i + 1];
+      const size_t r = (size_t)upper_off[s] + (l - 1);
+      memcpy(upper_nbr.data() + r * ix->stride_u, L.nbr.data() + b, (size_t)(e - b) * sizeof(uint32_t));
+      upper_deg[r] = (uint16_t)(e - b);
+    }
+  }
+  HX_CUDA(cudaMalloc((void**)&ix->d_nbr0, nbr0.size() * sizeof(uint32_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_deg0, n * sizeof(uint16_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_raw0, n * sizeof(uint16_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_upper_off, n * sizeof(uint32_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_upper_nbr, upper_nbr.size() * sizeof(uint32_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_upper_deg, upper_deg.size() * sizeof(uint16_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_level, n));
+  HX_CUDA(cudaMemcpy(ix->d_nbr0, nbr0.data(), nbr0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  HX_CUDA(cudaMemcpy(ix->d_deg0, deg0.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  HX_CUDA(cudaMemcpy(ix->d_raw0, raw0.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  HX_CUDA(cudaMemcpy(ix->d_upper_off, upper_off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  HX_CUDA(cudaMemcpy(ix->d_upper_nbr, upper_nbr.data(), upper_nbr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  HX_CUDA(cudaMemcpy(ix->d_upper_deg, upper_deg.data(), upper_deg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  HX_CUDA(cudaMemcpy(ix->d_level, level.data(), n, cudaMemcpyHostToDevice));
+  ix->staged.clear();
+  ix->graph_dirty = false;
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_build(hx_index* ix, const uint16_t* levels, uint64_t seed) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  HX_CUDA(cudaSetDevice(ix->device));
+  return hx_build_impl(ix, levels, seed);
+}
+
+extern "C" hx_status hx_index_graph_info(hx_index* ix, uint64_t* n_nodes, uint64_t* entry_point, uint16_t* max_layer,
+                                         uint32_t* layer0_stride, uint32_t* upper_stride) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  hx_status rc = hx_finalize_graph(ix);
+  if (rc) return rc;
+  if (n_nodes) *n_nodes = ix->n;
+  if (entry_point) *entry_point = ix->populated ? ix->entry_id : 0;
+  if (max_layer) *max_layer = (uint16_t)(ix->populated ? ix->max_layer : 0);
+  if (layer0_stride) *layer0_stride = ix->stride0;
+  if (upper_stride) *upper_stride = ix->stride_u;
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_download_graph(hx_index* ix, uint16_t* levels, uint32_t* deg0, uint32_t* nbr0,
+                                             uint64_t* n_upper_rows, uint32_t* upper_node, uint16_t* upper_layer,
+                                             uint32_t* upper_deg, uint32_t* upper_nbr, size_t upper_cap) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  hx_status rc = hx_finalize_graph(ix);
+  if (rc) return rc;
+  HX_CUDA(cudaSetDevice(ix->device));
+  const size_t n = ix->n;
+  if (n_upper_rows) *n_upper_rows = ix->n_upper_rows;
+  if (n == 0 || !ix->d_nbr0) return HX_OK;
+  std::vector<uint8_t> level(n);
+  HX_CUDA(cudaMemcpy(level.data(), ix->d_level, n, cudaMemcpyDeviceToHost));
+  if (levels)
+    for (size_t i = 0; i < n; ++i) levels[i] = level[i];
+  if (deg0) {
+    std::vector<uint16_t> d(n);
+    HX_CUDA(cudaMemcpy(d.data(), ix->d_deg0, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) deg0[i] = d[i];
+  }
+  if (nbr0) HX_CUDA(cudaMemcpy(nbr0, ix->d_nbr0, n * (size_t)ix->stride0 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (upper_node && upper_layer && upper_deg && upper_nbr) {
+    if (upper_cap < ix->n_upper_rows) {
+      hx_set_error("upper row capacity %zu < %zu", upper_cap, ix->n_upper_rows);
+      return HX_ERR_INVALID_PARAMETER;
+    }
+    const size_t rows = ix->n_upper_rows;
+    if (rows) {
+      std::vector<uint16_t> d(rows);
+      HX_CUDA(cudaMemcpy(d.data(), ix->d_upper_deg, rows * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+      for (size_t r = 0; r < rows; ++r) upper_deg[r] = d[r];
+      HX_CUDA(cudaMemcpy(upper_nbr, ix->d_upper_nbr, rows * (size_t)ix->stride_u * sizeof(uint32_t),
+                         cudaMemcpyDeviceToHost));
+      size_t r = 0;
+      for (size_t s = 0; s < n; ++s)
+        for (uint32_t l = 1; l <= level[s]; ++l) {
+          upper_node[r] = (uint32_t)s;
+          upper_layer[r] = (uint16_t)l;
+          ++r;
+        }
+    }
+  }
+  return HX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search parameter checks (SearchParams::new / with_ef, mod.rs:480-500)
+// ------------------------------------------------------------------------------------------------
+static hx_status check_params(const hx_index* ix, const hx_search_params* p, uint32_t* k, uint32_t* ef) {
+  if (!p) {
+    hx_set_error("null search params");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (p->k == 0) {
+    hx_set_error("result count must be non-zero");   // ResultCount::try_new
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  uint32_t e = p->ef == 0 ? std::max(p->k, 100u) : p->ef;
+  if (e < p->k) {
+    hx_set_error("search beam width must be at least %u, got %u", p->k, e);   // SearchBeamWidth::try_new
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (p->simhash_mode != HX_SIMHASH_OFF || p->pre_sampling_ratio != 1.0f) {
+    hx_set_error("only the strict-exhaustive mode (SimHashMode::Off, pre-sampling 1.0) is executed on the device; "
+                 "Adaptive/Always sampling is unpinned in the reference (SURVEY §8c)");
+    return HX_ERR_UNSUPPORTED;
+  }
+  if (p->query_dimension != 0 && p->query_dimension != ix->cfg.dimension) {
+    hx_set_error("invalid dimension: expected %u, got %u", ix->cfg.dimension, p->query_dimension);
+    return HX_ERR_INVALID_DIMENSION;
+  }
+  if (e > 4096) {
+    hx_set_error("beam width %u above the supported maximum 4096", e);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  *k = p->k;
+  *ef = e;
+  return HX_OK;
+}
+
+// Upload B host queries and produce q_hdr / q_status on the device (host-side for small B, kernel otherwise).
+static hx_status stage_queries(hx_index* ix, HxScratch* s, const float* queries, size_t B, uint32_t* launches) {
+  const uint32_t dim = ix->cfg.dimension;
+  hx_status rc;
+  if ((rc = s->d_queries.reserve(B * (size_t)dim))) return rc;
+  if ((rc = s->d_qhdr.reserve(B))) return rc;
+  if ((rc = s->d_qstatus.reserve(B))) return rc;
+  HX_CUDA(cudaMemcpyAsync(s->d_queries.p, queries, B * (size_t)dim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+  float limit = 0.f;
+  const bool has_limit = component_limit(ix->cfg.metric, dim, &limit);
+  if (B <= 8) {
+    if ((rc = s->h_qhdr.reserve(B))) return rc;
+    if ((rc = s->h_status.reserve(B))) return rc;
+    for (size_t b = 0; b < B; ++b) {
+      const uint32_t w = host_validate(queries + b * (size_t)dim, dim, ix->cfg.metric, has_limit, limit);
+      if (w != HX_ST_OK) return status_from_word(w, b, "query");
+      s->h_status.p[b] = 0;
+      s->h_qhdr.p[b] = ix->cfg.metric == HX_METRIC_COSINE ? host_cosine_norm(queries + b * (size_t)dim, dim) : 0.0f;
+    }
+    HX_CUDA(cudaMemcpyAsync(s->d_qhdr.p, s->h_qhdr.p, B * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    HX_CUDA(cudaMemcpyAsync(s->d_qstatus.p, s->h_status.p, B * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+  } else {
+    k_validate_and_header<<<(unsigned)((B + 7) / 8), 256, 0, s->stream>>>(s->d_queries.p, B, dim, dim, ix->cfg.metric,
+                                                                         limit, has_limit ? 1 : 0, s->d_qhdr.p,
+                                                                         s->d_qstatus.p);
+    HX_CUDA(cudaGetLastError());
+    (*launches)++;
+  }
+  return HX_OK;
+}
+
+static hx_status prepare_device_queries(hx_index* ix, HxScratch* s, const float* d_queries, size_t B,
+                                        cudaStream_t stream, uint32_t* launches) {
+  const uint32_t dim = ix->cfg.dimension;
+  hx_status rc;
+  if ((rc = s->d_qhdr.reserve(B))) return rc;
+  if ((rc = s->d_qstatus.reserve(B))) return rc;
+  float limit = 0.f;
+  const bool has_limit = component_limit(ix->cfg.metric, dim, &limit);
+  k_validate_and_header<<<(unsigned)((B + 7) / 8), 256, 0, stream>>>(d_queries, B, dim, dim, ix->cfg.metric, limit,
+                                                                    has_limit ? 1 : 0, s->d_qhdr.p, s->d_qstatus.p);
+  HX_CUDA(cudaGetLastError());
+  (*launches)++;
+  return HX_OK;
+}
+
+// ---- HNSW launch ---------------------------------------------------------------------------------
+static uint32_t hnsw_smem_bytes(const hx_index* ix, uint32_t ef, uint32_t fr_cap) {
+  return ix->ld * 4u + ef * 8u + HX_TIE_CAP * 8u + fr_cap * 8u;
+}
+
+static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries, size_t B, uint32_t k, uint32_t ef,
+                             uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts, uint32_t* d_qstats,
+                             cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1, bool* timed, uint32_t* launches) {
+  *timed = false;
+  hx_status rc = hx_finalize_graph(ix);
+  if (rc) return rc;
+  if (ix->n == 0 || !ix->populated || !ix->d_nbr0) {   // VectorIndexState::Empty => Ok(vec![]) (search.rs:1127-1128)
+    HX_CUDA(cudaMemsetAsync(d_out_counts, 0, B * sizeof(uint32_t), stream));
+    if (d_qstats) HX_CUDA(cudaMemsetAsync(d_qstats, 0, B * 4 * sizeof(uint32_t), stream));
+    return HX_OK;
+  }
+  const uint32_t fr_cap = round_up(std::max(ix->stride0, ix->stride_u), 32);
+  const uint32_t smem = hnsw_smem_bytes(ix, ef, fr_cap);
+  if (smem > 200 * 1024) {
+    hx_set_error("query working set %u bytes exceeds shared memory", smem);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  // persistent grid: enough CTAs to fill every SM, never more than the queries
+  int per_sm = 4;
+  uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ix->sm_count * per_sm);
+  const size_t stride = ((ix->n + 15) / 16) * 16;
+  if (s->stamp_grid < grid || s->stamp_n != ix->n || !s->d_stamps.p) {
+    const uint32_t want = (uint32_t)std::max<size_t>(grid, std::min<size_t>((size_t)ix->sm_count * per_sm, 64));
+    if ((rc = s->d_stamps.reserve((size_t)want * stride))) return rc;
+    if ((rc = s->d_epochs.reserve(want))) return rc;
+    HX_CUDA(cudaMemsetAsync(s->d_stamps.p, 0, (size_t)want * stride, stream));
+    HX_CUDA(cudaMemsetAsync(s->d_epochs.p, 0, want * sizeof(uint32_t), stream));
+    s->stamp_grid = want;
+    s->stamp_stride = stride;
+    s->stamp_n = ix->n;
+  }
+  if ((rc = s->d_err.reserve(1))) return rc;
+  HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, sizeof(uint32_t), stream));
+  HxHnswArgs a{};
+  a.queries = d_queries;
+  a.q_hdr = s->d_qhdr.p;
+  a.q_status = s->d_qstatus.p;
+  a.B = (uint32_t)B;
+  a.k = k;
+  a.ef = ef;
+  a.out_ids = d_out_ids;
+  a.out_scores = d_out_scores;
+  a.out_counts = d_out_counts;
+  a.q_stats = d_qstats;
+  a.stamps = s->d_stamps.p;
+  a.epochs = s->d_epochs.p;
+  a.stamp_stride = s->stamp_stride;
+  a.err_flags = s->d_err.p;
+  a.fr_cap = fr_cap;
+  const HxDev dev = ix->dev();
+  HX_CUDA(cudaEventRecord(e0, stream));
+  switch (ix->cfg.metric) {
+    case HX_METRIC_EUCLIDEAN:
+      if (smem > 48 * 1024)
+        HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<HXM_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_hnsw_search<HXM_EUCLIDEAN><<<grid, HX_HNSW_THREADS, smem, stream>>>(dev, a);
+      break;
+    case HX_METRIC_COSINE:
+      if (smem > 48 * 1024)
+        HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<HXM_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_hnsw_search<HXM_COSINE><<<grid, HX_HNSW_THREADS, smem, stream>>>(dev, a);
+      break;
+    default:
+      if (smem > 48 * 1024)
+        HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<HXM_MANHATTAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_hnsw_search<HXM_MANHATTAN><<<grid, HX_HNSW_THREADS, smem, stream>>>(dev, a);
+      break;
+  }
+  HX_CUDA(cudaGetLastError());
+  HX_CUDA(cudaEventRecord(e1, stream));
+  *timed = true;
+  (*launches)++;
+  return HX_OK;
+}
+
+static hx_status check_device_flags(uint32_t flags) {
+  if (flags & HXF_INVALID_SCORE) {
+    hx_set_error("vector distance kernel emitted an invalid score");   // model.rs:21-28
+    return HX_ERR_INVARIANT_VIOLATION;
+  }
+  if (flags & HXF_TIE_OVERFLOW) {
+    hx_set_error("more than %d exact score ties at the beam boundary", HX_TIE_CAP);
+    return HX_ERR_INVARIANT_VIOLATION;
+  }
+  return HX_OK;
+}
+
+extern "C" hx_status hx_search(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                               uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+  if (!ix) {
+    hx_set_error("null index handle");
+    return HX_ERR_INDEX_NOT_FOUND;
+  }
+  uint32_t k, ef;
+  hx_status rc = check_params(ix, p, &k, &ef);
+  if (rc) return rc;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return HX_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts) {
+    hx_set_error("hx_search: null pointer");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  HX_CUDA(cudaSetDevice(ix->device));
+  HxScratch* s = nullptr;
+  if ((rc = hx_acquire_scratch(ix, &s))) return rc;
+  ScratchGuard guard{ix, s};
+  uint32_t launches = 0;
+  if ((rc = stage_queries(ix, s, queries, B, &launches))) return rc;
+  if ((rc = s->d_out_ids.reserve(B * (size_t)k))) return rc;
+  if ((rc = s->d_out_scores.reserve(B * (size_t)k))) return rc;
+  if ((rc = s->d_out_counts.reserve(B))) return rc;
+  const bool want_stats = p->collect_stats != 0 && stats != nullptr;
+  if (want_stats && (rc = s->d_qstats.reserve(B * 4))) return rc;
+  bool timed = false;
+  if ((rc = launch_hnsw(ix, s, s->d_queries.p, B, k, ef, s->d_out_ids.p, s->d_out_scores.p, s->d_out_counts.p,
+                        want_stats ? s->d_qstats.p : nullptr, s->stream, s->ev0, s->ev1, &timed, &launches)))
+    return rc;
+  if ((rc = s->h_status.reserve(B))) return rc;
+  if ((rc = s->h_err.reserve(1))) return rc;
+  s->h_err.p[0] = 0;
+  HX_CUDA(cudaMemcpyAsync(out_ids, s->d_out_ids.p, B * (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_scores, s->d_out_scores.p, B * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_counts, s->d_out_counts.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(s->h_status.p, s->d_qstatus.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (s->d_err.p) HX_CUDA(cudaMemcpyAsync(s->h_err.p, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (want_stats) {
+    if ((rc = s->h_qstats.reserve(B * 4))) return rc;
+    HX_CUDA(cudaMemcpyAsync(s->h_qstats.p, s->d_qstats.p, B * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  }
+  HX_CUDA(cudaStreamSynchronize(s->stream));
+  for (size_t b = 0; b < B; ++b)
+    if (s->h_status.p[b] != HX_ST_OK) return status_from_word(s->h_status.p[b], b, "query");
+  if ((rc = check_device_flags(s->h_err.p[0]))) return rc;
+  float ms = 0.f;
+  if (timed && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
+    ix->last_kernel_ms = ms;
+    ix->last_kernel_launches = 1;
+  }
+  if (stats) {
+    stats->kernel_launches = launches;
+    if (want_stats) {
+      for (size_t b = 0; b < B; ++b) {
+        stats->expansion_steps += s->h_qstats.p[b * 4 + 0];
+        stats->neighbors_examined += s->h_qstats.p[b * 4 + 1];
+        stats->distance_computations += s->h_qstats.p[b * 4 + 2];
+        stats->upper_layer_steps += s->h_qstats.p[b * 4 + 3];
+        if (s->h_qstats.p[b * 4 + 2]) stats->vectors_loaded += s->h_qstats.p[b * 4 + 2] - 1;
+      }
+      stats->algorithmic_bytes = stats->expansion_steps * (5ull + 8ull * ix->lim0) +
+                                 stats->distance_computations * (4ull + 4ull * ix->cfg.dimension);
+    }
+  }
+  return HX_OK;
+}
+
+extern "C" hx_status hx_search_device(hx_index* ix, const float* d_queries, size_t B, const hx_search_params* p,
+                                      uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts,
+                                      void* cuda_stream, hx_stats* stats) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  uint32_t k, ef;
+  hx_status rc = check_params(ix, p, &k, &ef);
+  if (rc) return rc;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return HX_OK;
+  if (!d_queries || !d_out_ids || !d_out_scores || !d_out_counts) return HX_ERR_INVALID_PARAMETER;
+  HX_CUDA(cudaSetDevice(ix->device));
+  HxScratch* s = nullptr;
+  if ((rc = dev_scratch(ix, &s))) return rc;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  uint32_t launches = 0;
+  if ((rc = prepare_device_queries(ix, s, d_queries, B, stream, &launches))) return rc;
+  const bool want_stats = p->collect_stats != 0 && stats != nullptr;
+  if (want_stats && (rc = s->d_qstats.reserve(B * 4))) return rc;
+  cudaEvent_t e0, e1;
+  if ((rc = s->ring_next(&e0, &e1))) return rc;
+  bool timed = false;
+  if ((rc = launch_hnsw(ix, s, d_queries, B, k, ef, d_out_ids, d_out_scores, d_out_counts,
+                        want_stats ? s->d_qstats.p : nullptr, stream, e0, e1, &timed, &launches)))
+    return rc;
+  if (!timed && s->ring_pending) s->ring_pending--;
+  if (want_stats) {   // stats need a sync; the throughput path leaves collect_stats = 0
+    if ((rc = s->h_qstats.reserve(B * 4))) return rc;
+    HX_CUDA(cudaMemcpyAsync(s->h_qstats.p, s->d_qstats.p, B * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    HX_CUDA(cudaStreamSynchronize(stream));
+    for (size_t b = 0; b < B; ++b) {
+      stats->expansion_steps += s->h_qstats.p[b * 4 + 0];
+      stats->neighbors_examined += s->h_qstats.p[b * 4 + 1];
+      stats->distance_computations += s->h_qstats.p[b * 4 + 2];
+      stats->upper_layer_steps += s->h_qstats.p[b * 4 + 3];
+      if (s->h_qstats.p[b * 4 + 2]) stats->vectors_loaded += s->h_qstats.p[b * 4 + 2] - 1;
+    }
+    stats->algorithmic_bytes = stats->expansion_steps * (5ull + 8ull * ix->lim0) +
+                               stats->distance_computations * (4ull + 4ull * ix->cfg.dimension);
+  }
+  if (stats) stats->kernel_launches = launches;
+  return HX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// restricted search
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t hx_restricted_plan(uint64_t n_candidates, uint32_t dimension) {
+  // EXACT_CARDINALITY_THRESHOLD = 256, EXACT_VECTOR_BYTES_THRESHOLD = 4 MiB (restricted.rs:40-42,433-440)
+  const uint64_t bytes = n_candidates * (uint64_t)dimension * 4ull;
+  return (n_candidates <= 256 && bytes <= 4ull * 1024 * 1024) ? 0 : 1;
+}
+
+static uint32_t pick_chunk(uint64_t total_cands, int sm_count) {
+  // aim for >= 4 CTAs per SM over the whole launch; one CTA pass covers 32 rows
+  uint64_t c = total_cands / ((uint64_t)sm_count * 4) + 1;
+  c = (c + 31) / 32 * 32;
+  if (c < 32) c = 32;
+  if (c > 2048) c = 2048;
+  return (uint32_t)c;
+}
+
+// d_cand_slots / d_cand_offsets on the device; host knows max candidate count per query and the total.
+static hx_status launch_scan_select(hx_index* ix, HxScratch* s, const float* d_queries, size_t B, uint32_t k,
+                                    const uint32_t* d_slots, const uint64_t* d_offsets, bool shared, uint64_t n_shared,
+                                    uint64_t max_cands, uint64_t total_keys, uint64_t* d_out_ids, float* d_out_scores,
+                                    uint32_t* d_out_counts, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1,
+                                    uint32_t* launches) {
+  hx_status rc;
+  if ((rc = s->d_keys.reserve(total_keys))) return rc;
+  if ((rc = s->d_err.reserve(1))) return rc;
+  HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, sizeof(uint32_t), stream));
+  const HxDev dev = ix->dev();
+  HxScanArgs a{};
+  a.queries = d_queries;
+  a.q_hdr = s->d_qhdr.p;
+  a.q_status = s->d_qstatus.p;
+  a.B = (uint32_t)B;
+  a.cand_slots = d_slots;
+  a.cand_offsets = d_offsets;
+  a.keys = s->d_keys.p;
+  a.shared_set = shared ? 1u : 0u;
+  a.n_shared = n_shared;
+  a.chunk = pick_chunk(total_keys, ix->sm_count);
+  a.err_flags = s->d_err.p;
+  dim3 grid((unsigned)((max_cands + a.chunk - 1) / a.chunk), (unsigned)std::min<size_t>(B, 65535));
+  const uint32_t smem = ix->ld * 4u;
+  HX_CUDA(cudaEventRecord(e0, stream));
+  switch (ix->cfg.metric) {
+    case HX_METRIC_EUCLIDEAN:
+      if (smem > 48 * 1024)
+        HX_CUDA(cudaFuncSetAttribute(k_scan<HXM_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_scan<HXM_EUCLIDEAN><<<grid, HX_SCAN_THREADS, smem, stream>>>(dev, a);
+      break;
+    case HX_METRIC_COSINE:
+      if (smem > 48 * 1024)
+        HX_CUDA(cudaFuncSetAttribute(k_scan<HXM_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_scan<HXM_COSINE><<<grid, HX_SCAN_THREADS, smem, stream>>>(dev, a);
+      break;
+    default:
+      if (smem > 48 * 1024)
+        HX_CUDA(cudaFuncSetAttribute(k_scan<HXM_MANHATTAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_scan<HXM_MANHATTAN><<<grid, HX_SCAN_THREADS, smem, stream>>>(dev, a);
+      break;
+  }
+  HX_CUDA(cudaGetLastError());
+  HX_CUDA(cudaEventRecord(e1, stream));
+  (*launches)++;
+  HxSelectArgs sa{};
+  sa.keys = s->d_keys.p;
+  sa.cand_slots = d_slots;
+  sa.cand_offsets = d_offsets;
+  sa.q_status = s->d_qstatus.p;
+  sa.B = (uint32_t)B;
+  sa.k = k;
+  sa.shared_set = shared ? 1u : 0u;
+  sa.n_shared = n_shared;
+  sa.out_ids = d_out_ids;
+  sa.out_scores = d_out_scores;
+  sa.out_counts = d_out_counts;
+  k_select<<<(unsigned)std::min<size_t>(B, 65535), HX_SEL_THREADS, 0, stream>>>(dev, sa);
+  HX_CUDA(cudaGetLastError());
+  (*launches)++;
+  return HX_OK;
+}
+
+static hx_status restricted_host(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                 const uint64_t* cand_ids, const uint64_t* cand_offsets, size_t n_shared, bool shared,
+                                 uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+  if (!ix) {
+    hx_set_error("null index handle");
+    return HX_ERR_INDEX_NOT_FOUND;
+  }
+  uint32_t k, ef;
+  hx_status rc = check_params(ix, p, &k, &ef);
+  if (rc) return rc;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return HX_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts) return HX_ERR_INVALID_PARAMETER;
+  // candidate-set admission (restricted.rs:356-371, 200-213): |C| <= 1e6; k' = min(k,|C|) <= 800
+  uint64_t total = 0, max_c = 0;
+  bool any_nonempty = false;
+  for (size_t b = 0; b < B; ++b) {
+    const uint64_t c = shared ? n_shared : cand_offsets[b + 1] - cand_offsets[b];
+    if (c > 1000000ull) {
+      hx_set_error("restricted vector search accepts at most 1000000 unique candidates");
+      return HX_ERR_QUERY;
+    }
+    if (c > 0) {
+      any_nonempty = true;
+      if (std::min<uint64_t>(k, c) > 800) {
+        hx_set_error("restricted vector search result count must be at most 800, got %llu",
+                     (unsigned long long)std::min<uint64_t>(k, c));
+        return HX_ERR_QUERY;
+      }
+    }
+    max_c = std::max(max_c, c);
+    total += shared ? 0 : c;
+    if (shared) break;
+  }
+  if (shared) total = n_shared;
+  if (!any_nonempty || total == 0) {   // RestrictedVectorCandidates::Empty => Ok(vec![]) before any I/O (:539-541)
+    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
+    return HX_OK;
+  }
+  if ((shared && !cand_ids) || (!shared && (!cand_ids || !cand_offsets))) return HX_ERR_INVALID_PARAMETER;
+  HX_CUDA(cudaSetDevice(ix->device));
+  HxScratch* s = nullptr;
+  if ((rc = hx_acquire_scratch(ix, &s))) return rc;
+  ScratchGuard guard{ix, s};
+  uint32_t launches = 0;
+  if ((rc = stage_queries(ix, s, queries, B, &launches))) return rc;
+  if (ix->n == 0 || !ix->populated) {   // empty index => Ok(vec![]) after query validation (:563-566)
+    HX_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
+    return HX_OK;
+  }
+  if ((rc = s->d_cand_ids.reserve(total))) return rc;
+  if ((rc = s->d_cand_slots.reserve(total))) return rc;
+  if ((rc = s->d_cand_offsets.reserve(B + 1))) return rc;
+  HX_CUDA(cudaMemcpyAsync(s->d_cand_ids.p, cand_ids + (shared ? 0 : cand_offsets[0]), total * sizeof(uint64_t),
+                          cudaMemcpyHostToDevice, s->stream));
+  if (!shared) {
+    if ((rc = s->h_cand_offsets.reserve(B + 1))) return rc;
+    for (size_t b = 0; b <= B; ++b) s->h_cand_offsets.p[b] = cand_offsets[b] - cand_offsets[0];
+    HX_CUDA(cudaMemcpyAsync(s->d_cand_offsets.p, s->h_cand_offsets.p, (B + 1) * sizeof(uint64_t),
+                            cudaMemcpyHostToDevice, s->stream));
+  }
+  k_map_candidates<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
+      ix->d_ids, (uint32_t)ix->n, s->d_cand_ids.p, total, s->d_cand_slots.p, ix->contiguous ? 1 : 0, ix->first_id);
+  HX_CUDA(cudaGetLastError());
+  launches++;
+  if ((rc = s->d_out_ids.reserve(B * (size_t)k))) return rc;
+  if ((rc = s->d_out_scores.reserve(B * (size_t)k))) return rc;
+  if ((rc = s->d_out_counts.reserve(B))) return rc;
+  const uint64_t total_keys = shared ? (uint64_t)B * n_shared : total;
+  if ((rc = launch_scan_select(ix, s, s->d_queries.p, B, k, s->d_cand_slots.p, s->d_cand_offsets.p, shared, n_shared,
+                               max_c, total_keys, s->d_out_ids.p, s->d_out_scores.p, s->d_out_counts.p, s->stream,
+                               s->ev0, s->ev1, &launches)))
+    return rc;
+  if ((rc = s->h_status.reserve(B))) return rc;
+  if ((rc = s->h_err.reserve(1))) return rc;
+  HX_CUDA(cudaMemcpyAsync(out_ids, s->d_out_ids.p, B * (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_scores, s->d_out_scores.p, B * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_counts, s->d_out_counts.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(s->h_status.p, s->d_qstatus.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(s->h_err.p, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaStreamSynchronize(s->stream));
+  for (size_t b = 0; b < B; ++b)
+    if (s->h_status.p[b] != HX_ST_OK) return status_from_word(s->h_status.p[b], b, "query");
+  if ((rc = check_device_flags(s->h_err.p[0]))) return rc;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
+    ix->last_kernel_ms = ms;
+    ix->last_kernel_launches = 1;
+  }
+  if (stats) {
+    stats->kernel_launches = launches;
+    stats->distance_computations = total_keys;
+    stats->vectors_loaded = total_keys;
+    stats->algorithmic_bytes = total_keys * (4ull * ix->cfg.dimension + (ix->cfg.metric == HX_METRIC_COSINE ? 4 : 0));
+  }
+  return HX_OK;
+}
+
+extern "C" hx_status hx_search_restricted(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                          const uint64_t* cand_ids, size_t n_cand, uint64_t* out_ids,
+                                          float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+  return restricted_host(ix, queries, B, p, cand_ids, nullptr, n_cand, true, out_ids, out_scores, out_counts, stats);
+}
+
+extern "C" hx_status hx_search_restricted_multi(hx_index* ix, const float* queries, size_t B,
+                                                const hx_search_params* p, const uint64_t* cand_ids,
+                                                const uint64_t* cand_offsets, uint64_t* out_ids, float* out_scores,
+                                                uint32_t* out_counts, hx_stats* stats) {
+  if (B && !cand_offsets) return HX_ERR_INVALID_PARAMETER;
+  return restricted_host(ix, queries, B, p, cand_ids, cand_offsets, 0, false, out_ids, out_scores, out_counts, stats);
+}
+
+extern "C" hx_status hx_map_candidates_device(hx_index* ix, const uint64_t* d_cand_ids, uint64_t n,
+                                              uint32_t* d_out_slots, uint64_t* d_out_count, void* cuda_stream) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (n == 0) return HX_OK;
+  HX_CUDA(cudaSetDevice(ix->device));
+  k_map_candidates<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+      ix->d_ids, (uint32_t)ix->n, d_cand_ids, n, d_out_slots, ix->contiguous ? 1 : 0, ix->first_id);
+  HX_CUDA(cudaGetLastError());
+  (void)d_out_count;
+  return HX_OK;
+}
+
+extern "C" hx_status hx_search_restricted_device(hx_index* ix, const float* d_queries, size_t B,
+                                                 const hx_search_params* p, const uint32_t* d_cand_slots,
+                                                 const uint64_t* d_cand_offsets, uint64_t total_cands,
+                                                 uint64_t max_cands_per_query, uint64_t* d_out_ids,
+                                                 float* d_out_scores, uint32_t* d_out_counts, void* cuda_stream) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  uint32_t k, ef;
+  hx_status rc = check_params(ix, p, &k, &ef);
+  if (rc) return rc;
+  if (B == 0) return HX_OK;
+  if (!d_queries || !d_out_ids || !d_out_scores || !d_out_counts) return HX_ERR_INVALID_PARAMETER;
+  const bool shared = d_cand_offsets == nullptr;
+  const uint64_t max_c = shared ? total_cands : (max_cands_per_query ? max_cands_per_query : total_cands);
+  if (max_c > 1000000ull) {
+    hx_set_error("restricted vector search accepts at most 1000000 unique candidates");
+    return HX_ERR_QUERY;
+  }
+  if (std::min<uint64_t>(k, max_c) > 800) {
+    hx_set_error("restricted vector search result count must be at most 800");
+    return HX_ERR_QUERY;
+  }
+  HX_CUDA(cudaSetDevice(ix->device));
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  if (total_cands == 0 || ix->n == 0 || !ix->populated) {
+    HX_CUDA(cudaMemsetAsync(d_out_counts, 0, B * sizeof(uint32_t), stream));
+    return HX_OK;
+  }
+  if (!d_cand_slots) return HX_ERR_INVALID_PARAMETER;
+  HxScratch* s = nullptr;
+  if ((rc = dev_scratch(ix, &s))) return rc;
+  uint32_t launches = 0;
+  if ((rc = prepare_device_queries(ix, s, d_queries, B, stream, &launches))) return rc;
+  const uint64_t total_keys = shared ? (uint64_t)B * total_cands : total_cands;
+  cudaEvent_t e0, e1;
+  if ((rc = s->ring_next(&e0, &e1))) return rc;
+  return launch_scan_select(ix, s, d_queries, B, k, d_cand_slots, d_cand_offsets, shared, total_cands, max_c,
+                            total_keys, d_out_ids, d_out_scores, d_out_counts, stream, e0, e1, &launches);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded merge, dense path, timing
+// ------------------------------------------------------------------------------------------------
+extern "C" hx_status hx_merge_topk_device(int32_t device, const uint64_t* d_all_ids, const float* d_all_scores,
+                                          const uint32_t* d_all_counts, uint32_t n_shards, size_t B, uint32_t k,
+                                          uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts,
+                                          void* cuda_stream) {
+  if (n_shards == 0 || n_shards > 128 || k == 0) {
+    hx_set_error("hx_merge_topk_device: n_shards must be in 1..128 and k > 0");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (B == 0) return HX_OK;
+  HX_CUDA(cudaSetDevice(device));
+  k_merge_topk<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)cuda_stream>>>(
+      d_all_ids, d_all_scores, d_all_counts, n_shards, B, k, d_out_ids, d_out_scores, d_out_counts);
+  HX_CUDA(cudaGetLastError());
+  return HX_OK;
+}
+
+extern "C" hx_status hx_search_dense(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                     uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  HX_CUDA(cudaSetDevice(ix->device));
+  return hx_dense_impl(ix, queries, B, p, out_ids, out_scores, out_counts, stats);
+}
+
+extern "C" hx_status hx_last_kernel_ms(hx_index* ix, float* ms, uint32_t* launches) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  HX_CUDA(cudaSetDevice(ix->device));
+  HxScratch* s = ix->dev_scratch;
+  if (s && s->ring_pending) {
+    // device-path launches since the previous call: sum their CUDA-event durations (synchronises)
+    const size_t cap = s->ring0.size();
+    float total = 0.f;
+    uint32_t cnt = 0;
+    size_t idx = (s->ring0.size() < 512) ? 0 : s->ring_pos;   // oldest pending entry
+    if (s->ring0.size() < 512) idx = s->ring0.size() - s->ring_pending;
+    else idx = (s->ring_pos + cap - s->ring_pending) % cap;
+    for (size_t i = 0; i < s->ring_pending; ++i) {
+      const size_t j = (idx + i) % cap;
+      float t = 0.f;
+      if (cudaEventSynchronize(s->ring1[j]) == cudaSuccess &&
+          cudaEventElapsedTime(&t, s->ring0[j], s->ring1[j]) == cudaSuccess) {
+        total += t;
+        cnt++;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    s->ring_pending = 0;
+    ix->last_kernel_ms = total;
+    ix->last_kernel_launches = cnt;
+  }
+  if (ms) *ms = ix->last_kernel_ms;
+  if (launches) *launches = ix->last_kernel_launches;
+  return HX_OK;
+}

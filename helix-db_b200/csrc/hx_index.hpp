@@ -1,0 +1,163 @@
+// hx_index.hpp — host-side state of one device-resident index shard (opaque `hx_index` of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/helix_b200.h"
+#include "hx_common.cuh"
+
+// thread-local error text (hx_last_error)
+void hx_set_error(const char* fmt, ...);
+void hx_set_error_index(uint32_t idx);
+
+#define HX_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      hx_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);    \
+      return _e == cudaErrorMemoryAllocation ? HX_ERR_OUT_OF_MEMORY : HX_ERR_CUDA;                 \
+    }                                                                                              \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;   // elements
+  hx_status reserve(size_t n) {
+    if (n <= cap) return HX_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess) {
+      hx_set_error("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+      return HX_ERR_OUT_OF_MEMORY;
+    }
+    cap = want;
+    return HX_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  hx_status reserve(size_t n) {
+    if (n <= cap) return HX_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess) {
+      hx_set_error("cudaMallocHost(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+      return HX_ERR_OUT_OF_MEMORY;
+    }
+    cap = want;
+    return HX_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// One scratch set per in-flight host call (the handle is Send+Sync like the reference's index:
+// concurrent searches each take a private stream + buffers; SURVEY §8b "Threading").
+struct HxScratch {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf<float> d_queries, d_qhdr, d_out_scores;
+  DevBuf<uint32_t> d_qstatus, d_out_counts, d_qstats, d_err, d_epochs, d_cand_slots;
+  DevBuf<uint64_t> d_out_ids, d_cand_ids, d_cand_offsets, d_keys;
+  DevBuf<uint8_t> d_stamps;
+  size_t stamp_stride = 0;
+  uint32_t stamp_grid = 0;
+  size_t stamp_n = 0;
+  PinBuf<uint64_t> h_ids, h_cand_offsets;
+  PinBuf<float> h_scores, h_queries, h_qhdr;
+  PinBuf<uint32_t> h_counts, h_qstats, h_status, h_err;
+  bool busy = false;
+  // ring of event pairs for the device-buffer path (timed without host synchronisation)
+  std::vector<cudaEvent_t> ring0, ring1;
+  size_t ring_pos = 0, ring_pending = 0;
+  hx_status ring_next(cudaEvent_t* e0, cudaEvent_t* e1);
+  void destroy();
+};
+
+struct HxLayerRows {   // host staging of one mirrored HNSW layer (slot space)
+  std::vector<uint32_t> node;      // slot owning the row
+  std::vector<uint32_t> offsets;   // CSR into nbr
+  std::vector<uint32_t> nbr;       // neighbour slots (ascending); neighbours without a vector removed
+  std::vector<uint32_t> raw_len;   // row length as stored by the reference (for neighbors_examined)
+};
+
+struct hx_index {
+  hx_index_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  uint32_t lim0 = 32;   // MutationDegreeLimits.layer0 = max(m0, 2m)  (mutation.rs:179-199)
+  // vectors
+  size_t n = 0;
+  uint32_t ld = 0;
+  std::vector<uint64_t> ids_sorted;   // host copy: slot -> id
+  bool contiguous = false;
+  uint64_t first_id = 0;
+  float* d_vec = nullptr;
+  float* d_hdr = nullptr;
+  uint64_t* d_ids = nullptr;
+  // graph (device)
+  uint32_t* d_nbr0 = nullptr;
+  uint16_t* d_deg0 = nullptr;
+  uint16_t* d_raw0 = nullptr;
+  uint32_t* d_upper_off = nullptr;
+  uint32_t* d_upper_nbr = nullptr;
+  uint16_t* d_upper_deg = nullptr;
+  uint8_t* d_level = nullptr;
+  uint32_t stride0 = 0, stride_u = 0;
+  size_t n_upper_rows = 0;
+  // graph (host staging until finalize)
+  std::vector<HxLayerRows> staged;   // index = layer
+  bool graph_dirty = false;
+  bool populated = false;
+  uint64_t entry_id = 0;
+  uint32_t entry_slot = 0;
+  int max_layer = 0;
+  // bf16 copy for the dense path
+  void* d_vec_bf16 = nullptr;
+  float* d_sqnorm = nullptr;
+  // scratch pool
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<HxScratch*> pool;
+  HxScratch* dev_scratch = nullptr;   // device-buffer calls: stream-ordered by the caller, never pooled
+  // last dominant-kernel timing
+  float last_kernel_ms = 0.f;
+  uint32_t last_kernel_launches = 0;
+
+  HxDev dev() const;
+  void free_vectors();
+  void free_graph();
+};
+
+hx_status hx_acquire_scratch(hx_index* ix, HxScratch** out);
+void hx_release_scratch(hx_index* ix, HxScratch* s);
+hx_status hx_finalize_graph(hx_index* ix);
+bool hx_slot_of(const hx_index* ix, uint64_t id, uint32_t* slot);
+
+// implemented in k_build.cu / k_dense.cu
+hx_status hx_build_impl(hx_index* ix, const uint16_t* levels, uint64_t seed);
+hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_search_params* p, uint64_t* out_ids,
+                        float* out_scores, uint32_t* out_counts, hx_stats* stats);

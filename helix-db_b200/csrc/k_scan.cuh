@@ -1,0 +1,189 @@
+// k_scan.cuh — prefiltered brute-force scan + top-k selection.
+//
+// Restates VectorIndex::restricted_exact_scan (search/vector/restricted.rs:753-835) with
+// restricted_score_keys (:661-704): every present candidate is scored with D::distance and the k
+// smallest by (score, id) are returned sorted.  The reference takes this branch only for |C| <= 256
+// (restricted.rs:40-42,426-453) and otherwise walks the graph approximately; on the device the exact
+// scan is HBM-bound and cheap, so it answers every |C| <= 1e6 exactly.
+//
+// k_scan: grid (candidate chunks, queries).  One octet per candidate row (bit-exact octet kernel, rows
+// read with coalesced 128-bit loads, each row exactly once per query); emits one 64-bit key
+// score_bits<<32 | rank per candidate (rank = position in the ascending candidate list, so key order is
+// the reference's (score,id) order).  Algorithmic bytes per candidate: 4*dim (+4 header for cosine).
+// k_select: one CTA per query keeps the k smallest keys (threshold filter + bitonic merge in smem).
+#pragma once
+#include "hx_common.cuh"
+
+#define HX_SCAN_THREADS 256
+#define HX_SEL_THREADS 512
+#define HX_SEL_HALF 1024            // max k' (restricted k <= 800, restricted.rs:55)
+
+struct HxScanArgs {
+  const float* queries;          // [B][dim]
+  const float* q_hdr;            // [B]
+  const uint32_t* q_status;      // [B]
+  uint32_t B;
+  const uint32_t* cand_slots;    // candidate slots (HX_ABSENT = id without a vector row: skipped)
+  const uint64_t* cand_offsets;  // [B+1] (ignored when shared_set)
+  uint64_t* keys;                // one key per (query, candidate)
+  uint32_t shared_set;           // all queries scan cand_slots[0 .. n_shared)
+  uint64_t n_shared;
+  uint32_t chunk;                // candidates per CTA (multiple of 32)
+  uint32_t* err_flags;
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan(HxDev ix, HxScanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* sq = reinterpret_cast<float*>(smem);
+  const uint32_t tid = threadIdx.x, t = tid & 7u, oct = tid >> 3;
+  for (uint32_t q = blockIdx.y; q < a.B; q += gridDim.y) {
+    const uint64_t base = a.shared_set ? 0ull : a.cand_offsets[q];
+    const uint64_t n = a.shared_set ? a.n_shared : (a.cand_offsets[q + 1] - base);
+    const uint64_t start = (uint64_t)blockIdx.x * a.chunk;
+    if (start >= n || a.q_status[q] != 0u) continue;   // uniform per CTA
+    const uint64_t end = (start + a.chunk < n) ? start + a.chunk : n;
+    const float q_hdr = a.q_hdr[q];
+    for (uint32_t i = tid; i < ix.ld; i += HX_SCAN_THREADS)
+      sq[i] = i < ix.dim ? a.queries[(size_t)q * ix.dim + i] : 0.0f;
+    __syncthreads();
+    uint64_t* keys_out = a.keys + (a.shared_set ? (uint64_t)q * a.n_shared : base);
+    const uint32_t* slots = a.cand_slots + base;
+    if (METRIC == HXM_MANHATTAN) {
+      for (uint64_t r = start + tid; r < end; r += HX_SCAN_THREADS) {
+        const uint32_t slot = slots[r];
+        uint64_t key = HX_KEY_MAX;
+        if (slot != HX_ABSENT) {
+          float s = hx_manhattan_seq(ix.vec + (size_t)slot * ix.ld, sq, ix.dim);
+          if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+          key = hx_make_key(s, (uint32_t)r);
+        }
+        keys_out[r] = key;
+      }
+    } else {
+      for (uint64_t r = start + oct; r < end; r += HX_SCAN_THREADS / 8) {
+        const uint32_t slot = slots[r];
+        uint64_t key = HX_KEY_MAX;
+        if (slot != HX_ABSENT) {
+          float s = hx_octet_score<METRIC>(ix, sq, q_hdr, slot, t);
+          if (t == 0) {
+            if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+            key = hx_make_key(s, (uint32_t)r);
+          }
+        }
+        if (t == 0) keys_out[r] = key;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- top-k selection -----------------------------------------------------------------------------------
+struct HxSelectArgs {
+  const uint64_t* keys;
+  const uint32_t* cand_slots;
+  const uint64_t* cand_offsets;
+  const uint32_t* q_status;
+  uint32_t B, k;                 // k as requested; clamped to |C_q| per query (restricted.rs:200-213)
+  uint32_t shared_set;
+  uint64_t n_shared;
+  uint64_t* out_ids;             // [B][k]
+  float* out_scores;
+  uint32_t* out_counts;
+};
+
+// bitonic sort of 2*HX_SEL_HALF keys in shared memory, ascending
+__device__ __forceinline__ void hx_bitonic_sort_2048(uint64_t* s, uint32_t tid) {
+  const uint32_t N = 2 * HX_SEL_HALF;
+  for (uint32_t size = 2; size <= N; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (uint32_t p = tid; p < N / 2; p += HX_SEL_THREADS) {
+        const uint32_t i = 2 * p - (p & (stride - 1));   // index of the lower element of the pair
+        const uint32_t j = i + stride;
+        const bool up = ((i & size) == 0);
+        const uint64_t x = s[i], y = s[j];
+        if ((x > y) == up) { s[i] = y; s[j] = x; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSelectArgs a) {
+  __shared__ uint64_t buf[2 * HX_SEL_HALF];   // [0,1024): best so far (sorted), [1024,2048): incoming survivors
+  __shared__ uint32_t s_cnt;
+  __shared__ uint64_t s_thr;
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t q = blockIdx.x; q < a.B; q += gridDim.x) {
+    const uint64_t base = a.shared_set ? 0ull : a.cand_offsets[q];
+    const uint64_t n = a.shared_set ? a.n_shared : (a.cand_offsets[q + 1] - base);
+    if (a.q_status[q] != 0u || n == 0) {
+      if (tid == 0) a.out_counts[q] = 0;
+      continue;
+    }
+    const uint64_t* keys = a.keys + (a.shared_set ? (uint64_t)q * a.n_shared : base);
+    const uint32_t kk = (uint64_t)a.k < n ? a.k : (uint32_t)n;   // k' = min(k, |C|)
+    for (uint32_t i = tid; i < 2 * HX_SEL_HALF; i += HX_SEL_THREADS) buf[i] = HX_KEY_MAX;
+    if (tid == 0) { s_cnt = 0; s_thr = HX_KEY_MAX; }
+    __syncthreads();
+    for (uint64_t b0 = 0; b0 < n; b0 += HX_SEL_THREADS) {
+      const uint64_t r = b0 + tid;
+      if (r < n) {
+        const uint64_t key = keys[r];
+        if (key < s_thr) {
+          const uint32_t p = atomicAdd(&s_cnt, 1u);
+          buf[HX_SEL_HALF + p] = key;            // p < HX_SEL_HALF guaranteed by the flush rule below
+        }
+      }
+      __syncthreads();
+      if (s_cnt + HX_SEL_THREADS > HX_SEL_HALF) {   // next step could overflow: merge now (uniform)
+        hx_bitonic_sort_2048(buf, tid);
+        for (uint32_t i = tid; i < HX_SEL_HALF; i += HX_SEL_THREADS) buf[HX_SEL_HALF + i] = HX_KEY_MAX;
+        if (tid == 0) { s_cnt = 0; s_thr = buf[kk - 1]; }   // HX_KEY_MAX until kk keys are known
+        __syncthreads();
+      }
+    }
+    hx_bitonic_sort_2048(buf, tid);
+    // count valid (absent candidates carry HX_KEY_MAX and are never results)
+    const uint32_t* slots = a.cand_slots + base;
+    uint32_t cnt = 0;
+    for (uint32_t i = tid; i < kk; i += HX_SEL_THREADS) {
+      const uint64_t key = buf[i];
+      if (key != HX_KEY_MAX) {
+        const uint32_t rank = (uint32_t)(key & 0xffffffffu);
+        a.out_ids[(size_t)q * a.k + i] = ix.ids[slots[rank]];
+        a.out_scores[(size_t)q * a.k + i] = hx_key_score(key);
+        cnt++;
+      }
+    }
+    // block reduce of cnt
+    __shared__ uint32_t s_total;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&s_total, cnt);
+    __syncthreads();
+    if (tid == 0) a.out_counts[q] = s_total;
+    __syncthreads();
+  }
+}
+
+// ---- candidate id -> slot mapping (restricted.rs:615-659: ids without a vector row are skipped) ----------
+__global__ void k_map_candidates(const uint64_t* __restrict__ ids_sorted, uint32_t n, const uint64_t* __restrict__ cand,
+                                 uint64_t n_cand, uint32_t* __restrict__ out_slots, int contiguous, uint64_t first_id) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand) return;
+  const uint64_t id = cand[i];
+  uint32_t slot = HX_ABSENT;
+  if (contiguous) {
+    if (id >= first_id && id - first_id < (uint64_t)n) slot = (uint32_t)(id - first_id);
+  } else {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (ids_sorted[mid] < id) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && ids_sorted[lo] == id) slot = lo;
+  }
+  out_slots[i] = slot;
+}

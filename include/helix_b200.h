@@ -96,7 +96,9 @@ typedef struct {
   int32_t  simhash_mode;       /* hx_simhash_mode; only HX_SIMHASH_OFF is executed      */
   float    pre_sampling_ratio; /* must be 1.0 (strict exhaustive)                       */
   uint32_t collect_stats;      /* fill hx_stats (per-call sums)                         */
-  uint32_t reserved;
+  uint32_t query_dimension;    /* length of each query as the caller holds it; 0 = the
+                                  index dimension.  A mismatch is InvalidDimension and is
+                                  reported before any other check (domain.rs:117-122)   */
 } hx_search_params;
 
 /* Counter semantics mirror SearchStats (search/vector/mod.rs:668-679):
@@ -206,7 +208,8 @@ hx_status hx_search_device(hx_index* idx, const float* d_queries, size_t B,
 /* Candidates as device slot numbers (ascending), per query CSR. */
 hx_status hx_search_restricted_device(hx_index* idx, const float* d_queries, size_t B,
                                       const hx_search_params* p, const uint32_t* d_cand_slots,
-                                      const uint64_t* d_cand_offsets, uint64_t total_cands,
+                                      const uint64_t* d_cand_offsets /* NULL: one set shared by all B */,
+                                      uint64_t total_cands, uint64_t max_cands_per_query /* 0: unknown */,
                                       uint64_t* d_out_ids, float* d_out_scores,
                                       uint32_t* d_out_counts, void* cuda_stream);
 /* Map ascending candidate ids to device slots (absent ids dropped, restricted.rs:615-659). */
@@ -233,8 +236,10 @@ hx_status hx_search_dense(hx_index* idx, const float* queries, size_t B, const h
 const char* hx_last_error(void);          /* thread-local, valid until the next failing call     */
 uint32_t    hx_last_error_index(void);    /* component index for HX_ERR_INVALID_VECTOR_COMPONENT */
 const char* hx_version(void);
-/* Launch duration (ms, CUDA events on the launch stream) of the dominant kernel of the most
- * recent search call on this handle, and the number of launches it covered. */
+/* Device time (ms, CUDA events recorded on the launch stream around the dominant kernel:
+ * k_hnsw_search or k_scan) and launch count.  After host-buffer calls: the most recent call.
+ * After device-buffer calls: the SUM over every launch since the previous hx_last_kernel_ms
+ * (the call synchronises on the recorded events). */
 hx_status hx_last_kernel_ms(hx_index* idx, float* ms, uint32_t* launches);
 
 #ifdef __cplusplus

@@ -1,0 +1,61 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/helix_b200.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+import helix_db_b200 as hx
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "helix_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_list_agree():
+    assert declared_symbols() == sorted(hx.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = hx.load_library()
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"libhelix_b200.so does not export {name}"
+    assert b"sm_100a" in lib.hx_version()
+
+
+def test_no_torch_or_oracle_in_the_product_library():
+    # the boundary is plain C: no torch types, and the oracle is never linked into the product
+    import subprocess
+    out = subprocess.run(["ldd", str(hx.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "torch" not in out and "hx_oracle" not in out
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(hx.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "hxo_" not in syms
+
+
+def test_product_sources_never_reference_the_oracle():
+    for p in (ROOT / "helix-db_b200").rglob("*"):
+        if p.suffix in {".cu", ".cuh", ".hpp", ".h", ".py", ".sh"}:
+            t = p.read_text()
+            assert "hx_oracle" not in t and "import hxo" not in t and "from oracle" not in t, p
+
+
+def test_pure_entry_points_work_without_a_device():
+    lib = hx.load_library()
+    assert hx.restricted_plan(256, 128) == "Exact"          # restricted.rs:40-42,433-440
+    assert hx.restricted_plan(257, 128) == "FilteredGraph"
+    assert hx.restricted_plan(256, 4096) == "Exact"
+    assert hx.restricted_plan(256, 4097) == "FilteredGraph"
+    assert lib.hx_search(None, None, 0, None, None, None, None, None) == hx.HX_ERR_INDEX_NOT_FOUND
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(hx.HelixDbError) as e:
+        hx.VectorIndex(hx.Metric.Euclidean, hx.VectorIndexConfig("t", "embedding", 8))
+    assert e.value.code == hx.HX_ERR_CUDA and "no CPU fallback" in str(e.value)

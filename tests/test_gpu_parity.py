@@ -1,0 +1,399 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar: neighbour ids, ordering, scores AND the reference's SearchStats counters are compared bit for bit —
+the octet kernel reproduces the reference's AVX+FMA accumulation order, so no tolerance is needed for
+Euclidean / Cosine / Manhattan.  The independent f64 tolerance the reference states for its own kernels,
+max(d*2^-23, 1e-5) relative (tests/production_support/vector/magnitude_regressions.rs:286-328), is checked too.
+"""
+import math
+import struct
+
+import numpy as np
+import pytest
+
+import helix_db_b200 as hx
+from oracle import hxo
+
+pytestmark = pytest.mark.gpu
+
+METRICS = [(hx.Metric.Euclidean, hxo.EUCLIDEAN), (hx.Metric.Cosine, hxo.COSINE), (hx.Metric.Manhattan, hxo.MANHATTAN)]
+
+
+def bits(x):
+    return struct.unpack("<I", struct.pack("<f", float(x)))[0]
+
+
+def levels_for(n, m, seed):
+    rng = np.random.default_rng(seed)
+    ml = hxo.lib().hxo_default_ml_for_m(m)
+    return [int(hxo.lib().hxo_select_layer_from_uniform(ml, float(u))) for u in rng.random(n, dtype=np.float32)]
+
+
+def build_pair(gm, om, rows, ids=None, m=16, m0=32, efc=200, seed=1):
+    n, dim = rows.shape
+    ids = np.arange(n, dtype=np.uint64) if ids is None else np.asarray(ids, dtype=np.uint64)
+    ora = hxo.Index(om, dim, m=m, m0=m0, ef_construction=efc)
+    for i, lv in zip(range(n), levels_for(n, m, seed)):
+        ora.insert(int(ids[i]), rows[i], lv)
+    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("t", "embedding", dim).with_m(m).with_m0(m0).with_ef_construction(efc))
+    gpu.mirror_from_oracle(ora)
+    return gpu, ora
+
+
+def assert_same(gpu_ids, gpu_sc, gpu_cnt, ora_ids, ora_sc, what=""):
+    assert int(gpu_cnt) == len(ora_ids), f"{what}: count {gpu_cnt} vs {len(ora_ids)}"
+    assert gpu_ids[:gpu_cnt].tolist() == ora_ids.tolist(), f"{what}: ids differ"
+    assert gpu_sc[:gpu_cnt].tobytes() == ora_sc.tobytes(), f"{what}: score bits differ"
+
+
+# ---- phase-0 public result baseline through the C ABI ------------------------------------
+def test_phase0_public_result_and_io_baseline():
+    ora = hxo.Index(hxo.COSINE, 2, m=4, m0=8, ef_construction=16)
+    for node_id, vec, layer in [(1, [1.0, 0.0], 0), (2, [0.0, 1.0], 1), (3, [-1.0, 0.0], 2), (4, [0.0, -1.0], 0)]:
+        ora.insert(node_id, vec, layer)
+    gpu = hx.VectorIndex(hx.Metric.Cosine, hx.VectorIndexConfig("phase0", "embedding", 2).with_m(4).with_m0(8)
+                         .with_ef_construction(16))
+    gpu.mirror_from_oracle(ora)
+    params = hx.SearchParams.new(4).with_ef(16).with_simhash_mode(hx.SimHashMode.Off).with_pre_simhash_sampling_ratio(1.0)
+    results, stats = gpu.search_with_stats([1.0, 0.0], params)
+    plain = gpu.search([1.0, 0.0], params)
+    assert [(r.entity_id(), bits(r.score())) for r in plain] == [(r.entity_id(), bits(r.score())) for r in results]
+    assert [(r.entity_id(), bits(r.score())) for r in results] == [
+        (1, bits(0.0)), (2, bits(0.5)), (4, bits(0.5)), (3, bits(1.0))]
+    assert stats.expansion_steps == 4
+    assert stats.neighbors_examined == 12
+    assert stats.vectors_loaded == 3
+    assert stats.distance_computations == 4
+
+
+# ---- item 7: validation order + empty index -------------------------------------------------------------------
+def test_validation_order_and_empty_index():
+    gpu = hx.VectorIndex(hx.Metric.Cosine, hx.VectorIndexConfig("v", "embedding", 3))
+    p = hx.SearchParams.strict(1)
+    assert gpu.search([1.0, 0.0, 0.0], p) == []                       # empty index -> Ok([])
+    gpu.load_vectors([100, 101], [[0.0, 1.0, 0.0], [1.0, 0.0, 0.0]])
+    gpu.load_graph(1, [100, 101], [0, 2, 3], [99, 101, 100])           # 99 has no vector row
+    gpu.load_graph(0, [100, 101], [0, 1, 2], [101, 100])
+    gpu.set_entry(100, 1)
+    bad = hx.SearchParams.strict(1)
+    bad.query_dimension = 2
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu._search_raw(np.array([[1.0, 0.0]], dtype=np.float32), bad)
+    assert e.value.variant == "InvalidDimension"
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search([1.0, float("nan"), 0.0], p)
+    assert e.value.variant == "InvalidVectorComponent" and e.value.index == 1
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search([0.0, 0.0, 0.0], p)
+    assert e.value.variant == "ZeroNormCosineVector"
+    with pytest.raises(hx.HelixDbError) as e:                          # Adaptive sampling is unpinned: refused, not faked
+        gpu.search([1.0, 0.0, 0.0], hx.SearchParams.new(1))
+    assert e.value.variant == "Unsupported"
+    # greedy KAT (tests/production_support/vector/search.rs:231-291): from 100 on layer 1 the walk ends at 101
+    r = gpu.search([1.0, 0.0, 0.0], p)
+    assert [x.entity_id() for x in r] == [101] and bits(r[0].score()) == bits(0.0)
+    # the same validation runs on the device for larger batches (B > 8)
+    q = np.tile(np.array([[1.0, 0.0, 0.0]], dtype=np.float32), (20, 1))
+    q[13, 2] = np.inf
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search_batch(q, p)
+    assert e.value.variant == "InvalidVectorComponent" and e.value.index == 2
+    e_gpu = hx.VectorIndex(hx.Metric.Euclidean, hx.VectorIndexConfig("m", "embedding", 2))
+    e_gpu.load_vectors([1], [[1.0, 2.0]])
+    e_gpu.load_graph(0, [1], [0, 0], [])
+    e_gpu.set_entry(1, 0)
+    lim = hxo.component_limit(hxo.EUCLIDEAN, 2)
+    over = float(np.nextafter(np.float32(lim), np.float32(np.inf)))
+    with pytest.raises(hx.HelixDbError) as e:
+        e_gpu.search([0.0, over], hx.SearchParams.strict(1))
+    assert e.value.variant == "VectorComponentMagnitudeExceeded" and e.value.index == 1
+    assert len(e_gpu.search([0.0, lim], hx.SearchParams.strict(1))) == 1
+    with pytest.raises(hx.HelixDbError) as e:                          # rows are validated like decode_item_borrowed
+        e_gpu.load_vectors([1, 2], [[1.0, 2.0], [float("nan"), 0.0]])
+    assert e.value.variant == "InvalidVectorComponent"
+
+
+# ---- item 5: tie stability ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("gm,om", METRICS)
+def test_tie_stability(gm, om):
+    ora = hxo.Index(om, 2, m=4, m0=8, ef_construction=16)
+    for node_id in (2, 1, 3):
+        ora.insert(node_id, [1.0, 0.0], 0)
+    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("tie", "embedding", 2).with_m(4).with_m0(8).with_ef_construction(16))
+    gpu.mirror_from_oracle(ora)
+    r = gpu.search_restricted([1.0, 0.0], hx.SearchParams.strict(3), hx.RestrictedVectorCandidates.from_ids([3, 1, 2]))
+    assert [x.entity_id() for x in r] == [1, 2, 3] and [float(x.score()) for x in r] == [0.0, 0.0, 0.0]
+    r = gpu.search([1.0, 0.0], hx.SearchParams.strict(3, 16))
+    assert [x.entity_id() for x in r] == [1, 2, 3]
+
+
+# ---- item 6: circle fixtures (rows seeded directly, m=32/m0=64, cosine, ef=64) -----------------------------------------
+def circle_pair(n):
+    ora = hxo.Index(hxo.COSINE, 2, m=32, m0=64, ef_construction=200)
+    ids = np.arange(1, n + 1, dtype=np.uint64)
+    rows = np.stack([hxo.circle_vector(int(e), n) for e in ids])
+    ora.put_vectors(ids, rows)
+    offs, nb = [0], []
+    for e in ids:
+        r = hxo.skip_neighbors(int(e), n)
+        ora.put_neighbors(0, int(e), r)
+        nb.append(r)
+        offs.append(offs[-1] + len(r))
+    ora.set_entry(1, 0)
+    gpu = hx.VectorIndex(hx.Metric.Cosine, hx.VectorIndexConfig("circle", "embedding", 2).with_m(32).with_m0(64))
+    gpu.load_vectors(ids, rows)
+    gpu.load_graph(0, ids, np.array(offs, dtype=np.uint32), np.concatenate(nb))
+    gpu.set_entry(1, 0)
+    return gpu, ora
+
+
+@pytest.mark.parametrize("n,floor", [(24, 1.0), (10_000, 0.995)])
+def test_circle_fixture(n, floor):
+    gpu, ora = circle_pair(n)
+    params = hx.SearchParams.strict(10, 64)
+    params.collect_stats = True
+    matched = 0
+    for qi in range(24):
+        e = 1 + qi * (n // 24)
+        q = hxo.circle_vector(e, n)
+        st = hx.SearchStats()
+        ids, sc, cnt = gpu.search_batch(q.reshape(1, -1), params, st)
+        oi, os_, ost = ora.search(q, 10, ef=64, with_stats=True)
+        assert_same(ids[0], sc[0], cnt[0], oi, os_, f"circle n={n} q={qi}")          # exact ties at the beam edge included
+        assert st.expansion_steps == ost["expansion_steps"]
+        assert st.neighbors_examined == ost["neighbors_examined"]
+        assert st.distance_computations == ost["distance_computations"]
+        exact, _ = ora.search_exact(q, 10)
+        matched += len(set(ids[0, :cnt[0]].tolist()) & set(exact.tolist()))
+    assert matched / 240.0 >= floor
+
+
+# ---- C1: xorshift 128-d fixture, reference-style build, three metrics, bit-exact batch parity + stats ------------------
+@pytest.mark.parametrize("gm,om", METRICS)
+def test_c1_xorshift_hnsw_parity(gm, om):
+    n, dim, nq = 3000, 128, 64
+    rows = hxo.xorshift_vectors(0, n, dim)
+    queries = hxo.xorshift_vectors(n, nq, dim)
+    gpu, ora = build_pair(gm, om, rows)
+    params = hx.SearchParams.strict(10)
+    ids, sc, cnt = gpu.search_batch(queries, params)
+    recall = 0
+    for q in range(nq):
+        oi, os_ = ora.search(queries[q], 10)
+        assert_same(ids[q], sc[q], cnt[q], oi, os_, f"{gm.name} q={q}")
+        ex, _ = ora.search_exact(queries[q], 10)
+        recall += len(set(oi.tolist()) & set(ex.tolist()))
+    assert recall / (10.0 * nq) >= 0.95
+    # per-query counters, one query per call
+    params.collect_stats = True
+    for q in range(8):
+        st = hx.SearchStats()
+        gpu.search_batch(queries[q:q + 1], params, st)
+        _, _, ost = ora.search(queries[q], 10, with_stats=True)
+        for f in ("expansion_steps", "neighbors_examined", "distance_computations", "vectors_loaded"):
+            assert getattr(st, f) == ost[f], (f, q)
+        assert st.algorithmic_bytes == st.expansion_steps * (5 + 8 * 32) + st.distance_computations * (4 + 4 * dim)
+
+
+# ---- dimensions around the AVX cut-over (d < 32 scalar order; d % 32 != 0 tail), sparse ids, small ef ----------------
+@pytest.mark.parametrize("dim", [3, 8, 31, 32, 33, 70, 100, 768])
+@pytest.mark.parametrize("gm,om", METRICS[:2])
+def test_dimension_sweep(dim, gm, om):
+    n, nq = (600, 24) if dim < 768 else (400, 12)
+    rng = np.random.default_rng(dim)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    ids = np.sort(rng.choice(10**12, size=n, replace=False).astype(np.uint64)) * 3 + 1     # sparse u64 ids
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    gpu, ora = build_pair(gm, om, rows, ids=ids, m=8, m0=16, efc=40)
+    for ef, k in ((10, 10), (37, 5), (100, 10)):
+        params = hx.SearchParams.strict(k, ef)
+        gi, gs, gc = gpu.search_batch(queries, params)
+        for q in range(nq):
+            oi, os_ = ora.search(queries[q], k, ef=ef)
+            assert_same(gi[q], gs[q], gc[q], oi, os_, f"dim={dim} ef={ef} q={q}")
+    cand = ids[::3]
+    gi, gs, gc = gpu.search_restricted_batch(queries, hx.SearchParams.strict(7), hx.RestrictedVectorCandidates.from_ids(cand))
+    for q in range(nq):
+        oi, os_ = ora.search_restricted(queries[q], 7, cand)
+        assert_same(gi[q], gs[q], gc[q], oi, os_, f"restricted dim={dim} q={q}")
+
+
+# ---- f64 tolerance of the device scores, as the reference states it for its own kernels ---------------------------------
+def test_scores_within_reference_f64_tolerance():
+    dim, n = 1536, 64
+    rng = np.random.default_rng(5)
+    for gm, om in METRICS:
+        lim = hxo.component_limit(om, dim)
+        scale = 1.0 if lim is None else min(float(lim), 1e3)
+        rows = (rng.uniform(-1, 1, (n, dim)) * scale).astype(np.float32)
+        q = (rng.uniform(-1, 1, dim) * scale).astype(np.float32)
+        gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("tol", "embedding", dim))
+        gpu.load_vectors(np.arange(n, dtype=np.uint64), rows)
+        gpu.load_graph(0, np.arange(n, dtype=np.uint64), np.zeros(n + 1, dtype=np.uint32), [])
+        gpu.set_entry(0, 0)
+        gi, gs, gc = gpu.search_restricted_batch(q.reshape(1, -1), hx.SearchParams.strict(n),
+                                                 hx.RestrictedVectorCandidates.from_ids(np.arange(n)))
+        r64, q64 = rows.astype(np.float64), q.astype(np.float64)
+        if om == hxo.EUCLIDEAN:
+            exact = ((r64 - q64) ** 2).sum(1)
+        elif om == hxo.MANHATTAN:
+            exact = np.abs(r64 - q64).sum(1)
+        else:
+            exact = (1.0 - (r64 @ q64) / (np.linalg.norm(r64, axis=1) * np.linalg.norm(q64))) / 2.0
+        tol = max(dim * float(np.finfo(np.float32).eps), 1.0e-5)
+        for j in range(int(gc[0])):
+            e = exact[int(gi[0, j])]
+            assert abs(float(gs[0, j]) - e) <= max(abs(e), 1.0) * tol
+
+
+# ---- restricted exact scan: plan thresholds, clamps, errors, absent ids, per-query sets ---------------------------------------
+@pytest.mark.parametrize("gm,om", METRICS)
+def test_restricted_scan_edge_cases(gm, om):
+    n, dim = 5000, 64
+    rng = np.random.default_rng(11)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    ids = np.arange(10, 10 + 2 * n, 2, dtype=np.uint64)                 # even ids only: odd ids are absent
+    ora = hxo.Index(om, dim)
+    ora.put_vectors(ids, rows)
+    ora.put_neighbors(0, int(ids[0]), [])
+    ora.set_entry(int(ids[0]), 0)
+    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("r", "embedding", dim))
+    gpu.load_vectors(ids, rows)
+    gpu.load_graph(0, ids[:1], [0, 0], [])
+    gpu.set_entry(int(ids[0]), 0)
+    queries = rng.standard_normal((9, dim)).astype(np.float32)
+    for ncand, k in ((1, 10), (3, 10), (255, 10), (256, 10), (257, 10), (2000, 800), (5000, 1), (1500, 33)):
+        cand = np.sort(rng.choice(np.arange(0, 10 + 2 * n + 50, dtype=np.uint64), size=ncand, replace=False))
+        gi, gs, gc = gpu.search_restricted_batch(queries, hx.SearchParams.strict(k),
+                                                 hx.RestrictedVectorCandidates.from_ids(cand))
+        for q in range(len(queries)):
+            oi, os_ = ora.search_restricted(queries[q], k, cand)
+            assert_same(gi[q], gs[q], gc[q], oi, os_, f"|C|={ncand} k={k} q={q}")
+            assert set(gi[q, :gc[q]].tolist()) <= set(cand.tolist())     # every result id is a candidate
+    # empty candidate set -> Ok([]) ; k' = min(k,|C|) > 800 -> Query error
+    assert gpu.search_restricted(queries[0], hx.SearchParams.strict(5), hx.RestrictedVectorCandidates.from_ids([])) == []
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search_restricted(queries[0], hx.SearchParams.strict(801), hx.RestrictedVectorCandidates.from_ids(ids[:900]))
+    assert e.value.variant == "Query"
+    assert len(gpu.search_restricted(queries[0], hx.SearchParams.strict(801),
+                                     hx.RestrictedVectorCandidates.from_ids(ids[:700]))) == 700
+    # one candidate set per query
+    offs, cands = [0], []
+    for q in range(len(queries)):
+        c = np.sort(rng.choice(ids, size=50 + 37 * q, replace=False))
+        cands.append(c)
+        offs.append(offs[-1] + len(c))
+    gi, gs, gc = gpu.search_restricted_multi(queries, hx.SearchParams.strict(10), np.concatenate(cands), offs)
+    for q in range(len(queries)):
+        oi, os_ = ora.search_restricted(queries[q], 10, cands[q])
+        assert_same(gi[q], gs[q], gc[q], oi, os_, f"multi q={q}")
+
+
+def test_restricted_full_million_candidate_bound():
+    gpu = hx.VectorIndex(hx.Metric.Euclidean, hx.VectorIndexConfig("b", "embedding", 4))
+    gpu.load_vectors([1, 2], [[0, 0, 0, 1], [0, 0, 1, 0]])
+    gpu.load_graph(0, [1, 2], [0, 1, 2], [2, 1])
+    gpu.set_entry(1, 0)
+    big = np.arange(1_000_001, dtype=np.uint64)
+    ids = np.zeros((1, 1), dtype=np.uint64)
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search_restricted_batch(np.zeros((1, 4), np.float32) + 1, hx.SearchParams.strict(1),
+                                    hx.RestrictedVectorCandidates(big))
+    assert e.value.variant == "Query"
+    gi, gs, gc = gpu.search_restricted_batch(np.array([[0, 0, 0, 1]], np.float32), hx.SearchParams.strict(2),
+                                             hx.RestrictedVectorCandidates(big[:1_000_000]))
+    assert gi[0, :gc[0]].tolist() == [1, 2] and gs[0, 0] == 0.0
+
+
+# ---- persistent CTAs: more queries than CTAs, repeated launches across the stamp-epoch wrap ---------------------------
+def test_many_queries_and_epoch_wrap():
+    n, dim = 1500, 32
+    rng = np.random.default_rng(3)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    gpu, ora = build_pair(hx.Metric.Euclidean, hxo.EUCLIDEAN, rows, m=8, m0=16, efc=60)
+    queries = rng.standard_normal((1500, dim)).astype(np.float32)
+    params = hx.SearchParams.strict(5, 20)
+    gi, gs, gc = gpu.search_batch(queries, params)
+    oi, os_, oc, _, _ = ora.search_batch(queries, 5, 20, threads=4)
+    assert gc.tolist() == oc.tolist() and gi.tolist() == oi.tolist() and gs.tobytes() == os_.tobytes()
+    for it in range(300):                                  # one CTA, > 255 consecutive epochs
+        q = queries[it % 7: it % 7 + 1]
+        a, b, c = gpu.search_batch(q, params)
+        assert a[0].tolist() == oi[it % 7].tolist() and b[0].tobytes() == os_[it % 7].tobytes()
+
+
+# ---- sharded path: per-shard top-k merged by (score, id) equals the unsharded exact answer ---------------------------------------
+def test_merge_topk_matches_unsharded_scan():
+    import torch
+    n, dim, B, k, S = 4000, 48, 33, 10, 4
+    rng = np.random.default_rng(21)
+    rows = rng.integers(-3, 4, size=(n, dim)).astype(np.float32)        # many exact score ties across shards
+    ids = np.arange(n, dtype=np.uint64)
+    queries = rng.integers(-3, 4, size=(B, dim)).astype(np.float32)
+    ora = hxo.Index(hxo.EUCLIDEAN, dim)
+    ora.put_vectors(ids, rows)
+    ora.set_entry(0, 0)
+    all_ids = np.zeros((S, B, k), dtype=np.uint64)
+    all_sc = np.zeros((S, B, k), dtype=np.float32)
+    all_cnt = np.zeros((S, B), dtype=np.uint32)
+    per = n // S
+    for s in range(S):                                                   # contiguous id ranges
+        lo, hi = s * per, (s + 1) * per if s < S - 1 else n
+        g = hx.VectorIndex(hx.Metric.Euclidean, hx.VectorIndexConfig(f"s{s}", "embedding", dim))
+        g.load_vectors(ids[lo:hi], rows[lo:hi])
+        g.load_graph(0, ids[lo:lo + 1], [0, 0], [])
+        g.set_entry(int(ids[lo]), 0)
+        a, b, c = g.search_restricted_batch(queries, hx.SearchParams.strict(k), hx.RestrictedVectorCandidates(ids[lo:hi]))
+        all_ids[s], all_sc[s], all_cnt[s] = a, b, c
+        g.close()
+    dev = torch.device("cuda:0")
+    t_ids = torch.from_numpy(all_ids.view(np.int64)).to(dev)
+    t_sc = torch.from_numpy(all_sc).to(dev)
+    t_cnt = torch.from_numpy(all_cnt.view(np.int32)).to(dev)
+    o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
+    o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    hx.merge_topk_device(0, t_ids.data_ptr(), t_sc.data_ptr(), t_cnt.data_ptr(), S, B, k, o_ids.data_ptr(),
+                         o_sc.data_ptr(), o_cnt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for q in range(B):
+        ei, es = ora.search_exact(queries[q], k)
+        assert o_cnt[q].item() == k
+        assert o_ids[q].cpu().numpy().view(np.uint64).tolist() == ei.tolist()
+        assert o_sc[q].cpu().numpy().tobytes() == es.tobytes()
+
+
+# ---- device-buffer entry points (inputs resident in HBM) agree with the host-buffer calls ---------------------------------------
+def test_device_buffer_entry_points():
+    import torch
+    n, dim, B, k = 2500, 96, 700, 10
+    rng = np.random.default_rng(8)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    gpu, ora = build_pair(hx.Metric.Cosine, hxo.COSINE, rows, m=8, m0=16, efc=60)
+    queries = rng.standard_normal((B, dim)).astype(np.float32)
+    params = hx.SearchParams.strict(k, 40)
+    hi, hs, hc = gpu.search_batch(queries, params)
+    dev = torch.device("cuda:0")
+    dq = torch.from_numpy(queries).to(dev)
+    o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
+    o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        gpu.search_device(dq.data_ptr(), B, params, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert o_ids.cpu().numpy().view(np.uint64).tolist() == hi.tolist()
+    assert o_sc.cpu().numpy().tobytes() == hs.tobytes()
+    ms, launches = gpu.last_kernel_ms()
+    assert launches == 3 and ms > 0.0
+    # restricted: per-query candidate sets as device slots
+    cand = np.arange(0, n, 5, dtype=np.uint64)
+    d_c = torch.from_numpy(cand.view(np.int64)).to(dev)
+    d_slots = torch.zeros((len(cand),), dtype=torch.int32, device=dev)
+    gpu.map_candidates_device(d_c.data_ptr(), len(cand), d_slots.data_ptr(), stream)
+    gpu.search_restricted_device(dq.data_ptr(), B, hx.SearchParams.strict(k), d_slots.data_ptr(), 0, len(cand), 0,
+                                 o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+    torch.cuda.synchronize()
+    ri, rs, rc = gpu.search_restricted_batch(queries, hx.SearchParams.strict(k), hx.RestrictedVectorCandidates(cand))
+    assert o_ids.cpu().numpy().view(np.uint64).tolist() == ri.tolist()
+    assert o_sc.cpu().numpy().tobytes() == rs.tobytes()

@@ -397,3 +397,74 @@ def test_device_buffer_entry_points():
     ri, rs, rc = gpu.search_restricted_batch(queries, hx.SearchParams.strict(k), hx.RestrictedVectorCandidates(cand))
     assert o_ids.cpu().numpy().view(np.uint64).tolist() == ri.tolist()
     assert o_sc.cpu().numpy().tobytes() == rs.tobytes()
+
+
+# ---- device build: reference invariants, recall, and oracle parity on the device-built graph ---------------
+def _check_graph_invariants(g, lim0, m):
+    n, s0, su = g["n"], g["layer0_stride"], g["upper_stride"]
+    nbr0 = g["nbr0"].reshape(n, s0)
+    deg0 = g["deg0"]
+    assert deg0.max() <= lim0
+    adj = [set(nbr0[i, :deg0[i]].tolist()) for i in range(n)]
+    for i in range(n):
+        row = nbr0[i, :deg0[i]]
+        assert i not in adj[i]                                        # no self link
+        assert np.all(row[1:] > row[:-1])                             # strictly ascending
+    for i in range(n):
+        for j in adj[i]:
+            assert i in adj[j], f"layer-0 edge {i}->{j} is not bidirectional"
+    rows = len(g["upper_node"])
+    unbr = g["upper_nbr"].reshape(max(rows, 1), su) if rows else np.zeros((0, su), np.uint32)
+    upper = {}
+    for r in range(rows):
+        key = (int(g["upper_layer"][r]), int(g["upper_node"][r]))
+        d = int(g["upper_deg"][r])
+        assert d <= m
+        lst = unbr[r, :d]
+        assert np.all(lst[1:] > lst[:-1]) and key[1] not in lst.tolist()
+        upper[key] = set(lst.tolist())
+    for (layer, node), s in upper.items():
+        assert g["levels"][node] >= layer
+        for w in s:
+            assert node in upper[(layer, w)], f"layer-{layer} edge {node}->{w} is not bidirectional"
+    top = int(g["levels"].max())
+    assert g["max_layer"] == top and g["levels"][g["entry_slot"]] == top
+
+
+@pytest.mark.parametrize("gm,om,n,dim,m", [(hx.Metric.Euclidean, hxo.EUCLIDEAN, 4000, 64, 16),
+                                           (hx.Metric.Cosine, hxo.COSINE, 3000, 100, 8),
+                                           (hx.Metric.Manhattan, hxo.MANHATTAN, 1500, 24, 16)])
+def test_device_build(gm, om, n, dim, m):
+    rng = np.random.default_rng(n)
+    cent = rng.standard_normal((32, dim)).astype(np.float32)
+    rows = (cent[rng.integers(0, 32, n)] + 0.5 * rng.standard_normal((n, dim))).astype(np.float32)
+    ids = np.arange(100, 100 + n, dtype=np.uint64)
+    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("b", "embedding", dim).with_m(m).with_m0(2 * m).with_ef_construction(100))
+    gpu.load_vectors(ids, rows)
+    gpu.build(seed=42)
+    g = gpu.download_graph()
+    g["entry_slot"] = int(g["entry_point"] - 100)
+    _check_graph_invariants(g, 2 * m, m)
+    # level law: about 1/m of the nodes reach layer >= 1 (select_layer, mod.rs:769-796)
+    frac = float((g["levels"] >= 1).mean())
+    assert 0.5 / m < frac < 2.0 / m
+    # the oracle traverses the identical adjacency: results must agree bit for bit
+    ora = hxo.Index(om, dim, m=m, m0=2 * m, ef_construction=100)
+    ora.put_vectors(ids, rows)
+    ora.import_graph(g["levels"], g["deg0"], g["nbr0"], g["layer0_stride"], g["upper_node"], g["upper_layer"],
+                     g["upper_deg"], g["upper_nbr"], g["upper_stride"], g["entry_point"], g["max_layer"])
+    queries = (cent[rng.integers(0, 32, 48)] + 0.5 * rng.standard_normal((48, dim))).astype(np.float32)
+    gi, gs, gc = gpu.search_batch(queries, hx.SearchParams.strict(10))
+    hit = 0
+    for q in range(len(queries)):
+        oi, os_ = ora.search(queries[q], 10)
+        assert_same(gi[q], gs[q], gc[q], oi, os_, f"built graph q={q}")
+        ex, _ = ora.search_exact(queries[q], 10)
+        hit += len(set(oi.tolist()) & set(ex.tolist()))
+    assert hit / (10.0 * len(queries)) >= 0.95
+    # explicit levels are honoured (scripted layers [0,1,3] => entry = the level-3 node, index.rs:1919-1973)
+    lv = np.zeros(n, dtype=np.uint16)
+    lv[1], lv[2] = 1, 3
+    gpu.build(levels=lv)
+    gi2 = gpu.graph_info()
+    assert gi2["entry_point"] == 102 and gi2["max_layer"] == 3

@@ -1,0 +1,495 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec @ recall@10, DBpedia-1M-shaped d=768 top-10 (BASELINE.json), on 1/2/4/8 B200.
+
+A "step" is one pass of the hot path over one batch of Q independent single-query HNSW traversals
+(config C2: 1M x 768 f32, cosine, m=16/m0=32/ef_construction=200, ef=100, k=10; no cross-query sharing).
+
+  value   : whole-job queries/sec, queries already resident in HBM (hx_search_device), CUDA-event timed.
+  e2e     : the same metric through the reference-facing C-ABI call hx_search with HOST (pinned) buffers:
+            H2D of the queries and D2H of ids/scores/counts are inside the timed region.
+  roofline: k_hnsw_search, algorithmic bytes E*(5+8*32) + Dc*(4+4d) per launch / CUDA-event kernel time,
+            against the measured HBM peak in MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference: the CPU oracle (restatement of the reference's algorithm without its KV layer)
+            traversing the IDENTICAL graph on all host cores, one query per thread.
+  N > 1   : one process per GPU (torchrun).  Default "replica" mode partitions the QUERIES across full replicas
+            (no data-path collective; weak scaling: Q queries per GPU per step).  The same line carries a
+            "sharded" object: the 1M corpus split by id range, every rank searching every query on its shard,
+            ONE NCCL all-gather of the per-shard top-k and the (score,id) merge kernel inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SEED = 0x0DB9ED1A
+N_CENTROIDS = 1024
+SIGMA = 0.3
+K = 10
+EF = 100
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--queries-per-step", type=int, default=8192)
+    ap.add_argument("--metric", default="cosine", choices=["cosine", "euclidean"])
+    ap.add_argument("--recall-queries", type=int, default=512)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--workload", default="hnsw", choices=["hnsw", "prefilter"])
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = max(mx, float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel: str):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu summary, or None."""
+    p = ROOT / "profiles" / "ncu_summary.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(kernel, {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def build_index(hx, args, device, first_id, n, storage=0):
+    metric = hx.Metric.Cosine if args.metric == "cosine" else hx.Metric.Euclidean
+    cfg = hx.VectorIndexConfig("dbpedia_1m_synthetic", "embedding", args.dim)   # m=16, m0=32, ef_c=200 defaults
+    ix = hx.VectorIndex(metric, cfg, device=device, storage=storage)
+    t0 = time.perf_counter()
+    ix.generate_vectors(first_id, n, SEED, N_CENTROIDS, SIGMA)
+    t1 = time.perf_counter()
+    ix.build(seed=SEED)
+    t2 = time.perf_counter()
+    return ix, {"generate_s": round(t1 - t0, 2), "build_s": round(t2 - t1, 2)}
+
+
+def oracle_from_device(hxo, ix, args):
+    """Mirror the device index (vectors + graph) into the CPU oracle so both traverse identical adjacency."""
+    metric = hxo.COSINE if args.metric == "cosine" else hxo.EUCLIDEAN
+    ora = hxo.Index(metric, args.dim)
+    g = ix.download_graph()
+    n = g["n"]
+    chunk = 65536
+    for lo in range(0, n, chunk):
+        ids, rows = ix.download_vectors(lo, min(chunk, n - lo))
+        ora.put_vectors(ids, rows)
+    ora.import_graph(g["levels"], g["deg0"], g["nbr0"], g["layer0_stride"], g["upper_node"], g["upper_layer"],
+                     g["upper_deg"], g["upper_nbr"], g["upper_stride"], g["entry_point"], g["max_layer"])
+    return ora
+
+
+def exact_topk_device(hx, torch, ix, queries, n, first_id, k):
+    """Ground truth by the exact scan kernel over ALL rows (same metric, same (score,id) tie rule)."""
+    dev = torch.device("cuda", ix.device)
+    B = len(queries)
+    dq = torch.from_numpy(queries).to(dev)
+    slots = torch.arange(n, dtype=torch.int32, device=dev)
+    o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
+    o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    step = 64
+    for lo in range(0, B, step):
+        b = min(step, B - lo)
+        ix.search_restricted_device(dq[lo:lo + b].data_ptr(), b, hx.SearchParams.strict(k), slots.data_ptr(), 0, n, n,
+                                    o_ids[lo:lo + b].data_ptr(), o_sc[lo:lo + b].data_ptr(),
+                                    o_cnt[lo:lo + b].data_ptr(), stream)
+    torch.cuda.synchronize(dev)
+    ix.last_kernel_ms()
+    return o_ids.cpu().numpy().view(np.uint64)
+
+
+def recall_at_k(found, truth):
+    hit = 0
+    for f, t in zip(found, truth):
+        hit += len(set(f.tolist()) & set(t.tolist()))
+    return hit / float(truth.size)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import helix_db_b200 as hx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    n, dim, Q, k = args.n, args.dim, args.queries_per_step, K
+    hbm_peak, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- setup (untimed): corpus on the device, graph built on the device ---------------------------------------
+    ix, setup = build_index(hx, args, local_rank, 0, n)
+    n_sets = args.steps + args.warmup
+    # distinct queries every step and every rank (nothing can be answered from a previous step's cache lines)
+    qsets = [ix.generate_queries(SEED, Q, first_query=(rank * n_sets + s) * Q, n_centroids=N_CENTROIDS, sigma=SIGMA)
+             for s in range(n_sets)]
+    params = hx.SearchParams.strict(k, EF)
+    d_q = [torch.from_numpy(q).to(dev) for q in qsets]
+    o_ids = torch.zeros((Q, k), dtype=torch.int64, device=dev)
+    o_sc = torch.zeros((Q, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((Q,), dtype=torch.int32, device=dev)
+
+    def step_device(s):
+        ix.search_device(d_q[s].data_ptr(), Q, params, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+
+    # recall@10 on the first query set vs the exact scan
+    rq = min(args.recall_queries, Q)
+    truth = exact_topk_device(hx, torch, ix, qsets[0][:rq], n, 0, k)
+    step_device(0)
+    torch.cuda.synchronize(dev)
+    recall = recall_at_k(o_ids[:rq].cpu().numpy().view(np.uint64), truth)
+
+    # ---- value: W warm-up steps, then exactly K timed steps, barrier + synchronize on both sides ----------------------
+    for s in range(args.warmup):
+        step_device(s)
+    barrier()
+    ix.last_kernel_ms()                       # drop warm-up launches from the kernel-time accumulator
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms_total, kernel_launches = ix.last_kernel_ms()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps * Q / (ms_total / 1e3)
+
+    # algorithmic bytes per launch: replay the timed query sets with the reference's counters switched on (untimed)
+    st_sum = dict(expansion_steps=0, distance_computations=0, neighbors_examined=0, algorithmic_bytes=0)
+    params_st = hx.SearchParams.strict(k, EF)
+    params_st.collect_stats = True
+    for s in range(args.steps):
+        st = hx.SearchStats()
+        ix.search_device(d_q[args.warmup + s].data_ptr(), Q, params_st, o_ids.data_ptr(), o_sc.data_ptr(),
+                         o_cnt.data_ptr(), stream, st)
+        for f in st_sum:
+            st_sum[f] += int(getattr(st, f))
+    ix.last_kernel_ms()
+    bytes_per_launch = st_sum["algorithmic_bytes"] / args.steps
+    kernel_ms = kernel_ms_total / max(kernel_launches, 1)
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+
+    # ---- e2e: reference-facing C-ABI call with host (pinned) buffers -------------------------------------------------
+    h_q = [torch.from_numpy(q).pin_memory() for q in qsets]
+    h_ids = torch.zeros((Q, k), dtype=torch.int64).pin_memory()
+    h_sc = torch.zeros((Q, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.zeros((Q,), dtype=torch.int32).pin_memory()
+    import ctypes as C
+    L = hx.load_library()
+    cp = params._c()
+
+    def step_host(s):
+        rc = L.hx_search(ix.h, C.cast(h_q[s].data_ptr(), C.POINTER(C.c_float)), Q, C.byref(cp),
+                         C.cast(h_ids.data_ptr(), C.POINTER(C.c_uint64)), C.cast(h_sc.data_ptr(), C.POINTER(C.c_float)),
+                         C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None)
+        if rc != 0:
+            raise RuntimeError(f"hx_search failed: {L.hx_last_error().decode()}")
+
+    for s in range(args.warmup):
+        step_host(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_host(args.warmup + s)
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * Q / float(te.item())
+
+    # ---- batch-1 single-stream latency (one query per call, sequential) ------------------------------------------------
+    nb1 = 200
+    for i in range(20):
+        ix.search_device(d_q[0][i:i + 1].data_ptr(), 1, params, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+    torch.cuda.synchronize(dev)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for i in range(nb1):
+        ix.search_device(d_q[0][i:i + 1].data_ptr(), 1, params, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+    b1.record()
+    torch.cuda.synchronize(dev)
+    batch1_us = b0.elapsed_time(b1) / nb1 * 1e3
+    ix.last_kernel_ms()
+
+    # ---- sharded path (north_star): id-range shards of the SAME corpus, one all-gather, merge ----------------------------
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        sx, s_setup = build_index(hx, args, local_rank, lo, hi - lo)
+        # every rank searches the SAME queries (rank 0's sets) against its shard
+        sq = [ix.generate_queries(SEED, Q, first_query=s * Q, n_centroids=N_CENTROIDS, sigma=SIGMA) for s in range(n_sets)]
+        d_sq = [torch.from_numpy(q).to(dev) for q in sq]
+        l_ids = torch.zeros((Q, k), dtype=torch.int64, device=dev)
+        l_sc = torch.zeros((Q, k), dtype=torch.float32, device=dev)
+        l_cnt = torch.zeros((Q,), dtype=torch.int32, device=dev)
+        a_ids = torch.zeros((world, Q, k), dtype=torch.int64, device=dev)
+        a_sc = torch.zeros((world, Q, k), dtype=torch.float32, device=dev)
+        a_cnt = torch.zeros((world, Q), dtype=torch.int32, device=dev)
+        # one collective: ids, scores and counts travel in ONE packed buffer (12*k+4 bytes per query per shard)
+        pack = torch.zeros((Q, 3 * k + 1), dtype=torch.int32, device=dev)
+        apack = torch.zeros((world, Q, 3 * k + 1), dtype=torch.int32, device=dev)
+
+        def step_sharded(s):
+            sx.search_device(d_sq[s].data_ptr(), Q, params, l_ids.data_ptr(), l_sc.data_ptr(), l_cnt.data_ptr(), stream)
+            pack[:, :2 * k] = l_ids.view(torch.int32).view(Q, 2 * k)
+            pack[:, 2 * k:3 * k] = l_sc.view(torch.int32)
+            pack[:, 3 * k] = l_cnt
+            dist.all_gather_into_tensor(apack, pack)
+            a_ids.copy_(apack[:, :, :2 * k].contiguous().view(torch.int64).view(world, Q, k))
+            a_sc.copy_(apack[:, :, 2 * k:3 * k].contiguous().view(torch.float32))
+            a_cnt.copy_(apack[:, :, 3 * k])
+            hx.merge_topk_device(local_rank, a_ids.data_ptr(), a_sc.data_ptr(), a_cnt.data_ptr(), world, Q, k,
+                                 o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+
+        truth_s = exact_topk_device(hx, torch, ix, sq[0][:rq], n, 0, k)
+        step_sharded(0)
+        torch.cuda.synchronize(dev)
+        s_recall = recall_at_k(o_ids[:rq].cpu().numpy().view(np.uint64), truth_s)
+        for s in range(args.warmup):
+            step_sharded(s)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for s in range(args.steps):
+            step_sharded(args.warmup + s)
+        g1.record()
+        barrier()
+        ts = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sharded = {"value": round(args.steps * Q / (float(ts.item()) / 1e3), 1), "unit": "queries/s",
+                   "recall_at_10": round(s_recall, 4), "shard_vectors": hi - lo, "collective": "1 x all_gather_into_tensor "
+                   f"of {(12 * k + 4) * Q} B per rank per step (NCCL) + hx_merge_topk_device",
+                   "ms_per_step": round(float(ts.item()) / args.steps, 3), "shard_build_s": s_setup["build_s"]}
+        sx.close()
+
+    # ---- CPU baseline: the oracle on the box's host cores, same graph, bounded sample (rank 0, N = 1 only) -------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args, ix, qsets[0], truth[:rq] if rq else None)
+
+    if rank == 0:
+        line = {
+            "metric": "queries/sec @ recall@10, DBpedia-1M d=768 top-10, 1/2/4/8 B200 vs CPU ref",
+            "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "recall_at_10": round(recall, 4),
+            "config": {
+                "workload": f"C2: {n}x{dim} f32 {args.metric} HNSW top-10 (m=16, m0=32, ef_construction=200, ef={EF}), "
+                            f"independent single-query traversals (batch=1 semantics, no cross-query sharing), "
+                            f"{Q} queries per GPU per step",
+                "queries_per_step_per_gpu": Q, "parallelism": "single GPU" if world == 1 else
+                f"{world} full replicas, queries partitioned, no data-path collective",
+                "l2": "corpus 3.07 GB >> 126 MB L2; distinct queries every step and rank",
+                "graph": "built on the device (hx_index_build), identical adjacency mirrored into the CPU oracle",
+                "data_recipe": f"unit-normalised Gaussian mixture, {N_CENTROIDS} centroids, sigma={SIGMA}, seed=0x0DB9ED1A",
+                "setup": setup,
+            },
+            "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4,
+                    "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 4 + 4,
+                    "api": "hx_search (C ABI, pinned host buffers, blocking)"},
+            "gpu_launches": args.steps * 2,
+            "launches_per_step": {"k_validate_and_header": 1, "k_hnsw_search": 1},
+            "roofline": {"bound": "hbm", "kernel": "k_hnsw_search", "achieved": round(achieved, 1), "peak": hbm_peak,
+                         "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_hnsw_search"),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_per_launch),
+                         "kernel_ms_per_launch": round(kernel_ms, 4),
+                         "expansions_per_query": round(st_sum["expansion_steps"] / (args.steps * Q), 1),
+                         "distance_computations_per_query": round(st_sum["distance_computations"] / (args.steps * Q), 1)},
+            "single_stream_batch1": {"latency_us": round(batch1_us, 1), "qps": round(1e6 / batch1_us, 1),
+                                     "note": "one query per hx_search_device call, calls issued back to back"},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if sharded is not None:
+            line["sharded"] = sharded
+        print(json.dumps(line), flush=True)
+    ix.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, ix, queries, truth):
+    """The oracle (C restatement of the reference, no KV layer => an upper bound on the reference's CPU throughput)."""
+    from oracle import hxo
+
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ora = oracle_from_device(hxo, ix, args)
+    mirror_s = time.perf_counter() - t0
+    probe = min(256, len(queries))
+    _, _, _, _, secs = ora.search_batch(queries[:probe], K, EF, threads=cores)
+    qps_probe = probe / max(secs, 1e-9)
+    sample = int(max(probe, min(len(queries), qps_probe * args.cpu_seconds)))
+    ids, sc, cnt, st, secs = ora.search_batch(queries[:sample], K, EF, threads=cores)
+    rec = recall_at_k(ids[:len(truth)], truth) if truth is not None and len(truth) <= sample else None
+    _, _, _, _, secs1 = ora.search_batch(queries[:min(sample, 256)], K, EF, threads=1)
+    return {"value": round(sample / secs, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{sample} queries of the first step's set, one query per thread, {cores} threads, "
+                      f"identical graph and vectors",
+            "single_thread_qps": round(min(sample, 256) / secs1, 1), "recall_at_10": None if rec is None else round(rec, 4),
+            "distance_computations_per_query": round(st["distance_computations"] / sample, 1),
+            "mirror_s": round(mirror_s, 1)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust reference cannot be built
+    here: no rustc/cargo, un-vendored SlateDB fork) on all host cores, same config, metric and unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    import helix_db_b200 as hx
+    from oracle import hxo
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference", "unavailable": "the graph of config C2 is built on the device "
+                          "(hours on the CPU); no GPU visible in this process"}))
+        return
+    n, dim, Q = args.n, args.dim, args.queries_per_step
+    ix, setup = build_index(hx, args, 0, 0, n)
+    cores = os.cpu_count() or 1
+    queries = ix.generate_queries(SEED, Q, first_query=0, n_centroids=N_CENTROIDS, sigma=SIGMA)
+    rq = min(args.recall_queries, Q)
+    truth = exact_topk_device(hx, torch, ix, queries[:rq], n, 0, K)
+    ora = oracle_from_device(hxo, ix, args)
+    ix.close()
+    # a step = a bounded sample of the workload sized so that the whole run ends within a few minutes
+    _, _, _, _, secs = ora.search_batch(queries[:256], K, EF, threads=cores)
+    per_step = int(max(256, min(Q, (256 / max(secs, 1e-9)) * (args.cpu_seconds / max(args.steps, 1)))))
+    for _ in range(args.warmup):
+        ora.search_batch(queries[:per_step], K, EF, threads=cores)
+    total = 0.0
+    last = None
+    for _ in range(args.steps):
+        last = ora.search_batch(queries[:per_step], K, EF, threads=cores)
+        total += last[4]
+    value = args.steps * per_step / total
+    rec = recall_at_k(last[0][:min(rq, per_step)], truth[:min(rq, per_step)])
+    line = {
+        "impl": "reference",
+        "metric": "queries/sec @ recall@10, DBpedia-1M d=768 top-10, 1/2/4/8 B200 vs CPU ref",
+        "value": round(value, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(total / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "recall_at_10": round(rec, 4),
+        "config": {"workload": f"C2: {n}x{dim} f32 {args.metric} HNSW top-10 (m=16, m0=32, ef_construction=200, ef={EF}), "
+                               f"one query per host thread, {per_step} queries per step (bounded sample of the {Q}-query step)",
+                   "graph": "built on the device (setup only), identical adjacency for both arms", "setup": setup},
+        "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} queries per step x {args.steps} steps, {cores} threads"},
+        "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -429,8 +429,9 @@ extern "C" hx_status hx_index_generate_vectors(hx_index* ix, uint64_t first_id, 
   hx_status rc = alloc_vectors(ix, n);
   if (rc || n == 0) return rc;
   const size_t blocks = (n + 7) / 8;
-  k_generate_mixture<<<(unsigned)blocks, 256>>>(ix->d_vec, n, ix->cfg.dimension, ix->ld, seed, n_centroids, sigma, 0,
-                                               0x1111ull);
+  // the global id (not the slot) keys the generator, so id-range shards reproduce the unsharded corpus
+  k_generate_mixture<<<(unsigned)blocks, 256>>>(ix->d_vec, n, ix->cfg.dimension, ix->ld, seed, n_centroids, sigma,
+                                               first_id, 0x1111ull);
   k_iota_ids<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_ids, n, first_id);
   HX_CUDA(cudaGetLastError());
   ix->ids_sorted.resize(n);

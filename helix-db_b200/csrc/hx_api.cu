@@ -791,17 +791,37 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     hx_set_error("query working set %u bytes exceeds shared memory", smem);
     return HX_ERR_INVALID_PARAMETER;
   }
-  // persistent grid: enough CTAs to fill every SM, never more than the queries
-  int per_sm = 4;
-  uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ix->sm_count * per_sm);
+  // Two builds of the same algorithm (bit-identical results):
+  //  * B <  #SMs : one CTA per query (32 octets score a whole neighbour row at once) — lowest latency per query;
+  //  * B >= #SMs : one WARP per query, 8 warps per CTA, up to 32 queries in flight per SM — highest throughput.
+  const uint32_t wpc = HX_HNSW_THREADS / 32;
+  const uint32_t wstride = round_up(smem, 128);
+  const bool latency = B < (size_t)ix->sm_count || (size_t)wpc * wstride > 200 * 1024;
+  uint32_t grid, slots;
+  size_t smem_launch;
   const size_t stride = ((ix->n + 15) / 16) * 16;
-  if (s->stamp_grid < grid || s->stamp_n != ix->n || !s->d_stamps.p) {
-    const uint32_t want = (uint32_t)std::max<size_t>(grid, std::min<size_t>((size_t)ix->sm_count * per_sm, 64));
-    if ((rc = s->d_stamps.reserve((size_t)want * stride))) return rc;
-    if ((rc = s->d_epochs.reserve(want))) return rc;
-    HX_CUDA(cudaMemsetAsync(s->d_stamps.p, 0, (size_t)want * stride, stream));
-    HX_CUDA(cudaMemsetAsync(s->d_epochs.p, 0, want * sizeof(uint32_t), stream));
-    s->stamp_grid = want;
+  if (latency) {
+    grid = (uint32_t)std::min<size_t>(B, (size_t)ix->sm_count * 4);
+    slots = (uint32_t)ix->sm_count * 4;
+    smem_launch = smem;
+  } else {
+    uint32_t ctas_per_sm = 4;
+    while (ctas_per_sm > 1 && (size_t)ctas_per_sm * wpc * wstride > 200 * 1024) ctas_per_sm--;
+    uint32_t max_ctas = (uint32_t)ix->sm_count * ctas_per_sm;
+    // visited stamps cost n bytes per resident query: keep them under ~8 GB
+    const size_t budget = 8ull << 30;
+    while (max_ctas > (uint32_t)ix->sm_count && (size_t)max_ctas * wpc * stride > budget) max_ctas -= (uint32_t)ix->sm_count;
+    grid = (uint32_t)std::min<size_t>((B + wpc - 1) / wpc, max_ctas);
+    slots = (uint32_t)ix->sm_count * ctas_per_sm * wpc;
+    if ((size_t)slots * stride > budget) slots = max_ctas * wpc;
+    smem_launch = (size_t)wpc * wstride;
+  }
+  if (s->stamp_grid < slots || s->stamp_n != ix->n || !s->d_stamps.p) {
+    if ((rc = s->d_stamps.reserve((size_t)slots * stride))) return rc;
+    if ((rc = s->d_epochs.reserve(slots))) return rc;
+    HX_CUDA(cudaMemsetAsync(s->d_stamps.p, 0, (size_t)slots * stride, stream));
+    HX_CUDA(cudaMemsetAsync(s->d_epochs.p, 0, slots * sizeof(uint32_t), stream));
+    s->stamp_grid = slots;
     s->stamp_stride = stride;
     s->stamp_n = ix->n;
   }
@@ -825,23 +845,27 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   a.fr_cap = fr_cap;
   const HxDev dev = ix->dev();
   HX_CUDA(cudaEventRecord(e0, stream));
+#define HX_LAUNCH_HNSW(M)                                                                                          \
+  do {                                                                                                             \
+    if (latency) {                                                                                                 \
+      if (smem_launch > 48 * 1024)                                                                                 \
+        HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                     (int)smem_launch));                                                           \
+      k_hnsw_search<M, 8><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a);                                 \
+    } else {                                                                                                       \
+      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                   (int)smem_launch));                                                             \
+      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 8>, cudaFuncAttributePreferredSharedMemoryCarveout,       \
+                                   cudaSharedmemCarveoutMaxShared));                                               \
+      k_hnsw_search_warp<M, 8><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, wstride);                   \
+    }                                                                                                              \
+  } while (0)
   switch (ix->cfg.metric) {
-    case HX_METRIC_EUCLIDEAN:
-      if (smem > 48 * 1024)
-        HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<HXM_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      k_hnsw_search<HXM_EUCLIDEAN><<<grid, HX_HNSW_THREADS, smem, stream>>>(dev, a);
-      break;
-    case HX_METRIC_COSINE:
-      if (smem > 48 * 1024)
-        HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<HXM_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      k_hnsw_search<HXM_COSINE><<<grid, HX_HNSW_THREADS, smem, stream>>>(dev, a);
-      break;
-    default:
-      if (smem > 48 * 1024)
-        HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<HXM_MANHATTAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      k_hnsw_search<HXM_MANHATTAN><<<grid, HX_HNSW_THREADS, smem, stream>>>(dev, a);
-      break;
+    case HX_METRIC_EUCLIDEAN: HX_LAUNCH_HNSW(HXM_EUCLIDEAN); break;
+    case HX_METRIC_COSINE: HX_LAUNCH_HNSW(HXM_COSINE); break;
+    default: HX_LAUNCH_HNSW(HXM_MANHATTAN); break;
   }
+#undef HX_LAUNCH_HNSW
   HX_CUDA(cudaGetLastError());
   HX_CUDA(cudaEventRecord(e1, stream));
   *timed = true;

@@ -103,7 +103,22 @@ __device__ __forceinline__ float hx_octet_reduce(float4 acc) {
 // 8 threads of an octet (t = 0..7).  Every thread returns the same bits.
 // dim >= 32: euclid_similarity_avx_fma / dot_similarity_avx_fma order (simple_avx.rs:128-238);
 // dim <  32: the scalar loops (simple.rs:204-234), which are exactly the "tail" below with m = 0.
-template <bool IS_DOT>
+// One batch of NB consecutive 32-element chunks: all NB 128-bit loads are issued before the first FMA, so NB*16 bytes
+// per thread are in flight; the FMAs then run in chunk order (the accumulation order is unchanged by NB).
+template <bool IS_DOT, int NB>
+__device__ __forceinline__ void hx_octet_batch(float4& acc, const float4* __restrict__ r4, const float4* __restrict__ q4,
+                                               uint32_t c) {
+  float4 r[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) r[i] = hx_ldg4(r4 + (c + i) * 8);
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const float4 q = q4[(c + i) * 8];
+    if (IS_DOT) { HX_DOT_STEP(acc, q, r[i]) } else { HX_L2_STEP(acc, q, r[i]) }
+  }
+}
+
+template <bool IS_DOT, int NB = 8>
 __device__ __forceinline__ float hx_octet_kernel(const float* __restrict__ row, const float* __restrict__ q,
                                                  uint32_t dim, uint32_t t) {
   const uint32_t chunks = dim >> 5;
@@ -111,26 +126,12 @@ __device__ __forceinline__ float hx_octet_kernel(const float* __restrict__ row, 
   const float4* q4 = reinterpret_cast<const float4*>(q) + t;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t c = 0;
-  for (; c + 8 <= chunks; c += 8) {
-    float4 r0 = hx_ldg4(r4 + (c + 0) * 8), r1 = hx_ldg4(r4 + (c + 1) * 8);
-    float4 r2 = hx_ldg4(r4 + (c + 2) * 8), r3 = hx_ldg4(r4 + (c + 3) * 8);
-    float4 r5 = hx_ldg4(r4 + (c + 4) * 8), r6 = hx_ldg4(r4 + (c + 5) * 8);
-    float4 r7 = hx_ldg4(r4 + (c + 6) * 8), r8 = hx_ldg4(r4 + (c + 7) * 8);
-    float4 q0 = q4[(c + 0) * 8], q1 = q4[(c + 1) * 8], q2 = q4[(c + 2) * 8], q3 = q4[(c + 3) * 8];
-    float4 q5 = q4[(c + 4) * 8], q6 = q4[(c + 5) * 8], q7 = q4[(c + 6) * 8], q8 = q4[(c + 7) * 8];
-    if (IS_DOT) {
-      HX_DOT_STEP(acc, q0, r0) HX_DOT_STEP(acc, q1, r1) HX_DOT_STEP(acc, q2, r2) HX_DOT_STEP(acc, q3, r3)
-      HX_DOT_STEP(acc, q5, r5) HX_DOT_STEP(acc, q6, r6) HX_DOT_STEP(acc, q7, r7) HX_DOT_STEP(acc, q8, r8)
-    } else {
-      HX_L2_STEP(acc, q0, r0) HX_L2_STEP(acc, q1, r1) HX_L2_STEP(acc, q2, r2) HX_L2_STEP(acc, q3, r3)
-      HX_L2_STEP(acc, q5, r5) HX_L2_STEP(acc, q6, r6) HX_L2_STEP(acc, q7, r7) HX_L2_STEP(acc, q8, r8)
-    }
-  }
-  for (; c < chunks; ++c) {
-    float4 r0 = hx_ldg4(r4 + c * 8);
-    float4 q0 = q4[c * 8];
-    if (IS_DOT) { HX_DOT_STEP(acc, q0, r0) } else { HX_L2_STEP(acc, q0, r0) }
-  }
+  for (; c + NB <= chunks; c += NB) hx_octet_batch<IS_DOT, NB>(acc, r4, q4, c);
+  if (NB > 16 && c + 16 <= chunks) { hx_octet_batch<IS_DOT, 16>(acc, r4, q4, c); c += 16; }
+  if (NB > 8 && c + 8 <= chunks) { hx_octet_batch<IS_DOT, 8>(acc, r4, q4, c); c += 8; }
+  if (NB > 4 && c + 4 <= chunks) { hx_octet_batch<IS_DOT, 4>(acc, r4, q4, c); c += 4; }
+  if (NB > 2 && c + 2 <= chunks) { hx_octet_batch<IS_DOT, 2>(acc, r4, q4, c); c += 2; }
+  if (NB > 1 && c < chunks) { hx_octet_batch<IS_DOT, 1>(acc, r4, q4, c); c += 1; }
   float result = hx_octet_reduce(acc);   // all-zero accumulators reduce to +0.0 == the scalar loop's 0.0 start
   const uint32_t m = chunks << 5;
   for (uint32_t i = m; i < dim; ++i) {   // `result += d * d` / `result += a * b`: two roundings, never fused
@@ -223,13 +224,13 @@ __device__ __forceinline__ float hx_cosine_finish(float pq, float qn, float rn, 
 
 // Full metric score of one row for one octet. For Manhattan only thread t==0's value is meaningful
 // work-wise but all threads compute the same sequential sum (callers normally use the per-lane path).
-template <int METRIC>
+template <int METRIC, int NB = 8>
 __device__ __forceinline__ float hx_octet_score(const HxDev& ix, const float* __restrict__ q, float q_hdr,
                                                 uint32_t slot, uint32_t t) {
   const float* row = ix.vec + (size_t)slot * ix.ld;
-  if (METRIC == HXM_EUCLIDEAN) return hx_octet_kernel<false>(row, q, ix.dim, t);
+  if (METRIC == HXM_EUCLIDEAN) return hx_octet_kernel<false, NB>(row, q, ix.dim, t);
   if (METRIC == HXM_COSINE) {
-    float pq = hx_octet_kernel<true>(row, q, ix.dim, t);
+    float pq = hx_octet_kernel<true, NB>(row, q, ix.dim, t);
     return hx_cosine_finish(pq, q_hdr, __ldg(ix.hdr + slot), q, row, ix.dim);
   }
   return hx_manhattan_seq(row, q, ix.dim);

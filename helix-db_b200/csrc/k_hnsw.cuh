@@ -80,7 +80,8 @@ __device__ __forceinline__ void hx_beam_insert(HxBeam& b, uint32_t ef, uint64_t 
   __syncwarp();
 }
 
-template <int METRIC>
+// NB = 128-bit loads in flight per thread while scoring (8: throughput build, 4 CTAs/SM; 24: latency build for small batches)
+template <int METRIC, int NB>
 __global__ void __launch_bounds__(HX_HNSW_THREADS) k_hnsw_search(HxDev ix, HxHnswArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* sq = reinterpret_cast<float*>(smem);                                 // [ld]
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS) k_hnsw_search(HxDev ix, HxHns
       if (METRIC == HXM_MANHATTAN) {
         if (tid == 0) s = hx_manhattan_seq(ix.vec + (size_t)cur * ix.ld, sq, ix.dim);
       } else if (oct == 0) {
-        s = hx_octet_score<METRIC>(ix, sq, q_hdr, cur, t);
+        s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, cur, t);
       }
       if (tid == 0) {
         if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS) k_hnsw_search(HxDev ix, HxHns
             fdist[f] = hx_manhattan_seq(ix.vec + (size_t)row[f] * ix.ld, sq, ix.dim);
         } else {
           for (uint32_t f = oct; f < deg; f += 32) {
-            float s = hx_octet_score<METRIC>(ix, sq, q_hdr, row[f], t);
+            float s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, row[f], t);
             if (t == 0) fdist[f] = s;
           }
         }
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS) k_hnsw_search(HxDev ix, HxHns
           fdist[f] = hx_manhattan_seq(ix.vec + (size_t)frontier[f] * ix.ld, sq, ix.dim);
       } else {
         for (uint32_t f = oct; f < nf; f += 32) {
-          float s = hx_octet_score<METRIC>(ix, sq, q_hdr, frontier[f], t);
+          float s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, frontier[f], t);
           if (t == 0) fdist[f] = s;
         }
       }
@@ -340,5 +341,242 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS) k_hnsw_search(HxDev ix, HxHns
       }
     }
     __syncthreads();
+  }
+}
+
+// ---- warp-per-query variant (throughput) ---------------------------------------------------------------------------
+// A layer-0 expansion of a converged beam discovers only a handful of unvisited neighbours, so a 256-thread CTA per
+// query leaves most octets idle and — at 4 CTAs per SM — keeps only 4 dependent pointer chases in flight per SM.  Here
+// every WARP owns one query (its 4 octets score 4 neighbours per round), 8 warps per CTA, up to 32 queries in flight per
+// SM: enough independent row fetches to cover HBM latency.  Same algorithm, same order of every float operation and of
+// every admission as k_hnsw_search; __syncthreads became __syncwarp.  `wstride` = shared-memory bytes per warp.
+template <int METRIC, int NB>
+__global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev ix, HxHnswArgs a, uint32_t wstride) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, t = lane & 7u, oct = lane >> 3;
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  const uint32_t gw = blockIdx.x * warps_per_cta + warp;          // global warp id == stamp slot
+  const uint32_t total_warps = gridDim.x * warps_per_cta;
+  unsigned char* wmem = smem + (size_t)warp * wstride;
+  float* sq = reinterpret_cast<float*>(wmem);                                  // [ld]
+  uint64_t* beam_mem = reinterpret_cast<uint64_t*>(wmem + (size_t)ix.ld * 4);  // [ef]
+  uint64_t* tie = beam_mem + a.ef;                                             // [HX_TIE_CAP]
+  uint32_t* frontier = reinterpret_cast<uint32_t*>(tie + HX_TIE_CAP);          // [fr_cap]
+  float* fdist = reinterpret_cast<float*>(frontier + a.fr_cap);               // [fr_cap]
+  uint8_t* stamp = a.stamps + (size_t)gw * a.stamp_stride;
+  const unsigned FULL = 0xffffffffu;
+
+  for (uint32_t qi = gw; qi < a.B; qi += total_warps) {
+    if (a.q_status[qi] != 0u || !ix.populated) {
+      if (lane == 0) a.out_counts[qi] = 0;
+      continue;
+    }
+    const float q_hdr = a.q_hdr[qi];
+    for (uint32_t i = lane; i < ix.ld; i += 32) sq[i] = i < ix.dim ? a.queries[(size_t)qi * ix.dim + i] : 0.0f;
+    uint32_t epoch = 0;
+    if (lane == 0) epoch = a.epochs[gw] + 1u;
+    epoch = __shfl_sync(FULL, epoch, 0);
+    if (epoch >= 256u) {
+      uint4* s4 = reinterpret_cast<uint4*>(stamp);
+      const size_t n16 = a.stamp_stride >> 4;
+      for (size_t i = lane; i < n16; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+      epoch = 1u;
+    }
+    __syncwarp();
+    if (lane == 0) a.epochs[gw] = epoch;
+    const uint8_t ep8 = (uint8_t)epoch;
+
+    // ---- entry point
+    uint32_t cur = ix.entry_slot;
+    float cur_dist = 0.f;
+    {
+      float s = 0.f;
+      if (METRIC == HXM_MANHATTAN) {
+        if (lane == 0) s = hx_manhattan_seq(ix.vec + (size_t)cur * ix.ld, sq, ix.dim);
+      } else if (oct == 0) {
+        s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, cur, t);
+      }
+      s = __shfl_sync(FULL, s, 0);
+      if (!hx_score_ok(s) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+      cur_dist = s;
+    }
+    uint32_t upper_steps = 0;
+
+    // ---- upper layers: greedy descent (search.rs:169-224)
+    for (int layer = ix.max_layer; layer >= 1; --layer) {
+      for (;;) {
+        uint32_t deg = 0;
+        const uint32_t* row = nullptr;
+        {
+          const uint32_t off = ix.upper_off[cur];
+          if (off != HX_ABSENT && (int)ix.level[cur] >= layer) {
+            deg = ix.upper_deg[off + (uint32_t)layer - 1u];
+            row = ix.upper_nbr + (size_t)(off + (uint32_t)layer - 1u) * ix.stride_u;
+          }
+        }
+        if (METRIC == HXM_MANHATTAN) {
+          for (uint32_t f = lane; f < deg; f += 32) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)row[f] * ix.ld, sq, ix.dim);
+        } else {
+          for (uint32_t f = oct; f < deg; f += 4) {
+            float s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, row[f], t);
+            if (t == 0) fdist[f] = s;
+          }
+        }
+        __syncwarp();
+        float best = cur_dist;
+        uint32_t best_i = HX_ABSENT;
+        bool bad = false;
+        for (uint32_t base = 0; base < deg; base += 32) {
+          uint32_t f = base + lane;
+          float s = f < deg ? fdist[f] : __int_as_float(0x7f800000);
+          if (f < deg && !hx_score_ok(s)) bad = true;
+          float m = s;
+          uint32_t mi = f;
+          for (int o = 16; o > 0; o >>= 1) {
+            float om = __shfl_xor_sync(FULL, m, o);
+            uint32_t oi = __shfl_xor_sync(FULL, mi, o);
+            if (om < m || (om == m && oi < mi)) { m = om; mi = oi; }
+          }
+          if (m < best) { best = m; best_i = mi; }
+        }
+        if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+        __syncwarp();
+        if (best_i == HX_ABSENT) break;
+        cur = row[best_i];
+        cur_dist = best;
+        upper_steps++;
+      }
+    }
+
+    // ---- layer 0: beam search
+    HxBeam beam{beam_mem, 1u};
+    uint32_t tie_len = 0, dropped = 0;
+    uint32_t st_steps = 0, st_examined = 0, st_dc = 1;
+    if (lane == 0) {
+      beam_mem[0] = hx_make_key(cur_dist, cur << 1);
+      stamp[cur] = ep8;
+    }
+    __syncwarp();
+    for (;;) {
+      uint32_t first = HX_ABSENT;
+      for (uint32_t i = lane; i < beam.len; i += 32)
+        if (!(beam_mem[i] & 1ull)) { first = i; break; }
+      first = hx_warp_min(first);
+      uint32_t cur_slot = HX_ABSENT;
+      if (first != HX_ABSENT) {
+        uint64_t key = beam_mem[first];
+        __syncwarp();
+        if (lane == 0) beam_mem[first] = key | 1ull;
+        cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
+        st_steps++;
+      } else if (tie_len > 0) {
+        uint64_t key = tie[tie_len - 1];
+        tie_len--;
+        cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
+        st_steps++;
+      } else if (dropped) {
+        st_steps++;
+      }
+      if (cur_slot == HX_ABSENT) break;
+      uint32_t nf = 0;
+      {
+        const uint32_t deg = ix.deg0[cur_slot];
+        st_examined += ix.raw0[cur_slot];
+        const uint32_t* row = ix.nbr0 + (size_t)cur_slot * ix.stride0;
+        for (uint32_t base = 0; base < deg; base += 32) {
+          const uint32_t i = base + lane;
+          uint32_t nb = 0;
+          bool fresh = false;
+          if (i < deg) {
+            nb = row[i];
+            fresh = stamp[nb] != ep8;
+          }
+          const uint32_t mask = __ballot_sync(FULL, fresh);
+          if (fresh) {
+            frontier[nf + __popc(mask & ((1u << lane) - 1u))] = nb;
+            stamp[nb] = ep8;
+          }
+          nf += __popc(mask);
+        }
+        st_dc += nf;
+      }
+      __syncwarp();
+      if (METRIC == HXM_MANHATTAN) {
+        for (uint32_t f = lane; f < nf; f += 32) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)frontier[f] * ix.ld, sq, ix.dim);
+      } else {
+        for (uint32_t f = oct; f < nf; f += 4) {
+          float s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, frontier[f], t);
+          if (t == 0) fdist[f] = s;
+        }
+      }
+      __syncwarp();
+      for (uint32_t base = 0; base < nf; base += 32) {
+        const uint32_t f = base + lane;
+        float s = f < nf ? fdist[f] : 0.f;
+        uint32_t sbits = 0;
+        bool pass = false;
+        if (f < nf) {
+          if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+          sbits = __float_as_uint(s);
+          const uint32_t wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
+          pass = (sbits < wmax) || (beam.len < a.ef);
+        }
+        uint32_t mask = __ballot_sync(FULL, pass);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const uint32_t xb = __shfl_sync(FULL, sbits, src);
+          const uint32_t xslot = __shfl_sync(FULL, f < nf ? frontier[f] : 0u, src);
+          const uint32_t wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
+          if (!((xb < wmax) || (beam.len < a.ef))) continue;
+          const uint32_t old_wmax = wmax;
+          const bool was_full = beam.len == a.ef;
+          uint64_t ev;
+          hx_beam_insert(beam, a.ef, ((uint64_t)xb << 32) | ((uint64_t)xslot << 1), &ev, lane);
+          if (lane == 0) {
+            hx_prefetch_l2(ix.nbr0 + (size_t)xslot * ix.stride0);
+            hx_prefetch_l2(ix.deg0 + xslot);
+          }
+          if (was_full) {
+            const uint32_t new_wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
+            if (new_wmax < old_wmax && tie_len) { dropped = 1; tie_len = 0; }
+            if (!(ev & 1ull)) {
+              if ((uint32_t)(ev >> 32) == new_wmax) {
+                if (tie_len < HX_TIE_CAP) {
+                  if (lane == 0) tie[tie_len] = ev;
+                  tie_len++;
+                } else {
+                  if (lane == 0) atomicOr(a.err_flags, HXF_TIE_OVERFLOW);
+                  dropped = 1;
+                }
+              } else {
+                dropped = 1;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- results
+    const uint32_t len = beam.len;
+    const uint32_t cnt = len < a.k ? len : a.k;
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint64_t key = beam_mem[i];
+      a.out_ids[(size_t)qi * a.k + i] = ix.ids[(uint32_t)(key & 0xffffffffu) >> 1];
+      a.out_scores[(size_t)qi * a.k + i] = hx_key_score(key);
+    }
+    if (lane == 0) {
+      a.out_counts[qi] = cnt;
+      if (a.q_stats) {
+        a.q_stats[(size_t)qi * 4 + 0] = st_steps;
+        a.q_stats[(size_t)qi * 4 + 1] = st_examined;
+        a.q_stats[(size_t)qi * 4 + 2] = st_dc;
+        a.q_stats[(size_t)qi * 4 + 3] = upper_steps;
+      }
+    }
+    __syncwarp();
   }
 }

@@ -319,27 +319,14 @@ def run_ours(args):
         # every rank searches the SAME queries (rank 0's sets) against its shard
         sq = [ix.generate_queries(SEED, Q, first_query=s * Q, n_centroids=N_CENTROIDS, sigma=SIGMA) for s in range(n_sets)]
         d_sq = [torch.from_numpy(q).to(dev) for q in sq]
-        l_ids = torch.zeros((Q, k), dtype=torch.int64, device=dev)
-        l_sc = torch.zeros((Q, k), dtype=torch.float32, device=dev)
-        l_cnt = torch.zeros((Q,), dtype=torch.int32, device=dev)
-        a_ids = torch.zeros((world, Q, k), dtype=torch.int64, device=dev)
-        a_sc = torch.zeros((world, Q, k), dtype=torch.float32, device=dev)
-        a_cnt = torch.zeros((world, Q), dtype=torch.int32, device=dev)
-        # one collective: ids, scores and counts travel in ONE packed buffer (12*k+4 bytes per query per shard)
-        pack = torch.zeros((Q, 3 * k + 1), dtype=torch.int32, device=dev)
-        apack = torch.zeros((world, Q, 3 * k + 1), dtype=torch.int32, device=dev)
+        from importlib import import_module
+        sharding = import_module("helix_db_b200.sharding")
+        searcher = sharding.ShardedSearcher(hx, sx, world, rank, Q, k, dev)
 
         def step_sharded(s):
-            sx.search_device(d_sq[s].data_ptr(), Q, params, l_ids.data_ptr(), l_sc.data_ptr(), l_cnt.data_ptr(), stream)
-            pack[:, :2 * k] = l_ids.view(torch.int32).view(Q, 2 * k)
-            pack[:, 2 * k:3 * k] = l_sc.view(torch.int32)
-            pack[:, 3 * k] = l_cnt
-            dist.all_gather_into_tensor(apack, pack)
-            a_ids.copy_(apack[:, :, :2 * k].contiguous().view(torch.int64).view(world, Q, k))
-            a_sc.copy_(apack[:, :, 2 * k:3 * k].contiguous().view(torch.float32))
-            a_cnt.copy_(apack[:, :, 3 * k])
-            hx.merge_topk_device(local_rank, a_ids.data_ptr(), a_sc.data_ptr(), a_cnt.data_ptr(), world, Q, k,
-                                 o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+            # local search -> ONE packed all-gather (12*k+4 bytes per query per shard) -> (score,id) merge kernel
+            ids_, sc_, cnt_ = searcher.step(d_sq[s], params, stream)
+            o_ids.copy_(ids_)
 
         truth_s = exact_topk_device(hx, torch, ix, sq[0][:rq], n, 0, k)
         step_sharded(0)

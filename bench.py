@@ -34,9 +34,18 @@ sys.path.insert(0, str(ROOT))
 
 SEED = 0x0DB9ED1A
 N_CENTROIDS = 1024
-SIGMA = 0.3
 K = 10
 EF = 100
+# Synthetic corpus recipes (no network => no DBpedia download):
+#  "embedding" (default): 1024-component Gaussian mixture in a 32-d latent space (sigma 1.0: overlapping clusters) pushed
+#      through a fixed random 768x32 projection + 2 % isotropic noise, unit-normalised.  Intrinsic dimension ~32 like real
+#      sentence embeddings; HNSW (m=16, ef=100) reaches recall@10 ~0.97 on it, as it does on DBpedia-OpenAI-1M.
+#  "survey": SURVEY §8(d)'s literal example — 1024 isolated isotropic clusters in full 768-d (sigma 0.3).  Its landscape is
+#      flat between clusters, so ANY greedy HNSW descent (reference algorithm included) lands in a wrong cluster for ~7 %
+#      of the queries at 1M (profiles/r01_recall_diag_survey_mixture.json): recall@10 0.89 at ef=100, 0.91 at ef=200.
+RECIPES = {"embedding": dict(kind=32, sigma=1.0), "survey": dict(kind=0, sigma=0.3)}
+KIND = 32
+SIGMA = 1.0
 
 
 def parse():
@@ -54,7 +63,11 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--workload", default="hnsw", choices=["hnsw", "prefilter"])
-    return ap.parse_args()
+    ap.add_argument("--recipe", default="embedding", choices=sorted(RECIPES))
+    a = ap.parse_args()
+    global KIND, SIGMA
+    KIND, SIGMA = RECIPES[a.recipe]["kind"], RECIPES[a.recipe]["sigma"]
+    return a
 
 
 class ClockSampler:
@@ -135,7 +148,7 @@ def build_index(hx, args, device, first_id, n, storage=0):
     cfg = hx.VectorIndexConfig("dbpedia_1m_synthetic", "embedding", args.dim)   # m=16, m0=32, ef_c=200 defaults
     ix = hx.VectorIndex(metric, cfg, device=device, storage=storage)
     t0 = time.perf_counter()
-    ix.generate_vectors(first_id, n, SEED, N_CENTROIDS, SIGMA)
+    ix.generate_vectors(first_id, n, SEED, N_CENTROIDS, SIGMA, KIND)
     t1 = time.perf_counter()
     ix.build(seed=SEED)
     t2 = time.perf_counter()
@@ -212,7 +225,7 @@ def run_ours(args):
     ix, setup = build_index(hx, args, local_rank, 0, n)
     n_sets = args.steps + args.warmup
     # distinct queries every step and every rank (nothing can be answered from a previous step's cache lines)
-    qsets = [ix.generate_queries(SEED, Q, first_query=(rank * n_sets + s) * Q, n_centroids=N_CENTROIDS, sigma=SIGMA)
+    qsets = [ix.generate_queries(SEED, Q, first_query=(rank * n_sets + s) * Q, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
              for s in range(n_sets)]
     params = hx.SearchParams.strict(k, EF)
     d_q = [torch.from_numpy(q).to(dev) for q in qsets]
@@ -317,7 +330,7 @@ def run_ours(args):
         lo, hi = rank * n // world, (rank + 1) * n // world
         sx, s_setup = build_index(hx, args, local_rank, lo, hi - lo)
         # every rank searches the SAME queries (rank 0's sets) against its shard
-        sq = [ix.generate_queries(SEED, Q, first_query=s * Q, n_centroids=N_CENTROIDS, sigma=SIGMA) for s in range(n_sets)]
+        sq = [ix.generate_queries(SEED, Q, first_query=s * Q, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND) for s in range(n_sets)]
         d_sq = [torch.from_numpy(q).to(dev) for q in sq]
         from importlib import import_module
         sharding = import_module("helix_db_b200.sharding")
@@ -369,7 +382,9 @@ def run_ours(args):
                 f"{world} full replicas, queries partitioned, no data-path collective",
                 "l2": "corpus 3.07 GB >> 126 MB L2; distinct queries every step and rank",
                 "graph": "built on the device (hx_index_build), identical adjacency mirrored into the CPU oracle",
-                "data_recipe": f"unit-normalised Gaussian mixture, {N_CENTROIDS} centroids, sigma={SIGMA}, seed=0x0DB9ED1A",
+                "data_recipe": (f"{args.recipe}: unit-normalised {N_CENTROIDS}-component Gaussian mixture, sigma={SIGMA}, "
+                                + (f"rank-{KIND} latent space -> fixed random projection to {dim}-d + 2% noise"
+                                   if KIND else f"isolated isotropic clusters in {dim}-d") + ", seed=0x0DB9ED1A"),
                 "setup": setup,
             },
             "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4,
@@ -440,7 +455,7 @@ def run_reference(args):
     n, dim, Q = args.n, args.dim, args.queries_per_step
     ix, setup = build_index(hx, args, 0, 0, n)
     cores = os.cpu_count() or 1
-    queries = ix.generate_queries(SEED, Q, first_query=0, n_centroids=N_CENTROIDS, sigma=SIGMA)
+    queries = ix.generate_queries(SEED, Q, first_query=0, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
     rq = min(args.recall_queries, Q)
     truth = exact_topk_device(hx, torch, ix, queries[:rq], n, 0, K)
     ora = oracle_from_device(hxo, ix, args)

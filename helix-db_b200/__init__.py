@@ -134,9 +134,9 @@ def load_library():
     L.hx_index_load_vectors.restype = C.c_int32
     L.hx_index_load_vectors.argtypes = [vp, u64p, fp, sz]
     L.hx_index_generate_vectors.restype = C.c_int32
-    L.hx_index_generate_vectors.argtypes = [vp, C.c_uint64, sz, C.c_uint64, C.c_uint32, C.c_float]
+    L.hx_index_generate_vectors.argtypes = [vp, C.c_uint64, sz, C.c_uint64, C.c_uint32, C.c_float, C.c_uint32]
     L.hx_generate_queries.restype = C.c_int32
-    L.hx_generate_queries.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_float, C.c_uint64, sz, fp]
+    L.hx_generate_queries.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_float, C.c_uint64, sz, fp, C.c_uint32]
     L.hx_index_download_vectors.restype = C.c_int32
     L.hx_index_download_vectors.argtypes = [vp, sz, sz, fp, u64p]
     L.hx_index_load_graph.restype = C.c_int32
@@ -365,13 +365,13 @@ class VectorIndex:
             raise HelixDbError(HX_ERR_INVALID_DIMENSION, f"expected {ia.size}x{self.dim} floats, got {ra.size}")
         _ck(self.L.hx_index_load_vectors(self.h, ip, rp, ia.size))
 
-    def generate_vectors(self, first_id, n, seed, n_centroids=1024, sigma=0.3):
-        _ck(self.L.hx_index_generate_vectors(self.h, first_id, n, seed, n_centroids, sigma))
+    def generate_vectors(self, first_id, n, seed, n_centroids=1024, sigma=0.3, kind=0):
+        _ck(self.L.hx_index_generate_vectors(self.h, first_id, n, seed, n_centroids, sigma, kind))
 
-    def generate_queries(self, seed, n, first_query=0, n_centroids=1024, sigma=0.3):
+    def generate_queries(self, seed, n, first_query=0, n_centroids=1024, sigma=0.3, kind=0):
         out = np.empty((n, self.dim), dtype=np.float32)
         _ck(self.L.hx_generate_queries(self.h, seed, n_centroids, sigma, first_query, n,
-                                       out.ctypes.data_as(C.POINTER(C.c_float))))
+                                       out.ctypes.data_as(C.POINTER(C.c_float)), kind))
         return out
 
     def download_vectors(self, first_slot, n):

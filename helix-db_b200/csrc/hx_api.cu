@@ -421,17 +421,47 @@ extern "C" hx_status hx_index_load_vectors(hx_index* ix, const uint64_t* ids, co
   return HX_OK;
 }
 
+// kind 0: isolated isotropic clusters in full dimension (SURVEY §8d recipe); kind r in 2..64: rank-r latent mixture
+static hx_status launch_generator(hx_index* ix, float* d_out, size_t count, size_t ld, uint64_t seed,
+                                  uint32_t n_centroids, float sigma, uint64_t first_index, uint64_t tag, uint32_t kind) {
+  const uint32_t dim = ix->cfg.dimension;
+  if (kind == 0) {
+    k_generate_mixture<<<(unsigned)((count + 7) / 8), 256>>>(d_out, count, dim, ld, seed, n_centroids, sigma,
+                                                           first_index, tag);
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+  }
+  if (kind < 2 || kind > 64) {
+    hx_set_error("generator kind must be 0 or a latent rank in 2..64");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  float* d_A = nullptr;
+  HX_CUDA(cudaMalloc((void**)&d_A, (size_t)dim * kind * sizeof(float)));
+  k_generate_proj<<<(dim * kind + 255) / 256, 256>>>(d_A, dim, kind, seed);
+  k_generate_latent<<<(unsigned)((count + 7) / 8), 256>>>(d_out, count, dim, ld, seed, n_centroids, sigma, first_index,
+                                                         tag, d_A, kind, 0.02f);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(d_A);
+  if (e != cudaSuccess) {
+    hx_set_error("generator failed: %s", cudaGetErrorString(e));
+    return HX_ERR_CUDA;
+  }
+  return HX_OK;
+}
+
 extern "C" hx_status hx_index_generate_vectors(hx_index* ix, uint64_t first_id, size_t n, uint64_t seed,
-                                               uint32_t n_centroids, float sigma) {
+                                               uint32_t n_centroids, float sigma, uint32_t kind) {
   if (!ix) return HX_ERR_INDEX_NOT_FOUND;
   if (n_centroids == 0) return HX_ERR_INVALID_PARAMETER;
   HX_CUDA(cudaSetDevice(ix->device));
   hx_status rc = alloc_vectors(ix, n);
   if (rc || n == 0) return rc;
-  const size_t blocks = (n + 7) / 8;
   // the global id (not the slot) keys the generator, so id-range shards reproduce the unsharded corpus
-  k_generate_mixture<<<(unsigned)blocks, 256>>>(ix->d_vec, n, ix->cfg.dimension, ix->ld, seed, n_centroids, sigma,
-                                               first_id, 0x1111ull);
+  if ((rc = launch_generator(ix, ix->d_vec, n, ix->ld, seed, n_centroids, sigma, first_id, 0x1111ull, kind))) {
+    ix->free_vectors();
+    return rc;
+  }
   k_iota_ids<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_ids, n, first_id);
   HX_CUDA(cudaGetLastError());
   ix->ids_sorted.resize(n);
@@ -444,7 +474,7 @@ extern "C" hx_status hx_index_generate_vectors(hx_index* ix, uint64_t first_id, 
 }
 
 extern "C" hx_status hx_generate_queries(hx_index* ix, uint64_t seed, uint32_t n_centroids, float sigma,
-                                         uint64_t first_query, size_t n_queries, float* out_host) {
+                                         uint64_t first_query, size_t n_queries, float* out_host, uint32_t kind) {
   if (!ix) return HX_ERR_INDEX_NOT_FOUND;
   if (!out_host || n_centroids == 0) return HX_ERR_INVALID_PARAMETER;
   if (n_queries == 0) return HX_OK;
@@ -452,8 +482,11 @@ extern "C" hx_status hx_generate_queries(hx_index* ix, uint64_t seed, uint32_t n
   float* d = nullptr;
   const uint32_t dim = ix->cfg.dimension;
   HX_CUDA(cudaMalloc((void**)&d, n_queries * (size_t)ix->ld * sizeof(float)));
-  k_generate_mixture<<<(unsigned)((n_queries + 7) / 8), 256>>>(d, n_queries, dim, ix->ld, seed, n_centroids, sigma,
-                                                              first_query, 0x2222ull);
+  hx_status grc = launch_generator(ix, d, n_queries, ix->ld, seed, n_centroids, sigma, first_query, 0x2222ull, kind);
+  if (grc) {
+    cudaFree(d);
+    return grc;
+  }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpy2D(out_host, (size_t)dim * sizeof(float), d, (size_t)ix->ld * sizeof(float),

@@ -18,6 +18,7 @@
 // build is not claimed; structural invariants and recall are tested instead.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -630,7 +631,11 @@ hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed) 
   HX_CUDA(cudaMemcpy(ix->d_level, level.data(), n, cudaMemcpyHostToDevice));
   // ---- build-only state ----------------------------------------------------------------------------------------------
   const size_t urows = n + rows;
-  const uint32_t max_batch = (uint32_t)std::min<size_t>(16384, std::max<size_t>(1, n / 64));
+  uint32_t max_batch = (uint32_t)std::min<size_t>(16384, std::max<size_t>(1, n / 64));
+  if (const char* env = getenv("HX_BUILD_MAX_BATCH")) {   // experiment knob: rounds never exceed this many nodes
+    const long v = atol(env);
+    if (v > 0) max_batch = (uint32_t)std::min<long>(v, 65536);
+  }
   const uint32_t maxL_all = (uint32_t)top;
   const uint32_t pstride = lim0 + maxL_all * m;
   const uint32_t rstride = std::max(lim0, m);

@@ -79,6 +79,53 @@ __global__ void k_generate_mixture(float* __restrict__ out, size_t count, uint32
   for (uint32_t j = dim + lane; j < ld; j += 32) row[j] = 0.f;
 }
 
+// Embedding-like corpus: a Gaussian mixture in an r-dimensional latent space (overlapping clusters), pushed through a
+// fixed random projection A[dim][r] plus a little isotropic noise, then unit-normalised.  Unlike isolated isotropic
+// clusters in 768-d (intrinsic dimension 768, where every graph index degrades), this has intrinsic dimension ~r,
+// like real sentence/document embeddings.  One warp per row; requires r <= 64.
+__global__ void k_generate_proj(float* __restrict__ A, uint32_t dim, uint32_t r, uint64_t seed) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dim * r) A[i] = hx_gauss(seed * 0x9e3779b97f4a7c15ull + 0x7777000000000000ull + i) * rsqrtf((float)r);
+}
+__global__ void k_generate_latent(float* __restrict__ out, size_t count, uint32_t dim, size_t ld, uint64_t seed,
+                                  uint32_t n_centroids, float sigma, uint64_t first_index, uint64_t stream_tag,
+                                  const float* __restrict__ A, uint32_t r, float eps) {
+  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (w >= count) return;
+  const uint64_t gi = first_index + w;
+  const uint64_t c = hx_mix64(seed ^ hx_mix64(gi * 0x9e3779b97f4a7c15ull + stream_tag)) % n_centroids;
+  // latent coordinates: lane holds z[lane] and z[lane+32]
+  float z0 = 0.f, z1 = 0.f;
+  if (lane < r)
+    z0 = hx_gauss(seed * 0x100000001b3ull + (c << 20) + lane + 0x5555000000000000ull) +
+         sigma * hx_gauss(hx_mix64(seed + stream_tag) ^ (gi * 0xd1342543de82ef95ull + lane));
+  if (lane + 32 < r)
+    z1 = hx_gauss(seed * 0x100000001b3ull + (c << 20) + lane + 32 + 0x5555000000000000ull) +
+         sigma * hx_gauss(hx_mix64(seed + stream_tag) ^ (gi * 0xd1342543de82ef95ull + lane + 32));
+  float* row = out + w * ld;
+  float ss = 0.f;
+  for (uint32_t j = lane; j < ((dim + 31) / 32) * 32; j += 32) {
+    float x = 0.f;
+    const float* a = A + (size_t)(j < dim ? j : 0) * r;
+    for (uint32_t k = 0; k < r; ++k) {
+      const float zk = __shfl_sync(0xffffffffu, k < 32 ? z0 : z1, k & 31);
+      x += a[k] * zk;
+    }
+    if (j < dim) {
+      x += eps * hx_gauss(hx_mix64(seed + stream_tag + 0x33) ^ (gi * 0x2545f4914f6cdd1dull + j));
+      row[j] = x;
+      ss += x * x;
+    }
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+  for (uint32_t j = lane; j < dim; j += 32) row[j] *= inv;
+  for (uint32_t j = dim + lane; j < ld; j += 32) row[j] = 0.f;
+}
+
 __global__ void k_iota_ids(uint64_t* ids, size_t n, uint64_t first) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ids[i] = first + i;

@@ -131,13 +131,16 @@ void      hx_index_destroy(hx_index* idx);
  * cosine.  Replaces any previous contents. */
 hx_status hx_index_load_vectors(hx_index* idx, const uint64_t* ids, const float* rows, size_t n);
 
-/* Generate vectors on the device instead (bench only; no PCIe copy):
- * kind 0 = unit-normalised Gaussian mixture, ids = first_id..first_id+n-1.
- * Queries for the same mixture: hx_generate_queries. */
+/* Generate unit-normalised synthetic vectors on the device instead (bench only; no PCIe copy),
+ * ids = first_id..first_id+n-1, keyed by the global id so id-range shards reproduce the corpus.
+ * kind 0      : isolated isotropic Gaussian clusters in full dimension (the SURVEY §8d recipe);
+ * kind r=2..64: Gaussian mixture in an r-dimensional latent space pushed through a fixed random
+ *               projection (+2 % isotropic noise): intrinsic dimension ~r, like real embeddings.
+ * Queries from the same distribution: hx_generate_queries. */
 hx_status hx_index_generate_vectors(hx_index* idx, uint64_t first_id, size_t n, uint64_t seed,
-                                    uint32_t n_centroids, float sigma);
+                                    uint32_t n_centroids, float sigma, uint32_t kind);
 hx_status hx_generate_queries(hx_index* idx, uint64_t seed, uint32_t n_centroids, float sigma,
-                              uint64_t first_query, size_t n_queries, float* out_host);
+                              uint64_t first_query, size_t n_queries, float* out_host, uint32_t kind);
 /* Copy rows [first_slot, first_slot+n) (slot order) back to the host (f32, n*dimension). */
 hx_status hx_index_download_vectors(hx_index* idx, size_t first_slot, size_t n, float* out_rows,
                                     uint64_t* out_ids);

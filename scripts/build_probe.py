@@ -19,14 +19,14 @@ for n in [int(x) for x in (sys.argv[1:] or ["20000", "100000"])]:
     a = A()
     a.metric, a.dim = "cosine", 768
     ix = hx.VectorIndex(hx.Metric.Cosine, hx.VectorIndexConfig("p", "embedding", 768))
-    ix.generate_vectors(0, n, bench.SEED, bench.N_CENTROIDS, bench.SIGMA)
+    ix.generate_vectors(0, n, bench.SEED, bench.N_CENTROIDS, bench.SIGMA, bench.KIND)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ix.build(seed=bench.SEED)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     gi = ix.graph_info()
-    q = ix.generate_queries(bench.SEED, 256)
+    q = ix.generate_queries(bench.SEED, 256, n_centroids=bench.N_CENTROIDS, sigma=bench.SIGMA, kind=bench.KIND)
     truth = bench.exact_topk_device(hx, torch, ix, q, n, 0, 10)
     res = {"n": n, "build_s": round(build_s, 2), "max_layer": gi["max_layer"]}
     for ef in (50, 100, 200):

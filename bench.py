@@ -437,6 +437,148 @@ def cpu_baseline(args, ix, queries, truth):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_prefilter(args):
+    """Config C3: 1M x 768 prefiltered top-10 (graph-label filter), exact brute-force scan path, single B200.
+
+    A step = 100 queries, query b restricted to the label set {id : id mod 100 == b} (10 000 candidates = 1 % of the
+    corpus each), so one step reads every row of the 3.07 GB corpus exactly once (>> 126 MB L2)."""
+    import ctypes as C
+
+    import torch
+
+    import helix_db_b200 as hx
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    n, dim, k, sel = args.n, args.dim, K, 100
+    B = sel
+    hbm_peak, peak_src = measured_peaks()
+    metric = hx.Metric.Cosine if args.metric == "cosine" else hx.Metric.Euclidean
+    ix = hx.VectorIndex(metric, hx.VectorIndexConfig("dbpedia_1m_synthetic", "embedding", dim), device=local_rank)
+    ix.generate_vectors(0, n, SEED, N_CENTROIDS, SIGMA, KIND)
+    ix.load_graph(0, np.array([0], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
+    ix.set_entry(0, 0)
+    n_sets = args.steps + args.warmup
+    qsets = [ix.generate_queries(SEED, B, first_query=(rank * n_sets + s) * B, n_centroids=N_CENTROIDS, sigma=SIGMA,
+                                 kind=KIND) for s in range(n_sets)]
+    cand_lists = [np.arange(b, n, sel, dtype=np.uint64) for b in range(B)]
+    cand_ids = np.concatenate(cand_lists)
+    offs = np.zeros(B + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(c) for c in cand_lists])
+    per_q = int(max(len(c) for c in cand_lists))
+    total = int(offs[-1])
+    d_slots = torch.from_numpy(cand_ids.astype(np.uint32).view(np.int32)).to(dev)      # ids == slots here (first_id 0)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    d_q = [torch.from_numpy(q).to(dev) for q in qsets]
+    o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
+    o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    params = hx.SearchParams.strict(k)
+
+    def step_device(s):
+        ix.search_restricted_device(d_q[s].data_ptr(), B, params, d_slots.data_ptr(), d_offs.data_ptr(), total, per_q,
+                                    o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+
+    for s in range(args.warmup):
+        step_device(s)
+    torch.cuda.synchronize(dev)
+    ix.last_kernel_ms()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    kms, kl = ix.last_kernel_ms()
+    value = args.steps * B / (ms_total / 1e3)
+    bytes_per_launch = total * (4 * dim + (4 if args.metric == "cosine" else 0))
+    kernel_ms = kms / max(kl, 1)
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    dev_ids = o_ids.cpu().numpy().view(np.uint64).copy()
+    dev_sc = o_sc.cpu().numpy().copy()
+
+    # e2e: candidate ids, offsets and queries in pinned host memory -> hx_search_restricted_multi -> host results
+    L = hx.load_library()
+    cp = params._c()
+    h_q = [torch.from_numpy(q).pin_memory() for q in qsets]
+    h_c = torch.from_numpy(cand_ids.view(np.int64)).pin_memory()
+    h_o = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    h_ids = torch.zeros((B, k), dtype=torch.int64).pin_memory()
+    h_sc = torch.zeros((B, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.zeros((B,), dtype=torch.int32).pin_memory()
+
+    def step_host(s):
+        rc = L.hx_search_restricted_multi(ix.h, C.cast(h_q[s].data_ptr(), C.POINTER(C.c_float)), B, C.byref(cp),
+                                          C.cast(h_c.data_ptr(), C.POINTER(C.c_uint64)),
+                                          C.cast(h_o.data_ptr(), C.POINTER(C.c_uint64)),
+                                          C.cast(h_ids.data_ptr(), C.POINTER(C.c_uint64)),
+                                          C.cast(h_sc.data_ptr(), C.POINTER(C.c_float)),
+                                          C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None)
+        if rc != 0:
+            raise RuntimeError(L.hx_last_error().decode())
+
+    for s in range(args.warmup):
+        step_host(s)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_host(args.warmup + s)
+    t1 = time.perf_counter()
+    e2e_value = args.steps * B / (t1 - t0)
+    same = bool(h_ids.numpy().view(np.uint64).tolist() == dev_ids.tolist() and h_sc.numpy().tobytes() == dev_sc.tobytes())
+
+    cpu = None
+    if not args.no_cpu and rank == 0:
+        from oracle import hxo
+        om = hxo.COSINE if args.metric == "cosine" else hxo.EUCLIDEAN
+        ora = hxo.Index(om, dim)
+        for lo in range(0, n, 65536):
+            ids_, rows_ = ix.download_vectors(lo, min(65536, n - lo))
+            ora.put_vectors(ids_, rows_)
+        ora.set_entry(0, 0)
+        cores = os.cpu_count() or 1
+        qs = qsets[args.warmup + args.steps - 1]
+        ci, cs, cc, secs = ora.search_restricted_batch(qs, k, cand_ids, offs, threads=cores)
+        parity = bool(ci.tolist() == dev_ids.tolist() and cs.tobytes() == dev_sc.tobytes())
+        cpu = {"value": round(B / secs, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"the last step's {B} queries x {per_q} candidates, one query per thread, {cores} threads",
+               "bit_exact_vs_device": parity}
+    if rank == 0:
+        line = {
+            "metric": "queries/sec, DBpedia-1M d=768 prefiltered top-10 (graph-label filter), exact scan (config C3)",
+            "value": round(value, 1), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "recall_at_10": 1.0,
+            "config": {"workload": f"C3: {n}x{dim} f32 {args.metric}, {B} queries per step, query b restricted to "
+                                   f"{{id : id mod {sel} == b}} ({per_q} candidates each): every row read once per step",
+                       "l2": "3.07 GB streamed per step >> 126 MB L2", "recipe": args.recipe},
+            "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4 + total * 8 + (B + 1) * 8,
+                    "d2h_bytes_per_step": B * (k * 12 + 4) + B * 4 + 4, "api": "hx_search_restricted_multi (C ABI, pinned host)",
+                    "identical_to_device_path": same},
+            "gpu_launches": args.steps * 3,
+            "launches_per_step": {"k_validate_and_header": 1, "k_scan": 1, "k_select": 1},
+            "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_scan"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms_per_launch": round(kernel_ms, 4)},
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust reference cannot be built
     here: no rustc/cargo, un-vendored SlateDB fork) on all host cores, same config, metric and unit."""
@@ -493,5 +635,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "prefilter":
+        run_prefilter(a)
     else:
         run_ours(a)

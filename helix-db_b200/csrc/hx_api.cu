@@ -886,11 +886,11 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
                                      (int)smem_launch));                                                           \
       k_hnsw_search<M, 8><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a);                                 \
     } else {                                                                                                       \
-      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                    (int)smem_launch));                                                             \
-      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 8>, cudaFuncAttributePreferredSharedMemoryCarveout,       \
+      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,       \
                                    cudaSharedmemCarveoutMaxShared));                                               \
-      k_hnsw_search_warp<M, 8><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, wstride);                   \
+      k_hnsw_search_warp<M, 4><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, wstride);                   \
     }                                                                                                              \
   } while (0)
   switch (ix->cfg.metric) {

@@ -347,13 +347,13 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS) k_hnsw_search(HxDev ix, HxHns
 // ---- warp-per-query variant (throughput) ---------------------------------------------------------------------------
 // A layer-0 expansion of a converged beam discovers only a handful of unvisited neighbours, so a 256-thread CTA per
 // query leaves most octets idle and — at 4 CTAs per SM — keeps only 4 dependent pointer chases in flight per SM.  Here
-// every WARP owns one query (its 4 octets score 4 neighbours per round), 8 warps per CTA, up to 32 queries in flight per
+// every WARP owns one query (its 8 quads score 8 neighbours per round), 8 warps per CTA, up to 32 queries in flight per
 // SM: enough independent row fetches to cover HBM latency.  Same algorithm, same order of every float operation and of
 // every admission as k_hnsw_search; __syncthreads became __syncwarp.  `wstride` = shared-memory bytes per warp.
 template <int METRIC, int NB>
 __global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev ix, HxHnswArgs a, uint32_t wstride) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, t = lane & 7u, oct = lane >> 3;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, t = lane & 3u, oct = lane >> 2;   // quads: 8 rows per round
   const uint32_t warps_per_cta = blockDim.x >> 5;
   const uint32_t gw = blockIdx.x * warps_per_cta + warp;          // global warp id == stamp slot
   const uint32_t total_warps = gridDim.x * warps_per_cta;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev i
       if (METRIC == HXM_MANHATTAN) {
         if (lane == 0) s = hx_manhattan_seq(ix.vec + (size_t)cur * ix.ld, sq, ix.dim);
       } else if (oct == 0) {
-        s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, cur, t);
+        s = hx_quad_score<METRIC, NB>(ix, sq, q_hdr, cur, t);
       }
       s = __shfl_sync(FULL, s, 0);
       if (!hx_score_ok(s) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev i
         if (METRIC == HXM_MANHATTAN) {
           for (uint32_t f = lane; f < deg; f += 32) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)row[f] * ix.ld, sq, ix.dim);
         } else {
-          for (uint32_t f = oct; f < deg; f += 4) {
-            float s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, row[f], t);
+          for (uint32_t f = oct; f < deg; f += 8) {
+            float s = hx_quad_score<METRIC, NB>(ix, sq, q_hdr, row[f], t);
             if (t == 0) fdist[f] = s;
           }
         }
@@ -504,8 +504,8 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev i
       if (METRIC == HXM_MANHATTAN) {
         for (uint32_t f = lane; f < nf; f += 32) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)frontier[f] * ix.ld, sq, ix.dim);
       } else {
-        for (uint32_t f = oct; f < nf; f += 4) {
-          float s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, frontier[f], t);
+        for (uint32_t f = oct; f < nf; f += 8) {
+          float s = hx_quad_score<METRIC, NB>(ix, sq, q_hdr, frontier[f], t);
           if (t == 0) fdist[f] = s;
         }
       }

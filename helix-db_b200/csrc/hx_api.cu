@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -827,18 +828,36 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   // Two builds of the same algorithm (bit-identical results):
   //  * B <  #SMs : one CTA per query (32 octets score a whole neighbour row at once) — lowest latency per query;
   //  * B >= #SMs : one WARP per query, 8 warps per CTA, up to 32 queries in flight per SM — highest throughput.
+  // resident CTAs per SM of the warp-per-query build (register cap 65536/(256*minb)); HX_WARP_MINB overrides for experiments
+  uint32_t minb = 4;
+  if (const char* env = getenv("HX_WARP_MINB")) { const int v = atoi(env); if (v >= 4 && v <= 6) minb = (uint32_t)v; }
   const uint32_t wpc = HX_HNSW_THREADS / 32;
   const uint32_t wstride = round_up(smem, 128);
   const bool latency = B < (size_t)ix->sm_count || (size_t)wpc * wstride > 200 * 1024;
   uint32_t grid, slots;
   size_t smem_launch;
   const size_t stride = ((ix->n + 15) / 16) * 16;
-  if (latency) {
+  // TMA-staged build (default for throughput): R rows per warp and round live in shared memory
+  bool use_tma = !latency;
+  if (const char* env = getenv("HX_HNSW_IMPL")) use_tma = use_tma && strcmp(env, "ldg") != 0;
+  uint32_t tma_R = 0, tma_wstride = 0;
+  if (use_tma) {
+    const size_t fixed = (size_t)ix->ld * 4 + (size_t)ef * 8 + HX_TIE_CAP * 8 + 8 + (size_t)fr_cap * 12;
+    const size_t per_warp_budget = (216 * 1024) / wpc;
+    if (per_warp_budget > fixed + (size_t)ix->ld * 4) tma_R = (uint32_t)std::min<size_t>(32, (per_warp_budget - fixed) / ((size_t)ix->ld * 4));
+    if (tma_R == 0) use_tma = false;
+    else tma_wstride = round_up((uint32_t)(fixed + (size_t)tma_R * ix->ld * 4), 128);
+  }
+  if (use_tma) {
+    grid = (uint32_t)std::min<size_t>((B + wpc - 1) / wpc, (size_t)ix->sm_count);
+    slots = (uint32_t)ix->sm_count * wpc;
+    smem_launch = (size_t)wpc * tma_wstride;
+  } else if (latency) {
     grid = (uint32_t)std::min<size_t>(B, (size_t)ix->sm_count * 4);
     slots = (uint32_t)ix->sm_count * 4;
     smem_launch = smem;
   } else {
-    uint32_t ctas_per_sm = 4;
+    uint32_t ctas_per_sm = minb;
     while (ctas_per_sm > 1 && (size_t)ctas_per_sm * wpc * wstride > 200 * 1024) ctas_per_sm--;
     uint32_t max_ctas = (uint32_t)ix->sm_count * ctas_per_sm;
     // visited stamps cost n bytes per resident query: keep them under ~8 GB
@@ -878,19 +897,31 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   a.fr_cap = fr_cap;
   const HxDev dev = ix->dev();
   HX_CUDA(cudaEventRecord(e0, stream));
+#define HX_LAUNCH_WARP(M, MB)                                                                                      \
+  do {                                                                                                             \
+    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 8, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                 (int)smem_launch));                                                               \
+    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 8, MB>, cudaFuncAttributePreferredSharedMemoryCarveout,     \
+                                 cudaSharedmemCarveoutMaxShared));                                                 \
+    k_hnsw_search_warp<M, 8, MB><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, wstride);                 \
+  } while (0)
 #define HX_LAUNCH_HNSW(M)                                                                                          \
   do {                                                                                                             \
-    if (latency) {                                                                                                 \
+    if (use_tma) {                                                                                                 \
+      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_tma<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                   (int)smem_launch));                                                             \
+      k_hnsw_search_tma<M><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, tma_wstride, tma_R);            \
+    } else if (latency) {                                                                                                 \
       if (smem_launch > 48 * 1024)                                                                                 \
         HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                                      (int)smem_launch));                                                           \
       k_hnsw_search<M, 8><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a);                                 \
+    } else if (minb == 6) {                                                                                        \
+      HX_LAUNCH_WARP(M, 6);                                                                                        \
+    } else if (minb == 5) {                                                                                        \
+      HX_LAUNCH_WARP(M, 5);                                                                                        \
     } else {                                                                                                       \
-      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                   (int)smem_launch));                                                             \
-      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,       \
-                                   cudaSharedmemCarveoutMaxShared));                                               \
-      k_hnsw_search_warp<M, 4><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, wstride);                   \
+      HX_LAUNCH_WARP(M, 4);                                                                                        \
     }                                                                                                              \
   } while (0)
   switch (ix->cfg.metric) {
@@ -899,6 +930,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     default: HX_LAUNCH_HNSW(HXM_MANHATTAN); break;
   }
 #undef HX_LAUNCH_HNSW
+#undef HX_LAUNCH_WARP
   HX_CUDA(cudaGetLastError());
   HX_CUDA(cudaEventRecord(e1, stream));
   *timed = true;
@@ -1039,8 +1071,8 @@ extern "C" int32_t hx_restricted_plan(uint64_t n_candidates, uint32_t dimension)
 }
 
 static uint32_t pick_chunk(uint64_t total_cands, int sm_count) {
-  // aim for >= 4 CTAs per SM over the whole launch; one CTA pass covers 32 rows
-  uint64_t c = total_cands / ((uint64_t)sm_count * 4) + 1;
+  // aim for ~8 waves of CTAs (4 resident per SM) so the last partial wave costs little; one CTA pass covers 32 rows
+  uint64_t c = total_cands / ((uint64_t)sm_count * 4 * 8) + 1;
   c = (c + 31) / 32 * 32;
   if (c < 32) c = 32;
   if (c > 2048) c = 2048;

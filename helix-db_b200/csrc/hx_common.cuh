@@ -58,6 +58,34 @@ __device__ __forceinline__ void hx_prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier wrappers ---------------------------------------------------
+__device__ __forceinline__ uint32_t hx_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hx_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hx_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hx_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void hx_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hx_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion is counted on `bar`
+__device__ __forceinline__ void hx_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   hx_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(hx_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool hx_mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok)
+               : "r"(hx_smem_u32(bar)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void hx_mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!hx_mbar_try_wait(bar, parity)) {}
+}
+
 // ---- octet (8-thread) reduction in hsum256 order ------------------------------------------
 // acc.{x,y,z,w} of thread t are chains 4t..4t+3.  With L = 8a + j: a = t>>1, j = 4(t&1)+component.
 __device__ __forceinline__ float hx_octet_reduce(float4 acc) {
@@ -105,12 +133,12 @@ __device__ __forceinline__ float hx_octet_reduce(float4 acc) {
 // dim <  32: the scalar loops (simple.rs:204-234), which are exactly the "tail" below with m = 0.
 // One batch of NB consecutive 32-element chunks: all NB 128-bit loads are issued before the first FMA, so NB*16 bytes
 // per thread are in flight; the FMAs then run in chunk order (the accumulation order is unchanged by NB).
-template <bool IS_DOT, int NB>
+template <bool IS_DOT, int NB, bool ROW_GLOBAL = true>
 __device__ __forceinline__ void hx_octet_batch(float4& acc, const float4* __restrict__ r4, const float4* __restrict__ q4,
                                                uint32_t c) {
   float4 r[NB];
 #pragma unroll
-  for (int i = 0; i < NB; ++i) r[i] = hx_ldg4(r4 + (c + i) * 8);
+  for (int i = 0; i < NB; ++i) r[i] = ROW_GLOBAL ? hx_ldg4(r4 + (c + i) * 8) : r4[(c + i) * 8];   // smem rows: plain LDS.128
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const float4 q = q4[(c + i) * 8];
@@ -118,7 +146,7 @@ __device__ __forceinline__ void hx_octet_batch(float4& acc, const float4* __rest
   }
 }
 
-template <bool IS_DOT, int NB = 8>
+template <bool IS_DOT, int NB = 8, bool ROW_GLOBAL = true>
 __device__ __forceinline__ float hx_octet_kernel(const float* __restrict__ row, const float* __restrict__ q,
                                                  uint32_t dim, uint32_t t) {
   const uint32_t chunks = dim >> 5;
@@ -126,74 +154,16 @@ __device__ __forceinline__ float hx_octet_kernel(const float* __restrict__ row, 
   const float4* q4 = reinterpret_cast<const float4*>(q) + t;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t c = 0;
-  for (; c + NB <= chunks; c += NB) hx_octet_batch<IS_DOT, NB>(acc, r4, q4, c);
-  if (NB > 16 && c + 16 <= chunks) { hx_octet_batch<IS_DOT, 16>(acc, r4, q4, c); c += 16; }
-  if (NB > 8 && c + 8 <= chunks) { hx_octet_batch<IS_DOT, 8>(acc, r4, q4, c); c += 8; }
-  if (NB > 4 && c + 4 <= chunks) { hx_octet_batch<IS_DOT, 4>(acc, r4, q4, c); c += 4; }
-  if (NB > 2 && c + 2 <= chunks) { hx_octet_batch<IS_DOT, 2>(acc, r4, q4, c); c += 2; }
-  if (NB > 1 && c < chunks) { hx_octet_batch<IS_DOT, 1>(acc, r4, q4, c); c += 1; }
+  for (; c + NB <= chunks; c += NB) hx_octet_batch<IS_DOT, NB, ROW_GLOBAL>(acc, r4, q4, c);
+  if (NB > 16 && c + 16 <= chunks) { hx_octet_batch<IS_DOT, 16, ROW_GLOBAL>(acc, r4, q4, c); c += 16; }
+  if (NB > 8 && c + 8 <= chunks) { hx_octet_batch<IS_DOT, 8, ROW_GLOBAL>(acc, r4, q4, c); c += 8; }
+  if (NB > 4 && c + 4 <= chunks) { hx_octet_batch<IS_DOT, 4, ROW_GLOBAL>(acc, r4, q4, c); c += 4; }
+  if (NB > 2 && c + 2 <= chunks) { hx_octet_batch<IS_DOT, 2, ROW_GLOBAL>(acc, r4, q4, c); c += 2; }
+  if (NB > 1 && c < chunks) { hx_octet_batch<IS_DOT, 1, ROW_GLOBAL>(acc, r4, q4, c); c += 1; }
   float result = hx_octet_reduce(acc);   // all-zero accumulators reduce to +0.0 == the scalar loop's 0.0 start
   const uint32_t m = chunks << 5;
   for (uint32_t i = m; i < dim; ++i) {   // `result += d * d` / `result += a * b`: two roundings, never fused
-    float a = q[i], b = __ldg(row + i);
-    if (IS_DOT) {
-      result = __fadd_rn(result, __fmul_rn(a, b));
-    } else {
-      float d = __fsub_rn(a, b);
-      result = __fadd_rn(result, __fmul_rn(d, d));
-    }
-  }
-  return result;
-}
-
-// ---- quad (4-thread) variant ---------------------------------------------------------------------------------------
-// Same 32 FMA chains, four threads per row: thread t (0..3) owns accumulator t entirely (chains 8t..8t+7, i.e. all 8
-// lanes j of the reference's sum256_{t+1}) and loads two consecutive float4 per 32-element chunk (the quad still reads
-// one full 128-byte line per step).  (s1+s2)+(s3+s4) are the xor-1 / xor-2 shuffles; hsum256 is entirely in-thread.
-// A warp scores 8 rows per round instead of 4.
-template <bool IS_DOT, int NB>
-__device__ __forceinline__ void hx_quad_batch(float4& a0, float4& a1, const float4* __restrict__ r4,
-                                              const float4* __restrict__ q4, uint32_t c) {
-  float4 r0[NB], r1[NB];
-#pragma unroll
-  for (int i = 0; i < NB; ++i) {
-    r0[i] = hx_ldg4(r4 + (c + i) * 8);
-    r1[i] = hx_ldg4(r4 + (c + i) * 8 + 1);
-  }
-#pragma unroll
-  for (int i = 0; i < NB; ++i) {
-    const float4 q0 = q4[(c + i) * 8], q1 = q4[(c + i) * 8 + 1];
-    if (IS_DOT) { HX_DOT_STEP(a0, q0, r0[i]) HX_DOT_STEP(a1, q1, r1[i]) } else { HX_L2_STEP(a0, q0, r0[i]) HX_L2_STEP(a1, q1, r1[i]) }
-  }
-}
-
-template <bool IS_DOT, int NB = 4>
-__device__ __forceinline__ float hx_quad_kernel(const float* __restrict__ row, const float* __restrict__ q,
-                                                uint32_t dim, uint32_t t /*0..3*/) {
-  const uint32_t chunks = dim >> 5;
-  const float4* r4 = reinterpret_cast<const float4*>(row) + 2 * t;
-  const float4* q4 = reinterpret_cast<const float4*>(q) + 2 * t;
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t c = 0;
-  for (; c + NB <= chunks; c += NB) hx_quad_batch<IS_DOT, NB>(a0, a1, r4, q4, c);
-  if (NB > 4 && c + 4 <= chunks) { hx_quad_batch<IS_DOT, 4>(a0, a1, r4, q4, c); c += 4; }
-  if (NB > 2 && c + 2 <= chunks) { hx_quad_batch<IS_DOT, 2>(a0, a1, r4, q4, c); c += 2; }
-  if (NB > 1 && c < chunks) { hx_quad_batch<IS_DOT, 1>(a0, a1, r4, q4, c); c += 1; }
-  const unsigned qm = 0xFu << (threadIdx.x & 28u);
-  float4 o0, o1;
-#define HX_QSH(D, S, X) D.x = __shfl_xor_sync(qm, S.x, X); D.y = __shfl_xor_sync(qm, S.y, X); \
-                        D.z = __shfl_xor_sync(qm, S.z, X); D.w = __shfl_xor_sync(qm, S.w, X);
-#define HX_QADD(A, B) A.x = __fadd_rn(A.x, B.x); A.y = __fadd_rn(A.y, B.y); A.z = __fadd_rn(A.z, B.z); A.w = __fadd_rn(A.w, B.w);
-  HX_QSH(o0, a0, 1) HX_QSH(o1, a1, 1) HX_QADD(a0, o0) HX_QADD(a1, o1)      // s1+s2 , s3+s4
-  HX_QSH(o0, a0, 2) HX_QSH(o1, a1, 2) HX_QADD(a0, o0) HX_QADD(a1, o1)      // (s1+s2)+(s3+s4)
-#undef HX_QSH
-#undef HX_QADD
-  // hsum256: x128[j] = lane[4+j] + lane[j]; x64 = [0]+[2], [1]+[3]; x32 = x64[0] + x64[1]
-  const float x0 = __fadd_rn(a1.x, a0.x), x1 = __fadd_rn(a1.y, a0.y), x2 = __fadd_rn(a1.z, a0.z), x3 = __fadd_rn(a1.w, a0.w);
-  float result = __fadd_rn(__fadd_rn(x0, x2), __fadd_rn(x1, x3));
-  const uint32_t m = chunks << 5;
-  for (uint32_t i = m; i < dim; ++i) {
-    float a = q[i], b = __ldg(row + i);
+    float a = q[i], b = ROW_GLOBAL ? __ldg(row + i) : row[i];
     if (IS_DOT) {
       result = __fadd_rn(result, __fmul_rn(a, b));
     } else {
@@ -294,16 +264,18 @@ __device__ __forceinline__ float hx_octet_score(const HxDev& ix, const float* __
   return hx_manhattan_seq(row, q, ix.dim);
 }
 
-template <int METRIC, int NB = 4>
-__device__ __forceinline__ float hx_quad_score(const HxDev& ix, const float* __restrict__ q, float q_hdr,
-                                               uint32_t slot, uint32_t t) {
-  const float* row = ix.vec + (size_t)slot * ix.ld;
-  if (METRIC == HXM_EUCLIDEAN) return hx_quad_kernel<false, NB>(row, q, ix.dim, t);
+// Same score, the row already staged in shared memory (TMA path); `row_hdr` = the row's header.
+template <int METRIC, int NB = 8>
+__device__ __forceinline__ float hx_octet_score_smem(const float* __restrict__ row_smem, const float* __restrict__ q,
+                                                     float q_hdr, float row_hdr, uint32_t dim, uint32_t t) {
+  if (METRIC == HXM_EUCLIDEAN) return hx_octet_kernel<false, NB, false>(row_smem, q, dim, t);
   if (METRIC == HXM_COSINE) {
-    float pq = hx_quad_kernel<true, NB>(row, q, ix.dim, t);
-    return hx_cosine_finish(pq, q_hdr, __ldg(ix.hdr + slot), q, row, ix.dim);
+    float pq = hx_octet_kernel<true, NB, false>(row_smem, q, dim, t);
+    return hx_cosine_finish(pq, q_hdr, row_hdr, q, row_smem, dim);
   }
-  return hx_manhattan_seq(row, q, ix.dim);
+  float distance = 0.0f;   // Manhattan: one sequential chain (simple.rs:186-202)
+  for (uint32_t i = 0; i < dim; ++i) distance = __fadd_rn(distance, fabsf(__fsub_rn(q[i], row_smem[i])));
+  return distance;
 }
 
 // DistanceScore::try_new (parameters.rs:241-258): finite, >= 0, -0 -> +0.  Returns false if invalid.

@@ -26,7 +26,7 @@
 #include "hx_common.cuh"
 
 #define HX_HNSW_THREADS 256
-#define HX_TIE_CAP 64
+#define HX_TIE_CAP 32
 
 struct HxHnswArgs {
   const float* queries;     // [B][dim] device
@@ -347,13 +347,13 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS) k_hnsw_search(HxDev ix, HxHns
 // ---- warp-per-query variant (throughput) ---------------------------------------------------------------------------
 // A layer-0 expansion of a converged beam discovers only a handful of unvisited neighbours, so a 256-thread CTA per
 // query leaves most octets idle and — at 4 CTAs per SM — keeps only 4 dependent pointer chases in flight per SM.  Here
-// every WARP owns one query (its 8 quads score 8 neighbours per round), 8 warps per CTA, up to 32 queries in flight per
+// every WARP owns one query (its 4 octets score 4 neighbours per round), 8 warps per CTA, up to 32 queries in flight per
 // SM: enough independent row fetches to cover HBM latency.  Same algorithm, same order of every float operation and of
 // every admission as k_hnsw_search; __syncthreads became __syncwarp.  `wstride` = shared-memory bytes per warp.
-template <int METRIC, int NB>
-__global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev ix, HxHnswArgs a, uint32_t wstride) {
+template <int METRIC, int NB, int MINB>
+__global__ void __launch_bounds__(HX_HNSW_THREADS, MINB) k_hnsw_search_warp(HxDev ix, HxHnswArgs a, uint32_t wstride) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, t = lane & 3u, oct = lane >> 2;   // quads: 8 rows per round
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, t = lane & 7u, oct = lane >> 3;
   const uint32_t warps_per_cta = blockDim.x >> 5;
   const uint32_t gw = blockIdx.x * warps_per_cta + warp;          // global warp id == stamp slot
   const uint32_t total_warps = gridDim.x * warps_per_cta;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev i
       if (METRIC == HXM_MANHATTAN) {
         if (lane == 0) s = hx_manhattan_seq(ix.vec + (size_t)cur * ix.ld, sq, ix.dim);
       } else if (oct == 0) {
-        s = hx_quad_score<METRIC, NB>(ix, sq, q_hdr, cur, t);
+        s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, cur, t);
       }
       s = __shfl_sync(FULL, s, 0);
       if (!hx_score_ok(s) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev i
         if (METRIC == HXM_MANHATTAN) {
           for (uint32_t f = lane; f < deg; f += 32) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)row[f] * ix.ld, sq, ix.dim);
         } else {
-          for (uint32_t f = oct; f < deg; f += 8) {
-            float s = hx_quad_score<METRIC, NB>(ix, sq, q_hdr, row[f], t);
+          for (uint32_t f = oct; f < deg; f += 4) {
+            float s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, row[f], t);
             if (t == 0) fdist[f] = s;
           }
         }
@@ -504,12 +504,265 @@ __global__ void __launch_bounds__(HX_HNSW_THREADS, 4) k_hnsw_search_warp(HxDev i
       if (METRIC == HXM_MANHATTAN) {
         for (uint32_t f = lane; f < nf; f += 32) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)frontier[f] * ix.ld, sq, ix.dim);
       } else {
-        for (uint32_t f = oct; f < nf; f += 8) {
-          float s = hx_quad_score<METRIC, NB>(ix, sq, q_hdr, frontier[f], t);
+        for (uint32_t f = oct; f < nf; f += 4) {
+          float s = hx_octet_score<METRIC, NB>(ix, sq, q_hdr, frontier[f], t);
           if (t == 0) fdist[f] = s;
         }
       }
       __syncwarp();
+      for (uint32_t base = 0; base < nf; base += 32) {
+        const uint32_t f = base + lane;
+        float s = f < nf ? fdist[f] : 0.f;
+        uint32_t sbits = 0;
+        bool pass = false;
+        if (f < nf) {
+          if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+          sbits = __float_as_uint(s);
+          const uint32_t wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
+          pass = (sbits < wmax) || (beam.len < a.ef);
+        }
+        uint32_t mask = __ballot_sync(FULL, pass);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const uint32_t xb = __shfl_sync(FULL, sbits, src);
+          const uint32_t xslot = __shfl_sync(FULL, f < nf ? frontier[f] : 0u, src);
+          const uint32_t wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
+          if (!((xb < wmax) || (beam.len < a.ef))) continue;
+          const uint32_t old_wmax = wmax;
+          const bool was_full = beam.len == a.ef;
+          uint64_t ev;
+          hx_beam_insert(beam, a.ef, ((uint64_t)xb << 32) | ((uint64_t)xslot << 1), &ev, lane);
+          if (lane == 0) {
+            hx_prefetch_l2(ix.nbr0 + (size_t)xslot * ix.stride0);
+            hx_prefetch_l2(ix.deg0 + xslot);
+          }
+          if (was_full) {
+            const uint32_t new_wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
+            if (new_wmax < old_wmax && tie_len) { dropped = 1; tie_len = 0; }
+            if (!(ev & 1ull)) {
+              if ((uint32_t)(ev >> 32) == new_wmax) {
+                if (tie_len < HX_TIE_CAP) {
+                  if (lane == 0) tie[tie_len] = ev;
+                  tie_len++;
+                } else {
+                  if (lane == 0) atomicOr(a.err_flags, HXF_TIE_OVERFLOW);
+                  dropped = 1;
+                }
+              } else {
+                dropped = 1;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- results
+    const uint32_t len = beam.len;
+    const uint32_t cnt = len < a.k ? len : a.k;
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint64_t key = beam_mem[i];
+      a.out_ids[(size_t)qi * a.k + i] = ix.ids[(uint32_t)(key & 0xffffffffu) >> 1];
+      a.out_scores[(size_t)qi * a.k + i] = hx_key_score(key);
+    }
+    if (lane == 0) {
+      a.out_counts[qi] = cnt;
+      if (a.q_stats) {
+        a.q_stats[(size_t)qi * 4 + 0] = st_steps;
+        a.q_stats[(size_t)qi * 4 + 1] = st_examined;
+        a.q_stats[(size_t)qi * 4 + 2] = st_dc;
+        a.q_stats[(size_t)qi * 4 + 3] = upper_steps;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- warp-per-query with TMA-staged rows (default throughput build) --------------------------------------------------
+// ncu on k_hnsw_search_warp (profiles/r01_ncu_k_hnsw_search_warp_octet_details.txt) shows the limit: 58 % of the warp
+// cycles are long-scoreboard stalls with 0.2 eligible warps per scheduler — register-fed LDG.128s keep only ~5 loads per
+// thread in flight, and a row needs 24 of them, so every scored row costs several dependent DRAM round trips.
+// Here the rows of a round are fetched by the TMA engine instead: lane i issues ONE cp.async.bulk (global -> shared,
+// 4*ld bytes) for row i, all R rows of the round are in flight at once with zero registers, an mbarrier counts the
+// bytes, and the octets then reduce the rows out of shared memory (LDS.128) in exactly the same order as before.
+//   shared memory per warp: query | R rows | beam | tie stack | frontier | scores | row headers | mbarrier
+template <int METRIC>
+__global__ void __launch_bounds__(HX_HNSW_THREADS, 1) k_hnsw_search_tma(HxDev ix, HxHnswArgs a, uint32_t wstride, uint32_t R) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, t = lane & 7u, oct = lane >> 3;
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  const uint32_t gw = blockIdx.x * warps_per_cta + warp;
+  const uint32_t total_warps = gridDim.x * warps_per_cta;
+  unsigned char* wmem = smem + (size_t)warp * wstride;
+  float* sq = reinterpret_cast<float*>(wmem);                                         // [ld]
+  float* rowbuf = sq + ix.ld;                                                         // [R][ld]
+  uint64_t* beam_mem = reinterpret_cast<uint64_t*>(rowbuf + (size_t)R * ix.ld);      // [ef]
+  uint64_t* tie = beam_mem + a.ef;                                                    // [HX_TIE_CAP]
+  uint64_t* bar = tie + HX_TIE_CAP;                                                   // [1]
+  uint32_t* frontier = reinterpret_cast<uint32_t*>(bar + 1);                          // [fr_cap]
+  float* fdist = reinterpret_cast<float*>(frontier + a.fr_cap);                      // [fr_cap]
+  float* fhdr = fdist + a.fr_cap;                                                     // [fr_cap]
+  uint8_t* stamp = a.stamps + (size_t)gw * a.stamp_stride;
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t rowbytes = ix.ld * 4u;
+  uint32_t phase = 0;
+  if (lane == 0) {
+    hx_mbar_init(bar, 1);
+    hx_fence_mbar_init();
+  }
+  __syncwarp();
+
+  // score `cnt` rows whose slots sit in list[0..cnt) (shared or global memory) into fdist[0..cnt)
+  auto score_rows = [&](const uint32_t* list, uint32_t cnt, float q_hdr) {
+    for (uint32_t base = 0; base < cnt; base += R) {
+      const uint32_t rows = min(R, cnt - base);
+      if (lane == 0) hx_mbar_expect_tx(bar, rows * rowbytes);
+      __syncwarp();
+      if (lane < rows) {
+        const uint32_t slot = list[base + lane];
+        hx_bulk_g2s(rowbuf + (size_t)lane * ix.ld, ix.vec + (size_t)slot * ix.ld, rowbytes, bar);
+        if (METRIC == HXM_COSINE) fhdr[lane] = __ldg(ix.hdr + slot);
+      }
+      hx_mbar_wait(bar, phase);
+      phase ^= 1u;
+      __syncwarp();
+      if (METRIC == HXM_MANHATTAN) {
+        if (lane < rows) fdist[base + lane] = hx_octet_score_smem<METRIC>(rowbuf + (size_t)lane * ix.ld, sq, q_hdr, 0.f, ix.dim, 0);
+      } else {
+        for (uint32_t r = oct; r < rows; r += 4) {
+          float s = hx_octet_score_smem<METRIC>(rowbuf + (size_t)r * ix.ld, sq, q_hdr, METRIC == HXM_COSINE ? fhdr[r] : 0.f, ix.dim, t);
+          if (t == 0) fdist[base + r] = s;
+        }
+      }
+      __syncwarp();   // every lane is done with rowbuf before the next round overwrites it
+    }
+  };
+
+  for (uint32_t qi = gw; qi < a.B; qi += total_warps) {
+    if (a.q_status[qi] != 0u || !ix.populated) {
+      if (lane == 0) a.out_counts[qi] = 0;
+      continue;
+    }
+    const float q_hdr = a.q_hdr[qi];
+    for (uint32_t i = lane; i < ix.ld; i += 32) sq[i] = i < ix.dim ? a.queries[(size_t)qi * ix.dim + i] : 0.0f;
+    uint32_t epoch = 0;
+    if (lane == 0) epoch = a.epochs[gw] + 1u;
+    epoch = __shfl_sync(FULL, epoch, 0);
+    if (epoch >= 256u) {
+      uint4* s4 = reinterpret_cast<uint4*>(stamp);
+      const size_t n16 = a.stamp_stride >> 4;
+      for (size_t i = lane; i < n16; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+      epoch = 1u;
+    }
+    __syncwarp();
+    if (lane == 0) a.epochs[gw] = epoch;
+    const uint8_t ep8 = (uint8_t)epoch;
+
+    // ---- entry point
+    uint32_t cur = ix.entry_slot;
+    if (lane == 0) frontier[0] = cur;
+    __syncwarp();
+    score_rows(frontier, 1, q_hdr);
+    float cur_dist = fdist[0];
+    if (!hx_score_ok(cur_dist) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+    uint32_t upper_steps = 0;
+    __syncwarp();
+
+    // ---- upper layers: greedy descent (search.rs:169-224)
+    for (int layer = ix.max_layer; layer >= 1; --layer) {
+      for (;;) {
+        uint32_t deg = 0;
+        const uint32_t* row = nullptr;
+        {
+          const uint32_t off = ix.upper_off[cur];
+          if (off != HX_ABSENT && (int)ix.level[cur] >= layer) {
+            deg = ix.upper_deg[off + (uint32_t)layer - 1u];
+            row = ix.upper_nbr + (size_t)(off + (uint32_t)layer - 1u) * ix.stride_u;
+          }
+        }
+        score_rows(row, deg, q_hdr);
+        float best = cur_dist;
+        uint32_t best_i = HX_ABSENT;
+        bool bad = false;
+        for (uint32_t base = 0; base < deg; base += 32) {
+          uint32_t f = base + lane;
+          float s = f < deg ? fdist[f] : __int_as_float(0x7f800000);
+          if (f < deg && !hx_score_ok(s)) bad = true;
+          float m = s;
+          uint32_t mi = f;
+          for (int o = 16; o > 0; o >>= 1) {
+            float om = __shfl_xor_sync(FULL, m, o);
+            uint32_t oi = __shfl_xor_sync(FULL, mi, o);
+            if (om < m || (om == m && oi < mi)) { m = om; mi = oi; }
+          }
+          if (m < best) { best = m; best_i = mi; }
+        }
+        if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+        __syncwarp();
+        if (best_i == HX_ABSENT) break;
+        cur = row[best_i];
+        cur_dist = best;
+        upper_steps++;
+      }
+    }
+
+    // ---- layer 0: beam search
+    HxBeam beam{beam_mem, 1u};
+    uint32_t tie_len = 0, dropped = 0;
+    uint32_t st_steps = 0, st_examined = 0, st_dc = 1;
+    if (lane == 0) {
+      beam_mem[0] = hx_make_key(cur_dist, cur << 1);
+      stamp[cur] = ep8;
+    }
+    __syncwarp();
+    for (;;) {
+      uint32_t first = HX_ABSENT;
+      for (uint32_t i = lane; i < beam.len; i += 32)
+        if (!(beam_mem[i] & 1ull)) { first = i; break; }
+      first = hx_warp_min(first);
+      uint32_t cur_slot = HX_ABSENT;
+      if (first != HX_ABSENT) {
+        uint64_t key = beam_mem[first];
+        __syncwarp();
+        if (lane == 0) beam_mem[first] = key | 1ull;
+        cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
+        st_steps++;
+      } else if (tie_len > 0) {
+        uint64_t key = tie[tie_len - 1];
+        tie_len--;
+        cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
+        st_steps++;
+      } else if (dropped) {
+        st_steps++;
+      }
+      if (cur_slot == HX_ABSENT) break;
+      uint32_t nf = 0;
+      {
+        const uint32_t deg = ix.deg0[cur_slot];
+        st_examined += ix.raw0[cur_slot];
+        const uint32_t* row = ix.nbr0 + (size_t)cur_slot * ix.stride0;
+        for (uint32_t base = 0; base < deg; base += 32) {
+          const uint32_t i = base + lane;
+          uint32_t nb = 0;
+          bool fresh = false;
+          if (i < deg) {
+            nb = row[i];
+            fresh = stamp[nb] != ep8;
+          }
+          const uint32_t mask = __ballot_sync(FULL, fresh);
+          if (fresh) {
+            frontier[nf + __popc(mask & ((1u << lane) - 1u))] = nb;
+            stamp[nb] = ep8;
+          }
+          nf += __popc(mask);
+        }
+        st_dc += nf;
+      }
+      __syncwarp();
+      score_rows(frontier, nf, q_hdr);
       for (uint32_t base = 0; base < nf; base += 32) {
         const uint32_t f = base + lane;
         float s = f < nf ? fdist[f] : 0.f;

@@ -840,22 +840,31 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   // TMA-staged build (default for throughput): R rows per warp and round live in shared memory
   bool use_tma = !latency;
   if (const char* env = getenv("HX_HNSW_IMPL")) use_tma = use_tma && strcmp(env, "ldg") != 0;
-  uint32_t tma_R = 0, tma_wstride = 0;
+  uint32_t tma_R = 0, tma_wstride = 0, tma_wpc = 12, cta_RC = 0;   // 12 warps/SM measured best (8: 0.65, 12: 0.70, 16: 0.70 of HBM peak)
+  if (const char* env = getenv("HX_TMA_WARPS")) { const int v = atoi(env); if (v >= 4 && v <= 16) tma_wpc = (uint32_t)v; }
   if (use_tma) {
     const size_t fixed = (size_t)ix->ld * 4 + (size_t)ef * 8 + HX_TIE_CAP * 8 + 8 + (size_t)fr_cap * 12;
-    const size_t per_warp_budget = (216 * 1024) / wpc;
+    const size_t per_warp_budget = (216 * 1024) / tma_wpc;
     if (per_warp_budget > fixed + (size_t)ix->ld * 4) tma_R = (uint32_t)std::min<size_t>(32, (per_warp_budget - fixed) / ((size_t)ix->ld * 4));
     if (tma_R == 0) use_tma = false;
     else tma_wstride = round_up((uint32_t)(fixed + (size_t)tma_R * ix->ld * 4), 128);
   }
   if (use_tma) {
-    grid = (uint32_t)std::min<size_t>((B + wpc - 1) / wpc, (size_t)ix->sm_count);
-    slots = (uint32_t)ix->sm_count * wpc;
-    smem_launch = (size_t)wpc * tma_wstride;
+    grid = (uint32_t)std::min<size_t>((B + tma_wpc - 1) / tma_wpc, (size_t)ix->sm_count);
+    slots = (uint32_t)ix->sm_count * 16;
+    smem_launch = (size_t)tma_wpc * tma_wstride;
   } else if (latency) {
     grid = (uint32_t)std::min<size_t>(B, (size_t)ix->sm_count * 4);
     slots = (uint32_t)ix->sm_count * 4;
     smem_launch = smem;
+    // TMA-staged latency build when at least 8 rows fit next to the query state
+    const char* env = getenv("HX_HNSW_IMPL");
+    const size_t fixed = (size_t)ix->ld * 4 + (size_t)ef * 8 + HX_TIE_CAP * 8 + 8 + (size_t)fr_cap * 12;
+    if (!(env && strcmp(env, "ldg") == 0) && 200 * 1024 > fixed + 8 * (size_t)ix->ld * 4) {
+      cta_RC = (uint32_t)std::min<size_t>(32, (200 * 1024 - fixed) / ((size_t)ix->ld * 4));
+      smem_launch = fixed + (size_t)cta_RC * ix->ld * 4;
+      grid = (uint32_t)std::min<size_t>(B, (size_t)ix->sm_count);
+    }
   } else {
     uint32_t ctas_per_sm = minb;
     while (ctas_per_sm > 1 && (size_t)ctas_per_sm * wpc * wstride > 200 * 1024) ctas_per_sm--;
@@ -910,8 +919,12 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     if (use_tma) {                                                                                                 \
       HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_tma<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                    (int)smem_launch));                                                             \
-      k_hnsw_search_tma<M><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, tma_wstride, tma_R);            \
-    } else if (latency) {                                                                                                 \
+      k_hnsw_search_tma<M><<<grid, tma_wpc * 32, smem_launch, stream>>>(dev, a, tma_wstride, tma_R);               \
+    } else if (latency && cta_RC) {                                                                                \
+      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_cta_tma<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                   (int)smem_launch));                                                             \
+      k_hnsw_search_cta_tma<M><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, cta_RC);                    \
+    } else if (latency) {                                                                                          \
       if (smem_launch > 48 * 1024)                                                                                 \
         HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                                      (int)smem_launch));                                                           \

@@ -121,6 +121,21 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def available_cores():
+    """Host threads this process can really use: affinity mask capped by the cgroup CPU quota (cpu.max)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        txt = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if txt[0] != "max":
+            n = max(1, min(n, int(float(txt[0]) / float(txt[1]) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -417,7 +432,7 @@ def cpu_baseline(args, ix, queries, truth):
     """The oracle (C restatement of the reference, no KV layer => an upper bound on the reference's CPU throughput)."""
     from oracle import hxo
 
-    cores = os.cpu_count() or 1
+    cores = available_cores()
     t0 = time.perf_counter()
     ora = oracle_from_device(hxo, ix, args)
     mirror_s = time.perf_counter() - t0
@@ -546,7 +561,7 @@ def run_prefilter(args):
             ids_, rows_ = ix.download_vectors(lo, min(65536, n - lo))
             ora.put_vectors(ids_, rows_)
         ora.set_entry(0, 0)
-        cores = os.cpu_count() or 1
+        cores = available_cores()
         qs = qsets[args.warmup + args.steps - 1]
         ci, cs, cc, secs = ora.search_restricted_batch(qs, k, cand_ids, offs, threads=cores)
         parity = bool(ci.tolist() == dev_ids.tolist() and cs.tobytes() == dev_sc.tobytes())
@@ -596,7 +611,7 @@ def run_reference(args):
         return
     n, dim, Q = args.n, args.dim, args.queries_per_step
     ix, setup = build_index(hx, args, 0, 0, n)
-    cores = os.cpu_count() or 1
+    cores = available_cores()
     queries = ix.generate_queries(SEED, Q, first_query=0, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
     rq = min(args.recall_queries, Q)
     truth = exact_topk_device(hx, torch, ix, queries[:rq], n, 0, K)

@@ -1,9 +1,523 @@
-// k_dense.cu — tensor-core batched distance path (configs C4/C5).  Placeholder until the tcgen05 kernel lands.
+// k_dense.cu — tensor-core batched distance path (configs C4/C5): exhaustive top-k of B queries against every row.
+//
+// The only place on this hot path where the work is a dense contraction: S[b][i] = <q_b, x_i> for B = 1024..4096
+// queries against the whole shard is a (B x d) x (d x N) GEMM with arithmetic intensity ~B flop/byte, far beyond the
+// HBM ridge.  It runs on the 5th-generation tensor cores:
+//   * operands in bf16 (a bf16 copy of the corpus is kept when hx_index_config.storage == 1), fp32 accumulation in TMEM;
+//   * tiles 128 queries x 256 rows x 64 (K), 4-stage TMA ring (cp.async.bulk.tensor, 128-byte swizzle) feeding
+//     tcgen05.mma.cta_group::1.kind::f16 issued by one elected thread; accumulators double-buffered in TMEM (2 x 256 cols);
+//   * fused epilogue: 4 warps read the accumulator with tcgen05.ld, turn it into the metric's score with the stored
+//     row norms, and keep the HX_DENSE_T best rows of the tile per query (register insertion), emitting
+//     score_bits<<32|slot keys — the B x N score matrix is never written.
+// The approximate (bf16) keys only NOMINATE candidates: k_select keeps the k' best keys per query and the exact fp32
+// scan kernel (bit-exact reference arithmetic) re-ranks them, so returned scores are exact and ordering follows the
+// reference's (score, id) rule; recall vs the exhaustive exact scan is measured, not assumed.
+//
+// Reference behaviour this stands in for: the same answer VectorIndex::search_restricted gives with every id as a
+// candidate (restricted_exact_scan, search/vector/restricted.rs:753-835), i.e. exact brute-force top-k.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "hx_index.hpp"
+#include "k_scan.cuh"
+#include "k_util.cuh"
+
+#define HXD_BM 128          // queries per tile (UMMA M)
+#define HXD_BN 256          // corpus rows per tile (UMMA N)
+#define HXD_BK 64           // bf16 elements per k-block = 128 bytes = one swizzle atom
+#define HXD_STAGES 4
+#define HXD_T 8             // best rows kept per (query, tile)
+#define HXD_THREADS 256     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-7: epilogue
+#define HXD_A_BYTES (HXD_BM * HXD_BK * 2)
+#define HXD_B_BYTES (HXD_BN * HXD_BK * 2)
+#define HXD_STAGE_BYTES (HXD_A_BYTES + HXD_B_BYTES)
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hxd_tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          hx_smem_u32(smem_dst)),
+      "l"(map), "r"(hx_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void hxd_prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void hxd_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hx_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void hxd_tmem_alloc(uint32_t* smem_out, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hx_smem_u32(smem_out)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void hxd_tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void hxd_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void hxd_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, M=128, N=256, K=16 (bf16), fp32 accumulate
+__device__ __forceinline__ void hxd_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when they have completed
+__device__ __forceinline__ void hxd_umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hx_smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = TMEM lane base+i)
+__device__ __forceinline__ void hxd_tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile stored by TMA with the 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 64 |
+// version [46,48) = 1 (Blackwell) | layout_type [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t hxd_make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)1u << 16;
+  d |= (uint64_t)64u << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)2u << 61;
+  return d;
+}
+
+struct HxDenseArgs {
+  uint32_t n_rows;            // corpus rows (unpadded)
+  uint32_t n_queries;         // B (unpadded)
+  uint32_t k_blocks;          // ldb / 64
+  uint32_t m_tiles, n_tiles;
+  const float* row_aux;       // cosine: 1/|x_i|   ; euclidean: |x_i|^2            (from the bf16-rounded rows)
+  const float* q_aux;         // cosine: 1/|q_b|   ; euclidean: |q_b|^2
+  uint64_t* keys;             // [B][n_tiles][HXD_T]
+  int32_t metric;
+};
+
+__global__ void __launch_bounds__(HXD_THREADS, 1)
+k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, HxDenseArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // HXD_STAGES x (A 16 KB | B 32 KB); the 128-byte swizzle needs 1024-byte aligned tiles: align inside the window
+  unsigned char* smem = smem_raw + ((1024u - (hx_smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* tiles = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + HXD_STAGES * HXD_STAGE_BYTES);
+  uint64_t* empty = full + HXD_STAGES;
+  uint64_t* tfull = empty + HXD_STAGES;     // [2] accumulator stage ready for the epilogue
+  uint64_t* tempty = tfull + 2;             // [2] accumulator stage drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* aux = reinterpret_cast<float*>(tmem_slot + 4);   // [2][HXD_BN] row aux of the tile being drained
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  if (threadIdx.x == 0) {
+    hxd_prefetch_tmap(&map_q);
+    hxd_prefetch_tmap(&map_x);
+    for (int s = 0; s < HXD_STAGES; ++s) {
+      hx_mbar_init(full + s, 1);
+      hx_mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      hx_mbar_init(tfull + s, 1);
+      hx_mbar_init(tempty + s, 128);
+    }
+    hx_fence_mbar_init();
+  }
+  if (warp == 2) hxd_tmem_alloc(tmem_slot, 512);
+  hxd_fence_before();
+  __syncthreads();
+  hxd_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t total_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane) =====
+    if (lane == 0) {
+      uint32_t stage = 0, ph = 0;
+      for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const uint32_t nt = tile / a.m_tiles, mt = tile % a.m_tiles;   // m fastest: neighbouring CTAs share the corpus tile (L2)
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          hx_mbar_wait(empty + stage, ph ^ 1u);
+          unsigned char* sa = tiles + (size_t)stage * HXD_STAGE_BYTES;
+          hx_mbar_expect_tx(full + stage, HXD_STAGE_BYTES);
+          hxd_tma_load_2d(sa, &map_q, full + stage, (int)(kb * HXD_BK), (int)(mt * HXD_BM));
+          hxd_tma_load_2d(sa + HXD_A_BYTES, &map_x, full + stage, (int)(kb * HXD_BK), (int)(nt * HXD_BN));
+          if (++stage == HXD_STAGES) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      // InstrDescriptor: c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 at 17 | M>>4 at 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HXD_BN >> 3) << 17) | ((uint32_t)(HXD_BM >> 4) << 24);
+      uint32_t stage = 0, ph = 0, acc = 0, acc_ph = 0;
+      for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        hx_mbar_wait(tempty + acc, acc_ph ^ 1u);   // epilogue has drained this accumulator stage
+        hxd_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * HXD_BN;
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          hx_mbar_wait(full + stage, ph);
+          hxd_fence_after();
+          const uint32_t sa = hx_smem_u32(tiles + (size_t)stage * HXD_STAGE_BYTES);
+          const uint64_t adesc = hxd_make_desc(sa), bdesc = hxd_make_desc(sa + HXD_A_BYTES);
+#pragma unroll
+          for (uint32_t k = 0; k < HXD_BK / 16; ++k)   // 16 bf16 = 32 bytes along K inside the swizzle atom: start address += 2
+            hxd_umma(tmem_d, adesc + 2ull * k, bdesc + 2ull * k, idesc, (kb | k) ? 1u : 0u);
+          hxd_umma_commit(empty + stage);             // smem slot reusable once these MMAs have read it
+          if (++stage == HXD_STAGES) { stage = 0; ph ^= 1u; }
+        }
+        hxd_umma_commit(tfull + acc);                 // accumulator complete
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread = one query row of the tile =====
+    const uint32_t q4 = warp - 4;                     // TMEM lane quarter this warp may access
+    const uint32_t row_in_tile = q4 * 32 + lane;
+    const uint32_t et = threadIdx.x - 128;            // 0..127
+    uint32_t acc = 0, acc_ph = 0;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t nt = tile / a.m_tiles, mt = tile % a.m_tiles;
+      const uint32_t qrow = mt * HXD_BM + row_in_tile;
+      const uint32_t n0 = nt * HXD_BN;
+      float* ax = aux + acc * HXD_BN;
+      for (uint32_t c = et; c < HXD_BN; c += 128) ax[c] = (n0 + c < a.n_rows) ? a.row_aux[n0 + c] : 0.f;
+      const float qa = qrow < a.n_queries ? a.q_aux[qrow] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // aux visible to the 4 epilogue warps
+      hx_mbar_wait(tfull + acc, acc_ph);
+      hxd_fence_after();
+      uint64_t best[HXD_T];
+#pragma unroll
+      for (int i = 0; i < HXD_T; ++i) best[i] = HX_KEY_MAX;
+      const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + acc * HXD_BN;
+      for (uint32_t c0 = 0; c0 < HXD_BN; c0 += 32) {
+        uint32_t r[32];
+        hxd_tmem_ld32(taddr + c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t col = c0 + j;
+          const float s = __uint_as_float(r[j]);
+          float sc;
+          if (a.metric == HXM_COSINE) sc = 0.5f - 0.5f * s * qa * ax[col];   // (1 - cos)/2
+          else sc = qa + ax[col] - 2.0f * s;                                  // |q|^2 + |x|^2 - 2<q,x>
+          sc = fmaxf(sc, 0.0f);
+          const uint64_t key = (n0 + col < a.n_rows) ? hx_make_key(sc, n0 + col) : HX_KEY_MAX;
+          if (key < best[HXD_T - 1]) {
+            best[HXD_T - 1] = key;
+#pragma unroll
+            for (int i = HXD_T - 1; i > 0; --i)
+              if (best[i] < best[i - 1]) { const uint64_t tkey = best[i]; best[i] = best[i - 1]; best[i - 1] = tkey; }
+          }
+        }
+      }
+      hxd_fence_before();
+      hxd_mbar_arrive(tempty + acc);   // 128 arrivals free the accumulator stage
+      if (qrow < a.n_queries) {
+        uint64_t* out = a.keys + ((size_t)qrow * a.n_tiles + nt) * HXD_T;
+#pragma unroll
+        for (int i = 0; i < HXD_T; ++i) out[i] = best[i];
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+    }
+  }
+  hxd_fence_before();
+  __syncthreads();
+  if (warp == 2) hxd_tmem_dealloc(tmem_base, 512);
+}
+
+// f32 rows -> bf16 rows (round to nearest even) with zero padding to ldb, plus the per-row aux term computed from the
+// ROUNDED values (so that approximate scores are self-consistent)
+__global__ void k_to_bf16(const float* __restrict__ src, size_t rows, uint32_t dim, size_t ld_src, __nv_bfloat16* __restrict__ dst,
+                          uint32_t ldb, float* __restrict__ aux, int metric) {
+  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (w >= rows) return;
+  const float* s = src + w * ld_src;
+  __nv_bfloat16* d = dst + w * (size_t)ldb;
+  float ss = 0.f;
+  for (uint32_t j = lane; j < ldb; j += 32) {
+    const float x = j < dim ? s[j] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(x);
+    d[j] = b;
+    const float xb = __bfloat162float(b);
+    ss += xb * xb;
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  if (lane == 0) aux[w] = metric == HXM_COSINE ? (ss > 0.f ? rsqrtf(ss) : 0.f) : ss;
+}
+
+// keys[q][j] hold GLOBAL slots in their low word; turn the selected ones into a per-query candidate slot list
+__global__ void k_keys_to_slots(const uint64_t* __restrict__ sel_ids_as_slots, size_t total, uint32_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = (uint32_t)sel_ids_as_slots[i];
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static hx_status make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t ldb, uint32_t box_rows) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+      hx_set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return HX_ERR_CUDA;
+    }
+    fn = (PFN_encodeTiled)p;
+  }
+  const cuuint64_t dims[2] = {ldb, rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
+  const cuuint32_t box[2] = {HXD_BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    hx_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HX_ERR_CUDA;
+  }
+  return HX_OK;
+}
+
+// lazily build the bf16 copy of the corpus
+static hx_status ensure_bf16(hx_index* ix, uint32_t ldb) {
+  if (ix->d_vec_bf16) return HX_OK;
+  const size_t n_pad = (ix->n + HXD_BN - 1) / HXD_BN * HXD_BN;
+  HX_CUDA(cudaMalloc(&ix->d_vec_bf16, n_pad * (size_t)ldb * 2));
+  HX_CUDA(cudaMemset(ix->d_vec_bf16, 0, n_pad * (size_t)ldb * 2));
+  HX_CUDA(cudaMalloc((void**)&ix->d_sqnorm, n_pad * sizeof(float)));
+  HX_CUDA(cudaMemset(ix->d_sqnorm, 0, n_pad * sizeof(float)));
+  k_to_bf16<<<(unsigned)((ix->n + 7) / 8), 256>>>(ix->d_vec, ix->n, ix->cfg.dimension, ix->ld, (__nv_bfloat16*)ix->d_vec_bf16, ldb,
+                                                  ix->d_sqnorm, ix->cfg.metric);
+  HX_CUDA(cudaGetLastError());
+  return HX_OK;
+}
 
 hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_search_params* p, uint64_t* out_ids,
                         float* out_scores, uint32_t* out_counts, hx_stats* stats) {
-  (void)ix; (void)queries; (void)B; (void)p; (void)out_ids; (void)out_scores; (void)out_counts; (void)stats;
-  hx_set_error("hx_search_dense: tensor-core path not available in this build");
-  return HX_ERR_UNSUPPORTED;
+  if (!p || p->k == 0) {
+    hx_set_error("result count must be non-zero");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (p->k > 800) {
+    hx_set_error("dense search result count must be at most 800");
+    return HX_ERR_QUERY;
+  }
+  if (ix->cfg.storage != 1) {
+    hx_set_error("hx_search_dense needs hx_index_config.storage == 1 (bf16 copy of the corpus)");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (ix->cfg.metric == HX_METRIC_MANHATTAN) {
+    hx_set_error("the L1 metric is not a contraction: use hx_search_restricted");
+    return HX_ERR_UNSUPPORTED;
+  }
+  if (p->query_dimension != 0 && p->query_dimension != ix->cfg.dimension) {
+    hx_set_error("invalid dimension: expected %u, got %u", ix->cfg.dimension, p->query_dimension);
+    return HX_ERR_INVALID_DIMENSION;
+  }
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return HX_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts) return HX_ERR_INVALID_PARAMETER;
+  if (ix->n == 0 || !ix->populated) {
+    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
+    return HX_OK;
+  }
+  const uint32_t dim = ix->cfg.dimension, k = p->k;
+  const uint32_t ldb = (dim + HXD_BK - 1) / HXD_BK * HXD_BK;
+  hx_status rc = ensure_bf16(ix, ldb);
+  if (rc) return rc;
+  const size_t n = ix->n;
+  const uint32_t m_tiles = (uint32_t)((B + HXD_BM - 1) / HXD_BM), n_tiles = (uint32_t)((n + HXD_BN - 1) / HXD_BN);
+  const size_t B_pad = (size_t)m_tiles * HXD_BM, n_pad = (size_t)n_tiles * HXD_BN;
+  const uint32_t kprime = (uint32_t)std::min<size_t>(std::max<uint32_t>(4 * k, 64), std::min<size_t>(800, n));
+
+  // ---- device buffers (freed at the end; this path is for large batches, allocation cost is amortised) ----
+  float *d_q = nullptr, *d_qaux = nullptr, *d_sel_sc = nullptr, *d_out_sc = nullptr, *d_qhdr = nullptr;
+  __nv_bfloat16* d_qb = nullptr;
+  uint64_t *d_keys = nullptr, *d_sel_ids = nullptr, *d_out_ids = nullptr, *d_keys2 = nullptr;
+  uint32_t *d_sel_cnt = nullptr, *d_out_cnt = nullptr, *d_status = nullptr, *d_cslots = nullptr, *d_err = nullptr;
+  uint64_t* d_coffs = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_q); cudaFree(d_qaux); cudaFree(d_sel_sc); cudaFree(d_out_sc); cudaFree(d_qhdr); cudaFree(d_qb); cudaFree(d_keys);
+    cudaFree(d_sel_ids); cudaFree(d_out_ids); cudaFree(d_keys2); cudaFree(d_sel_cnt); cudaFree(d_out_cnt); cudaFree(d_status);
+    cudaFree(d_cslots); cudaFree(d_err); cudaFree(d_coffs);
+  };
+#define HXD_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      hx_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      cleanup();                                                                               \
+      return _e == cudaErrorMemoryAllocation ? HX_ERR_OUT_OF_MEMORY : HX_ERR_CUDA;             \
+    }                                                                                          \
+  } while (0)
+  const size_t nkeys = B * (size_t)n_tiles * HXD_T;
+  HXD_CUDA(cudaMalloc((void**)&d_q, B * (size_t)dim * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_qhdr, B * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_status, B * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_qb, B_pad * (size_t)ldb * 2));
+  HXD_CUDA(cudaMalloc((void**)&d_qaux, B_pad * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_keys, nkeys * 8));
+  HXD_CUDA(cudaMalloc((void**)&d_sel_ids, B * (size_t)kprime * 8));
+  HXD_CUDA(cudaMalloc((void**)&d_sel_sc, B * (size_t)kprime * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_sel_cnt, B * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_cslots, B * (size_t)kprime * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_coffs, (B + 1) * 8));
+  HXD_CUDA(cudaMalloc((void**)&d_keys2, B * (size_t)kprime * 8));
+  HXD_CUDA(cudaMalloc((void**)&d_out_ids, B * (size_t)k * 8));
+  HXD_CUDA(cudaMalloc((void**)&d_out_sc, B * (size_t)k * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_out_cnt, B * 4));
+  HXD_CUDA(cudaMalloc((void**)&d_err, 4));
+  HXD_CUDA(cudaMemset(d_err, 0, 4));
+  HXD_CUDA(cudaMemset(d_sel_ids, 0xFF, B * (size_t)kprime * 8));   // unfilled nominee slots read as HX_ABSENT
+  HXD_CUDA(cudaMemset(d_qb, 0, B_pad * (size_t)ldb * 2));
+  HXD_CUDA(cudaMemset(d_qaux, 0, B_pad * 4));
+  HXD_CUDA(cudaMemcpy(d_q, queries, B * (size_t)dim * 4, cudaMemcpyHostToDevice));
+  uint32_t launches = 0;
+  // validation + exact headers (same order of checks as every other entry point)
+  float limit = 0.f;
+  bool has_limit = false;
+  if (ix->cfg.metric == HX_METRIC_EUCLIDEAN) {
+    const double exact = std::sqrt((double)FLT_MAX / ((double)dim * 8.0));
+    limit = (float)exact;
+    if ((double)limit > exact) limit = std::nextafter(limit, 0.0f);
+    has_limit = true;
+  }
+  k_validate_and_header<<<(unsigned)((B + 7) / 8), 256>>>(d_q, B, dim, dim, ix->cfg.metric, limit, has_limit ? 1 : 0, d_qhdr, d_status);
+  k_to_bf16<<<(unsigned)((B + 7) / 8), 256>>>(d_q, B, dim, dim, d_qb, ldb, d_qaux, ix->cfg.metric);
+  launches += 2;
+  HXD_CUDA(cudaGetLastError());
+  {
+    std::vector<uint32_t> st(B);
+    HXD_CUDA(cudaMemcpy(st.data(), d_status, B * 4, cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b)
+      if (st[b] != HX_ST_OK) {
+        cleanup();
+        const uint32_t code = st[b] >> 24;
+        hx_set_error_index(st[b] & 0xffffffu);
+        hx_set_error("query %zu failed validation (code %u)", b, code);
+        return code == HX_ST_COMPONENT ? HX_ERR_INVALID_VECTOR_COMPONENT
+                                       : (code == HX_ST_ZERO_NORM ? HX_ERR_ZERO_NORM_COSINE : HX_ERR_MAGNITUDE_EXCEEDED);
+      }
+  }
+  // ---- tensor-core pass ----
+  CUtensorMap map_q, map_x;
+  if ((rc = make_map(&map_q, d_qb, B_pad, ldb, HXD_BM)) || (rc = make_map(&map_x, ix->d_vec_bf16, n_pad, ldb, HXD_BN))) {
+    cleanup();
+    return rc;
+  }
+  HxDenseArgs a{};
+  a.n_rows = (uint32_t)n;
+  a.n_queries = (uint32_t)B;
+  a.k_blocks = ldb / HXD_BK;
+  a.m_tiles = m_tiles;
+  a.n_tiles = n_tiles;
+  a.row_aux = ix->d_sqnorm;
+  a.q_aux = d_qaux;
+  a.keys = d_keys;
+  a.metric = ix->cfg.metric;
+  const size_t smem = (size_t)HXD_STAGES * HXD_STAGE_BYTES + 16 * 8 + 16 + 2 * HXD_BN * 4 + 1024;
+  HXD_CUDA(cudaFuncSetAttribute(k_dense_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint32_t grid = (uint32_t)std::min<size_t>((size_t)m_tiles * n_tiles, (size_t)ix->sm_count);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, 0);
+  k_dense_scores<<<grid, HXD_THREADS, smem>>>(map_q, map_x, a);
+  cudaEventRecord(e1, 0);
+  launches++;
+  HXD_CUDA(cudaGetLastError());
+  // ---- k' nominees per query by approximate key, then the exact re-rank with the reference arithmetic ----
+  HxDev dev = ix->dev();
+  HxSelectArgs s1{};
+  s1.keys = d_keys;
+  s1.cand_slots = nullptr;
+  s1.cand_offsets = nullptr;
+  s1.q_status = d_status;
+  s1.B = (uint32_t)B;
+  s1.k = kprime;
+  s1.shared_set = 2;   // keys carry global slots in their low word (no candidate indirection)
+  s1.n_shared = (uint64_t)n_tiles * HXD_T;
+  s1.out_ids = d_sel_ids;
+  s1.out_scores = d_sel_sc;
+  s1.out_counts = d_sel_cnt;
+  k_select<<<(unsigned)std::min<size_t>(B, 65535), HX_SEL_THREADS>>>(dev, s1);
+  k_keys_to_slots<<<(unsigned)((B * (size_t)kprime + 255) / 256), 256>>>(d_sel_ids, B * (size_t)kprime, d_cslots);
+  launches += 2;
+  {
+    std::vector<uint64_t> offs(B + 1);
+    for (size_t b = 0; b <= B; ++b) offs[b] = b * (uint64_t)kprime;
+    HXD_CUDA(cudaMemcpy(d_coffs, offs.data(), (B + 1) * 8, cudaMemcpyHostToDevice));
+  }
+  HxScanArgs sa{};
+  sa.queries = d_q;
+  sa.q_hdr = d_qhdr;
+  sa.q_status = d_status;
+  sa.B = (uint32_t)B;
+  sa.cand_slots = d_cslots;
+  sa.cand_offsets = d_coffs;
+  sa.keys = d_keys2;
+  sa.shared_set = 0;
+  sa.n_shared = 0;
+  sa.chunk = 32 * ((kprime + 31) / 32);
+  sa.err_flags = d_err;
+  {
+    dim3 g(1, (unsigned)std::min<size_t>(B, 65535));
+    const uint32_t sm = ix->ld * 4u;
+    if (ix->cfg.metric == HX_METRIC_COSINE) k_scan<HXM_COSINE><<<g, HX_SCAN_THREADS, sm>>>(dev, sa);
+    else k_scan<HXM_EUCLIDEAN><<<g, HX_SCAN_THREADS, sm>>>(dev, sa);
+  }
+  HxSelectArgs s2{};
+  s2.keys = d_keys2;
+  s2.cand_slots = d_cslots;
+  s2.cand_offsets = d_coffs;
+  s2.q_status = d_status;
+  s2.B = (uint32_t)B;
+  s2.k = k;
+  s2.shared_set = 0;
+  s2.n_shared = 0;
+  s2.out_ids = d_out_ids;
+  s2.out_scores = d_out_sc;
+  s2.out_counts = d_out_cnt;
+  k_select<<<(unsigned)std::min<size_t>(B, 65535), HX_SEL_THREADS>>>(dev, s2);
+  launches += 2;
+  HXD_CUDA(cudaGetLastError());
+  HXD_CUDA(cudaMemcpy(out_ids, d_out_ids, B * (size_t)k * 8, cudaMemcpyDeviceToHost));
+  HXD_CUDA(cudaMemcpy(out_scores, d_out_sc, B * (size_t)k * 4, cudaMemcpyDeviceToHost));
+  HXD_CUDA(cudaMemcpy(out_counts, d_out_cnt, B * 4, cudaMemcpyDeviceToHost));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) {
+    ix->last_kernel_ms = ms;
+    ix->last_kernel_launches = 1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (stats) {
+    stats->kernel_launches = launches;
+    stats->distance_computations = (uint64_t)B * n;
+    stats->algorithmic_bytes = (uint64_t)n * ldb * 2;   // corpus streamed once; the bound is the tensor pipe: 2*B*N*d flop
+    stats->reserved = (uint64_t)(2.0 * (double)B * (double)n * (double)ldb);   // flop of the contraction
+  }
+  cleanup();
+  return HX_OK;
 }

@@ -33,7 +33,7 @@ struct HxScanArgs {
 };
 
 template <int METRIC>
-__global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan(HxDev ix, HxScanArgs a) {
+static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan(HxDev ix, HxScanArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* sq = reinterpret_cast<float*>(smem);
   const uint32_t tid = threadIdx.x, t = tid & 7u, oct = tid >> 3;
@@ -85,9 +85,9 @@ struct HxSelectArgs {
   const uint64_t* cand_offsets;
   const uint32_t* q_status;
   uint32_t B, k;                 // k as requested; clamped to |C_q| per query (restricted.rs:200-213)
-  uint32_t shared_set;
+  uint32_t shared_set;           // 0: per-query CSR sets, 1: one shared set, 2: keys carry global slots (no indirection)
   uint64_t n_shared;
-  uint64_t* out_ids;             // [B][k]
+  uint64_t* out_ids;             // [B][k] (mode 2: the slot itself)
   float* out_scores;
   uint32_t* out_counts;
 };
@@ -110,7 +110,7 @@ __device__ __forceinline__ void hx_bitonic_sort_2048(uint64_t* s, uint32_t tid) 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSelectArgs a) {
+static __global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSelectArgs a) {
   __shared__ uint64_t buf[2 * HX_SEL_HALF];   // [0,1024): best so far (sorted), [1024,2048): incoming survivors
   __shared__ uint32_t s_cnt;
   __shared__ uint64_t s_thr;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSelectArg
       const uint64_t key = buf[i];
       if (key != HX_KEY_MAX) {
         const uint32_t rank = (uint32_t)(key & 0xffffffffu);
-        a.out_ids[(size_t)q * a.k + i] = ix.ids[slots[rank]];
+        a.out_ids[(size_t)q * a.k + i] = a.shared_set == 2 ? (uint64_t)rank : ix.ids[slots[rank]];
         a.out_scores[(size_t)q * a.k + i] = hx_key_score(key);
         cnt++;
       }
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSelectArg
 }
 
 // ---- candidate id -> slot mapping (restricted.rs:615-659: ids without a vector row are skipped) ----------
-__global__ void k_map_candidates(const uint64_t* __restrict__ ids_sorted, uint32_t n, const uint64_t* __restrict__ cand,
+static __global__ void k_map_candidates(const uint64_t* __restrict__ ids_sorted, uint32_t n, const uint64_t* __restrict__ cand,
                                  uint64_t n_cand, uint32_t* __restrict__ out_slots, int contiguous, uint64_t first_id) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cand) return;

@@ -11,7 +11,7 @@
 // ValidatedMetricVector::try_new (domain.rs:113-154) for each of `count` vectors of `dim` floats with
 // row stride `ld`, plus D::new_header (cosine norm, cosine.rs:89-93). One warp per vector.
 // Check order: finiteness (first bad index) -> cosine zero norm -> magnitude (first bad index).
-__global__ void k_validate_and_header(const float* __restrict__ v, size_t count, uint32_t dim, size_t ld, int metric,
+static __global__ void k_validate_and_header(const float* __restrict__ v, size_t count, uint32_t dim, size_t ld, int metric,
                                       float limit, int has_limit, float* __restrict__ hdr_out,
                                       uint32_t* __restrict__ status_out) {
   const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -55,7 +55,7 @@ __device__ __forceinline__ float hx_gauss(uint64_t key) {
   return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 // row i = normalise(centroid[c(i)] + sigma * N(0,I)); one warp per row; `stream_tag` separates corpus / queries
-__global__ void k_generate_mixture(float* __restrict__ out, size_t count, uint32_t dim, size_t ld, uint64_t seed,
+static __global__ void k_generate_mixture(float* __restrict__ out, size_t count, uint32_t dim, size_t ld, uint64_t seed,
                                    uint32_t n_centroids, float sigma, uint64_t first_index, uint64_t stream_tag) {
   const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
@@ -83,11 +83,11 @@ __global__ void k_generate_mixture(float* __restrict__ out, size_t count, uint32
 // fixed random projection A[dim][r] plus a little isotropic noise, then unit-normalised.  Unlike isolated isotropic
 // clusters in 768-d (intrinsic dimension 768, where every graph index degrades), this has intrinsic dimension ~r,
 // like real sentence/document embeddings.  One warp per row; requires r <= 64.
-__global__ void k_generate_proj(float* __restrict__ A, uint32_t dim, uint32_t r, uint64_t seed) {
+static __global__ void k_generate_proj(float* __restrict__ A, uint32_t dim, uint32_t r, uint64_t seed) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < dim * r) A[i] = hx_gauss(seed * 0x9e3779b97f4a7c15ull + 0x7777000000000000ull + i) * rsqrtf((float)r);
 }
-__global__ void k_generate_latent(float* __restrict__ out, size_t count, uint32_t dim, size_t ld, uint64_t seed,
+static __global__ void k_generate_latent(float* __restrict__ out, size_t count, uint32_t dim, size_t ld, uint64_t seed,
                                   uint32_t n_centroids, float sigma, uint64_t first_index, uint64_t stream_tag,
                                   const float* __restrict__ A, uint32_t r, float eps) {
   const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -126,13 +126,13 @@ __global__ void k_generate_latent(float* __restrict__ out, size_t count, uint32_
   for (uint32_t j = dim + lane; j < ld; j += 32) row[j] = 0.f;
 }
 
-__global__ void k_iota_ids(uint64_t* ids, size_t n, uint64_t first) {
+static __global__ void k_iota_ids(uint64_t* ids, size_t n, uint64_t first) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ids[i] = first + i;
 }
 
 // ---- merge of per-shard top-k lists: one warp per query, lane s walks shard s's sorted list -------
-__global__ void k_merge_topk(const uint64_t* __restrict__ all_ids, const float* __restrict__ all_scores,
+static __global__ void k_merge_topk(const uint64_t* __restrict__ all_ids, const float* __restrict__ all_scores,
                              const uint32_t* __restrict__ all_counts, uint32_t n_shards, size_t B, uint32_t k,
                              uint64_t* __restrict__ out_ids, float* __restrict__ out_scores,
                              uint32_t* __restrict__ out_counts) {

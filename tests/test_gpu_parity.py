@@ -468,3 +468,40 @@ def test_device_build(gm, om, n, dim, m):
     gpu.build(levels=lv)
     gi2 = gpu.graph_info()
     assert gi2["entry_point"] == 102 and gi2["max_layer"] == 3
+
+
+# ---- dense tensor-core path (tcgen05 bf16 contraction nominates, exact fp32 re-rank decides) -------------------------------------
+@pytest.mark.parametrize("gm,om,n,dim,B", [(hx.Metric.Cosine, hxo.COSINE, 5000, 768, 300),
+                                          (hx.Metric.Euclidean, hxo.EUCLIDEAN, 3000, 100, 130),
+                                          (hx.Metric.Cosine, hxo.COSINE, 700, 64, 5)])
+def test_dense_tensor_core_path(gm, om, n, dim, B):
+    rng = np.random.default_rng(n + dim)
+    lat = rng.standard_normal((n, 16)).astype(np.float32)
+    proj = rng.standard_normal((16, dim)).astype(np.float32)
+    rows = (lat @ proj + 0.05 * rng.standard_normal((n, dim))).astype(np.float32)
+    queries = (rng.standard_normal((B, 16)).astype(np.float32) @ proj).astype(np.float32)
+    if om == hxo.COSINE:
+        rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    ids = np.arange(n, dtype=np.uint64) + 7
+    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("d", "embedding", dim), storage=1)
+    gpu.load_vectors(ids, rows)
+    gpu.load_graph(0, ids[:1], [0, 0], [])
+    gpu.set_entry(int(ids[0]), 0)
+    k = 10
+    di, ds, dc = gpu.search_dense_batch(queries, hx.SearchParams.strict(k))
+    ei, es, ec = gpu.search_restricted_batch(queries, hx.SearchParams.strict(k), hx.RestrictedVectorCandidates(ids))
+    assert dc.tolist() == ec.tolist() == [k] * B
+    hit = 0
+    for q in range(B):
+        exact = {int(i): es[q, j].tobytes() for j, i in enumerate(ei[q])}
+        hit += len(set(di[q].tolist()) & set(exact))
+        for j, i in enumerate(di[q]):                      # every returned score is the exact fp32 reference score
+            if int(i) in exact:
+                assert ds[q, j].tobytes() == exact[int(i)]
+        keys = [(float(ds[q, j]), int(di[q, j])) for j in range(k)]
+        assert keys == sorted(keys)                        # (score, id) order
+    assert hit / float(B * k) >= 0.99
+    storage0 = hx.VectorIndex(gm, hx.VectorIndexConfig("d0", "embedding", dim))
+    storage0.load_vectors(ids[:10], rows[:10])
+    with pytest.raises(hx.HelixDbError):
+        storage0.search_dense_batch(queries[:1], hx.SearchParams.strict(1))

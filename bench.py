@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
-    ap.add_argument("--workload", default="hnsw", choices=["hnsw", "prefilter"])
+    ap.add_argument("--workload", default="hnsw", choices=["hnsw", "prefilter", "dense"])
     ap.add_argument("--recipe", default="embedding", choices=sorted(RECIPES))
     a = ap.parse_args()
     global KIND, SIGMA
@@ -594,6 +594,60 @@ def run_prefilter(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_dense(args):
+    """Config C4-shaped (per GPU): exhaustive top-10 of a large query batch against the whole shard through the tensor
+    cores (hx_search_dense: tcgen05 bf16 contraction -> per-tile nominees -> exact fp32 re-rank)."""
+    import torch
+
+    import helix_db_b200 as hx
+
+    torch.cuda.set_device(0)
+    n, dim, k = args.n, args.dim, K
+    B = args.queries_per_step if args.queries_per_step != 8192 else 1024
+    metric = hx.Metric.Cosine if args.metric == "cosine" else hx.Metric.Euclidean
+    ix = hx.VectorIndex(metric, hx.VectorIndexConfig("dense", "embedding", dim), device=0, storage=1)
+    ix.generate_vectors(0, n, SEED, N_CENTROIDS, SIGMA, KIND)
+    ix.load_graph(0, np.array([0], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
+    ix.set_entry(0, 0)
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    qsets = [ix.generate_queries(SEED, B, first_query=s * B, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
+             for s in range(args.steps + args.warmup)]
+    params = hx.SearchParams.strict(k)
+    for s in range(args.warmup):
+        ix.search_dense_batch(qsets[s], params)
+    sampler = ClockSampler(0)
+    sampler.start()
+    kms, t0 = 0.0, time.perf_counter()
+    last = None
+    for s in range(args.steps):
+        last = ix.search_dense_batch(qsets[args.warmup + s], params)
+        kms += ix.last_kernel_ms()[0]
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ldb = (dim + 63) // 64 * 64
+    flop = 2.0 * B * n * ldb
+    kernel_ms = kms / args.steps
+    rq = min(128, B)
+    truth = exact_topk_device(hx, torch, ix, qsets[args.warmup + args.steps - 1][:rq], n, 0, k)
+    rec = recall_at_k(last[0][:rq], truth)
+    line = {"metric": "queries/sec, exhaustive top-10 through the tensor cores (config C4 shape, one shard)",
+            "value": round(args.steps * B / wall, 1), "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(wall / args.steps * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (fp32 accumulate) + f32 exact re-rank", "data": "synthetic",
+            "recall_at_10": round(rec, 4),
+            "config": {"workload": f"dense: {B} queries x {n} rows x d={dim}, k={k}, host buffers (hx_search_dense)",
+                       "recipe": args.recipe},
+            "roofline": {"bound": "tensor", "kernel": "k_dense_scores", "achieved": round(flop / (kernel_ms * 1e-3) / 1e12, 1),
+                         "peak": tf_peak, "unit": "TFLOP/s", "frac": round(flop / (kernel_ms * 1e-3) / 1e12 / tf_peak, 4),
+                         "traffic": ncu_traffic("k_dense_scores"), "flop_per_launch": flop,
+                         "kernel_ms_per_launch": round(kernel_ms, 4), "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"},
+            "gpu_launches": args.steps * 7, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust reference cannot be built
     here: no rustc/cargo, un-vendored SlateDB fork) on all host cores, same config, metric and unit."""
@@ -652,5 +706,7 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.workload == "prefilter":
         run_prefilter(a)
+    elif a.workload == "dense":
+        run_dense(a)
     else:
         run_ours(a)

@@ -197,6 +197,7 @@ void HxScratch::destroy() {
   d_qstatus.release(); d_out_counts.release(); d_qstats.release(); d_err.release(); d_epochs.release();
   d_cand_slots.release(); d_out_ids.release(); d_cand_ids.release(); d_cand_offsets.release(); d_keys.release();
   d_stamps.release();
+  for (auto& m : misc) m.release();
   h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
   h_counts.release(); h_qstats.release(); h_status.release(); h_err.release();
 }

@@ -83,6 +83,7 @@ struct HxScratch {
   DevBuf<uint32_t> d_qstatus, d_out_counts, d_qstats, d_err, d_epochs, d_cand_slots;
   DevBuf<uint64_t> d_out_ids, d_cand_ids, d_cand_offsets, d_keys;
   DevBuf<uint8_t> d_stamps;
+  DevBuf<uint8_t> misc[16];   // dense path buffers (kept across calls)
   size_t stamp_stride = 0;
   uint32_t stamp_grid = 0;
   size_t stamp_n = 0;

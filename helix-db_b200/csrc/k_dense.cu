@@ -30,7 +30,7 @@
 #define HXD_BN 256          // corpus rows per tile (UMMA N)
 #define HXD_BK 64           // bf16 elements per k-block = 128 bytes = one swizzle atom
 #define HXD_STAGES 4
-#define HXD_T 8             // best rows kept per (query, tile)
+#define HXD_T 16            // best rows kept per (query, work unit = one m-tile x a contiguous run of n-tiles)
 #define HXD_THREADS 256     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-7: epilogue
 #define HXD_A_BYTES (HXD_BM * HXD_BK * 2)
 #define HXD_B_BYTES (HXD_BN * HXD_BK * 2)
@@ -105,9 +105,10 @@ struct HxDenseArgs {
   uint32_t n_queries;         // B (unpadded)
   uint32_t k_blocks;          // ldb / 64
   uint32_t m_tiles, n_tiles;
+  uint32_t n_split;           // work unit u: m-tile u % m_tiles, n-tiles [r*n_tiles/n_split, (r+1)*n_tiles/n_split), r = u / m_tiles
   const float* row_aux;       // cosine: 1/|x_i|   ; euclidean: |x_i|^2            (from the bf16-rounded rows)
   const float* q_aux;         // cosine: 1/|q_b|   ; euclidean: |q_b|^2
-  uint64_t* keys;             // [B][n_tiles][HXD_T]
+  uint64_t* keys;             // [B][n_split][HXD_T]
   int32_t metric;
 };
 
@@ -143,22 +144,26 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   __syncthreads();
   hxd_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t total_tiles = a.m_tiles * a.n_tiles;
+  const uint32_t total_units = a.m_tiles * a.n_split;
 
   if (warp == 0) {
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
       uint32_t stage = 0, ph = 0;
-      for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const uint32_t nt = tile / a.m_tiles, mt = tile % a.m_tiles;   // m fastest: neighbouring CTAs share the corpus tile (L2)
-        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-          hx_mbar_wait(empty + stage, ph ^ 1u);
-          unsigned char* sa = tiles + (size_t)stage * HXD_STAGE_BYTES;
-          hx_mbar_expect_tx(full + stage, HXD_STAGE_BYTES);
-          hxd_tma_load_2d(sa, &map_q, full + stage, (int)(kb * HXD_BK), (int)(mt * HXD_BM));
-          hxd_tma_load_2d(sa + HXD_A_BYTES, &map_x, full + stage, (int)(kb * HXD_BK), (int)(nt * HXD_BN));
-          if (++stage == HXD_STAGES) { stage = 0; ph ^= 1u; }
-        }
+      for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+        // units with the same n-range and different m-tiles run on neighbouring CTAs in step: the corpus tile is read
+        // from HBM once and served to the others by L2
+        const uint32_t mt = u % a.m_tiles, r = u / a.m_tiles;
+        const uint32_t nt0 = (uint32_t)((uint64_t)r * a.n_tiles / a.n_split), nt1 = (uint32_t)((uint64_t)(r + 1) * a.n_tiles / a.n_split);
+        for (uint32_t nt = nt0; nt < nt1; ++nt)
+          for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+            hx_mbar_wait(empty + stage, ph ^ 1u);
+            unsigned char* sa = tiles + (size_t)stage * HXD_STAGE_BYTES;
+            hx_mbar_expect_tx(full + stage, HXD_STAGE_BYTES);
+            hxd_tma_load_2d(sa, &map_q, full + stage, (int)(kb * HXD_BK), (int)(mt * HXD_BM));
+            hxd_tma_load_2d(sa + HXD_A_BYTES, &map_x, full + stage, (int)(kb * HXD_BK), (int)(nt * HXD_BN));
+            if (++stage == HXD_STAGES) { stage = 0; ph ^= 1u; }
+          }
       }
     }
   } else if (warp == 1) {
@@ -167,7 +172,10 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       // InstrDescriptor: c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 at 17 | M>>4 at 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HXD_BN >> 3) << 17) | ((uint32_t)(HXD_BM >> 4) << 24);
       uint32_t stage = 0, ph = 0, acc = 0, acc_ph = 0;
-      for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+       const uint32_t r = u / a.m_tiles;
+       const uint32_t nt0 = (uint32_t)((uint64_t)r * a.n_tiles / a.n_split), nt1 = (uint32_t)((uint64_t)(r + 1) * a.n_tiles / a.n_split);
+       for (uint32_t nt = nt0; nt < nt1; ++nt) {
         hx_mbar_wait(tempty + acc, acc_ph ^ 1u);   // epilogue has drained this accumulator stage
         hxd_fence_after();
         const uint32_t tmem_d = tmem_base + acc * HXD_BN;
@@ -184,6 +192,7 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         hxd_umma_commit(tfull + acc);                 // accumulator complete
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+       }
       }
     }
   } else if (warp >= 4) {
@@ -192,48 +201,57 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const uint32_t row_in_tile = q4 * 32 + lane;
     const uint32_t et = threadIdx.x - 128;            // 0..127
     uint32_t acc = 0, acc_ph = 0;
-    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const uint32_t nt = tile / a.m_tiles, mt = tile % a.m_tiles;
+    for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const uint32_t mt = u % a.m_tiles, r = u / a.m_tiles;
+      const uint32_t nt0 = (uint32_t)((uint64_t)r * a.n_tiles / a.n_split), nt1 = (uint32_t)((uint64_t)(r + 1) * a.n_tiles / a.n_split);
       const uint32_t qrow = mt * HXD_BM + row_in_tile;
-      const uint32_t n0 = nt * HXD_BN;
-      float* ax = aux + acc * HXD_BN;
-      for (uint32_t c = et; c < HXD_BN; c += 128) ax[c] = (n0 + c < a.n_rows) ? a.row_aux[n0 + c] : 0.f;
       const float qa = qrow < a.n_queries ? a.q_aux[qrow] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // aux visible to the 4 epilogue warps
-      hx_mbar_wait(tfull + acc, acc_ph);
-      hxd_fence_after();
+      // running best-T of this query over the whole run of tiles: after a few tiles the threshold rejects almost every
+      // column, so the (warp-divergent) insertion path is rarely entered and the epilogue stays under the MMA time
       uint64_t best[HXD_T];
 #pragma unroll
       for (int i = 0; i < HXD_T; ++i) best[i] = HX_KEY_MAX;
-      const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + acc * HXD_BN;
-      for (uint32_t c0 = 0; c0 < HXD_BN; c0 += 32) {
-        uint32_t r[32];
-        hxd_tmem_ld32(taddr + c0, r);
+      for (uint32_t nt = nt0; nt < nt1; ++nt) {
+        const uint32_t n0 = nt * HXD_BN;
+        float* ax = aux + acc * HXD_BN;
+        for (uint32_t c = et; c < HXD_BN; c += 128) ax[c] = (n0 + c < a.n_rows) ? a.row_aux[n0 + c] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // aux visible to the 4 epilogue warps
+        hx_mbar_wait(tfull + acc, acc_ph);
+        hxd_fence_after();
+        const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + acc * HXD_BN;
+        const uint32_t thr_hi = (uint32_t)(best[HXD_T - 1] >> 32);
+        for (uint32_t c0 = 0; c0 < HXD_BN; c0 += 32) {
+          uint32_t rr[32];
+          hxd_tmem_ld32(taddr + c0, rr);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const uint32_t col = c0 + j;
-          const float s = __uint_as_float(r[j]);
-          float sc;
-          if (a.metric == HXM_COSINE) sc = 0.5f - 0.5f * s * qa * ax[col];   // (1 - cos)/2
-          else sc = qa + ax[col] - 2.0f * s;                                  // |q|^2 + |x|^2 - 2<q,x>
-          sc = fmaxf(sc, 0.0f);
-          const uint64_t key = (n0 + col < a.n_rows) ? hx_make_key(sc, n0 + col) : HX_KEY_MAX;
-          if (key < best[HXD_T - 1]) {
-            best[HXD_T - 1] = key;
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t col = c0 + j;
+            const float s = __uint_as_float(rr[j]);
+            float sc;
+            if (a.metric == HXM_COSINE) sc = 0.5f - 0.5f * s * qa * ax[col];   // (1 - cos)/2
+            else sc = qa + ax[col] - 2.0f * s;                                  // |q|^2 + |x|^2 - 2<q,x>
+            sc = fmaxf(sc, 0.0f);
+            // cheap 32-bit pre-test against the score of the current T-th best (stale within the tile is fine: it only admits more)
+            if (__float_as_uint(sc) <= thr_hi && n0 + col < a.n_rows) {
+              const uint64_t key = hx_make_key(sc, n0 + col);
+              if (key < best[HXD_T - 1]) {
+                best[HXD_T - 1] = key;
 #pragma unroll
-            for (int i = HXD_T - 1; i > 0; --i)
-              if (best[i] < best[i - 1]) { const uint64_t tkey = best[i]; best[i] = best[i - 1]; best[i - 1] = tkey; }
+                for (int i = HXD_T - 1; i > 0; --i)
+                  if (best[i] < best[i - 1]) { const uint64_t tkey = best[i]; best[i] = best[i - 1]; best[i - 1] = tkey; }
+              }
+            }
           }
         }
+        hxd_fence_before();
+        hxd_mbar_arrive(tempty + acc);   // 128 arrivals free the accumulator stage
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
-      hxd_fence_before();
-      hxd_mbar_arrive(tempty + acc);   // 128 arrivals free the accumulator stage
       if (qrow < a.n_queries) {
-        uint64_t* out = a.keys + ((size_t)qrow * a.n_tiles + nt) * HXD_T;
+        uint64_t* out = a.keys + ((size_t)qrow * a.n_split + r) * HXD_T;
 #pragma unroll
         for (int i = 0; i < HXD_T; ++i) out[i] = best[i];
       }
-      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
   }
   hxd_fence_before();
@@ -351,17 +369,11 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   const size_t B_pad = (size_t)m_tiles * HXD_BM, n_pad = (size_t)n_tiles * HXD_BN;
   const uint32_t kprime = (uint32_t)std::min<size_t>(std::max<uint32_t>(4 * k, 64), std::min<size_t>(800, n));
 
-  // ---- device buffers (freed at the end; this path is for large batches, allocation cost is amortised) ----
-  float *d_q = nullptr, *d_qaux = nullptr, *d_sel_sc = nullptr, *d_out_sc = nullptr, *d_qhdr = nullptr;
-  __nv_bfloat16* d_qb = nullptr;
-  uint64_t *d_keys = nullptr, *d_sel_ids = nullptr, *d_out_ids = nullptr, *d_keys2 = nullptr;
-  uint32_t *d_sel_cnt = nullptr, *d_out_cnt = nullptr, *d_status = nullptr, *d_cslots = nullptr, *d_err = nullptr;
-  uint64_t* d_coffs = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_q); cudaFree(d_qaux); cudaFree(d_sel_sc); cudaFree(d_out_sc); cudaFree(d_qhdr); cudaFree(d_qb); cudaFree(d_keys);
-    cudaFree(d_sel_ids); cudaFree(d_out_ids); cudaFree(d_keys2); cudaFree(d_sel_cnt); cudaFree(d_out_cnt); cudaFree(d_status);
-    cudaFree(d_cslots); cudaFree(d_err); cudaFree(d_coffs);
-  };
+  // ---- device buffers: kept in a pooled scratch set across calls ----
+  HxScratch* scr = nullptr;
+  if ((rc = hx_acquire_scratch(ix, &scr))) return rc;
+  struct Rel { hx_index* ix; HxScratch* s; ~Rel() { hx_release_scratch(ix, s); } } rel{ix, scr};
+  auto cleanup = [&]() {};
 #define HXD_CUDA(call)                                                                         \
   do {                                                                                         \
     cudaError_t _e = (call);                                                                   \
@@ -371,23 +383,33 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
       return _e == cudaErrorMemoryAllocation ? HX_ERR_OUT_OF_MEMORY : HX_ERR_CUDA;             \
     }                                                                                          \
   } while (0)
-  const size_t nkeys = B * (size_t)n_tiles * HXD_T;
-  HXD_CUDA(cudaMalloc((void**)&d_q, B * (size_t)dim * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_qhdr, B * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_status, B * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_qb, B_pad * (size_t)ldb * 2));
-  HXD_CUDA(cudaMalloc((void**)&d_qaux, B_pad * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_keys, nkeys * 8));
-  HXD_CUDA(cudaMalloc((void**)&d_sel_ids, B * (size_t)kprime * 8));
-  HXD_CUDA(cudaMalloc((void**)&d_sel_sc, B * (size_t)kprime * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_sel_cnt, B * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_cslots, B * (size_t)kprime * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_coffs, (B + 1) * 8));
-  HXD_CUDA(cudaMalloc((void**)&d_keys2, B * (size_t)kprime * 8));
-  HXD_CUDA(cudaMalloc((void**)&d_out_ids, B * (size_t)k * 8));
-  HXD_CUDA(cudaMalloc((void**)&d_out_sc, B * (size_t)k * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_out_cnt, B * 4));
-  HXD_CUDA(cudaMalloc((void**)&d_err, 4));
+  const size_t nkeys_calc_unused = 0;
+  (void)nkeys_calc_unused;
+  // runs per m-tile: enough units to fill the SMs, and enough that one run's best-T comfortably covers its share of the
+  // k' nominees even when the true neighbours cluster in id space (8x head-room)
+  const uint32_t n_split = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_tiles,
+      std::max<size_t>(std::max<size_t>(4, (size_t)ix->sm_count / m_tiles), (8 * (size_t)kprime + HXD_T - 1) / HXD_T)));
+  const size_t nkeys = B * (size_t)n_split * HXD_T;
+  int mi = 0;
+  auto take = [&](size_t bytes, void** out) -> hx_status {
+    hx_status r = scr->misc[mi].reserve(bytes + 256);
+    *out = scr->misc[mi].p;
+    ++mi;
+    return r;
+  };
+  float *d_q, *d_qaux, *d_sel_sc, *d_out_sc, *d_qhdr;
+  __nv_bfloat16* d_qb;
+  uint64_t *d_keys, *d_sel_ids, *d_out_ids, *d_keys2, *d_coffs;
+  uint32_t *d_sel_cnt, *d_out_cnt, *d_status, *d_cslots, *d_err;
+  if ((rc = take(B * (size_t)dim * 4, (void**)&d_q)) || (rc = take(B * 4, (void**)&d_qhdr)) ||
+      (rc = take(B * 4, (void**)&d_status)) || (rc = take(B_pad * (size_t)ldb * 2, (void**)&d_qb)) ||
+      (rc = take(B_pad * 4, (void**)&d_qaux)) || (rc = take(nkeys * 8, (void**)&d_keys)) ||
+      (rc = take(B * (size_t)kprime * 8, (void**)&d_sel_ids)) || (rc = take(B * (size_t)kprime * 4, (void**)&d_sel_sc)) ||
+      (rc = take(B * 4, (void**)&d_sel_cnt)) || (rc = take(B * (size_t)kprime * 4, (void**)&d_cslots)) ||
+      (rc = take((B + 1) * 8, (void**)&d_coffs)) || (rc = take(B * (size_t)kprime * 8, (void**)&d_keys2)) ||
+      (rc = take(B * (size_t)k * 8, (void**)&d_out_ids)) || (rc = take(B * (size_t)k * 4, (void**)&d_out_sc)) ||
+      (rc = take(B * 4, (void**)&d_out_cnt)) || (rc = take(4, (void**)&d_err)))
+    return rc;
   HXD_CUDA(cudaMemset(d_err, 0, 4));
   HXD_CUDA(cudaMemset(d_sel_ids, 0xFF, B * (size_t)kprime * 8));   // unfilled nominee slots read as HX_ABSENT
   HXD_CUDA(cudaMemset(d_qb, 0, B_pad * (size_t)ldb * 2));
@@ -432,13 +454,14 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   a.k_blocks = ldb / HXD_BK;
   a.m_tiles = m_tiles;
   a.n_tiles = n_tiles;
+  a.n_split = n_split;
   a.row_aux = ix->d_sqnorm;
   a.q_aux = d_qaux;
   a.keys = d_keys;
   a.metric = ix->cfg.metric;
   const size_t smem = (size_t)HXD_STAGES * HXD_STAGE_BYTES + 16 * 8 + 16 + 2 * HXD_BN * 4 + 1024;
   HXD_CUDA(cudaFuncSetAttribute(k_dense_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const uint32_t grid = (uint32_t)std::min<size_t>((size_t)m_tiles * n_tiles, (size_t)ix->sm_count);
+  const uint32_t grid = (uint32_t)std::min<size_t>((size_t)m_tiles * n_split, (size_t)ix->sm_count);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -457,7 +480,7 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   s1.B = (uint32_t)B;
   s1.k = kprime;
   s1.shared_set = 2;   // keys carry global slots in their low word (no candidate indirection)
-  s1.n_shared = (uint64_t)n_tiles * HXD_T;
+  s1.n_shared = (uint64_t)n_split * HXD_T;
   s1.out_ids = d_sel_ids;
   s1.out_scores = d_sel_sc;
   s1.out_counts = d_sel_cnt;

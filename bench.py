@@ -406,8 +406,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 4 + 4,
                     "api": "hx_search (C ABI, pinned host buffers, blocking)"},
             "gpu_launches": args.steps * 2,
-            "launches_per_step": {"k_validate_and_header": 1, "k_hnsw_search": 1},
-            "roofline": {"bound": "hbm", "kernel": "k_hnsw_search", "achieved": round(achieved, 1), "peak": hbm_peak,
+            "launches_per_step": {"k_validate_and_header": 1, "k_hnsw_search_tma": 1},
+            "roofline": {"bound": "hbm", "kernel": "k_hnsw_search_tma", "achieved": round(achieved, 1), "peak": hbm_peak,
                          "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_hnsw_search"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_per_launch),
                          "kernel_ms_per_launch": round(kernel_ms, 4),

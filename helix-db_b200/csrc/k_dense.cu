@@ -31,7 +31,8 @@
 #define HXD_BK 64           // bf16 elements per k-block = 128 bytes = one swizzle atom
 #define HXD_STAGES 4
 #define HXD_T 16            // best rows kept per (query, work unit = one m-tile x a contiguous run of n-tiles)
-#define HXD_THREADS 256     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-7: epilogue
+#define HXD_THREADS 384     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-11: epilogue (2 per TMEM lane quarter)
+#define HXD_EPI_THREADS 256
 #define HXD_A_BYTES (HXD_BM * HXD_BK * 2)
 #define HXD_B_BYTES (HXD_BN * HXD_BK * 2)
 #define HXD_STAGE_BYTES (HXD_A_BYTES + HXD_B_BYTES)
@@ -108,7 +109,7 @@ struct HxDenseArgs {
   uint32_t n_split;           // work unit u: m-tile u % m_tiles, n-tiles [r*n_tiles/n_split, (r+1)*n_tiles/n_split), r = u / m_tiles
   const float* row_aux;       // cosine: 1/|x_i|   ; euclidean: |x_i|^2            (from the bf16-rounded rows)
   const float* q_aux;         // cosine: 1/|q_b|   ; euclidean: |q_b|^2
-  uint64_t* keys;             // [B][n_split][HXD_T]
+  uint64_t* keys;             // [B][n_split][2][HXD_T]  (two column halves per query row)
   int32_t metric;
 };
 
@@ -135,7 +136,7 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       hx_mbar_init(tfull + s, 1);
-      hx_mbar_init(tempty + s, 128);
+      hx_mbar_init(tempty + s, HXD_EPI_THREADS);
     }
     hx_fence_mbar_init();
   }
@@ -196,61 +197,89 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread = one query row of the tile =====
-    const uint32_t q4 = warp - 4;                     // TMEM lane quarter this warp may access
+    // ===== epilogue: 8 warps; thread = one query row x one half (128 columns) of the tile =====
+    // ncu on the first version (profiles/): the tensor pipe sat at 10 % because 4 warps x 256 columns x ~30 instructions
+    // per column could not drain an accumulator as fast as the MMAs filled it.  Now the test is done in the dot-product
+    // domain (one FMUL/FFMA + one compare per column: the score is monotone in it), padded rows carry a sentinel that
+    // can never pass, row terms are read as float4, and two warps share each TMEM lane quarter.
+    const uint32_t ew = warp - 4;                     // 0..7
+    const uint32_t q4 = ew & 3u;                      // TMEM lane quarter this warp may access (warp id % 4)
+    const uint32_t half = ew >> 2;                    // column half
     const uint32_t row_in_tile = q4 * 32 + lane;
-    const uint32_t et = threadIdx.x - 128;            // 0..127
+    const uint32_t et = threadIdx.x - 128;            // 0..255
     uint32_t acc = 0, acc_ph = 0;
     for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
       const uint32_t mt = u % a.m_tiles, r = u / a.m_tiles;
       const uint32_t nt0 = (uint32_t)((uint64_t)r * a.n_tiles / a.n_split), nt1 = (uint32_t)((uint64_t)(r + 1) * a.n_tiles / a.n_split);
       const uint32_t qrow = mt * HXD_BM + row_in_tile;
       const float qa = qrow < a.n_queries ? a.q_aux[qrow] : 0.f;
-      // running best-T of this query over the whole run of tiles: after a few tiles the threshold rejects almost every
-      // column, so the (warp-divergent) insertion path is rarely entered and the epilogue stays under the MMA time
-      uint64_t best[HXD_T];
+      // running best-T (largest t) of this query over the whole run of tiles; t = s*ax (cosine) or 2s - ax (euclidean)
+      float bt[HXD_T];
+      uint32_t bs[HXD_T];
 #pragma unroll
-      for (int i = 0; i < HXD_T; ++i) best[i] = HX_KEY_MAX;
+      for (int i = 0; i < HXD_T; ++i) { bt[i] = -__int_as_float(0x7f800000); bs[i] = HX_ABSENT; }
       for (uint32_t nt = nt0; nt < nt1; ++nt) {
         const uint32_t n0 = nt * HXD_BN;
         float* ax = aux + acc * HXD_BN;
-        for (uint32_t c = et; c < HXD_BN; c += 128) ax[c] = (n0 + c < a.n_rows) ? a.row_aux[n0 + c] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // aux visible to the 4 epilogue warps
+        {
+          const uint32_t c = et;                        // 256 threads stage the 256 row terms of the tile
+          float v = (n0 + c < a.n_rows) ? a.row_aux[n0 + c] : 0.f;
+          if (n0 + c >= a.n_rows) v = a.metric == HXM_COSINE ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
+          ax[c] = v;                                    // padded rows: t = NaN / -inf never beats the threshold
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         hx_mbar_wait(tfull + acc, acc_ph);
         hxd_fence_after();
-        const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + acc * HXD_BN;
-        const uint32_t thr_hi = (uint32_t)(best[HXD_T - 1] >> 32);
-        for (uint32_t c0 = 0; c0 < HXD_BN; c0 += 32) {
+        const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + acc * HXD_BN + half * (HXD_BN / 2);
+        const float4* ax4 = reinterpret_cast<const float4*>(ax + half * (HXD_BN / 2));
+        for (uint32_t c0 = 0; c0 < HXD_BN / 2; c0 += 32) {
           uint32_t rr[32];
           hxd_tmem_ld32(taddr + c0, rr);
+          const float thr = bt[HXD_T - 1];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const uint32_t col = c0 + j;
-            const float s = __uint_as_float(rr[j]);
-            float sc;
-            if (a.metric == HXM_COSINE) sc = 0.5f - 0.5f * s * qa * ax[col];   // (1 - cos)/2
-            else sc = qa + ax[col] - 2.0f * s;                                  // |q|^2 + |x|^2 - 2<q,x>
-            sc = fmaxf(sc, 0.0f);
-            // cheap 32-bit pre-test against the score of the current T-th best (stale within the tile is fine: it only admits more)
-            if (__float_as_uint(sc) <= thr_hi && n0 + col < a.n_rows) {
-              const uint64_t key = hx_make_key(sc, n0 + col);
-              if (key < best[HXD_T - 1]) {
-                best[HXD_T - 1] = key;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 x = ax4[(c0 >> 2) + j4];
+            float tv[4];
+            if (a.metric == HXM_COSINE) {
+              tv[0] = __uint_as_float(rr[4 * j4 + 0]) * x.x; tv[1] = __uint_as_float(rr[4 * j4 + 1]) * x.y;
+              tv[2] = __uint_as_float(rr[4 * j4 + 2]) * x.z; tv[3] = __uint_as_float(rr[4 * j4 + 3]) * x.w;
+            } else {
+              tv[0] = fmaf(2.0f, __uint_as_float(rr[4 * j4 + 0]), -x.x); tv[1] = fmaf(2.0f, __uint_as_float(rr[4 * j4 + 1]), -x.y);
+              tv[2] = fmaf(2.0f, __uint_as_float(rr[4 * j4 + 2]), -x.z); tv[3] = fmaf(2.0f, __uint_as_float(rr[4 * j4 + 3]), -x.w);
+            }
+            if (tv[0] > thr || tv[1] > thr || tv[2] > thr || tv[3] > thr) {   // rare once the threshold has warmed up
 #pragma unroll
-                for (int i = HXD_T - 1; i > 0; --i)
-                  if (best[i] < best[i - 1]) { const uint64_t tkey = best[i]; best[i] = best[i - 1]; best[i - 1] = tkey; }
+              for (int e = 0; e < 4; ++e) {
+                if (tv[e] > bt[HXD_T - 1]) {
+                  bt[HXD_T - 1] = tv[e];
+                  bs[HXD_T - 1] = n0 + half * (HXD_BN / 2) + c0 + 4 * j4 + e;
+#pragma unroll
+                  for (int i = HXD_T - 1; i > 0; --i)
+                    if (bt[i] > bt[i - 1]) {
+                      const float tf = bt[i]; bt[i] = bt[i - 1]; bt[i - 1] = tf;
+                      const uint32_t tsl = bs[i]; bs[i] = bs[i - 1]; bs[i - 1] = tsl;
+                    }
+                }
               }
             }
           }
         }
         hxd_fence_before();
-        hxd_mbar_arrive(tempty + acc);   // 128 arrivals free the accumulator stage
+        hxd_mbar_arrive(tempty + acc);   // 256 arrivals free the accumulator stage
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
       if (qrow < a.n_queries) {
-        uint64_t* out = a.keys + ((size_t)qrow * a.n_split + r) * HXD_T;
+        uint64_t* out = a.keys + (((size_t)qrow * a.n_split + r) * 2 + half) * HXD_T;
 #pragma unroll
-        for (int i = 0; i < HXD_T; ++i) out[i] = best[i];
+        for (int i = 0; i < HXD_T; ++i) {
+          uint64_t key = HX_KEY_MAX;
+          if (bs[i] != HX_ABSENT) {
+            float sc = a.metric == HXM_COSINE ? 0.5f - 0.5f * bt[i] * qa : qa - bt[i];   // (1-cos)/2 ; |q|^2 + |x|^2 - 2<q,x>
+            sc = fmaxf(sc, 0.0f);
+            key = hx_make_key(sc, bs[i]);
+          }
+          out[i] = key;
+        }
       }
     }
   }
@@ -389,7 +418,7 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   // k' nominees even when the true neighbours cluster in id space (8x head-room)
   const uint32_t n_split = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_tiles,
       std::max<size_t>(std::max<size_t>(4, (size_t)ix->sm_count / m_tiles), (8 * (size_t)kprime + HXD_T - 1) / HXD_T)));
-  const size_t nkeys = B * (size_t)n_split * HXD_T;
+  const size_t nkeys = B * (size_t)n_split * 2 * HXD_T;
   int mi = 0;
   auto take = [&](size_t bytes, void** out) -> hx_status {
     hx_status r = scr->misc[mi].reserve(bytes + 256);
@@ -480,7 +509,7 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   s1.B = (uint32_t)B;
   s1.k = kprime;
   s1.shared_set = 2;   // keys carry global slots in their low word (no candidate indirection)
-  s1.n_shared = (uint64_t)n_split * HXD_T;
+  s1.n_shared = (uint64_t)n_split * 2 * HXD_T;
   s1.out_ids = d_sel_ids;
   s1.out_scores = d_sel_sc;
   s1.out_counts = d_sel_cnt;

@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -33,6 +34,7 @@
 #define HXD_T 16            // best rows kept per (query, work unit = one m-tile x a contiguous run of n-tiles)
 #define HXD_THREADS 384     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-11: epilogue (2 per TMEM lane quarter)
 #define HXD_EPI_THREADS 256
+#define HXD_STAGE_CAP 12    // per-thread staging entries (shared memory) between the column test and the top-T insertion
 #define HXD_A_BYTES (HXD_BM * HXD_BK * 2)
 #define HXD_B_BYTES (HXD_BN * HXD_BK * 2)
 #define HXD_STAGE_BYTES (HXD_A_BYTES + HXD_B_BYTES)
@@ -88,6 +90,15 @@ __device__ __forceinline__ void hxd_tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void hxd_tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major operand tile stored by TMA with the 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart.
 // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 64 |
 // version [46,48) = 1 (Blackwell) | layout_type [61,64) = 2 (SWIZZLE_128B).
@@ -111,6 +122,7 @@ struct HxDenseArgs {
   const float* q_aux;         // cosine: 1/|q_b|   ; euclidean: |q_b|^2
   uint64_t* keys;             // [B][n_split][2][HXD_T]  (two column halves per query row)
   int32_t metric;
+  uint32_t debug;             // experiments: bit0 = epilogue drains without reading TMEM, bit1 = no TMA after the first ring fill
 };
 
 __global__ void __launch_bounds__(HXD_THREADS, 1)
@@ -125,6 +137,8 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* tempty = tfull + 2;             // [2] accumulator stage drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* aux = reinterpret_cast<float*>(tmem_slot + 4);   // [2][HXD_BN] row aux of the tile being drained
+  float* stg_t = aux + 2 * HXD_BN;                          // [HXD_STAGE_CAP][256] staged t values   (entry-major: conflict-free)
+  uint32_t* stg_s = reinterpret_cast<uint32_t*>(stg_t + HXD_STAGE_CAP * HXD_EPI_THREADS);   // [HXD_STAGE_CAP][256] staged slots
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   if (threadIdx.x == 0) {
@@ -160,9 +174,13 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
             hx_mbar_wait(empty + stage, ph ^ 1u);
             unsigned char* sa = tiles + (size_t)stage * HXD_STAGE_BYTES;
-            hx_mbar_expect_tx(full + stage, HXD_STAGE_BYTES);
-            hxd_tma_load_2d(sa, &map_q, full + stage, (int)(kb * HXD_BK), (int)(mt * HXD_BM));
-            hxd_tma_load_2d(sa + HXD_A_BYTES, &map_x, full + stage, (int)(kb * HXD_BK), (int)(nt * HXD_BN));
+            if ((a.debug & 2u) && (ph || nt != nt0 || u != blockIdx.x)) {
+              hxd_mbar_arrive(full + stage);              // experiment: operands stay whatever the first fill left
+            } else {
+              hx_mbar_expect_tx(full + stage, HXD_STAGE_BYTES);
+              hxd_tma_load_2d(sa, &map_q, full + stage, (int)(kb * HXD_BK), (int)(mt * HXD_BM));
+              hxd_tma_load_2d(sa + HXD_A_BYTES, &map_x, full + stage, (int)(kb * HXD_BK), (int)(nt * HXD_BN));
+            }
             if (++stage == HXD_STAGES) { stage = 0; ph ^= 1u; }
           }
       }
@@ -218,6 +236,8 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t bs[HXD_T];
 #pragma unroll
       for (int i = 0; i < HXD_T; ++i) { bt[i] = -__int_as_float(0x7f800000); bs[i] = HX_ABSENT; }
+      float thr = -__int_as_float(0x7f800000);
+      uint32_t cnt = 0;
       for (uint32_t nt = nt0; nt < nt1; ++nt) {
         const uint32_t n0 = nt * HXD_BN;
         float* ax = aux + acc * HXD_BN;
@@ -232,36 +252,52 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         hxd_fence_after();
         const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + acc * HXD_BN + half * (HXD_BN / 2);
         const float4* ax4 = reinterpret_cast<const float4*>(ax + half * (HXD_BN / 2));
-        for (uint32_t c0 = 0; c0 < HXD_BN / 2; c0 += 32) {
-          uint32_t rr[32];
-          hxd_tmem_ld32(taddr + c0, rr);
-          const float thr = bt[HXD_T - 1];
+        const uint32_t slot0 = n0 + half * (HXD_BN / 2);
+        // The loop body is deliberately small and NOT unrolled: the first version inlined the insertion network at every
+        // column (10k SASS instructions, instruction-cache bound: tensor pipe 9 %).  Columns that beat the running
+        // threshold are only STAGED (two predicated shared-memory stores); the single insertion-network instance below
+        // drains the staging area.
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < HXD_BN / 2 && !(a.debug & 1u); c0 += 8) {
+          uint32_t rr[8];
+          hxd_tmem_ld8(taddr + c0, rr);
+          const float4 x0 = ax4[(c0 >> 2)], x1 = ax4[(c0 >> 2) + 1];
+          float tv[8];
+          if (a.metric == HXM_COSINE) {
+            tv[0] = __uint_as_float(rr[0]) * x0.x; tv[1] = __uint_as_float(rr[1]) * x0.y;
+            tv[2] = __uint_as_float(rr[2]) * x0.z; tv[3] = __uint_as_float(rr[3]) * x0.w;
+            tv[4] = __uint_as_float(rr[4]) * x1.x; tv[5] = __uint_as_float(rr[5]) * x1.y;
+            tv[6] = __uint_as_float(rr[6]) * x1.z; tv[7] = __uint_as_float(rr[7]) * x1.w;
+          } else {
+            tv[0] = fmaf(2.0f, __uint_as_float(rr[0]), -x0.x); tv[1] = fmaf(2.0f, __uint_as_float(rr[1]), -x0.y);
+            tv[2] = fmaf(2.0f, __uint_as_float(rr[2]), -x0.z); tv[3] = fmaf(2.0f, __uint_as_float(rr[3]), -x0.w);
+            tv[4] = fmaf(2.0f, __uint_as_float(rr[4]), -x1.x); tv[5] = fmaf(2.0f, __uint_as_float(rr[5]), -x1.y);
+            tv[6] = fmaf(2.0f, __uint_as_float(rr[6]), -x1.z); tv[7] = fmaf(2.0f, __uint_as_float(rr[7]), -x1.w);
+          }
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 x = ax4[(c0 >> 2) + j4];
-            float tv[4];
-            if (a.metric == HXM_COSINE) {
-              tv[0] = __uint_as_float(rr[4 * j4 + 0]) * x.x; tv[1] = __uint_as_float(rr[4 * j4 + 1]) * x.y;
-              tv[2] = __uint_as_float(rr[4 * j4 + 2]) * x.z; tv[3] = __uint_as_float(rr[4 * j4 + 3]) * x.w;
-            } else {
-              tv[0] = fmaf(2.0f, __uint_as_float(rr[4 * j4 + 0]), -x.x); tv[1] = fmaf(2.0f, __uint_as_float(rr[4 * j4 + 1]), -x.y);
-              tv[2] = fmaf(2.0f, __uint_as_float(rr[4 * j4 + 2]), -x.z); tv[3] = fmaf(2.0f, __uint_as_float(rr[4 * j4 + 3]), -x.w);
+          for (int e = 0; e < 8; ++e)
+            if (tv[e] > thr) {
+              stg_t[cnt * HXD_EPI_THREADS + et] = tv[e];
+              stg_s[cnt * HXD_EPI_THREADS + et] = slot0 + c0 + e;
+              ++cnt;
             }
-            if (tv[0] > thr || tv[1] > thr || tv[2] > thr || tv[3] > thr) {   // rare once the threshold has warmed up
+          if (cnt > HXD_STAGE_CAP - 8 || c0 + 8 >= HXD_BN / 2) {   // drain: the only instance of the insertion network
+#pragma unroll 1
+            for (uint32_t i = 0; i < cnt; ++i) {
+              const float tvi = stg_t[i * HXD_EPI_THREADS + et];
+              if (tvi > bt[HXD_T - 1]) {
+                bt[HXD_T - 1] = tvi;
+                bs[HXD_T - 1] = stg_s[i * HXD_EPI_THREADS + et];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (tv[e] > bt[HXD_T - 1]) {
-                  bt[HXD_T - 1] = tv[e];
-                  bs[HXD_T - 1] = n0 + half * (HXD_BN / 2) + c0 + 4 * j4 + e;
-#pragma unroll
-                  for (int i = HXD_T - 1; i > 0; --i)
-                    if (bt[i] > bt[i - 1]) {
-                      const float tf = bt[i]; bt[i] = bt[i - 1]; bt[i - 1] = tf;
-                      const uint32_t tsl = bs[i]; bs[i] = bs[i - 1]; bs[i - 1] = tsl;
-                    }
-                }
+                for (int j = HXD_T - 1; j > 0; --j)
+                  if (bt[j] > bt[j - 1]) {
+                    const float tf = bt[j]; bt[j] = bt[j - 1]; bt[j - 1] = tf;
+                    const uint32_t tsl = bs[j]; bs[j] = bs[j - 1]; bs[j - 1] = tsl;
+                  }
               }
             }
+            cnt = 0;
+            thr = bt[HXD_T - 1];
           }
         }
         hxd_fence_before();
@@ -488,7 +524,8 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   a.q_aux = d_qaux;
   a.keys = d_keys;
   a.metric = ix->cfg.metric;
-  const size_t smem = (size_t)HXD_STAGES * HXD_STAGE_BYTES + 16 * 8 + 16 + 2 * HXD_BN * 4 + 1024;
+  a.debug = getenv("HX_DENSE_DEBUG") ? (uint32_t)atoi(getenv("HX_DENSE_DEBUG")) : 0u;
+  const size_t smem = (size_t)HXD_STAGES * HXD_STAGE_BYTES + 16 * 8 + 16 + 2 * HXD_BN * 4 + (size_t)HXD_STAGE_CAP * HXD_EPI_THREADS * 8 + 1024;
   HXD_CUDA(cudaFuncSetAttribute(k_dense_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const uint32_t grid = (uint32_t)std::min<size_t>((size_t)m_tiles * n_split, (size_t)ix->sm_count);
   cudaEvent_t e0, e1;

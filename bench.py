@@ -185,25 +185,42 @@ def oracle_from_device(hxo, ix, args):
     return ora
 
 
-def exact_topk_device(hx, torch, ix, queries, n, first_id, k):
-    """Ground truth by the exact scan kernel over ALL rows (same metric, same (score,id) tie rule)."""
+def exact_topk_device_full(hx, torch, ix, queries, n, first_id, k):
+    """Ground truth by the exact scan kernel over ALL rows (same metric, same (score,id) tie rule).  The restricted
+    entry point accepts at most 1e6 candidates (the reference's bound), so larger shards are scanned in 1M-row ranges
+    whose top-k lists are merged by the (score,id) merge kernel.  Returns (ids u64 [B,k], scores f32 [B,k], counts)."""
     dev = torch.device("cuda", ix.device)
     B = len(queries)
     dq = torch.from_numpy(queries).to(dev)
-    slots = torch.arange(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    R = 1_000_000
+    ranges = [(a, min(n, a + R)) for a in range(0, n, R)]
+    a_ids = torch.zeros((len(ranges), B, k), dtype=torch.int64, device=dev)
+    a_sc = torch.zeros((len(ranges), B, k), dtype=torch.float32, device=dev)
+    a_cnt = torch.zeros((len(ranges), B), dtype=torch.int32, device=dev)
+    step = 64
+    for ri, (a, b) in enumerate(ranges):
+        slots = torch.arange(a, b, dtype=torch.int32, device=dev)
+        for lo in range(0, B, step):
+            bb = min(step, B - lo)
+            ix.search_restricted_device(dq[lo:lo + bb].data_ptr(), bb, hx.SearchParams.strict(k), slots.data_ptr(), 0,
+                                        b - a, b - a, a_ids[ri, lo:lo + bb].data_ptr(), a_sc[ri, lo:lo + bb].data_ptr(),
+                                        a_cnt[ri, lo:lo + bb].data_ptr(), stream)
+        torch.cuda.synchronize(dev)
+    ix.last_kernel_ms()
+    if len(ranges) == 1:
+        return a_ids[0].cpu().numpy().view(np.uint64), a_sc[0].cpu().numpy(), a_cnt[0].cpu().numpy()
     o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
     o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
     o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    step = 64
-    for lo in range(0, B, step):
-        b = min(step, B - lo)
-        ix.search_restricted_device(dq[lo:lo + b].data_ptr(), b, hx.SearchParams.strict(k), slots.data_ptr(), 0, n, n,
-                                    o_ids[lo:lo + b].data_ptr(), o_sc[lo:lo + b].data_ptr(),
-                                    o_cnt[lo:lo + b].data_ptr(), stream)
+    hx.merge_topk_device(ix.device, a_ids.data_ptr(), a_sc.data_ptr(), a_cnt.data_ptr(), len(ranges), B, k,
+                         o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
     torch.cuda.synchronize(dev)
-    ix.last_kernel_ms()
-    return o_ids.cpu().numpy().view(np.uint64)
+    return o_ids.cpu().numpy().view(np.uint64), o_sc.cpu().numpy(), o_cnt.cpu().numpy()
+
+
+def exact_topk_device(hx, torch, ix, queries, n, first_id, k):
+    return exact_topk_device_full(hx, torch, ix, queries, n, first_id, k)[0]
 
 
 def recall_at_k(found, truth):
@@ -595,56 +612,121 @@ def run_prefilter(args):
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_dense(args):
-    """Config C4-shaped (per GPU): exhaustive top-10 of a large query batch against the whole shard through the tensor
-    cores (hx_search_dense: tcgen05 bf16 contraction -> per-tile nominees -> exact fp32 re-rank)."""
+    """Configs C4/C5 shape: exhaustive top-10 of a large query batch through the tensor cores (hx_search_dense: tcgen05
+    bf16 contraction -> per-run nominees -> exact fp32 re-rank).  With --gpus N the corpus (--n rows in total) is split by
+    id range, every rank scores every query against its shard, ONE NCCL all-gather moves the per-shard top-k and the
+    merge kernel selects the global top-k by (score, id)."""
     import torch
 
     import helix_db_b200 as hx
 
-    torch.cuda.set_device(0)
-    n, dim, k = args.n, args.dim, K
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    n_total, dim, k = args.n, args.dim, K
     B = args.queries_per_step if args.queries_per_step != 8192 else 1024
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    n = hi - lo
     metric = hx.Metric.Cosine if args.metric == "cosine" else hx.Metric.Euclidean
-    ix = hx.VectorIndex(metric, hx.VectorIndexConfig("dense", "embedding", dim), device=0, storage=1)
-    ix.generate_vectors(0, n, SEED, N_CENTROIDS, SIGMA, KIND)
-    ix.load_graph(0, np.array([0], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
-    ix.set_entry(0, 0)
+    ix = hx.VectorIndex(metric, hx.VectorIndexConfig("dense", "embedding", dim), device=local_rank, storage=1)
+    ix.generate_vectors(lo, n, SEED, N_CENTROIDS, SIGMA, KIND)
+    ix.load_graph(0, np.array([lo], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
+    ix.set_entry(lo, 0)
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    # every rank answers the SAME queries
     qsets = [ix.generate_queries(SEED, B, first_query=s * B, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
              for s in range(args.steps + args.warmup)]
     params = hx.SearchParams.strict(k)
+    sharding = None
+    if world > 1:
+        from importlib import import_module
+        sharding = import_module("helix_db_b200.sharding")
+        pack = torch.zeros((B, 3 * k + 1), dtype=torch.int32, device=dev)
+        apack = torch.zeros((world, B, 3 * k + 1), dtype=torch.int32, device=dev)
+        o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
+        o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
+        o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+
+    def merge_across_ranks(ids, sc, cnt, nq, pk, apk, oi, osc, ocn):
+        sharding.pack_topk(torch.from_numpy(ids.view(np.int64).copy()).to(dev), torch.from_numpy(sc.copy()).to(dev),
+                           torch.from_numpy(cnt.astype(np.int32)).to(dev), pk)
+        sharding.all_gather_topk(pk, world, apk)
+        a_ids, a_sc, a_cnt = sharding.unpack_topk(apk, k)
+        hx.merge_topk_device(local_rank, a_ids.data_ptr(), a_sc.data_ptr(), a_cnt.data_ptr(), world, nq, k,
+                             oi.data_ptr(), osc.data_ptr(), ocn.data_ptr(), stream)
+        torch.cuda.synchronize(dev)
+        return oi.cpu().numpy().view(np.uint64)
+
+    def step(s):
+        ids, sc, cnt = ix.search_dense_batch(qsets[s], params)
+        kms = ix.last_kernel_ms()[0]
+        if world == 1:
+            return ids, kms
+        return merge_across_ranks(ids, sc, cnt, B, pack, apack, o_ids, o_sc, o_cnt), kms
+
     for s in range(args.warmup):
-        ix.search_dense_batch(qsets[s], params)
-    sampler = ClockSampler(0)
-    sampler.start()
+        step(s)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     kms, t0 = 0.0, time.perf_counter()
     last = None
     for s in range(args.steps):
-        last = ix.search_dense_batch(qsets[args.warmup + s], params)
-        kms += ix.last_kernel_ms()[0]
+        last, km = step(args.warmup + s)
+        kms += km
+    torch.cuda.synchronize(dev)
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    wall = float(tw.item())
+    clocks = sampler.stop() if rank == 0 else None
     ldb = (dim + 63) // 64 * 64
     flop = 2.0 * B * n * ldb
     kernel_ms = kms / args.steps
-    rq = min(128, B)
-    truth = exact_topk_device(hx, torch, ix, qsets[args.warmup + args.steps - 1][:rq], n, 0, k)
-    rec = recall_at_k(last[0][:rq], truth)
-    line = {"metric": "queries/sec, exhaustive top-10 through the tensor cores (config C4 shape, one shard)",
-            "value": round(args.steps * B / wall, 1), "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(wall / args.steps * 1e3, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (fp32 accumulate) + f32 exact re-rank", "data": "synthetic",
-            "recall_at_10": round(rec, 4),
-            "config": {"workload": f"dense: {B} queries x {n} rows x d={dim}, k={k}, host buffers (hx_search_dense)",
-                       "recipe": args.recipe},
-            "roofline": {"bound": "tensor", "kernel": "k_dense_scores", "achieved": round(flop / (kernel_ms * 1e-3) / 1e12, 1),
-                         "peak": tf_peak, "unit": "TFLOP/s", "frac": round(flop / (kernel_ms * 1e-3) / 1e12 / tf_peak, 4),
-                         "traffic": ncu_traffic("k_dense_scores"), "flop_per_launch": flop,
-                         "kernel_ms_per_launch": round(kernel_ms, 4), "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"},
-            "gpu_launches": args.steps * 7, "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    # recall of the (merged) answer vs the exact scan of every shard, merged the same way
+    rq = min(64, B)
+    gi, gs, gc = exact_topk_device_full(hx, torch, ix, qsets[args.warmup + args.steps - 1][:rq], n, lo, k)
+    if world > 1:
+        p2 = torch.zeros((rq, 3 * k + 1), dtype=torch.int32, device=dev)
+        ap2 = torch.zeros((world, rq, 3 * k + 1), dtype=torch.int32, device=dev)
+        t_o = torch.zeros((rq, k), dtype=torch.int64, device=dev)
+        t_s = torch.zeros((rq, k), dtype=torch.float32, device=dev)
+        t_c = torch.zeros((rq,), dtype=torch.int32, device=dev)
+        truth = merge_across_ranks(gi, gs, gc, rq, p2, ap2, t_o, t_s, t_c)
+    else:
+        truth = gi
+    rec = recall_at_k(last[:rq], truth)
+    if rank == 0:
+        line = {"metric": "queries/sec, exhaustive top-10 through the tensor cores (configs C4/C5 shape)",
+                "value": round(args.steps * B / wall, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(wall / args.steps * 1e3, 3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16 (fp32 accumulate) + f32 exact re-rank",
+                "data": "synthetic", "recall_at_10": round(rec, 4),
+                "config": {"workload": f"dense: {B} queries x {n_total} rows x d={dim}, k={k}, host buffers (hx_search_dense)"
+                                       + (f", {world} id-range shards of {n} rows, 1 all-gather + merge" if world > 1 else ""),
+                           "recipe": args.recipe},
+                "roofline": {"bound": "tensor", "kernel": "k_dense_scores", "achieved": round(flop / (kernel_ms * 1e-3) / 1e12, 1),
+                             "peak": tf_peak, "unit": "TFLOP/s", "frac": round(flop / (kernel_ms * 1e-3) / 1e12 / tf_peak, 4),
+                             "traffic": ncu_traffic("k_dense_scores"), "flop_per_launch_per_gpu": flop,
+                             "kernel_ms_per_launch": round(kernel_ms, 4),
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); per GPU"},
+                "gpu_launches": args.steps * 7, "clocks": clocks}
+        print(json.dumps(line), flush=True)
     ix.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------------------------

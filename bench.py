@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--queries-per-step", type=int, default=8192)
     ap.add_argument("--metric", default="cosine", choices=["cosine", "euclidean"])

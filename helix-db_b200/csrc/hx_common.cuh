@@ -221,6 +221,52 @@ __device__ __forceinline__ float hx_cosine_norm(const float* __restrict__ v, uin
   return __double2float_rn(n);
 }
 
+// Warp-cooperative scaled_l2_norm with the SAME operations in the SAME order (cosine.rs:12-36).  The recurrence is
+// sequential only through `scale` (the running maximum) and the order of the additions.  For a block of 32 elements in
+// which no magnitude exceeds the current scale — every block but the handful where the running maximum still grows —
+// the 32 divisions and squarings are independent (same divisor), so the lanes compute them in parallel and only the 32
+// additions are replayed in element order.  A block containing a new maximum is replayed element by element.
+// All lanes return the same bits.
+__device__ __forceinline__ float hx_cosine_norm_warp(const float* __restrict__ v, uint32_t dim, uint32_t lane) {
+  const unsigned FULL = 0xffffffffu;
+  double scale = 0.0, scaled_sum = 1.0;
+  for (uint32_t base = 0; base < dim; base += 32) {
+    const uint32_t i = base + lane;
+    const double mag = i < dim ? (double)fabsf(v[i]) : 0.0;
+    const uint32_t cnt = min(32u, dim - base);
+    if (__any_sync(FULL, scale < mag)) {
+      for (uint32_t j = 0; j < cnt; ++j) {
+        const double m = __shfl_sync(FULL, mag, j);
+        if (m == 0.0) continue;
+        if (scale < m) {
+          const double ratio = __ddiv_rn(scale, m);
+          scaled_sum = __dadd_rn(1.0, __dmul_rn(__dmul_rn(scaled_sum, ratio), ratio));
+          scale = m;
+        } else {
+          const double ratio = __ddiv_rn(m, scale);
+          scaled_sum = __dadd_rn(scaled_sum, __dmul_rn(ratio, ratio));
+        }
+      }
+    } else {
+      double sq = 0.0;
+      const bool nz = mag != 0.0;
+      if (nz) {
+        const double ratio = __ddiv_rn(mag, scale);
+        sq = __dmul_rn(ratio, ratio);
+      }
+      const uint32_t nzmask = __ballot_sync(FULL, nz);
+      for (uint32_t j = 0; j < cnt; ++j) {
+        const double x = __shfl_sync(FULL, sq, j);
+        if ((nzmask >> j) & 1u) scaled_sum = __dadd_rn(scaled_sum, x);
+      }
+    }
+  }
+  double n = scale == 0.0 ? 0.0 : __dmul_rn(scale, __dsqrt_rn(scaled_sum));
+  const double mx = (double)FLT_MAX;
+  if (n > mx) n = mx;
+  return __double2float_rn(n);
+}
+
 // stable_half_cosine (cosine.rs:39-59): f64 fallback, sequential.
 static __device__ __noinline__ float hx_stable_half_cosine(const float* __restrict__ p, const float* __restrict__ q,
                                                     uint32_t dim) {

@@ -33,10 +33,10 @@ static __global__ void k_validate_and_header(const float* __restrict__ v, size_t
   if (bad_fin != HX_ABSENT) st = (HX_ST_COMPONENT << 24) | (bad_fin & 0xffffffu);
   else if (metric == HXM_COSINE && !nonzero) st = (HX_ST_ZERO_NORM << 24);
   else if (bad_mag != HX_ABSENT) st = (HX_ST_MAGNITUDE << 24) | (bad_mag & 0xffffffu);
+  float h = 0.0f;
+  if (metric == HXM_COSINE && st == HX_ST_OK) h = hx_cosine_norm_warp(x, dim, lane);   // st is warp-uniform
   if (lane == 0) {
     status_out[w] = st;
-    float h = 0.0f;
-    if (metric == HXM_COSINE && st == HX_ST_OK) h = hx_cosine_norm(x, dim);
     hdr_out[w] = h;
   }
 }

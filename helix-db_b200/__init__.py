@@ -110,7 +110,8 @@ ABI_SYMBOLS = [
     "hx_index_build", "hx_index_graph_info", "hx_index_download_graph", "hx_search", "hx_search_restricted",
     "hx_search_restricted_multi", "hx_restricted_plan", "hx_search_device", "hx_search_restricted_device",
     "hx_map_candidates_device", "hx_merge_topk_device", "hx_search_dense", "hx_last_error", "hx_last_error_index",
-    "hx_version", "hx_last_kernel_ms",
+    "hx_version", "hx_last_kernel_ms", "hx_index_load_vector_rows", "hx_index_load_neighbor_rows",
+    "hx_decode_neighbor_row", "hx_encode_neighbor_row", "hx_index_export_neighbor_row",
 ]
 
 _lib = None
@@ -175,6 +176,17 @@ def load_library():
     L.hx_version.restype = C.c_char_p
     L.hx_last_kernel_ms.restype = C.c_int32
     L.hx_last_kernel_ms.argtypes = [vp, fp, u32p]
+    u8p = C.POINTER(C.c_uint8)
+    L.hx_index_load_vector_rows.restype = C.c_int32
+    L.hx_index_load_vector_rows.argtypes = [vp, u64p, u8p, sz]
+    L.hx_index_load_neighbor_rows.restype = C.c_int32
+    L.hx_index_load_neighbor_rows.argtypes = [vp, C.c_uint16, u64p, u8p, u64p, sz]
+    L.hx_decode_neighbor_row.restype = C.c_int32
+    L.hx_decode_neighbor_row.argtypes = [C.c_uint16, u8p, sz, u64p, sz, C.POINTER(sz), u64p, C.POINTER(C.c_int32)]
+    L.hx_encode_neighbor_row.restype = C.c_int32
+    L.hx_encode_neighbor_row.argtypes = [C.c_uint16, u64p, sz, u8p, sz, C.POINTER(sz)]
+    L.hx_index_export_neighbor_row.restype = C.c_int32
+    L.hx_index_export_neighbor_row.argtypes = [vp, C.c_uint16, C.c_uint64, u8p, sz, C.POINTER(sz)]
     _lib = L
     return L
 
@@ -390,6 +402,29 @@ class VectorIndex:
     def set_entry(self, entry_point, max_layer):
         _ck(self.L.hx_index_set_entry(self.h, entry_point, max_layer))
 
+    def load_vector_rows(self, ids, rows: bytes):
+        """Hydrate from the reference's encoded item rows `[header f32][f32 x dim]` (mod.rs:866-949)."""
+        ia, ip = _u64(ids)
+        buf = (C.c_uint8 * max(len(rows), 1)).from_buffer_copy(rows if rows else b"\0")
+        if len(rows) != ia.size * (4 + 4 * self.dim):
+            raise HelixDbError(HX_ERR_INVARIANT_VIOLATION, "item rows must be 4+4*dimension bytes each")
+        _ck(self.L.hx_index_load_vector_rows(self.h, ip, buf, ia.size))
+
+    def load_neighbor_rows(self, layer, node_ids, rows):
+        """Hydrate one layer from encoded neighbour row values (list of bytes, one per node)."""
+        na, np_ = _u64(node_ids)
+        blob = b"".join(rows)
+        offs = np.zeros(len(rows) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(r) for r in rows])
+        buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
+        _ck(self.L.hx_index_load_neighbor_rows(self.h, layer, np_, buf, offs.ctypes.data_as(C.POINTER(C.c_uint64)), na.size))
+
+    def export_neighbor_row(self, layer, node_id) -> bytes:
+        out = (C.c_uint8 * (8 * 4096 + 8))()
+        n = C.c_size_t(0)
+        _ck(self.L.hx_index_export_neighbor_row(self.h, layer, node_id, out, len(out), C.byref(n)))
+        return bytes(out[:n.value])
+
     def build(self, levels=None, seed=0):
         if levels is None:
             _ck(self.L.hx_index_build(self.h, None, seed))
@@ -548,6 +583,27 @@ def merge_topk_device(device, d_all_ids, d_all_scores, d_all_counts, n_shards, B
                       d_out_counts, stream_ptr=0):
     _ck(load_library().hx_merge_topk_device(device, d_all_ids, d_all_scores, d_all_counts, n_shards, B, k, d_out_ids,
                                             d_out_scores, d_out_counts, stream_ptr))
+
+
+def decode_neighbor_row(layer: int, row: bytes):
+    """Decode one encoded neighbour row value (values/vectors.rs, values/vectors/neighbors.rs) -> (ids, simhash|None)."""
+    L = load_library()
+    buf = (C.c_uint8 * max(len(row), 1)).from_buffer_copy(row if row else b"\0")
+    cap = max(len(row) // 8 + 1, 1)
+    out = np.zeros(cap, dtype=np.uint64)
+    cnt, sh, has = C.c_size_t(0), C.c_uint64(0), C.c_int32(0)
+    _ck(L.hx_decode_neighbor_row(layer, buf, len(row), out.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(cnt),
+                                 C.byref(sh), C.byref(has)))
+    return out[:cnt.value].tolist(), (int(sh.value) if has.value else None)
+
+
+def encode_neighbor_row(layer: int, ids) -> bytes:
+    L = load_library()
+    a, p = _u64(ids)
+    out = (C.c_uint8 * (8 * a.size + 8))()
+    n = C.c_size_t(0)
+    _ck(L.hx_encode_neighbor_row(layer, p, a.size, out, len(out), C.byref(n)))
+    return bytes(out[:n.value])
 
 
 def restricted_plan(n_candidates: int, dimension: int) -> str:

@@ -564,6 +564,181 @@ extern "C" hx_status hx_index_load_graph(hx_index* ix, uint16_t layer, const uin
   return HX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// row-image import / export
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+static inline uint64_t be64(const uint8_t* p) { return ((uint64_t)be32(p) << 32) | be32(p + 4); }
+static inline void put_be32(uint8_t* p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
+static inline void put_be64(uint8_t* p, uint64_t v) { put_be32(p, (uint32_t)(v >> 32)); put_be32(p + 4, (uint32_t)v); }
+
+extern "C" hx_status hx_decode_neighbor_row(uint16_t layer, const uint8_t* row, size_t len, uint64_t* out_ids, size_t cap,
+                                            size_t* out_count, uint64_t* out_simhash, int32_t* out_has_simhash) {
+  if (out_count) *out_count = 0;
+  if (out_has_simhash) *out_has_simhash = 0;
+  if (len && !row) return HX_ERR_INVALID_PARAMETER;
+  size_t off = 0, count = 0;
+  if (layer == 0) {
+    if (len == 0) return HX_OK;   // missing row == the deployed empty-neighbour state (values/vectors.rs:181-183)
+    const uint8_t type = row[0];
+    if (type == 0x12) {           // ENCODING_TYPE_LAYER0_NEIGHBORS
+      if (len < 5) { hx_set_error("layer-0 row too short: %zu bytes", len); return HX_ERR_INVARIANT_VIOLATION; }
+      count = be32(row + 1);
+      off = 5;
+    } else if (type == 0x13) {    // ENCODING_TYPE_LAYER0_RECORD
+      if (len < 6) { hx_set_error("layer-0 record too short: %zu bytes", len); return HX_ERR_INVARIANT_VIOLATION; }
+      const uint8_t flags = row[1];
+      if (flags & ~0x01u) { hx_set_error("invalid layer-0 record flags: %#04x", flags); return HX_ERR_INVARIANT_VIOLATION; }
+      count = be32(row + 2);
+      off = 6;
+      if (flags & 1) {
+        if (len < off + 8) { hx_set_error("layer-0 record too short for its SimHash"); return HX_ERR_INVARIANT_VIOLATION; }
+        uint64_t bits = 0;
+        for (int i = 0; i < 8; ++i) bits |= (uint64_t)row[off + i] << (8 * i);   // little endian
+        if (out_simhash) *out_simhash = bits;
+        if (out_has_simhash) *out_has_simhash = 1;
+        off += 8;
+      }
+    } else {
+      hx_set_error("invalid layer-0 encoding type %#04x", type);
+      return HX_ERR_INVARIANT_VIOLATION;
+    }
+  } else {
+    if (len < 4) { hx_set_error("upper-layer row too short: %zu bytes", len); return HX_ERR_INVARIANT_VIOLATION; }
+    count = be32(row);
+    off = 4;
+  }
+  if (len != off + count * 8) {
+    hx_set_error("neighbour row length %zu does not match its count %zu (expected %zu)", len, count, off + count * 8);
+    return HX_ERR_INVARIANT_VIOLATION;
+  }
+  if (out_count) *out_count = count;
+  if (count > cap) {
+    hx_set_error("neighbour row holds %zu ids, caller capacity %zu", count, cap);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  for (size_t i = 0; i < count; ++i) out_ids[i] = be64(row + off + 8 * i);
+  return HX_OK;
+}
+
+extern "C" hx_status hx_encode_neighbor_row(uint16_t layer, const uint64_t* ids, size_t n, uint8_t* out, size_t cap,
+                                            size_t* out_len) {
+  if (n && !ids) return HX_ERR_INVALID_PARAMETER;
+  // layer 0 canonicalises to sorted unique ids (encode_layer0_neighbors, values/vectors.rs:97-110)
+  std::vector<uint64_t> canon(ids, ids + n);
+  if (layer == 0) {
+    bool sorted = true;
+    for (size_t i = 1; i < n; ++i)
+      if (!(canon[i - 1] < canon[i])) { sorted = false; break; }
+    if (!sorted) {
+      std::sort(canon.begin(), canon.end());
+      canon.erase(std::unique(canon.begin(), canon.end()), canon.end());
+    }
+  }
+  const size_t hdr = layer == 0 ? 5 : 4, need = hdr + canon.size() * 8;
+  if (out_len) *out_len = need;
+  if (!out || cap < need) {
+    hx_set_error("encoded neighbour row needs %zu bytes, capacity %zu", need, cap);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  size_t off = 0;
+  if (layer == 0) out[off++] = 0x12;
+  put_be32(out + off, (uint32_t)canon.size());
+  off += 4;
+  for (uint64_t id : canon) { put_be64(out + off, id); off += 8; }
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_load_vector_rows(hx_index* ix, const uint64_t* ids, const uint8_t* rows, size_t n) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (n && (!ids || !rows)) return HX_ERR_INVALID_PARAMETER;
+  const uint32_t dim = ix->cfg.dimension;
+  const size_t rb = 4 + 4 * (size_t)dim;
+  std::vector<float> vecs(n * (size_t)dim);
+  std::vector<uint32_t> hdr_bits(n);
+  for (size_t i = 0; i < n; ++i) {
+    memcpy(&hdr_bits[i], rows + i * rb, 4);
+    memcpy(vecs.data() + i * (size_t)dim, rows + i * rb + 4, 4 * (size_t)dim);
+  }
+  hx_status rc = hx_index_load_vectors(ix, ids, vecs.data(), n);
+  if (rc || n == 0) return rc;
+  // decode_item_borrowed: `bytes_of(&header) != bytes_of(&expected_header)` => HeaderMismatch (mod.rs:942-945)
+  std::vector<float> dev_hdr(n);
+  HX_CUDA(cudaMemcpy(dev_hdr.data(), ix->d_hdr, n * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t slot;
+    if (!hx_slot_of(ix, ids[i], &slot)) continue;
+    uint32_t expect;
+    memcpy(&expect, &dev_hdr[slot], 4);
+    if (expect != hdr_bits[i]) {
+      hx_set_error("vector item row of node %llu: stored header does not match the recomputed header",
+                   (unsigned long long)ids[i]);
+      ix->free_vectors();
+      return HX_ERR_INVARIANT_VIOLATION;
+    }
+  }
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_load_neighbor_rows(hx_index* ix, uint16_t layer, const uint64_t* node_ids,
+                                                 const uint8_t* blob, const uint64_t* row_offsets, size_t n) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (n && (!node_ids || !row_offsets)) return HX_ERR_INVALID_PARAMETER;
+  std::vector<uint32_t> offs(n + 1, 0);
+  std::vector<uint64_t> nbrs;
+  std::vector<uint64_t> tmp(4096);
+  for (size_t i = 0; i < n; ++i) {
+    const size_t len = (size_t)(row_offsets[i + 1] - row_offsets[i]);
+    size_t count = 0;
+    hx_status rc = hx_decode_neighbor_row(layer, blob + row_offsets[i], len, tmp.data(), tmp.size(), &count, nullptr, nullptr);
+    if (rc == HX_ERR_INVALID_PARAMETER && count > tmp.size()) {
+      tmp.resize(count);
+      rc = hx_decode_neighbor_row(layer, blob + row_offsets[i], len, tmp.data(), tmp.size(), &count, nullptr, nullptr);
+    }
+    if (rc) return rc;
+    nbrs.insert(nbrs.end(), tmp.begin(), tmp.begin() + count);
+    offs[i + 1] = (uint32_t)nbrs.size();
+  }
+  return hx_index_load_graph(ix, layer, node_ids, offs.data(), nbrs.data(), n);
+}
+
+extern "C" hx_status hx_index_export_neighbor_row(hx_index* ix, uint16_t layer, uint64_t node_id, uint8_t* out, size_t cap,
+                                                  size_t* out_len) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  hx_status rc = hx_finalize_graph(ix);
+  if (rc) return rc;
+  uint32_t slot;
+  if (!hx_slot_of(ix, node_id, &slot) || !ix->d_nbr0) {
+    hx_set_error("node %llu has no rows in the device mirror", (unsigned long long)node_id);
+    return HX_ERR_INDEX_NOT_FOUND;
+  }
+  HX_CUDA(cudaSetDevice(ix->device));
+  std::vector<uint32_t> row;
+  if (layer == 0) {
+    uint16_t deg = 0;
+    HX_CUDA(cudaMemcpy(&deg, ix->d_deg0 + slot, sizeof(deg), cudaMemcpyDeviceToHost));
+    row.resize(deg);
+    if (deg) HX_CUDA(cudaMemcpy(row.data(), ix->d_nbr0 + (size_t)slot * ix->stride0, deg * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  } else {
+    uint8_t lvl = 0;
+    uint32_t off = HX_ABSENT;
+    HX_CUDA(cudaMemcpy(&lvl, ix->d_level + slot, 1, cudaMemcpyDeviceToHost));
+    HX_CUDA(cudaMemcpy(&off, ix->d_upper_off + slot, 4, cudaMemcpyDeviceToHost));
+    if (lvl < layer || off == HX_ABSENT) {
+      hx_set_error("node %llu has no row on layer %u", (unsigned long long)node_id, layer);
+      return HX_ERR_INDEX_NOT_FOUND;
+    }
+    uint16_t deg = 0;
+    const size_t r = (size_t)off + layer - 1;
+    HX_CUDA(cudaMemcpy(&deg, ix->d_upper_deg + r, sizeof(deg), cudaMemcpyDeviceToHost));
+    row.resize(deg);
+    if (deg) HX_CUDA(cudaMemcpy(row.data(), ix->d_upper_nbr + r * ix->stride_u, deg * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  std::vector<uint64_t> ids(row.size());
+  for (size_t i = 0; i < row.size(); ++i) ids[i] = ix->ids_sorted[row[i]];
+  return hx_encode_neighbor_row(layer, ids.data(), ids.size(), out, cap, out_len);
+}
+
 extern "C" hx_status hx_index_set_entry(hx_index* ix, uint64_t entry_point, uint16_t max_layer) {
   if (!ix) return HX_ERR_INDEX_NOT_FOUND;
   uint32_t slot;

@@ -156,6 +156,32 @@ hx_status hx_index_load_graph(hx_index* idx, uint16_t layer, const uint64_t* nod
 /* VectorIndexState::Populated{entry_point,max_layer} (configuration.rs). */
 hx_status hx_index_set_entry(hx_index* idx, uint64_t entry_point, uint16_t max_layer);
 
+/* ---- row-image import / export ----------------------------------------------
+ * The reference's encoded row VALUES are accepted as they are stored, so hydration needs no
+ * decode step on the Rust side.
+ *  vector item rows  `[header f32][f32 x dimension]`, native endian, 4+4*dimension bytes each
+ *      (encode_item, search/vector/mod.rs:866-871; golden bytes magnitude_regressions.rs:333-338).
+ *      Checked like decode_item_borrowed (mod.rs:889-949): exact length, finite components,
+ *      magnitude bound, and the stored header must equal the recomputed one bit for bit
+ *      (cosine norm / 0.0 bias) — otherwise HX_ERR_INVARIANT_VIOLATION (HeaderMismatch).
+ *  neighbour rows: layer 0  = empty | `[0x12][count u32 BE][id u64 BE...]`
+ *                             | `[0x13][flags][count u32 BE][simhash u64 LE if flags&1][id u64 BE...]`
+ *                  (encoding/v1/values/vectors.rs:26-200),
+ *                  layer>=1 = `[count u32 BE][id u64 BE...]` (values/vectors/neighbors.rs:57-110).
+ *      Exact lengths are required (trailing bytes are corruption). */
+hx_status hx_index_load_vector_rows(hx_index* idx, const uint64_t* ids, const uint8_t* rows, size_t n);
+hx_status hx_index_load_neighbor_rows(hx_index* idx, uint16_t layer, const uint64_t* node_ids,
+                                      const uint8_t* blob, const uint64_t* row_offsets /* n+1 */, size_t n);
+/* Pure codecs (no device needed). decode: returns the ids (and the SimHash bits of a 0x13 row). */
+hx_status hx_decode_neighbor_row(uint16_t layer, const uint8_t* row, size_t len, uint64_t* out_ids,
+                                 size_t cap, size_t* out_count, uint64_t* out_simhash, int32_t* out_has_simhash);
+hx_status hx_encode_neighbor_row(uint16_t layer, const uint64_t* ids, size_t n, uint8_t* out, size_t cap,
+                                 size_t* out_len);
+/* Encode one row of the device graph (e.g. after hx_index_build) for persistence through the
+ * reference's normal mutation path. */
+hx_status hx_index_export_neighbor_row(hx_index* idx, uint16_t layer, uint64_t node_id, uint8_t* out,
+                                       size_t cap, size_t* out_len);
+
 /* Build the HNSW graph on the device from the loaded vectors (SURVEY §8(f).1:
  * insert_hnsw / search_layer_beam / select_diverse / add_bidirectional_link,
  * mutation.rs:787-1005,1498-1591, restated as batched concurrent insertion).

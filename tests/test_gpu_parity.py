@@ -505,3 +505,36 @@ def test_dense_tensor_core_path(gm, om, n, dim, B):
     storage0.load_vectors(ids[:10], rows[:10])
     with pytest.raises(hx.HelixDbError):
         storage0.search_dense_batch(queries[:1], hx.SearchParams.strict(1))
+
+
+# ---- row-image import: hydrate from the reference's encoded rows, search, export ---------------------------
+@pytest.mark.parametrize("gm,om", METRICS[:2])
+def test_row_image_import_and_export(gm, om):
+    n, dim = 800, 48
+    rng = np.random.default_rng(17)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    ids = np.arange(n, dtype=np.uint64) * 5 + 3
+    gpu_ref, ora = build_pair(gm, om, rows, ids=ids, m=8, m0=16, efc=40)
+    # encode every row the way the reference stores it: [header f32][f32 x dim], native endian (mod.rs:866-871)
+    item_rows = b"".join(struct.pack("<f", hxo.header(om, rows[i])) + rows[i].tobytes() for i in range(n))
+    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("img", "embedding", dim).with_m(8).with_m0(16).with_ef_construction(40))
+    gpu.load_vector_rows(ids, item_rows)
+    graph, state = ora.export_graph()
+    for layer, (nodes, offs, nbrs) in graph.items():
+        enc = [hx.encode_neighbor_row(layer, nbrs[offs[i]:offs[i + 1]]) for i in range(len(nodes))]
+        gpu.load_neighbor_rows(layer, nodes, enc)
+    gpu.set_entry(*state)
+    queries = rng.standard_normal((40, dim)).astype(np.float32)
+    gi, gs, gc = gpu.search_batch(queries, hx.SearchParams.strict(10))
+    for q in range(len(queries)):
+        oi, os_ = ora.search(queries[q], 10)
+        assert_same(gi[q], gs[q], gc[q], oi, os_, f"row image q={q}")
+    # export: the device row encodes back to the reference's bytes
+    some = int(ids[7])
+    assert gpu.export_neighbor_row(0, some) == hx.encode_neighbor_row(0, ora.neighbors(0, some))
+    # a stored header that does not match the recomputed one is a decode error (HeaderMismatch, mod.rs:942-945)
+    bad = bytearray(item_rows)
+    bad[0:4] = struct.pack("<f", 123.0)
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.load_vector_rows(ids, bytes(bad))
+    assert e.value.variant == "InvariantViolation"

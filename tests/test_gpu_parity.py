@@ -538,3 +538,38 @@ def test_row_image_import_and_export(gm, om):
     with pytest.raises(hx.HelixDbError) as e:
         gpu.load_vector_rows(ids, bytes(bad))
     assert e.value.variant == "InvariantViolation"
+
+
+# ---- the handle is Send + Sync: concurrent searches from several host threads (one query batch per thread) -------------------
+def test_concurrent_host_threads():
+    import threading
+    n, dim = 3000, 64
+    rng = np.random.default_rng(23)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    gpu, ora = build_pair(hx.Metric.Euclidean, hxo.EUCLIDEAN, rows, m=8, m0=16, efc=60)
+    queries = rng.standard_normal((6, 200, dim)).astype(np.float32)
+    params = hx.SearchParams.strict(10, 50)
+    expected = [gpu.search_batch(queries[t], params) for t in range(6)]
+    cand = hx.RestrictedVectorCandidates(np.arange(0, n, 3, dtype=np.uint64))
+    expected_r = [gpu.search_restricted_batch(queries[t][:20], params, cand) for t in range(6)]
+    results, errors = [None] * 6, []
+
+    def worker(t):
+        try:
+            for _ in range(5):
+                a = gpu.search_batch(queries[t], params)
+                b = gpu.search_restricted_batch(queries[t][:20], params, cand)
+            results[t] = (a, b)
+        except Exception as e:   # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t in range(6):
+        (ai, as_, ac), (bi, bs, bc) = results[t]
+        assert ai.tolist() == expected[t][0].tolist() and as_.tobytes() == expected[t][1].tobytes()
+        assert bi.tolist() == expected_r[t][0].tolist() and bs.tobytes() == expected_r[t][1].tobytes()

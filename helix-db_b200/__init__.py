@@ -17,6 +17,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import os
+from dataclasses import dataclass
 from pathlib import Path
 
 import numpy as np
@@ -112,6 +113,7 @@ ABI_SYMBOLS = [
     "hx_map_candidates_device", "hx_merge_topk_device", "hx_search_dense", "hx_last_error", "hx_last_error_index",
     "hx_version", "hx_last_kernel_ms", "hx_index_load_vector_rows", "hx_index_load_neighbor_rows",
     "hx_decode_neighbor_row", "hx_encode_neighbor_row", "hx_index_export_neighbor_row",
+    "hx_parse_vector_key", "hx_encode_vector_key",
 ]
 
 _lib = None
@@ -187,6 +189,10 @@ def load_library():
     L.hx_encode_neighbor_row.argtypes = [C.c_uint16, u64p, sz, u8p, sz, C.POINTER(sz)]
     L.hx_index_export_neighbor_row.restype = C.c_int32
     L.hx_index_export_neighbor_row.argtypes = [vp, C.c_uint16, C.c_uint64, u8p, sz, C.POINTER(sz)]
+    L.hx_parse_vector_key.restype = C.c_int32
+    L.hx_parse_vector_key.argtypes = [u8p, sz, vp]
+    L.hx_encode_vector_key.restype = C.c_int32
+    L.hx_encode_vector_key.argtypes = [vp, u8p, sz, C.POINTER(sz)]
     _lib = L
     return L
 
@@ -603,6 +609,49 @@ def encode_neighbor_row(layer: int, ids) -> bytes:
     out = (C.c_uint8 * (8 * a.size + 8))()
     n = C.c_size_t(0)
     _ck(L.hx_encode_neighbor_row(layer, p, a.size, out, len(out), C.byref(n)))
+    return bytes(out[:n.value])
+
+
+class KeyKind(enum.IntEnum):
+    """Row families of one vector index (encoding/v1/keys/vectors.rs:23-52)."""
+    Other = 0
+    Vector = 1
+    Layer0Neighbors = 2
+    UpperNeighbors = 3
+    SimHash = 4
+    UpperVector = 5
+    Metadata = 6
+
+
+class _CVectorKey(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("layer", C.c_uint16), ("reserved", C.c_uint16), ("index_id", C.c_uint64),
+                ("order_code", C.c_uint64), ("node_id", C.c_uint64)]
+
+
+@dataclass(frozen=True)
+class VectorKey:
+    kind: KeyKind
+    index_id: int
+    node_id: int = 0
+    layer: int = 0
+    order_code: int = 0
+
+
+def parse_vector_key(key: bytes) -> VectorKey:
+    """VectorKey::parse_from_slice (keys/vectors.rs:311-470) for the row families the mirror consumes."""
+    L = load_library()
+    buf = (C.c_uint8 * max(len(key), 1)).from_buffer_copy(key if key else b"\0")
+    out = _CVectorKey()
+    _ck(L.hx_parse_vector_key(buf, len(key), C.byref(out)))
+    return VectorKey(KeyKind(out.kind), int(out.index_id), int(out.node_id), int(out.layer), int(out.order_code))
+
+
+def encode_vector_key(key: VectorKey) -> bytes:
+    L = load_library()
+    ck = _CVectorKey(int(key.kind), key.layer, 0, key.index_id, key.order_code, key.node_id)
+    out = (C.c_uint8 * 32)()
+    n = C.c_size_t(0)
+    _ck(L.hx_encode_vector_key(C.byref(ck), out, len(out), C.byref(n)))
     return bytes(out[:n.value])
 
 

@@ -649,6 +649,82 @@ extern "C" hx_status hx_encode_neighbor_row(uint16_t layer, const uint64_t* ids,
   return HX_OK;
 }
 
+// ---- row keys (encoding/v1/keys/vectors.rs) -----------------------------------------------------------------------
+extern "C" hx_status hx_parse_vector_key(const uint8_t* key, size_t len, hx_vector_key* out) {
+  if (!out || (len && !key)) return HX_ERR_INVALID_PARAMETER;
+  memset(out, 0, sizeof(*out));
+  if (len == 0) { hx_set_error("empty key"); return HX_ERR_INVARIANT_VIOLATION; }
+  const uint8_t lane = key[0];
+  if (lane == 0x03) {                       // KEY_SPACE_INDEX / INDEX_TYPE_VECTOR: metadata + txn guard (keys/vectors.rs:321-361)
+    if (len < 2 || key[1] != 0x03) { hx_set_error("not a vector-index key"); return HX_ERR_INVARIANT_VIOLATION; }
+    if (len != 10 && len != 11) { hx_set_error("invalid vector default key length %zu", len); return HX_ERR_INVARIANT_VIOLATION; }
+    out->index_id = be64(key + 2);
+    if (len == 11) {
+      if (key[10] == 0x01) out->kind = HX_KEY_METADATA;
+      else if (key[10] != 0x09) { hx_set_error("invalid vector default key kind %#04x", key[10]); return HX_ERR_INVARIANT_VIOLATION; }
+    }
+    return HX_OK;
+  }
+  if (lane != 0xF0 && lane != 0xF1) { hx_set_error("invalid key prefix %#04x", lane); return HX_ERR_INVARIANT_VIOLATION; }
+  if (len < 9) { hx_set_error("vector key too short: %zu bytes", len); return HX_ERR_INVARIANT_VIOLATION; }
+  out->index_id = be64(key + 1);
+  if (len == 9) return HX_OK;               // lane prefix key
+  const uint8_t kind = key[9];
+  const size_t NODE = 18, LAYER_NODE = 20, ORDERED = 26, KINDPFX = 10, REVERSE = 28;
+  auto bad_len = [&]() { hx_set_error("invalid vector key length %zu for kind %#04x", len, kind); return HX_ERR_INVARIANT_VIOLATION; };
+  if (lane == 0xF0) {                       // vector-hot lane (:363-404)
+    switch (kind) {
+      case 0x16: if (len != NODE) return bad_len(); out->kind = HX_KEY_LAYER0_NEIGHBORS; out->node_id = be64(key + 10); return HX_OK;
+      case 0x11: if (len != LAYER_NODE) return bad_len(); out->kind = HX_KEY_UPPER_NEIGHBORS;
+                 out->layer = (uint16_t)((key[10] << 8) | key[11]); out->node_id = be64(key + 12); return HX_OK;
+      case 0x12: if (len != NODE) return bad_len(); out->kind = HX_KEY_SIMHASH; out->node_id = be64(key + 10); return HX_OK;
+      case 0x13: if (len != NODE) return bad_len(); out->kind = HX_KEY_UPPER_VECTOR; out->node_id = be64(key + 10); return HX_OK;
+      default: hx_set_error("invalid vector-hot key kind %#04x", kind); return HX_ERR_INVARIANT_VIOLATION;
+    }
+  }
+  switch (kind) {                           // layer-0 lane (:406-467)
+    case 0x02:
+      if (len == KINDPFX) return HX_OK;
+      if (len != ORDERED) return bad_len();
+      out->kind = HX_KEY_VECTOR; out->order_code = be64(key + 10); out->node_id = be64(key + 18); return HX_OK;
+    case 0x17: if (len != KINDPFX && len != ORDERED) return bad_len(); return HX_OK;
+    case 0x04: if (len != KINDPFX && len != LAYER_NODE) return bad_len(); return HX_OK;
+    case 0x05: if (len != NODE) return bad_len(); return HX_OK;
+    case 0x15: if (len != NODE && len != REVERSE) return bad_len(); return HX_OK;
+    default: hx_set_error("invalid vector-l0 key kind %#04x", kind); return HX_ERR_INVARIANT_VIOLATION;
+  }
+}
+
+extern "C" hx_status hx_encode_vector_key(const hx_vector_key* k, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!k) return HX_ERR_INVALID_PARAMETER;
+  size_t need = 0;
+  switch (k->kind) {
+    case HX_KEY_VECTOR: need = 26; break;
+    case HX_KEY_LAYER0_NEIGHBORS: case HX_KEY_SIMHASH: case HX_KEY_UPPER_VECTOR: need = 18; break;
+    case HX_KEY_UPPER_NEIGHBORS: need = 20; break;
+    case HX_KEY_METADATA: need = 11; break;
+    default: hx_set_error("key kind %d cannot be encoded", k->kind); return HX_ERR_INVALID_PARAMETER;
+  }
+  if (out_len) *out_len = need;
+  if (!out || cap < need) { hx_set_error("encoded key needs %zu bytes, capacity %zu", need, cap); return HX_ERR_INVALID_PARAMETER; }
+  size_t off = 0;
+  if (k->kind == HX_KEY_METADATA) {
+    out[off++] = 0x03; out[off++] = 0x03; put_be64(out + off, k->index_id); off += 8; out[off++] = 0x01;
+    return HX_OK;
+  }
+  out[off++] = k->kind == HX_KEY_VECTOR ? 0xF1 : 0xF0;
+  put_be64(out + off, k->index_id); off += 8;
+  switch (k->kind) {
+    case HX_KEY_VECTOR: out[off++] = 0x02; put_be64(out + off, k->order_code); off += 8; break;
+    case HX_KEY_LAYER0_NEIGHBORS: out[off++] = 0x16; break;
+    case HX_KEY_UPPER_NEIGHBORS: out[off++] = 0x11; out[off++] = (uint8_t)(k->layer >> 8); out[off++] = (uint8_t)k->layer; break;
+    case HX_KEY_SIMHASH: out[off++] = 0x12; break;
+    default: out[off++] = 0x13; break;
+  }
+  put_be64(out + off, k->node_id);
+  return HX_OK;
+}
+
 extern "C" hx_status hx_index_load_vector_rows(hx_index* ix, const uint64_t* ids, const uint8_t* rows, size_t n) {
   if (!ix) return HX_ERR_INDEX_NOT_FOUND;
   if (n && (!ids || !rows)) return HX_ERR_INVALID_PARAMETER;

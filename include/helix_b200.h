@@ -182,6 +182,37 @@ hx_status hx_encode_neighbor_row(uint16_t layer, const uint64_t* ids, size_t n, 
 hx_status hx_index_export_neighbor_row(hx_index* idx, uint16_t layer, uint64_t node_id, uint8_t* out,
                                        size_t cap, size_t* out_len);
 
+/* ---- row KEYS of the vector families the mirror consumes (encoding/v1/keys/vectors.rs:23-52) -------
+ *  HX_KEY_VECTOR           `[0xF1][index_id u64 BE][0x02][order_code u64 BE][node_id u64 BE]`  (:805-892)
+ *  HX_KEY_LAYER0_NEIGHBORS `[0xF0][index_id][0x16][node_id]`                                   (:673-745)
+ *  HX_KEY_UPPER_NEIGHBORS  `[0xF0][index_id][0x11][layer u16 BE][node_id]`                     (:1370-1457)
+ *  HX_KEY_SIMHASH          `[0xF0][index_id][0x12][node_id]`                                   (:1459-1530)
+ *  HX_KEY_UPPER_VECTOR     `[0xF0][index_id][0x13][node_id]`                                   (:1532-1603)
+ *  HX_KEY_METADATA         `[0x03][0x03][index_id][0x01]`                                      (:479-544)
+ * Exact lengths are required, like VectorKey::parse_from_slice (:311-470); any other vector-keyspace
+ * key (prefix keys, entry candidates, reverse edges, directory, txn guard) parses as HX_KEY_OTHER so a
+ * hydration loop can skip it; a key outside the vector keyspaces or with a wrong length for its kind
+ * is HX_ERR_INVARIANT_VIOLATION. */
+typedef enum {
+  HX_KEY_OTHER = 0,
+  HX_KEY_VECTOR = 1,
+  HX_KEY_LAYER0_NEIGHBORS = 2,
+  HX_KEY_UPPER_NEIGHBORS = 3,
+  HX_KEY_SIMHASH = 4,
+  HX_KEY_UPPER_VECTOR = 5,
+  HX_KEY_METADATA = 6
+} hx_key_kind;
+typedef struct {
+  int32_t  kind;        /* hx_key_kind */
+  uint16_t layer;       /* HX_KEY_UPPER_NEIGHBORS only */
+  uint16_t reserved;
+  uint64_t index_id;
+  uint64_t order_code;  /* HX_KEY_VECTOR only (SimHash-interleaved locality code, simhash.rs:44-59) */
+  uint64_t node_id;
+} hx_vector_key;
+hx_status hx_parse_vector_key(const uint8_t* key, size_t len, hx_vector_key* out);
+hx_status hx_encode_vector_key(const hx_vector_key* key, uint8_t* out, size_t cap, size_t* out_len);
+
 /* Build the HNSW graph on the device from the loaded vectors (SURVEY §8(f).1:
  * insert_hnsw / search_layer_beam / select_diverse / add_bidirectional_link,
  * mutation.rs:787-1005,1498-1591, restated as batched concurrent insertion).

@@ -146,12 +146,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel: str):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu summary, or None."""
+def ncu_traffic(kernel: str, shape: dict):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu summary — only when the capture was taken on
+    a launch of this very shape (a number for another launch size would not be "per launch like achieved"), else None."""
     p = ROOT / "profiles" / "ncu_summary.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(kernel, {}).get("dram_bytes_per_launch")
+            e = json.loads(p.read_text()).get(kernel, {})
+            return e.get("dram_bytes_per_launch") if e.get("shape") == shape else None
         except Exception:
             return None
     return None
@@ -425,7 +427,7 @@ def run_ours(args):
             "gpu_launches": args.steps * 2,
             "launches_per_step": {"k_validate_and_header": 1, "k_hnsw_search_tma": 1},
             "roofline": {"bound": "hbm", "kernel": "k_hnsw_search_tma", "achieved": round(achieved, 1), "peak": hbm_peak,
-                         "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_hnsw_search"),
+                         "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_hnsw_search", {"queries": Q, "rows": n, "dim": dim, "ef": ef}),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_per_launch),
                          "kernel_ms_per_launch": round(kernel_ms, 4),
                          "expansions_per_query": round(st_sum["expansion_steps"] / (args.steps * Q), 1),
@@ -600,7 +602,7 @@ def run_prefilter(args):
             "gpu_launches": args.steps * 3,
             "launches_per_step": {"k_validate_and_header": 1, "k_scan": 1, "k_select": 1},
             "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_scan"), "peak_source": peak_src,
+                         "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_scan", {"queries": B, "candidates": per_q, "dim": dim}), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms_per_launch": round(kernel_ms, 4)},
             "clocks": clocks,
         }
@@ -718,7 +720,7 @@ def run_dense(args):
                            "recipe": args.recipe},
                 "roofline": {"bound": "tensor", "kernel": "k_dense_scores", "achieved": round(flop / (kernel_ms * 1e-3) / 1e12, 1),
                              "peak": tf_peak, "unit": "TFLOP/s", "frac": round(flop / (kernel_ms * 1e-3) / 1e12 / tf_peak, 4),
-                             "traffic": ncu_traffic("k_dense_scores"), "flop_per_launch_per_gpu": flop,
+                             "traffic": ncu_traffic("k_dense_scores", {"queries": B, "rows": n, "dim": dim}), "flop_per_launch_per_gpu": flop,
                              "kernel_ms_per_launch": round(kernel_ms, 4),
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); per GPU"},
                 "gpu_launches": args.steps * 7, "clocks": clocks}

@@ -13,6 +13,7 @@
 
 #include "hx_index.hpp"
 #include "k_hnsw.cuh"
+#include "k_hnsw_ring.cuh"
 #include "k_scan.cuh"
 #include "k_util.cuh"
 
@@ -197,6 +198,7 @@ void HxScratch::destroy() {
   d_qstatus.release(); d_out_counts.release(); d_qstats.release(); d_err.release(); d_epochs.release();
   d_cand_slots.release(); d_out_ids.release(); d_cand_ids.release(); d_cand_offsets.release(); d_keys.release();
   d_stamps.release();
+  d_vtab.release(); d_vpool.release(); d_vbusy.release();
   for (auto& m : misc) m.release();
   h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
   h_counts.release(); h_qstats.release(); h_status.release(); h_err.release();
@@ -1101,7 +1103,64 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     if (tma_R == 0) use_tma = false;
     else tma_wstride = round_up((uint32_t)(fixed + (size_t)tma_R * ix->ld * 4), 128);
   }
-  if (use_tma) {
+  // Ring build (k_hnsw_ring.cuh): L2-resident visited hash sets, per-slot mbarrier ring, warp-per-row reduction.
+  // Default for Euclidean / cosine whenever the batch fills the GPU; HX_HNSW_IMPL=tma|ldg select the first generation.
+  bool use_ring = !latency && ix->cfg.metric != HX_METRIC_MANHATTAN;
+  if (const char* env = getenv("HX_HNSW_IMPL")) use_ring = use_ring && strcmp(env, "ring") == 0;
+  uint32_t ring_R = 0, ring_wstride = 0, ring_wpc = 0, ring_qch = 0, vt_cap = 0;
+  if (use_ring) {
+    const uint32_t chunks = ix->ld / 32;
+    ring_qch = chunks <= 8 ? 8 : chunks <= 24 ? 24 : chunks <= 48 ? 48 : 0;
+    const size_t rowbytes = (size_t)ix->ld * 4;
+    const size_t fixed0 = (ring_qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 12;
+    const size_t budget = 227 * 1024;
+    uint32_t want_wpc = 16, want_R = 0;
+    if (const char* env = getenv("HX_RING_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 16) want_wpc = (uint32_t)v; }
+    if (const char* env = getenv("HX_RING_R")) { const int v = atoi(env); if (v >= 1 && v <= 32) want_R = (uint32_t)v; }
+    // few queries: fewer warps per CTA so that the batch spreads over all SMs (and each warp gets a deeper ring)
+    const uint32_t spread = (uint32_t)std::max<size_t>(1, (B + ix->sm_count - 1) / (size_t)ix->sm_count);
+    want_wpc = std::min(want_wpc, spread);
+    for (uint32_t w = want_wpc; w >= 1; --w) {
+      const size_t per_warp = (budget / w) & ~(size_t)127;
+      if (per_warp <= fixed0 + 8 + rowbytes) continue;
+      uint32_t r = (uint32_t)std::min<size_t>(32, (per_warp - fixed0) / (rowbytes + 8));
+      if (want_R) r = std::min(r, want_R);
+      if (r >= 4 || w == 1 || (want_R && r == want_R)) { ring_wpc = w; ring_R = r; break; }
+    }
+    if (ring_R == 0) use_ring = false;
+    else ring_wstride = round_up((uint32_t)(fixed0 + (size_t)ring_R * (rowbytes + 8)), 128);
+    uint32_t lg = 12;
+    while ((1u << lg) < 64u * ef && lg < 24) lg++;
+    if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) lg = (uint32_t)v; }
+    vt_cap = 1u << lg;
+  }
+  HxRingArgs rg{};
+  if (use_ring) {
+    use_tma = false;
+    grid = (uint32_t)std::min<size_t>((B + ring_wpc - 1) / ring_wpc, (size_t)ix->sm_count);
+    slots = 0;
+    smem_launch = (size_t)ring_wpc * ring_wstride;
+    const size_t vslots = (size_t)grid * ring_wpc;
+    uint32_t pool_n = 32;
+    if (const char* env = getenv("HX_VT_POOL")) { const int v = atoi(env); if (v >= 0 && v <= 1024) pool_n = (uint32_t)v; }
+    const uint32_t pool_cap = std::max<uint32_t>(vt_cap * 16u, 65536u);
+    if ((rc = s->d_vtab.reserve(vslots * vt_cap))) return rc;
+    if (s->vpool_n != pool_n || s->vpool_cap != pool_cap || !s->d_vbusy.p) {
+      if ((rc = s->d_vpool.reserve((size_t)std::max(pool_n, 1u) * pool_cap))) return rc;
+      if ((rc = s->d_vbusy.reserve(std::max(pool_n, 1u)))) return rc;
+      HX_CUDA(cudaMemsetAsync(s->d_vbusy.p, 0, std::max(pool_n, 1u) * sizeof(uint32_t), stream));
+      s->vpool_n = pool_n;
+      s->vpool_cap = pool_cap;
+    }
+    rg.vtab = s->d_vtab.p;
+    rg.vt_cap = vt_cap;
+    rg.pool = s->d_vpool.p;
+    rg.pool_busy = s->d_vbusy.p;
+    rg.pool_n = pool_n;
+    rg.pool_cap = pool_cap;
+    rg.l2_hint = 1;
+    if (const char* env = getenv("HX_L2_HINT")) rg.l2_hint = atoi(env) ? 1u : 0u;
+  } else if (use_tma) {
     grid = (uint32_t)std::min<size_t>((B + tma_wpc - 1) / tma_wpc, (size_t)ix->sm_count);
     slots = (uint32_t)ix->sm_count * 16;
     smem_launch = (size_t)tma_wpc * tma_wstride;
@@ -1129,7 +1188,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     if ((size_t)slots * stride > budget) slots = max_ctas * wpc;
     smem_launch = (size_t)wpc * wstride;
   }
-  if (s->stamp_grid < slots || s->stamp_n != ix->n || !s->d_stamps.p) {
+  if (slots && (s->stamp_grid < slots || s->stamp_n != ix->n || !s->d_stamps.p)) {
     if ((rc = s->d_stamps.reserve((size_t)slots * stride))) return rc;
     if ((rc = s->d_epochs.reserve(slots))) return rc;
     HX_CUDA(cudaMemsetAsync(s->d_stamps.p, 0, (size_t)slots * stride, stream));
@@ -1138,8 +1197,9 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     s->stamp_stride = stride;
     s->stamp_n = ix->n;
   }
-  if ((rc = s->d_err.reserve(1))) return rc;
-  HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, sizeof(uint32_t), stream));
+  if ((rc = s->d_err.reserve(2))) return rc;   // [0] error flags, [1] query counter of the ring build
+  HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, 2 * sizeof(uint32_t), stream));
+  rg.counter = s->d_err.p + 1;
   HxHnswArgs a{};
   a.queries = d_queries;
   a.q_hdr = s->d_qhdr.p;
@@ -1166,9 +1226,21 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
                                  cudaSharedmemCarveoutMaxShared));                                                 \
     k_hnsw_search_warp<M, 8, MB><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, wstride);                 \
   } while (0)
+#define HX_LAUNCH_RING(M, Q)                                                                                       \
+  do {                                                                                                             \
+    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_ring<M, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                 (int)smem_launch));                                                               \
+    k_hnsw_search_ring<M, Q><<<grid, ring_wpc * 32, smem_launch, stream>>>(dev, a, rg, ring_wstride, ring_R);      \
+  } while (0)
 #define HX_LAUNCH_HNSW(M)                                                                                          \
   do {                                                                                                             \
-    if (use_tma) {                                                                                                 \
+    if (use_ring && M != HXM_MANHATTAN) {                                                                          \
+      constexpr int MR = M == HXM_MANHATTAN ? HXM_EUCLIDEAN : M;                                                   \
+      if (ring_qch == 8) HX_LAUNCH_RING(MR, 8);                                                                    \
+      else if (ring_qch == 24) HX_LAUNCH_RING(MR, 24);                                                             \
+      else if (ring_qch == 48) HX_LAUNCH_RING(MR, 48);                                                             \
+      else HX_LAUNCH_RING(MR, 0);                                                                                  \
+    } else if (use_tma) {                                                                                                 \
       HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_tma<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                    (int)smem_launch));                                                             \
       k_hnsw_search_tma<M><<<grid, tma_wpc * 32, smem_launch, stream>>>(dev, a, tma_wstride, tma_R);               \
@@ -1195,6 +1267,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     default: HX_LAUNCH_HNSW(HXM_MANHATTAN); break;
   }
 #undef HX_LAUNCH_HNSW
+#undef HX_LAUNCH_RING
 #undef HX_LAUNCH_WARP
   HX_CUDA(cudaGetLastError());
   HX_CUDA(cudaEventRecord(e1, stream));
@@ -1206,6 +1279,10 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
 static hx_status check_device_flags(uint32_t flags) {
   if (flags & HXF_INVALID_SCORE) {
     hx_set_error("vector distance kernel emitted an invalid score");   // model.rs:21-28
+    return HX_ERR_INVARIANT_VIOLATION;
+  }
+  if (flags & HXF_VT_OVERFLOW) {
+    hx_set_error("visited-set overflow: a query visited more nodes than the overflow tables hold");
     return HX_ERR_INVARIANT_VIOLATION;
   }
   if (flags & HXF_TIE_OVERFLOW) {

@@ -83,6 +83,8 @@ struct HxScratch {
   DevBuf<uint32_t> d_qstatus, d_out_counts, d_qstats, d_err, d_epochs, d_cand_slots;
   DevBuf<uint64_t> d_out_ids, d_cand_ids, d_cand_offsets, d_keys;
   DevBuf<uint8_t> d_stamps;
+  DevBuf<uint32_t> d_vtab, d_vpool, d_vbusy;   // ring build: visited hash sets, overflow pool, pool busy flags
+  uint32_t vpool_n = 0xffffffffu, vpool_cap = 0;
   DevBuf<uint8_t> misc[16];   // dense path buffers (kept across calls)
   size_t stamp_stride = 0;
   uint32_t stamp_grid = 0;

@@ -322,6 +322,42 @@ def test_many_queries_and_epoch_wrap():
         assert a[0].tolist() == oi[it % 7].tolist() and b[0].tobytes() == os_[it % 7].tobytes()
 
 
+# ---- every build of the traversal kernel answers with the same bits: ring (default), first-generation TMA / LDG builds,
+# ---- and the ring build with visited tables so small that every query re-hashes into the overflow pool ------------------
+@pytest.mark.parametrize("gm,om,dim", [(hx.Metric.Euclidean, hxo.EUCLIDEAN, 70), (hx.Metric.Cosine, hxo.COSINE, 768),
+                                       (hx.Metric.Cosine, hxo.COSINE, 40), (hx.Metric.Euclidean, hxo.EUCLIDEAN, 1600)])
+def test_traversal_builds_agree(gm, om, dim, monkeypatch):
+    n, nq = (1200, 320) if dim < 1000 else (500, 300)
+    rng = np.random.default_rng(dim + 7)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    gpu, ora = build_pair(gm, om, rows, m=8, m0=16, efc=60)
+    k, ef = 10, 64
+    oi, os_, oc, ost, _ = ora.search_batch(queries, k, ef, threads=4)
+    params = hx.SearchParams.strict(k, ef)
+    params.collect_stats = True
+    variants = [{}, {"HX_HNSW_IMPL": "tma"}, {"HX_HNSW_IMPL": "ldg"}, {"HX_VT_CAP_LOG2": "6"},
+                {"HX_RING_WARPS": "5", "HX_RING_R": "2", "HX_L2_HINT": "0"}, {"HX_RING_R": "1"}]
+    for env in variants:
+        for key in ("HX_HNSW_IMPL", "HX_VT_CAP_LOG2", "HX_RING_WARPS", "HX_RING_R", "HX_L2_HINT"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        st = hx.SearchStats()
+        gi, gs, gc = gpu.search_batch(queries, params, st)
+        assert gc.tolist() == oc.tolist(), env
+        assert gi.tolist() == oi.tolist(), env
+        assert gs.tobytes() == os_.tobytes(), env
+        for f in ("expansion_steps", "neighbors_examined", "distance_computations"):
+            assert getattr(st, f) == ost[f], (f, env)
+    # a pool of zero overflow tables: the overflow is reported, never silently truncated
+    monkeypatch.setenv("HX_VT_CAP_LOG2", "6")
+    monkeypatch.setenv("HX_VT_POOL", "0")
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search_batch(queries, params)
+    assert e.value.variant == "InvariantViolation"
+
+
 # ---- sharded path: per-shard top-k merged by (score, id) equals the unsharded exact answer ---------------------------------------
 def test_merge_topk_matches_unsharded_scan():
     import torch

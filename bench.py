@@ -401,6 +401,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args, ix, qsets[0], truth[:rq] if rq else None)
 
+    impl = os.environ.get("HX_HNSW_IMPL", "ring")
+    hnsw_kernel = {"ring": "k_hnsw_search_ring", "tma": "k_hnsw_search_tma", "ldg": "k_hnsw_search_warp"}.get(impl, impl)
     if rank == 0:
         line = {
             "metric": "queries/sec @ recall@10, DBpedia-1M d=768 top-10, 1/2/4/8 B200 vs CPU ref",
@@ -425,9 +427,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 4 + 4,
                     "api": "hx_search (C ABI, pinned host buffers, blocking)"},
             "gpu_launches": args.steps * 2,
-            "launches_per_step": {"k_validate_and_header": 1, "k_hnsw_search_tma": 1},
-            "roofline": {"bound": "hbm", "kernel": "k_hnsw_search_tma", "achieved": round(achieved, 1), "peak": hbm_peak,
-                         "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_hnsw_search", {"queries": Q, "rows": n, "dim": dim, "ef": ef}),
+            "launches_per_step": {"k_validate_and_header": 1, hnsw_kernel: 1},
+            "roofline": {"bound": "hbm", "kernel": hnsw_kernel, "achieved": round(achieved, 1), "peak": hbm_peak,
+                         "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_hnsw_search", {"queries": Q, "rows": n, "dim": dim, "ef": EF}),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_per_launch),
                          "kernel_ms_per_launch": round(kernel_ms, 4),
                          "expansions_per_query": round(st_sum["expansion_steps"] / (args.steps * Q), 1),

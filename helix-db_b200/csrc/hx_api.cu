@@ -1103,17 +1103,28 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     if (tma_R == 0) use_tma = false;
     else tma_wstride = round_up((uint32_t)(fixed + (size_t)tma_R * ix->ld * 4), 128);
   }
-  // Ring build (k_hnsw_ring.cuh): L2-resident visited hash sets, per-slot mbarrier ring, warp-per-row reduction.
-  // Default for Euclidean / cosine whenever the batch fills the GPU; HX_HNSW_IMPL=tma|ldg select the first generation.
-  bool use_ring = !latency && ix->cfg.metric != HX_METRIC_MANHATTAN;
+  // Ring builds (k_hnsw_ring.cuh): visited hash sets, per-slot mbarrier ring, warp-per-row reduction.  Default for
+  // Euclidean / cosine: warp-per-query when the batch fills the GPU, CTA-per-query (visited set in shared memory) below
+  // that.  HX_HNSW_IMPL=tma|ldg (throughput) and HX_LAT_IMPL=tma|ldg (latency) select the first generation for A/B runs.
+  const bool small_batch = B < (size_t)ix->sm_count;
+  const bool ring_metric = ix->cfg.metric != HX_METRIC_MANHATTAN;
+  bool use_ring = !small_batch && ring_metric;
   if (const char* env = getenv("HX_HNSW_IMPL")) use_ring = use_ring && strcmp(env, "ring") == 0;
-  uint32_t ring_R = 0, ring_wstride = 0, ring_wpc = 0, ring_qch = 0, vt_cap = 0;
-  if (use_ring) {
+  bool use_cta_ring = small_batch && ring_metric;
+  if (const char* env = getenv("HX_LAT_IMPL")) use_cta_ring = use_cta_ring && strcmp(env, "ring") == 0;
+  uint32_t ring_R = 0, ring_wstride = 0, ring_wpc = 0, ring_qch = 0, vt_cap = 0, cta_vt_cap = 0, cta_warps = 8;
+  const size_t rowbytes = (size_t)ix->ld * 4;
+  const size_t ring_budget = 227 * 1024;
+  if (use_ring || use_cta_ring) {
     const uint32_t chunks = ix->ld / 32;
     ring_qch = chunks <= 8 ? 8 : chunks <= 24 ? 24 : chunks <= 48 ? 48 : 0;
-    const size_t rowbytes = (size_t)ix->ld * 4;
+    uint32_t lg = 12;
+    while ((1u << lg) < 64u * ef && lg < 24) lg++;
+    if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) lg = (uint32_t)v; }
+    vt_cap = 1u << lg;
+  }
+  if (use_ring) {
     const size_t fixed0 = (ring_qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 12;
-    const size_t budget = 227 * 1024;
     uint32_t want_wpc = 16, want_R = 0;
     if (const char* env = getenv("HX_RING_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 16) want_wpc = (uint32_t)v; }
     if (const char* env = getenv("HX_RING_R")) { const int v = atoi(env); if (v >= 1 && v <= 32) want_R = (uint32_t)v; }
@@ -1121,7 +1132,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     const uint32_t spread = (uint32_t)std::max<size_t>(1, (B + ix->sm_count - 1) / (size_t)ix->sm_count);
     want_wpc = std::min(want_wpc, spread);
     for (uint32_t w = want_wpc; w >= 1; --w) {
-      const size_t per_warp = (budget / w) & ~(size_t)127;
+      const size_t per_warp = (ring_budget / w) & ~(size_t)127;
       if (per_warp <= fixed0 + 8 + rowbytes) continue;
       uint32_t r = (uint32_t)std::min<size_t>(32, (per_warp - fixed0) / (rowbytes + 8));
       if (want_R) r = std::min(r, want_R);
@@ -1129,22 +1140,40 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     }
     if (ring_R == 0) use_ring = false;
     else ring_wstride = round_up((uint32_t)(fixed0 + (size_t)ring_R * (rowbytes + 8)), 128);
-    uint32_t lg = 12;
-    while ((1u << lg) < 64u * ef && lg < 24) lg++;
-    if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) lg = (uint32_t)v; }
-    vt_cap = 1u << lg;
+  }
+  size_t cta_ring_smem = 0;
+  if (use_cta_ring) {
+    // rows in flight first (up to 32), then the largest visited table that still fits (at least 1024 entries)
+    const size_t fixed0 = (ring_qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 8 + 256;
+    cta_vt_cap = vt_cap;
+    while (cta_vt_cap > 1024 && fixed0 + (size_t)cta_vt_cap * 4 + 8 * (rowbytes + 8) > ring_budget) cta_vt_cap >>= 1;
+    if (fixed0 + (size_t)cta_vt_cap * 4 + rowbytes + 8 > ring_budget) {
+      use_cta_ring = false;
+    } else {
+      ring_R = (uint32_t)std::min<size_t>(32, (ring_budget - fixed0 - (size_t)cta_vt_cap * 4) / (rowbytes + 8));
+      if (const char* env = getenv("HX_RING_R")) { const int v = atoi(env); if (v >= 1 && v <= 32) ring_R = std::min(ring_R, (uint32_t)v); }
+      cta_ring_smem = fixed0 - 256 + (size_t)cta_vt_cap * 4 + (size_t)ring_R * (rowbytes + 8);
+      cta_warps = ring_qch == 48 ? 8 : 12;
+      if (const char* env = getenv("HX_LAT_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= (int)cta_warps) cta_warps = (uint32_t)v; }
+    }
   }
   HxRingArgs rg{};
-  if (use_ring) {
+  if (use_ring || use_cta_ring) {
     use_tma = false;
-    grid = (uint32_t)std::min<size_t>((B + ring_wpc - 1) / ring_wpc, (size_t)ix->sm_count);
     slots = 0;
-    smem_launch = (size_t)ring_wpc * ring_wstride;
-    const size_t vslots = (size_t)grid * ring_wpc;
+    size_t vslots = 0;
+    if (use_ring) {
+      grid = (uint32_t)std::min<size_t>((B + ring_wpc - 1) / ring_wpc, (size_t)ix->sm_count);
+      smem_launch = (size_t)ring_wpc * ring_wstride;
+      vslots = (size_t)grid * ring_wpc;
+    } else {
+      grid = (uint32_t)B;   // B < #SMs
+      smem_launch = cta_ring_smem;
+    }
     uint32_t pool_n = 32;
     if (const char* env = getenv("HX_VT_POOL")) { const int v = atoi(env); if (v >= 0 && v <= 1024) pool_n = (uint32_t)v; }
     const uint32_t pool_cap = std::max<uint32_t>(vt_cap * 16u, 65536u);
-    if ((rc = s->d_vtab.reserve(vslots * vt_cap))) return rc;
+    if (vslots && (rc = s->d_vtab.reserve(vslots * vt_cap))) return rc;
     if (s->vpool_n != pool_n || s->vpool_cap != pool_cap || !s->d_vbusy.p) {
       if ((rc = s->d_vpool.reserve((size_t)std::max(pool_n, 1u) * pool_cap))) return rc;
       if ((rc = s->d_vbusy.reserve(std::max(pool_n, 1u)))) return rc;
@@ -1160,6 +1189,15 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     rg.pool_cap = pool_cap;
     rg.l2_hint = 1;
     if (const char* env = getenv("HX_L2_HINT")) rg.l2_hint = atoi(env) ? 1u : 0u;
+    rg.batch_admit = 1;
+    if (const char* env = getenv("HX_LAT_ADMIT")) rg.batch_admit = strcmp(env, "seq") == 0 ? 0u : 1u;
+    if (const char* env = getenv("HX_PHASE_PROF")) {   // diagnostics: cycle sums per phase of the latency build
+      if (atoi(env)) {
+        if ((rc = s->d_prof.reserve(8))) return rc;
+        if (!s->prof_init) { HX_CUDA(cudaMemsetAsync(s->d_prof.p, 0, 8 * sizeof(unsigned long long), stream)); s->prof_init = true; }
+        rg.prof = s->d_prof.p;
+      }
+    }
   } else if (use_tma) {
     grid = (uint32_t)std::min<size_t>((B + tma_wpc - 1) / tma_wpc, (size_t)ix->sm_count);
     slots = (uint32_t)ix->sm_count * 16;
@@ -1169,7 +1207,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     slots = (uint32_t)ix->sm_count * 4;
     smem_launch = smem;
     // TMA-staged latency build when at least 8 rows fit next to the query state
-    const char* env = getenv("HX_HNSW_IMPL");
+    const char* env = getenv("HX_LAT_IMPL");
     const size_t fixed = (size_t)ix->ld * 4 + (size_t)ef * 8 + HX_TIE_CAP * 8 + 8 + (size_t)fr_cap * 12;
     if (!(env && strcmp(env, "ldg") == 0) && 200 * 1024 > fixed + 8 * (size_t)ix->ld * 4) {
       cta_RC = (uint32_t)std::min<size_t>(32, (200 * 1024 - fixed) / ((size_t)ix->ld * 4));
@@ -1232,9 +1270,27 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
                                  (int)smem_launch));                                                               \
     k_hnsw_search_ring<M, Q><<<grid, ring_wpc * 32, smem_launch, stream>>>(dev, a, rg, ring_wstride, ring_R);      \
   } while (0)
+#define HX_LAUNCH_CTA_RING2(M, Q, NBV)                                                                             \
+  do {                                                                                                             \
+    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_cta_ring<M, Q, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 (int)smem_launch));                                                               \
+    k_hnsw_search_cta_ring<M, Q, NBV><<<grid, cta_warps * 32, smem_launch, stream>>>(dev, a, rg, ring_R,           \
+                                                                                     cta_vt_cap);                  \
+  } while (0)
+#define HX_LAUNCH_CTA_RING(M, Q)                                                                                   \
+  do {                                                                                                             \
+    if (ef <= 128) HX_LAUNCH_CTA_RING2(M, Q, 4);                                                                   \
+    else HX_LAUNCH_CTA_RING2(M, Q, 0);                                                                             \
+  } while (0)
 #define HX_LAUNCH_HNSW(M)                                                                                          \
   do {                                                                                                             \
-    if (use_ring && M != HXM_MANHATTAN) {                                                                          \
+    if (use_cta_ring && M != HXM_MANHATTAN) {                                                                      \
+      constexpr int MR = M == HXM_MANHATTAN ? HXM_EUCLIDEAN : M;                                                   \
+      if (ring_qch == 8) HX_LAUNCH_CTA_RING(MR, 8);                                                                \
+      else if (ring_qch == 24) HX_LAUNCH_CTA_RING(MR, 24);                                                         \
+      else if (ring_qch == 48) HX_LAUNCH_CTA_RING(MR, 48);                                                         \
+      else HX_LAUNCH_CTA_RING(MR, 0);                                                                              \
+    } else if (use_ring && M != HXM_MANHATTAN) {                                                                   \
       constexpr int MR = M == HXM_MANHATTAN ? HXM_EUCLIDEAN : M;                                                   \
       if (ring_qch == 8) HX_LAUNCH_RING(MR, 8);                                                                    \
       else if (ring_qch == 24) HX_LAUNCH_RING(MR, 24);                                                             \
@@ -1268,6 +1324,8 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   }
 #undef HX_LAUNCH_HNSW
 #undef HX_LAUNCH_RING
+#undef HX_LAUNCH_CTA_RING
+#undef HX_LAUNCH_CTA_RING2
 #undef HX_LAUNCH_WARP
   HX_CUDA(cudaGetLastError());
   HX_CUDA(cudaEventRecord(e1, stream));
@@ -1701,6 +1759,15 @@ extern "C" hx_status hx_last_kernel_ms(hx_index* ix, float* ms, uint32_t* launch
     s->ring_pending = 0;
     ix->last_kernel_ms = total;
     ix->last_kernel_launches = cnt;
+  }
+  if (s && s->prof_init && s->d_prof.p) {   // HX_PHASE_PROF diagnostics: print and reset the phase cycle sums
+    unsigned long long h[8];
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h, s->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "HX_PHASE_PROF cycles: pop=%llu row+deg=%llu visited+issue=%llu wait+score=%llu admit=%llu\n", h[0], h[1],
+              h[2], h[3], h[4]);
+      cudaMemset(s->d_prof.p, 0, sizeof(h));
+    }
   }
   if (ms) *ms = ix->last_kernel_ms;
   if (launches) *launches = ix->last_kernel_launches;

@@ -85,6 +85,8 @@ struct HxScratch {
   DevBuf<uint8_t> d_stamps;
   DevBuf<uint32_t> d_vtab, d_vpool, d_vbusy;   // ring build: visited hash sets, overflow pool, pool busy flags
   uint32_t vpool_n = 0xffffffffu, vpool_cap = 0;
+  DevBuf<unsigned long long> d_prof;   // HX_PHASE_PROF diagnostics
+  bool prof_init = false;
   DevBuf<uint8_t> misc[16];   // dense path buffers (kept across calls)
   size_t stamp_stride = 0;
   uint32_t stamp_grid = 0;

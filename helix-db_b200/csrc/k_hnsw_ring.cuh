@@ -32,6 +32,8 @@ struct HxRingArgs {
   uint32_t pool_n, pool_cap;
   uint32_t* counter;     // next query index (zeroed before the launch)
   uint32_t l2_hint;      // 1: evict-first cache hint on row copies
+  uint32_t batch_admit;  // 1: one-pass admission of a frontier (latency build, register beam)
+  unsigned long long* prof;   // optional [8] cycle sums of the latency build's phases (HX_PHASE_PROF=1, diagnostics only)
 };
 
 __device__ __forceinline__ uint64_t hx_policy_evict_first() {
@@ -467,5 +469,540 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
       atomicExch(rg.pool_busy + pool_idx, 0u);
     }
     __syncwarp();
+  }
+}
+
+// ---- sorted beam held in the registers of one warp (latency build) ----------------------------------------------------------
+// Position p = 32 r + lane lives in v[r] of that lane; positions >= len hold HX_KEY_MAX, whose bit 0 ("expanded") is set,
+// so neither the rank count nor the search for the first unexpanded entry needs a length test.  An insertion is one
+// redux for the rank and one shuffle-up per register for the shift — no shared-memory round trips on the admission chain.
+template <int NB>
+struct HxRegBeam {
+  uint64_t v[NB];
+  uint32_t len;
+};
+template <int NB>
+__device__ __forceinline__ uint64_t hx_rbeam_get(const HxRegBeam<NB>& b, uint32_t p) {
+  uint64_t t = 0;   // mask-select (not `if`): keeps v[] in registers — a compare chain is turned into an indexed local load
+#pragma unroll
+  for (int r = 0; r < NB; ++r) t |= b.v[r] & (0ull - (uint64_t)((uint32_t)r == (p >> 5)));
+  return __shfl_sync(0xffffffffu, t, p & 31u);
+}
+// Insert `key` (absent, and below the current maximum when the beam is full).  Returns the evicted entry or HX_KEY_MAX.
+template <int NB>
+__device__ __forceinline__ uint64_t hx_rbeam_insert(HxRegBeam<NB>& b, uint32_t ef, uint64_t key, uint32_t lane) {
+  const unsigned FULL = 0xffffffffu;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int r = 0; r < NB; ++r) cnt += (b.v[r] < key) ? 1u : 0u;
+  const uint32_t pos = __reduce_add_sync(FULL, cnt);
+  const bool full = b.len == ef;
+  uint64_t ev = HX_KEY_MAX;
+  if (full) ev = hx_rbeam_get(b, ef - 1u);
+#pragma unroll
+  for (int r = NB - 1; r >= 0; --r) {
+    const uint64_t up = __shfl_up_sync(FULL, b.v[r], 1);
+    const uint64_t carry = r > 0 ? __shfl_sync(FULL, b.v[r > 0 ? r - 1 : 0], 31) : 0ull;
+    const uint64_t prev = lane == 0 ? carry : up;   // the entry at position p - 1
+    const uint32_t p = (uint32_t)r * 32u + lane;
+    if (p > pos) b.v[r] = prev;
+    else if (p == pos) b.v[r] = key;
+    if (p >= ef) b.v[r] = HX_KEY_MAX;               // what slid past the end of a full beam is gone
+  }
+  if (!full) b.len += 1;
+  return ev;
+}
+template <int NB>
+__device__ __forceinline__ uint32_t hx_rbeam_first_unexpanded(const HxRegBeam<NB>& b) {
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    const uint32_t m = __ballot_sync(0xffffffffu, !(b.v[r] & 1ull));
+    if (m) return (uint32_t)r * 32u + (uint32_t)__ffs((int)m) - 1u;
+  }
+  return HX_ABSENT;
+}
+
+// Admit up to 32 scored neighbours (lane f holds candidate f, in neighbour-id order) in ONE pass, with exactly the outcome
+// of the reference's sequential loop (search.rs:934-953: `dist < w.max || len < ef`, push, evict the maximum):
+//  * sequentially, candidate c is admitted iff fewer than ef members of (beam  U  earlier admitted candidates) have a
+//    score <= s_c  (w.max is the ef-th smallest member, and the test is on the score alone, strict).  A rejected earlier
+//    candidate c' with s_c' <= s_c forces c's rejection too, so "earlier admitted" may be replaced by "earlier":
+//        admitted(c)  <=>  #{x in beam : s_x <= s_c} + #{c' before c : s_c' <= s_c} < ef      (induction on id order)
+//  * the beam afterwards is the ef smallest keys of beam U admitted; evictions happen in descending key order, so the
+//    tie stack (evicted-unexpanded entries whose score equals the final w.max, pushed in eviction order) and `dropped`
+//    (any other evicted-unexpanded entry; or older ties once w.max has decreased) follow from the merged ranks.
+// `stage` = ef u64 of shared memory.  Returns the mask of admitted lanes.
+template <int NB>
+__device__ __forceinline__ uint32_t hx_rbeam_admit_batch(HxRegBeam<NB>& b, uint32_t& wmax, uint64_t* tie, uint32_t& tie_len,
+                                                         uint32_t& dropped, uint64_t* stage, uint32_t ef, uint32_t sbits,
+                                                         uint32_t slot, bool valid, uint32_t lane, uint32_t* err_flags) {
+  const unsigned FULL = 0xffffffffu;
+  const bool pass = valid && ((sbits < wmax) || (b.len < ef));   // necessary: w.max never increases
+  const uint32_t pm = __ballot_sync(FULL, pass);
+  if (!pm) return 0u;
+  uint32_t cW = 0, cC = 0;
+  for (uint32_t m = pm; m; m &= m - 1) {
+    const int j = __ffs((int)m) - 1;
+    const uint32_t sj = __shfl_sync(FULL, sbits, j);
+    const uint64_t bound = ((uint64_t)sj + 1ull) << 32;   // every key with score <= s_j is below it
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < NB; ++r) c += (b.v[r] < bound) ? 1u : 0u;
+    const uint32_t tot = __reduce_add_sync(FULL, c);
+    if ((int)lane == j) cW = tot;
+    if (pass && (int)lane > j && sj <= sbits) cC++;
+  }
+  const bool adm = pass && (cW + cC < ef);
+  const uint32_t am = __ballot_sync(FULL, adm);
+  if (!am) return 0u;
+  const uint32_t n_adm = (uint32_t)__popc(am);
+  const uint64_t key = ((uint64_t)sbits << 32) | ((uint64_t)slot << 1);
+  uint32_t sh[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) sh[r] = 0;
+  uint32_t rW = 0, rA = 0;
+  for (uint32_t m = am; m; m &= m - 1) {
+    const int j = __ffs((int)m) - 1;
+    const uint64_t ka = __shfl_sync(FULL, key, j);
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      const uint32_t lt = (b.v[r] < ka) ? 1u : 0u;   // keys are distinct (a visited slot is never scored again)
+      c += lt;
+      sh[r] += 1u - lt;
+    }
+    const uint32_t tot = __reduce_add_sync(FULL, c);
+    if ((int)lane == j) rW = tot;
+    if (adm && ka < key) rA++;
+  }
+  const uint32_t old_len = b.len, total = old_len + n_adm, new_len = total < ef ? total : ef;
+  const bool was_full = old_len == ef;
+  const uint32_t old_wmax = wmax;
+  uint32_t q[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    const uint32_t p = (uint32_t)r * 32u + lane;
+    q[r] = p < old_len ? p + sh[r] : HX_ABSENT;
+    if (q[r] < ef) stage[q[r]] = b.v[r];
+  }
+  const uint32_t qc = adm ? rW + rA : HX_ABSENT;
+  if (qc < ef) stage[qc] = key;
+  __syncwarp();
+  if (new_len == ef) wmax = (uint32_t)(stage[ef - 1u] >> 32);
+  if (total > ef) {   // evictions: only a full beam evicts, and it is full now
+    if (was_full && wmax < old_wmax && tie_len) { dropped = 1; tie_len = 0; }
+    bool ev_tie = false, ev_other = false;
+#pragma unroll
+    for (int r = 0; r < NB; ++r)
+      if (q[r] != HX_ABSENT && q[r] >= ef && !(b.v[r] & 1ull)) {
+        if ((uint32_t)(b.v[r] >> 32) == wmax) ev_tie = true; else ev_other = true;
+      }
+    if (qc != HX_ABSENT && qc >= ef) {
+      if (sbits == wmax) ev_tie = true; else ev_other = true;
+    }
+    if (__any_sync(FULL, ev_other)) dropped = 1;
+    if (__any_sync(FULL, ev_tie)) {
+      // rare: exact score ties at the beam boundary; push in eviction order (descending merged rank)
+      for (uint32_t qq = total; qq-- > ef;) {
+        uint64_t mine = HX_KEY_MAX;
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+          if (q[r] == qq) mine = b.v[r];
+        if (qc == qq) mine = key;
+        const uint32_t owner = __ballot_sync(FULL, mine != HX_KEY_MAX);
+        const uint64_t e = __shfl_sync(FULL, mine, owner ? __ffs((int)owner) - 1 : 0);
+        if (!owner || (e & 1ull) || (uint32_t)(e >> 32) != wmax) continue;
+        if (tie_len < HX_TIE_CAP) {
+          if (lane == 0) tie[tie_len] = e;
+          tie_len++;
+        } else {
+          if (lane == 0) atomicOr(err_flags, HXF_TIE_OVERFLOW);
+          dropped = 1;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    const uint32_t p = (uint32_t)r * 32u + lane;
+    b.v[r] = p < new_len ? stage[p] : HX_KEY_MAX;
+  }
+  b.len = new_len;
+  __syncwarp();
+  return am;
+}
+
+// visited set in shared memory (the table of the latency build until it outgrows it): shared-space CAS, no generic path
+__device__ __forceinline__ bool hx_vt_test_and_set_smem(uint32_t tab_s32, uint32_t mask, uint32_t shift, uint32_t key) {
+  uint32_t h = (key * 2654435761u) >> shift;
+  for (;;) {
+    uint32_t old;
+    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(tab_s32 + h * 4u), "r"(HX_VT_EMPTY), "r"(key) : "memory");
+    if (old == HX_VT_EMPTY) return true;
+    if (old == key) return false;
+    h = (h + 1u) & mask;
+  }
+}
+
+// ---- CTA-per-query, ring-staged rows (latency build, B < #SMs) -----------------------------------------------------------
+// One CTA owns the query.  Warp 0 walks the beam — held in its REGISTERS (NB x 32 entries; NB = 0: shared memory, any
+// ef): pops the nearest unexpanded entry, reads its neighbour row (L2: prefetched when the entry was admitted; the row of
+// the entry most likely to be popped next is already loaded while the current frontier is being scored), and
+// tests-and-sets the visited hash set — in SHARED memory, so the visited filter costs no global round trip.  Then every
+// warp w issues the bulk copies of the rows it will reduce (rows w, w+W, ...; one mbarrier per row, the query in
+// registers), reduces them as they land, and warp 0 admits the scores in neighbour-id order.  Bit-identical to every
+// other build.
+#define HX_CTA_RING_MAX_THREADS 384
+template <int METRIC, int QCH, int NB>
+__global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
+    k_hnsw_search_cta_ring(HxDev ix, HxHnswArgs a, HxRingArgs rg, uint32_t RC, uint32_t vt_smem_cap) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* sq = reinterpret_cast<float*>(smem);                                            // [ld] when QCH == 0
+  float* ring = sq + (QCH == 0 ? ix.ld : 0u);                                            // [RC][ld]
+  uint64_t* beam_mem = reinterpret_cast<uint64_t*>(ring + (size_t)RC * ix.ld);          // [ef] beam (NB == 0) / merge stage
+  uint64_t* tie = beam_mem + a.ef;                                                       // [HX_TIE_CAP]
+  uint64_t* bars = tie + HX_TIE_CAP;                                                     // [RC]
+  uint32_t* frontier = reinterpret_cast<uint32_t*>(bars + RC);                           // [fr_cap]
+  float* fdist = reinterpret_cast<float*>(frontier + a.fr_cap);                         // [fr_cap]
+  uint32_t* vts = reinterpret_cast<uint32_t*>(fdist + a.fr_cap);                        // [vt_smem_cap]
+  __shared__ uint32_t s_nf, s_cur, s_done, s_changed;
+  __shared__ float s_cur_dist;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, W = blockDim.x >> 5;
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t rowbytes = ix.ld * 4u;
+  const uint64_t policy = hx_policy_evict_first();
+  uint32_t ph = 0;   // phase parity of every row slot's mbarrier, identical in all threads
+  if (tid < RC) hx_mbar_init(bars + tid, 1);
+  hx_fence_mbar_init();
+  __syncthreads();
+
+  float qr[QCH > 0 ? QCH : 1];
+  const float* qg = nullptr;
+  float q_hdr = 0.f;
+
+  // all threads: reduce list[0..cnt) (shared memory, visible to every warp) into fdist.  Warp w owns slots and rows
+  // w, w+W, ...: it issues their copies itself (lane j -> its j-th row), so a slot is only ever touched by one warp.
+  auto score_list = [&](const uint32_t* list, uint32_t cnt) {
+    for (uint32_t base = 0; base < cnt; base += RC) {
+      const uint32_t rows = min(RC, cnt - base);
+      const uint32_t mine = lane * W + warp;   // the row this lane issues
+      float rh = 0.f;
+      if (mine < rows) {
+        const uint32_t slot = list[base + mine];
+        hx_mbar_expect_tx(bars + mine, rowbytes);
+        if (rg.l2_hint) hx_bulk_g2s_hint(ring + (size_t)mine * ix.ld, ix.vec + (size_t)slot * ix.ld, rowbytes, bars + mine, policy);
+        else hx_bulk_g2s(ring + (size_t)mine * ix.ld, ix.vec + (size_t)slot * ix.ld, rowbytes, bars + mine);
+        if (METRIC == HXM_COSINE) rh = __ldg(ix.hdr + slot);
+      }
+      uint32_t j = 0;
+      for (uint32_t r = warp; r < rows; r += W, ++j) {
+        const float row_hdr = __shfl_sync(FULL, rh, j);
+        hx_mbar_wait(bars + r, (ph >> r) & 1u);
+        const float sc = hx_warp_score<METRIC, QCH>(ring + (size_t)r * ix.ld, qr, sq, qg, q_hdr, row_hdr, ix.dim, lane);
+        if (lane == 0) fdist[base + r] = sc;
+      }
+      ph ^= rows >= 32u ? FULL : ((1u << rows) - 1u);
+      __syncthreads();   // scores visible to warp 0 (and `list` free to be rewritten)
+    }
+  };
+
+  for (uint32_t qi = blockIdx.x; qi < a.B; qi += gridDim.x) {
+    if (a.q_status[qi] != 0u || !ix.populated) {   // uniform per CTA
+      if (tid == 0) a.out_counts[qi] = 0;
+      continue;
+    }
+    q_hdr = a.q_hdr[qi];
+    qg = a.queries + (size_t)qi * ix.dim;
+    if (QCH > 0) {
+#pragma unroll
+      for (int c = 0; c < (QCH > 0 ? QCH : 1); ++c) qr[c] = (uint32_t)(c * 32) + lane < ix.dim ? qg[c * 32 + lane] : 0.f;
+    } else {
+      for (uint32_t i = tid; i < ix.ld; i += blockDim.x) sq[i] = i < ix.dim ? qg[i] : 0.0f;
+    }
+    for (uint32_t i = tid; i < vt_smem_cap; i += blockDim.x) vts[i] = HX_VT_EMPTY;
+    HxVisited vt = hx_vt_make(vts, vt_smem_cap);   // warp 0's copy is the live one
+    const uint32_t vts_s32 = hx_smem_u32(vts);
+    int pool_idx = -1;
+
+    // ---- entry point
+    uint32_t cur = ix.entry_slot;
+    if (tid == 0) frontier[0] = cur;
+    __syncthreads();
+    score_list(frontier, 1);
+    float cur_dist = fdist[0];
+    if (tid == 0 && !hx_score_ok(cur_dist)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+    uint32_t upper_steps = 0;
+    __syncthreads();
+
+    // ---- upper layers: greedy descent (search.rs:169-224)
+    for (int layer = ix.max_layer; layer >= 1; --layer) {
+      for (;;) {
+        uint32_t deg = 0;
+        {
+          const uint32_t off = ix.upper_off[cur];
+          if (off != HX_ABSENT && (int)ix.level[cur] >= layer) {
+            deg = ix.upper_deg[off + (uint32_t)layer - 1u];
+            const uint32_t* row = ix.upper_nbr + (size_t)(off + (uint32_t)layer - 1u) * ix.stride_u;
+            for (uint32_t f = tid; f < deg; f += blockDim.x) frontier[f] = row[f];
+          }
+        }
+        __syncthreads();
+        score_list(frontier, deg);
+        if (warp == 0) {
+          float best = cur_dist;
+          uint32_t best_i = HX_ABSENT;
+          bool bad = false;
+          for (uint32_t base = 0; base < deg; base += 32) {
+            uint32_t f = base + lane;
+            float s = f < deg ? fdist[f] : __int_as_float(0x7f800000);
+            if (f < deg && !hx_score_ok(s)) bad = true;
+            float m = s;
+            uint32_t mi = f;
+            for (int o = 16; o > 0; o >>= 1) {
+              float om = __shfl_xor_sync(FULL, m, o);
+              uint32_t oi = __shfl_xor_sync(FULL, mi, o);
+              if (om < m || (om == m && oi < mi)) { m = om; mi = oi; }
+            }
+            if (m < best) { best = m; best_i = mi; }
+          }
+          if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+          if (lane == 0) {
+            if (best_i != HX_ABSENT) { s_cur = frontier[best_i]; s_cur_dist = best; s_changed = 1u; }
+            else s_changed = 0u;
+          }
+        }
+        __syncthreads();
+        const uint32_t changed = s_changed;
+        if (changed) { cur = s_cur; cur_dist = s_cur_dist; upper_steps++; }
+        __syncthreads();
+        if (!changed) break;
+      }
+    }
+
+    // ---- layer 0 (beam state lives in warp 0)
+    HxBeam beam{beam_mem, 0u};                 // NB == 0
+    HxRegBeam<(NB > 0 ? NB : 1)> rb;           // NB > 0
+#pragma unroll
+    for (int r = 0; r < (NB > 0 ? NB : 1); ++r) rb.v[r] = HX_KEY_MAX;
+    rb.len = 0;
+    uint32_t wmax = 0xffffffffu;               // score bits of the last entry once the beam is full
+    uint32_t tie_len = 0, dropped = 0;
+    uint32_t st_steps = 0, st_examined = 0, st_dc = 1;
+    bool failed = false;
+    // speculative neighbour row: the row of the entry predicted to be popped next, loaded during the scoring phase
+    uint32_t sp_slot = HX_ABSENT, sp_nb = 0, sp_deg = 0, sp_raw = 0;
+    if (warp == 0) {
+      const uint64_t key0 = hx_make_key(cur_dist, cur << 1);
+      if (NB > 0) {
+        hx_rbeam_insert(rb, a.ef, key0, lane);
+        if (rb.len == a.ef) wmax = (uint32_t)(hx_rbeam_get(rb, a.ef - 1u) >> 32);
+      } else {
+        if (lane == 0) beam_mem[0] = key0;
+        beam.len = 1;
+      }
+      if (lane == 0) hx_vt_test_and_set_smem(vts_s32, vt.mask, vt.shift, cur);
+      __syncwarp();
+    }
+    long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0, pt4 = 0, pt5 = 0;
+    unsigned long long pa[6] = {0, 0, 0, 0, 0, 0};
+    const bool prof = rg.prof != nullptr && tid == 0;
+    for (;;) {
+      if (warp == 0) {
+        if (prof) pt0 = clock64();
+        // -- pop the nearest candidate (search.rs:538-551)
+        uint32_t cur_slot = HX_ABSENT;
+        uint32_t first;
+        if (NB > 0) first = hx_rbeam_first_unexpanded(rb);
+        else first = hx_beam_first_unexpanded(beam_mem, beam.len, lane);
+        if (first != HX_ABSENT) {
+          uint64_t key;
+          if (NB > 0) {
+            key = hx_rbeam_get(rb, first);
+#pragma unroll
+            for (int r = 0; r < (NB > 0 ? NB : 1); ++r)
+              if ((uint32_t)r * 32u + lane == first) rb.v[r] |= 1ull;
+          } else {
+            key = beam_mem[first];
+            __syncwarp();
+            if (lane == 0) beam_mem[first] = key | 1ull;
+          }
+          cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
+          st_steps++;
+        } else if (tie_len > 0) {
+          uint64_t key = tie[tie_len - 1];
+          tie_len--;
+          cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
+          st_steps++;
+        } else if (dropped) {
+          st_steps++;
+        }
+        uint32_t nf = 0;
+        if (cur_slot != HX_ABSENT) {
+          const uint32_t* row = ix.nbr0 + (size_t)cur_slot * ix.stride0;
+          if (prof) pt1 = clock64();
+          uint32_t nb, deg, raw;
+          if (cur_slot == sp_slot) {   // predicted: the row is already in registers
+            nb = sp_nb; deg = sp_deg; raw = sp_raw;
+          } else {
+            nb = row[lane];            // stride0 >= 32: in bounds; issued together with the degree
+            deg = ix.deg0[cur_slot];
+            raw = ix.raw0[cur_slot];
+          }
+          st_examined += raw;
+          if (st_dc + deg > vt.limit) {
+            if (pool_idx >= 0 || (pool_idx = hx_vt_grow_warp(vt, rg, lane)) < 0) {
+              if (lane == 0) atomicOr(a.err_flags, HXF_VT_OVERFLOW);
+              failed = true;
+              cur_slot = HX_ABSENT;
+            }
+          }
+          if (prof) { pt2 = clock64(); pa[0] += pt1 - pt0; pa[1] += pt2 - pt1; }
+          if (!failed) {
+            for (uint32_t base = 0; base < deg; base += 32) {
+              const uint32_t i = base + lane;
+              if (base) nb = i < deg ? row[i] : 0u;
+              bool fresh = false;
+              if (i < deg) fresh = pool_idx < 0 ? hx_vt_test_and_set_smem(vts_s32, vt.mask, vt.shift, nb) : hx_vt_test_and_set(vt, nb);
+              const uint32_t mask = __ballot_sync(FULL, fresh);
+              if (fresh) frontier[nf + __popc(mask & ((1u << lane) - 1u))] = nb;
+              nf += __popc(mask);
+            }
+            st_dc += nf;
+            if (prof) { pt3 = clock64(); pa[2] += pt3 - pt2; }
+          }
+        }
+        if (lane == 0) {
+          s_nf = nf;
+          s_done = (cur_slot == HX_ABSENT) ? 1u : 0u;
+        }
+      }
+      __syncthreads();
+      if (s_done) break;
+      const uint32_t nf = s_nf;
+      if (warp == 0) {
+        // predict the next pop: the first unexpanded entry as the beam stands now (right unless a new score beats it)
+        uint32_t pf;
+        if (NB > 0) pf = hx_rbeam_first_unexpanded(rb);
+        else pf = hx_beam_first_unexpanded(beam_mem, beam.len, lane);
+        sp_slot = HX_ABSENT;
+        if (pf != HX_ABSENT) {
+          const uint64_t pk = NB > 0 ? hx_rbeam_get(rb, pf) : beam_mem[pf];
+          sp_slot = (uint32_t)(pk & 0xffffffffu) >> 1;
+          sp_nb = ix.nbr0[(size_t)sp_slot * ix.stride0 + lane];
+          sp_deg = ix.deg0[sp_slot];
+          sp_raw = ix.raw0[sp_slot];
+        }
+      }
+      score_list(frontier, nf);
+      if (prof) { pt4 = clock64(); pa[3] += pt4 - pt3; }
+      // -- admit in neighbour-id order (search.rs:934-953)
+      if (warp == 0) {
+        for (uint32_t base = 0; base < nf; base += 32) {
+          const uint32_t f = base + lane;
+          float s = f < nf ? fdist[f] : 0.f;
+          uint32_t sbits = 0;
+          bool pass = false;
+          const uint32_t blen = NB > 0 ? rb.len : beam.len;
+          if (NB == 0 && blen) wmax = (uint32_t)(beam_mem[blen - 1] >> 32);
+          if (f < nf) {
+            if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+            sbits = __float_as_uint(s);
+            pass = (sbits < wmax) || (blen < a.ef);   // w.max only decreases once full: a fail now is final
+          }
+          uint32_t mask = __ballot_sync(FULL, pass);
+          const uint32_t myslot = f < nf ? frontier[f] : 0u;
+          if (NB > 0 && rg.batch_admit) {
+            const uint32_t am = hx_rbeam_admit_batch(rb, wmax, tie, tie_len, dropped, beam_mem, a.ef, sbits, myslot, f < nf,
+                                                     lane, a.err_flags);
+            if ((am >> lane) & 1u) {   // warm the rows we will need if these candidates are expanded
+              hx_prefetch_l2(ix.nbr0 + (size_t)myslot * ix.stride0);
+              hx_prefetch_l2(ix.deg0 + myslot);
+            }
+            continue;
+          }
+          while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t xb = __shfl_sync(FULL, sbits, src);
+            const uint32_t xslot = __shfl_sync(FULL, myslot, src);
+            const uint32_t len_now = NB > 0 ? rb.len : beam.len;
+            if (NB == 0) wmax = (uint32_t)(beam_mem[len_now - 1] >> 32);
+            if (!((xb < wmax) || (len_now < a.ef))) continue;
+            const uint32_t old_wmax = wmax;
+            const bool was_full = len_now == a.ef;
+            uint64_t ev;
+            const uint64_t nkey = ((uint64_t)xb << 32) | ((uint64_t)xslot << 1);
+            if (NB > 0) {
+              ev = hx_rbeam_insert(rb, a.ef, nkey, lane);
+              if (rb.len == a.ef) wmax = (uint32_t)(hx_rbeam_get(rb, a.ef - 1u) >> 32);
+            } else {
+              hx_beam_insert2(beam, a.ef, nkey, &ev, lane);
+            }
+            if (lane == 0) {   // warm the row we will need if this candidate is expanded
+              hx_prefetch_l2(ix.nbr0 + (size_t)xslot * ix.stride0);
+              hx_prefetch_l2(ix.deg0 + xslot);
+            }
+            if (was_full) {
+              const uint32_t new_wmax = NB > 0 ? wmax : (uint32_t)(beam_mem[beam.len - 1] >> 32);
+              if (new_wmax < old_wmax && tie_len) { dropped = 1; tie_len = 0; }
+              if (!(ev & 1ull)) {   // evicted while still unexpanded
+                if ((uint32_t)(ev >> 32) == new_wmax) {
+                  if (tie_len < HX_TIE_CAP) {
+                    if (lane == 0) tie[tie_len] = ev;
+                    tie_len++;
+                  } else {
+                    if (lane == 0) atomicOr(a.err_flags, HXF_TIE_OVERFLOW);
+                    dropped = 1;
+                  }
+                } else {
+                  dropped = 1;
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      if (prof) { pt5 = clock64(); pa[4] += pt5 - pt4; }
+      // no barrier here: only warp 0 touches the beam; the next barrier orders the reuse of frontier / fdist
+    }
+    if (prof)
+      for (int i = 0; i < 5; ++i) atomicAdd(rg.prof + i, pa[i]);
+
+    // ---- results: the beam is sorted by (score,id); take k (search.rs:994-1004,1229)
+    if (warp == 0) {
+      const uint32_t len = failed ? 0u : (NB > 0 ? rb.len : beam.len);
+      const uint32_t cnt = len < a.k ? len : a.k;
+      if (NB > 0) {
+#pragma unroll
+        for (int r = 0; r < (NB > 0 ? NB : 1); ++r) {
+          const uint32_t p = (uint32_t)r * 32u + lane;
+          if (p < cnt) {
+            a.out_ids[(size_t)qi * a.k + p] = ix.ids[(uint32_t)(rb.v[r] & 0xffffffffu) >> 1];
+            a.out_scores[(size_t)qi * a.k + p] = hx_key_score(rb.v[r]);
+          }
+        }
+      } else {
+        for (uint32_t i = lane; i < cnt; i += 32) {
+          const uint64_t key = beam_mem[i];
+          a.out_ids[(size_t)qi * a.k + i] = ix.ids[(uint32_t)(key & 0xffffffffu) >> 1];
+          a.out_scores[(size_t)qi * a.k + i] = hx_key_score(key);
+        }
+      }
+      if (lane == 0) {
+        a.out_counts[qi] = cnt;
+        if (a.q_stats) {
+          a.q_stats[(size_t)qi * 4 + 0] = st_steps;
+          a.q_stats[(size_t)qi * 4 + 1] = st_examined;
+          a.q_stats[(size_t)qi * 4 + 2] = st_dc;
+          a.q_stats[(size_t)qi * 4 + 3] = upper_steps;
+        }
+        if (pool_idx >= 0) {
+          __threadfence();
+          atomicExch(rg.pool_busy + pool_idx, 0u);
+        }
+      }
+    }
+    __syncthreads();
   }
 }

@@ -350,12 +350,65 @@ def test_traversal_builds_agree(gm, om, dim, monkeypatch):
         assert gs.tobytes() == os_.tobytes(), env
         for f in ("expansion_steps", "neighbors_examined", "distance_computations"):
             assert getattr(st, f) == ost[f], (f, env)
+    # small batches (B < #SMs) take the CTA-per-query builds: ring (visited set in shared memory) vs first generation
+    nsmall = 40
+    for env in [{}, {"HX_LAT_IMPL": "tma"}, {"HX_LAT_IMPL": "ldg"}, {"HX_VT_CAP_LOG2": "6"}, {"HX_RING_R": "3"},
+                {"HX_LAT_WARPS": "3", "HX_L2_HINT": "0"}]:
+        for key in ("HX_HNSW_IMPL", "HX_LAT_IMPL", "HX_VT_CAP_LOG2", "HX_RING_WARPS", "HX_RING_R", "HX_L2_HINT", "HX_LAT_WARPS"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        gi, gs, gc = gpu.search_batch(queries[:nsmall], params)
+        assert gc.tolist() == oc[:nsmall].tolist(), env
+        assert gi.tolist() == oi[:nsmall].tolist(), env
+        assert gs.tobytes() == os_[:nsmall].tobytes(), env
+    monkeypatch.delenv("HX_LAT_WARPS", raising=False)
+    monkeypatch.delenv("HX_L2_HINT", raising=False)
+    # beams wider than 128 entries take the shared-memory beam of the latency build (the register beam holds 4 x 32)
+    wi, ws, wc, _, _ = ora.search_batch(queries[:nsmall], k, 200, threads=4)
+    gi, gs, gc = gpu.search_batch(queries[:nsmall], hx.SearchParams.strict(k, 200))
+    assert gc.tolist() == wc.tolist() and gi.tolist() == wi.tolist() and gs.tobytes() == ws.tobytes()
+    gi, gs, gc = gpu.search_batch(queries[:nsmall], hx.SearchParams.strict(k, 128))
+    wi, ws, wc, _, _ = ora.search_batch(queries[:nsmall], k, 128, threads=4)
+    assert gc.tolist() == wc.tolist() and gi.tolist() == wi.tolist() and gs.tobytes() == ws.tobytes()
     # a pool of zero overflow tables: the overflow is reported, never silently truncated
     monkeypatch.setenv("HX_VT_CAP_LOG2", "6")
     monkeypatch.setenv("HX_VT_POOL", "0")
     with pytest.raises(hx.HelixDbError) as e:
         gpu.search_batch(queries, params)
     assert e.value.variant == "InvariantViolation"
+
+
+# ---- exact score ties at the beam boundary (duplicate vectors): the tie stack / `dropped` bookkeeping decides
+# ---- expansion_steps, so ids, scores AND counters must match for every admission strategy ----------------------------------
+@pytest.mark.parametrize("gm,om", METRICS[:2])
+def test_exact_ties_at_beam_boundary(gm, om, monkeypatch):
+    rng = np.random.default_rng(99)
+    n, dim, nq = 1000, 4, 200
+    rows = rng.integers(0, 5, size=(n, dim)).astype(np.float32) + 1.0      # 625 grid positions: many identical vectors
+    queries = (rng.random((nq, dim)) * 5.0 + 0.5).astype(np.float32)
+    gpu, ora = build_pair(gm, om, rows, m=6, m0=12, efc=40)
+    for ef, k in ((4, 4), (10, 10), (33, 10)):
+        oi, os_, oc, _, _ = ora.search_batch(queries, k, ef, threads=4)
+        per_q = [ora.search(queries[q], k, ef=ef, with_stats=True)[2] for q in range(24)]
+        params = hx.SearchParams.strict(k, ef)
+        for env in ({}, {"HX_LAT_ADMIT": "seq"}, {"HX_LAT_IMPL": "tma"}):
+            for key in ("HX_LAT_ADMIT", "HX_LAT_IMPL"):
+                monkeypatch.delenv(key, raising=False)
+            for key, val in env.items():
+                monkeypatch.setenv(key, val)
+            gi, gs, gc = gpu.search_batch(queries, params)                     # warp-per-query builds
+            assert gc.tolist() == oc.tolist() and gi.tolist() == oi.tolist() and gs.tobytes() == os_.tobytes(), (ef, env)
+            gi, gs, gc = gpu.search_batch(queries[:100], params)               # CTA-per-query builds
+            assert gc.tolist() == oc[:100].tolist() and gi.tolist() == oi[:100].tolist(), (ef, env)
+            assert gs.tobytes() == os_[:100].tobytes(), (ef, env)
+            params.collect_stats = True
+            for q in range(24):
+                st = hx.SearchStats()
+                gpu.search_batch(queries[q:q + 1], params, st)
+                for f in ("expansion_steps", "neighbors_examined", "distance_computations"):
+                    assert getattr(st, f) == per_q[q][f], (f, q, ef, env)
+            params.collect_stats = False
 
 
 # ---- sharded path: per-shard top-k merged by (score, id) equals the unsharded exact answer ---------------------------------------

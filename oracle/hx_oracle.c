@@ -447,6 +447,10 @@ struct hxo_index {
   uint64_t entry_id;
   uint16_t max_layer;
   uint64_t count;
+  /* node fingerprints ([0x12] SimHash rows), allocated by hxo_index_put_simhash */
+  uint64_t* simhash;
+  uint8_t* has_simhash;
+  size_t sim_cap;
 };
 
 static uint64_t mix64(uint64_t x) {
@@ -559,6 +563,8 @@ void hxo_index_free(hxo_index* ix) {
   free(ix->level);
   free(ix->hk);
   free(ix->hv);
+  free(ix->simhash);
+  free(ix->has_simhash);
   free(ix);
 }
 
@@ -1304,6 +1310,516 @@ int hxo_index_import_graph(hxo_index* ix, const uint16_t* levels, const uint32_t
   free(tmp);
   free(rank2slot);
   return hxo_index_set_entry(ix, entry_point, max_layer);
+}
+
+/* ==========================================================================================
+ * Non-exhaustive layer 0: policy, session RNG, SimHash (see hx_oracle.h for what is pinned)
+ * ========================================================================================== */
+void hxo_policy_defaults(hxo_policy_cfg* c) { /* SearchParams::new mod.rs:482-500; config/indexes.rs:398-406 */
+  memset(c, 0, sizeof(*c));
+  c->mode = HXO_SIMHASH_ADAPTIVE;
+  c->threshold = 43;
+  c->sampling_ratio = 0.8f;
+  c->has_pre_override = 0;
+  c->pre_override = 1.0f;
+  c->adaptive_enabled = 1;
+  c->failure_prob = 0.1f;
+  c->bypass_min_frontier = 24;
+  c->bypass_window_expansions = 4;
+  c->bypass_min_filter_rate = 0.12f;
+  c->read_budget_multiplier = 3;
+}
+
+static inline float clampf(float x, float lo, float hi) { /* f32::clamp */
+  if (x < lo) return lo;
+  if (x > hi) return hi;
+  return x;
+}
+static inline float maxf_(float a, float b) { return a > b ? a : b; } /* f32::max for non-NaN operands */
+static inline float minf_(float a, float b) { return a < b ? a : b; }
+static inline uint32_t max_u32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+/* policy.rs:558-574 */
+static float adaptive_sampling_ratio(float base, const hxo_policy_ctx* c) {
+  if (base >= 1.0f) return base;
+  if (c->search_frontier_len < max_u32(c->ef / 3, 8)) return 1.0f;
+  const float current = c->current, delta = c->delta;
+  if (delta <= 1e-6f) return base;
+  const float relative_quality = clampf(1.0f - clampf(current / delta, 0.0f, 1.0f), 0.0f, 1.0f);
+  return minf_(clampf(base + (1.0f - base) * relative_quality, base, 1.0f), maxf_(0.90f, base));
+}
+/* policy.rs:576-597 */
+static uint32_t adaptive_threshold(const hxo_policy_ctx* c, uint32_t configured, float failure) {
+  uint32_t value;
+  if (configured == 0) {
+    value = 0;
+  } else if (!c->topk_ready) {
+    value = 1;
+  } else {
+    const float normalized = clampf(c->delta, 0.0f, 1.0f);
+    const float cosine_similarity = clampf(1.0f - 2.0f * normalized, -1.0f, 1.0f);
+    const float collision = 1.0f - acosf(cosine_similarity) / 3.14159274101257324f; /* std::f32::consts::PI */
+    const float bits = 64.0f;
+    const float margin = sqrtf((bits * logf(1.0f / failure)) / 2.0f);
+    const float t = clampf(floorf(bits * collision - margin), 1.0f, bits);
+    value = (uint32_t)t;
+    if (value > configured) value = configured;
+  }
+  return value;
+}
+/* policy.rs:526-537 */
+static void activate_sampling(int kind, float prob, uint32_t frontier_len, uint32_t ef, int* out_kind, float* out_prob) {
+  if (prob <= 0.0f || prob >= 1.0f || frontier_len > max_u32(ef / 4, 8)) {
+    *out_kind = kind;
+    *out_prob = prob;
+  } else {
+    *out_kind = HXO_SAMPLING_EXHAUSTIVE;
+    *out_prob = 1.0f;
+  }
+}
+/* policy.rs:539-556 */
+static void pre_sampling_decision(float base_ratio, uint32_t frontier_len, uint32_t ef, int* out_kind, float* out_prob) {
+  if (base_ratio >= 1.0f || frontier_len <= max_u32(ef / 4, 8)) {
+    *out_kind = HXO_SAMPLING_EXHAUSTIVE;
+    *out_prob = 1.0f;
+    return;
+  }
+  float ratio = clampf(base_ratio * 0.65f, 0.25f, 0.9f);
+  const uint64_t twice = (uint64_t)ef * 2u;
+  if (base_ratio <= 0.0f) {
+    ratio = 0.0f;
+  } else if ((uint64_t)frontier_len > (twice > 32 ? twice : 32)) {
+    ratio = maxf_(ratio * 0.8f, 0.20f);
+  }
+  *out_kind = HXO_SAMPLING_FIXED;
+  *out_prob = ratio;
+}
+
+void hxo_policy_decide(int metric, const hxo_policy_cfg* cfg, const hxo_policy_ctx* ctx, hxo_policy_decision* d) {
+  memset(d, 0, sizeof(*d));
+  /* --- AdaptiveBypassPolicy::from_deployed + decide (policy.rs:196-291) */
+  int bypassed = 0, next_state = HXO_BYPASS_READY, trigger = HXO_TRIGGER_NONE;
+  uint32_t next_remaining = 0;
+  if (cfg->mode == HXO_SIMHASH_ADAPTIVE) {
+    const uint32_t window = cfg->bypass_window_expansions;
+    uint64_t rb = (uint64_t)ctx->ef * cfg->read_budget_multiplier; /* saturating_mul on usize: no overflow here */
+    if (rb < cfg->bypass_min_frontier) rb = cfg->bypass_min_frontier;
+    int decided = 0;
+    if (ctx->bypass_state == HXO_BYPASS_BYPASSING) {
+      bypassed = 1;
+      if (ctx->bypass_remaining - 1 > 0) {
+        next_state = HXO_BYPASS_BYPASSING;
+        next_remaining = ctx->bypass_remaining - 1;
+      } else {
+        next_state = HXO_BYPASS_COOLING;
+        next_remaining = window;
+      }
+      decided = 1;
+    } else if (ctx->bypass_state == HXO_BYPASS_COOLING && ctx->bypass_remaining > 1) {
+      next_state = HXO_BYPASS_COOLING;
+      next_remaining = ctx->bypass_remaining - 1;
+      decided = 1;
+    }
+    if (!decided) {
+      const int budget_exhausted = ctx->simhash_filter_reads >= rb;
+      const float filter_rate =
+          ctx->window_examined == 0 ? 1.0f : (float)ctx->window_filtered / (float)ctx->window_examined;
+      const int low_yield = ctx->window_expansions >= window && filter_rate < cfg->bypass_min_filter_rate;
+      const int trg = (budget_exhausted ? 1 : 0) | (low_yield ? 2 : 0);
+      if (ctx->candidate_frontier_len < cfg->bypass_min_frontier || trg == HXO_TRIGGER_NONE) {
+        /* inactive(): not bypassed, Ready, None */
+      } else {
+        bypassed = 1;
+        trigger = trg;
+        if (window - 1 > 0) {
+          next_state = HXO_BYPASS_BYPASSING;
+          next_remaining = window - 1;
+        } else {
+          next_state = HXO_BYPASS_COOLING;
+          next_remaining = window;
+        }
+      }
+    }
+  }
+  /* --- Layer0Policy::from_deployed (policy.rs:58-107) */
+  enum { F_DISABLED, F_FIXED, F_ADAPTIVE } filtering = F_DISABLED;
+  if (cfg->mode != HXO_SIMHASH_OFF && metric == HXO_COSINE) {
+    if (cfg->mode == HXO_SIMHASH_ALWAYS) filtering = F_FIXED;
+    else filtering = cfg->adaptive_enabled ? F_ADAPTIVE : F_FIXED;
+  }
+  int base_kind;
+  float base_prob;
+  if (cfg->mode == HXO_SIMHASH_OFF) {
+    base_kind = HXO_SAMPLING_EXHAUSTIVE;
+    base_prob = 1.0f;
+  } else if (cfg->mode == HXO_SIMHASH_ADAPTIVE && cfg->adaptive_enabled) {
+    base_kind = HXO_SAMPLING_ADAPTIVE;
+    base_prob = adaptive_sampling_ratio(cfg->sampling_ratio, ctx);
+  } else {
+    base_kind = HXO_SAMPLING_FIXED;
+    base_prob = cfg->sampling_ratio;
+  }
+  /* --- decide (policy.rs:119-175) */
+  activate_sampling(base_kind, base_prob, ctx->candidate_frontier_len, ctx->ef, &d->samp_kind, &d->samp_prob);
+  d->base_sampling_probability = base_prob;
+  pre_sampling_decision(cfg->has_pre_override ? cfg->pre_override : base_prob, ctx->candidate_frontier_len, ctx->ef,
+                        &d->pre_kind, &d->pre_prob);
+  d->next_state = next_state;
+  d->next_remaining = next_remaining;
+  d->trigger = trigger;
+  if (bypassed) {
+    d->bypassed = 1;
+    return;
+  }
+  if (filtering == F_DISABLED) return;
+  d->fetch_missing = 1;
+  d->filter_cached = 1;
+  d->has_threshold = 1;
+  d->threshold = filtering == F_FIXED ? cfg->threshold : adaptive_threshold(ctx, cfg->threshold, cfg->failure_prob);
+}
+
+float hxo_candidate_probability(const hxo_policy_decision* d, uint32_t similarity_bits) { /* policy.rs:415-430 */
+  const float base = d->samp_kind == HXO_SAMPLING_EXHAUSTIVE ? 1.0f : d->samp_prob;
+  if (d->samp_kind != HXO_SAMPLING_ADAPTIVE) return base;
+  if (base <= 0.0f || base >= 1.0f) return base;
+  const float similarity_ratio = (float)(similarity_bits < 64 ? similarity_bits : 64) / 64.0f;
+  const float threshold_ratio = d->has_threshold ? (float)d->threshold / 64.0f : 0.0f;
+  return clampf(base + (1.0f - base) * maxf_(similarity_ratio - threshold_ratio, 0.0f), base, 1.0f);
+}
+
+/* ---- session RNG: rand 0.10 StdRng = ChaCha12; seed_from_u64 = PCG32 expansion (rand_core) -------- */
+static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+#define HXO_QR(a, b, c, d) \
+  a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); \
+  a += b; d ^= a; d = rotl32(d, 8);  c += d; b ^= c; b = rotl32(b, 7);
+void hxo_chacha_block(const uint32_t key[8], uint64_t counter, uint64_t stream, int rounds, uint32_t out[16]) {
+  uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                     key[4],      key[5],      key[6],      key[7],      (uint32_t)counter, (uint32_t)(counter >> 32),
+                     (uint32_t)stream, (uint32_t)(stream >> 32)};
+  uint32_t x[16];
+  memcpy(x, in, sizeof(x));
+  for (int i = 0; i < rounds / 2; ++i) {
+    HXO_QR(x[0], x[4], x[8], x[12]) HXO_QR(x[1], x[5], x[9], x[13]) HXO_QR(x[2], x[6], x[10], x[14]) HXO_QR(x[3], x[7], x[11], x[15])
+    HXO_QR(x[0], x[5], x[10], x[15]) HXO_QR(x[1], x[6], x[11], x[12]) HXO_QR(x[2], x[7], x[8], x[13]) HXO_QR(x[3], x[4], x[9], x[14])
+  }
+  for (int i = 0; i < 16; ++i) out[i] = x[i] + in[i];
+}
+void hxo_session_seeded(hxo_session* s, uint64_t seed) { /* randomness.rs:122-132: the RNG is built lazily */
+  memset(s, 0, sizeof(*s));
+  s->seed = seed;
+}
+uint64_t hxo_session_seed_for(uint64_t query_simhash, uint64_t entry_point, uint64_t ef) { /* randomness.rs:109-114 */
+  return query_simhash ^ rotl64(entry_point, 17) ^ rotl64(ef, 7);
+}
+static void session_start(hxo_session* s) { /* SeedableRng::seed_from_u64: PCG32 fills the 32-byte key */
+  uint64_t state = s->seed;
+  for (int i = 0; i < 8; ++i) {
+    state = state * 6364136223846793005ull + 11634580027462260723ull;
+    const uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+    const uint32_t rot = (uint32_t)(state >> 59);
+    s->key[i] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31)); /* rotate_right; little-endian words */
+  }
+  s->block = 0;
+  s->pos = 16;
+  s->started = 1;
+}
+uint32_t hxo_session_next_u32(hxo_session* s) {
+  if (!s->started) session_start(s);
+  if (s->pos >= 16) {
+    hxo_chacha_block(s->key, s->block++, 0, 12, s->buf); /* ChaCha12, 64-bit block counter, stream 0 */
+    s->pos = 0;
+  }
+  return s->buf[s->pos++];
+}
+int hxo_session_should_sample(hxo_session* s, float ratio) { /* randomness.rs:141-153 */
+  if (ratio >= 1.0f) return 1;
+  if (ratio <= 0.0f) return 0;
+  const float u = (float)(hxo_session_next_u32(s) >> 8) * (1.0f / 16777216.0f); /* StandardUniform for f32 */
+  return u < ratio;
+}
+int64_t hxo_session_choose_index(hxo_session* s, uint64_t count) { /* randomness.rs:155-158 */
+  if (count == 0) return -1;
+  if (count > 0xffffffffull) { /* UniformUsize falls to u64 sampling above u32::MAX: not reachable (row lengths) */
+    return -1;
+  }
+  const uint32_t range = (uint32_t)count;
+  const uint64_t m = (uint64_t)hxo_session_next_u32(s) * range;
+  uint32_t result = (uint32_t)(m >> 32);
+  const uint32_t lo_order = (uint32_t)m;
+  if (lo_order > (uint32_t)(0u - range)) {
+    const uint32_t new_hi = (uint32_t)(((uint64_t)hxo_session_next_u32(s) * range) >> 32);
+    if ((uint64_t)lo_order + new_hi > 0xffffffffull) result += 1;
+  }
+  return (int64_t)result;
+}
+
+/* ---- SimHash ------------------------------------------------------------------------------------------ */
+uint64_t hxo_simhash_from_planes(const float* planes, const float* v, uint32_t dim) { /* unaligned_vector/simhash.rs:263-290 */
+  uint64_t bits = 0;
+  for (uint32_t p = 0; p < 64; ++p) {
+    float dot = 0.0f;
+    const float* h = planes + (size_t)p * dim;
+    for (uint32_t i = 0; i < dim; ++i) dot += v[i] * h[i]; /* two roundings (-ffp-contract=off) */
+    if (dot > 0.0f) bits |= 1ull << p;
+  }
+  return bits;
+}
+uint32_t hxo_simhash_collision_count(uint64_t a, uint64_t b) { return 64u - (uint32_t)__builtin_popcountll(a ^ b); }
+uint64_t hxo_order_code_from_simhash_bits(uint64_t bits) { /* simhash.rs:44-59 */
+  const uint16_t b0 = (uint16_t)(bits >> 48), b1 = (uint16_t)(bits >> 32), b2 = (uint16_t)(bits >> 16), b3 = (uint16_t)bits;
+  uint64_t code = 0;
+  for (int bit = 15; bit >= 0; --bit) {
+    code = (code << 1) | ((b0 >> bit) & 1u);
+    code = (code << 1) | ((b1 >> bit) & 1u);
+    code = (code << 1) | ((b2 >> bit) & 1u);
+    code = (code << 1) | ((b3 >> bit) & 1u);
+  }
+  return code;
+}
+
+int hxo_index_put_simhash(hxo_index* ix, const uint64_t* ids, const uint64_t* bits, size_t n) {
+  if (ix->sim_cap < ix->cap) {
+    ix->simhash = (uint64_t*)realloc(ix->simhash, ix->cap * sizeof(uint64_t));
+    ix->has_simhash = (uint8_t*)realloc(ix->has_simhash, ix->cap);
+    memset(ix->has_simhash + ix->sim_cap, 0, ix->cap - ix->sim_cap);
+    ix->sim_cap = ix->cap;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t s = slot_of(ix, ids[i]);
+    if (s == UINT32_MAX) return HXO_ERR_INVARIANT_VIOLATION;
+    ix->simhash[s] = bits[i];
+    ix->has_simhash[s] = 1;
+  }
+  return HXO_OK;
+}
+
+/* V/search.rs:267-1067 with STRICT_EXHAUSTIVE = false */
+typedef struct { uint32_t slot; uint32_t sim; } sampled_nb;
+static int layer0_policy(const hxo_index* ix, scratch* sc, const float* q, float q_hdr, uint32_t entry_slot, uint64_t entry_id,
+                         uint32_t k, uint32_t ef, const hxo_policy_cfg* cfg, uint64_t qsim, hxo_stats* st,
+                         hxo_policy_stats* ps) {
+  scratch_begin(sc, ix->n);
+  if (entry_slot == UINT32_MAX || !ix->has_vec[entry_slot]) return HXO_OK;
+  hxo_session session;
+  hxo_session_seeded(&session, hxo_session_seed_for(qsim, entry_id, ef)); /* search.rs:343-348 */
+  heap topk = {0};
+  const uint32_t topk_target = k > 1 ? k : 1;
+  uint64_t window_examined = 0, window_filtered = 0, window_expansions = 0;
+  int bypass_state = HXO_BYPASS_READY;
+  uint32_t bypass_remaining = 0;
+  const uint64_t simhash_filter_reads = 0; /* resident store: memory_store.rs:331-337 */
+  size_t fill = 0;                         /* simhash_fill_slots */
+  int rc = HXO_OK;
+  sampled_nb *sampled = NULL, *deferred = NULL;
+  uint32_t* simfront = NULL;
+  size_t cap = 0;
+
+  float entry_dist = dist_q(ix, q, q_hdr, entry_slot);
+  if (st) st->distance_computations++;
+  rc = hxo_score_validate(&entry_dist);
+  if (rc) return rc;
+  cand e = {entry_dist, entry_slot};
+  heap_push(ix, &sc->cands, 0, e);
+  heap_push(ix, &sc->w, 1, e);
+  heap_push(ix, &topk, 1, e);
+  visited_insert(sc, entry_slot);
+
+  while (sc->cands.n) {
+    if (st) st->expansion_steps++;
+    cand current = heap_pop(ix, &sc->cands, 0);
+    if (sc->w.n + fill >= ef && current.score > sc->w.a[0].score) break; /* :544-551 */
+    uint32_t deg;
+    const uint32_t* nbrs = row_get(ix, 0, current.slot, &deg);
+    if (st) st->neighbors_examined += deg;
+    if (cap < deg + 1) {
+      cap = deg + 64;
+      sc->frontier = (uint32_t*)realloc(sc->frontier, cap * sizeof(uint32_t));
+      sc->frontier_cap = cap;
+      simfront = (uint32_t*)realloc(simfront, cap * sizeof(uint32_t));
+      sampled = (sampled_nb*)realloc(sampled, cap * sizeof(sampled_nb));
+      deferred = (sampled_nb*)realloc(deferred, cap * sizeof(sampled_nb));
+    }
+    uint32_t nf = 0;
+    for (uint32_t i = 0; i < deg; ++i)
+      if (!visited_contains(sc, nbrs[i])) sc->frontier[nf++] = nbrs[i]; /* :583-589 */
+    if (!nf) continue;
+
+    /* :603-637 decision */
+    hxo_policy_ctx ctx;
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.topk_ready = topk.n >= topk_target;
+    ctx.ef = ef;
+    ctx.search_frontier_len = (uint32_t)sc->w.n;
+    ctx.candidate_frontier_len = nf;
+    ctx.current = current.score;
+    ctx.delta = topk.n ? topk.a[0].score : current.score;
+    ctx.bypass_state = bypass_state;
+    ctx.bypass_remaining = bypass_remaining;
+    ctx.simhash_filter_reads = simhash_filter_reads;
+    ctx.window_examined = window_examined;
+    ctx.window_filtered = window_filtered;
+    ctx.window_expansions = window_expansions;
+    hxo_policy_decision dec;
+    hxo_policy_decide(ix->metric, cfg, &ctx, &dec);
+    bypass_state = dec.next_state;
+    bypass_remaining = dec.next_remaining;
+    if (ps) {
+      if (dec.trigger & HXO_TRIGGER_READ_BUDGET) ps->simhash_bypass_trigger_budget++;
+      if (dec.trigger & HXO_TRIGGER_LOW_YIELD) ps->simhash_bypass_trigger_low_yield++;
+    }
+    const float active_sampling_ratio = dec.samp_kind == HXO_SAMPLING_EXHAUSTIVE ? 1.0f : dec.samp_prob;
+    const uint32_t active_threshold = dec.has_threshold ? dec.threshold : 0;
+
+    /* :651-678 stage-0 pre-sampling */
+    uint32_t nsf = 0;
+    const int pre_enabled = dec.pre_kind != HXO_SAMPLING_EXHAUSTIVE;
+    if (pre_enabled) {
+      for (uint32_t i = 0; i < nf; ++i) {
+        if (hxo_session_should_sample(&session, dec.pre_prob)) simfront[nsf++] = sc->frontier[i];
+        else if (ps) ps->pre_simhash_sample_dropped++;
+      }
+      if (nsf == 0) {
+        const int64_t idx = hxo_session_choose_index(&session, nf);
+        if (idx < 0) continue;
+        simfront[nsf++] = sc->frontier[idx];
+      }
+      if (ps) ps->pre_simhash_sample_kept += nsf;
+    } else {
+      memcpy(simfront, sc->frontier, nf * sizeof(uint32_t));
+      nsf = nf;
+    }
+    if (ps && dec.bypassed) { /* :681-685 */
+      ps->simhash_bypass_expansions++;
+      ps->simhash_skipped_candidates += nsf;
+    }
+
+    /* :709-786 threshold gate + sampling */
+    uint32_t ns = 0, nd = 0;
+    const int should_sample = !pre_enabled && dec.samp_kind != HXO_SAMPLING_EXHAUSTIVE && active_sampling_ratio > 0.0f;
+    uint64_t examined_round = 0, filtered_round = 0;
+    for (uint32_t i = 0; i < nsf; ++i) {
+      const uint32_t nb = simfront[i];
+      const int has_hash = dec.filter_cached && ix->has_simhash && ix->has_simhash[nb];
+      if (has_hash) {
+        examined_round++;
+        if (ps) ps->simhash_examined++;
+        if (hxo_simhash_collision_count(ix->simhash[nb], qsim) < active_threshold) { /* !passes_threshold */
+          if (ps) ps->simhash_filtered++;
+          filtered_round++;
+          if (visited_insert(sc, nb) && sc->w.n + fill < ef) fill++; /* :742-748 */
+          continue;
+        }
+      } else if (ps && dec.fetch_missing) {
+        ps->simhash_missing_hash++;
+      }
+      if (ps) ps->simhash_passed_before_sampling++;
+      const uint32_t similarity_bits = has_hash ? hxo_simhash_collision_count(ix->simhash[nb], qsim) : 32u; /* 64 - hamming */
+      if (should_sample) {
+        const float p = hxo_candidate_probability(&dec, similarity_bits);
+        if (hxo_session_should_sample(&session, p)) sampled[ns++] = (sampled_nb){nb, similarity_bits};
+        else deferred[nd++] = (sampled_nb){nb, similarity_bits};
+      } else if (active_sampling_ratio <= 0.0f) {
+        deferred[nd++] = (sampled_nb){nb, similarity_bits};
+      } else {
+        sampled[ns++] = (sampled_nb){nb, similarity_bits};
+      }
+    }
+    if (dec.filter_cached && examined_round > 0) { /* :788-800 */
+      window_examined += examined_round;
+      window_filtered += filtered_round;
+      window_expansions += 1;
+      if (window_expansions > cfg->bypass_window_expansions) {
+        window_examined /= 2;
+        window_filtered /= 2;
+        window_expansions = cfg->bypass_window_expansions / 2;
+      }
+    }
+    if (active_sampling_ratio > 0.0f && ns == 0 && nd > 0) { /* :802-823 */
+      uint32_t best = 0;
+      for (uint32_t i = 0; i < nd; ++i)
+        if (deferred[i].sim > best) best = deferred[i].sim;
+      uint32_t nbest = 0;
+      for (uint32_t i = 0; i < nd; ++i)
+        if (deferred[i].sim == best) nbest++;
+      const int64_t idx = hxo_session_choose_index(&session, nbest);
+      if (idx < 0) continue;
+      uint32_t seen = 0;
+      for (uint32_t i = 0; i < nd; ++i)
+        if (deferred[i].sim == best && seen++ == (uint32_t)idx) { /* swap_remove(idx) returns element idx */
+          sampled[ns++] = deferred[i];
+          break;
+        }
+    }
+    if (ps) ps->simhash_passed_after_sampling += ns;
+
+    /* :830-953 mark visited, score, admit */
+    for (uint32_t i = 0; i < ns; ++i) {
+      const uint32_t nb = sampled[i].slot;
+      if (!visited_insert(sc, nb)) continue; /* mark_sampled_neighbors_visited */
+      if (!ix->has_vec[nb]) continue;
+      if (st) st->vectors_loaded++;
+      float d = dist_q(ix, q, q_hdr, nb);
+      if (st) st->distance_computations++;
+      rc = hxo_score_validate(&d);
+      if (rc) goto done;
+      if (d < sc->w.a[0].score || sc->w.n + fill < ef) { /* :927-928 */
+        cand c = {d, nb};
+        heap_push(ix, &sc->cands, 0, c);
+        heap_push(ix, &sc->w, 1, c);
+        heap_push(ix, &topk, 1, c);
+        if (topk.n > topk_target) heap_pop(ix, &topk, 1);
+        while (sc->w.n + fill > ef) { /* :940-951 */
+          if (fill > 0) fill--;
+          else if (sc->w.n > ef) heap_pop(ix, &sc->w, 1);
+          else break;
+        }
+      }
+    }
+  }
+done:
+  if (ps) ps->rng_draws = session.started ? session.block * 16 - (16 - session.pos) : 0;
+  free(topk.a);
+  free(sampled);
+  free(deferred);
+  free(simfront);
+  return rc;
+}
+
+int hxo_search_policy(const hxo_index* ix, const float* query, uint32_t query_dim, uint32_t k, uint32_t ef,
+                      const hxo_policy_cfg* cfg, uint64_t qsim, uint64_t* out_ids, float* out_scores, uint32_t* out_count,
+                      hxo_stats* st, hxo_policy_stats* ps) {
+  scratch* sc = &tls_scratch;
+  if (st) memset(st, 0, sizeof(*st));
+  if (ps) memset(ps, 0, sizeof(*ps));
+  *out_count = 0;
+  if (k == 0) return HXO_ERR_INVALID_PARAMETER;
+  if (ef == 0) ef = k > 100 ? k : 100;
+  if (ef < k) return HXO_ERR_INVALID_PARAMETER;
+  uint32_t bad;
+  int rc = hxo_validate_vector(ix->metric, ix->dim, query, query_dim, &bad);
+  if (rc) return rc;
+  if (!ix->populated) return HXO_OK;
+  const float qh = hxo_header(ix->metric, query, ix->dim);
+  uint32_t entry = slot_of(ix, ix->entry_id);
+  for (int layer = ix->max_layer; layer >= 1; --layer) {
+    if (entry == UINT32_MAX) break;
+    rc = greedy_slot(ix, sc, query, qh, entry, (uint16_t)layer, &entry, st);
+    if (rc) return rc;
+  }
+  /* requires_query_simhash() false (Off, no pre-sampling override < 1) is the strict-exhaustive specialisation */
+  const int strict = cfg->mode == HXO_SIMHASH_OFF && !(cfg->has_pre_override && cfg->pre_override < 1.0f);
+  if (strict) rc = layer0_strict(ix, sc, query, qh, entry, ef, st);
+  else rc = layer0_policy(ix, sc, query, qh, entry, entry == UINT32_MAX ? 0 : ix->ids[entry], k, ef, cfg, qsim, st, ps);
+  if (rc) return rc;
+  qsort_r(sc->w.a, sc->w.n, sizeof(cand), cmp_cand_ctx, (void*)ix);
+  const uint32_t n = sc->w.n < k ? (uint32_t)sc->w.n : k;
+  for (uint32_t i = 0; i < n; ++i) {
+    out_ids[i] = ix->ids[sc->w.a[i].slot];
+    out_scores[i] = sc->w.a[i].score;
+  }
+  *out_count = n;
+  return HXO_OK;
 }
 
 /* ------------------------------------------------------------------------------------------

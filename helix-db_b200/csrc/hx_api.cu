@@ -14,6 +14,7 @@
 #include "hx_index.hpp"
 #include "k_hnsw.cuh"
 #include "k_hnsw_ring.cuh"
+#include "k_hnsw_policy.cuh"
 #include "k_scan.cuh"
 #include "k_util.cuh"
 
@@ -145,6 +146,9 @@ void hx_index::free_vectors() {
   if (d_ids) cudaFree(d_ids);
   if (d_vec_bf16) cudaFree(d_vec_bf16);
   if (d_sqnorm) cudaFree(d_sqnorm);
+  if (d_simhash) cudaFree(d_simhash);
+  if (d_has_simhash) cudaFree(d_has_simhash);
+  d_simhash = nullptr; d_has_simhash = nullptr; simhash_count = 0;
   d_vec = nullptr; d_hdr = nullptr; d_ids = nullptr; d_vec_bf16 = nullptr; d_sqnorm = nullptr;
   n = 0;
   ids_sorted.clear();
@@ -198,7 +202,7 @@ void HxScratch::destroy() {
   d_qstatus.release(); d_out_counts.release(); d_qstats.release(); d_err.release(); d_epochs.release();
   d_cand_slots.release(); d_out_ids.release(); d_cand_ids.release(); d_cand_offsets.release(); d_keys.release();
   d_stamps.release();
-  d_vtab.release(); d_vpool.release(); d_vbusy.release();
+  d_vtab.release(); d_vpool.release(); d_vbusy.release(); d_prof.release(); d_pstats.release(); d_qsim.release();
   for (auto& m : misc) m.release();
   h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
   h_counts.release(); h_qstats.release(); h_status.release(); h_err.release();
@@ -323,6 +327,7 @@ extern "C" void hx_index_destroy(hx_index* ix) {
   }
   ix->free_graph();
   ix->free_vectors();
+  if (ix->d_planes_t) cudaFree(ix->d_planes_t);
   delete ix;
 }
 
@@ -979,6 +984,10 @@ extern "C" hx_status hx_index_download_graph(hx_index* ix, uint16_t* levels, uin
 // ------------------------------------------------------------------------------------------------
 // search parameter checks (SearchParams::new / with_ef, mod.rs:480-500)
 // ------------------------------------------------------------------------------------------------
+static inline bool params_strict(const hx_search_params* p) {   // !requires_query_simhash() (mod.rs:556-561)
+  return p->simhash_mode == HX_SIMHASH_OFF && !(p->pre_sampling_ratio >= 0.0f && p->pre_sampling_ratio < 1.0f);
+}
+
 static hx_status check_params(const hx_index* ix, const hx_search_params* p, uint32_t* k, uint32_t* ef) {
   if (!p) {
     hx_set_error("null search params");
@@ -993,10 +1002,13 @@ static hx_status check_params(const hx_index* ix, const hx_search_params* p, uin
     hx_set_error("search beam width must be at least %u, got %u", p->k, e);   // SearchBeamWidth::try_new
     return HX_ERR_INVALID_PARAMETER;
   }
-  if (p->simhash_mode != HX_SIMHASH_OFF || p->pre_sampling_ratio != 1.0f) {
-    hx_set_error("only the strict-exhaustive mode (SimHashMode::Off, pre-sampling 1.0) is executed on the device; "
-                 "Adaptive/Always sampling is unpinned in the reference (SURVEY §8c)");
-    return HX_ERR_UNSUPPORTED;
+  if (p->simhash_mode < HX_SIMHASH_OFF || p->simhash_mode > HX_SIMHASH_ALWAYS) {
+    hx_set_error("unknown SimHash mode %d", p->simhash_mode);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (p->pre_sampling_ratio > 1.0f || p->pre_sampling_ratio != p->pre_sampling_ratio) {
+    hx_set_error("pre-SimHash sampling ratio must lie in the unit interval");   // UnitInterval::try_new
+    return HX_ERR_INVALID_PARAMETER;
   }
   if (p->query_dimension != 0 && p->query_dimension != ix->cfg.dimension) {
     hx_set_error("invalid dimension: expected %u, got %u", ix->cfg.dimension, p->query_dimension);
@@ -1350,8 +1362,18 @@ static hx_status check_device_flags(uint32_t flags) {
   return HX_OK;
 }
 
+static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                  uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats);
+
 extern "C" hx_status hx_search(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
                                uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+  if (p && !(p->simhash_mode == HX_SIMHASH_OFF && !(p->pre_sampling_ratio >= 0.0f && p->pre_sampling_ratio < 1.0f)))
+    return hx_search_ex(ix, queries, B, p, nullptr, nullptr, out_ids, out_scores, out_counts, stats, nullptr);
+  return hx_search_strict(ix, queries, B, p, out_ids, out_scores, out_counts, stats);
+}
+
+static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                  uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats) {
   if (!ix) {
     hx_set_error("null index handle");
     return HX_ERR_INDEX_NOT_FOUND;
@@ -1428,6 +1450,10 @@ extern "C" hx_status hx_search_device(hx_index* ix, const float* d_queries, size
   if (stats) memset(stats, 0, sizeof(*stats));
   if (B == 0) return HX_OK;
   if (!d_queries || !d_out_ids || !d_out_scores || !d_out_counts) return HX_ERR_INVALID_PARAMETER;
+  if (!params_strict(p)) {
+    hx_set_error("the device-buffer entry point executes the strict-exhaustive specialisation only; use hx_search_ex");
+    return HX_ERR_UNSUPPORTED;
+  }
   HX_CUDA(cudaSetDevice(ix->device));
   HxScratch* s = nullptr;
   if ((rc = dev_scratch(ix, &s))) return rc;
@@ -1731,6 +1757,362 @@ extern "C" hx_status hx_search_dense(hx_index* ix, const float* queries, size_t 
   if (!ix) return HX_ERR_INDEX_NOT_FOUND;
   HX_CUDA(cudaSetDevice(ix->device));
   return hx_dense_impl(ix, queries, B, p, out_ids, out_scores, out_counts, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SimHash policy mode (search.rs:595-992, policy.rs) — the production-default SearchParams
+// ------------------------------------------------------------------------------------------------
+extern "C" void hx_policy_params_default(hx_policy_params* p) {   // SearchParams::new (mod.rs:482-500)
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->bypass_min_frontier = 24;
+  p->bypass_window_expansions = 4;
+  p->bypass_min_filter_rate = 0.12f;
+  p->read_budget_multiplier = 3;
+  p->sampling_ratio_override = -1.0f;
+  p->failure_prob_override = -1.0f;
+}
+
+extern "C" uint64_t hx_order_code_from_simhash_bits(uint64_t bits) {   // simhash.rs:44-59
+  const uint16_t b0 = (uint16_t)(bits >> 48), b1 = (uint16_t)(bits >> 32), b2 = (uint16_t)(bits >> 16), b3 = (uint16_t)bits;
+  uint64_t code = 0;
+  for (int bit = 15; bit >= 0; --bit) {
+    code = (code << 1) | ((b0 >> bit) & 1u);
+    code = (code << 1) | ((b1 >> bit) & 1u);
+    code = (code << 1) | ((b2 >> bit) & 1u);
+    code = (code << 1) | ((b3 >> bit) & 1u);
+  }
+  return code;
+}
+
+extern "C" hx_status hx_index_set_simhash_config(hx_index* ix, const hx_simhash_config* cfg) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (!cfg || cfg->simhash_threshold > 64 || !(cfg->sampling_ratio >= 0.0f && cfg->sampling_ratio <= 1.0f) ||
+      !(cfg->adaptive_failure_prob > 0.0f && cfg->adaptive_failure_prob < 1.0f)) {
+    hx_set_error("invalid SimHash configuration");   // CollisionThreshold / UnitInterval / FailureProbability::try_new
+    return HX_ERR_INVALID_VECTOR_CONFIG;
+  }
+  ix->simcfg = *cfg;
+  return HX_OK;
+}
+
+static hx_status ensure_simhash_arrays(hx_index* ix) {
+  if (ix->n == 0) {
+    hx_set_error("no vectors loaded");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (!ix->d_simhash) {
+    HX_CUDA(cudaMalloc((void**)&ix->d_simhash, ix->n * sizeof(uint64_t)));
+    HX_CUDA(cudaMalloc((void**)&ix->d_has_simhash, ix->n));
+    HX_CUDA(cudaMemset(ix->d_simhash, 0, ix->n * sizeof(uint64_t)));
+    HX_CUDA(cudaMemset(ix->d_has_simhash, 0, ix->n));
+    ix->simhash_count = 0;
+  }
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_load_simhash(hx_index* ix, const uint64_t* ids, const uint64_t* bits, size_t n) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (n && (!ids || !bits)) return HX_ERR_INVALID_PARAMETER;
+  HX_CUDA(cudaSetDevice(ix->device));
+  hx_status rc = ensure_simhash_arrays(ix);
+  if (rc) return rc;
+  std::vector<uint64_t> h(ix->n);
+  std::vector<uint8_t> has(ix->n);
+  HX_CUDA(cudaMemcpy(h.data(), ix->d_simhash, ix->n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  HX_CUDA(cudaMemcpy(has.data(), ix->d_has_simhash, ix->n, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t slot;
+    if (!hx_slot_of(ix, ids[i], &slot)) {
+      hx_set_error("SimHash row for node %llu which has no vector row", (unsigned long long)ids[i]);
+      return HX_ERR_INVARIANT_VIOLATION;
+    }
+    h[slot] = bits[i];
+    has[slot] = 1;
+  }
+  HX_CUDA(cudaMemcpy(ix->d_simhash, h.data(), ix->n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  HX_CUDA(cudaMemcpy(ix->d_has_simhash, has.data(), ix->n, cudaMemcpyHostToDevice));
+  size_t c = 0;
+  for (uint8_t b : has) c += b;
+  ix->simhash_count = c;
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_set_simhash_planes(hx_index* ix, const float* planes) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (!planes) return HX_ERR_INVALID_PARAMETER;
+  HX_CUDA(cudaSetDevice(ix->device));
+  const uint32_t dim = ix->cfg.dimension;
+  std::vector<float> t((size_t)dim * 64);
+  for (uint32_t p = 0; p < 64; ++p)
+    for (uint32_t i = 0; i < dim; ++i) t[(size_t)i * 64 + p] = planes[(size_t)p * dim + i];
+  if (!ix->d_planes_t) HX_CUDA(cudaMalloc((void**)&ix->d_planes_t, t.size() * sizeof(float)));
+  HX_CUDA(cudaMemcpy(ix->d_planes_t, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return HX_OK;
+}
+
+// SimHasher::hash_from_slice (unaligned_vector/simhash.rs:263-290): thread (row, plane) walks the row sequentially,
+// `dot += value * plane` with two roundings; bit = dot > 0.  64 threads per row, planes transposed so a warp reads
+// 32 consecutive plane values per element and the row element is a broadcast.
+__global__ void k_simhash_project(const float* __restrict__ rows, size_t n, uint32_t dim, uint32_t ld,
+                                  const float* __restrict__ planes_t, uint64_t* __restrict__ out, uint8_t* has) {
+  const size_t row = (size_t)blockIdx.x * (blockDim.x / 64) + threadIdx.x / 64;
+  const uint32_t p = threadIdx.x & 63u;
+  if (row >= n) return;
+  const float* v = rows + row * ld;
+  float dot = 0.0f;
+  for (uint32_t i = 0; i < dim; ++i) dot = __fadd_rn(dot, __fmul_rn(v[i], planes_t[(size_t)i * 64 + p]));
+  const uint32_t m = __ballot_sync(0xffffffffu, dot > 0.0f);
+  // the two warps of a row combine through shared memory
+  __shared__ uint32_t halves[8][2];
+  const uint32_t r_in_blk = threadIdx.x / 64;
+  if ((threadIdx.x & 31u) == 0) halves[r_in_blk][(threadIdx.x >> 5) & 1u] = m;
+  __syncthreads();
+  if (p == 0) {
+    out[row] = ((uint64_t)halves[r_in_blk][1] << 32) | halves[r_in_blk][0];
+    if (has) has[row] = 1;
+  }
+}
+
+extern "C" hx_status hx_index_compute_simhash(hx_index* ix) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  HX_CUDA(cudaSetDevice(ix->device));
+  if (!ix->d_planes_t) {
+    hx_set_error("SimHash hyperplanes not set (hx_index_set_simhash_planes)");
+    return HX_ERR_INVALID_VECTOR_CONFIG;
+  }
+  hx_status rc = ensure_simhash_arrays(ix);
+  if (rc) return rc;
+  const unsigned blocks = (unsigned)((ix->n + 7) / 8);
+  k_simhash_project<<<blocks, 512>>>(ix->d_vec, ix->n, ix->cfg.dimension, ix->ld, ix->d_planes_t, ix->d_simhash, ix->d_has_simhash);
+  HX_CUDA(cudaGetLastError());
+  HX_CUDA(cudaDeviceSynchronize());
+  ix->simhash_count = ix->n;
+  return HX_OK;
+}
+
+extern "C" hx_status hx_index_download_simhash(hx_index* ix, size_t first_slot, size_t n, uint64_t* out_bits) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (!ix->d_simhash || first_slot + n > ix->n || !out_bits) return HX_ERR_INVALID_PARAMETER;
+  HX_CUDA(cudaSetDevice(ix->device));
+  HX_CUDA(cudaMemcpy(out_bits, ix->d_simhash + first_slot, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return HX_OK;
+}
+
+static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_queries, size_t B, uint32_t k, uint32_t ef,
+                               const hx_search_params* p, const hx_policy_params* pol, const uint64_t* d_qsim,
+                               uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts, uint32_t* d_qstats,
+                               cudaStream_t stream, uint32_t* launches) {
+  hx_status rc = hx_finalize_graph(ix);
+  if (rc) return rc;
+  if (ix->n == 0 || !ix->populated || !ix->d_nbr0) {
+    HX_CUDA(cudaMemsetAsync(d_out_counts, 0, B * sizeof(uint32_t), stream));
+    if (d_qstats) HX_CUDA(cudaMemsetAsync(d_qstats, 0, B * 4 * sizeof(uint32_t), stream));
+    return HX_OK;
+  }
+  const uint32_t fr_cap = round_up(std::max(ix->stride0, ix->stride_u), 32);
+  const size_t rowbytes = (size_t)ix->ld * 4;
+  const size_t fixed0 = rowbytes + (size_t)ef * 8 + (size_t)k * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 13 + 28 * 4 + 16;
+  const size_t budget = 227 * 1024;
+  uint32_t wpc = 0, R = 0;
+  const uint32_t spread = (uint32_t)std::max<size_t>(1, (B + ix->sm_count - 1) / (size_t)ix->sm_count);
+  for (uint32_t w = std::min(16u, spread); w >= 1; --w) {
+    const size_t per_warp = (budget / w) & ~(size_t)127;
+    if (per_warp <= fixed0 + 8 + rowbytes) continue;
+    const uint32_t r = (uint32_t)std::min<size_t>(32, (per_warp - fixed0) / (rowbytes + 8));
+    if (r >= 4 || w == 1) { wpc = w; R = r; break; }
+  }
+  if (R == 0) {
+    hx_set_error("query working set exceeds shared memory (dimension %u, ef %u)", ix->cfg.dimension, ef);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  const uint32_t wstride = round_up((uint32_t)(fixed0 + (size_t)R * (rowbytes + 8)), 128);
+  uint32_t lg = 12;
+  while ((1u << lg) < 64u * ef && lg < 24) lg++;
+  if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) lg = (uint32_t)v; }
+  const uint32_t vt_cap = 1u << lg;
+  const uint32_t grid = (uint32_t)std::min<size_t>((B + wpc - 1) / wpc, (size_t)ix->sm_count);
+  const size_t vslots = (size_t)grid * wpc;
+  uint32_t pool_n = 32;
+  if (const char* env = getenv("HX_VT_POOL")) { const int v = atoi(env); if (v >= 0 && v <= 1024) pool_n = (uint32_t)v; }
+  const uint32_t pool_cap = std::max<uint32_t>(vt_cap * 16u, 65536u);
+  if ((rc = s->d_vtab.reserve(vslots * vt_cap))) return rc;
+  if (s->vpool_n != pool_n || s->vpool_cap != pool_cap || !s->d_vbusy.p) {
+    if ((rc = s->d_vpool.reserve((size_t)std::max(pool_n, 1u) * pool_cap))) return rc;
+    if ((rc = s->d_vbusy.reserve(std::max(pool_n, 1u)))) return rc;
+    HX_CUDA(cudaMemsetAsync(s->d_vbusy.p, 0, std::max(pool_n, 1u) * sizeof(uint32_t), stream));
+    s->vpool_n = pool_n;
+    s->vpool_cap = pool_cap;
+  }
+  if ((rc = s->d_err.reserve(2))) return rc;
+  HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, 2 * sizeof(uint32_t), stream));
+  if ((rc = s->d_pstats.reserve(12))) return rc;
+  HX_CUDA(cudaMemsetAsync(s->d_pstats.p, 0, 12 * sizeof(unsigned long long), stream));
+  HxRingArgs rg{};
+  rg.vtab = s->d_vtab.p;
+  rg.vt_cap = vt_cap;
+  rg.pool = s->d_vpool.p;
+  rg.pool_busy = s->d_vbusy.p;
+  rg.pool_n = pool_n;
+  rg.pool_cap = pool_cap;
+  rg.counter = s->d_err.p + 1;
+  rg.l2_hint = 1;
+  HxHnswArgs a{};
+  a.queries = d_queries;
+  a.q_hdr = s->d_qhdr.p;
+  a.q_status = s->d_qstatus.p;
+  a.B = (uint32_t)B;
+  a.k = k;
+  a.ef = ef;
+  a.out_ids = d_out_ids;
+  a.out_scores = d_out_scores;
+  a.out_counts = d_out_counts;
+  a.q_stats = d_qstats;
+  a.err_flags = s->d_err.p;
+  a.fr_cap = fr_cap;
+  HxPolicyArgs pa{};
+  pa.cfg.mode = p->simhash_mode;
+  pa.cfg.threshold = ix->simcfg.simhash_threshold;
+  pa.cfg.sampling_ratio = pol->sampling_ratio_override >= 0.0f ? pol->sampling_ratio_override : ix->simcfg.sampling_ratio;
+  pa.cfg.has_pre_override = p->pre_sampling_ratio >= 0.0f ? 1 : 0;
+  pa.cfg.pre_override = p->pre_sampling_ratio >= 0.0f ? p->pre_sampling_ratio : 1.0f;
+  pa.cfg.adaptive_enabled = ix->simcfg.adaptive_enabled ? 1 : 0;
+  pa.cfg.failure_prob = pol->failure_prob_override >= 0.0f ? pol->failure_prob_override : ix->simcfg.adaptive_failure_prob;
+  pa.cfg.bypass_min_frontier = pol->bypass_min_frontier;
+  pa.cfg.bypass_window_expansions = pol->bypass_window_expansions;
+  pa.cfg.bypass_min_filter_rate = pol->bypass_min_filter_rate;
+  pa.cfg.read_budget_multiplier = pol->read_budget_multiplier;
+  pa.node_simhash = ix->d_simhash;
+  pa.node_has_simhash = ix->d_has_simhash;
+  pa.query_simhash = d_qsim;
+  pa.pstats = s->d_pstats.p;
+  const HxDev dev = ix->dev();
+  const size_t smem_launch = (size_t)wpc * wstride;
+#define HX_LAUNCH_POLICY(M)                                                                                        \
+  do {                                                                                                             \
+    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_policy<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                 (int)smem_launch));                                                               \
+    k_hnsw_search_policy<M><<<grid, wpc * 32, smem_launch, stream>>>(dev, a, rg, pa, wstride, R);                  \
+  } while (0)
+  switch (ix->cfg.metric) {
+    case HX_METRIC_EUCLIDEAN: HX_LAUNCH_POLICY(HXM_EUCLIDEAN); break;
+    case HX_METRIC_COSINE: HX_LAUNCH_POLICY(HXM_COSINE); break;
+    default: HX_LAUNCH_POLICY(HXM_MANHATTAN); break;
+  }
+#undef HX_LAUNCH_POLICY
+  HX_CUDA(cudaGetLastError());
+  (*launches)++;
+  return HX_OK;
+}
+
+extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                  const hx_policy_params* policy, const uint64_t* query_simhash, uint64_t* out_ids,
+                                  float* out_scores, uint32_t* out_counts, hx_stats* stats, hx_policy_stats* pstats) {
+  if (!ix) {
+    hx_set_error("null index handle");
+    return HX_ERR_INDEX_NOT_FOUND;
+  }
+  uint32_t k, ef;
+  hx_status rc = check_params(ix, p, &k, &ef);
+  if (rc) return rc;
+  if (pstats) memset(pstats, 0, sizeof(*pstats));
+  if (params_strict(p)) {   // the exhaustive specialisation never looks at fingerprints or the policy
+    hx_search_params q = *p;
+    q.simhash_mode = HX_SIMHASH_OFF;
+    q.pre_sampling_ratio = 1.0f;
+    return hx_search_strict(ix, queries, B, &q, out_ids, out_scores, out_counts, stats);
+  }
+  hx_policy_params pol;
+  hx_policy_params_default(&pol);
+  if (policy) pol = *policy;
+  if (pol.bypass_min_frontier == 0 || pol.bypass_window_expansions == 0 || pol.read_budget_multiplier == 0 ||
+      !(pol.bypass_min_filter_rate >= 0.0f && pol.bypass_min_filter_rate <= 1.0f) || pol.sampling_ratio_override > 1.0f ||
+      pol.failure_prob_override >= 1.0f || pol.failure_prob_override == 0.0f) {
+    hx_set_error("invalid SimHash policy parameters");   // VectorParameterError (mod.rs:563-600)
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return HX_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts) {
+    hx_set_error("hx_search_ex: null pointer");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  HX_CUDA(cudaSetDevice(ix->device));
+  // filtering needs the node fingerprints (cosine only, policy.rs:67-88); sampling needs the query's for its seed
+  const bool filtering = ix->cfg.metric == HX_METRIC_COSINE && p->simhash_mode != HX_SIMHASH_OFF;
+  if (filtering && ix->n && !ix->d_simhash) {
+    hx_set_error("SimHash rows not loaded: call hx_index_load_simhash or hx_index_compute_simhash before a filtered search");
+    return HX_ERR_INVALID_VECTOR_CONFIG;
+  }
+  if (!query_simhash && !ix->d_planes_t) {
+    hx_set_error("no query fingerprints given and no hyperplanes set (hx_index_set_simhash_planes)");
+    return HX_ERR_INVALID_VECTOR_CONFIG;
+  }
+  HxScratch* s = nullptr;
+  if ((rc = hx_acquire_scratch(ix, &s))) return rc;
+  ScratchGuard guard{ix, s};
+  uint32_t launches = 0;
+  if ((rc = stage_queries(ix, s, queries, B, &launches))) return rc;
+  if ((rc = s->d_out_ids.reserve(B * (size_t)k))) return rc;
+  if ((rc = s->d_out_scores.reserve(B * (size_t)k))) return rc;
+  if ((rc = s->d_out_counts.reserve(B))) return rc;
+  if ((rc = s->d_qsim.reserve(B))) return rc;
+  if (query_simhash) {
+    HX_CUDA(cudaMemcpyAsync(s->d_qsim.p, query_simhash, B * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  } else {
+    k_simhash_project<<<(unsigned)((B + 7) / 8), 512, 0, s->stream>>>(s->d_queries.p, B, ix->cfg.dimension, ix->cfg.dimension,
+                                                                     ix->d_planes_t, s->d_qsim.p, nullptr);
+    HX_CUDA(cudaGetLastError());
+    launches++;
+  }
+  const bool want_stats = p->collect_stats != 0 && stats != nullptr;
+  if (want_stats && (rc = s->d_qstats.reserve(B * 4))) return rc;
+  HX_CUDA(cudaEventRecord(s->ev0, s->stream));
+  if ((rc = launch_policy(ix, s, s->d_queries.p, B, k, ef, p, &pol, s->d_qsim.p, s->d_out_ids.p, s->d_out_scores.p,
+                          s->d_out_counts.p, want_stats ? s->d_qstats.p : nullptr, s->stream, &launches)))
+    return rc;
+  HX_CUDA(cudaEventRecord(s->ev1, s->stream));
+  if ((rc = s->h_status.reserve(B))) return rc;
+  if ((rc = s->h_err.reserve(1))) return rc;
+  s->h_err.p[0] = 0;
+  HX_CUDA(cudaMemcpyAsync(out_ids, s->d_out_ids.p, B * (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_scores, s->d_out_scores.p, B * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_counts, s->d_out_counts.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(s->h_status.p, s->d_qstatus.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (s->d_err.p) HX_CUDA(cudaMemcpyAsync(s->h_err.p, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (want_stats) {
+    if ((rc = s->h_qstats.reserve(B * 4))) return rc;
+    HX_CUDA(cudaMemcpyAsync(s->h_qstats.p, s->d_qstats.p, B * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  }
+  unsigned long long hps[12] = {0};
+  if (pstats && s->d_pstats.p)
+    HX_CUDA(cudaMemcpyAsync(hps, s->d_pstats.p, sizeof(hps), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaStreamSynchronize(s->stream));
+  for (size_t b = 0; b < B; ++b)
+    if (s->h_status.p[b] != HX_ST_OK) return status_from_word(s->h_status.p[b], b, "query");
+  if ((rc = check_device_flags(s->h_err.p[0]))) return rc;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
+    ix->last_kernel_ms = ms;
+    ix->last_kernel_launches = 1;
+  }
+  if (pstats) memcpy(pstats, hps, sizeof(hps));
+  if (stats) {
+    stats->kernel_launches = launches;
+    if (want_stats) {
+      for (size_t b = 0; b < B; ++b) {
+        stats->expansion_steps += s->h_qstats.p[b * 4 + 0];
+        stats->neighbors_examined += s->h_qstats.p[b * 4 + 1];
+        stats->distance_computations += s->h_qstats.p[b * 4 + 2];
+        stats->upper_layer_steps += s->h_qstats.p[b * 4 + 3];
+        if (s->h_qstats.p[b * 4 + 2]) stats->vectors_loaded += s->h_qstats.p[b * 4 + 2] - 1;
+      }
+      stats->algorithmic_bytes = stats->expansion_steps * (5ull + 8ull * ix->lim0) +
+                                 stats->distance_computations * (4ull + 4ull * ix->cfg.dimension) +
+                                 (pstats ? pstats->simhash_examined * 8ull : 0ull);
+    }
+  }
+  return HX_OK;
 }
 
 extern "C" hx_status hx_last_kernel_ms(hx_index* ix, float* ms, uint32_t* launches) {

@@ -86,6 +86,8 @@ struct HxScratch {
   DevBuf<uint32_t> d_vtab, d_vpool, d_vbusy;   // ring build: visited hash sets, overflow pool, pool busy flags
   uint32_t vpool_n = 0xffffffffu, vpool_cap = 0;
   DevBuf<unsigned long long> d_prof;   // HX_PHASE_PROF diagnostics
+  DevBuf<unsigned long long> d_pstats; // policy counters
+  DevBuf<uint64_t> d_qsim;             // query fingerprints
   bool prof_init = false;
   DevBuf<uint8_t> misc[16];   // dense path buffers (kept across calls)
   size_t stamp_stride = 0;
@@ -140,6 +142,12 @@ struct hx_index {
   uint64_t entry_id = 0;
   uint32_t entry_slot = 0;
   int max_layer = 0;
+  // SimHash policy state (production-default search mode)
+  hx_simhash_config simcfg{43u, 0.8f, 1u, 0.1f};
+  uint64_t* d_simhash = nullptr;       // [n] slot order
+  uint8_t* d_has_simhash = nullptr;    // [n]
+  float* d_planes_t = nullptr;         // [dim][64] (transposed for coalesced projection)
+  size_t simhash_count = 0;
   // bf16 copy for the dense path
   void* d_vec_bf16 = nullptr;
   float* d_sqnorm = nullptr;

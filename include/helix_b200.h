@@ -54,7 +54,7 @@ enum {
   HX_ERR_INVALID_PARAMETER = 9,        /* VectorParameterError: k == 0, ef < k, null pointer             */
   HX_ERR_CUDA = 10,                    /* a CUDA runtime call failed (see hx_last_error)                 */
   HX_ERR_OUT_OF_MEMORY = 11,
-  HX_ERR_UNSUPPORTED = 12              /* e.g. SimHash Adaptive mode (parity unpinned)       */
+  HX_ERR_UNSUPPORTED = 12              /* a mode or size the device path does not execute                */
 };
 
 /* ---- metrics -------------------------------------------------------------- */
@@ -85,16 +85,21 @@ typedef struct {
 
 /* ---- per-query parameters ---------------------------------------------------- */
 /* Mirrors SearchParams (search/vector/mod.rs:411-621).  SearchParams::new(k):
- * ef = max(k, 100).  mode HX_SIMHASH_OFF + pre_sampling_ratio 1.0 is the
- * reference's strict-exhaustive specialisation (STRICT_EXHAUSTIVE, search.rs:
- * 296-304,595-596) — the only mode whose results are pinned. */
+ * ef = max(k, 100), SimHashMode::Adaptive.  mode HX_SIMHASH_OFF + pre_sampling_ratio 1.0 is the
+ * reference's strict-exhaustive specialisation (STRICT_EXHAUSTIVE, search.rs:296-304,595-596), whose
+ * results the reference pins by value.  ADAPTIVE / ALWAYS (the production default) run the
+ * SimHash filtering / sampling / adaptive-bypass policy of search.rs:595-992 + policy.rs; they need the node
+ * fingerprints (hx_index_load_simhash or hx_index_compute_simhash) and are checked against the CPU oracle's
+ * restatement; see hx_search_ex for what the reference itself pins there. */
 typedef enum { HX_SIMHASH_OFF = 0, HX_SIMHASH_ADAPTIVE = 1, HX_SIMHASH_ALWAYS = 2 } hx_simhash_mode;
 
 typedef struct {
   uint32_t k;                  /* results per query, > 0                                */
   uint32_t ef;                 /* beam width, >= k; 0 => max(k,100)                    */
-  int32_t  simhash_mode;       /* hx_simhash_mode; only HX_SIMHASH_OFF is executed      */
-  float    pre_sampling_ratio; /* must be 1.0 (strict exhaustive)                       */
+  int32_t  simhash_mode;       /* hx_simhash_mode                                       */
+  float    pre_sampling_ratio; /* pre_simhash_sampling_ratio_override: a value in [0,1] = Some(v), negative = None.
+                                  OFF + 1.0 (or OFF + None) is the strict-exhaustive specialisation; every other
+                                  combination runs the policy kernel (hx_search_ex semantics, default policy params) */
   uint32_t collect_stats;      /* fill hx_stats (per-call sums)                         */
   uint32_t query_dimension;    /* length of each query as the caller holds it; 0 = the
                                   index dimension.  A mismatch is InvalidDimension and is
@@ -291,6 +296,63 @@ hx_status hx_merge_topk_device(int32_t device, const uint64_t* d_all_ids, const 
 hx_status hx_search_dense(hx_index* idx, const float* queries, size_t B, const hx_search_params* p,
                           uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
                           hx_stats* stats);
+
+/* ---- SimHash filtering / sampling policy: the production-default search mode ------------------------------
+ * SearchParams::new(k) is SimHashMode::Adaptive: layer 0 then runs Layer0Policy::decide per expansion
+ * (policy.rs:119-175: adaptive collision threshold :576-597, adaptive sampling :558-574, pre-/post-sampling activation
+ * :526-556, bypass windows :196-291), gates every unvisited neighbour on its 64-bit SimHash
+ * (unaligned_vector/simhash.rs:37-55: collisions = 64 - popcount(a ^ b) >= threshold; cosine only, policy.rs:67-88),
+ * accounts filtered nodes as virtual beam-fill slots (search.rs:742-748,940-951) and fetches vectors only for the
+ * survivors.  Index-level settings mirror VectorIndexConfig (config/indexes.rs:398-406); per-query ones the rest of
+ * SearchParams (mod.rs:431-454).
+ *
+ * Fingerprints are DATA, not recomputed secrets: the reference persists one per node ([0x12] rows, 8 bytes LE,
+ * values/vectors/simhash.rs:37-41) -> hx_index_load_simhash; the query's fingerprint is computed by the caller's
+ * SimHasher (hash_from_slice, unaligned_vector/simhash.rs:263-290) and passed in, or — when the caller hands over the
+ * hyperplane table (SimHasher::hyperplanes(), 64 x dimension f32) — projected on the device with the same sequential
+ * `dot += v*h` order.  Bernoulli draws use the reference's query-derived seed (randomness.rs:109-114) over ChaCha12
+ * (rand 0.10 StdRng, restated from the published algorithm: the reference pins no stream value); they only happen for
+ * frontiers larger than max(ef/4, 8).  "SimHash filter reads" follow the resident-store case (no KV reads). */
+typedef struct {
+  uint32_t simhash_threshold;      /* 0..64, default 43 (simhash.rs:35)            */
+  float    sampling_ratio;         /* default 0.8                                   */
+  uint32_t adaptive_enabled;       /* default 1                                     */
+  float    adaptive_failure_prob;  /* default 0.1, in (0,1)                         */
+} hx_simhash_config;
+hx_status hx_index_set_simhash_config(hx_index* idx, const hx_simhash_config* cfg);
+hx_status hx_index_load_simhash(hx_index* idx, const uint64_t* ids, const uint64_t* bits, size_t n);
+/* planes: 64 x dimension f32, plane-major (SimHasher::hyperplanes()). */
+hx_status hx_index_set_simhash_planes(hx_index* idx, const float* planes);
+/* hash_from_slice of every loaded row on the device (needs the planes); replaces loaded fingerprints. */
+hx_status hx_index_compute_simhash(hx_index* idx);
+hx_status hx_index_download_simhash(hx_index* idx, size_t first_slot, size_t n, uint64_t* out_bits);
+/* locality order code of the canonical vector key (simhash.rs:44-59); pure */
+uint64_t  hx_order_code_from_simhash_bits(uint64_t bits);
+
+typedef struct {                      /* SearchParams fields beyond hx_search_params; hx_policy_params_default() first */
+  uint32_t bypass_min_frontier;       /* 24   */
+  uint32_t bypass_window_expansions;  /* 4    */
+  float    bypass_min_filter_rate;    /* 0.12 */
+  uint32_t read_budget_multiplier;    /* 3    */
+  float    sampling_ratio_override;   /* simhash_sampling_ratio_override; negative = None */
+  float    failure_prob_override;     /* simhash_failure_prob_override;   negative = None */
+  uint32_t reserved[2];
+} hx_policy_params;
+void hx_policy_params_default(hx_policy_params* p);
+
+/* Sums over the B queries of the SimHash-related SearchStats counters (mod.rs:640-700). */
+typedef struct {
+  uint64_t simhash_filtered, simhash_examined, simhash_missing_hash, simhash_passed_before_sampling,
+      simhash_passed_after_sampling, simhash_bypass_expansions, simhash_skipped_candidates, pre_simhash_sample_kept,
+      pre_simhash_sample_dropped, simhash_bypass_trigger_budget, simhash_bypass_trigger_low_yield, rng_draws;
+} hx_policy_stats;
+
+/* hx_search with the full SearchParams surface.  policy == NULL: SearchParams::new defaults.  query_simhash == NULL:
+ * projected on the device from the planes (HX_ERR_INVALID_VECTOR_CONFIG when there are none).  The strict-exhaustive
+ * combination is forwarded to the exhaustive kernels (identical results to hx_search). */
+hx_status hx_search_ex(hx_index* idx, const float* queries, size_t B, const hx_search_params* p,
+                       const hx_policy_params* policy, const uint64_t* query_simhash, uint64_t* out_ids,
+                       float* out_scores, uint32_t* out_counts, hx_stats* stats, hx_policy_stats* policy_stats);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char* hx_last_error(void);          /* thread-local, valid until the next failing call     */

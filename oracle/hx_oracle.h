@@ -7,9 +7,11 @@
  * relative to /root/reference/crates/db/src/search/vector/).
  *
  * Pinning: checked against the reference's own known-answer tests (SURVEY §8c,
- * tests/test_oracle_kat.py).  NOT pinned: SimHash bit values and Adaptive-mode
- * sampling (they live in rand 0.10.2 / chacha20 0.10.1, absent from the tree and
- * pinned by no committed value) — only strict-exhaustive search is restated.
+ * tests/test_oracle_kat.py).  Strict-exhaustive search and the layer-0 policy functions are
+ * pinned by values the reference's tests assert.  NOT pinned (the section at the end of this
+ * header says exactly what): the stream of the query session RNG (rand 0.10.2 / chacha20 0.10.1
+ * are absent from the tree; restated from their published algorithm) and SimHash hyperplane
+ * values (never generated here: fingerprints and planes are inputs).
  */
 #ifndef HX_ORACLE_H
 #define HX_ORACLE_H

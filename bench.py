@@ -376,13 +376,22 @@ def run_ours(args):
         d_ids, _, d_cnt = ix.search_ex(qsets[0], pnew, stats=st_d, policy_stats=ps_d)
         d_recall = recall_at_k(d_ids[:rq], truth)
         pnew.collect_stats = False
+        cpn, poln = pnew._c(), pnew._policy()
+
+        def step_default(s):
+            rc = L.hx_search_ex(ix.h, C.cast(h_q[s].data_ptr(), C.POINTER(C.c_float)), Q, C.byref(cpn), C.byref(poln), None,
+                                C.cast(h_ids.data_ptr(), C.POINTER(C.c_uint64)), C.cast(h_sc.data_ptr(), C.POINTER(C.c_float)),
+                                C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None, None)
+            if rc != 0:
+                raise RuntimeError(f"hx_search_ex failed: {L.hx_last_error().decode()}")
+
         for s in range(args.warmup):
-            ix.search_ex(qsets[s], pnew)
+            step_default(s)
         barrier()
         kms_sum = 0.0
         t0 = time.perf_counter()
         for s in range(args.steps):
-            ix.search_ex(qsets[args.warmup + s], pnew)
+            step_default(args.warmup + s)
             kms_sum += ix.last_kernel_ms()[0]
         td = time.perf_counter() - t0
         default_mode = {

@@ -1203,6 +1203,8 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     if (const char* env = getenv("HX_L2_HINT")) rg.l2_hint = atoi(env) ? 1u : 0u;
     rg.batch_admit = 1;
     if (const char* env = getenv("HX_LAT_ADMIT")) rg.batch_admit = strcmp(env, "seq") == 0 ? 0u : 1u;
+    rg.l2_spec = 0;   // measured: the speculative row prefetch costs more than it hides (profiles/r01_latency_*); opt-in
+    if (const char* env = getenv("HX_LAT_SPEC")) rg.l2_spec = atoi(env) ? 1u : 0u;
     if (const char* env = getenv("HX_PHASE_PROF")) {   // diagnostics: cycle sums per phase of the latency build
       if (atoi(env)) {
         if ((rc = s->d_prof.reserve(8))) return rc;
@@ -1912,15 +1914,22 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   }
   const uint32_t fr_cap = round_up(std::max(ix->stride0, ix->stride_u), 32);
   const size_t rowbytes = (size_t)ix->ld * 4;
-  const size_t fixed0 = rowbytes + (size_t)ef * 8 + (size_t)k * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 13 + 28 * 4 + 16;
+  // the query stays in shared memory: holding it in registers (QCH = 24) spills at the 128-register cap of a 512-thread CTA
+  // and measured 2x slower (profiles/r01_policy_sweep.json)
+  const uint32_t pol_qch = 0;
+  const size_t fixed0 = (pol_qch ? 0 : rowbytes) + (size_t)ef * 8 + (size_t)k * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 13 +
+                        28 * 4 + 16;
   const size_t budget = 227 * 1024;
   uint32_t wpc = 0, R = 0;
   const uint32_t spread = (uint32_t)std::max<size_t>(1, (B + ix->sm_count - 1) / (size_t)ix->sm_count);
-  for (uint32_t w = std::min(16u, spread); w >= 1; --w) {
+  uint32_t pol_warps = 16, pol_minR = 3;   // fewer rows per expansion survive the gate: 3 slots suffice
+  if (const char* env = getenv("HX_POL_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 16) pol_warps = (uint32_t)v; }
+  if (const char* env = getenv("HX_POL_MINR")) { const int v = atoi(env); if (v >= 1 && v <= 32) pol_minR = (uint32_t)v; }
+  for (uint32_t w = std::min(pol_warps, spread); w >= 1; --w) {
     const size_t per_warp = (budget / w) & ~(size_t)127;
     if (per_warp <= fixed0 + 8 + rowbytes) continue;
     const uint32_t r = (uint32_t)std::min<size_t>(32, (per_warp - fixed0) / (rowbytes + 8));
-    if (r >= 4 || w == 1) { wpc = w; R = r; break; }
+    if (r >= pol_minR || w == 1) { wpc = w; R = r; break; }
   }
   if (R == 0) {
     hx_set_error("query working set exceeds shared memory (dimension %u, ef %u)", ix->cfg.dimension, ef);
@@ -1957,6 +1966,8 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   rg.pool_cap = pool_cap;
   rg.counter = s->d_err.p + 1;
   rg.l2_hint = 1;
+  rg.l2_spec = 1;   // policy kernel: fingerprints requested together with the visited probe (HX_POL_EARLY_SIM=0: after it)
+  if (const char* env = getenv("HX_POL_EARLY_SIM")) rg.l2_spec = atoi(env) ? 1u : 0u;
   HxHnswArgs a{};
   a.queries = d_queries;
   a.q_hdr = s->d_qhdr.p;
@@ -1983,16 +1994,20 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   pa.cfg.bypass_min_filter_rate = pol->bypass_min_filter_rate;
   pa.cfg.read_budget_multiplier = pol->read_budget_multiplier;
   pa.node_simhash = ix->d_simhash;
-  pa.node_has_simhash = ix->d_has_simhash;
+  pa.node_has_simhash = ix->simhash_count == ix->n ? nullptr : ix->d_has_simhash;   // all present: skip the byte load
   pa.query_simhash = d_qsim;
   pa.pstats = s->d_pstats.p;
   const HxDev dev = ix->dev();
   const size_t smem_launch = (size_t)wpc * wstride;
+#define HX_LAUNCH_POLICY2(M, Q)                                                                                    \
+  do {                                                                                                             \
+    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_policy<M, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                 (int)smem_launch));                                                               \
+    k_hnsw_search_policy<M, Q><<<grid, wpc * 32, smem_launch, stream>>>(dev, a, rg, pa, wstride, R);               \
+  } while (0)
 #define HX_LAUNCH_POLICY(M)                                                                                        \
   do {                                                                                                             \
-    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_policy<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                 (int)smem_launch));                                                               \
-    k_hnsw_search_policy<M><<<grid, wpc * 32, smem_launch, stream>>>(dev, a, rg, pa, wstride, R);                  \
+    HX_LAUNCH_POLICY2(M, 0);                                                                                       \
   } while (0)
   switch (ix->cfg.metric) {
     case HX_METRIC_EUCLIDEAN: HX_LAUNCH_POLICY(HXM_EUCLIDEAN); break;
@@ -2000,6 +2015,7 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
     default: HX_LAUNCH_POLICY(HXM_MANHATTAN); break;
   }
 #undef HX_LAUNCH_POLICY
+#undef HX_LAUNCH_POLICY2
   HX_CUDA(cudaGetLastError());
   (*launches)++;
   return HX_OK;

@@ -236,7 +236,7 @@ __device__ __forceinline__ bool hx_vt_contains(const HxVisited& v, uint32_t key)
 // shared memory per warp: query | R row slots | beam[ef] | topk[k] | tie | R mbarriers | frontier | fdist | fhdr(aliases fsim) |
 //                         fstate (bytes) | session (28 words)
 #define HX_POLICY_MAX_THREADS 512
-template <int METRIC>
+template <int METRIC, int QCH>
 __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy(HxDev ix, HxHnswArgs a, HxRingArgs rg,
                                                                                 HxPolicyArgs pa, uint32_t wstride, uint32_t R) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
   const uint32_t warps_per_cta = blockDim.x >> 5;
   const uint32_t gw = blockIdx.x * warps_per_cta + warp;
   unsigned char* wmem = smem + (size_t)warp * wstride;
-  float* sq = reinterpret_cast<float*>(wmem);                                            // [ld]
-  float* ring = sq + ix.ld;                                                              // [R][ld]
+  constexpr bool Q_SMEM = QCH == 0 || METRIC == HXM_MANHATTAN;   // Manhattan walks the query sequentially: keep it in smem
+  float* sq = reinterpret_cast<float*>(wmem);                                            // [ld] when Q_SMEM
+  float* ring = sq + (Q_SMEM ? ix.ld : 0u);                                              // [R][ld]
   uint64_t* beam_mem = reinterpret_cast<uint64_t*>(ring + (size_t)R * ix.ld);           // [ef]
   uint64_t* topk_mem = beam_mem + a.ef;                                                  // [k]
   uint64_t* tie = topk_mem + a.k;                                                        // [HX_TIE_CAP]
@@ -263,10 +264,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
   if (lane < R) hx_mbar_init(bars + lane, 1);
   hx_fence_mbar_init();
   __syncwarp();
-  const float qr_dummy[1] = {0.f};
+  float qr[(!Q_SMEM && QCH > 0) ? QCH : 1];
   const float* qg = nullptr;
   float q_hdr = 0.f;
-  unsigned long long ps[12];
+  uint32_t ps[12];   // per-warp sums (a warp handles a handful of queries per launch: 32 bits are plenty)
 #pragma unroll
   for (int i = 0; i < 12; ++i) ps[i] = 0;   // lane 0's copy is the one that is reported
 
@@ -290,8 +291,8 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
         const float* row = ring + (size_t)s * ix.ld;
         for (uint32_t i = 0; i < ix.dim; ++i) sc = __fadd_rn(sc, fabsf(__fsub_rn(sq[i], row[i])));
       } else {
-        sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), 0>(ring + (size_t)s * ix.ld, qr_dummy, sq, qg, q_hdr,
-                                                                                 METRIC == HXM_COSINE ? fhdr[j] : 0.f, ix.dim, lane);
+        sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
+            ring + (size_t)s * ix.ld, qr, sq, qg, q_hdr, METRIC == HXM_COSINE ? fhdr[j] : 0.f, ix.dim, lane);
       }
       if (lane == 0) fdist[j] = sc;
       __syncwarp();
@@ -312,7 +313,12 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     }
     q_hdr = a.q_hdr[qi];
     qg = a.queries + (size_t)qi * ix.dim;
-    for (uint32_t i = lane; i < ix.ld; i += 32) sq[i] = i < ix.dim ? qg[i] : 0.0f;
+    if (Q_SMEM) {
+      for (uint32_t i = lane; i < ix.ld; i += 32) sq[i] = i < ix.dim ? qg[i] : 0.0f;
+    } else {
+#pragma unroll
+      for (int c = 0; c < ((!Q_SMEM && QCH > 0) ? QCH : 1); ++c) qr[c] = (uint32_t)(c * 32) + lane < ix.dim ? qg[c * 32 + lane] : 0.f;
+    }
     const uint64_t qsim = pa.query_simhash[qi];
     HxVisited vt = hx_vt_make(rg.vtab + (size_t)gw * rg.vt_cap, rg.vt_cap);
     int pool_idx = -1;
@@ -422,12 +428,29 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
             break;
           }
         }
+        const bool want_sim = METRIC == HXM_COSINE && pa.cfg.mode != HXP_OFF;   // the gate can only be active then
         for (uint32_t base = 0; base < deg; base += 32) {
           const uint32_t i = base + lane;
           if (base) nb = i < deg ? row[i] : 0u;
+          // the fingerprint is requested together with the visited probe (both depend on the row only): one round trip
+          uint64_t h = 0;
+          bool hh = false;
+          const bool early = rg.l2_spec != 0;
+          if (early && want_sim && i < deg) {
+            hh = pa.node_has_simhash == nullptr || pa.node_has_simhash[nb] != 0;
+            h = pa.node_simhash[nb];
+          }
           const bool fresh = i < deg && !hx_vt_contains(vt, nb);
+          if (!early && want_sim && fresh) {
+            hh = pa.node_has_simhash == nullptr || pa.node_has_simhash[nb] != 0;
+            h = pa.node_simhash[nb];
+          }
           const uint32_t mask = __ballot_sync(FULL, fresh);
-          if (fresh) frontier[nf + __popc(mask & ((1u << lane) - 1u))] = nb;
+          if (fresh) {
+            const uint32_t pos = nf + __popc(mask & ((1u << lane) - 1u));
+            frontier[pos] = nb;
+            fsim[pos] = hh ? 64u - (uint32_t)__popcll(h ^ qsim) : 0x80000000u;   // bit 31: no fingerprint
+          }
           nf += __popc(mask);
         }
       }
@@ -451,12 +474,13 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
         uint32_t kept = 0, rejected = 0;
         if (lane == 0) {
           for (uint32_t i = 0; i < nf; ++i) {
-            if (hxp_should_sample(sess, dec.pre_prob)) frontier[kept++] = frontier[i];
+            if (hxp_should_sample(sess, dec.pre_prob)) { fsim[kept] = fsim[i]; frontier[kept++] = frontier[i]; }
             else rejected++;
           }
           if (kept == 0) {   // never leave a non-empty frontier unexplored: one uniform pick (:666-672)
             const uint32_t idx = hxp_choose_index(sess, nf);
             frontier[0] = frontier[idx];
+            fsim[0] = fsim[idx];
             kept = 1;
           }
         }
@@ -477,9 +501,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
         bool has_hash = false, filtered = false;
         if (f < nsf) {
           nb = frontier[f];
-          has_hash = dec.filter_cached && (pa.node_has_simhash == nullptr || pa.node_has_simhash[nb] != 0);
+          const uint32_t raw = fsim[f];
+          has_hash = dec.filter_cached && !(raw & 0x80000000u);
           if (has_hash) {
-            sim = 64u - (uint32_t)__popcll(pa.node_simhash[nb] ^ qsim);
+            sim = raw;
             filtered = sim < active_threshold;
           }
           fsim[f] = sim;
@@ -622,7 +647,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
       }
       if (sess_mem[25]) {
         const uint64_t blk = ((uint64_t)sess_mem[27] << 32) | sess_mem[26];
-        ps[11] += blk * 16ull - (16ull - sess_mem[24]);
+        ps[11] += (uint32_t)(blk * 16ull - (16ull - sess_mem[24]));
       }
     }
     __syncwarp();
@@ -634,5 +659,5 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
   }
   if (pa.pstats && lane == 0)
     for (int i = 0; i < 12; ++i)
-      if (ps[i]) atomicAdd(pa.pstats + i, ps[i]);
+      if (ps[i]) atomicAdd(pa.pstats + i, (unsigned long long)ps[i]);
 }

@@ -33,6 +33,7 @@ struct HxRingArgs {
   uint32_t* counter;     // next query index (zeroed before the launch)
   uint32_t l2_hint;      // 1: evict-first cache hint on row copies
   uint32_t batch_admit;  // 1: one-pass admission of a frontier (latency build, register beam)
+  uint32_t l2_spec;      // 1: latency build prefetches the predicted next expansion's rows into L2
   unsigned long long* prof;   // optional [8] cycle sums of the latency build's phases (HX_PHASE_PROF=1, diagnostics only)
 };
 
@@ -48,6 +49,11 @@ __device__ __forceinline__ void hx_bulk_g2s_hint(void* dst_smem, const void* src
           hx_smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(hx_smem_u32(bar)), "l"(policy)
       : "memory");
+}
+
+// bulk prefetch of `bytes` (multiple of 16) into L2, no shared-memory destination
+__device__ __forceinline__ void hx_bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
 // ---- visited hash set --------------------------------------------------------------------------------------------------
@@ -540,39 +546,45 @@ __device__ __forceinline__ uint32_t hx_rbeam_admit_batch(HxRegBeam<NB>& b, uint3
   const bool pass = valid && ((sbits < wmax) || (b.len < ef));   // necessary: w.max never increases
   const uint32_t pm = __ballot_sync(FULL, pass);
   if (!pm) return 0u;
-  uint32_t cW = 0, cC = 0;
-  for (uint32_t m = pm; m; m &= m - 1) {
-    const int j = __ffs((int)m) - 1;
-    const uint32_t sj = __shfl_sync(FULL, sbits, j);
-    const uint64_t bound = ((uint64_t)sj + 1ull) << 32;   // every key with score <= s_j is below it
-    uint32_t c = 0;
+  // ranks against the beam by binary search over its sorted shared-memory mirror (`stage` holds the beam as of the
+  // previous admission; bit 0 of a key never decides an order because slots are distinct): cW = #keys below the score
+  // bound, rW = #keys below the candidate's own key.  Both searches walk the same (warp-uniform) halving schedule.
+  const uint64_t key = ((uint64_t)sbits << 32) | ((uint64_t)slot << 1);
+  const uint64_t bound = ((uint64_t)sbits + 1ull) << 32;   // every key with score <= s is below it
+  uint32_t cW = 0, rW = 0;
+  {
+    uint32_t n = b.len, bb = 0, bk = 0;
+    if (n) {
+      while (n > 1) {
+        const uint32_t half = n >> 1;
+        const uint64_t xb = stage[bb + half - 1], xk = stage[bk + half - 1];
+        bb = xb < bound ? bb + half : bb;
+        bk = xk < key ? bk + half : bk;
+        n -= half;
+      }
+      cW = bb + (stage[bb] < bound ? 1u : 0u);
+      rW = bk + (stage[bk] < key ? 1u : 0u);
+    }
+  }
+  uint32_t cC = 0;   // earlier passing candidates with a score <= mine (rejected ones can only have larger scores)
 #pragma unroll
-    for (int r = 0; r < NB; ++r) c += (b.v[r] < bound) ? 1u : 0u;
-    const uint32_t tot = __reduce_add_sync(FULL, c);
-    if ((int)lane == j) cW = tot;
-    if (pass && (int)lane > j && sj <= sbits) cC++;
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t sj = __shfl_sync(FULL, sbits, j);
+    cC += (((pm >> j) & 1u) && j < (int)lane && sj <= sbits) ? 1u : 0u;
   }
   const bool adm = pass && (cW + cC < ef);
   const uint32_t am = __ballot_sync(FULL, adm);
   if (!am) return 0u;
   const uint32_t n_adm = (uint32_t)__popc(am);
-  const uint64_t key = ((uint64_t)sbits << 32) | ((uint64_t)slot << 1);
   uint32_t sh[NB];
 #pragma unroll
   for (int r = 0; r < NB; ++r) sh[r] = 0;
-  uint32_t rW = 0, rA = 0;
+  uint32_t rA = 0;
   for (uint32_t m = am; m; m &= m - 1) {
     const int j = __ffs((int)m) - 1;
     const uint64_t ka = __shfl_sync(FULL, key, j);
-    uint32_t c = 0;
 #pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      const uint32_t lt = (b.v[r] < ka) ? 1u : 0u;   // keys are distinct (a visited slot is never scored again)
-      c += lt;
-      sh[r] += 1u - lt;
-    }
-    const uint32_t tot = __reduce_add_sync(FULL, c);
-    if ((int)lane == j) rW = tot;
+    for (int r = 0; r < NB; ++r) sh[r] += (ka < b.v[r]) ? 1u : 0u;   // sentinels (HX_KEY_MAX) count too: never used
     if (adm && ka < key) rA++;
   }
   const uint32_t old_len = b.len, total = old_len + n_adm, new_len = total < ef ? total : ef;
@@ -682,7 +694,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
 
   // all threads: reduce list[0..cnt) (shared memory, visible to every warp) into fdist.  Warp w owns slots and rows
   // w, w+W, ...: it issues their copies itself (lane j -> its j-th row), so a slot is only ever touched by one warp.
-  auto score_list = [&](const uint32_t* list, uint32_t cnt) {
+  auto score_list = [&](const uint32_t* list, uint32_t cnt, auto&& after_issue) {
     for (uint32_t base = 0; base < cnt; base += RC) {
       const uint32_t rows = min(RC, cnt - base);
       const uint32_t mine = lane * W + warp;   // the row this lane issues
@@ -694,6 +706,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
         else hx_bulk_g2s(ring + (size_t)mine * ix.ld, ix.vec + (size_t)slot * ix.ld, rowbytes, bars + mine);
         if (METRIC == HXM_COSINE) rh = __ldg(ix.hdr + slot);
       }
+      if (base == 0) after_issue();   // work that may overlap the copies' flight (warp 0: speculative L2 prefetch)
       uint32_t j = 0;
       for (uint32_t r = warp; r < rows; r += W, ++j) {
         const float row_hdr = __shfl_sync(FULL, rh, j);
@@ -728,7 +741,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
     uint32_t cur = ix.entry_slot;
     if (tid == 0) frontier[0] = cur;
     __syncthreads();
-    score_list(frontier, 1);
+    score_list(frontier, 1, [] {});
     float cur_dist = fdist[0];
     if (tid == 0 && !hx_score_ok(cur_dist)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
     uint32_t upper_steps = 0;
@@ -747,7 +760,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
           }
         }
         __syncthreads();
-        score_list(frontier, deg);
+        score_list(frontier, deg, [] {});
         if (warp == 0) {
           float best = cur_dist;
           uint32_t best_i = HX_ABSENT;
@@ -796,6 +809,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
       if (NB > 0) {
         hx_rbeam_insert(rb, a.ef, key0, lane);
         if (rb.len == a.ef) wmax = (uint32_t)(hx_rbeam_get(rb, a.ef - 1u) >> 32);
+        if (lane == 0) beam_mem[0] = key0;   // sorted mirror of the beam for the one-pass admission's binary searches
       } else {
         if (lane == 0) beam_mem[0] = key0;
         beam.len = 1;
@@ -893,7 +907,31 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
           sp_raw = ix.raw0[sp_slot];
         }
       }
-      score_list(frontier, nf);
+      score_list(frontier, nf, [&] {
+        // Rows of the predicted next expansion: start pulling its unvisited neighbours' vectors into L2 now, while this
+        // frontier is in flight / being reduced.  Read-only probe of the visited set; a wrong guess only costs bandwidth.
+        if (warp == 0 && rg.l2_spec && sp_slot != HX_ABSENT && lane < sp_deg) {
+          bool vis;
+          if (pool_idx < 0) {
+            uint32_t h = (sp_nb * 2654435761u) >> vt.shift;
+            for (;;) {
+              const uint32_t cur_e = ((volatile uint32_t*)vts)[h];
+              if (cur_e == HX_VT_EMPTY) { vis = false; break; }
+              if (cur_e == sp_nb) { vis = true; break; }
+              h = (h + 1u) & vt.mask;
+            }
+          } else {
+            uint32_t h = (sp_nb * 2654435761u) >> vt.shift;
+            for (;;) {
+              const uint32_t cur_e = ((volatile uint32_t*)vt.tab)[h];
+              if (cur_e == HX_VT_EMPTY) { vis = false; break; }
+              if (cur_e == sp_nb) { vis = true; break; }
+              h = (h + 1u) & vt.mask;
+            }
+          }
+          if (!vis) hx_bulk_prefetch_l2(ix.vec + (size_t)sp_nb * ix.ld, rowbytes);
+        }
+      });
       if (prof) { pt4 = clock64(); pa[3] += pt4 - pt3; }
       // -- admit in neighbour-id order (search.rs:934-953)
       if (warp == 0) {

@@ -21,7 +21,7 @@ import bench  # noqa: E402
 import helix_db_b200 as hx  # noqa: E402
 
 KNOBS = ("HX_HNSW_IMPL", "HX_RING_WARPS", "HX_RING_R", "HX_VT_CAP_LOG2", "HX_L2_HINT", "HX_TMA_WARPS", "HX_VT_POOL",
-         "HX_LAT_IMPL", "HX_LAT_WARPS", "HX_PHASE_PROF")
+         "HX_LAT_IMPL", "HX_LAT_WARPS", "HX_PHASE_PROF", "HX_LAT_SPEC", "HX_LAT_ADMIT", "HX_POL_QCH", "HX_POL_WARPS", "HX_POL_MINR", "HX_POL_EARLY_SIM")
 DEFAULT_VARIANTS = [
     ("tma12", {"HX_HNSW_IMPL": "tma"}),
     ("ring16", {}),
@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--metric", default="cosine")
     ap.add_argument("--variants", default="")
     ap.add_argument("--batch1", action="store_true", help="also time one-query calls for every variant")
+    ap.add_argument("--policy", action="store_true", help="time the production-default mode (hx_search_ex) instead")
     ap.add_argument("--out", default="hnsw_sweep.json")
     a = ap.parse_args()
     variants = DEFAULT_VARIANTS
@@ -58,6 +59,36 @@ def main():
     out = {"setup": setup, "n": a.n, "dim": a.dim, "runs": []}
     peak, _ = bench.measured_peaks()
     k = 10
+    if a.policy:
+        planes = np.random.default_rng(42).standard_normal((64, a.dim)).astype(np.float32)
+        ix.set_simhash_planes(planes)
+        ix.compute_simhash()
+        B = int(a.B.split(",")[0])
+        qs = [ix.generate_queries(bench.SEED, B, first_query=s * B, n_centroids=bench.N_CENTROIDS, sigma=bench.SIGMA,
+                                  kind=bench.KIND) for s in range(a.reps + 1)]
+        ref = None
+        for name, env in variants:
+            for key in KNOBS:
+                os.environ.pop(key, None)
+            os.environ.update(env)
+            p = hx.SearchParams.new(k)
+            ids0, sc0, cnt0 = ix.search_ex(qs[0], p)
+            got = (ids0.tobytes(), sc0.tobytes())
+            same = True if ref is None else got == ref
+            ref = ref or got
+            kms = 0.0
+            for s in range(a.reps):
+                ix.search_ex(qs[1 + s], p)
+                kms += ix.last_kernel_ms()[0]
+            kms /= a.reps
+            run = {"variant": name, "env": env, "B": B, "policy_kernel_ms": round(kms, 3), "kernel_qps": round(B / kms * 1e3, 1),
+                   "same_bits_as_first": same}
+            print(json.dumps(run), flush=True)
+            out["runs"].append(run)
+        (ROOT / "gpurun_out").mkdir(exist_ok=True)
+        (ROOT / "gpurun_out" / a.out).write_text(json.dumps(out, indent=1))
+        ix.close()
+        return
     for B in [int(x) for x in a.B.split(",")]:
         qs = [ix.generate_queries(bench.SEED, B, first_query=s * B, n_centroids=bench.N_CENTROIDS, sigma=bench.SIGMA,
                                   kind=bench.KIND) for s in range(a.reps + 1)]

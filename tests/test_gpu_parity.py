@@ -86,9 +86,9 @@ def test_validation_order_and_empty_index():
     with pytest.raises(hx.HelixDbError) as e:
         gpu.search([0.0, 0.0, 0.0], p)
     assert e.value.variant == "ZeroNormCosineVector"
-    with pytest.raises(hx.HelixDbError) as e:                          # Adaptive sampling is unpinned: refused, not faked
-        gpu.search([1.0, 0.0, 0.0], hx.SearchParams.new(1))
-    assert e.value.variant == "Unsupported"
+    with pytest.raises(hx.HelixDbError) as e:                          # the default (Adaptive) mode filters on SimHash rows:
+        gpu.search([1.0, 0.0, 0.0], hx.SearchParams.new(1))           # without them the search is refused, not degraded
+    assert e.value.variant == "InvalidVectorConfig"
     # greedy KAT (tests/production_support/vector/search.rs:231-291): from 100 on layer 1 the walk ends at 101
     r = gpu.search([1.0, 0.0, 0.0], p)
     assert [x.entity_id() for x in r] == [101] and bits(r[0].score()) == bits(0.0)

@@ -138,7 +138,8 @@ ABI_SYMBOLS = [
     "hx_decode_neighbor_row", "hx_encode_neighbor_row", "hx_index_export_neighbor_row",
     "hx_parse_vector_key", "hx_encode_vector_key", "hx_index_set_simhash_config", "hx_index_load_simhash",
     "hx_index_set_simhash_planes", "hx_index_compute_simhash", "hx_index_download_simhash",
-    "hx_order_code_from_simhash_bits", "hx_policy_params_default", "hx_search_ex",
+    "hx_order_code_from_simhash_bits", "hx_policy_params_default", "hx_search_ex", "hx_candidates_create",
+    "hx_candidates_destroy", "hx_candidates_len", "hx_search_restricted_sets",
 ]
 
 _lib = None
@@ -232,6 +233,15 @@ def load_library():
     L.hx_order_code_from_simhash_bits.argtypes = [C.c_uint64]
     L.hx_policy_params_default.restype = None
     L.hx_policy_params_default.argtypes = [C.POINTER(_PolicyParams)]
+    L.hx_candidates_create.restype = C.c_int32
+    L.hx_candidates_create.argtypes = [vp, u64p, sz, C.POINTER(vp)]
+    L.hx_candidates_destroy.restype = None
+    L.hx_candidates_destroy.argtypes = [vp]
+    L.hx_candidates_len.restype = C.c_uint64
+    L.hx_candidates_len.argtypes = [vp]
+    L.hx_search_restricted_sets.restype = C.c_int32
+    L.hx_search_restricted_sets.argtypes = [vp, fp, sz, C.POINTER(_Params), C.POINTER(vp), sz, u64p, fp, u32p,
+                                            C.POINTER(SearchStats)]
     L.hx_search_ex.restype = C.c_int32
     L.hx_search_ex.argtypes = [vp, fp, sz, C.POINTER(_Params), C.POINTER(_PolicyParams), u64p, u64p, fp, u32p,
                                C.POINTER(SearchStats), C.POINTER(PolicyStats)]
@@ -377,6 +387,27 @@ class SearchParams:
         ratio = -1.0 if self._pre_ratio is None else self._pre_ratio      # negative = no override (Option::None)
         return _Params(self._k, self._ef, int(self._mode), ratio, 1 if self.collect_stats else 0,
                        int(self.query_dimension))
+
+
+class DeviceCandidates:
+    """A candidate set resident on the device (hx_candidates)."""
+
+    def __init__(self, L, h, n):
+        self.L, self.h, self.n = L, h, n
+
+    def __len__(self):
+        return int(self.n)
+
+    def close(self):
+        if self.h:
+            self.L.hx_candidates_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class RestrictedVectorCandidates:
@@ -654,6 +685,31 @@ class VectorIndex:
                                         ids.ctypes.data_as(C.POINTER(C.c_uint64)),
                                         sc.ctypes.data_as(C.POINTER(C.c_float)),
                                         cnt.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(st)))
+        return ids, sc, cnt
+
+    def cache_candidates(self, allowed: "RestrictedVectorCandidates") -> "DeviceCandidates":
+        """Upload a candidate set once (label bitmap reuse); returns a handle for search_restricted_sets."""
+        ca, cp = _u64(allowed.ids)
+        h = C.c_void_p()
+        _ck(self.L.hx_candidates_create(self.h, cp, ca.size, C.byref(h)))
+        return DeviceCandidates(self.L, h, ca.size)
+
+    def search_restricted_sets(self, queries, params: SearchParams, sets, stats=None):
+        """One DeviceCandidates per query, or a single one shared by all queries."""
+        qa, qp = _f32(queries)
+        B = qa.size // self.dim
+        cp = params._c()
+        k = cp.k
+        sets = list(sets) if isinstance(sets, (list, tuple)) else [sets]
+        arr = (C.c_void_p * len(sets))(*[x.h for x in sets])
+        ids = np.zeros((B, k), dtype=np.uint64)
+        sc = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        st = stats if stats is not None else SearchStats()
+        _ck(self.L.hx_search_restricted_sets(self.h, qp, B, C.byref(cp), arr, len(sets),
+                                             ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                             sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                             cnt.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(st)))
         return ids, sc, cnt
 
     def search_restricted_multi(self, queries, params: SearchParams, cand_ids, cand_offsets, stats=None):

@@ -343,6 +343,7 @@ static hx_status alloc_vectors(hx_index* ix, size_t n) {
   HX_CUDA(cudaMalloc((void**)&ix->d_hdr, n * sizeof(float)));
   HX_CUDA(cudaMalloc((void**)&ix->d_ids, n * sizeof(uint64_t)));
   ix->n = n;
+  ix->vector_generation++;
   return HX_OK;
 }
 
@@ -1508,11 +1509,17 @@ static uint32_t pick_chunk(uint64_t total_cands, int sm_count) {
 }
 
 // d_cand_slots / d_cand_offsets on the device; host knows max candidate count per query and the total.
+struct HxSetRefs {   // device arrays describing one device-resident candidate set per query
+  const uint32_t* const* q_slots = nullptr;
+  const uint64_t* q_len = nullptr;
+  const uint64_t* q_keyoff = nullptr;
+};
+
 static hx_status launch_scan_select(hx_index* ix, HxScratch* s, const float* d_queries, size_t B, uint32_t k,
                                     const uint32_t* d_slots, const uint64_t* d_offsets, bool shared, uint64_t n_shared,
                                     uint64_t max_cands, uint64_t total_keys, uint64_t* d_out_ids, float* d_out_scores,
                                     uint32_t* d_out_counts, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1,
-                                    uint32_t* launches) {
+                                    uint32_t* launches, const HxSetRefs* sets = nullptr) {
   hx_status rc;
   if ((rc = s->d_keys.reserve(total_keys))) return rc;
   if ((rc = s->d_err.reserve(1))) return rc;
@@ -1530,6 +1537,7 @@ static hx_status launch_scan_select(hx_index* ix, HxScratch* s, const float* d_q
   a.n_shared = n_shared;
   a.chunk = pick_chunk(total_keys, ix->sm_count);
   a.err_flags = s->d_err.p;
+  if (sets) { a.q_slots = sets->q_slots; a.q_len = sets->q_len; a.q_keyoff = sets->q_keyoff; }
   dim3 grid((unsigned)((max_cands + a.chunk - 1) / a.chunk), (unsigned)std::min<size_t>(B, 65535));
   const uint32_t smem = ix->ld * 4u;
   HX_CUDA(cudaEventRecord(e0, stream));
@@ -1565,6 +1573,7 @@ static hx_status launch_scan_select(hx_index* ix, HxScratch* s, const float* d_q
   sa.out_ids = d_out_ids;
   sa.out_scores = d_out_scores;
   sa.out_counts = d_out_counts;
+  if (sets) { sa.q_slots = sets->q_slots; sa.q_len = sets->q_len; sa.q_keyoff = sets->q_keyoff; }
   k_select<<<(unsigned)std::min<size_t>(B, 65535), HX_SEL_THREADS, 0, stream>>>(dev, sa);
   HX_CUDA(cudaGetLastError());
   (*launches)++;
@@ -1682,6 +1691,162 @@ extern "C" hx_status hx_search_restricted_multi(hx_index* ix, const float* queri
                                                 uint32_t* out_counts, hx_stats* stats) {
   if (B && !cand_offsets) return HX_ERR_INVALID_PARAMETER;
   return restricted_host(ix, queries, B, p, cand_ids, cand_offsets, 0, false, out_ids, out_scores, out_counts, stats);
+}
+
+// ---- device-resident candidate sets ------------------------------------------------------------------------------------------
+// The reference's label / equality indexes are RoaringTreemap values keyed by the snapshot (encoding/v1/indexes/label.rs:10-14);
+// a prefilter that is reused across queries need not cross PCIe as 8 bytes per candidate on every call: the ids are uploaded and
+// mapped to slots once (ids without a vector row dropped, restricted.rs:615-659) and queries then name the set.
+struct hx_candidates {
+  hx_index* ix = nullptr;
+  uint32_t* d_slots = nullptr;   // ascending; HX_ABSENT for ids without a vector row (never results)
+  uint64_t n = 0;
+  uint64_t generation = 0;
+};
+
+extern "C" hx_status hx_candidates_create(hx_index* ix, const uint64_t* cand_ids, size_t n, hx_candidates** out) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (!out || (n && !cand_ids)) return HX_ERR_INVALID_PARAMETER;
+  *out = nullptr;
+  if (n > 1000000ull) {   // RestrictedVectorCandidates::from_ids (restricted.rs:356-371)
+    hx_set_error("restricted vector search accepts at most 1000000 unique candidates");
+    return HX_ERR_QUERY;
+  }
+  for (size_t i = 1; i < n; ++i)
+    if (cand_ids[i] <= cand_ids[i - 1]) {
+      hx_set_error("candidate ids must be ascending and unique (RoaringTreemap iteration order)");
+      return HX_ERR_INVALID_PARAMETER;
+    }
+  HX_CUDA(cudaSetDevice(ix->device));
+  hx_candidates* c = new hx_candidates();
+  c->ix = ix;
+  c->n = n;
+  c->generation = ix->vector_generation;
+  if (n) {
+    uint64_t* d_ids = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_ids, n * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_slots, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_ids, cand_ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      k_map_candidates<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_ids, (uint32_t)ix->n, d_ids, n, c->d_slots,
+                                                             ix->contiguous ? 1 : 0, ix->first_id);
+      e = cudaDeviceSynchronize();
+    }
+    if (d_ids) cudaFree(d_ids);
+    if (e != cudaSuccess) {
+      hx_set_error("candidate set upload failed: %s", cudaGetErrorString(e));
+      if (c->d_slots) cudaFree(c->d_slots);
+      delete c;
+      return e == cudaErrorMemoryAllocation ? HX_ERR_OUT_OF_MEMORY : HX_ERR_CUDA;
+    }
+  }
+  *out = c;
+  return HX_OK;
+}
+
+extern "C" void hx_candidates_destroy(hx_candidates* c) {
+  if (!c) return;
+  if (c->d_slots) {
+    cudaSetDevice(c->ix->device);
+    cudaFree(c->d_slots);
+  }
+  delete c;
+}
+
+extern "C" uint64_t hx_candidates_len(const hx_candidates* c) { return c ? c->n : 0; }
+
+extern "C" hx_status hx_search_restricted_sets(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                               hx_candidates* const* sets, size_t n_sets, uint64_t* out_ids,
+                                               float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+  if (!ix) {
+    hx_set_error("null index handle");
+    return HX_ERR_INDEX_NOT_FOUND;
+  }
+  uint32_t k, ef;
+  hx_status rc = check_params(ix, p, &k, &ef);
+  if (rc) return rc;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return HX_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts || !sets || (n_sets != 1 && n_sets != B)) {
+    hx_set_error("hx_search_restricted_sets: one set for all queries or one per query");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  uint64_t total_keys = 0, max_c = 0;
+  for (size_t b = 0; b < B; ++b) {
+    const hx_candidates* c = sets[n_sets == 1 ? 0 : b];
+    if (!c || c->ix != ix || c->generation != ix->vector_generation) {
+      hx_set_error("candidate set %zu does not belong to this index image (vectors were reloaded?)", b);
+      return HX_ERR_INVARIANT_VIOLATION;
+    }
+    if (c->n > 0 && std::min<uint64_t>(k, c->n) > 800) {   // RestrictedResultCount (restricted.rs:200-213)
+      hx_set_error("restricted vector search result count must be at most 800, got %llu",
+                   (unsigned long long)std::min<uint64_t>(k, c->n));
+      return HX_ERR_QUERY;
+    }
+    total_keys += c->n;
+    max_c = std::max<uint64_t>(max_c, c->n);
+  }
+  if (total_keys == 0) {
+    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
+    return HX_OK;
+  }
+  HX_CUDA(cudaSetDevice(ix->device));
+  HxScratch* s = nullptr;
+  if ((rc = hx_acquire_scratch(ix, &s))) return rc;
+  ScratchGuard guard{ix, s};
+  uint32_t launches = 0;
+  if ((rc = stage_queries(ix, s, queries, B, &launches))) return rc;
+  if (ix->n == 0 || !ix->populated) {
+    HX_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
+    return HX_OK;
+  }
+  // per-query (pointer, length, key offset): 24 bytes per query over PCIe instead of 8 bytes per candidate
+  if ((rc = s->h_cand_offsets.reserve(3 * B))) return rc;
+  if ((rc = s->d_cand_offsets.reserve(3 * B))) return rc;
+  uint64_t koff = 0;
+  for (size_t b = 0; b < B; ++b) {
+    const hx_candidates* c = sets[n_sets == 1 ? 0 : b];
+    s->h_cand_offsets.p[b] = (uint64_t)(uintptr_t)c->d_slots;
+    s->h_cand_offsets.p[B + b] = c->n;
+    s->h_cand_offsets.p[2 * B + b] = koff;
+    koff += c->n;
+  }
+  HX_CUDA(cudaMemcpyAsync(s->d_cand_offsets.p, s->h_cand_offsets.p, 3 * B * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                          s->stream));
+  HxSetRefs refs;
+  refs.q_slots = reinterpret_cast<const uint32_t* const*>(s->d_cand_offsets.p);
+  refs.q_len = s->d_cand_offsets.p + B;
+  refs.q_keyoff = s->d_cand_offsets.p + 2 * B;
+  if ((rc = s->d_out_ids.reserve(B * (size_t)k))) return rc;
+  if ((rc = s->d_out_scores.reserve(B * (size_t)k))) return rc;
+  if ((rc = s->d_out_counts.reserve(B))) return rc;
+  if ((rc = launch_scan_select(ix, s, s->d_queries.p, B, k, nullptr, nullptr, false, 0, max_c, total_keys, s->d_out_ids.p,
+                               s->d_out_scores.p, s->d_out_counts.p, s->stream, s->ev0, s->ev1, &launches, &refs)))
+    return rc;
+  if ((rc = s->h_status.reserve(B))) return rc;
+  if ((rc = s->h_err.reserve(1))) return rc;
+  HX_CUDA(cudaMemcpyAsync(out_ids, s->d_out_ids.p, B * (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_scores, s->d_out_scores.p, B * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_counts, s->d_out_counts.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(s->h_status.p, s->d_qstatus.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(s->h_err.p, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaStreamSynchronize(s->stream));
+  for (size_t b = 0; b < B; ++b)
+    if (s->h_status.p[b] != HX_ST_OK) return status_from_word(s->h_status.p[b], b, "query");
+  if ((rc = check_device_flags(s->h_err.p[0]))) return rc;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
+    ix->last_kernel_ms = ms;
+    ix->last_kernel_launches = 1;
+  }
+  if (stats) {
+    stats->kernel_launches = launches;
+    stats->distance_computations = total_keys;
+    stats->vectors_loaded = total_keys;
+    stats->algorithmic_bytes = total_keys * (4ull * ix->cfg.dimension + (ix->cfg.metric == HX_METRIC_COSINE ? 4 : 0));
+  }
+  return HX_OK;
 }
 
 extern "C" hx_status hx_map_candidates_device(hx_index* ix, const uint64_t* d_cand_ids, uint64_t n,

@@ -122,6 +122,7 @@ struct hx_index {
   std::vector<uint64_t> ids_sorted;   // host copy: slot -> id
   bool contiguous = false;
   uint64_t first_id = 0;
+  uint64_t vector_generation = 0;     // bumped whenever the slot numbering changes (hx_candidates are tied to it)
   float* d_vec = nullptr;
   float* d_hdr = nullptr;
   uint64_t* d_ids = nullptr;

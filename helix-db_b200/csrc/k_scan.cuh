@@ -30,6 +30,10 @@ struct HxScanArgs {
   uint64_t n_shared;
   uint32_t chunk;                // candidates per CTA (multiple of 32)
   uint32_t* err_flags;
+  // device-resident candidate sets (hx_candidates): per query a pointer, a length and the position of its keys
+  const uint32_t* const* q_slots;  // [B] or nullptr
+  const uint64_t* q_len;           // [B]
+  const uint64_t* q_keyoff;        // [B]
 };
 
 template <int METRIC>
@@ -38,8 +42,8 @@ static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan(HxDev ix, HxSca
   float* sq = reinterpret_cast<float*>(smem);
   const uint32_t tid = threadIdx.x, t = tid & 7u, oct = tid >> 3;
   for (uint32_t q = blockIdx.y; q < a.B; q += gridDim.y) {
-    const uint64_t base = a.shared_set ? 0ull : a.cand_offsets[q];
-    const uint64_t n = a.shared_set ? a.n_shared : (a.cand_offsets[q + 1] - base);
+    const uint64_t base = a.q_slots ? 0ull : (a.shared_set ? 0ull : a.cand_offsets[q]);
+    const uint64_t n = a.q_slots ? a.q_len[q] : (a.shared_set ? a.n_shared : (a.cand_offsets[q + 1] - base));
     const uint64_t start = (uint64_t)blockIdx.x * a.chunk;
     if (start >= n || a.q_status[q] != 0u) continue;   // uniform per CTA
     const uint64_t end = (start + a.chunk < n) ? start + a.chunk : n;
@@ -47,8 +51,8 @@ static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan(HxDev ix, HxSca
     for (uint32_t i = tid; i < ix.ld; i += HX_SCAN_THREADS)
       sq[i] = i < ix.dim ? a.queries[(size_t)q * ix.dim + i] : 0.0f;
     __syncthreads();
-    uint64_t* keys_out = a.keys + (a.shared_set ? (uint64_t)q * a.n_shared : base);
-    const uint32_t* slots = a.cand_slots + base;
+    uint64_t* keys_out = a.keys + (a.q_slots ? a.q_keyoff[q] : (a.shared_set ? (uint64_t)q * a.n_shared : base));
+    const uint32_t* slots = a.q_slots ? a.q_slots[q] : a.cand_slots + base;
     if (METRIC == HXM_MANHATTAN) {
       for (uint64_t r = start + tid; r < end; r += HX_SCAN_THREADS) {
         const uint32_t slot = slots[r];
@@ -90,6 +94,9 @@ struct HxSelectArgs {
   uint64_t* out_ids;             // [B][k] (mode 2: the slot itself)
   float* out_scores;
   uint32_t* out_counts;
+  const uint32_t* const* q_slots;  // device-resident candidate sets (see HxScanArgs)
+  const uint64_t* q_len;
+  const uint64_t* q_keyoff;
 };
 
 // bitonic sort of 2*HX_SEL_HALF keys in shared memory, ascending
@@ -116,13 +123,13 @@ static __global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSe
   __shared__ uint64_t s_thr;
   const uint32_t tid = threadIdx.x;
   for (uint32_t q = blockIdx.x; q < a.B; q += gridDim.x) {
-    const uint64_t base = a.shared_set ? 0ull : a.cand_offsets[q];
-    const uint64_t n = a.shared_set ? a.n_shared : (a.cand_offsets[q + 1] - base);
+    const uint64_t base = a.q_slots ? 0ull : (a.shared_set ? 0ull : a.cand_offsets[q]);
+    const uint64_t n = a.q_slots ? a.q_len[q] : (a.shared_set ? a.n_shared : (a.cand_offsets[q + 1] - base));
     if (a.q_status[q] != 0u || n == 0) {
       if (tid == 0) a.out_counts[q] = 0;
       continue;
     }
-    const uint64_t* keys = a.keys + (a.shared_set ? (uint64_t)q * a.n_shared : base);
+    const uint64_t* keys = a.keys + (a.q_slots ? a.q_keyoff[q] : (a.shared_set ? (uint64_t)q * a.n_shared : base));
     const uint32_t kk = (uint64_t)a.k < n ? a.k : (uint32_t)n;   // k' = min(k, |C|)
     for (uint32_t i = tid; i < 2 * HX_SEL_HALF; i += HX_SEL_THREADS) buf[i] = HX_KEY_MAX;
     if (tid == 0) { s_cnt = 0; s_thr = HX_KEY_MAX; }
@@ -146,7 +153,7 @@ static __global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSe
     }
     hx_bitonic_sort_2048(buf, tid);
     // count valid (absent candidates carry HX_KEY_MAX and are never results)
-    const uint32_t* slots = a.cand_slots + base;
+    const uint32_t* slots = a.q_slots ? a.q_slots[q] : a.cand_slots + base;
     uint32_t cnt = 0;
     for (uint32_t i = tid; i < kk; i += HX_SEL_THREADS) {
       const uint64_t key = buf[i];

@@ -258,6 +258,21 @@ hx_status hx_search_restricted_multi(hx_index* idx, const float* queries, size_t
                                      const uint64_t* cand_offsets, uint64_t* out_ids,
                                      float* out_scores, uint32_t* out_counts, hx_stats* stats);
 
+/* ---- device-resident candidate sets (prefilter reuse) ------------------------------------------------------
+ * The reference's label / equality indexes are RoaringTreemap values tied to a snapshot
+ * (encoding/v1/indexes/label.rs:10-14; SURVEY §8d: "allow label bitmaps to be cached device-side keyed by the same
+ * snapshot sequence").  hx_candidates_create uploads one candidate set (ascending unique ids, <= 1e6,
+ * restricted.rs:356-371) and maps it to device slots once; hx_search_restricted_sets then names a set per query
+ * (n_sets == B) or one for all (n_sets == 1): 24 bytes per query cross PCIe instead of 8 bytes per candidate.
+ * Same exact answer as hx_search_restricted.  A set is invalidated by reloading the index's vectors. */
+typedef struct hx_candidates hx_candidates;
+hx_status hx_candidates_create(hx_index* idx, const uint64_t* cand_ids, size_t n, hx_candidates** out);
+void      hx_candidates_destroy(hx_candidates* set);
+uint64_t  hx_candidates_len(const hx_candidates* set);
+hx_status hx_search_restricted_sets(hx_index* idx, const float* queries, size_t B, const hx_search_params* p,
+                                    hx_candidates* const* sets, size_t n_sets, uint64_t* out_ids,
+                                    float* out_scores, uint32_t* out_counts, hx_stats* stats);
+
 /* RestrictedExecutionPlan chosen by the reference for this |C| and dimension
  * (restricted.rs:40-42,426-453): 0 = Exact, 1 = FilteredGraph.  Informational: the
  * device path always answers exactly. */

@@ -287,6 +287,28 @@ def test_restricted_scan_edge_cases(gm, om):
     for q in range(len(queries)):
         oi, os_ = ora.search_restricted(queries[q], 10, cands[q])
         assert_same(gi[q], gs[q], gc[q], oi, os_, f"multi q={q}")
+    # the same sets resident on the device (uploaded and mapped once): identical answers, absent ids included
+    with_absent = [np.sort(np.concatenate([c, np.array([1, 3, 10**9], dtype=np.uint64)])) for c in cands]
+    dsets = [gpu.cache_candidates(hx.RestrictedVectorCandidates.from_ids(c)) for c in with_absent]
+    assert len(dsets[0]) == len(with_absent[0])
+    si, ss, scnt = gpu.search_restricted_sets(queries, hx.SearchParams.strict(10), dsets)
+    assert si.tolist() == gi.tolist() and ss.tobytes() == gs.tobytes() and scnt.tolist() == gc.tolist()
+    si, ss, scnt = gpu.search_restricted_sets(queries, hx.SearchParams.strict(10), dsets[3])     # one set for all queries
+    for q in range(len(queries)):
+        oi, os_ = ora.search_restricted(queries[q], 10, cands[3])
+        assert_same(si[q], ss[q], scnt[q], oi, os_, f"shared device set q={q}")
+    empty = gpu.cache_candidates(hx.RestrictedVectorCandidates.from_ids([]))
+    assert gpu.search_restricted_sets(queries, hx.SearchParams.strict(10), empty)[2].tolist() == [0] * len(queries)
+    big = gpu.cache_candidates(hx.RestrictedVectorCandidates.from_ids(ids[:900]))
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search_restricted_sets(queries, hx.SearchParams.strict(801), big)
+    assert e.value.variant == "Query"
+    gpu.load_vectors(ids, rows)                                            # a reloaded image invalidates the sets
+    gpu.load_graph(0, ids[:1], [0, 0], [])
+    gpu.set_entry(int(ids[0]), 0)
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search_restricted_sets(queries, hx.SearchParams.strict(10), dsets)
+    assert e.value.variant == "InvariantViolation"
 
 
 def test_restricted_full_million_candidate_bound():

@@ -2158,6 +2158,7 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   pa.cfg.bypass_window_expansions = pol->bypass_window_expansions;
   pa.cfg.bypass_min_filter_rate = pol->bypass_min_filter_rate;
   pa.cfg.read_budget_multiplier = pol->read_budget_multiplier;
+  pa.cfg.threshold_margin = sqrtf((64.0f * logf(1.0f / pa.cfg.failure_prob)) / 2.0f);   // policy.rs:592, host libm
   pa.node_simhash = ix->d_simhash;
   pa.node_has_simhash = ix->simhash_count == ix->n ? nullptr : ix->d_has_simhash;   // all present: skip the byte load
   pa.query_simhash = d_qsim;

@@ -30,6 +30,7 @@ struct HxPolicyCfg {   // SearchParams + VectorIndexConfig fields the policy rea
   uint32_t bypass_min_frontier, bypass_window_expansions;
   float bypass_min_filter_rate;
   uint32_t read_budget_multiplier;
+  float threshold_margin;   // sqrt(64 * ln(1/failure) / 2), computed once on the host (policy.rs:592)
 };
 
 struct HxPolicyArgs {
@@ -65,17 +66,16 @@ __device__ __forceinline__ float hxp_adaptive_sampling_ratio(float base, uint32_
   const float cap = 0.90f > base ? 0.90f : base;
   return v < cap ? v : cap;
 }
-// policy.rs:576-597.  acos / ln go through double precision and are rounded once to f32 (the host's libm results are
-// correctly rounded for these arguments; the integer threshold only changes at a floor boundary).
-__device__ __forceinline__ uint32_t hxp_adaptive_threshold(bool topk_ready, float delta, uint32_t configured, float failure) {
+// policy.rs:576-597.  The margin sqrt(64 ln(1/eps) / 2) is a per-query constant (host libm, passed in); acos goes through
+// double precision and is rounded once to f32 (the integer threshold only changes at a floor boundary).  FP64 is slow on
+// this part, and delta only moves when the running top-k improves: callers memoise on delta's bits.
+__device__ __forceinline__ uint32_t hxp_adaptive_threshold(bool topk_ready, float delta, uint32_t configured, float margin) {
   if (configured == 0u) return 0u;
   if (!topk_ready) return 1u;
   const float normalized = hxp_clamp(delta, 0.0f, 1.0f);
   const float cs = hxp_clamp(__fsub_rn(1.0f, __fmul_rn(2.0f, normalized)), -1.0f, 1.0f);
   const float ac = (float)acos((double)cs);
   const float collision = __fsub_rn(1.0f, __fdiv_rn(ac, 3.14159274101257324f));
-  const float ln = (float)log((double)__fdiv_rn(1.0f, failure));
-  const float margin = __fsqrt_rn(__fdiv_rn(__fmul_rn(64.0f, ln), 2.0f));
   const float t = hxp_clamp(floorf(__fsub_rn(__fmul_rn(64.0f, collision), margin)), 1.0f, 64.0f);
   const uint32_t v = (uint32_t)t;
   return v < configured ? v : configured;
@@ -85,7 +85,8 @@ __device__ __forceinline__ uint32_t hxp_adaptive_threshold(bool topk_ready, floa
 __device__ __forceinline__ HxDecision hxp_decide(int metric, const HxPolicyCfg& c, bool topk_ready, uint32_t ef,
                                                  uint32_t search_len, uint32_t frontier_len, float current, float delta,
                                                  int bstate, uint32_t bremaining, uint64_t filter_reads, uint64_t w_examined,
-                                                 uint64_t w_filtered, uint64_t w_expansions) {
+                                                 uint64_t w_filtered, uint64_t w_expansions, uint32_t& memo_key,
+                                                 uint32_t& memo_thr) {
   HxDecision d;
   d.fetch_missing = d.filter_cached = d.has_threshold = 0;
   d.threshold = 0;
@@ -147,7 +148,16 @@ __device__ __forceinline__ HxDecision hxp_decide(int metric, const HxPolicyCfg& 
   if (bypassed) { d.bypassed = 1; return d; }
   if (filtering == 0) return d;
   d.fetch_missing = d.filter_cached = d.has_threshold = 1;
-  d.threshold = filtering == 1 ? c.threshold : hxp_adaptive_threshold(topk_ready, delta, c.threshold, c.failure_prob);
+  if (filtering == 1) {
+    d.threshold = c.threshold;
+  } else {
+    const uint32_t mk = topk_ready ? __float_as_uint(delta) : 0xFFFFFFFEu;   // valid scores are below 0x7f800000
+    if (mk != memo_key) {
+      memo_thr = hxp_adaptive_threshold(topk_ready, delta, c.threshold, c.threshold_margin);
+      memo_key = mk;
+    }
+    d.threshold = memo_thr;
+  }
   return d;
 }
 // SamplingDecision::candidate_probability (policy.rs:415-430)
@@ -384,6 +394,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     int bstate = HXP_READY;
     uint32_t bremaining = 0;
     uint32_t vcount = 1;                                 // entries in the visited set
+    uint32_t memo_key = 0xffffffffu, memo_thr = 0;       // adaptive threshold memo (keyed by delta's bits)
     HxSession sess{sess_mem, qsim ^ ((ix.ids[cur] << 17) | (ix.ids[cur] >> 47)) ^ (((uint64_t)a.ef << 7) | ((uint64_t)a.ef >> 57))};
     if (lane == 0) {
       const uint64_t k0 = hx_make_key(cur_dist, cur << 1);
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
       const bool topk_ready = topk.len >= topk_target;
       const float delta = topk.len ? hx_key_score(topk_mem[topk.len - 1]) : __uint_as_float(cur_bits);
       const HxDecision dec = hxp_decide(METRIC, pa.cfg, topk_ready, a.ef, beam.len, nf, __uint_as_float(cur_bits), delta, bstate,
-                                        bremaining, 0ull, w_examined, w_filtered, w_expansions);
+                                        bremaining, 0ull, w_examined, w_filtered, w_expansions, memo_key, memo_thr);
       bstate = dec.next_state;
       bremaining = dec.next_remaining;
       if (dec.trigger & 1) ps[9]++;

@@ -56,6 +56,7 @@ class SearchParams {
  public:
   explicit SearchParams(uint32_t k) : k_(k), ef_(std::max(k, 100u)) {
     if (k == 0) throw HelixDbError(HX_ERR_INVALID_PARAMETER, "result count must be non-zero");
+    hx_policy_params_default(&policy_);
   }
   SearchParams& with_ef(uint32_t ef) {
     if (ef < k_) throw HelixDbError(HX_ERR_INVALID_PARAMETER, "search beam width must cover k");
@@ -63,7 +64,28 @@ class SearchParams {
     return *this;
   }
   SearchParams& with_simhash_mode(SimHashMode m) { mode_ = m; return *this; }
-  SearchParams& with_pre_simhash_sampling_ratio(float r) { ratio_ = r; has_ratio_ = true; return *this; }
+  SearchParams& with_pre_simhash_sampling_ratio(float r) {
+    if (!(r >= 0.0f && r <= 1.0f)) throw HelixDbError(HX_ERR_INVALID_PARAMETER, "ratio must be in the unit interval");
+    ratio_ = r; has_ratio_ = true; return *this;
+  }
+  // mod.rs:563-613
+  SearchParams& with_simhash_bypass_tuning(uint32_t min_frontier, uint32_t window_expansions, float min_filter_rate,
+                                           uint32_t read_budget_multiplier) {
+    if (!min_frontier || !window_expansions || !read_budget_multiplier || !(min_filter_rate >= 0.0f && min_filter_rate <= 1.0f))
+      throw HelixDbError(HX_ERR_INVALID_PARAMETER, "invalid SimHash bypass tuning");
+    policy_.bypass_min_frontier = min_frontier; policy_.bypass_window_expansions = window_expansions;
+    policy_.bypass_min_filter_rate = min_filter_rate; policy_.read_budget_multiplier = read_budget_multiplier;
+    return *this;
+  }
+  SearchParams& with_simhash_sampling_ratio(float r) {
+    if (!(r >= 0.0f && r <= 1.0f)) throw HelixDbError(HX_ERR_INVALID_PARAMETER, "ratio must be in the unit interval");
+    policy_.sampling_ratio_override = r; return *this;
+  }
+  SearchParams& with_simhash_failure_prob(float p) {
+    if (!(p > 0.0f && p < 1.0f)) throw HelixDbError(HX_ERR_INVALID_PARAMETER, "failure probability must be in (0, 1)");
+    policy_.failure_prob_override = p; return *this;
+  }
+  const hx_policy_params& policy() const { return policy_; }
   static SearchParams strict(uint32_t k) { return SearchParams(k).with_simhash_mode(SimHashMode::Off).with_pre_simhash_sampling_ratio(1.0f); }
   uint32_t k() const { return k_; }
   uint32_t ef() const { return ef_; }
@@ -73,7 +95,7 @@ class SearchParams {
     p.k = k_;
     p.ef = ef_;
     p.simhash_mode = static_cast<int32_t>(mode_);
-    p.pre_sampling_ratio = has_ratio_ ? ratio_ : (mode_ == SimHashMode::Off ? 1.0f : 0.8f);
+    p.pre_sampling_ratio = has_ratio_ ? ratio_ : -1.0f;   // negative = no override (Option::None)
     p.query_dimension = query_dimension;
     return p;
   }
@@ -83,6 +105,7 @@ class SearchParams {
   SimHashMode mode_ = SimHashMode::Adaptive;
   float ratio_ = 1.0f;
   bool has_ratio_ = false;
+  hx_policy_params policy_{};
 };
 
 // RestrictedVectorCandidates::from_ids: duplicates collapse, ascending, at most 1e6 (restricted.rs:356-371)
@@ -131,13 +154,33 @@ class VectorIndex {
   void set_entry(uint64_t entry_point, uint16_t max_layer) { check(hx_index_set_entry(h_, entry_point, max_layer)); }
   void build(uint64_t seed = 0) { check(hx_index_build(h_, nullptr, seed)); }
 
-  // VectorIndex::search (index.rs:1578): results sorted by (score, id), at most k
-  std::vector<SearchResult> search(const std::vector<float>& query, const SearchParams& params) const {
+  // SimHash state of the production-default mode: the index configuration (config/indexes.rs:398-406), the persisted
+  // [0x12] fingerprints, optionally the hyperplane table (SimHasher::hyperplanes(), 64 x dimension)
+  void set_simhash_config(uint32_t threshold = 43, float sampling_ratio = 0.8f, bool adaptive_enabled = true,
+                          float adaptive_failure_prob = 0.1f) {
+    hx_simhash_config c{threshold, sampling_ratio, adaptive_enabled ? 1u : 0u, adaptive_failure_prob};
+    check(hx_index_set_simhash_config(h_, &c));
+  }
+  void load_simhash(const std::vector<uint64_t>& ids, const std::vector<uint64_t>& bits) {
+    if (ids.size() != bits.size()) throw HelixDbError(HX_ERR_INVALID_PARAMETER, "one fingerprint per id");
+    check(hx_index_load_simhash(h_, ids.data(), bits.data(), ids.size()));
+  }
+  void set_simhash_planes(const std::vector<float>& planes) {
+    if (planes.size() != 64u * dim_) throw HelixDbError(HX_ERR_INVALID_DIMENSION, "hyperplane table must be 64 x dimension");
+    check(hx_index_set_simhash_planes(h_, planes.data()));
+  }
+  void compute_simhash() { check(hx_index_compute_simhash(h_)); }
+
+  // VectorIndex::search (index.rs:1578): results sorted by (score, id), at most k.  Every SearchParams is served: the
+  // strict-exhaustive specialisation and the SimHash policy modes (query fingerprint given, or projected from the planes).
+  std::vector<SearchResult> search(const std::vector<float>& query, const SearchParams& params,
+                                   const uint64_t* query_simhash = nullptr) const {
     hx_search_params p = params.raw(static_cast<uint32_t>(query.size()));
     std::vector<uint64_t> ids(params.k());
     std::vector<float> scores(params.k());
     uint32_t count = 0;
-    check(hx_search(h_, query.data(), 1, &p, ids.data(), scores.data(), &count, nullptr));
+    check(hx_search_ex(h_, query.data(), 1, &p, &params.policy(), query_simhash, ids.data(), scores.data(), &count, nullptr,
+                       nullptr));
     std::vector<SearchResult> out(count);
     for (uint32_t i = 0; i < count; ++i) out[i] = SearchResult{ids[i], scores[i]};
     return out;

@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--rows", dest="n", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=768)
-    ap.add_argument("--queries-per-step", type=int, default=8192)
+    ap.add_argument("--queries-per-step", type=int, default=32768)
     ap.add_argument("--metric", default="cosine", choices=["cosine", "euclidean"])
     ap.add_argument("--recall-queries", type=int, default=512)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -196,6 +196,8 @@ void HxScratch::destroy() {
   ring0.clear();
   ring1.clear();
   if (stream) cudaStreamDestroy(stream);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (ev_copy) cudaEventDestroy(ev_copy);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   d_queries.release(); d_qhdr.release(); d_out_scores.release();
@@ -205,7 +207,7 @@ void HxScratch::destroy() {
   d_vtab.release(); d_vpool.release(); d_vbusy.release(); d_prof.release(); d_pstats.release(); d_qsim.release();
   for (auto& m : misc) m.release();
   h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
-  h_counts.release(); h_qstats.release(); h_status.release(); h_err.release();
+  h_counts.release(); h_qstats.release(); h_status.release(); h_err.release(); h_avail.release();
 }
 
 hx_status hx_acquire_scratch(hx_index* ix, HxScratch** out) {
@@ -1075,9 +1077,24 @@ static uint32_t hnsw_smem_bytes(const hx_index* ix, uint32_t ef, uint32_t fr_cap
   return ix->ld * 4u + ef * 8u + HX_TIE_CAP * 8u + fr_cap * 8u;
 }
 
+struct HxFusedArgs {   // pipelined host-buffer search: validation inside the ring kernel, start gated on `avail`
+  const uint32_t* avail = nullptr;
+  float limit = 0.f;
+  int has_limit = 0;
+};
+
+// true when launch_hnsw will take the warp-per-query ring build for this call
+static bool hnsw_uses_ring(const hx_index* ix, size_t B) {
+  if (B < (size_t)ix->sm_count || ix->cfg.metric == HX_METRIC_MANHATTAN) return false;
+  if ((size_t)ix->ld * 8 > 160 * 1024) return false;   // a warp's query + one row slot must fit (launch_hnsw re-checks)
+  if (const char* env = getenv("HX_HNSW_IMPL")) return strcmp(env, "ring") == 0;
+  return true;
+}
+
 static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries, size_t B, uint32_t k, uint32_t ef,
                              uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts, uint32_t* d_qstats,
-                             cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1, bool* timed, uint32_t* launches) {
+                             cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1, bool* timed, uint32_t* launches,
+                             const HxFusedArgs* fused = nullptr) {
   *timed = false;
   hx_status rc = hx_finalize_graph(ix);
   if (rc) return rc;
@@ -1250,7 +1267,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     s->stamp_stride = stride;
     s->stamp_n = ix->n;
   }
-  if ((rc = s->d_err.reserve(2))) return rc;   // [0] error flags, [1] query counter of the ring build
+  if ((rc = s->d_err.reserve(4))) return rc;   // [0] error flags, [1] query counter of the ring build, [2] queries landed
   HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, 2 * sizeof(uint32_t), stream));
   rg.counter = s->d_err.p + 1;
   HxHnswArgs a{};
@@ -1269,6 +1286,18 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   a.stamp_stride = s->stamp_stride;
   a.err_flags = s->d_err.p;
   a.fr_cap = fr_cap;
+  if (fused) {
+    if (!use_ring) {
+      hx_set_error("internal: fused validation needs the ring build");
+      return HX_ERR_INVARIANT_VIOLATION;
+    }
+    a.fused_validate = 1;
+    a.q_status_w = s->d_qstatus.p;
+    a.q_hdr_w = s->d_qhdr.p;
+    a.limit = fused->limit;
+    a.has_limit = fused->has_limit;
+    a.avail = fused->avail;
+  }
   const HxDev dev = ix->dev();
   HX_CUDA(cudaEventRecord(e0, stream));
 #define HX_LAUNCH_WARP(M, MB)                                                                                      \
@@ -1395,16 +1424,56 @@ static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, 
   if ((rc = hx_acquire_scratch(ix, &s))) return rc;
   ScratchGuard guard{ix, s};
   uint32_t launches = 0;
-  if ((rc = stage_queries(ix, s, queries, B, &launches))) return rc;
+  // Large batches on the ring build are pipelined: the queries cross PCIe in chunks on a second stream, each chunk followed
+  // by a 4-byte copy that publishes how many queries have landed; the search kernel is already running, validates every
+  // query itself (no separate k_validate_and_header launch) and only waits for the chunk a query belongs to.
+  bool pipelined = B >= 1024 && hnsw_uses_ring(ix, B) && ix->n != 0 && ix->populated;
+  if (const char* env = getenv("HX_PIPELINE")) pipelined = pipelined && atoi(env) != 0;
+  HxFusedArgs fz;
+  if (pipelined) {
+    const uint32_t dim = ix->cfg.dimension;
+    if ((rc = hx_finalize_graph(ix))) return rc;
+    if (!ix->d_nbr0) pipelined = false;
+    if (pipelined) {
+      if ((rc = s->d_queries.reserve(B * (size_t)dim))) return rc;
+      if ((rc = s->d_qhdr.reserve(B))) return rc;
+      if ((rc = s->d_qstatus.reserve(B))) return rc;
+      if ((rc = s->d_err.reserve(4))) return rc;
+      if (!s->copy_stream) {
+        HX_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        HX_CUDA(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
+      }
+      const size_t chunks = 8;
+      if ((rc = s->h_avail.reserve(chunks))) return rc;
+      HX_CUDA(cudaMemsetAsync(s->d_err.p + 2, 0, sizeof(uint32_t), s->stream));
+      HX_CUDA(cudaEventRecord(s->ev_copy, s->stream));
+      HX_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_copy, 0));
+      for (size_t c = 0; c < chunks; ++c) {
+        const size_t lo = B * c / chunks, hi = B * (c + 1) / chunks;
+        if (hi == lo) continue;
+        HX_CUDA(cudaMemcpyAsync(s->d_queries.p + lo * dim, queries + lo * dim, (hi - lo) * (size_t)dim * sizeof(float),
+                                cudaMemcpyHostToDevice, s->copy_stream));
+        s->h_avail.p[c] = (uint32_t)hi;
+        HX_CUDA(cudaMemcpyAsync(s->d_err.p + 2, s->h_avail.p + c, sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+      }
+      fz.avail = s->d_err.p + 2;
+      fz.has_limit = component_limit(ix->cfg.metric, dim, &fz.limit) ? 1 : 0;
+    }
+  }
+  if (!pipelined && (rc = stage_queries(ix, s, queries, B, &launches))) return rc;
   if ((rc = s->d_out_ids.reserve(B * (size_t)k))) return rc;
   if ((rc = s->d_out_scores.reserve(B * (size_t)k))) return rc;
   if ((rc = s->d_out_counts.reserve(B))) return rc;
   const bool want_stats = p->collect_stats != 0 && stats != nullptr;
   if (want_stats && (rc = s->d_qstats.reserve(B * 4))) return rc;
   bool timed = false;
-  if ((rc = launch_hnsw(ix, s, s->d_queries.p, B, k, ef, s->d_out_ids.p, s->d_out_scores.p, s->d_out_counts.p,
-                        want_stats ? s->d_qstats.p : nullptr, s->stream, s->ev0, s->ev1, &timed, &launches)))
+  rc = launch_hnsw(ix, s, s->d_queries.p, B, k, ef, s->d_out_ids.p, s->d_out_scores.p, s->d_out_counts.p,
+                   want_stats ? s->d_qstats.p : nullptr, s->stream, s->ev0, s->ev1, &timed, &launches,
+                   pipelined ? &fz : nullptr);
+  if (rc) {
+    if (pipelined) cudaStreamSynchronize(s->copy_stream);   // do not leave copies in flight into a released scratch set
     return rc;
+  }
   if ((rc = s->h_status.reserve(B))) return rc;
   if ((rc = s->h_err.reserve(1))) return rc;
   s->h_err.p[0] = 0;

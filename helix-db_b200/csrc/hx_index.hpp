@@ -78,6 +78,8 @@ struct PinBuf {
 // concurrent searches each take a private stream + buffers; SURVEY §8b "Threading").
 struct HxScratch {
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host->device query chunks of the pipelined hx_search (created on first use)
+  cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_queries, d_qhdr, d_out_scores;
   DevBuf<uint32_t> d_qstatus, d_out_counts, d_qstats, d_err, d_epochs, d_cand_slots;
@@ -95,7 +97,7 @@ struct HxScratch {
   size_t stamp_n = 0;
   PinBuf<uint64_t> h_ids, h_cand_offsets;
   PinBuf<float> h_scores, h_queries, h_qhdr;
-  PinBuf<uint32_t> h_counts, h_qstats, h_status, h_err;
+  PinBuf<uint32_t> h_counts, h_qstats, h_status, h_err, h_avail;
   bool busy = false;
   // ring of event pairs for the device-buffer path (timed without host synchronisation)
   std::vector<cudaEvent_t> ring0, ring1;

@@ -42,6 +42,14 @@ struct HxHnswArgs {
   size_t stamp_stride;
   uint32_t* err_flags;
   uint32_t fr_cap;          // frontier capacity (>= max row length, multiple of 32)
+  // ring build, host-buffer calls: validation fused into the search (each warp validates its own query) and the search
+  // gated on `avail` (queries [0, *avail) have landed), so the kernel starts while the queries are still crossing PCIe
+  uint32_t fused_validate;
+  uint32_t* q_status_w;     // [B] written when fused_validate
+  float* q_hdr_w;           // [B]
+  float limit;
+  int32_t has_limit;
+  const uint32_t* avail;    // nullptr: everything is resident
 };
 
 // ---- sorted beam in shared memory, maintained by warp 0 -----------------------------------------------

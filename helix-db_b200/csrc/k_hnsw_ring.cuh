@@ -20,6 +20,7 @@
 //    leaves most warps idle).
 #pragma once
 #include "k_hnsw.cuh"
+#include "k_util.cuh"
 
 #define HX_VT_EMPTY 0xFFFFFFFFu
 #define HXF_VT_OVERFLOW 8u
@@ -49,6 +50,13 @@ __device__ __forceinline__ void hx_bulk_g2s_hint(void* dst_smem, const void* src
           hx_smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(hx_smem_u32(bar)), "l"(policy)
       : "memory");
+}
+
+// acquire load at system scope: the writer is the copy engine (a host-to-device copy of the availability counter)
+__device__ __forceinline__ uint32_t hx_ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // bulk prefetch of `bytes` (multiple of 16) into L2, no shared-memory destination
@@ -281,12 +289,28 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
     if (lane == 0) qi = atomicAdd(rg.counter, 1u);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= a.B) break;
-    if (a.q_status[qi] != 0u || !ix.populated) {
-      if (lane == 0) a.out_counts[qi] = 0;
-      continue;
-    }
-    q_hdr = a.q_hdr[qi];
     qg = a.queries + (size_t)qi * ix.dim;
+    if (a.avail) {   // the query may still be on its way from the host
+      if (lane == 0)
+        while (hx_ld_acquire_sys(a.avail) <= qi) __nanosleep(200);
+      __syncwarp();
+    }
+    if (a.fused_validate) {   // ValidatedMetricVector::try_new + D::new_header by the warp that owns the query
+      float h;
+      const uint32_t st = hx_validate_warp(qg, ix.dim, ix.metric, a.limit, a.has_limit, lane, &h);
+      if (lane == 0) { a.q_status_w[qi] = st; a.q_hdr_w[qi] = h; }
+      if (st != 0u || !ix.populated) {
+        if (lane == 0) a.out_counts[qi] = 0;
+        continue;
+      }
+      q_hdr = h;
+    } else {
+      if (a.q_status[qi] != 0u || !ix.populated) {
+        if (lane == 0) a.out_counts[qi] = 0;
+        continue;
+      }
+      q_hdr = a.q_hdr[qi];
+    }
     if (QCH > 0) {
 #pragma unroll
       for (int c = 0; c < (QCH > 0 ? QCH : 1); ++c) qr[c] = (uint32_t)(c * 32) + lane < ix.dim ? qg[c * 32 + lane] : 0.f;

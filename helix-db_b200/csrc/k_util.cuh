@@ -11,13 +11,9 @@
 // ValidatedMetricVector::try_new (domain.rs:113-154) for each of `count` vectors of `dim` floats with
 // row stride `ld`, plus D::new_header (cosine norm, cosine.rs:89-93). One warp per vector.
 // Check order: finiteness (first bad index) -> cosine zero norm -> magnitude (first bad index).
-static __global__ void k_validate_and_header(const float* __restrict__ v, size_t count, uint32_t dim, size_t ld, int metric,
-                                      float limit, int has_limit, float* __restrict__ hdr_out,
-                                      uint32_t* __restrict__ status_out) {
-  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t lane = threadIdx.x & 31u;
-  if (w >= count) return;
-  const float* x = v + w * ld;
+// One warp validates one vector: returns the status word, *hdr_out = the cosine norm (0 for the other metrics / on error).
+__device__ __forceinline__ uint32_t hx_validate_warp(const float* __restrict__ x, uint32_t dim, int metric, float limit,
+                                                     int has_limit, uint32_t lane, float* hdr_out) {
   uint32_t bad_fin = HX_ABSENT, bad_mag = HX_ABSENT, nonzero = 0;
   for (uint32_t i = lane; i < dim; i += 32) {
     const float c = x[i];
@@ -35,6 +31,18 @@ static __global__ void k_validate_and_header(const float* __restrict__ v, size_t
   else if (bad_mag != HX_ABSENT) st = (HX_ST_MAGNITUDE << 24) | (bad_mag & 0xffffffu);
   float h = 0.0f;
   if (metric == HXM_COSINE && st == HX_ST_OK) h = hx_cosine_norm_warp(x, dim, lane);   // st is warp-uniform
+  *hdr_out = h;
+  return st;
+}
+
+static __global__ void k_validate_and_header(const float* __restrict__ v, size_t count, uint32_t dim, size_t ld, int metric,
+                                      float limit, int has_limit, float* __restrict__ hdr_out,
+                                      uint32_t* __restrict__ status_out) {
+  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (w >= count) return;
+  float h;
+  const uint32_t st = hx_validate_warp(v + w * ld, dim, metric, limit, has_limit, lane, &h);
   if (lane == 0) {
     status_out[w] = st;
     hdr_out[w] = h;

@@ -433,6 +433,47 @@ def test_exact_ties_at_beam_boundary(gm, om, monkeypatch):
             params.collect_stats = False
 
 
+# ---- large host batches are pipelined: chunked H2D on a second stream, validation fused into the search kernel ----------
+@pytest.mark.parametrize("gm,om", METRICS[:2])
+def test_pipelined_host_search(gm, om, monkeypatch):
+    n, dim, nq = 1500, 40, 3000
+    rng = np.random.default_rng(8)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    gpu, ora = build_pair(gm, om, rows, m=8, m0=16, efc=60)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    params = hx.SearchParams.strict(5, 24)
+    oi, os_, oc, ost, _ = ora.search_batch(queries, 5, 24, threads=4)
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("HX_PIPELINE", pipe)
+        st = hx.SearchStats()
+        params.collect_stats = True
+        gi, gs, gc = gpu.search_batch(queries, params, st)
+        assert gc.tolist() == oc.tolist() and gi.tolist() == oi.tolist() and gs.tobytes() == os_.tobytes(), pipe
+        assert st.expansion_steps == ost["expansion_steps"] and st.distance_computations == ost["distance_computations"]
+        assert st.kernel_launches == (1 if pipe == "1" else 2)            # no separate validation launch when pipelined
+        bad = queries.copy()
+        bad[2711, 7] = np.nan                                              # in the last chunk
+        bad[2900, 3] = np.inf
+        with pytest.raises(hx.HelixDbError) as e:
+            gpu.search_batch(bad, params)
+        assert e.value.variant == "InvalidVectorComponent" and e.value.index == 7
+        if om == hxo.COSINE:
+            bad = queries.copy()
+            bad[17] = 0.0
+            with pytest.raises(hx.HelixDbError) as e:
+                gpu.search_batch(bad, params)
+            assert e.value.variant == "ZeroNormCosineVector"
+        else:
+            lim = hxo.component_limit(om, dim)
+            bad = queries.copy()
+            bad[1234, 39] = float(np.nextafter(np.float32(lim), np.float32(np.inf)))
+            with pytest.raises(hx.HelixDbError) as e:
+                gpu.search_batch(bad, params)
+            assert e.value.variant == "VectorComponentMagnitudeExceeded" and e.value.index == 39
+        gi2, gs2, gc2 = gpu.search_batch(queries, params)                  # the handle is healthy after an error
+        assert gi2.tolist() == oi.tolist()
+
+
 # ---- sharded path: per-shard top-k merged by (score, id) equals the unsharded exact answer ---------------------------------------
 def test_merge_topk_matches_unsharded_scan():
     import torch

@@ -1219,6 +1219,8 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     rg.pool_cap = pool_cap;
     rg.l2_hint = 1;
     if (const char* env = getenv("HX_L2_HINT")) rg.l2_hint = atoi(env) ? 1u : 0u;
+    rg.prefetch_below = ef / 2 + 1;
+    if (const char* env = getenv("HX_PREFETCH_BELOW")) { const int v = atoi(env); if (v >= 0) rg.prefetch_below = (uint32_t)v; }
     rg.batch_admit = 1;
     if (const char* env = getenv("HX_LAT_ADMIT")) rg.batch_admit = strcmp(env, "seq") == 0 ? 0u : 1u;
     rg.l2_spec = 0;   // measured: the speculative row prefetch costs more than it hides (profiles/r01_latency_*); opt-in
@@ -2397,8 +2399,8 @@ extern "C" hx_status hx_last_kernel_ms(hx_index* ix, float* ms, uint32_t* launch
     unsigned long long h[8];
     cudaDeviceSynchronize();
     if (cudaMemcpy(h, s->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
-      fprintf(stderr, "HX_PHASE_PROF cycles: pop=%llu row+deg=%llu visited+issue=%llu wait+score=%llu admit=%llu\n", h[0], h[1],
-              h[2], h[3], h[4]);
+      fprintf(stderr, "HX_PHASE_PROF cycles: pop=%llu row+deg=%llu visited+issue=%llu wait+score=%llu admit=%llu  "
+                      "predicted-next hits=%llu of %llu expansions\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
       cudaMemset(s->d_prof.p, 0, sizeof(h));
     }
   }

@@ -34,6 +34,7 @@ struct HxRingArgs {
   uint32_t* counter;     // next query index (zeroed before the launch)
   uint32_t l2_hint;      // 1: evict-first cache hint on row copies
   uint32_t batch_admit;  // 1: one-pass admission of a frontier (latency build, register beam)
+  uint32_t prefetch_below;  // warp ring build: L2-prefetch the neighbour row of an admitted entry only below this beam position
   uint32_t l2_spec;      // 1: latency build prefetches the predicted next expansion's rows into L2
   unsigned long long* prof;   // optional [8] cycle sums of the latency build's phases (HX_PHASE_PROF=1, diagnostics only)
 };
@@ -121,11 +122,13 @@ __device__ __forceinline__ int hx_vt_grow_warp(HxVisited& v, const HxRingArgs& r
 
 // ---- sorted beam, faster insertion -----------------------------------------------------------------------------------
 // Same contract as hx_beam_insert; position by one redux, the shift staged through registers 128 entries per pass.
-__device__ __forceinline__ void hx_beam_insert2(HxBeam& b, uint32_t ef, uint64_t key, uint64_t* evicted, uint32_t lane) {
+__device__ __forceinline__ void hx_beam_insert2(HxBeam& b, uint32_t ef, uint64_t key, uint64_t* evicted, uint32_t lane,
+                                                uint32_t* pos_out = nullptr) {
   const unsigned FULL = 0xffffffffu;
   uint32_t cnt = 0;
   for (uint32_t i = lane; i < b.len; i += 32) cnt += (b.a[i] < key) ? 1u : 0u;
   const uint32_t pos = __reduce_add_sync(FULL, cnt);
+  if (pos_out) *pos_out = pos;
   uint32_t end;   // entries [pos, end) move up by one
   if (b.len == ef) {
     *evicted = b.a[b.len - 1];
@@ -448,8 +451,11 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
           const uint32_t old_wmax = wmax;
           const bool was_full = beam.len == a.ef;
           uint64_t ev;
-          hx_beam_insert2(beam, a.ef, ((uint64_t)xb << 32) | ((uint64_t)xslot << 1), &ev, lane);
-          if (lane == 0) {
+          uint32_t ipos;
+          hx_beam_insert2(beam, a.ef, ((uint64_t)xb << 32) | ((uint64_t)xslot << 1), &ev, lane, &ipos);
+          // warm the neighbour row only for entries that enter the near half of the beam: those are the ones that get
+          // expanded (~100 of ~500 admissions per query); the rest would just be DRAM traffic
+          if (lane == 0 && ipos < rg.prefetch_below) {
             hx_prefetch_l2(ix.nbr0 + (size_t)xslot * ix.stride0);
             hx_prefetch_l2(ix.deg0 + xslot);
           }
@@ -880,6 +886,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
           if (prof) pt1 = clock64();
           uint32_t nb, deg, raw;
           if (cur_slot == sp_slot) {   // predicted: the row is already in registers
+            if (prof) pa[5]++;
             nb = sp_nb; deg = sp_deg; raw = sp_raw;
           } else {
             nb = row[lane];            // stride0 >= 32: in bounds; issued together with the degree
@@ -1028,8 +1035,10 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
       if (prof) { pt5 = clock64(); pa[4] += pt5 - pt4; }
       // no barrier here: only warp 0 touches the beam; the next barrier orders the reuse of frontier / fdist
     }
-    if (prof)
-      for (int i = 0; i < 5; ++i) atomicAdd(rg.prof + i, pa[i]);
+    if (prof) {
+      for (int i = 0; i < 6; ++i) atomicAdd(rg.prof + i, pa[i]);
+      atomicAdd(rg.prof + 6, (unsigned long long)st_steps);
+    }
 
     // ---- results: the beam is sorted by (score,id); take k (search.rs:994-1004,1229)
     if (warp == 0) {

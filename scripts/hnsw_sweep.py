@@ -21,7 +21,7 @@ import bench  # noqa: E402
 import helix_db_b200 as hx  # noqa: E402
 
 KNOBS = ("HX_HNSW_IMPL", "HX_RING_WARPS", "HX_RING_R", "HX_VT_CAP_LOG2", "HX_L2_HINT", "HX_TMA_WARPS", "HX_VT_POOL",
-         "HX_LAT_IMPL", "HX_LAT_WARPS", "HX_PHASE_PROF", "HX_LAT_SPEC", "HX_LAT_ADMIT", "HX_POL_QCH", "HX_POL_WARPS", "HX_POL_MINR", "HX_POL_EARLY_SIM")
+         "HX_LAT_IMPL", "HX_LAT_WARPS", "HX_PHASE_PROF", "HX_LAT_SPEC", "HX_LAT_ADMIT", "HX_POL_QCH", "HX_POL_WARPS", "HX_POL_MINR", "HX_POL_EARLY_SIM", "HX_PREFETCH_BELOW", "HX_PIPELINE")
 DEFAULT_VARIANTS = [
     ("tma12", {"HX_HNSW_IMPL": "tma"}),
     ("ring16", {}),

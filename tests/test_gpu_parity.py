@@ -374,18 +374,24 @@ def test_traversal_builds_agree(gm, om, dim, monkeypatch):
             assert getattr(st, f) == ost[f], (f, env)
     # small batches (B < #SMs) take the CTA-per-query builds: ring (visited set in shared memory) vs first generation
     nsmall = 40
+    _, _, _, sst, _ = ora.search_batch(queries[:nsmall], k, ef, threads=4)
+    small_stats = (sst["expansion_steps"], sst["neighbors_examined"], sst["distance_computations"])
     for env in [{}, {"HX_LAT_IMPL": "tma"}, {"HX_LAT_IMPL": "ldg"}, {"HX_VT_CAP_LOG2": "6"}, {"HX_RING_R": "3"},
-                {"HX_LAT_WARPS": "3", "HX_L2_HINT": "0"}]:
-        for key in ("HX_HNSW_IMPL", "HX_LAT_IMPL", "HX_VT_CAP_LOG2", "HX_RING_WARPS", "HX_RING_R", "HX_L2_HINT", "HX_LAT_WARPS"):
+                {"HX_LAT_WARPS": "3", "HX_L2_HINT": "0"}, {"HX_LAT_SPEC": "0"}, {"HX_LAT_WARPS": "1"},
+                {"HX_LAT_ADMIT": "seq", "HX_VT_CAP_LOG2": "7"}]:
+        for key in ("HX_HNSW_IMPL", "HX_LAT_IMPL", "HX_VT_CAP_LOG2", "HX_RING_WARPS", "HX_RING_R", "HX_L2_HINT", "HX_LAT_WARPS",
+                    "HX_LAT_SPEC", "HX_LAT_ADMIT"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
-        gi, gs, gc = gpu.search_batch(queries[:nsmall], params)
+        st = hx.SearchStats()
+        gi, gs, gc = gpu.search_batch(queries[:nsmall], params, st)
         assert gc.tolist() == oc[:nsmall].tolist(), env
         assert gi.tolist() == oi[:nsmall].tolist(), env
         assert gs.tobytes() == os_[:nsmall].tobytes(), env
-    monkeypatch.delenv("HX_LAT_WARPS", raising=False)
-    monkeypatch.delenv("HX_L2_HINT", raising=False)
+        assert (st.expansion_steps, st.neighbors_examined, st.distance_computations) == small_stats, env
+    for key in ("HX_LAT_WARPS", "HX_L2_HINT", "HX_LAT_SPEC", "HX_LAT_ADMIT", "HX_VT_CAP_LOG2"):
+        monkeypatch.delenv(key, raising=False)
     # beams wider than 128 entries take the shared-memory beam of the latency build (the register beam holds 4 x 32)
     wi, ws, wc, _, _ = ora.search_batch(queries[:nsmall], k, 200, threads=4)
     gi, gs, gc = gpu.search_batch(queries[:nsmall], hx.SearchParams.strict(k, 200))

@@ -1172,28 +1172,17 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     else ring_wstride = round_up((uint32_t)(fixed0 + (size_t)ring_R * (rowbytes + 8)), 128);
   }
   size_t cta_ring_smem = 0;
-  uint32_t cta_RCB = 0;   // row slots of the lookahead bank
   if (use_cta_ring) {
-    // rows in flight first (up to 32), then the largest visited table that still fits (at least 1024 entries), then the
-    // lookahead bank with whatever is left (at least 8 slots, else no lookahead)
-    const size_t fixed0 = (ring_qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 8 + 8 + 256 + 256;
+    // rows in flight first (up to 32), then the largest visited table that still fits (at least 1024 entries)
+    const size_t fixed0 = (ring_qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 8 + 256;
     cta_vt_cap = vt_cap;
     while (cta_vt_cap > 1024 && fixed0 + (size_t)cta_vt_cap * 4 + 8 * (rowbytes + 8) > ring_budget) cta_vt_cap >>= 1;
     if (fixed0 + (size_t)cta_vt_cap * 4 + rowbytes + 8 > ring_budget) {
       use_cta_ring = false;
     } else {
-      bool spec = ix->stride0 == 32;   // lookahead: every frontier (<= 32 rows) must fit the second bank
-      if (const char* env = getenv("HX_LAT_SPEC")) spec = spec && atoi(env) != 0;
-      const size_t avail_rows = (ring_budget - fixed0 - (size_t)cta_vt_cap * 4) / (rowbytes + 8);
-      if (spec && avail_rows >= 32 + 12) {   // bank B = 32 slots, bank A = what is left (>= 12; larger frontiers take two passes)
-        cta_RCB = 32;
-        ring_R = (uint32_t)std::min<size_t>(32, avail_rows - 32);
-      } else {
-        ring_R = (uint32_t)std::min<size_t>(32, avail_rows);
-      }
+      ring_R = (uint32_t)std::min<size_t>(32, (ring_budget - fixed0 - (size_t)cta_vt_cap * 4) / (rowbytes + 8));
       if (const char* env = getenv("HX_RING_R")) { const int v = atoi(env); if (v >= 1 && v <= 32) ring_R = std::min(ring_R, (uint32_t)v); }
-      const size_t used = fixed0 + (size_t)cta_vt_cap * 4 + (size_t)ring_R * (rowbytes + 8);
-      cta_ring_smem = used - 256 + (size_t)cta_RCB * (rowbytes + 8);
+      cta_ring_smem = fixed0 - 256 + (size_t)cta_vt_cap * 4 + (size_t)ring_R * (rowbytes + 8);
       cta_warps = ring_qch == 48 ? 8 : 12;
       if (const char* env = getenv("HX_LAT_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= (int)cta_warps) cta_warps = (uint32_t)v; }
     }
@@ -1234,11 +1223,12 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     if (const char* env = getenv("HX_PREFETCH_BELOW")) { const int v = atoi(env); if (v >= 0) rg.prefetch_below = (uint32_t)v; }
     rg.batch_admit = 1;
     if (const char* env = getenv("HX_LAT_ADMIT")) rg.batch_admit = strcmp(env, "seq") == 0 ? 0u : 1u;
-    rg.l2_spec = cta_RCB ? 1u : 0u;   // latency build: lookahead into the second bank of row slots
+    rg.l2_spec = 0;   // measured: the speculative row prefetch costs more than it hides (profiles/r01_latency_*); opt-in
+    if (const char* env = getenv("HX_LAT_SPEC")) rg.l2_spec = atoi(env) ? 1u : 0u;
     if (const char* env = getenv("HX_PHASE_PROF")) {   // diagnostics: cycle sums per phase of the latency build
       if (atoi(env)) {
-        if ((rc = s->d_prof.reserve(12))) return rc;
-        if (!s->prof_init) { HX_CUDA(cudaMemsetAsync(s->d_prof.p, 0, 12 * sizeof(unsigned long long), stream)); s->prof_init = true; }
+        if ((rc = s->d_prof.reserve(8))) return rc;
+        if (!s->prof_init) { HX_CUDA(cudaMemsetAsync(s->d_prof.p, 0, 8 * sizeof(unsigned long long), stream)); s->prof_init = true; }
         rg.prof = s->d_prof.p;
       }
     }
@@ -1331,7 +1321,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_cta_ring<M, Q, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  (int)smem_launch));                                                               \
     k_hnsw_search_cta_ring<M, Q, NBV><<<grid, cta_warps * 32, smem_launch, stream>>>(dev, a, rg, ring_R,           \
-                                                                                     cta_vt_cap, cta_RCB);         \
+                                                                                     cta_vt_cap);                  \
   } while (0)
 #define HX_LAUNCH_CTA_RING(M, Q)                                                                                   \
   do {                                                                                                             \
@@ -1393,10 +1383,6 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
 static hx_status check_device_flags(uint32_t flags) {
   if (flags & HXF_INVALID_SCORE) {
     hx_set_error("vector distance kernel emitted an invalid score");   // model.rs:21-28
-    return HX_ERR_INVARIANT_VIOLATION;
-  }
-  if (flags & HXF_BEAM_CAPACITY) {
-    hx_set_error("lookahead frontier disagreed with the visited set");
     return HX_ERR_INVARIANT_VIOLATION;
   }
   if (flags & HXF_VT_OVERFLOW) {
@@ -2410,12 +2396,11 @@ extern "C" hx_status hx_last_kernel_ms(hx_index* ix, float* ms, uint32_t* launch
     ix->last_kernel_launches = cnt;
   }
   if (s && s->prof_init && s->d_prof.p) {   // HX_PHASE_PROF diagnostics: print and reset the phase cycle sums
-    unsigned long long h[12];
+    unsigned long long h[8];
     cudaDeviceSynchronize();
     if (cudaMemcpy(h, s->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
       fprintf(stderr, "HX_PHASE_PROF cycles: pop=%llu row+deg=%llu visited+issue=%llu wait+score=%llu admit=%llu  "
-                      "predicted-next hits=%llu of %llu expansions; lookahead(warp 1): row+probe=%llu issue+hdr=%llu; warp 0 at "
-                      "sync A=%llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+                      "predicted-next hits=%llu of %llu expansions\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
       cudaMemset(s->d_prof.p, 0, sizeof(h));
     }
   }

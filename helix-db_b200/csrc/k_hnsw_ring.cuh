@@ -65,10 +65,6 @@ __device__ __forceinline__ void hx_bulk_prefetch_l2(const void* src_gmem, uint32
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ void hx_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hx_smem_u32(bar)) : "memory");
-}
-
 // ---- visited hash set --------------------------------------------------------------------------------------------------
 struct HxVisited {
   uint32_t* tab;
@@ -692,49 +688,33 @@ __device__ __forceinline__ bool hx_vt_test_and_set_smem(uint32_t tab_s32, uint32
 
 // ---- CTA-per-query, ring-staged rows (latency build, B < #SMs) -----------------------------------------------------------
 // One CTA owns the query.  Warp 0 walks the beam — held in its REGISTERS (NB x 32 entries; NB = 0: shared memory, any
-// ef): pops the nearest unexpanded entry, reads its neighbour row (L2: prefetched when the entry was admitted),
-// tests-and-sets the visited hash set — in SHARED memory, so the visited filter costs no global round trip — every warp
-// w then issues the bulk copies of the rows it will reduce (rows w, w+W, ...; one mbarrier per row, the query in
-// registers), reduces them as they land, and warp 0 admits the scores in neighbour-id order (one pass).
-//
-// Lookahead: while warp 0 admits expansion i, warp 1 already prepares expansion i+1 for the entry that will most likely
-// be popped next (the nearest unexpanded entry as the beam stood before the admission: right 78 % of the time on the C2
-// corpus): it reads that entry's neighbour row, probes the visited set READ-ONLY (nothing is marked — marking early
-// would hide nodes from the expansions in between), and starts the bulk copies of the unvisited neighbours into a second
-// bank of row slots, so their DRAM round trip overlaps the admission.  If the next pop is the predicted entry, its
-// frontier is exactly that list (the visited set did not change in between): warp 0 only marks it and the rows are
-// already in shared memory; otherwise the bank is drained and the expansion proceeds as usual.  Results, scores and
-// counters are bit-identical either way (the same nodes are scored in the same order).
+// ef): pops the nearest unexpanded entry, reads its neighbour row (L2: prefetched when the entry was admitted; the row of
+// the entry most likely to be popped next is already loaded while the current frontier is being scored), and
+// tests-and-sets the visited hash set — in SHARED memory, so the visited filter costs no global round trip.  Then every
+// warp w issues the bulk copies of the rows it will reduce (rows w, w+W, ...; one mbarrier per row, the query in
+// registers), reduces them as they land, and warp 0 admits the scores in neighbour-id order.  Bit-identical to every
+// other build.
 #define HX_CTA_RING_MAX_THREADS 384
 template <int METRIC, int QCH, int NB>
 __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
-    k_hnsw_search_cta_ring(HxDev ix, HxHnswArgs a, HxRingArgs rg, uint32_t RC, uint32_t vt_smem_cap, uint32_t RCB) {
+    k_hnsw_search_cta_ring(HxDev ix, HxHnswArgs a, HxRingArgs rg, uint32_t RC, uint32_t vt_smem_cap) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* sq = reinterpret_cast<float*>(smem);                                            // [ld] when QCH == 0
-  float* ring = sq + (QCH == 0 ? ix.ld : 0u);                                            // [RC][ld]   bank A
-  float* ringB = ring + (size_t)RC * ix.ld;                                              // [RCB][ld]  bank B (lookahead)
-  uint64_t* beam_mem = reinterpret_cast<uint64_t*>(ringB + (size_t)RCB * ix.ld);        // [ef] beam (NB == 0) / merge stage
+  float* ring = sq + (QCH == 0 ? ix.ld : 0u);                                            // [RC][ld]
+  uint64_t* beam_mem = reinterpret_cast<uint64_t*>(ring + (size_t)RC * ix.ld);          // [ef] beam (NB == 0) / merge stage
   uint64_t* tie = beam_mem + a.ef;                                                       // [HX_TIE_CAP]
   uint64_t* bars = tie + HX_TIE_CAP;                                                     // [RC]
-  uint64_t* barsB = bars + RC;                                                           // [RCB]
-  uint32_t* frontier = reinterpret_cast<uint32_t*>(barsB + RCB + 1);                     // [fr_cap]
+  uint32_t* frontier = reinterpret_cast<uint32_t*>(bars + RC);                           // [fr_cap]
   float* fdist = reinterpret_cast<float*>(frontier + a.fr_cap);                         // [fr_cap]
-  uint32_t* sp_list = reinterpret_cast<uint32_t*>(fdist + a.fr_cap);                    // [32]
-  float* sp_hdr = reinterpret_cast<float*>(sp_list + 32);                                // [32]
-  uint32_t* vts = reinterpret_cast<uint32_t*>(sp_hdr + 32);                              // [vt_smem_cap]
-  __shared__ uint32_t s_nf, s_cur, s_done, s_changed, s_useB;
-  __shared__ uint32_t s_sp_pred, s_sp_cnt, s_sp_raw, s_sp_issued;
-  __shared__ uint32_t* s_vt_tab;
-  __shared__ uint32_t s_vt_mask, s_vt_shift;
+  uint32_t* vts = reinterpret_cast<uint32_t*>(fdist + a.fr_cap);                        // [vt_smem_cap]
+  __shared__ uint32_t s_nf, s_cur, s_done, s_changed;
   __shared__ float s_cur_dist;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, W = blockDim.x >> 5;
   const unsigned FULL = 0xffffffffu;
   const uint32_t rowbytes = ix.ld * 4u;
   const uint64_t policy = hx_policy_evict_first();
-  const bool lookahead = rg.l2_spec != 0 && RCB >= 32 && W >= 2 && ix.stride0 == 32;   // every frontier fits bank B
-  uint32_t ph = 0, phB = 0;   // phase parity of every row slot's mbarrier (bank A / bank B), identical in all threads
+  uint32_t ph = 0;   // phase parity of every row slot's mbarrier, identical in all threads
   if (tid < RC) hx_mbar_init(bars + tid, 1);
-  if (tid < RCB) hx_mbar_init(barsB + tid, 1);
   hx_fence_mbar_init();
   __syncthreads();
 
@@ -744,7 +724,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
 
   // all threads: reduce list[0..cnt) (shared memory, visible to every warp) into fdist.  Warp w owns slots and rows
   // w, w+W, ...: it issues their copies itself (lane j -> its j-th row), so a slot is only ever touched by one warp.
-  auto score_list = [&](const uint32_t* list, uint32_t cnt) {
+  auto score_list = [&](const uint32_t* list, uint32_t cnt, auto&& after_issue) {
     for (uint32_t base = 0; base < cnt; base += RC) {
       const uint32_t rows = min(RC, cnt - base);
       const uint32_t mine = lane * W + warp;   // the row this lane issues
@@ -756,6 +736,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
         else hx_bulk_g2s(ring + (size_t)mine * ix.ld, ix.vec + (size_t)slot * ix.ld, rowbytes, bars + mine);
         if (METRIC == HXM_COSINE) rh = __ldg(ix.hdr + slot);
       }
+      if (base == 0) after_issue();   // work that may overlap the copies' flight (warp 0: speculative L2 prefetch)
       uint32_t j = 0;
       for (uint32_t r = warp; r < rows; r += W, ++j) {
         const float row_hdr = __shfl_sync(FULL, rh, j);
@@ -766,24 +747,6 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
       ph ^= rows >= 32u ? FULL : ((1u << rows) - 1u);
       __syncthreads();   // scores visible to warp 0 (and `list` free to be rewritten)
     }
-  };
-  // bank B: rows 0..cnt-1 were started by the lookahead; `consume` = reduce them (else only retire their barriers)
-  auto take_bankB = [&](uint32_t cnt, bool consume) {
-    float rh = 0.f;   // lane j: header of this warp's j-th row (requested before the first wait)
-    if (consume && METRIC == HXM_COSINE) {
-      const uint32_t mine = lane * W + warp;
-      if (mine < cnt) rh = __ldg(ix.hdr + sp_list[mine]);
-    }
-    uint32_t j = 0;
-    for (uint32_t r = warp; r < cnt; r += W, ++j) {
-      const float row_hdr = __shfl_sync(FULL, rh, j);
-      hx_mbar_wait(barsB + r, (phB >> r) & 1u);
-      if (consume) {
-        const float sc = hx_warp_score<METRIC, QCH>(ringB + (size_t)r * ix.ld, qr, sq, qg, q_hdr, row_hdr, ix.dim, lane);
-        if (lane == 0) fdist[r] = sc;
-      }
-    }
-    phB ^= cnt >= 32u ? FULL : ((1u << cnt) - 1u);
   };
 
   for (uint32_t qi = blockIdx.x; qi < a.B; qi += gridDim.x) {
@@ -800,19 +763,15 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
       for (uint32_t i = tid; i < ix.ld; i += blockDim.x) sq[i] = i < ix.dim ? qg[i] : 0.0f;
     }
     for (uint32_t i = tid; i < vt_smem_cap; i += blockDim.x) vts[i] = HX_VT_EMPTY;
-    HxVisited vt = hx_vt_make(vts, vt_smem_cap);   // warp 0's copy is the live one; the lookahead reads the s_vt_* mirror
+    HxVisited vt = hx_vt_make(vts, vt_smem_cap);   // warp 0's copy is the live one
     const uint32_t vts_s32 = hx_smem_u32(vts);
     int pool_idx = -1;
-    if (tid == 0) {
-      s_vt_tab = vts; s_vt_mask = vt.mask; s_vt_shift = vt.shift;
-      s_sp_pred = HX_ABSENT; s_sp_cnt = 0; s_sp_raw = 0; s_sp_issued = 0; s_useB = 0;
-    }
 
     // ---- entry point
     uint32_t cur = ix.entry_slot;
     if (tid == 0) frontier[0] = cur;
     __syncthreads();
-    score_list(frontier, 1);
+    score_list(frontier, 1, [] {});
     float cur_dist = fdist[0];
     if (tid == 0 && !hx_score_ok(cur_dist)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
     uint32_t upper_steps = 0;
@@ -831,7 +790,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
           }
         }
         __syncthreads();
-        score_list(frontier, deg);
+        score_list(frontier, deg, [] {});
         if (warp == 0) {
           float best = cur_dist;
           uint32_t best_i = HX_ABSENT;
@@ -873,8 +832,8 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
     uint32_t tie_len = 0, dropped = 0;
     uint32_t st_steps = 0, st_examined = 0, st_dc = 1;
     bool failed = false;
-    bool spec_round = false;                   // a lookahead ran at the end of the previous expansion (uniform)
-    uint32_t pred_prev = HX_ABSENT;            // warp 0: the entry that lookahead prepared
+    // speculative neighbour row: the row of the entry predicted to be popped next, loaded during the scoring phase
+    uint32_t sp_slot = HX_ABSENT, sp_nb = 0, sp_deg = 0, sp_raw = 0;
     if (warp == 0) {
       const uint64_t key0 = hx_make_key(cur_dist, cur << 1);
       if (NB > 0) {
@@ -921,31 +880,29 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
         } else if (dropped) {
           st_steps++;
         }
-        // a lookahead hit: the previous round prepared exactly this entry (rows of degree <= 32 only, so the guess is the
-        // whole condition and warp 0 never has to wait for the other warps' result)
-        bool hit = spec_round && cur_slot != HX_ABSENT && cur_slot == pred_prev;
         uint32_t nf = 0;
         if (cur_slot != HX_ABSENT) {
           const uint32_t* row = ix.nbr0 + (size_t)cur_slot * ix.stride0;
           if (prof) pt1 = clock64();
-          uint32_t nb = 0, deg = 32u;   // on a hit the degree is not known here: 32 is its bound (stride0 == 32)
-          if (!hit) {
+          uint32_t nb, deg, raw;
+          if (cur_slot == sp_slot) {   // predicted: the row is already in registers
+            if (prof) pa[5]++;
+            nb = sp_nb; deg = sp_deg; raw = sp_raw;
+          } else {
             nb = row[lane];            // stride0 >= 32: in bounds; issued together with the degree
             deg = ix.deg0[cur_slot];
-            st_examined += ix.raw0[cur_slot];
+            raw = ix.raw0[cur_slot];
           }
+          st_examined += raw;
           if (st_dc + deg > vt.limit) {
             if (pool_idx >= 0 || (pool_idx = hx_vt_grow_warp(vt, rg, lane)) < 0) {
               if (lane == 0) atomicOr(a.err_flags, HXF_VT_OVERFLOW);
               failed = true;
               cur_slot = HX_ABSENT;
-              hit = false;
-            } else if (lane == 0) {
-              s_vt_tab = vt.tab; s_vt_mask = vt.mask; s_vt_shift = vt.shift;
             }
           }
           if (prof) { pt2 = clock64(); pa[0] += pt1 - pt0; pa[1] += pt2 - pt1; }
-          if (!failed && !hit) {
+          if (!failed) {
             for (uint32_t base = 0; base < deg; base += 32) {
               const uint32_t i = base + lane;
               if (base) nb = i < deg ? row[i] : 0u;
@@ -956,112 +913,57 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
               nf += __popc(mask);
             }
             st_dc += nf;
-          }
-          if (prof && !failed) { pt3 = clock64(); pa[2] += pt3 - pt2; }
-        }
-        // -- predict the next pop for this round's lookahead: the nearest unexpanded entry as the beam stands now
-        uint32_t pred = HX_ABSENT;
-        if (lookahead && cur_slot != HX_ABSENT) {
-          uint32_t pf;
-          if (NB > 0) pf = hx_rbeam_first_unexpanded(rb);
-          else pf = hx_beam_first_unexpanded(beam_mem, beam.len, lane);
-          if (pf != HX_ABSENT) {
-            const uint64_t pk = NB > 0 ? hx_rbeam_get(rb, pf) : beam_mem[pf];
-            pred = (uint32_t)(pk & 0xffffffffu) >> 1;
+            if (prof) { pt3 = clock64(); pa[2] += pt3 - pt2; }
           }
         }
-        pred_prev = pred;
         if (lane == 0) {
           s_nf = nf;
           s_done = (cur_slot == HX_ABSENT) ? 1u : 0u;
-          s_useB = hit ? 1u : 0u;
-          s_sp_pred = pred;
         }
       }
-      long long ps0 = 0;
-      if (prof) ps0 = clock64();
       __syncthreads();
-      if (prof) atomicAdd(rg.prof + 9, (unsigned long long)(clock64() - ps0));
-      const bool useB = s_useB != 0u;
-      if (spec_round && !useB) {   // rows of a wrong guess (or of the last round) still have to be retired
-        const uint32_t stale = s_sp_issued;
-        if (stale) take_bankB(stale, false);
-      }
       if (s_done) break;
-      uint32_t nf;
-      if (useB) {
-        nf = s_sp_cnt;
-        if (warp == 0) {
-          // the unvisited neighbours were listed (in row order) against the same visited set — nothing was marked in
-          // between — so this is exactly the frontier: mark it now
-          if (prof) pa[5]++;
-          if (lane < nf) {
-            const uint32_t x = sp_list[lane];
-            const bool fresh = pool_idx < 0 ? hx_vt_test_and_set_smem(vts_s32, vt.mask, vt.shift, x) : hx_vt_test_and_set(vt, x);
-            if (!fresh) atomicOr(a.err_flags, HXF_BEAM_CAPACITY);
-            frontier[lane] = x;
-          }
-          st_examined += s_sp_raw;
-          st_dc += nf;
-          if (prof) { pt3 = clock64(); pa[2] += pt3 - pt2; }
+      const uint32_t nf = s_nf;
+      if (warp == 0) {
+        // predict the next pop: the first unexpanded entry as the beam stands now (right unless a new score beats it)
+        uint32_t pf;
+        if (NB > 0) pf = hx_rbeam_first_unexpanded(rb);
+        else pf = hx_beam_first_unexpanded(beam_mem, beam.len, lane);
+        sp_slot = HX_ABSENT;
+        if (pf != HX_ABSENT) {
+          const uint64_t pk = NB > 0 ? hx_rbeam_get(rb, pf) : beam_mem[pf];
+          sp_slot = (uint32_t)(pk & 0xffffffffu) >> 1;
+          sp_nb = ix.nbr0[(size_t)sp_slot * ix.stride0 + lane];
+          sp_deg = ix.deg0[sp_slot];
+          sp_raw = ix.raw0[sp_slot];
         }
-        take_bankB(nf, true);
-        __syncthreads();
-      } else {
-        nf = s_nf;
-        score_list(frontier, nf);
       }
-      if (prof) { pt4 = clock64(); pa[3] += pt4 - pt3; }
-      // -- warps 1..W-1: lookahead for the predicted next expansion, overlapping warp 0's admission.  Every warp derives
-      //    the same list from the same row and the same (currently quiescent) visited set and starts its share of the copies.
-      if (lookahead && warp >= 1) {
-        const bool prof1 = rg.prof != nullptr && tid == 32;
-        long long lt0 = 0, lt1 = 0, lt2 = 0;
-        if (prof1) lt0 = lt1 = clock64();
-        // warp 1 reads the predicted entry's row and probes the (currently quiescent) visited set; the list goes through
-        // shared memory to the other warps, which meet on named barrier 1 and start their share of the copies
-        if (warp == 1) {
-          const uint32_t p = s_sp_pred;
-          uint32_t cnt = 0, raw = 0;
-          if (p != HX_ABSENT) {
-            const uint32_t nb = ix.nbr0[(size_t)p * ix.stride0 + lane];
-            const uint32_t deg = ix.deg0[p];   // <= 32 (stride0 == 32)
-            raw = ix.raw0[p];
-            bool fresh = false;
-            if (lane < deg) {   // read-only probe
-              const uint32_t* tab = s_vt_tab;
-              const uint32_t vmask = s_vt_mask;
-              uint32_t h = (nb * 2654435761u) >> s_vt_shift;
-              fresh = true;
-              for (;;) {
-                const uint32_t e = ((volatile const uint32_t*)tab)[h];
-                if (e == HX_VT_EMPTY) break;
-                if (e == nb) { fresh = false; break; }
-                h = (h + 1u) & vmask;
-              }
+      score_list(frontier, nf, [&] {
+        // Rows of the predicted next expansion: start pulling its unvisited neighbours' vectors into L2 now, while this
+        // frontier is in flight / being reduced.  Read-only probe of the visited set; a wrong guess only costs bandwidth.
+        if (warp == 0 && rg.l2_spec && sp_slot != HX_ABSENT && lane < sp_deg) {
+          bool vis;
+          if (pool_idx < 0) {
+            uint32_t h = (sp_nb * 2654435761u) >> vt.shift;
+            for (;;) {
+              const uint32_t cur_e = ((volatile uint32_t*)vts)[h];
+              if (cur_e == HX_VT_EMPTY) { vis = false; break; }
+              if (cur_e == sp_nb) { vis = true; break; }
+              h = (h + 1u) & vt.mask;
             }
-            const uint32_t mask = __ballot_sync(FULL, fresh);
-            cnt = (uint32_t)__popc(mask);
-            if (fresh) sp_list[__popc(mask & ((1u << lane) - 1u))] = nb;
+          } else {
+            uint32_t h = (sp_nb * 2654435761u) >> vt.shift;
+            for (;;) {
+              const uint32_t cur_e = ((volatile uint32_t*)vt.tab)[h];
+              if (cur_e == HX_VT_EMPTY) { vis = false; break; }
+              if (cur_e == sp_nb) { vis = true; break; }
+              h = (h + 1u) & vt.mask;
+            }
           }
-          if (lane == 0) { s_sp_cnt = cnt; s_sp_raw = raw; s_sp_issued = cnt; }
+          if (!vis) hx_bulk_prefetch_l2(ix.vec + (size_t)sp_nb * ix.ld, rowbytes);
         }
-        if (prof1) lt1 = clock64();
-        asm volatile("bar.sync 1, %0;" ::"r"((W - 1u) * 32u) : "memory");
-        {
-          const uint32_t cnt = s_sp_cnt;
-          const uint32_t j = lane * (W - 1u) + (warp - 1u);   // this lane's row of the list
-          if (j < cnt) {
-            const uint32_t nb = sp_list[j];
-            hx_mbar_expect_tx(barsB + j, rowbytes);
-            if (rg.l2_hint) hx_bulk_g2s_hint(ringB + (size_t)j * ix.ld, ix.vec + (size_t)nb * ix.ld, rowbytes, barsB + j, policy);
-            else hx_bulk_g2s(ringB + (size_t)j * ix.ld, ix.vec + (size_t)nb * ix.ld, rowbytes, barsB + j);
-            if (METRIC == HXM_COSINE) hx_prefetch_l2(ix.hdr + nb);   // read by the consumer (an L2 hit by then)
-          }
-        }
-        if (prof1) { lt2 = clock64(); atomicAdd(rg.prof + 7, (unsigned long long)(lt1 - lt0)); atomicAdd(rg.prof + 8, (unsigned long long)(lt2 - lt1)); }
-      }
-      spec_round = lookahead;
+      });
+      if (prof) { pt4 = clock64(); pa[3] += pt4 - pt3; }
       // -- admit in neighbour-id order (search.rs:934-953)
       if (warp == 0) {
         for (uint32_t base = 0; base < nf; base += 32) {
@@ -1084,7 +986,6 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
             if ((am >> lane) & 1u) {   // warm the rows we will need if these candidates are expanded
               hx_prefetch_l2(ix.nbr0 + (size_t)myslot * ix.stride0);
               hx_prefetch_l2(ix.deg0 + myslot);
-              hx_prefetch_l2(ix.raw0 + myslot);
             }
             continue;
           }
@@ -1109,7 +1010,6 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
             if (lane == 0) {   // warm the row we will need if this candidate is expanded
               hx_prefetch_l2(ix.nbr0 + (size_t)xslot * ix.stride0);
               hx_prefetch_l2(ix.deg0 + xslot);
-              hx_prefetch_l2(ix.raw0 + xslot);
             }
             if (was_full) {
               const uint32_t new_wmax = NB > 0 ? wmax : (uint32_t)(beam_mem[beam.len - 1] >> 32);

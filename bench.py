@@ -476,8 +476,8 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4,
                     "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 4 + 4,
                     "api": "hx_search (C ABI, pinned host buffers, blocking)"},
-            "gpu_launches": args.steps * 2,
-            "launches_per_step": {"k_validate_and_header": 1, hnsw_kernel: 1},
+            "gpu_launches": args.steps * (1 if impl == "ring" else 2),
+            "launches_per_step": ({hnsw_kernel: 1} if impl == "ring" else {"k_validate_and_header": 1, hnsw_kernel: 1}),
             "roofline": {"bound": "hbm", "kernel": hnsw_kernel, "achieved": round(achieved, 1), "peak": hbm_peak,
                          "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_hnsw_search", {"queries": Q, "rows": n, "dim": dim, "ef": EF}),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_per_launch),

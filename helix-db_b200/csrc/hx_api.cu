@@ -1533,14 +1533,28 @@ extern "C" hx_status hx_search_device(hx_index* ix, const float* d_queries, size
   if ((rc = dev_scratch(ix, &s))) return rc;
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   uint32_t launches = 0;
-  if ((rc = prepare_device_queries(ix, s, d_queries, B, stream, &launches))) return rc;
+  // the ring build validates each query itself (ValidatedMetricVector::try_new + header by the warp that owns it): no
+  // separate k_validate_and_header launch in front of it
+  HxFusedArgs fz;
+  bool fused = false;
+  if (hnsw_uses_ring(ix, B) && ix->n != 0 && ix->populated) {
+    if ((rc = hx_finalize_graph(ix))) return rc;
+    fused = ix->d_nbr0 != nullptr;
+  }
+  if (fused) {
+    if ((rc = s->d_qhdr.reserve(B))) return rc;
+    if ((rc = s->d_qstatus.reserve(B))) return rc;
+    fz.has_limit = component_limit(ix->cfg.metric, ix->cfg.dimension, &fz.limit) ? 1 : 0;
+  } else if ((rc = prepare_device_queries(ix, s, d_queries, B, stream, &launches))) {
+    return rc;
+  }
   const bool want_stats = p->collect_stats != 0 && stats != nullptr;
   if (want_stats && (rc = s->d_qstats.reserve(B * 4))) return rc;
   cudaEvent_t e0, e1;
   if ((rc = s->ring_next(&e0, &e1))) return rc;
   bool timed = false;
   if ((rc = launch_hnsw(ix, s, d_queries, B, k, ef, d_out_ids, d_out_scores, d_out_counts,
-                        want_stats ? s->d_qstats.p : nullptr, stream, e0, e1, &timed, &launches)))
+                        want_stats ? s->d_qstats.p : nullptr, stream, e0, e1, &timed, &launches, fused ? &fz : nullptr)))
     return rc;
   if (!timed && s->ring_pending) s->ring_pending--;
   if (want_stats) {   // stats need a sync; the throughput path leaves collect_stats = 0

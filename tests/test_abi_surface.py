@@ -59,3 +59,21 @@ def test_product_path_fails_loudly_without_cuda():
     with pytest.raises(hx.HelixDbError) as e:
         hx.VectorIndex(hx.Metric.Euclidean, hx.VectorIndexConfig("t", "embedding", 8))
     assert e.value.code == hx.HX_ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_policy_defaults_and_order_code_without_a_device():
+    import ctypes as C
+    lib = hx.load_library()
+    p = hx._PolicyParams()
+    lib.hx_policy_params_default(C.byref(p))                 # SearchParams::new (mod.rs:482-500)
+    assert (p.bypass_min_frontier, p.bypass_window_expansions, p.read_budget_multiplier) == (24, 4, 3)
+    assert abs(p.bypass_min_filter_rate - 0.12) < 1e-7 and p.sampling_ratio_override < 0 and p.failure_prob_override < 0
+    assert lib.hx_order_code_from_simhash_bits(0) == 0       # simhash.rs:313-330
+    assert lib.hx_order_code_from_simhash_bits(2**64 - 1) == 2**64 - 1
+    for shift, bit in ((63, 63), (47, 62), (31, 61), (15, 60)):
+        assert lib.hx_order_code_from_simhash_bits(1 << shift) == 1 << bit
+    sp = hx.SearchParams.new(10)
+    assert sp.requires_query_simhash() and sp._c().pre_sampling_ratio < 0          # Option::None travels as a negative
+    assert not hx.SearchParams.strict(10).requires_query_simhash()
+    t = hx.SearchParams.throughput_profile_floor_92(10)
+    assert t.ef() == 48 and abs(t._c().pre_sampling_ratio - 0.20) < 1e-7

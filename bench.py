@@ -364,6 +364,8 @@ def run_ours(args):
     # (the fingerprints are data to the kernel either way).  Host buffers through hx_search_ex, fingerprints of the queries
     # projected on the device inside the timed region.
     default_mode = None
+    default_planes = None
+    d_ids_first = None
     if not args.no_default_mode and args.metric == "cosine":
         planes = np.random.default_rng(42).standard_normal((64, dim)).astype(np.float32)
         ix.set_simhash_planes(planes)
@@ -374,6 +376,7 @@ def run_ours(args):
         pnew.collect_stats = True
         st_d, ps_d = hx.SearchStats(), hx.PolicyStats()
         d_ids, _, d_cnt = ix.search_ex(qsets[0], pnew, stats=st_d, policy_stats=ps_d)
+        d_ids_first = d_ids
         d_recall = recall_at_k(d_ids[:rq], truth)
         pnew.collect_stats = False
         cpn, poln = pnew._c(), pnew._policy()
@@ -394,6 +397,13 @@ def run_ours(args):
             step_default(args.warmup + s)
             kms_sum += ix.last_kernel_ms()[0]
         td = time.perf_counter() - t0
+        # one query per call (the reference's usage: one query per tokio task)
+        for i in range(10):
+            ix.search_ex(qsets[0][i:i + 1], pnew)
+        t0 = time.perf_counter()
+        for i in range(100):
+            ix.search_ex(qsets[0][i:i + 1], pnew)
+        single_us = (time.perf_counter() - t0) / 100 * 1e6
         default_mode = {
             "params": "SearchParams::new(10): ef=100, SimHashMode::Adaptive, threshold 43, sampling 0.8, failure 0.1",
             "e2e_qps": round(args.steps * Q / td, 1), "kernel": "k_hnsw_search_policy",
@@ -405,8 +415,10 @@ def run_ours(args):
             "rng_draws_per_query": round(ps_d.rng_draws / Q, 2),
             "alg_GBps": round(st_d.algorithmic_bytes / (kms_sum / args.steps * 1e-3) / 1e9, 1) if kms_sum else None,
             "simhash_projection_s": round(simhash_s, 3),
+            "single_query_us": round(single_us, 1),
             "note": "hyperplanes: numpy default_rng(42) Gaussian stand-in for the reference's StdRng(42) table",
         }
+        default_planes = planes
 
     # ---- sharded path (north_star): id-range shards of the SAME corpus, one all-gather, merge ----------------------------
     sharded = None
@@ -449,7 +461,15 @@ def run_ours(args):
     # ---- CPU baseline: the oracle on the box's host cores, same graph, bounded sample (rank 0, N = 1 only) -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args, ix, qsets[0], truth[:rq] if rq else None)
+        cpu = cpu_baseline(args, ix, qsets[0], truth[:rq] if rq else None,
+                           default_planes if default_mode is not None else None)
+        if default_mode is not None and "default_mode_qps" in cpu:
+            default_mode["cpu_port_qps"] = cpu.pop("default_mode_qps")
+            default_mode["cpu_port_recall_at_10"] = cpu.pop("default_mode_recall")
+            pi = cpu.pop("_default_ids")
+            cpu.pop("default_mode_sample", None)
+            default_mode["cpu_port_identical_to_device"] = bool(d_ids_first is not None and
+                                                                pi.tolist() == d_ids_first[:len(pi)].tolist())
 
     impl = os.environ.get("HX_HNSW_IMPL", "ring")
     hnsw_kernel = {"ring": "k_hnsw_search_ring", "tma": "k_hnsw_search_tma", "ldg": "k_hnsw_search_warp"}.get(impl, impl)
@@ -501,7 +521,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, ix, queries, truth):
+def cpu_baseline(args, ix, queries, truth, planes=None):
     """The oracle (C restatement of the reference, no KV layer => an upper bound on the reference's CPU throughput)."""
     from oracle import hxo
 
@@ -516,12 +536,26 @@ def cpu_baseline(args, ix, queries, truth):
     ids, sc, cnt, st, secs = ora.search_batch(queries[:sample], K, EF, threads=cores)
     rec = recall_at_k(ids[:len(truth)], truth) if truth is not None and len(truth) <= sample else None
     _, _, _, _, secs1 = ora.search_batch(queries[:min(sample, 256)], K, EF, threads=1)
-    return {"value": round(sample / secs, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+    extra = {}
+    if planes is not None:   # the production-default mode on the CPU: same fingerprints, same policy
+        n = args.n
+        ora.put_simhash(np.arange(n, dtype=np.uint64), ix.download_simhash(0, n))
+        dq = min(sample, 4096)
+        qsim = np.array([hxo.simhash_from_planes(planes, q) for q in queries[:dq]], dtype=np.uint64)
+        cfg = hxo.policy_defaults()
+        pi, _, pc, psecs = ora.search_policy_batch(queries[:dq], K, EF, cfg, qsim, threads=cores)
+        extra["default_mode_qps"] = round(dq / psecs, 1)
+        extra["default_mode_recall"] = round(recall_at_k(pi[:len(truth)], truth), 4) if truth is not None and len(truth) <= dq else None
+        extra["default_mode_sample"] = dq
+        extra["_default_ids"] = pi
+    out = {"value": round(sample / secs, 1), "unit": "queries/s", "cores": cores, "kind": "port",
             "sample": f"{sample} queries of the first step's set, one query per thread, {cores} threads, "
                       f"identical graph and vectors",
             "single_thread_qps": round(min(sample, 256) / secs1, 1), "recall_at_10": None if rec is None else round(rec, 4),
             "distance_computations_per_query": round(st["distance_computations"] / sample, 1),
             "mirror_s": round(mirror_s, 1)}
+    out.update(extra)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------

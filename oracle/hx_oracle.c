@@ -1946,3 +1946,57 @@ double hxo_search_exact_batch(const hxo_index* ix, const float* queries, size_t 
   job.mode = 2;
   return run_batch(&job, threads);
 }
+
+/* Threaded driver for the non-exhaustive mode (one query per thread at a time, like hxo_search_batch). */
+typedef struct {
+  const hxo_index* ix;
+  const float* queries;
+  const uint64_t* qsim;
+  size_t nq;
+  uint32_t k, ef;
+  const hxo_policy_cfg* cfg;
+  uint64_t* out_ids;
+  float* out_scores;
+  uint32_t* out_counts;
+  size_t next;
+  pthread_mutex_t mu;
+  int rc;
+} policy_job;
+
+static void* policy_worker(void* arg) {
+  policy_job* j = (policy_job*)arg;
+  for (;;) {
+    pthread_mutex_lock(&j->mu);
+    const size_t q = j->next++;
+    pthread_mutex_unlock(&j->mu);
+    if (q >= j->nq) break;
+    uint32_t cnt = 0;
+    const int rc = hxo_search_policy(j->ix, j->queries + q * j->ix->dim, j->ix->dim, j->k, j->ef, j->cfg, j->qsim[q],
+                                     j->out_ids + q * j->k, j->out_scores + q * j->k, &cnt, NULL, NULL);
+    j->out_counts[q] = cnt;
+    if (rc) j->rc = rc;
+  }
+  scratch_free(&tls_scratch);
+  return NULL;
+}
+
+double hxo_search_policy_batch(const hxo_index* ix, const float* queries, const uint64_t* qsim, size_t nq, uint32_t k,
+                               uint32_t ef, const hxo_policy_cfg* cfg, int threads, uint64_t* out_ids, float* out_scores,
+                               uint32_t* out_counts) {
+  policy_job j;
+  memset(&j, 0, sizeof(j));
+  j.ix = ix; j.queries = queries; j.qsim = qsim; j.nq = nq; j.k = k; j.ef = ef; j.cfg = cfg;
+  j.out_ids = out_ids; j.out_scores = out_scores; j.out_counts = out_counts;
+  pthread_mutex_init(&j.mu, NULL);
+  if (threads < 1) threads = 1;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int i = 0; i < threads; ++i) pthread_create(&th[i], NULL, policy_worker, &j);
+  for (int i = 0; i < threads; ++i) pthread_join(th[i], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  free(th);
+  pthread_mutex_destroy(&j.mu);
+  if (j.rc) return -1.0;
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

@@ -237,6 +237,10 @@ int hxo_index_put_simhash(hxo_index* idx, const uint64_t* ids, const uint64_t* b
 int hxo_search_policy(const hxo_index* idx, const float* query, uint32_t query_dim, uint32_t k, uint32_t ef,
                       const hxo_policy_cfg* cfg, uint64_t query_simhash, uint64_t* out_ids, float* out_scores,
                       uint32_t* out_count, hxo_stats* stats, hxo_policy_stats* pstats);
+/* threaded driver (one query per thread at a time); returns wall seconds, < 0 on error */
+double hxo_search_policy_batch(const hxo_index* idx, const float* queries, const uint64_t* query_simhash, size_t nq,
+                               uint32_t k, uint32_t ef, const hxo_policy_cfg* cfg, int threads, uint64_t* out_ids,
+                               float* out_scores, uint32_t* out_counts);
 
 #ifdef __cplusplus
 }

@@ -256,6 +256,9 @@ def lib():
     L.hxo_search_policy.restype = C.c_int
     L.hxo_search_policy.argtypes = [C.c_void_p, fp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PolicyCfg), C.c_uint64,
                                     u64p, fp, u32p, C.POINTER(Stats), C.POINTER(PolicyStats)]
+    L.hxo_search_policy_batch.restype = C.c_double
+    L.hxo_search_policy_batch.argtypes = [C.c_void_p, fp, u64p, sz, C.c_uint32, C.c_uint32, C.POINTER(PolicyCfg), C.c_int,
+                                          u64p, fp, u32p]
     _lib = L
     return L
 
@@ -488,6 +491,21 @@ class Index:
         self._ck(rc)
         n = int(cnt.value)
         return ids[:n].copy(), sc[:n].copy(), st.as_dict(), ps.as_dict()
+
+    def search_policy_batch(self, queries, k, ef, cfg, query_simhash, threads=1):
+        qa, qp = _f32(queries)
+        sa, sp = _u64(query_simhash)
+        nq = qa.size // self.dim
+        ids = np.zeros((nq, k), dtype=np.uint64)
+        sc = np.zeros((nq, k), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        secs = self.L.hxo_search_policy_batch(self.h, qp, sp, nq, k, ef, C.byref(cfg), threads,
+                                              ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                              cnt.ctypes.data_as(C.POINTER(C.c_uint32)))
+        if secs < 0:
+            raise OracleError(-1)
+        return ids, sc, cnt, float(secs)
 
     def search_restricted(self, query, k, cand_ids):
         qa, qp = _f32(query)

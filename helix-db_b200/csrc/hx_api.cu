@@ -2175,7 +2175,10 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   uint32_t pol_warps = 16, pol_minR = 3;   // fewer rows per expansion survive the gate: 3 slots suffice
   if (const char* env = getenv("HX_POL_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 16) pol_warps = (uint32_t)v; }
   if (const char* env = getenv("HX_POL_MINR")) { const int v = atoi(env); if (v >= 1 && v <= 32) pol_minR = (uint32_t)v; }
-  for (uint32_t w = std::min(pol_warps, spread); w >= 1; --w) {
+  // B < #SMs: one CTA per query (warp 0 runs the query, 7 more warps reduce rows with it)
+  bool pol_cta = B < (size_t)ix->sm_count;
+  if (const char* env = getenv("HX_POL_CTA")) pol_cta = pol_cta && atoi(env) != 0;
+  for (uint32_t w = pol_cta ? 1u : std::min(pol_warps, spread); w >= 1; --w) {
     const size_t per_warp = (budget / w) & ~(size_t)127;
     if (per_warp <= fixed0 + 8 + rowbytes) continue;
     const uint32_t r = (uint32_t)std::min<size_t>(32, (per_warp - fixed0) / (rowbytes + 8));
@@ -2252,9 +2255,15 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   const size_t smem_launch = (size_t)wpc * wstride;
 #define HX_LAUNCH_POLICY2(M, Q)                                                                                    \
   do {                                                                                                             \
-    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_policy<M, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                 (int)smem_launch));                                                               \
-    k_hnsw_search_policy<M, Q><<<grid, wpc * 32, smem_launch, stream>>>(dev, a, rg, pa, wstride, R);               \
+    if (pol_cta) {                                                                                                 \
+      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_policy<M, Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                   (int)smem_launch));                                                             \
+      k_hnsw_search_policy<M, Q, true><<<grid, 8 * 32, smem_launch, stream>>>(dev, a, rg, pa, wstride, R);         \
+    } else {                                                                                                       \
+      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_policy<M, Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                   (int)smem_launch));                                                             \
+      k_hnsw_search_policy<M, Q, false><<<grid, wpc * 32, smem_launch, stream>>>(dev, a, rg, pa, wstride, R);      \
+    }                                                                                                              \
   } while (0)
 #define HX_LAUNCH_POLICY(M)                                                                                        \
   do {                                                                                                             \

@@ -246,14 +246,21 @@ __device__ __forceinline__ bool hx_vt_contains(const HxVisited& v, uint32_t key)
 // shared memory per warp: query | R row slots | beam[ef] | topk[k] | tie | R mbarriers | frontier | fdist | fhdr(aliases fsim) |
 //                         fstate (bytes) | session (28 words)
 #define HX_POLICY_MAX_THREADS 512
-template <int METRIC, int QCH>
+// CTA = false: one warp per query (throughput).  CTA = true (B < #SMs): one CTA per query — warp 0 runs the very same
+// per-query code, and whenever it has rows to score it wakes the other warps, which issue and reduce their share of the
+// rows (row r -> warp r mod W), exactly like the latency build of the exhaustive kernel.
+template <int METRIC, int QCH, bool CTA>
 __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy(HxDev ix, HxHnswArgs a, HxRingArgs rg,
                                                                                 HxPolicyArgs pa, uint32_t wstride, uint32_t R) {
   extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint32_t s_cmd, s_cnt;      // CTA mode: warp 0 -> helpers (1 = score s_cnt rows of `frontier`, 2 = done)
+  __shared__ float s_qhdr;
+  __shared__ const float* s_qg;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t warps_per_cta = blockDim.x >> 5;
-  const uint32_t gw = blockIdx.x * warps_per_cta + warp;
-  unsigned char* wmem = smem + (size_t)warp * wstride;
+  const uint32_t W = warps_per_cta;
+  const uint32_t gw = CTA ? blockIdx.x : blockIdx.x * warps_per_cta + warp;
+  unsigned char* wmem = smem + (CTA ? (size_t)0 : (size_t)warp * wstride);
   constexpr bool Q_SMEM = QCH == 0 || METRIC == HXM_MANHATTAN;   // Manhattan walks the query sequentially: keep it in smem
   float* sq = reinterpret_cast<float*>(wmem);                                            // [ld] when Q_SMEM
   float* ring = sq + (Q_SMEM ? ix.ld : 0u);                                              // [R][ld]
@@ -271,9 +278,15 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
   const uint32_t rowbytes = ix.ld * 4u;
   const uint64_t policy = hx_policy_evict_first();
   uint32_t ph = 0;
-  if (lane < R) hx_mbar_init(bars + lane, 1);
-  hx_fence_mbar_init();
-  __syncwarp();
+  if (CTA) {
+    if (threadIdx.x < R) hx_mbar_init(bars + threadIdx.x, 1);
+    hx_fence_mbar_init();
+    __syncthreads();
+  } else {
+    if (lane < R) hx_mbar_init(bars + lane, 1);
+    hx_fence_mbar_init();
+    __syncwarp();
+  }
   float qr[(!Q_SMEM && QCH > 0) ? QCH : 1];
   const float* qg = nullptr;
   float q_hdr = 0.f;
@@ -286,7 +299,56 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     if (rg.l2_hint) hx_bulk_g2s_hint(ring + (size_t)s * ix.ld, ix.vec + (size_t)slot * ix.ld, rowbytes, bars + s, policy);
     else hx_bulk_g2s(ring + (size_t)s * ix.ld, ix.vec + (size_t)slot * ix.ld, rowbytes, bars + s);
   };
+  // CTA mode: every warp's share of one pass of `rows` rows starting at list[base] (slot = row index within the pass)
+  auto score_share = [&](const uint32_t* list, uint32_t base, uint32_t rows) {
+    const uint32_t mine = lane * W + warp;
+    float rh = 0.f;
+    if (mine < rows) {
+      const uint32_t slot = list[base + mine];
+      issue(mine, slot);
+      if (METRIC == HXM_COSINE) rh = __ldg(ix.hdr + slot);
+    }
+    uint32_t j = 0;
+    for (uint32_t r = warp; r < rows; r += W, ++j) {
+      const float row_hdr = __shfl_sync(FULL, rh, j);
+      hx_mbar_wait(bars + r, (ph >> r) & 1u);
+      float sc;
+      if (METRIC == HXM_MANHATTAN) {
+        sc = 0.0f;
+        const float* row = ring + (size_t)r * ix.ld;
+        for (uint32_t i = 0; i < ix.dim; ++i) sc = __fadd_rn(sc, fabsf(__fsub_rn(sq[i], row[i])));
+      } else {
+        sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
+            ring + (size_t)r * ix.ld, qr, sq, qg, q_hdr, row_hdr, ix.dim, lane);
+      }
+      if (lane == 0) fdist[base + r] = sc;
+    }
+    ph ^= rows >= 32u ? FULL : ((1u << rows) - 1u);
+  };
+  if (CTA && warp != 0) {   // helpers: score on command until warp 0 says done
+    for (;;) {
+      __syncthreads();
+      if (s_cmd == 2u) return;
+      const uint32_t cnt = s_cnt;
+      q_hdr = s_qhdr;
+      qg = s_qg;
+      for (uint32_t base = 0; base < cnt; base += R) {
+        score_share(frontier, base, min(R, cnt - base));
+        __syncthreads();
+      }
+    }
+  }
   auto score_list = [&](const uint32_t* list, uint32_t cnt) {
+    if (CTA) {   // list == frontier (always, in this kernel)
+      if (cnt == 0) return;
+      if (lane == 0) { s_cmd = 1u; s_cnt = cnt; s_qhdr = q_hdr; s_qg = qg; }
+      __syncthreads();
+      for (uint32_t base = 0; base < cnt; base += R) {
+        score_share(list, base, min(R, cnt - base));
+        __syncthreads();
+      }
+      return;
+    }
     if (lane < min(R, cnt)) issue(lane, list[lane]);
     if (METRIC == HXM_COSINE)
       for (uint32_t f = lane; f < cnt; f += 32) fhdr[f] = __ldg(ix.hdr + list[f]);
@@ -667,6 +729,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
       atomicExch(rg.pool_busy + pool_idx, 0u);
     }
     __syncwarp();
+  }
+  if (CTA) {   // warp 0: release the helpers
+    if (lane == 0) s_cmd = 2u;
+    __syncthreads();
   }
   if (pa.pstats && lane == 0)
     for (int i = 0; i < 12; ++i)

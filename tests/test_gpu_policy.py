@@ -54,6 +54,18 @@ def compare(gpu, ora, queries, qsim, params, cfg, what):
     for f in ("expansion_steps", "neighbors_examined", "distance_computations", "vectors_loaded"):
         assert getattr(st, f) == tot[f], (what, f)
     assert ps.as_dict() == ptot, what
+    # small batches (B < #SMs) run the CTA-per-query build of the same kernel: same bits, same counters
+    st2, ps2 = hx.SearchStats(), hx.PolicyStats()
+    si, ss, scnt = gpu.search_ex(queries[:40], params, query_simhash=qsim[:40], stats=st2, policy_stats=ps2)
+    assert si.tolist() == gi[:40].tolist() and ss.tobytes() == gs[:40].tobytes() and scnt.tolist() == gc[:40].tolist(), what
+    st3, ps3 = hx.SearchStats(), hx.PolicyStats()
+    import os
+    os.environ["HX_POL_CTA"] = "0"
+    try:
+        gpu.search_ex(queries[:40], params, query_simhash=qsim[:40], stats=st3, policy_stats=ps3)
+    finally:
+        del os.environ["HX_POL_CTA"]
+    assert ps2.as_dict() == ps3.as_dict() and st2.expansion_steps == st3.expansion_steps, what
     return ptot
 
 

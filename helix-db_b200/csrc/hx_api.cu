@@ -208,6 +208,7 @@ void HxScratch::destroy() {
   for (auto& m : misc) m.release();
   h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
   h_counts.release(); h_qstats.release(); h_status.release(); h_err.release(); h_avail.release();
+  d_block.release(); h_block.release();
 }
 
 hx_status hx_acquire_scratch(hx_index* ix, HxScratch** out) {
@@ -1396,6 +1397,64 @@ static hx_status check_device_flags(uint32_t flags) {
   return HX_OK;
 }
 
+// ---- result download -------------------------------------------------------------------------------------------------------
+// Small calls (one query per call is the reference's usage) are dominated by fixed costs: five device-to-host copies of a few
+// bytes each cost more than the data.  Their results are packed into one block by a tiny kernel and cross PCIe in ONE copy.
+static __global__ void k_pack_small(const uint64_t* __restrict__ ids, const float* __restrict__ scores,
+                                    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ status,
+                                    const uint32_t* __restrict__ err, uint32_t n_ids, uint32_t B, unsigned char* __restrict__ out) {
+  uint64_t* o_ids = reinterpret_cast<uint64_t*>(out);
+  float* o_sc = reinterpret_cast<float*>(o_ids + n_ids);
+  uint32_t* o_cnt = reinterpret_cast<uint32_t*>(o_sc + n_ids);
+  uint32_t* o_st = o_cnt + B;
+  for (uint32_t i = threadIdx.x; i < n_ids; i += blockDim.x) { o_ids[i] = ids[i]; o_sc[i] = scores[i]; }
+  for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) { o_cnt[i] = counts[i]; o_st[i] = status[i]; }
+  if (threadIdx.x == 0) o_st[B] = err ? err[0] : 0u;
+}
+
+struct HxDownload {
+  bool packed = false;
+  size_t n_ids = 0, B = 0;
+};
+// enqueue the download of ids / scores / counts / per-query status / error flags on s->stream
+static hx_status enqueue_results(HxScratch* s, size_t B, uint32_t k, uint64_t* out_ids, float* out_scores,
+                                 uint32_t* out_counts, uint32_t* launches, HxDownload* dl) {
+  hx_status rc;
+  dl->n_ids = B * (size_t)k;
+  dl->B = B;
+  if ((rc = s->h_status.reserve(B))) return rc;
+  if ((rc = s->h_err.reserve(1))) return rc;
+  s->h_err.p[0] = 0;
+  if (dl->n_ids <= 4096 && s->d_err.p) {
+    const size_t bytes = dl->n_ids * 12 + B * 8 + 4;
+    if ((rc = s->d_block.reserve(bytes))) return rc;
+    if ((rc = s->h_block.reserve(bytes))) return rc;
+    k_pack_small<<<1, 256, 0, s->stream>>>(s->d_out_ids.p, s->d_out_scores.p, s->d_out_counts.p, s->d_qstatus.p, s->d_err.p,
+                                          (uint32_t)dl->n_ids, (uint32_t)B, s->d_block.p);
+    HX_CUDA(cudaGetLastError());
+    (*launches)++;
+    HX_CUDA(cudaMemcpyAsync(s->h_block.p, s->d_block.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    dl->packed = true;
+    return HX_OK;
+  }
+  HX_CUDA(cudaMemcpyAsync(out_ids, s->d_out_ids.p, dl->n_ids * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_scores, s->d_out_scores.p, dl->n_ids * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(out_counts, s->d_out_counts.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HX_CUDA(cudaMemcpyAsync(s->h_status.p, s->d_qstatus.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (s->d_err.p) HX_CUDA(cudaMemcpyAsync(s->h_err.p, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  return HX_OK;
+}
+// after the stream has been synchronised
+static void finish_results(HxScratch* s, const HxDownload& dl, uint64_t* out_ids, float* out_scores, uint32_t* out_counts) {
+  if (!dl.packed) return;
+  const unsigned char* b = s->h_block.p;
+  memcpy(out_ids, b, dl.n_ids * 8);
+  memcpy(out_scores, b + dl.n_ids * 8, dl.n_ids * 4);
+  memcpy(out_counts, b + dl.n_ids * 12, dl.B * 4);
+  memcpy(s->h_status.p, b + dl.n_ids * 12 + dl.B * 4, dl.B * 4);
+  memcpy(s->h_err.p, b + dl.n_ids * 12 + dl.B * 8, 4);
+}
+
 static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
                                   uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats);
 
@@ -1476,19 +1535,14 @@ static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, 
     if (pipelined) cudaStreamSynchronize(s->copy_stream);   // do not leave copies in flight into a released scratch set
     return rc;
   }
-  if ((rc = s->h_status.reserve(B))) return rc;
-  if ((rc = s->h_err.reserve(1))) return rc;
-  s->h_err.p[0] = 0;
-  HX_CUDA(cudaMemcpyAsync(out_ids, s->d_out_ids.p, B * (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-  HX_CUDA(cudaMemcpyAsync(out_scores, s->d_out_scores.p, B * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-  HX_CUDA(cudaMemcpyAsync(out_counts, s->d_out_counts.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-  HX_CUDA(cudaMemcpyAsync(s->h_status.p, s->d_qstatus.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-  if (s->d_err.p) HX_CUDA(cudaMemcpyAsync(s->h_err.p, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HxDownload dl;
+  if ((rc = enqueue_results(s, B, k, out_ids, out_scores, out_counts, &launches, &dl))) return rc;
   if (want_stats) {
     if ((rc = s->h_qstats.reserve(B * 4))) return rc;
     HX_CUDA(cudaMemcpyAsync(s->h_qstats.p, s->d_qstats.p, B * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   }
   HX_CUDA(cudaStreamSynchronize(s->stream));
+  finish_results(s, dl, out_ids, out_scores, out_counts);
   for (size_t b = 0; b < B; ++b)
     if (s->h_status.p[b] != HX_ST_OK) return status_from_word(s->h_status.p[b], b, "query");
   if ((rc = check_device_flags(s->h_err.p[0]))) return rc;
@@ -2348,14 +2402,8 @@ extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, 
                           s->d_out_counts.p, want_stats ? s->d_qstats.p : nullptr, s->stream, &launches)))
     return rc;
   HX_CUDA(cudaEventRecord(s->ev1, s->stream));
-  if ((rc = s->h_status.reserve(B))) return rc;
-  if ((rc = s->h_err.reserve(1))) return rc;
-  s->h_err.p[0] = 0;
-  HX_CUDA(cudaMemcpyAsync(out_ids, s->d_out_ids.p, B * (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-  HX_CUDA(cudaMemcpyAsync(out_scores, s->d_out_scores.p, B * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-  HX_CUDA(cudaMemcpyAsync(out_counts, s->d_out_counts.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-  HX_CUDA(cudaMemcpyAsync(s->h_status.p, s->d_qstatus.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-  if (s->d_err.p) HX_CUDA(cudaMemcpyAsync(s->h_err.p, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HxDownload dl;
+  if ((rc = enqueue_results(s, B, k, out_ids, out_scores, out_counts, &launches, &dl))) return rc;
   if (want_stats) {
     if ((rc = s->h_qstats.reserve(B * 4))) return rc;
     HX_CUDA(cudaMemcpyAsync(s->h_qstats.p, s->d_qstats.p, B * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
@@ -2364,6 +2412,7 @@ extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, 
   if (pstats && s->d_pstats.p)
     HX_CUDA(cudaMemcpyAsync(hps, s->d_pstats.p, sizeof(hps), cudaMemcpyDeviceToHost, s->stream));
   HX_CUDA(cudaStreamSynchronize(s->stream));
+  finish_results(s, dl, out_ids, out_scores, out_counts);
   for (size_t b = 0; b < B; ++b)
     if (s->h_status.p[b] != HX_ST_OK) return status_from_word(s->h_status.p[b], b, "query");
   if ((rc = check_device_flags(s->h_err.p[0]))) return rc;

@@ -92,6 +92,8 @@ struct HxScratch {
   DevBuf<uint64_t> d_qsim;             // query fingerprints
   bool prof_init = false;
   DevBuf<uint8_t> misc[16];   // dense path buffers (kept across calls)
+  DevBuf<uint8_t> d_block;    // small calls: results packed into one block -> one device-to-host copy
+  PinBuf<uint8_t> h_block;
   size_t stamp_stride = 0;
   uint32_t stamp_grid = 0;
   size_t stamp_n = 0;

@@ -1386,6 +1386,10 @@ static hx_status check_device_flags(uint32_t flags) {
     hx_set_error("vector distance kernel emitted an invalid score");   // model.rs:21-28
     return HX_ERR_INVARIANT_VIOLATION;
   }
+  if (flags & HXF_COPY_TIMEOUT) {
+    hx_set_error("the host-to-device copy of the queries did not complete (pipelined search gave up waiting)");
+    return HX_ERR_CUDA;
+  }
   if (flags & HXF_VT_OVERFLOW) {
     hx_set_error("visited-set overflow: a query visited more nodes than the overflow tables hold");
     return HX_ERR_INVARIANT_VIOLATION;

@@ -24,6 +24,7 @@
 
 #define HX_VT_EMPTY 0xFFFFFFFFu
 #define HXF_VT_OVERFLOW 8u
+#define HXF_COPY_TIMEOUT 16u
 
 struct HxRingArgs {
   uint32_t* vtab;        // [slots][vt_cap] visited hash tables (slot = global warp id / CTA id)
@@ -294,9 +295,24 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
     if (qi >= a.B) break;
     qg = a.queries + (size_t)qi * ix.dim;
     if (a.avail) {   // the query may still be on its way from the host
-      if (lane == 0)
-        while (hx_ld_acquire_sys(a.avail) <= qi) __nanosleep(200);
-      __syncwarp();
+      uint32_t gone = 0;
+      if (lane == 0) {
+        // a few seconds without progress means the copy stream died: give the launch up instead of hanging the device
+        uint32_t spins = 0;
+        while (hx_ld_acquire_sys(a.avail) <= qi) {
+          __nanosleep(200);
+          if ((++spins & 0xfffu) == 0u && ((*(volatile uint32_t*)a.err_flags & HXF_COPY_TIMEOUT) || spins > (1u << 24))) {
+            atomicOr(a.err_flags, HXF_COPY_TIMEOUT);
+            gone = 1;
+            break;
+          }
+        }
+      }
+      gone = __shfl_sync(FULL, gone, 0);
+      if (gone) {
+        if (lane == 0) { a.out_counts[qi] = 0; if (a.q_status_w) a.q_status_w[qi] = 0; }
+        continue;
+      }
     }
     if (a.fused_validate) {   // ValidatedMetricVector::try_new + D::new_header by the warp that owns the query
       float h;

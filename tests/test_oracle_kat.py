@@ -458,3 +458,32 @@ def test_session_rng_structure(hxo):
     L.hxo_chacha_block(key.ctypes.data_as(_C.POINTER(_C.c_uint32)), 1 | (0x09000000 << 32), 0x4A000000, 20,
                        out.ctypes.data_as(_C.POINTER(_C.c_uint32)))
     assert out[:4].tolist() == [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3] and out[15] == 0x4e3c50a2
+
+
+def test_policy_path_with_neutral_parameters_reproduces_the_pinned_strict_search(hxo):
+    """Consistency of the non-exhaustive restatement with the value-pinned strict one: with a zero threshold and sampling
+    ratio 1.0 no neighbour is filtered, deferred or drawn for, so layer0_policy must walk exactly like layer0_strict
+    (same results, same counters) — for every metric and mode."""
+    rng = np.random.default_rng(4)
+    n, dim = 1200, 24
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    queries = rng.standard_normal((40, dim)).astype(np.float32)
+    planes = rng.standard_normal((64, dim)).astype(np.float32)
+    ml = hxo.lib().hxo_default_ml_for_m(8)
+    for metric in (hxo.COSINE, hxo.EUCLIDEAN, hxo.MANHATTAN):
+        ora = hxo.Index(metric, dim, m=8, m0=16, ef_construction=50)
+        r2 = np.random.default_rng(9)
+        for i in range(n):
+            ora.insert(i, rows[i], int(hxo.lib().hxo_select_layer_from_uniform(ml, float(r2.random(dtype=np.float32)))))
+        ora.put_simhash(np.arange(n, dtype=np.uint64),
+                        np.array([hxo.simhash_from_planes(planes, rows[i]) for i in range(n)], dtype=np.uint64))
+        for mode in (hxo.SIMHASH_ALWAYS, hxo.SIMHASH_ADAPTIVE, hxo.SIMHASH_OFF):
+            cfg = hxo.policy_defaults(mode=mode, threshold=0, sampling_ratio=1.0)
+            for q in queries:
+                qs = hxo.simhash_from_planes(planes, q)
+                si, ss, sst = ora.search(q, 10, ef=30, with_stats=True)
+                pi, psc, pst, pps = ora.search_policy(q, 10, 30, cfg, qs)
+                assert pi.tolist() == si.tolist() and psc.tobytes() == ss.tobytes()
+                for f in ("expansion_steps", "neighbors_examined", "distance_computations", "vectors_loaded"):
+                    assert pst[f] == sst[f], (f, metric, mode)
+                assert pps["simhash_filtered"] == 0 and pps["rng_draws"] == 0

@@ -480,6 +480,28 @@ def test_pipelined_host_search(gm, om, monkeypatch):
         assert gi2.tolist() == oi.tolist()
 
 
+# ---- wide beams: ef far above the register beam (128) and k in the hundreds, both batch regimes -------------------------
+@pytest.mark.parametrize("gm,om", METRICS[:2])
+def test_wide_beam_and_large_k(gm, om):
+    n, dim = 4000, 64
+    rng = np.random.default_rng(31)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    gpu, ora = build_pair(gm, om, rows, m=8, m0=16, efc=60)
+    queries = rng.standard_normal((200, dim)).astype(np.float32)
+    for k, ef in ((200, 1000), (64, 4096), (1, 129)):
+        oi, os_, oc, ost, _ = ora.search_batch(queries, k, ef, threads=4)
+        params = hx.SearchParams.strict(k, ef)
+        params.collect_stats = True
+        st = hx.SearchStats()
+        gi, gs, gc = gpu.search_batch(queries, params, st)                 # warp-per-query build
+        assert gc.tolist() == oc.tolist() and gi.tolist() == oi.tolist() and gs.tobytes() == os_.tobytes(), (k, ef)
+        assert st.expansion_steps == ost["expansion_steps"] and st.distance_computations == ost["distance_computations"]
+        gi, gs, gc = gpu.search_batch(queries[:12], params)                # CTA-per-query build, shared-memory beam
+        assert gc.tolist() == oc[:12].tolist() and gi.tolist() == oi[:12].tolist() and gs.tobytes() == os_[:12].tobytes()
+    with pytest.raises(hx.HelixDbError):
+        gpu.search_batch(queries[:2], hx.SearchParams.strict(10, 5000))    # above the supported beam width
+
+
 # ---- sharded path: per-shard top-k merged by (score, id) equals the unsharded exact answer ---------------------------------------
 def test_merge_topk_matches_unsharded_scan():
     import torch

@@ -77,3 +77,18 @@ def test_policy_defaults_and_order_code_without_a_device():
     assert not hx.SearchParams.strict(10).requires_query_simhash()
     t = hx.SearchParams.throughput_profile_floor_92(10)
     assert t.ef() == 48 and abs(t._c().pre_sampling_ratio - 0.20) < 1e-7
+
+
+def test_cpp_host_mirror_compiles_against_the_header(tmp_path):
+    # helix-db_b200/host/vector_index.hpp is the C++ host side a non-Python caller links: it must follow the C ABI header
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        import pytest
+        pytest.skip("g++ not available")
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "%s"\nint main() { helix::SearchParams p(10); p.with_simhash_failure_prob(0.2f)'
+                   '.with_simhash_bypass_tuning(24, 4, 0.12f, 3); return p.raw().k == 10 && !helix::SearchParams::strict(3)'
+                   '.requires_query_simhash() ? 0 : 1; }\n' % (ROOT / "helix-db_b200" / "host" / "vector_index.hpp"))
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -377,7 +377,7 @@ def test_traversal_builds_agree(gm, om, dim, monkeypatch):
     _, _, _, sst, _ = ora.search_batch(queries[:nsmall], k, ef, threads=4)
     small_stats = (sst["expansion_steps"], sst["neighbors_examined"], sst["distance_computations"])
     for env in [{}, {"HX_LAT_IMPL": "tma"}, {"HX_LAT_IMPL": "ldg"}, {"HX_VT_CAP_LOG2": "6"}, {"HX_RING_R": "3"},
-                {"HX_LAT_WARPS": "3", "HX_L2_HINT": "0"}, {"HX_LAT_SPEC": "0"}, {"HX_LAT_WARPS": "1"},
+                {"HX_LAT_WARPS": "3", "HX_L2_HINT": "0"}, {"HX_LAT_SPEC": "1"}, {"HX_LAT_WARPS": "1"},
                 {"HX_LAT_ADMIT": "seq", "HX_VT_CAP_LOG2": "7"}]:
         for key in ("HX_HNSW_IMPL", "HX_LAT_IMPL", "HX_VT_CAP_LOG2", "HX_RING_WARPS", "HX_RING_R", "HX_L2_HINT", "HX_LAT_WARPS",
                     "HX_LAT_SPEC", "HX_LAT_ADMIT"):

@@ -2246,11 +2246,22 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
     hx_set_error("query working set exceeds shared memory (dimension %u, ef %u)", ix->cfg.dimension, ef);
     return HX_ERR_INVALID_PARAMETER;
   }
-  const uint32_t wstride = round_up((uint32_t)(fixed0 + (size_t)R * (rowbytes + 8)), 128);
+  uint32_t wstride = round_up((uint32_t)(fixed0 + (size_t)R * (rowbytes + 8)), 128);
   uint32_t lg = 12;
   while ((1u << lg) < 64u * ef && lg < 24) lg++;
   if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) lg = (uint32_t)v; }
-  const uint32_t vt_cap = 1u << lg;
+  uint32_t vt_cap = 1u << lg;
+  size_t cta_vt_bytes = 0;
+  if (pol_cta) {   // the visited set sits in shared memory behind the query's region: shrink rows / table until it fits
+    while (vt_cap > 1024 && (size_t)vt_cap * 4 > budget / 4) vt_cap >>= 1;
+    while (R > 4 && fixed0 + (size_t)R * (rowbytes + 8) + 256 + (size_t)vt_cap * 4 > budget) R--;
+    wstride = round_up((uint32_t)(fixed0 + (size_t)R * (rowbytes + 8)), 128);
+    if ((size_t)wstride + (size_t)vt_cap * 4 > budget) {
+      hx_set_error("query working set exceeds shared memory (dimension %u, ef %u)", ix->cfg.dimension, ef);
+      return HX_ERR_INVALID_PARAMETER;
+    }
+    cta_vt_bytes = (size_t)vt_cap * 4;
+  }
   const uint32_t grid = (uint32_t)std::min<size_t>((B + wpc - 1) / wpc, (size_t)ix->sm_count);
   const size_t vslots = (size_t)grid * wpc;
   uint32_t pool_n = 32;
@@ -2310,7 +2321,7 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   pa.query_simhash = d_qsim;
   pa.pstats = s->d_pstats.p;
   const HxDev dev = ix->dev();
-  const size_t smem_launch = (size_t)wpc * wstride;
+  const size_t smem_launch = (size_t)wpc * wstride + cta_vt_bytes;
 #define HX_LAUNCH_POLICY2(M, Q)                                                                                    \
   do {                                                                                                             \
     if (pol_cta) {                                                                                                 \

@@ -392,7 +392,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
       for (int c = 0; c < ((!Q_SMEM && QCH > 0) ? QCH : 1); ++c) qr[c] = (uint32_t)(c * 32) + lane < ix.dim ? qg[c * 32 + lane] : 0.f;
     }
     const uint64_t qsim = pa.query_simhash[qi];
-    HxVisited vt = hx_vt_make(rg.vtab + (size_t)gw * rg.vt_cap, rg.vt_cap);
+    // CTA build: the visited set of the one query lives in shared memory (after the warp-0 region); it moves to a pool
+    // table in global memory only if it outgrows it
+    uint32_t* vt_home = CTA ? reinterpret_cast<uint32_t*>(smem + wstride) : rg.vtab + (size_t)gw * rg.vt_cap;
+    HxVisited vt = hx_vt_make(vt_home, rg.vt_cap);
     int pool_idx = -1;
     bool failed = false;
     hx_vt_clear_warp(vt.tab, rg.vt_cap, lane);

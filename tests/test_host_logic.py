@@ -35,3 +35,26 @@ def test_search_result_equality_is_bitwise():
     a, b = hx.SearchResult(1, 0.5), hx.SearchResult(1, 0.5)
     assert a == b and a.entity_id() == 1 and float(a.score()) == 0.5
     assert hx.SearchResult(1, 0.0) != hx.SearchResult(1, -0.0)
+
+
+def test_policy_builder_methods_validate_like_the_reference():
+    p = hx.SearchParams.new(10)
+    pol = p._policy()                                   # SearchParams::new defaults (mod.rs:482-500)
+    assert (pol.bypass_min_frontier, pol.bypass_window_expansions, pol.read_budget_multiplier) == (24, 4, 3)
+    assert pol.sampling_ratio_override < 0 and pol.failure_prob_override < 0 and p._c().pre_sampling_ratio < 0
+    q = p.with_simhash_bypass_tuning(8, 2, 0.5, 5).with_simhash_sampling_ratio(0.25).with_simhash_failure_prob(0.2)
+    pol = q._policy()
+    assert (pol.bypass_min_frontier, pol.bypass_window_expansions, pol.read_budget_multiplier) == (8, 2, 5)
+    assert abs(pol.sampling_ratio_override - 0.25) < 1e-7 and abs(pol.failure_prob_override - 0.2) < 1e-7
+    for bad in ((0, 4, 0.1, 3), (24, 0, 0.1, 3), (24, 4, 1.5, 3), (24, 4, 0.1, 0)):   # mod.rs:563-592
+        with pytest.raises(hx.VectorParameterError):
+            hx.SearchParams.new(10).with_simhash_bypass_tuning(*bad)
+    with pytest.raises(hx.VectorParameterError):
+        hx.SearchParams.new(10).with_simhash_sampling_ratio(1.5)
+    for bad in (0.0, 1.0, -0.1):                          # FailureProbability is the open unit interval
+        with pytest.raises(hx.VectorParameterError):
+            hx.SearchParams.new(10).with_simhash_failure_prob(bad)
+    with pytest.raises(hx.VectorParameterError):
+        hx.SearchParams.new(10).with_pre_simhash_sampling_ratio(-0.5)
+    t = hx.SearchParams.throughput_profile_floor_92(100)  # mod.rs:615-621: ef = max(k, 48)
+    assert t.ef() == 100 and t.requires_query_simhash()

@@ -127,6 +127,22 @@ class PolicyStats(C.Structure):
         return {f: int(getattr(self, f)) for f, _ in self._fields_}
 
 
+class _ServiceConfig(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("ef", C.c_uint32), ("capacity", C.c_uint32), ("max_batch", C.c_uint32),
+                ("n_streams", C.c_uint32), ("ctas_per_sm", C.c_uint32), ("cta_warps", C.c_uint32),
+                ("rows_in_flight", C.c_uint32), ("visited_log2", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+class ServiceStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("submitted", "completed", "launches", "max_batch_seen", "dispatcher_sleeps",
+                                          "completer_wakes")] + \
+               [(n, C.c_uint32) for n in ("cta_warps", "rows_in_flight", "visited_cap", "smem_bytes", "ctas_per_sm",
+                                          "reserved")]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_ if f != "reserved"}
+
+
 # every symbol include/helix_b200.h declares (checked by tests/test_abi_surface.py)
 ABI_SYMBOLS = [
     "hx_index_create", "hx_index_destroy", "hx_index_load_vectors", "hx_index_generate_vectors",
@@ -140,6 +156,8 @@ ABI_SYMBOLS = [
     "hx_index_set_simhash_planes", "hx_index_compute_simhash", "hx_index_download_simhash",
     "hx_order_code_from_simhash_bits", "hx_policy_params_default", "hx_search_ex", "hx_candidates_create",
     "hx_candidates_destroy", "hx_candidates_len", "hx_search_restricted_sets",
+    "hx_search_batch", "hx_device_flags", "hx_service_create", "hx_service_destroy", "hx_service_submit",
+    "hx_service_poll", "hx_service_wait", "hx_service_search", "hx_service_get_stats",
 ]
 
 _lib = None
@@ -245,6 +263,25 @@ def load_library():
     L.hx_search_ex.restype = C.c_int32
     L.hx_search_ex.argtypes = [vp, fp, sz, C.POINTER(_Params), C.POINTER(_PolicyParams), u64p, u64p, fp, u32p,
                                C.POINTER(SearchStats), C.POINTER(PolicyStats)]
+    i32p = C.POINTER(C.c_int32)
+    L.hx_search_batch.restype = C.c_int32
+    L.hx_search_batch.argtypes = [vp, fp, sz, C.POINTER(_Params), u64p, fp, u32p, i32p, C.POINTER(SearchStats)]
+    L.hx_device_flags.restype = C.c_int32
+    L.hx_device_flags.argtypes = [vp, vp, u32p, i32p]
+    L.hx_service_create.restype = C.c_int32
+    L.hx_service_create.argtypes = [vp, C.POINTER(_ServiceConfig), C.POINTER(vp)]
+    L.hx_service_destroy.restype = None
+    L.hx_service_destroy.argtypes = [vp]
+    L.hx_service_submit.restype = C.c_int32
+    L.hx_service_submit.argtypes = [vp, fp, u64p]
+    L.hx_service_poll.restype = C.c_int32
+    L.hx_service_poll.argtypes = [vp, C.c_uint64, i32p, u64p, fp, u32p]
+    L.hx_service_wait.restype = C.c_int32
+    L.hx_service_wait.argtypes = [vp, C.c_uint64, u64p, fp, u32p]
+    L.hx_service_search.restype = C.c_int32
+    L.hx_service_search.argtypes = [vp, fp, u64p, fp, u32p]
+    L.hx_service_get_stats.restype = C.c_int32
+    L.hx_service_get_stats.argtypes = [vp, C.POINTER(ServiceStats)]
     _lib = L
     return L
 
@@ -573,17 +610,6 @@ class VectorIndex:
                   upper_deg=ud[:rows], upper_nbr=unb[:rows * su])
         return gi
 
-    def mirror_from_oracle(self, oracle_index):
-        """Upload the rows of an oracle.hxo.Index (tests only; the oracle object is passed in by the test)."""
-        ids = oracle_index.node_ids()
-        rows = np.stack([oracle_index.vector(int(i)) for i in ids]) if len(ids) else np.zeros((0, self.dim), np.float32)
-        self.load_vectors(ids, rows)
-        graph, state = oracle_index.export_graph()
-        for layer, (nodes, offs, nbrs) in graph.items():
-            self.load_graph(layer, nodes, offs, nbrs)
-        if state is not None:
-            self.set_entry(state[0], state[1])
-
     # ---- SimHash policy state (production-default mode) ----
     def set_simhash_config(self, threshold=43, sampling_ratio=0.8, adaptive_enabled=True, adaptive_failure_prob=0.1):
         """VectorIndexConfig simhash_threshold / sampling_ratio / adaptive_enabled / adaptive_failure_prob
@@ -663,6 +689,34 @@ class VectorIndex:
 
     def search_batch(self, queries, params: SearchParams, stats=None):
         return self._search_raw(np.asarray(queries, dtype=np.float32), params, stats)
+
+    def search_batch_status(self, queries, params: SearchParams, stats=None):
+        """hx_search_batch: one status per query (an invalid query, or one that exhausts a device-side bound, fails alone).
+        Returns (ids, scores, counts, status[B])."""
+        qa, qp = _f32(queries)
+        qd = params.query_dimension or self.dim
+        B = qa.size // qd
+        cp = params._c()
+        k = cp.k
+        ids = np.zeros((B, k), dtype=np.uint64)
+        sc = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        status = np.zeros(B, dtype=np.int32)
+        st = stats if stats is not None else SearchStats()
+        _ck(self.L.hx_search_batch(self.h, qp, B, C.byref(cp), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                   sc.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                   status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
+        return ids, sc, cnt, status
+
+    def device_flags(self, stream_ptr=0):
+        """hx_device_flags: (flags, status) of the device-buffer calls issued on the stream since the last read."""
+        fl, stc = C.c_uint32(0), C.c_int32(0)
+        _ck(self.L.hx_device_flags(self.h, stream_ptr, C.byref(fl), C.byref(stc)))
+        return int(fl.value), int(stc.value)
+
+    def service(self, k: int, ef: int = 0, **kw) -> "SearchService":
+        """A query service on this index: concurrent one-query callers coalesced into shared launches."""
+        return SearchService(self, k, ef, **kw)
 
     def search_restricted(self, query, params: SearchParams, allowed: RestrictedVectorCandidates):
         """VectorIndex::search_restricted (restricted.rs:466-479); exact for every |C| <= 1e6."""
@@ -765,6 +819,78 @@ class VectorIndex:
         ms, n = C.c_float(0), C.c_uint32(0)
         _ck(self.L.hx_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+
+class SearchService:
+    """hx_service: the reference's calling pattern (one query per call from many concurrent tasks, read_index.rs:81-101)
+    served by shared launches.  ``search`` blocks; ``submit`` / ``poll`` are the async pair."""
+
+    def __init__(self, index: VectorIndex, k: int, ef: int = 0, capacity: int = 0, max_batch: int = 0, n_streams: int = 0,
+                 ctas_per_sm: int = 0, cta_warps: int = 0, rows_in_flight: int = 0, visited_log2: int = 0):
+        self.L, self.index, self.k = index.L, index, int(k)
+        cfg = _ServiceConfig(int(k), int(ef), capacity, max_batch, n_streams, ctas_per_sm, cta_warps, rows_in_flight,
+                             visited_log2)
+        h = C.c_void_p()
+        _ck(self.L.hx_service_create(index.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hx_service_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit(self, query) -> int:
+        qa, qp = _f32(query)
+        if qa.size != self.index.dim:
+            raise HelixDbError(HX_ERR_INVALID_DIMENSION, f"invalid dimension: expected {self.index.dim}, got {qa.size}")
+        t = C.c_uint64(0)
+        _ck(self.L.hx_service_submit(self.h, qp, C.byref(t)))
+        return int(t.value)
+
+    def _out(self):
+        return np.zeros(self.k, dtype=np.uint64), np.zeros(self.k, dtype=np.float32), C.c_uint32(0)
+
+    def poll(self, ticket: int):
+        """None while the query is running, else the list of SearchResult (raises the query's own error)."""
+        ids, sc, cnt = self._out()
+        done = C.c_int32(0)
+        _ck(self.L.hx_service_poll(self.h, ticket, C.byref(done), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                   sc.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
+        if not done.value:
+            return None
+        return [SearchResult(ids[i], sc[i]) for i in range(int(cnt.value))]
+
+    def wait(self, ticket: int):
+        ids, sc, cnt = self._out()
+        _ck(self.L.hx_service_wait(self.h, ticket, ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                   sc.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
+        return [SearchResult(ids[i], sc[i]) for i in range(int(cnt.value))]
+
+    def search(self, query):
+        qa, qp = _f32(query)
+        if qa.size != self.index.dim:
+            raise HelixDbError(HX_ERR_INVALID_DIMENSION, f"invalid dimension: expected {self.index.dim}, got {qa.size}")
+        ids, sc, cnt = self._out()
+        _ck(self.L.hx_service_search(self.h, qp, ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                     sc.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
+        return [SearchResult(ids[i], sc[i]) for i in range(int(cnt.value))]
+
+    def stats(self) -> dict:
+        st = ServiceStats()
+        _ck(self.L.hx_service_get_stats(self.h, C.byref(st)))
+        return st.as_dict()
 
 
 def merge_topk_device(device, d_all_ids, d_all_scores, d_all_counts, n_shards, B, k, d_out_ids, d_out_scores,

@@ -98,6 +98,25 @@ static uint32_t host_validate(const float* v, uint32_t dim, int metric, bool has
   return HX_ST_OK;
 }
 
+static hx_status status_from_word(uint32_t w, size_t which, const char* what);
+
+// Empty / unpopulated index: the reference validates the query first (search.rs:1101-1128, restricted.rs:539-566) and only
+// then answers Ok(vec![]).  No device work: every query is validated on the host.
+static hx_status answer_empty_index(const hx_index* ix, const float* queries, size_t B, uint32_t* out_counts,
+                                    hx_status* out_status) {
+  float limit = 0.f;
+  const uint32_t dim = ix->cfg.dimension;
+  const bool has_limit = component_limit(ix->cfg.metric, dim, &limit);
+  for (size_t b = 0; b < B; ++b) {
+    const uint32_t w = host_validate(queries + b * (size_t)dim, dim, ix->cfg.metric, has_limit, limit);
+    const hx_status st = w == 0u ? HX_OK : status_from_word(w, b, "query");
+    out_counts[b] = 0;
+    if (out_status) out_status[b] = st;
+    else if (st) return st;
+  }
+  return HX_OK;
+}
+
 static hx_status status_from_word(uint32_t w, size_t which, const char* what) {
   const uint32_t code = w >> 24, idx = w & 0xffffffu;
   hx_set_error_index(idx);
@@ -204,6 +223,7 @@ void HxScratch::destroy() {
   d_qstatus.release(); d_out_counts.release(); d_qstats.release(); d_err.release(); d_epochs.release();
   d_cand_slots.release(); d_out_ids.release(); d_cand_ids.release(); d_cand_offsets.release(); d_keys.release();
   d_stamps.release();
+  d_tiepool.release(); d_tiebusy.release(); d_qerr.release(); h_qerr.release();
   d_vtab.release(); d_vpool.release(); d_vbusy.release(); d_prof.release(); d_pstats.release(); d_qsim.release();
   for (auto& m : misc) m.release();
   h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
@@ -220,7 +240,7 @@ hx_status hx_acquire_scratch(hx_index* ix, HxScratch** out) {
         *out = s;
         return HX_OK;
       }
-    if (ix->pool.size() < 4) {
+    if (ix->pool.size() < HX_SCRATCH_POOL_MAX) {
       HxScratch* s = new HxScratch();
       cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
       if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
@@ -248,11 +268,14 @@ void hx_release_scratch(hx_index* ix, HxScratch* s) {
   ix->cv.notify_one();
 }
 
-// Device-buffer calls are ordered by the caller's stream and share one dedicated scratch set.
-static hx_status dev_scratch(hx_index* ix, HxScratch** out) {
+// Device-buffer calls are ordered by the caller's stream: one dedicated scratch set per stream, so calls issued on
+// different streams (from different threads) never share the error word, the query counter or the visited tables.
+static hx_status dev_scratch(hx_index* ix, cudaStream_t stream, HxScratch** out) {
   std::lock_guard<std::mutex> lk(ix->mu);
-  if (!ix->dev_scratch) ix->dev_scratch = new HxScratch();
-  *out = ix->dev_scratch;
+  HxScratch*& s = ix->dev_scratch[stream];
+  if (!s) s = new HxScratch();
+  ix->last_dev_scratch = s;
+  *out = s;
   return HX_OK;
 }
 
@@ -324,10 +347,11 @@ extern "C" void hx_index_destroy(hx_index* ix) {
     s->destroy();
     delete s;
   }
-  if (ix->dev_scratch) {
-    ix->dev_scratch->destroy();
-    delete ix->dev_scratch;
+  for (auto& kv : ix->dev_scratch) {
+    kv.second->destroy();
+    delete kv.second;
   }
+  ix->dev_scratch.clear();
   ix->free_graph();
   ix->free_vectors();
   if (ix->d_planes_t) cudaFree(ix->d_planes_t);
@@ -842,7 +866,11 @@ extern "C" hx_status hx_index_set_entry(hx_index* ix, uint64_t entry_point, uint
 
 // Turn the staged per-layer CSR rows into the fixed-stride device image.
 hx_status hx_finalize_graph(hx_index* ix) {
-  if (!ix->graph_dirty) return HX_OK;
+  if (!ix->graph_dirty.load(std::memory_order_acquire)) return HX_OK;
+  // Searches may race to be the first after a load: exactly one finalises, the others wait here and then see the
+  // finished image (the search path never mutates index state otherwise).
+  std::lock_guard<std::mutex> fin(ix->fin_mu);
+  if (!ix->graph_dirty.load(std::memory_order_acquire)) return HX_OK;
   HX_CUDA(cudaSetDevice(ix->device));
   const size_t n = ix->n;
   // free previous device graph but keep staging
@@ -853,7 +881,7 @@ hx_status hx_finalize_graph(hx_index* ix) {
   ix->populated = pop;
   ix->staged.swap(staged);
   if (n == 0) {
-    ix->graph_dirty = false;
+    ix->graph_dirty.store(false, std::memory_order_release);
     return HX_OK;
   }
   uint32_t max0 = ix->lim0, maxu = ix->cfg.m;
@@ -918,7 +946,7 @@ hx_status hx_finalize_graph(hx_index* ix) {
   HX_CUDA(cudaMemcpy(ix->d_upper_deg, upper_deg.data(), upper_deg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   HX_CUDA(cudaMemcpy(ix->d_level, level.data(), n, cudaMemcpyHostToDevice));
   ix->staged.clear();
-  ix->graph_dirty = false;
+  ix->graph_dirty.store(false, std::memory_order_release);
   return HX_OK;
 }
 
@@ -1028,7 +1056,8 @@ static hx_status check_params(const hx_index* ix, const hx_search_params* p, uin
 }
 
 // Upload B host queries and produce q_hdr / q_status on the device (host-side for small B, kernel otherwise).
-static hx_status stage_queries(hx_index* ix, HxScratch* s, const float* queries, size_t B, uint32_t* launches) {
+static hx_status stage_queries(hx_index* ix, HxScratch* s, const float* queries, size_t B, uint32_t* launches,
+                               bool per_query = false) {
   const uint32_t dim = ix->cfg.dimension;
   hx_status rc;
   if ((rc = s->d_queries.reserve(B * (size_t)dim))) return rc;
@@ -1042,9 +1071,9 @@ static hx_status stage_queries(hx_index* ix, HxScratch* s, const float* queries,
     if ((rc = s->h_status.reserve(B))) return rc;
     for (size_t b = 0; b < B; ++b) {
       const uint32_t w = host_validate(queries + b * (size_t)dim, dim, ix->cfg.metric, has_limit, limit);
-      if (w != HX_ST_OK) return status_from_word(w, b, "query");
-      s->h_status.p[b] = 0;
-      s->h_qhdr.p[b] = ix->cfg.metric == HX_METRIC_COSINE ? host_cosine_norm(queries + b * (size_t)dim, dim) : 0.0f;
+      if (w != HX_ST_OK && !per_query) return status_from_word(w, b, "query");
+      s->h_status.p[b] = w;   // per-query mode: the kernels skip a query whose status word is set
+      s->h_qhdr.p[b] = (w == HX_ST_OK && ix->cfg.metric == HX_METRIC_COSINE) ? host_cosine_norm(queries + b * (size_t)dim, dim) : 0.0f;
     }
     HX_CUDA(cudaMemcpyAsync(s->d_qhdr.p, s->h_qhdr.p, B * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     HX_CUDA(cudaMemcpyAsync(s->d_qstatus.p, s->h_status.p, B * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
@@ -1074,8 +1103,104 @@ static hx_status prepare_device_queries(hx_index* ix, HxScratch* s, const float*
 }
 
 // ---- HNSW launch ---------------------------------------------------------------------------------
+#define HX_TIE_POOL_N 8u
+#define HX_TIE_POOL_CAP 65536u
+// overflow regions of the tie stack + per-query error words on one scratch set
+static hx_status setup_tie_pool(HxScratch* s, HxRingArgs* rg, cudaStream_t stream) {
+  hx_status rc;
+  if (!s->tiepool_init) {
+    if ((rc = s->d_tiepool.reserve((size_t)HX_TIE_POOL_N * HX_TIE_POOL_CAP))) return rc;
+    if ((rc = s->d_tiebusy.reserve(HX_TIE_POOL_N))) return rc;
+    HX_CUDA(cudaMemsetAsync(s->d_tiebusy.p, 0, HX_TIE_POOL_N * sizeof(uint32_t), stream));
+    s->tiepool_init = true;
+  }
+  rg->tie_pool = s->d_tiepool.p;
+  rg->tie_busy = s->d_tiebusy.p;
+  rg->tie_pool_n = HX_TIE_POOL_N;
+  rg->tie_pool_cap = HX_TIE_POOL_CAP;
+  return HX_OK;
+}
+
 static uint32_t hnsw_smem_bytes(const hx_index* ix, uint32_t ef, uint32_t fr_cap) {
   return ix->ld * 4u + ef * 8u + HX_TIE_CAP * 8u + fr_cap * 8u;
+}
+
+// ---- CTA-per-query ring build: configuration + launch (shared by hx_search's small-batch path and the query service) ----
+// Shared memory per CTA: [query (QCH == 0)] | RC row slots | beam / merge stage [ef] | tie stack | RC mbarriers | frontier |
+// scores | visited table.  `budget` = dynamic shared memory the CTA may take (227 KB: one CTA per SM; ~113 KB: two).
+bool hx_cta_ring_config(const hx_index* ix, uint32_t ef, uint32_t want_warps, uint32_t want_rc, uint32_t want_vt_log2,
+                        size_t budget, HxCtaRingCfg* c) {
+  const uint32_t chunks = ix->ld / 32;
+  const size_t rowbytes = (size_t)ix->ld * 4;
+  c->qch = chunks <= 8 ? 8 : chunks <= 24 ? 24 : chunks <= 48 ? 48 : 0;
+  c->fr_cap = round_up(std::max(std::max(ix->stride0, ix->stride_u), 32u), 32);
+  uint32_t lg = 12;
+  while ((1u << lg) < 64u * ef && lg < 24) lg++;
+  if (want_vt_log2 >= 6 && want_vt_log2 <= 24) lg = want_vt_log2;
+  uint32_t vt = 1u << lg;
+  const size_t fixed0 = (c->qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)c->fr_cap * 8 + 256;
+  const uint32_t min_rows = want_rc ? std::min(want_rc, 8u) : 8u;
+  while (vt > 1024 && fixed0 + (size_t)vt * 4 + min_rows * (rowbytes + 8) > budget) vt >>= 1;
+  if (fixed0 + (size_t)vt * 4 + rowbytes + 8 > budget) return false;
+  uint32_t rc = (uint32_t)std::min<size_t>(32, (budget - fixed0 - (size_t)vt * 4) / (rowbytes + 8));
+  if (want_rc) rc = std::min(rc, want_rc);
+  c->RC = rc;
+  c->vt_cap = vt;
+  c->smem = fixed0 - 256 + (size_t)vt * 4 + (size_t)rc * (rowbytes + 8);
+  const uint32_t max_warps = c->qch == 48 ? 8 : 12;
+  c->warps = want_warps ? std::min(want_warps, max_warps) : max_warps;
+  c->ef = ef;
+  return true;
+}
+
+template <typename F>
+static hx_status cta_ring_prepare(F* fn, int device, size_t smem) {
+  // the attribute is per function and device: set it once per (instantiation, device, size) instead of on every launch
+  static std::atomic<size_t> set_for[64];
+  const int d = device & 63;
+  if (set_for[d].load(std::memory_order_relaxed) < smem) {
+    HX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set_for[d].store(smem, std::memory_order_relaxed);
+  }
+  return HX_OK;
+}
+
+hx_status hx_launch_cta_ring(hx_index* ix, const HxCtaRingCfg& c, const HxHnswArgs& a, const HxRingArgs& rg, uint32_t grid,
+                             cudaStream_t stream, int* ctas_per_sm) {
+  const HxDev dev = ix->dev();
+  hx_status rc = HX_OK;
+#define HX_CTA_GO(M, Q, NBV)                                                                                          \
+  do {                                                                                                                \
+    if ((rc = cta_ring_prepare(k_hnsw_search_cta_ring<M, Q, NBV>, ix->device, c.smem))) return rc;                     \
+    if (ctas_per_sm)                                                                                                  \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_hnsw_search_cta_ring<M, Q, NBV>, (int)c.warps * 32, \
+                                                    c.smem);                                                          \
+    if (grid)                                                                                                         \
+      k_hnsw_search_cta_ring<M, Q, NBV><<<grid, c.warps * 32, c.smem, stream>>>(dev, a, rg, c.RC, c.vt_cap);          \
+  } while (0)
+#define HX_CTA_NB(M, Q)                                                                                               \
+  do {                                                                                                                \
+    if (c.ef <= 128) HX_CTA_GO(M, Q, 4);                                                                              \
+    else HX_CTA_GO(M, Q, 0);                                                                                          \
+  } while (0)
+#define HX_CTA_Q(M)                                                                                                   \
+  do {                                                                                                                \
+    if (c.qch == 8) HX_CTA_NB(M, 8);                                                                                  \
+    else if (c.qch == 24) HX_CTA_NB(M, 24);                                                                           \
+    else if (c.qch == 48) HX_CTA_NB(M, 48);                                                                           \
+    else HX_CTA_NB(M, 0);                                                                                             \
+  } while (0)
+  if (ix->cfg.metric == HX_METRIC_EUCLIDEAN) HX_CTA_Q(HXM_EUCLIDEAN);
+  else if (ix->cfg.metric == HX_METRIC_COSINE) HX_CTA_Q(HXM_COSINE);
+  else {
+    hx_set_error("the CTA ring build serves the Euclidean and cosine metrics");
+    return HX_ERR_UNSUPPORTED;
+  }
+#undef HX_CTA_Q
+#undef HX_CTA_NB
+#undef HX_CTA_GO
+  if (grid) HX_CUDA(cudaGetLastError());
+  return HX_OK;
 }
 
 struct HxFusedArgs {   // pipelined host-buffer search: validation inside the ring kernel, start gated on `avail`
@@ -1095,11 +1220,13 @@ static bool hnsw_uses_ring(const hx_index* ix, size_t B) {
 static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries, size_t B, uint32_t k, uint32_t ef,
                              uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts, uint32_t* d_qstats,
                              cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1, bool* timed, uint32_t* launches,
-                             const HxFusedArgs* fused = nullptr) {
+                             const HxFusedArgs* fused = nullptr, bool sticky_flags = false) {
   *timed = false;
   hx_status rc = hx_finalize_graph(ix);
   if (rc) return rc;
+  if ((rc = s->d_qerr.reserve(B))) return rc;
   if (ix->n == 0 || !ix->populated || !ix->d_nbr0) {   // VectorIndexState::Empty => Ok(vec![]) (search.rs:1127-1128)
+    HX_CUDA(cudaMemsetAsync(s->d_qerr.p, 0, B * sizeof(uint32_t), stream));
     HX_CUDA(cudaMemsetAsync(d_out_counts, 0, B * sizeof(uint32_t), stream));
     if (d_qstats) HX_CUDA(cudaMemsetAsync(d_qstats, 0, B * 4 * sizeof(uint32_t), stream));
     return HX_OK;
@@ -1173,19 +1300,21 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     else ring_wstride = round_up((uint32_t)(fixed0 + (size_t)ring_R * (rowbytes + 8)), 128);
   }
   size_t cta_ring_smem = 0;
+  HxCtaRingCfg cta_cfg{};
   if (use_cta_ring) {
     // rows in flight first (up to 32), then the largest visited table that still fits (at least 1024 entries)
-    const size_t fixed0 = (ring_qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 8 + 256;
-    cta_vt_cap = vt_cap;
-    while (cta_vt_cap > 1024 && fixed0 + (size_t)cta_vt_cap * 4 + 8 * (rowbytes + 8) > ring_budget) cta_vt_cap >>= 1;
-    if (fixed0 + (size_t)cta_vt_cap * 4 + rowbytes + 8 > ring_budget) {
+    uint32_t want_rc = 0, want_warps = 0;
+    if (const char* env = getenv("HX_RING_R")) { const int v = atoi(env); if (v >= 1 && v <= 32) want_rc = (uint32_t)v; }
+    if (const char* env = getenv("HX_LAT_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 12) want_warps = (uint32_t)v; }
+    uint32_t want_lg = 0;
+    if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) want_lg = (uint32_t)v; }
+    if (!hx_cta_ring_config(ix, ef, want_warps, want_rc, want_lg, ring_budget, &cta_cfg) || cta_cfg.fr_cap != fr_cap) {
       use_cta_ring = false;
     } else {
-      ring_R = (uint32_t)std::min<size_t>(32, (ring_budget - fixed0 - (size_t)cta_vt_cap * 4) / (rowbytes + 8));
-      if (const char* env = getenv("HX_RING_R")) { const int v = atoi(env); if (v >= 1 && v <= 32) ring_R = std::min(ring_R, (uint32_t)v); }
-      cta_ring_smem = fixed0 - 256 + (size_t)cta_vt_cap * 4 + (size_t)ring_R * (rowbytes + 8);
-      cta_warps = ring_qch == 48 ? 8 : 12;
-      if (const char* env = getenv("HX_LAT_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= (int)cta_warps) cta_warps = (uint32_t)v; }
+      cta_vt_cap = cta_cfg.vt_cap;
+      ring_R = cta_cfg.RC;
+      cta_ring_smem = cta_cfg.smem;
+      cta_warps = cta_cfg.warps;
     }
   }
   HxRingArgs rg{};
@@ -1222,6 +1351,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     if (const char* env = getenv("HX_L2_HINT")) rg.l2_hint = atoi(env) ? 1u : 0u;
     rg.prefetch_below = ef / 2 + 1;
     if (const char* env = getenv("HX_PREFETCH_BELOW")) { const int v = atoi(env); if (v >= 0) rg.prefetch_below = (uint32_t)v; }
+    if ((rc = setup_tie_pool(s, &rg, stream))) return rc;
     rg.batch_admit = 1;
     if (const char* env = getenv("HX_LAT_ADMIT")) rg.batch_admit = strcmp(env, "seq") == 0 ? 0u : 1u;
     rg.l2_spec = 0;   // measured: the speculative row prefetch costs more than it hides (profiles/r01_latency_*); opt-in
@@ -1270,9 +1400,13 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     s->stamp_stride = stride;
     s->stamp_n = ix->n;
   }
+  const bool had_err = s->d_err.p != nullptr;
   if ((rc = s->d_err.reserve(4))) return rc;   // [0] error flags, [1] query counter of the ring build, [2] queries landed
-  HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, 2 * sizeof(uint32_t), stream));
+  // device-buffer calls keep the flag word sticky (ORed over launches until hx_device_flags reads and clears it)
+  if (sticky_flags && had_err) HX_CUDA(cudaMemsetAsync(s->d_err.p + 1, 0, sizeof(uint32_t), stream));
+  else HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, 2 * sizeof(uint32_t), stream));
   rg.counter = s->d_err.p + 1;
+  if (!(use_ring || use_cta_ring)) HX_CUDA(cudaMemsetAsync(s->d_qerr.p, 0, B * sizeof(uint32_t), stream));   // first-generation kernels report batch flags only
   HxHnswArgs a{};
   a.queries = d_queries;
   a.q_hdr = s->d_qhdr.p;
@@ -1288,6 +1422,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   a.epochs = s->d_epochs.p;
   a.stamp_stride = s->stamp_stride;
   a.err_flags = s->d_err.p;
+  a.q_err = s->d_qerr.p;
   a.fr_cap = fr_cap;
   if (fused) {
     if (!use_ring) {
@@ -1317,26 +1452,10 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
                                  (int)smem_launch));                                                               \
     k_hnsw_search_ring<M, Q><<<grid, ring_wpc * 32, smem_launch, stream>>>(dev, a, rg, ring_wstride, ring_R);      \
   } while (0)
-#define HX_LAUNCH_CTA_RING2(M, Q, NBV)                                                                             \
-  do {                                                                                                             \
-    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_cta_ring<M, Q, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                 (int)smem_launch));                                                               \
-    k_hnsw_search_cta_ring<M, Q, NBV><<<grid, cta_warps * 32, smem_launch, stream>>>(dev, a, rg, ring_R,           \
-                                                                                     cta_vt_cap);                  \
-  } while (0)
-#define HX_LAUNCH_CTA_RING(M, Q)                                                                                   \
-  do {                                                                                                             \
-    if (ef <= 128) HX_LAUNCH_CTA_RING2(M, Q, 4);                                                                   \
-    else HX_LAUNCH_CTA_RING2(M, Q, 0);                                                                             \
-  } while (0)
 #define HX_LAUNCH_HNSW(M)                                                                                          \
   do {                                                                                                             \
     if (use_cta_ring && M != HXM_MANHATTAN) {                                                                      \
-      constexpr int MR = M == HXM_MANHATTAN ? HXM_EUCLIDEAN : M;                                                   \
-      if (ring_qch == 8) HX_LAUNCH_CTA_RING(MR, 8);                                                                \
-      else if (ring_qch == 24) HX_LAUNCH_CTA_RING(MR, 24);                                                         \
-      else if (ring_qch == 48) HX_LAUNCH_CTA_RING(MR, 48);                                                         \
-      else HX_LAUNCH_CTA_RING(MR, 0);                                                                              \
+      if ((rc = hx_launch_cta_ring(ix, cta_cfg, a, rg, grid, stream, nullptr))) return rc;                          \
     } else if (use_ring && M != HXM_MANHATTAN) {                                                                   \
       constexpr int MR = M == HXM_MANHATTAN ? HXM_EUCLIDEAN : M;                                                   \
       if (ring_qch == 8) HX_LAUNCH_RING(MR, 8);                                                                    \
@@ -1371,8 +1490,6 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   }
 #undef HX_LAUNCH_HNSW
 #undef HX_LAUNCH_RING
-#undef HX_LAUNCH_CTA_RING
-#undef HX_LAUNCH_CTA_RING2
 #undef HX_LAUNCH_WARP
   HX_CUDA(cudaGetLastError());
   HX_CUDA(cudaEventRecord(e1, stream));
@@ -1395,46 +1512,52 @@ static hx_status check_device_flags(uint32_t flags) {
     return HX_ERR_INVARIANT_VIOLATION;
   }
   if (flags & HXF_TIE_OVERFLOW) {
-    hx_set_error("more than %d exact score ties at the beam boundary", HX_TIE_CAP);
+    hx_set_error("more than %u exact score ties at the beam boundary (tie-stack overflow regions exhausted)",
+                 (unsigned)(HX_TIE_CAP + HX_TIE_POOL_CAP));
     return HX_ERR_INVARIANT_VIOLATION;
   }
   return HX_OK;
 }
 
 // ---- result download -------------------------------------------------------------------------------------------------------
-// Small calls (one query per call is the reference's usage) are dominated by fixed costs: five device-to-host copies of a few
+// Small calls (one query per call is the reference's usage) are dominated by fixed costs: six device-to-host copies of a few
 // bytes each cost more than the data.  Their results are packed into one block by a tiny kernel and cross PCIe in ONE copy.
 static __global__ void k_pack_small(const uint64_t* __restrict__ ids, const float* __restrict__ scores,
                                     const uint32_t* __restrict__ counts, const uint32_t* __restrict__ status,
-                                    const uint32_t* __restrict__ err, uint32_t n_ids, uint32_t B, unsigned char* __restrict__ out) {
+                                    const uint32_t* __restrict__ qerr, const uint32_t* __restrict__ err, uint32_t n_ids,
+                                    uint32_t B, unsigned char* __restrict__ out) {
   uint64_t* o_ids = reinterpret_cast<uint64_t*>(out);
   float* o_sc = reinterpret_cast<float*>(o_ids + n_ids);
   uint32_t* o_cnt = reinterpret_cast<uint32_t*>(o_sc + n_ids);
   uint32_t* o_st = o_cnt + B;
+  uint32_t* o_qe = o_st + B;
   for (uint32_t i = threadIdx.x; i < n_ids; i += blockDim.x) { o_ids[i] = ids[i]; o_sc[i] = scores[i]; }
-  for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) { o_cnt[i] = counts[i]; o_st[i] = status[i]; }
-  if (threadIdx.x == 0) o_st[B] = err ? err[0] : 0u;
+  for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) { o_cnt[i] = counts[i]; o_st[i] = status[i]; o_qe[i] = qerr ? qerr[i] : 0u; }
+  if (threadIdx.x == 0) o_qe[B] = err ? err[0] : 0u;
 }
 
 struct HxDownload {
   bool packed = false;
   size_t n_ids = 0, B = 0;
 };
-// enqueue the download of ids / scores / counts / per-query status / error flags on s->stream
+// enqueue the download of ids / scores / counts / per-query status / per-query error flags / batch flags on s->stream
 static hx_status enqueue_results(HxScratch* s, size_t B, uint32_t k, uint64_t* out_ids, float* out_scores,
                                  uint32_t* out_counts, uint32_t* launches, HxDownload* dl) {
   hx_status rc;
   dl->n_ids = B * (size_t)k;
   dl->B = B;
   if ((rc = s->h_status.reserve(B))) return rc;
+  if ((rc = s->h_qerr.reserve(B))) return rc;
   if ((rc = s->h_err.reserve(1))) return rc;
   s->h_err.p[0] = 0;
+  const bool have_qerr = s->d_qerr.p != nullptr && s->d_qerr.cap >= B;
   if (dl->n_ids <= 4096 && s->d_err.p) {
-    const size_t bytes = dl->n_ids * 12 + B * 8 + 4;
+    const size_t bytes = dl->n_ids * 12 + B * 12 + 4;
     if ((rc = s->d_block.reserve(bytes))) return rc;
     if ((rc = s->h_block.reserve(bytes))) return rc;
-    k_pack_small<<<1, 256, 0, s->stream>>>(s->d_out_ids.p, s->d_out_scores.p, s->d_out_counts.p, s->d_qstatus.p, s->d_err.p,
-                                          (uint32_t)dl->n_ids, (uint32_t)B, s->d_block.p);
+    k_pack_small<<<1, 256, 0, s->stream>>>(s->d_out_ids.p, s->d_out_scores.p, s->d_out_counts.p, s->d_qstatus.p,
+                                          have_qerr ? s->d_qerr.p : nullptr, s->d_err.p, (uint32_t)dl->n_ids, (uint32_t)B,
+                                          s->d_block.p);
     HX_CUDA(cudaGetLastError());
     (*launches)++;
     HX_CUDA(cudaMemcpyAsync(s->h_block.p, s->d_block.p, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -1445,6 +1568,8 @@ static hx_status enqueue_results(HxScratch* s, size_t B, uint32_t k, uint64_t* o
   HX_CUDA(cudaMemcpyAsync(out_scores, s->d_out_scores.p, dl->n_ids * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   HX_CUDA(cudaMemcpyAsync(out_counts, s->d_out_counts.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   HX_CUDA(cudaMemcpyAsync(s->h_status.p, s->d_qstatus.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  if (have_qerr) HX_CUDA(cudaMemcpyAsync(s->h_qerr.p, s->d_qerr.p, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  else memset(s->h_qerr.p, 0, B * sizeof(uint32_t));
   if (s->d_err.p) HX_CUDA(cudaMemcpyAsync(s->h_err.p, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   return HX_OK;
 }
@@ -1456,11 +1581,47 @@ static void finish_results(HxScratch* s, const HxDownload& dl, uint64_t* out_ids
   memcpy(out_scores, b + dl.n_ids * 8, dl.n_ids * 4);
   memcpy(out_counts, b + dl.n_ids * 12, dl.B * 4);
   memcpy(s->h_status.p, b + dl.n_ids * 12 + dl.B * 4, dl.B * 4);
-  memcpy(s->h_err.p, b + dl.n_ids * 12 + dl.B * 8, 4);
+  memcpy(s->h_qerr.p, b + dl.n_ids * 12 + dl.B * 8, dl.B * 4);
+  memcpy(s->h_err.p, b + dl.n_ids * 12 + dl.B * 12, 4);
+}
+
+// Per-query outcome of a finished batch.  The reference runs one query per call, so one query's failure must not take
+// the others down: with `out_status` every query gets its own code (and the call returns HX_OK); without it the call
+// fails with the first failing query's error, like B sequential reference calls stopped at the first Err.
+static hx_status report_batch(HxScratch* s, size_t B, uint32_t* out_counts, hx_status* out_status) {
+  hx_status first = HX_OK;
+  const uint32_t batch_flags = s->h_err.p[0];
+  for (size_t b = 0; b < B; ++b) {
+    hx_status st = HX_OK;
+    if (s->h_status.p[b] != HX_ST_OK) st = status_from_word(s->h_status.p[b], b, "query");
+    else if (s->h_qerr.p[b]) st = check_device_flags(s->h_qerr.p[b]);
+    if (out_status) {
+      out_status[b] = st;
+      if (st) out_counts[b] = 0;
+    } else if (st) {
+      return st;
+    }
+    if (st && !first) first = st;
+  }
+  if (!out_status && batch_flags) {   // a flag no query owns (copy time-out, first-generation kernels)
+    hx_status rc = check_device_flags(batch_flags);
+    if (rc) return rc;
+  }
+  if (out_status && batch_flags && !first) {   // batch-level failure with no owner: every query is suspect
+    const hx_status rc = check_device_flags(batch_flags);
+    if (rc)
+      for (size_t b = 0; b < B; ++b) { out_status[b] = rc; out_counts[b] = 0; }
+  }
+  return HX_OK;
 }
 
 static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
-                                  uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats);
+                                  uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats,
+                                  hx_status* out_status = nullptr);
+static hx_status hx_search_policy(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                  const hx_policy_params* policy, const uint64_t* query_simhash, uint64_t* out_ids,
+                                  float* out_scores, uint32_t* out_counts, hx_stats* stats, hx_policy_stats* pstats,
+                                  hx_status* out_status);
 
 extern "C" hx_status hx_search(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
                                uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats) {
@@ -1469,8 +1630,23 @@ extern "C" hx_status hx_search(hx_index* ix, const float* queries, size_t B, con
   return hx_search_strict(ix, queries, B, p, out_ids, out_scores, out_counts, stats);
 }
 
+// B independent queries with a status PER QUERY (the reference runs one query per call: one invalid query, or one
+// query that exhausts a device-side bound, fails alone).  Returns HX_OK whenever the batch itself could be executed.
+extern "C" hx_status hx_search_batch(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                     uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_status* out_status,
+                                     hx_stats* stats) {
+  if (B && !out_status) {
+    hx_set_error("hx_search_batch: out_status is required");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (p && !(p->simhash_mode == HX_SIMHASH_OFF && !(p->pre_sampling_ratio >= 0.0f && p->pre_sampling_ratio < 1.0f)))
+    return hx_search_policy(ix, queries, B, p, nullptr, nullptr, out_ids, out_scores, out_counts, stats, nullptr, out_status);
+  return hx_search_strict(ix, queries, B, p, out_ids, out_scores, out_counts, stats, out_status);
+}
+
 static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
-                                  uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+                                  uint64_t* out_ids, float* out_scores, uint32_t* out_counts, hx_stats* stats,
+                                  hx_status* out_status) {
   if (!ix) {
     hx_set_error("null index handle");
     return HX_ERR_INDEX_NOT_FOUND;
@@ -1485,6 +1661,7 @@ static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, 
     return HX_ERR_INVALID_PARAMETER;
   }
   HX_CUDA(cudaSetDevice(ix->device));
+  if (ix->n == 0 || !ix->populated) return answer_empty_index(ix, queries, B, out_counts, out_status);
   HxScratch* s = nullptr;
   if ((rc = hx_acquire_scratch(ix, &s))) return rc;
   ScratchGuard guard{ix, s};
@@ -1525,7 +1702,7 @@ static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, 
       fz.has_limit = component_limit(ix->cfg.metric, dim, &fz.limit) ? 1 : 0;
     }
   }
-  if (!pipelined && (rc = stage_queries(ix, s, queries, B, &launches))) return rc;
+  if (!pipelined && (rc = stage_queries(ix, s, queries, B, &launches, out_status != nullptr))) return rc;
   if ((rc = s->d_out_ids.reserve(B * (size_t)k))) return rc;
   if ((rc = s->d_out_scores.reserve(B * (size_t)k))) return rc;
   if ((rc = s->d_out_counts.reserve(B))) return rc;
@@ -1547,9 +1724,7 @@ static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, 
   }
   HX_CUDA(cudaStreamSynchronize(s->stream));
   finish_results(s, dl, out_ids, out_scores, out_counts);
-  for (size_t b = 0; b < B; ++b)
-    if (s->h_status.p[b] != HX_ST_OK) return status_from_word(s->h_status.p[b], b, "query");
-  if ((rc = check_device_flags(s->h_err.p[0]))) return rc;
+  if ((rc = report_batch(s, B, out_counts, out_status))) return rc;
   float ms = 0.f;
   if (timed && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
     ix->last_kernel_ms = ms;
@@ -1588,8 +1763,8 @@ extern "C" hx_status hx_search_device(hx_index* ix, const float* d_queries, size
   }
   HX_CUDA(cudaSetDevice(ix->device));
   HxScratch* s = nullptr;
-  if ((rc = dev_scratch(ix, &s))) return rc;
   cudaStream_t stream = (cudaStream_t)cuda_stream;
+  if ((rc = dev_scratch(ix, stream, &s))) return rc;
   uint32_t launches = 0;
   // the ring build validates each query itself (ValidatedMetricVector::try_new + header by the warp that owns it): no
   // separate k_validate_and_header launch in front of it
@@ -1612,7 +1787,8 @@ extern "C" hx_status hx_search_device(hx_index* ix, const float* d_queries, size
   if ((rc = s->ring_next(&e0, &e1))) return rc;
   bool timed = false;
   if ((rc = launch_hnsw(ix, s, d_queries, B, k, ef, d_out_ids, d_out_scores, d_out_counts,
-                        want_stats ? s->d_qstats.p : nullptr, stream, e0, e1, &timed, &launches, fused ? &fz : nullptr)))
+                        want_stats ? s->d_qstats.p : nullptr, stream, e0, e1, &timed, &launches, fused ? &fz : nullptr,
+                        /*sticky_flags=*/true)))
     return rc;
   if (!timed && s->ring_pending) s->ring_pending--;
   if (want_stats) {   // stats need a sync; the throughput path leaves collect_stats = 0
@@ -1630,6 +1806,31 @@ extern "C" hx_status hx_search_device(hx_index* ix, const float* d_queries, size
                                stats->distance_computations * (4ull + 4ull * ix->cfg.dimension);
   }
   if (stats) stats->kernel_launches = launches;
+  return HX_OK;
+}
+
+// Error flags raised by the device-buffer calls issued on `cuda_stream` since the previous hx_device_flags on that
+// stream (ORed over launches; synchronises the stream; clears the word).  *out_status = the HelixDbError the flags map to.
+extern "C" hx_status hx_device_flags(hx_index* ix, void* cuda_stream, uint32_t* out_flags, hx_status* out_status) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  HX_CUDA(cudaSetDevice(ix->device));
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  HxScratch* s = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    auto it = ix->dev_scratch.find(stream);
+    if (it != ix->dev_scratch.end()) s = it->second;
+  }
+  uint32_t flags = 0;
+  if (s && s->d_err.p) {
+    HX_CUDA(cudaMemcpyAsync(&flags, s->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, sizeof(uint32_t), stream));
+    HX_CUDA(cudaStreamSynchronize(stream));
+  } else {
+    HX_CUDA(cudaStreamSynchronize(stream));
+  }
+  if (out_flags) *out_flags = flags;
+  if (out_status) *out_status = check_device_flags(flags);
   return HX_OK;
 }
 
@@ -1763,17 +1964,25 @@ static hx_status restricted_host(hx_index* ix, const float* queries, size_t B, c
     return HX_OK;
   }
   if ((shared && !cand_ids) || (!shared && (!cand_ids || !cand_offsets))) return HX_ERR_INVALID_PARAMETER;
+  // RoaringTreemap iteration order: ascending and unique within a set (the (score,id) tie rule and the "no duplicate
+  // results" guarantee depend on it; hx_candidates_create checks the same)
+  for (size_t b = 0; b < (shared ? 1 : B); ++b) {
+    const uint64_t lo = shared ? 0 : cand_offsets[b], hi = shared ? n_shared : cand_offsets[b + 1];
+    for (uint64_t i = lo + 1; i < hi; ++i)
+      if (cand_ids[i] <= cand_ids[i - 1]) {
+        hx_set_error("candidate ids must be ascending and unique (RoaringTreemap iteration order); set %zu position %llu",
+                     b, (unsigned long long)(i - lo));
+        return HX_ERR_INVALID_PARAMETER;
+      }
+  }
   HX_CUDA(cudaSetDevice(ix->device));
+  if (ix->n == 0 || !ix->populated)   // empty index => Ok(vec![]) after query validation (:563-566)
+    return answer_empty_index(ix, queries, B, out_counts, nullptr);
   HxScratch* s = nullptr;
   if ((rc = hx_acquire_scratch(ix, &s))) return rc;
   ScratchGuard guard{ix, s};
   uint32_t launches = 0;
   if ((rc = stage_queries(ix, s, queries, B, &launches))) return rc;
-  if (ix->n == 0 || !ix->populated) {   // empty index => Ok(vec![]) after query validation (:563-566)
-    HX_CUDA(cudaStreamSynchronize(s->stream));
-    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
-    return HX_OK;
-  }
   if ((rc = s->d_cand_ids.reserve(total))) return rc;
   if ((rc = s->d_cand_slots.reserve(total))) return rc;
   if ((rc = s->d_cand_offsets.reserve(B + 1))) return rc;
@@ -1934,16 +2143,12 @@ extern "C" hx_status hx_search_restricted_sets(hx_index* ix, const float* querie
     return HX_OK;
   }
   HX_CUDA(cudaSetDevice(ix->device));
+  if (ix->n == 0 || !ix->populated) return answer_empty_index(ix, queries, B, out_counts, nullptr);
   HxScratch* s = nullptr;
   if ((rc = hx_acquire_scratch(ix, &s))) return rc;
   ScratchGuard guard{ix, s};
   uint32_t launches = 0;
   if ((rc = stage_queries(ix, s, queries, B, &launches))) return rc;
-  if (ix->n == 0 || !ix->populated) {
-    HX_CUDA(cudaStreamSynchronize(s->stream));
-    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
-    return HX_OK;
-  }
   // per-query (pointer, length, key offset): 24 bytes per query over PCIe instead of 8 bytes per candidate
   if ((rc = s->h_cand_offsets.reserve(3 * B))) return rc;
   if ((rc = s->d_cand_offsets.reserve(3 * B))) return rc;
@@ -2033,7 +2238,7 @@ extern "C" hx_status hx_search_restricted_device(hx_index* ix, const float* d_qu
   }
   if (!d_cand_slots) return HX_ERR_INVALID_PARAMETER;
   HxScratch* s = nullptr;
-  if ((rc = dev_scratch(ix, &s))) return rc;
+  if ((rc = dev_scratch(ix, stream, &s))) return rc;
   uint32_t launches = 0;
   if ((rc = prepare_device_queries(ix, s, d_queries, B, stream, &launches))) return rc;
   const uint64_t total_keys = shared ? (uint64_t)B * total_cands : total_cands;
@@ -2288,6 +2493,8 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   rg.pool_cap = pool_cap;
   rg.counter = s->d_err.p + 1;
   rg.l2_hint = 1;
+  if ((rc = setup_tie_pool(s, &rg, stream))) return rc;
+  if ((rc = s->d_qerr.reserve(B))) return rc;
   rg.l2_spec = 1;   // policy kernel: fingerprints requested together with the visited probe (HX_POL_EARLY_SIM=0: after it)
   if (const char* env = getenv("HX_POL_EARLY_SIM")) rg.l2_spec = atoi(env) ? 1u : 0u;
   HxHnswArgs a{};
@@ -2302,6 +2509,7 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   a.out_counts = d_out_counts;
   a.q_stats = d_qstats;
   a.err_flags = s->d_err.p;
+  a.q_err = s->d_qerr.p;
   a.fr_cap = fr_cap;
   HxPolicyArgs pa{};
   pa.cfg.mode = p->simhash_mode;
@@ -2353,6 +2561,13 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
 extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
                                   const hx_policy_params* policy, const uint64_t* query_simhash, uint64_t* out_ids,
                                   float* out_scores, uint32_t* out_counts, hx_stats* stats, hx_policy_stats* pstats) {
+  return hx_search_policy(ix, queries, B, p, policy, query_simhash, out_ids, out_scores, out_counts, stats, pstats, nullptr);
+}
+
+static hx_status hx_search_policy(hx_index* ix, const float* queries, size_t B, const hx_search_params* p,
+                                  const hx_policy_params* policy, const uint64_t* query_simhash, uint64_t* out_ids,
+                                  float* out_scores, uint32_t* out_counts, hx_stats* stats, hx_policy_stats* pstats,
+                                  hx_status* out_status) {
   if (!ix) {
     hx_set_error("null index handle");
     return HX_ERR_INDEX_NOT_FOUND;
@@ -2365,7 +2580,7 @@ extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, 
     hx_search_params q = *p;
     q.simhash_mode = HX_SIMHASH_OFF;
     q.pre_sampling_ratio = 1.0f;
-    return hx_search_strict(ix, queries, B, &q, out_ids, out_scores, out_counts, stats);
+    return hx_search_strict(ix, queries, B, &q, out_ids, out_scores, out_counts, stats, out_status);
   }
   hx_policy_params pol;
   hx_policy_params_default(&pol);
@@ -2383,6 +2598,7 @@ extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, 
     return HX_ERR_INVALID_PARAMETER;
   }
   HX_CUDA(cudaSetDevice(ix->device));
+  if (ix->n == 0 || !ix->populated) return answer_empty_index(ix, queries, B, out_counts, out_status);
   // filtering needs the node fingerprints (cosine only, policy.rs:67-88); sampling needs the query's for its seed
   const bool filtering = ix->cfg.metric == HX_METRIC_COSINE && p->simhash_mode != HX_SIMHASH_OFF;
   if (filtering && ix->n && !ix->d_simhash) {
@@ -2397,7 +2613,7 @@ extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, 
   if ((rc = hx_acquire_scratch(ix, &s))) return rc;
   ScratchGuard guard{ix, s};
   uint32_t launches = 0;
-  if ((rc = stage_queries(ix, s, queries, B, &launches))) return rc;
+  if ((rc = stage_queries(ix, s, queries, B, &launches, out_status != nullptr))) return rc;
   if ((rc = s->d_out_ids.reserve(B * (size_t)k))) return rc;
   if ((rc = s->d_out_scores.reserve(B * (size_t)k))) return rc;
   if ((rc = s->d_out_counts.reserve(B))) return rc;
@@ -2428,9 +2644,7 @@ extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, 
     HX_CUDA(cudaMemcpyAsync(hps, s->d_pstats.p, sizeof(hps), cudaMemcpyDeviceToHost, s->stream));
   HX_CUDA(cudaStreamSynchronize(s->stream));
   finish_results(s, dl, out_ids, out_scores, out_counts);
-  for (size_t b = 0; b < B; ++b)
-    if (s->h_status.p[b] != HX_ST_OK) return status_from_word(s->h_status.p[b], b, "query");
-  if ((rc = check_device_flags(s->h_err.p[0]))) return rc;
+  if ((rc = report_batch(s, B, out_counts, out_status))) return rc;
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) {
     ix->last_kernel_ms = ms;
@@ -2458,40 +2672,52 @@ extern "C" hx_status hx_search_ex(hx_index* ix, const float* queries, size_t B, 
 extern "C" hx_status hx_last_kernel_ms(hx_index* ix, float* ms, uint32_t* launches) {
   if (!ix) return HX_ERR_INDEX_NOT_FOUND;
   HX_CUDA(cudaSetDevice(ix->device));
-  HxScratch* s = ix->dev_scratch;
-  if (s && s->ring_pending) {
-    // device-path launches since the previous call: sum their CUDA-event durations (synchronises)
-    const size_t cap = s->ring0.size();
-    float total = 0.f;
-    uint32_t cnt = 0;
-    size_t idx = (s->ring0.size() < 512) ? 0 : s->ring_pos;   // oldest pending entry
-    if (s->ring0.size() < 512) idx = s->ring0.size() - s->ring_pending;
-    else idx = (s->ring_pos + cap - s->ring_pending) % cap;
-    for (size_t i = 0; i < s->ring_pending; ++i) {
-      const size_t j = (idx + i) % cap;
-      float t = 0.f;
-      if (cudaEventSynchronize(s->ring1[j]) == cudaSuccess &&
-          cudaEventElapsedTime(&t, s->ring0[j], s->ring1[j]) == cudaSuccess) {
-        total += t;
-        cnt++;
-      } else {
-        cudaGetLastError();
+  std::vector<HxScratch*> devs;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (auto& kv : ix->dev_scratch) devs.push_back(kv.second);
+  }
+  float total = 0.f;
+  uint32_t cnt = 0;
+  bool any = false;
+  for (HxScratch* s : devs) {
+    if (s->ring_pending) {
+      // device-path launches since the previous call: sum their CUDA-event durations (synchronises)
+      any = true;
+      const size_t cap = s->ring0.size();
+      size_t idx;
+      if (s->ring0.size() < 512) idx = s->ring0.size() - s->ring_pending;
+      else idx = (s->ring_pos + cap - s->ring_pending) % cap;
+      for (size_t i = 0; i < s->ring_pending; ++i) {
+        const size_t j = (idx + i) % cap;
+        float t = 0.f;
+        if (cudaEventSynchronize(s->ring1[j]) == cudaSuccess &&
+            cudaEventElapsedTime(&t, s->ring0[j], s->ring1[j]) == cudaSuccess) {
+          total += t;
+          cnt++;
+        } else {
+          cudaGetLastError();
+        }
+      }
+      s->ring_pending = 0;
+    }
+    if (s->prof_init && s->d_prof.p) {   // HX_PHASE_PROF diagnostics: print and reset the phase cycle sums
+      unsigned long long h[8];
+      cudaDeviceSynchronize();
+      if (cudaMemcpy(h, s->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        fprintf(stderr, "HX_PHASE_PROF cycles: pop=%llu row+deg=%llu visited+issue=%llu wait+score=%llu admit=%llu  "
+                        "predicted-next hits=%llu of %llu expansions\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+        cudaMemset(s->d_prof.p, 0, sizeof(h));
       }
     }
-    s->ring_pending = 0;
+  }
+  if (any) {
     ix->last_kernel_ms = total;
     ix->last_kernel_launches = cnt;
-  }
-  if (s && s->prof_init && s->d_prof.p) {   // HX_PHASE_PROF diagnostics: print and reset the phase cycle sums
-    unsigned long long h[8];
-    cudaDeviceSynchronize();
-    if (cudaMemcpy(h, s->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
-      fprintf(stderr, "HX_PHASE_PROF cycles: pop=%llu row+deg=%llu visited+issue=%llu wait+score=%llu admit=%llu  "
-                      "predicted-next hits=%llu of %llu expansions\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
-      cudaMemset(s->d_prof.p, 0, sizeof(h));
-    }
   }
   if (ms) *ms = ix->last_kernel_ms;
   if (launches) *launches = ix->last_kernel_launches;
   return HX_OK;
 }
+
+#include "hx_service.inl"

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -87,6 +89,11 @@ struct HxScratch {
   DevBuf<uint8_t> d_stamps;
   DevBuf<uint32_t> d_vtab, d_vpool, d_vbusy;   // ring build: visited hash sets, overflow pool, pool busy flags
   uint32_t vpool_n = 0xffffffffu, vpool_cap = 0;
+  DevBuf<uint64_t> d_tiepool;                  // overflow regions of the tie stack (HxRingArgs::tie_pool)
+  DevBuf<uint32_t> d_tiebusy;
+  bool tiepool_init = false;
+  DevBuf<uint32_t> d_qerr;                     // per-query error flags
+  PinBuf<uint32_t> h_qerr;
   DevBuf<unsigned long long> d_prof;   // HX_PHASE_PROF diagnostics
   DevBuf<unsigned long long> d_pstats; // policy counters
   DevBuf<uint64_t> d_qsim;             // query fingerprints
@@ -142,7 +149,8 @@ struct hx_index {
   size_t n_upper_rows = 0;
   // graph (host staging until finalize)
   std::vector<HxLayerRows> staged;   // index = layer
-  bool graph_dirty = false;
+  std::atomic<bool> graph_dirty{false};   // set by the load calls, cleared by hx_finalize_graph (under fin_mu)
+  std::mutex fin_mu;
   bool populated = false;
   uint64_t entry_id = 0;
   uint32_t entry_slot = 0;
@@ -160,19 +168,38 @@ struct hx_index {
   std::mutex mu;
   std::condition_variable cv;
   std::vector<HxScratch*> pool;
-  HxScratch* dev_scratch = nullptr;   // device-buffer calls: stream-ordered by the caller, never pooled
+  // device-buffer calls are ordered by the caller's stream: one scratch set PER STREAM (calls on different streams may
+  // run concurrently and must not share the error word, the query counter or the visited tables)
+  std::map<cudaStream_t, HxScratch*> dev_scratch;
+  HxScratch* last_dev_scratch = nullptr;   // the stream hx_last_kernel_ms reports (most recent device-buffer call)
   // last dominant-kernel timing
-  float last_kernel_ms = 0.f;
-  uint32_t last_kernel_launches = 0;
+  std::atomic<float> last_kernel_ms{0.f};
+  std::atomic<uint32_t> last_kernel_launches{0};
+  // mirror version (SURVEY §8b snapshot semantics): the host stamps the (generation, visible sequence) the image was
+  // hydrated at; the Rust guard (read_index.rs:53-65) compares it with the request's snapshot before dispatching here
+  std::atomic<uint64_t> mirror_generation{0}, mirror_visible_seq{0};
 
   HxDev dev() const;
   void free_vectors();
   void free_graph();
 };
 
+#define HX_SCRATCH_POOL_MAX 64   // concurrent host-buffer calls per handle before a caller has to wait
 hx_status hx_acquire_scratch(hx_index* ix, HxScratch** out);
 void hx_release_scratch(hx_index* ix, HxScratch* s);
 hx_status hx_finalize_graph(hx_index* ix);
+
+// CTA-per-query ring build (k_hnsw_ring.cuh): launch configuration shared by hx_search's small-batch path and hx_service
+struct HxCtaRingCfg {
+  uint32_t qch, warps, RC, vt_cap, fr_cap, ef;
+  size_t smem;
+};
+struct HxHnswArgs;
+struct HxRingArgs;
+bool hx_cta_ring_config(const hx_index* ix, uint32_t ef, uint32_t want_warps, uint32_t want_rc, uint32_t want_vt_log2,
+                        size_t budget, HxCtaRingCfg* c);
+hx_status hx_launch_cta_ring(hx_index* ix, const HxCtaRingCfg& c, const HxHnswArgs& a, const HxRingArgs& rg, uint32_t grid,
+                             cudaStream_t stream, int* ctas_per_sm);
 bool hx_slot_of(const hx_index* ix, uint64_t id, uint32_t* slot);
 
 // implemented in k_build.cu / k_dense.cu

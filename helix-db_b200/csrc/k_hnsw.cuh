@@ -50,6 +50,10 @@ struct HxHnswArgs {
   float limit;
   int32_t has_limit;
   const uint32_t* avail;    // nullptr: everything is resident
+  // ring builds: per-query outcome.  q_err[qi] = error flags raised by query qi alone (a tie-stack or visited-set overflow
+  // fails that query, not the batch); done[qi] (host-mapped, service path) = 0x80000000 | flags once the results are visible
+  uint32_t* q_err;          // optional [B]
+  uint32_t* done;           // optional [B]
 };
 
 // ---- sorted beam in shared memory, maintained by warp 0 -----------------------------------------------

@@ -379,8 +379,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     if (lane == 0) qi = atomicAdd(rg.counter, 1u);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= a.B) break;
+    uint32_t qflags = 0;   // error flags raised by THIS query
     if (a.q_status[qi] != 0u || !ix.populated) {
       if (lane == 0) a.out_counts[qi] = 0;
+      hx_query_done(a, qi, 0u, lane);
       continue;
     }
     q_hdr = a.q_hdr[qi];
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     __syncwarp();
     score_list(frontier, 1);
     float cur_dist = fdist[0];
-    if (!hx_score_ok(cur_dist) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+    if (!hx_score_ok(cur_dist)) qflags |= HXF_INVALID_SCORE;
     uint32_t upper_steps = 0;
     __syncwarp();
     for (int layer = ix.max_layer; layer >= 1; --layer) {
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
           }
           if (m < best) { best = m; best_i = mi; }
         }
-        if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+        if (bad) qflags |= HXF_INVALID_SCORE;
         __syncwarp();
         if (best_i == HX_ABSENT) break;
         cur = frontier[best_i];
@@ -452,7 +454,8 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     HxBeam beam{beam_mem, 1u};
     HxBeam topk{topk_mem, 1u};
     const uint32_t topk_target = a.k > 1u ? a.k : 1u;   // == a.k (k >= 1)
-    uint32_t tie_len = 0, dropped = 0;
+    HxTie tq = hx_tie_make(tie);
+    uint32_t dropped = 0;
     uint32_t st_steps = 0, st_examined = 0, st_dc = 1;
     uint32_t fill = 0;                                   // simhash_fill_slots
     uint64_t w_examined = 0, w_filtered = 0, w_expansions = 0;
@@ -480,9 +483,8 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
         cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
         cur_bits = (uint32_t)(key >> 32);
         st_steps++;
-      } else if (tie_len > 0) {
-        uint64_t key = tie[tie_len - 1];
-        tie_len--;
+      } else if (tq.len > 0) {
+        const uint64_t key = hx_tie_pop(tq);
         cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
         cur_bits = (uint32_t)(key >> 32);
         st_steps++;
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
         st_examined += ix.raw0[cur_slot];
         if (vcount + deg > vt.limit) {
           if (pool_idx >= 0 || (pool_idx = hx_vt_grow_warp(vt, rg, lane)) < 0) {
-            if (lane == 0) atomicOr(a.err_flags, HXF_VT_OVERFLOW);
+            qflags |= HXF_VT_OVERFLOW;
             failed = true;
             break;
           }
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
       score_list(frontier, ns);
       for (uint32_t f = 0; f < ns; ++f) {
         float s = fdist[f];
-        if (!hx_score_ok(s)) { if (lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE); }
+        if (!hx_score_ok(s)) qflags |= HXF_INVALID_SCORE;
         const uint32_t sbits = __float_as_uint(s);
         const uint32_t wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
         if (!(sbits < wmax || beam.len + fill < a.ef)) continue;
@@ -685,16 +687,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
         }
         if (was_full) {
           const uint32_t new_wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
-          if (new_wmax < old_wmax && tie_len) { dropped = 1; tie_len = 0; }
+          if (new_wmax < old_wmax && tq.len) { dropped = 1; tq.len = 0; }
           if (!(ev & 1ull)) {
             if ((uint32_t)(ev >> 32) == new_wmax) {
-              if (tie_len < HX_TIE_CAP) {
-                if (lane == 0) tie[tie_len] = ev;
-                tie_len++;
-              } else {
-                if (lane == 0) atomicOr(a.err_flags, HXF_TIE_OVERFLOW);
-                dropped = 1;
-              }
+              if (!hx_tie_push(tq, ev, rg, lane)) { qflags |= HXF_TIE_OVERFLOW; failed = true; }
             } else {
               dropped = 1;
             }
@@ -703,6 +699,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
         }
       }
       __syncwarp();
+      if (failed) break;
     }
 
     // ---- results
@@ -731,6 +728,8 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
       __threadfence();
       atomicExch(rg.pool_busy + pool_idx, 0u);
     }
+    hx_tie_release(tq, rg, lane);
+    hx_query_done(a, qi, qflags, lane);
     __syncwarp();
   }
   if (CTA) {   // warp 0: release the helpers

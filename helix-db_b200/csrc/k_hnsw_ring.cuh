@@ -38,7 +38,75 @@ struct HxRingArgs {
   uint32_t prefetch_below;  // warp ring build: L2-prefetch the neighbour row of an admitted entry only below this beam position
   uint32_t l2_spec;      // 1: latency build prefetches the predicted next expansion's rows into L2
   unsigned long long* prof;   // optional [8] cycle sums of the latency build's phases (HX_PHASE_PROF=1, diagnostics only)
+  // overflow regions of the tie stack (evicted-unexpanded entries whose score equals w.max): the reference's candidates heap
+  // is unbounded, so a corpus with many exactly equal scores (duplicate rows, quantised data) must not fail the search
+  uint64_t* tie_pool;         // [tie_pool_n][tie_pool_cap]
+  uint32_t* tie_busy;         // [tie_pool_n]
+  uint32_t tie_pool_n, tie_pool_cap;
 };
+
+// ---- tie stack: HX_TIE_CAP entries in shared memory, then a pool region in global memory ---------------------------------
+struct HxTie {
+  uint64_t* s;      // shared memory [HX_TIE_CAP]
+  uint64_t* ovf;    // claimed overflow region or nullptr
+  int ovf_idx;
+  uint32_t len;
+};
+__device__ __forceinline__ HxTie hx_tie_make(uint64_t* s) {
+  HxTie t;
+  t.s = s; t.ovf = nullptr; t.ovf_idx = -1; t.len = 0;
+  return t;
+}
+// warp-uniform; false = no overflow region free / region full (the caller fails THIS query only)
+__device__ __forceinline__ bool hx_tie_push(HxTie& t, uint64_t e, const HxRingArgs& rg, uint32_t lane) {
+  if (t.len < HX_TIE_CAP) {
+    if (lane == 0) t.s[t.len] = e;
+    t.len++;
+    return true;
+  }
+  if (t.ovf_idx < 0) {
+    int got = -1;
+    if (lane == 0)
+      for (uint32_t i = 0; i < rg.tie_pool_n; ++i)
+        if (atomicCAS(rg.tie_busy + i, 0u, 1u) == 0u) { got = (int)i; break; }   // never waits: no deadlock with the visited pool
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (got < 0) return false;
+    t.ovf_idx = got;
+    t.ovf = rg.tie_pool + (size_t)got * rg.tie_pool_cap;
+  }
+  const uint32_t o = t.len - HX_TIE_CAP;
+  if (o >= rg.tie_pool_cap) return false;
+  if (lane == 0) t.ovf[o] = e;
+  t.len++;
+  __syncwarp();
+  return true;
+}
+__device__ __forceinline__ uint64_t hx_tie_pop(HxTie& t) {
+  t.len--;
+  return t.len >= HX_TIE_CAP ? ((volatile uint64_t*)t.ovf)[t.len - HX_TIE_CAP] : t.s[t.len];
+}
+__device__ __forceinline__ void hx_tie_release(HxTie& t, const HxRingArgs& rg, uint32_t lane) {
+  if (t.ovf_idx >= 0 && lane == 0) {
+    __threadfence();
+    atomicExch(rg.tie_busy + t.ovf_idx, 0u);
+  }
+  t.ovf_idx = -1;
+  t.ovf = nullptr;
+  t.len = 0;
+}
+
+// per-query completion: error flags of THIS query (q_err) and, for the service path, the host-mapped done word.
+// Called by one whole warp after it has written the query's results.
+__device__ __forceinline__ void hx_query_done(const HxHnswArgs& a, uint32_t qi, uint32_t qflags, uint32_t lane) {
+  qflags = __reduce_or_sync(0xffffffffu, qflags);
+  if (a.done) __threadfence_system();   // results (possibly in host-mapped memory) before the done word
+  __syncwarp();
+  if (lane == 0) {
+    if (qflags) atomicOr(a.err_flags, qflags);
+    if (a.q_err) a.q_err[qi] = qflags;
+    if (a.done) *((volatile uint32_t*)a.done + qi) = 0x80000000u | qflags;
+  }
+}
 
 __device__ __forceinline__ uint64_t hx_policy_evict_first() {
   uint64_t p;
@@ -294,6 +362,7 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= a.B) break;
     qg = a.queries + (size_t)qi * ix.dim;
+    uint32_t qflags = 0;   // error flags raised by THIS query
     if (a.avail) {   // the query may still be on its way from the host
       uint32_t gone = 0;
       if (lane == 0) {
@@ -311,6 +380,7 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
       gone = __shfl_sync(FULL, gone, 0);
       if (gone) {
         if (lane == 0) { a.out_counts[qi] = 0; if (a.q_status_w) a.q_status_w[qi] = 0; }
+        hx_query_done(a, qi, HXF_COPY_TIMEOUT, lane);
         continue;
       }
     }
@@ -320,12 +390,14 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
       if (lane == 0) { a.q_status_w[qi] = st; a.q_hdr_w[qi] = h; }
       if (st != 0u || !ix.populated) {
         if (lane == 0) a.out_counts[qi] = 0;
+        hx_query_done(a, qi, 0u, lane);
         continue;
       }
       q_hdr = h;
     } else {
       if (a.q_status[qi] != 0u || !ix.populated) {
         if (lane == 0) a.out_counts[qi] = 0;
+        hx_query_done(a, qi, 0u, lane);
         continue;
       }
       q_hdr = a.q_hdr[qi];
@@ -347,7 +419,7 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
     __syncwarp();
     score_list(frontier, 1);
     float cur_dist = fdist[0];
-    if (!hx_score_ok(cur_dist) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+    if (!hx_score_ok(cur_dist)) qflags |= HXF_INVALID_SCORE;
     uint32_t upper_steps = 0;
     __syncwarp();
 
@@ -382,7 +454,7 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
           }
           if (m < best) { best = m; best_i = mi; }
         }
-        if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+        if (bad) qflags |= HXF_INVALID_SCORE;
         __syncwarp();
         if (best_i == HX_ABSENT) break;
         cur = frontier[best_i];
@@ -394,7 +466,8 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
 
     // ---- layer 0: beam search
     HxBeam beam{beam_mem, 1u};
-    uint32_t tie_len = 0, dropped = 0;
+    HxTie tq = hx_tie_make(tie);
+    uint32_t dropped = 0;
     uint32_t st_steps = 0, st_examined = 0, st_dc = 1;
     if (lane == 0) {
       beam_mem[0] = hx_make_key(cur_dist, cur << 1);
@@ -410,9 +483,8 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
         if (lane == 0) beam_mem[first] = key | 1ull;
         cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
         st_steps++;
-      } else if (tie_len > 0) {
-        uint64_t key = tie[tie_len - 1];
-        tie_len--;
+      } else if (tq.len > 0) {
+        const uint64_t key = hx_tie_pop(tq);
         cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
         st_steps++;
       } else if (dropped) {
@@ -427,7 +499,7 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
         st_examined += ix.raw0[cur_slot];
         if (st_dc + deg > vt.limit) {               // keep the visited set below 13/16 full
           if (pool_idx >= 0 || (pool_idx = hx_vt_grow_warp(vt, rg, lane)) < 0) {
-            if (lane == 0) atomicOr(a.err_flags, HXF_VT_OVERFLOW);
+            qflags |= HXF_VT_OVERFLOW;
             failed = true;
             break;
           }
@@ -451,7 +523,7 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
         uint32_t sbits = 0;
         bool pass = false;
         if (f < nf) {
-          if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+          if (!hx_score_ok(s)) qflags |= HXF_INVALID_SCORE;
           sbits = __float_as_uint(s);
           const uint32_t wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
           pass = (sbits < wmax) || (beam.len < a.ef);
@@ -477,16 +549,10 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
           }
           if (was_full) {
             const uint32_t new_wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
-            if (new_wmax < old_wmax && tie_len) { dropped = 1; tie_len = 0; }
+            if (new_wmax < old_wmax && tq.len) { dropped = 1; tq.len = 0; }
             if (!(ev & 1ull)) {
               if ((uint32_t)(ev >> 32) == new_wmax) {
-                if (tie_len < HX_TIE_CAP) {
-                  if (lane == 0) tie[tie_len] = ev;
-                  tie_len++;
-                } else {
-                  if (lane == 0) atomicOr(a.err_flags, HXF_TIE_OVERFLOW);
-                  dropped = 1;
-                }
+                if (!hx_tie_push(tq, ev, rg, lane)) { qflags |= HXF_TIE_OVERFLOW; failed = true; }
               } else {
                 dropped = 1;
               }
@@ -496,6 +562,7 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
         }
       }
       __syncwarp();
+      if (failed) break;
     }
 
     // ---- results
@@ -520,6 +587,8 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
       __threadfence();
       atomicExch(rg.pool_busy + pool_idx, 0u);
     }
+    hx_tie_release(tq, rg, lane);
+    hx_query_done(a, qi, qflags, lane);
     __syncwarp();
   }
 }
@@ -585,9 +654,9 @@ __device__ __forceinline__ uint32_t hx_rbeam_first_unexpanded(const HxRegBeam<NB
 //    (any other evicted-unexpanded entry; or older ties once w.max has decreased) follow from the merged ranks.
 // `stage` = ef u64 of shared memory.  Returns the mask of admitted lanes.
 template <int NB>
-__device__ __forceinline__ uint32_t hx_rbeam_admit_batch(HxRegBeam<NB>& b, uint32_t& wmax, uint64_t* tie, uint32_t& tie_len,
+__device__ __forceinline__ uint32_t hx_rbeam_admit_batch(HxRegBeam<NB>& b, uint32_t& wmax, HxTie& tq, const HxRingArgs& rg,
                                                          uint32_t& dropped, uint64_t* stage, uint32_t ef, uint32_t sbits,
-                                                         uint32_t slot, bool valid, uint32_t lane, uint32_t* err_flags) {
+                                                         uint32_t slot, bool valid, uint32_t lane, uint32_t& qflags) {
   const unsigned FULL = 0xffffffffu;
   const bool pass = valid && ((sbits < wmax) || (b.len < ef));   // necessary: w.max never increases
   const uint32_t pm = __ballot_sync(FULL, pass);
@@ -648,7 +717,7 @@ __device__ __forceinline__ uint32_t hx_rbeam_admit_batch(HxRegBeam<NB>& b, uint3
   __syncwarp();
   if (new_len == ef) wmax = (uint32_t)(stage[ef - 1u] >> 32);
   if (total > ef) {   // evictions: only a full beam evicts, and it is full now
-    if (was_full && wmax < old_wmax && tie_len) { dropped = 1; tie_len = 0; }
+    if (was_full && wmax < old_wmax && tq.len) { dropped = 1; tq.len = 0; }
     bool ev_tie = false, ev_other = false;
 #pragma unroll
     for (int r = 0; r < NB; ++r)
@@ -670,13 +739,7 @@ __device__ __forceinline__ uint32_t hx_rbeam_admit_batch(HxRegBeam<NB>& b, uint3
         const uint32_t owner = __ballot_sync(FULL, mine != HX_KEY_MAX);
         const uint64_t e = __shfl_sync(FULL, mine, owner ? __ffs((int)owner) - 1 : 0);
         if (!owner || (e & 1ull) || (uint32_t)(e >> 32) != wmax) continue;
-        if (tie_len < HX_TIE_CAP) {
-          if (lane == 0) tie[tie_len] = e;
-          tie_len++;
-        } else {
-          if (lane == 0) atomicOr(err_flags, HXF_TIE_OVERFLOW);
-          dropped = 1;
-        }
+        if (!hx_tie_push(tq, e, rg, lane)) { qflags |= HXF_TIE_OVERFLOW; dropped = 1; }
       }
     }
   }
@@ -766,8 +829,10 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
   };
 
   for (uint32_t qi = blockIdx.x; qi < a.B; qi += gridDim.x) {
+    uint32_t qflags = 0;   // error flags raised by THIS query (warp 0's copy is the one reported)
     if (a.q_status[qi] != 0u || !ix.populated) {   // uniform per CTA
       if (tid == 0) a.out_counts[qi] = 0;
+      if (warp == 0) hx_query_done(a, qi, 0u, lane);
       continue;
     }
     q_hdr = a.q_hdr[qi];
@@ -789,7 +854,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
     __syncthreads();
     score_list(frontier, 1, [] {});
     float cur_dist = fdist[0];
-    if (tid == 0 && !hx_score_ok(cur_dist)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+    if (tid == 0 && !hx_score_ok(cur_dist)) qflags |= HXF_INVALID_SCORE;
     uint32_t upper_steps = 0;
     __syncthreads();
 
@@ -824,7 +889,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
             }
             if (m < best) { best = m; best_i = mi; }
           }
-          if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+          if (bad) qflags |= HXF_INVALID_SCORE;
           if (lane == 0) {
             if (best_i != HX_ABSENT) { s_cur = frontier[best_i]; s_cur_dist = best; s_changed = 1u; }
             else s_changed = 0u;
@@ -845,7 +910,8 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
     for (int r = 0; r < (NB > 0 ? NB : 1); ++r) rb.v[r] = HX_KEY_MAX;
     rb.len = 0;
     uint32_t wmax = 0xffffffffu;               // score bits of the last entry once the beam is full
-    uint32_t tie_len = 0, dropped = 0;
+    HxTie tq = hx_tie_make(tie);
+    uint32_t dropped = 0;
     uint32_t st_steps = 0, st_examined = 0, st_dc = 1;
     bool failed = false;
     // speculative neighbour row: the row of the entry predicted to be popped next, loaded during the scoring phase
@@ -888,14 +954,14 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
           }
           cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
           st_steps++;
-        } else if (tie_len > 0) {
-          uint64_t key = tie[tie_len - 1];
-          tie_len--;
+        } else if (tq.len > 0) {
+          const uint64_t key = hx_tie_pop(tq);
           cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
           st_steps++;
         } else if (dropped) {
           st_steps++;
         }
+        if (failed) cur_slot = HX_ABSENT;   // a tie-stack overflow during the previous admission ends this query
         uint32_t nf = 0;
         if (cur_slot != HX_ABSENT) {
           const uint32_t* row = ix.nbr0 + (size_t)cur_slot * ix.stride0;
@@ -912,7 +978,7 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
           st_examined += raw;
           if (st_dc + deg > vt.limit) {
             if (pool_idx >= 0 || (pool_idx = hx_vt_grow_warp(vt, rg, lane)) < 0) {
-              if (lane == 0) atomicOr(a.err_flags, HXF_VT_OVERFLOW);
+              qflags |= HXF_VT_OVERFLOW;
               failed = true;
               cur_slot = HX_ABSENT;
             }
@@ -990,15 +1056,16 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
           const uint32_t blen = NB > 0 ? rb.len : beam.len;
           if (NB == 0 && blen) wmax = (uint32_t)(beam_mem[blen - 1] >> 32);
           if (f < nf) {
-            if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+            if (!hx_score_ok(s)) qflags |= HXF_INVALID_SCORE;
             sbits = __float_as_uint(s);
             pass = (sbits < wmax) || (blen < a.ef);   // w.max only decreases once full: a fail now is final
           }
           uint32_t mask = __ballot_sync(FULL, pass);
           const uint32_t myslot = f < nf ? frontier[f] : 0u;
           if (NB > 0 && rg.batch_admit) {
-            const uint32_t am = hx_rbeam_admit_batch(rb, wmax, tie, tie_len, dropped, beam_mem, a.ef, sbits, myslot, f < nf,
-                                                     lane, a.err_flags);
+            const uint32_t am = hx_rbeam_admit_batch(rb, wmax, tq, rg, dropped, beam_mem, a.ef, sbits, myslot, f < nf,
+                                                     lane, qflags);
+            if (qflags & HXF_TIE_OVERFLOW) failed = true;
             if ((am >> lane) & 1u) {   // warm the rows we will need if these candidates are expanded
               hx_prefetch_l2(ix.nbr0 + (size_t)myslot * ix.stride0);
               hx_prefetch_l2(ix.deg0 + myslot);
@@ -1029,16 +1096,10 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
             }
             if (was_full) {
               const uint32_t new_wmax = NB > 0 ? wmax : (uint32_t)(beam_mem[beam.len - 1] >> 32);
-              if (new_wmax < old_wmax && tie_len) { dropped = 1; tie_len = 0; }
+              if (new_wmax < old_wmax && tq.len) { dropped = 1; tq.len = 0; }
               if (!(ev & 1ull)) {   // evicted while still unexpanded
                 if ((uint32_t)(ev >> 32) == new_wmax) {
-                  if (tie_len < HX_TIE_CAP) {
-                    if (lane == 0) tie[tie_len] = ev;
-                    tie_len++;
-                  } else {
-                    if (lane == 0) atomicOr(a.err_flags, HXF_TIE_OVERFLOW);
-                    dropped = 1;
-                  }
+                  if (!hx_tie_push(tq, ev, rg, lane)) { qflags |= HXF_TIE_OVERFLOW; failed = true; }
                 } else {
                   dropped = 1;
                 }
@@ -1089,6 +1150,8 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
           atomicExch(rg.pool_busy + pool_idx, 0u);
         }
       }
+      hx_tie_release(tq, rg, lane);
+      hx_query_done(a, qi, qflags, lane);
     }
     __syncthreads();
   }

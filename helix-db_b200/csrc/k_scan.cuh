@@ -144,7 +144,9 @@ static __global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSe
         }
       }
       __syncthreads();
-      if (s_cnt + HX_SEL_THREADS > HX_SEL_HALF) {   // next step could overflow: merge now (uniform)
+      const uint32_t filled = s_cnt;   // snapshot between two barriers: no thread can bump s_cnt before all have read it
+      __syncthreads();
+      if (filled + HX_SEL_THREADS > HX_SEL_HALF) {   // next step could overflow: merge now (block-uniform)
         hx_bitonic_sort_2048(buf, tid);
         for (uint32_t i = tid; i < HX_SEL_HALF; i += HX_SEL_THREADS) buf[HX_SEL_HALF + i] = HX_KEY_MAX;
         if (tid == 0) { s_cnt = 0; s_thr = buf[kk - 1]; }   // HX_KEY_MAX until kk keys are known

@@ -198,10 +198,64 @@ class VectorIndex {
     return out;
   }
   hx_index* raw() const { return h_; }
+  uint32_t dimension() const { return dim_; }
 
  private:
   hx_index* h_ = nullptr;
   uint32_t dim_;
+};
+
+// hx_service: the reference's calling pattern — ONE query per call from many concurrent tasks (read_index.rs:81-101) —
+// served by shared launches.  search() is the blocking drop-in; submit()/poll() is the pair an async runtime maps a task to.
+class SearchService {
+ public:
+  // borrows an index handle (the owner keeps it alive for the service's lifetime)
+  SearchService(hx_index* index, uint32_t k, uint32_t ef = 0, uint32_t capacity = 0, uint32_t max_batch = 0,
+                uint32_t ctas_per_sm = 0)
+      : k_(k) {
+    hx_service_config c{};
+    c.k = k;
+    c.ef = ef;
+    c.capacity = capacity;
+    c.max_batch = max_batch;
+    c.ctas_per_sm = ctas_per_sm;
+    check(hx_service_create(index, &c, &h_));
+  }
+  explicit SearchService(hx_service* adopt_borrowed, uint32_t k, bool) : h_(adopt_borrowed), k_(k), owned_(false) {}
+  ~SearchService() { if (owned_) hx_service_destroy(h_); }
+  SearchService(const SearchService&) = delete;
+  SearchService& operator=(const SearchService&) = delete;
+
+  uint64_t submit(const float* query) const {
+    uint64_t t = 0;
+    check(hx_service_submit(h_, query, &t));
+    return t;
+  }
+  // false while the query is running; true once `out` holds its results (the ticket is consumed)
+  bool poll(uint64_t ticket, uint64_t* ids, float* scores, uint32_t* count) const {
+    int32_t done = 0;
+    check(hx_service_poll(h_, ticket, &done, ids, scores, count));
+    return done != 0;
+  }
+  void search(const float* query, uint64_t* ids, float* scores, uint32_t* count) const {
+    check(hx_service_search(h_, query, ids, scores, count));
+  }
+  std::vector<SearchResult> search(const std::vector<float>& query) const {
+    std::vector<uint64_t> ids(k_);
+    std::vector<float> scores(k_);
+    uint32_t count = 0;
+    search(query.data(), ids.data(), scores.data(), &count);
+    std::vector<SearchResult> out(count);
+    for (uint32_t i = 0; i < count; ++i) out[i] = SearchResult{ids[i], scores[i]};
+    return out;
+  }
+  uint32_t k() const { return k_; }
+  hx_service* raw() const { return h_; }
+
+ private:
+  hx_service* h_ = nullptr;
+  uint32_t k_;
+  bool owned_ = true;
 };
 
 }   // namespace helix

@@ -22,7 +22,11 @@
  * max layer are uploaded once and searched many times.
  *
  * Threading: an `hx_index*` may be searched concurrently from several host
- * threads (each call takes a private stream + scratch block from a pool);
+ * threads: each host-buffer call takes a private stream + scratch block from a
+ * pool (64 per handle, then callers queue), device-buffer calls use one scratch
+ * set per caller stream, and the first search after a load finalises the graph
+ * image under a lock.  One-query-per-call traffic belongs on an hx_service
+ * (below), which coalesces concurrent callers into shared launches.
  * load/build calls must not overlap searches on the same handle.
  */
 #ifndef HELIX_B200_H
@@ -278,6 +282,62 @@ hx_status hx_search_restricted_sets(hx_index* idx, const float* queries, size_t 
  * device path always answers exactly. */
 int32_t hx_restricted_plan(uint64_t n_candidates, uint32_t dimension);
 
+/* B independent queries with a status PER QUERY.  The reference runs one query per call
+ * (read_index.rs:81-101), so in a batch one invalid query (or one query that exhausts a device-side
+ * bound such as the tie-stack overflow regions) must fail alone: out_status[b] carries the code
+ * hx_search would have returned for query b on its own, out_counts[b] = 0 for a failed query, and the
+ * call returns HX_OK whenever the batch itself could be executed.  Same kernels and results as
+ * hx_search (strict-exhaustive params) / hx_search_ex with default policy (any other params). */
+hx_status hx_search_batch(hx_index* idx, const float* queries, size_t B, const hx_search_params* p,
+                          uint64_t* out_ids, float* out_scores, uint32_t* out_counts,
+                          hx_status* out_status /* B */, hx_stats* stats);
+
+/* ---- query service: the reference's calling pattern ---------------------------------------------
+ * Production traffic reaches this path as ONE query per call from many concurrent tokio tasks, no
+ * intra-query parallelism (read_index.rs:81-101, called per request from
+ * execution/interpreter/access/search/storage.rs:142-192).  A service coalesces those callers: a caller
+ * writes its query into a slot of a pinned submission ring (lock-free ticket), a dispatcher thread turns
+ * whatever is pending into ONE launch of the CTA-per-query traversal kernel (grid = pending queries, several
+ * launches in flight on a stream pool, 2-3 CTAs resident per SM), the kernel writes each query's results
+ * straight into host-mapped memory and then publishes a per-query done word; nobody ever calls
+ * cudaStreamSynchronize.  hx_service_submit / hx_service_poll are the async pair a tokio task maps to
+ * (submit, then poll from the task's waker loop or a oneshot fed by a reaper thread); hx_service_search is
+ * the blocking form (futex wait, woken by the service's completer thread).  Results are bit-identical to
+ * hx_search: same kernel, same admission order.  Strict-exhaustive SearchParams; k and ef are fixed per
+ * service (they size the result slots).  Thread-safe; any number of services per index. */
+typedef struct hx_service hx_service;
+typedef struct {
+  uint32_t k;               /* results per query (> 0)                                                */
+  uint32_t ef;              /* beam width; 0 => max(k, 100)                                           */
+  uint32_t capacity;        /* submission-ring slots = max queries in flight; 0 => 1024 (rounded up to 2^n) */
+  uint32_t max_batch;       /* max queries per launch; 0 => 128                                       */
+  uint32_t n_streams;       /* launches in flight; 0 => 32                                            */
+  uint32_t ctas_per_sm;     /* resident CTAs (= queries) per SM the launch shape is sized for; 0 => 2 */
+  uint32_t cta_warps;       /* warps per CTA of the traversal kernel; 0 => 12 / 6 / 4 for 1 / 2 / 3+ CTAs per SM */
+  uint32_t rows_in_flight;  /* vector rows staged per CTA; 0 => as many as fit                        */
+  uint32_t visited_log2;    /* log2 of the shared-memory visited-table size; 0 => auto               */
+  uint32_t reserved[3];
+} hx_service_config;
+typedef struct {
+  uint64_t submitted, completed, launches, max_batch_seen, dispatcher_sleeps, completer_wakes;
+  uint32_t cta_warps, rows_in_flight, visited_cap, smem_bytes, ctas_per_sm, reserved;
+} hx_service_stats;
+hx_status hx_service_create(hx_index* idx, const hx_service_config* cfg, hx_service** out);
+void      hx_service_destroy(hx_service* svc);   /* waits for queries in flight */
+/* Validate (dimension known from the index; finiteness -> cosine zero norm -> magnitude, domain.rs:113-154), copy the
+ * query into a ring slot and return its ticket.  Blocks only while the ring is full (back-pressure). */
+hx_status hx_service_submit(hx_service* svc, const float* query, uint64_t* out_ticket);
+/* Non-blocking.  *out_done = 0: still running.  *out_done = 1: results copied out (out_ids/out_scores hold k entries,
+ * *out_count <= k), the return value is the query's own status, the ticket is consumed. */
+hx_status hx_service_poll(hx_service* svc, uint64_t ticket, int32_t* out_done, uint64_t* out_ids, float* out_scores,
+                          uint32_t* out_count);
+/* Blocking: returns when the ticket's results are out (futex wait; consumes the ticket). */
+hx_status hx_service_wait(hx_service* svc, uint64_t ticket, uint64_t* out_ids, float* out_scores, uint32_t* out_count);
+/* submit + wait: the drop-in for one ValidatedVectorReadIndex::search call. */
+hx_status hx_service_search(hx_service* svc, const float* query, uint64_t* out_ids, float* out_scores,
+                            uint32_t* out_count);
+hx_status hx_service_get_stats(hx_service* svc, hx_service_stats* out);
+
 /* ---- search (device buffers: inputs already resident in HBM) ------------------------- */
 /* Same semantics, no validation copy, no host sync: everything is enqueued on
  * `cuda_stream` (a cudaStream_t, 0 = legacy default stream).  d_queries must have been
@@ -285,6 +345,12 @@ int32_t hx_restricted_plan(uint64_t n_candidates, uint32_t dimension);
 hx_status hx_search_device(hx_index* idx, const float* d_queries, size_t B,
                            const hx_search_params* p, uint64_t* d_out_ids, float* d_out_scores,
                            uint32_t* d_out_counts, void* cuda_stream, hx_stats* stats_or_null);
+/* Device-buffer calls never synchronise, so they cannot report a per-call device error: the flags raised by the
+ * launches issued on `cuda_stream` since the previous hx_device_flags on that stream are ORed into one word
+ * (1 invalid score, 4 tie-stack overflow, 8 visited-set overflow, 16 copy time-out).  This call synchronises the stream,
+ * returns and clears the word; *out_status = the HelixDbError it maps to (HX_OK when 0).  Device-buffer calls on
+ * DIFFERENT streams use separate scratch sets and may run concurrently from different threads. */
+hx_status hx_device_flags(hx_index* idx, void* cuda_stream, uint32_t* out_flags, hx_status* out_status);
 /* Candidates as device slot numbers (ascending), per query CSR. */
 hx_status hx_search_restricted_device(hx_index* idx, const float* d_queries, size_t B,
                                       const hx_search_params* p, const uint32_t* d_cand_slots,

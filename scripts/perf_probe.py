@@ -81,7 +81,9 @@ def hnsw_probe(n=20000, dim=768, B=4096, reps=3):
         ora.insert(i, rows[i], int(hxo.lib().hxo_select_layer_from_uniform(ml, float(rng.random(dtype=np.float32)))))
     build_s = time.time() - t0
     ix = hx.VectorIndex(hx.Metric.Cosine, hx.VectorIndexConfig("h", "embedding", dim))
-    ix.mirror_from_oracle(ora)
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / 'tests'))
+    from hx_testutil import mirror_from_oracle
+    mirror_from_oracle(ix, ora)
     p = hx.SearchParams.strict(10)
     dq = torch.from_numpy(q).to(dev)
     o_ids = torch.zeros((B, 10), dtype=torch.int64, device=dev)

@@ -13,6 +13,7 @@ import pytest
 
 import helix_db_b200 as hx
 from oracle import hxo
+from hx_testutil import mirror_from_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -36,7 +37,7 @@ def build_pair(gm, om, rows, ids=None, m=16, m0=32, efc=200, seed=1):
     for i, lv in zip(range(n), levels_for(n, m, seed)):
         ora.insert(int(ids[i]), rows[i], lv)
     gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("t", "embedding", dim).with_m(m).with_m0(m0).with_ef_construction(efc))
-    gpu.mirror_from_oracle(ora)
+    mirror_from_oracle(gpu, ora)
     return gpu, ora
 
 
@@ -53,7 +54,7 @@ def test_phase0_public_result_and_io_baseline():
         ora.insert(node_id, vec, layer)
     gpu = hx.VectorIndex(hx.Metric.Cosine, hx.VectorIndexConfig("phase0", "embedding", 2).with_m(4).with_m0(8)
                          .with_ef_construction(16))
-    gpu.mirror_from_oracle(ora)
+    mirror_from_oracle(gpu, ora)
     params = hx.SearchParams.new(4).with_ef(16).with_simhash_mode(hx.SimHashMode.Off).with_pre_simhash_sampling_ratio(1.0)
     results, stats = gpu.search_with_stats([1.0, 0.0], params)
     plain = gpu.search([1.0, 0.0], params)
@@ -120,7 +121,7 @@ def test_tie_stability(gm, om):
     for node_id in (2, 1, 3):
         ora.insert(node_id, [1.0, 0.0], 0)
     gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("tie", "embedding", 2).with_m(4).with_m0(8).with_ef_construction(16))
-    gpu.mirror_from_oracle(ora)
+    mirror_from_oracle(gpu, ora)
     r = gpu.search_restricted([1.0, 0.0], hx.SearchParams.strict(3), hx.RestrictedVectorCandidates.from_ids([3, 1, 2]))
     assert [x.entity_id() for x in r] == [1, 2, 3] and [float(x.score()) for x in r] == [0.0, 0.0, 0.0]
     r = gpu.search([1.0, 0.0], hx.SearchParams.strict(3, 16))

@@ -11,10 +11,17 @@ A "step" is one pass of the hot path over one batch of Q independent single-quer
             against the measured HBM peak in MEASURED_PEAKS.json.
   cpu_baseline / --impl reference: the CPU oracle (restatement of the reference's algorithm without its KV layer)
             traversing the IDENTICAL graph on all host cores, one query per thread.
-  N > 1   : one process per GPU (torchrun).  Default "replica" mode partitions the QUERIES across full replicas
-            (no data-path collective; weak scaling: Q queries per GPU per step).  The same line carries a
-            "sharded" object: the 1M corpus split by id range, every rank searching every query on its shard,
-            ONE NCCL all-gather of the per-shard top-k and the (score,id) merge kernel inside the timed region.
+  N > 1   : one process per GPU (torchrun).  `value` is the "replica" mode: the QUERIES are partitioned across full
+            replicas (no data-path collective; weak scaling: Q queries per GPU per step).  The same line carries a
+            "sharded" object: the 1M corpus split by id range, every rank searching every query on its shard through
+            hx_search_sharded_device (C ABI: local search into the send block, ONE ncclAllGather issued by the library,
+            (score,id) merge kernel), per-shard ef tuned to iso-recall with the unsharded index; and "dense_c4": the
+            C4 shape (1.25M x 768 bf16 rows per GPU, batch 1024) through the tensor-core path, sharded the same way.
+  N = 1   : the line also carries driver-visible sub-results for the other BASELINE configs, each with its own
+            roofline / e2e / cpu_baseline / parity flags: "prefilter" (C3 label sets + the reference's contiguous
+            100/1k/10k/100k shapes), "dense_c4" (one C4 shard), "concurrent_callers" (the reference's calling pattern:
+            1..256 callers x one query per call through hx_service), "euclid_d1536" (the reference's own traversal
+            fixture shape: 1M x 1536, Euclidean).
 """
 from __future__ import annotations
 
@@ -64,6 +71,12 @@ def parse():
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--no-default-mode", action="store_true")
     ap.add_argument("--workload", default="hnsw", choices=["hnsw", "prefilter", "dense"])
+    ap.add_argument("--no-subresults", action="store_true", help="skip the prefilter / dense / callers / d1536 sub-results")
+    ap.add_argument("--no-d1536", action="store_true")
+    ap.add_argument("--d1536-rows", type=int, default=1_000_000)
+    ap.add_argument("--dense-rows-per-gpu", type=int, default=1_250_000)
+    ap.add_argument("--dense-batch", type=int, default=1024)
+    ap.add_argument("--callers-seconds", type=float, default=1.0)
     ap.add_argument("--recipe", default="embedding", choices=sorted(RECIPES))
     a = ap.parse_args()
     global KIND, SIGMA
@@ -226,11 +239,460 @@ def exact_topk_device(hx, torch, ix, queries, n, first_id, k):
     return exact_topk_device_full(hx, torch, ix, queries, n, first_id, k)[0]
 
 
+def c2_config(args, world, setup=None):
+    """The `config` object of the C2 line — shared verbatim by our arm and the --impl reference arm."""
+    n, dim, Q = args.n, args.dim, args.queries_per_step
+    cfg = {
+        "workload": f"C2: {n}x{dim} f32 {args.metric} HNSW top-10 (m=16, m0=32, ef_construction=200, ef={EF}), "
+                    f"independent single-query traversals (batch=1 semantics, no cross-query sharing), "
+                    f"{Q} queries per GPU per step",
+        "queries_per_step_per_gpu": Q,
+        "parallelism": "single GPU" if world == 1 else f"{world} full replicas, queries partitioned, no data-path collective",
+        "value_mode": "single GPU" if world == 1 else "replicas (the id-range-sharded path is the `sharded` object)",
+        "l2": f"corpus {n * dim * 4 / 1e9:.2f} GB >> 126 MB L2; distinct queries every step and rank",
+        "graph": "built on the device (hx_index_build), identical adjacency mirrored into the CPU oracle",
+        "data_recipe": (f"{args.recipe}: unit-normalised {N_CENTROIDS}-component Gaussian mixture, sigma={SIGMA}, "
+                        + (f"rank-{KIND} latent space -> fixed random projection to {dim}-d + 2% noise"
+                           if KIND else f"isolated isotropic clusters in {dim}-d") + ", seed=0x0DB9ED1A"),
+    }
+    if setup is not None:
+        cfg["setup"] = setup
+    return cfg
+
+
 def recall_at_k(found, truth):
     hit = 0
     for f, t in zip(found, truth):
         hit += len(set(f.tolist()) & set(t.tolist()))
     return hit / float(truth.size)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Sub-results carried by the default line (driver-visible evidence for every BASELINE config, VERDICT r1 item 1c)
+REF_PREFILTER_SHAPES = [("prefilter-100", 0, 100), ("prefilter-1000", 100, 1_000), ("prefilter-10000", 1_100, 10_000),
+                        ("prefilter-100000", 11_100, 100_000)]   # index_lifecycle_scale.rs:583-613 (contiguous id ranges)
+
+
+def _timed_device(torch, dev, steps, warmup, fn):
+    for s in range(warmup):
+        fn(s)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        fn(warmup + s)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1)
+
+
+def measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=None, label_steps=None):
+    """Config C3 on an index whose ids are 0..n-1: (a) the graph-label filter — 100 queries per step, query b restricted to
+    {id : id mod 100 == b} (1 % each: one step streams every row once), (b) the reference's own prefilter shapes — one
+    contiguous id range of 100 / 1k / 10k / 100k candidates shared by 64 queries.  Exact scan (k_scan + k_select);
+    the oracle's restricted_exact_scan checks ids and score bits."""
+    import ctypes as C
+    k, sel = K, 100
+    B = sel
+    steps = label_steps or args.steps
+    hbm_peak, peak_src = measured_peaks()
+    n_sets = steps + args.warmup
+    qsets = [ix.generate_queries(SEED, B, first_query=20_000_000 + s * B, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
+             for s in range(n_sets)]
+    cand_lists = [np.arange(b, n, sel, dtype=np.uint64) for b in range(B)]
+    cand_ids = np.concatenate(cand_lists)
+    offs = np.zeros(B + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(c) for c in cand_lists])
+    per_q = int(max(len(c) for c in cand_lists))
+    total = int(offs[-1])
+    d_slots = torch.from_numpy(cand_ids.astype(np.uint32).view(np.int32)).to(dev)      # ids == slots here (first_id 0)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    d_q = [torch.from_numpy(q).to(dev) for q in qsets]
+    o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
+    o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    params = hx.SearchParams.strict(k)
+    hdr = 4 if args.metric == "cosine" else 0
+
+    def step_device(s):
+        ix.search_restricted_device(d_q[s].data_ptr(), B, params, d_slots.data_ptr(), d_offs.data_ptr(), total, per_q,
+                                    o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+
+    ix.last_kernel_ms()
+    for s in range(args.warmup):
+        step_device(s)
+    torch.cuda.synchronize(dev)
+    ix.last_kernel_ms()
+    ms_total = _timed_device(torch, dev, steps, 0, lambda s: step_device(args.warmup + s))
+    kms, kl = ix.last_kernel_ms()
+    value = steps * B / (ms_total / 1e3)
+    bytes_per_launch = total * (4 * dim + hdr)
+    kernel_ms = kms / max(kl, 1)
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    dev_ids = o_ids.cpu().numpy().view(np.uint64).copy()
+    dev_sc = o_sc.cpu().numpy().copy()
+    last_q = qsets[args.warmup + steps - 1]
+    L = hx.load_library()
+    cp = params._c()
+    h_q = [torch.from_numpy(q).pin_memory() for q in qsets]
+    h_c = torch.from_numpy(cand_ids.view(np.int64)).pin_memory()
+    h_o = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    h_ids = torch.zeros((B, k), dtype=torch.int64).pin_memory()
+    h_sc = torch.zeros((B, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.zeros((B,), dtype=torch.int32).pin_memory()
+
+    def step_host(s):
+        rc = L.hx_search_restricted_multi(ix.h, C.cast(h_q[s].data_ptr(), C.POINTER(C.c_float)), B, C.byref(cp),
+                                          C.cast(h_c.data_ptr(), C.POINTER(C.c_uint64)),
+                                          C.cast(h_o.data_ptr(), C.POINTER(C.c_uint64)),
+                                          C.cast(h_ids.data_ptr(), C.POINTER(C.c_uint64)),
+                                          C.cast(h_sc.data_ptr(), C.POINTER(C.c_float)),
+                                          C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None)
+        if rc != 0:
+            raise RuntimeError(L.hx_last_error().decode())
+
+    for s in range(args.warmup):
+        step_host(s)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        step_host(args.warmup + s)
+    e2e_value = steps * B / (time.perf_counter() - t0)
+    same = bool(h_ids.numpy().view(np.uint64).tolist() == dev_ids.tolist() and h_sc.numpy().tobytes() == dev_sc.tobytes())
+    # label sets resident on the device (hx_candidates: uploaded + mapped once, like a label bitmap cached per snapshot)
+    t0 = time.perf_counter()
+    dsets = [ix.cache_candidates(hx.RestrictedVectorCandidates(c)) for c in cand_lists]
+    cache_s = time.perf_counter() - t0
+    set_arr = (C.c_void_p * B)(*[d.h for d in dsets])
+
+    def step_host_sets(s):
+        rc = L.hx_search_restricted_sets(ix.h, C.cast(h_q[s].data_ptr(), C.POINTER(C.c_float)), B, C.byref(cp), set_arr, B,
+                                         C.cast(h_ids.data_ptr(), C.POINTER(C.c_uint64)),
+                                         C.cast(h_sc.data_ptr(), C.POINTER(C.c_float)),
+                                         C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None)
+        if rc != 0:
+            raise RuntimeError(L.hx_last_error().decode())
+
+    for s in range(args.warmup):
+        step_host_sets(s)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        step_host_sets(args.warmup + s)
+    e2e_sets = steps * B / (time.perf_counter() - t0)
+    same_sets = bool(h_ids.numpy().view(np.uint64).tolist() == dev_ids.tolist() and h_sc.numpy().tobytes() == dev_sc.tobytes())
+    for d in dsets:
+        d.close()
+
+    # ---- the reference's contiguous shapes: one candidate range shared by 64 queries ----
+    shapes = []
+    SB = 64
+    sq = ix.generate_queries(SEED, SB, first_query=21_000_000, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
+    d_sq = torch.from_numpy(sq).to(dev)
+    s_ids = torch.zeros((SB, k), dtype=torch.int64, device=dev)
+    s_sc = torch.zeros((SB, k), dtype=torch.float32, device=dev)
+    s_cnt = torch.zeros((SB,), dtype=torch.int32, device=dev)
+    for name, start, count in REF_PREFILTER_SHAPES:
+        if start + count > n:
+            continue
+        cids = np.arange(start, start + count, dtype=np.uint64)
+        dsl = torch.from_numpy(cids.astype(np.uint32).view(np.int32)).to(dev)
+
+        def step_shape(_s):
+            ix.search_restricted_device(d_sq.data_ptr(), SB, params, dsl.data_ptr(), 0, count, count, s_ids.data_ptr(),
+                                        s_sc.data_ptr(), s_cnt.data_ptr(), stream)
+
+        ix.last_kernel_ms()
+        ms = _timed_device(torch, dev, steps, args.warmup, step_shape)
+        kms2, kl2 = ix.last_kernel_ms()
+        g_ids = s_ids.cpu().numpy().view(np.uint64).copy()
+        g_sc = s_sc.cpu().numpy().copy()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hi, hs, hc = ix.search_restricted_batch(sq, params, hx.RestrictedVectorCandidates(cids))
+        e2e = steps * SB / (time.perf_counter() - t0)
+        ent = {"shape": name, "candidates": count, "id_range": [start, start + count], "queries_per_step": SB,
+               "value": round(steps * SB / (ms / 1e3), 1), "e2e": round(e2e, 1), "unit": "queries/s",
+               "kernel_ms_per_launch": round(kms2 / max(kl2, 1), 4),
+               "scan_GBps": round(SB * count * (4 * dim + hdr) / (kms2 / max(kl2, 1) * 1e-3) / 1e9, 1) if kms2 else None,
+               "reference_plan": hx.restricted_plan(count, dim),
+               "host_path_identical_to_device_path": bool(hi.tolist() == g_ids.tolist() and hs.tobytes() == g_sc.tobytes())}
+        if ora is not None:
+            nchk = 8 if count <= 10_000 else 2
+            ok = True
+            t0 = time.perf_counter()
+            for b in range(nchk):
+                ei, es = ora.search_restricted(sq[b], k, cids)
+                ok = ok and g_ids[b, :len(ei)].tolist() == ei.tolist() and g_sc[b, :len(ei)].tobytes() == es.tobytes()
+            ent["oracle_bit_exact"] = bool(ok)
+            ent["cpu_port_qps_1thread"] = round(nchk / (time.perf_counter() - t0), 1)
+        shapes.append(ent)
+
+    cpu = None
+    if ora is not None:
+        cores = available_cores()
+        ci, cs, cc, secs = ora.search_restricted_batch(last_q, k, cand_ids, offs, threads=cores)
+        parity = bool(ci.tolist() == dev_ids.tolist() and cs.tobytes() == dev_sc.tobytes())
+        cpu = {"value": round(B / secs, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"the last step's {B} queries x {per_q} candidates, one query per thread, {cores} threads",
+               "bit_exact_vs_device": parity}
+    out = {
+        "metric": "queries/sec, DBpedia-1M d=768 prefiltered top-10 (graph-label filter), exact scan (config C3)",
+        "value": round(value, 1), "unit": "queries/s", "steps": steps, "ms_per_step": round(ms_total / steps, 4),
+        "recall_at_10": 1.0, "dtype": "f32",
+        "config": {"workload": f"C3: {n}x{dim} f32 {args.metric}, {B} queries per step, query b restricted to "
+                               f"{{id : id mod {sel} == b}} ({per_q} candidates each): every row read once per step",
+                   "l2": f"{n * dim * 4 / 1e9:.2f} GB streamed per step >> 126 MB L2"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4 + total * 8 + (B + 1) * 8,
+                "d2h_bytes_per_step": B * (k * 12 + 4) + B * 4 + 4, "api": "hx_search_restricted_multi (C ABI, pinned host)",
+                "identical_to_device_path": same},
+        "e2e_device_resident_sets": {"value": round(e2e_sets, 1), "unit": "queries/s",
+                                     "h2d_bytes_per_step": B * dim * 4 + B * 24, "d2h_bytes_per_step": B * (k * 12 + 4) + B * 4 + 4,
+                                     "api": "hx_search_restricted_sets (label sets uploaded once with hx_candidates_create)",
+                                     "sets_upload_s": round(cache_s, 3), "identical_to_device_path": same_sets},
+        "gpu_launches": steps * 3, "launches_per_step": {"k_validate_and_header": 1, "k_scan": 1, "k_select": 1},
+        "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(achieved / hbm_peak, 4),
+                     "traffic": ncu_traffic("k_scan", {"queries": B, "candidates": per_q, "dim": dim}), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms_per_launch": round(kernel_ms, 4)},
+        "reference_shapes": shapes,
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    return out
+
+
+def measure_callers(hx, ix, queries, k, ef, seconds):
+    """The reference's calling pattern (read_index.rs:81-101: one query per call, one call per tokio task, many tasks):
+    N concurrent callers through hx_service, driven by the C++ host harness (host/hx_callers.cpp).  `blocking` = N OS
+    threads each in hx_service_search; `tasks` = N logical callers multiplexed on 8 threads with submit / poll."""
+    from helix_db_b200 import callers
+    ref_ids, ref_sc, ref_cnt = ix.search_batch(queries, hx.SearchParams.strict(k, ef))
+    svc = ix.service(k, ef, capacity=2048, max_batch=128)
+    info = svc.stats()
+    rows = []
+    all_exact = True
+    for mode, ncall, nthr in (("blocking", 1, 0), ("blocking", 16, 0), ("blocking", 64, 0), ("blocking", 256, 0),
+                              ("tasks", 256, 8), ("tasks", 1024, 8)):
+        rep, ids, sc, cnt = callers.run(svc, ix, queries, k, ef, ncall, mode=mode, n_threads=nthr, seconds=seconds)
+        exact = bool(ids.tolist() == ref_ids.tolist() and sc.tobytes() == ref_sc.tobytes() and cnt.tolist() == ref_cnt.tolist())
+        all_exact = all_exact and exact and rep["errors"] == 0
+        rows.append({"mode": mode, "callers": ncall, "host_threads": rep["threads"], "qps": round(rep["qps"], 1),
+                     "p50_us": rep["p50_us"], "p99_us": rep["p99_us"], "max_us": rep["max_us"],
+                     "completed": rep["completed"], "bit_exact_vs_hx_search": exact})
+    st = svc.stats()
+    svc.close()
+    direct = []
+    for ncall in (1, 16):   # round-1 path for comparison: a blocking B = 1 hx_search per caller thread, no service
+        rep, _, _, _ = callers.run(None, ix, queries[:1024], k, ef, ncall, mode="direct", seconds=min(seconds, 0.5))
+        direct.append({"callers": ncall, "qps": round(rep["qps"], 1), "p50_us": rep["p50_us"], "p99_us": rep["p99_us"]})
+    best256 = max((r for r in rows if r["callers"] == 256), key=lambda r: r["qps"])
+    return {"api": "hx_service_submit / hx_service_poll / hx_service_search (C ABI), one query per call",
+            "kernel": "k_hnsw_search_cta_ring, one CTA per query, results written to host-mapped slots",
+            "launch_shape": {x: info[x] for x in ("cta_warps", "rows_in_flight", "visited_cap", "smem_bytes", "ctas_per_sm")},
+            "queries_pool": int(len(queries)), "runs": rows, "at_256_callers": {"qps": best256["qps"], "p99_us": best256["p99_us"],
+                                                                              "mode": best256["mode"]},
+            "launches": st["launches"], "queries_per_launch_avg": round(st["completed"] / max(st["launches"], 1), 2),
+            "max_batch_seen": st["max_batch_seen"], "all_bit_exact": all_exact,
+            "direct_hx_search_b1_per_thread": direct}
+
+
+def measure_dense(hx, torch, args, world, rank, local_rank, dev, stream, uid):
+    """C4 shape: exhaustive top-10 of a 1024-query batch against 1.25M x 768 bf16 rows PER GPU through the tensor cores
+    (k_dense_scores: tcgen05 + TMEM + TMA), nominees re-ranked by the exact fp32 scan; with N > 1 the corpus is the
+    id-range union of the ranks' shards (8 GPUs = C4's 10M rows) and every step ends with ONE ncclAllGather + merge
+    (hx_search_sharded*, issued by the library)."""
+    from helix_db_b200 import sharding as sh
+    rows, dim, k, B = args.dense_rows_per_gpu, args.dim, K, args.dense_batch
+    lo = rank * rows
+    metric = hx.Metric.Cosine if args.metric == "cosine" else hx.Metric.Euclidean
+    ix = hx.VectorIndex(metric, hx.VectorIndexConfig("dense_c4", "embedding", dim), device=local_rank, storage=1)
+    t0 = time.perf_counter()
+    ix.generate_vectors(lo, rows, SEED, N_CENTROIDS, SIGMA, KIND)
+    ix.load_graph(0, np.array([lo], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
+    ix.set_entry(lo, 0)
+    gen_s = time.perf_counter() - t0
+    g = sh.ShardGroup(ix, world, rank, uid)
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    steps = args.steps
+    qsets = [ix.generate_queries(SEED, B, first_query=30_000_000 + s * B, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
+             for s in range(steps + args.warmup)]          # every rank answers the SAME queries
+    params = hx.SearchParams.strict(k)
+    d_q = [torch.from_numpy(q).to(dev) for q in qsets]
+    o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
+    o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+
+    def step_device(s):
+        g.search_device(sh.DENSE, d_q[s].data_ptr(), B, params, k, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+
+    ms_total = _timed_device(torch, dev, steps, args.warmup, step_device)
+    import torch.distributed as dist
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    dev_ids = o_ids.cpu().numpy().view(np.uint64).copy()
+    # e2e: host buffers through hx_search_sharded (H2D queries, D2H merged results, one stream sync)
+    h_q = [torch.from_numpy(q).pin_memory().numpy() for q in qsets]
+    for s in range(args.warmup):
+        g.search(sh.DENSE, h_q[s], params, k)
+    if world > 1:
+        dist.barrier()
+    kms = lms = cms = 0.0
+    t0 = time.perf_counter()
+    for s in range(steps):
+        e_ids, e_sc, e_cnt = g.search(sh.DENSE, h_q[args.warmup + s], params, k)
+        a, b = g.last_ms()
+        lms += a
+        cms += b
+        kms += ix.last_kernel_ms()[0]
+    wall = time.perf_counter() - t0
+    tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    wall = float(tw.item())
+    same = bool(e_ids.tolist() == dev_ids.tolist())
+    ldb = (dim + 63) // 64 * 64
+    flop = 2.0 * B * rows * ldb
+    kernel_ms = kms / steps
+    # recall of the merged answer vs the exact scan of every shard merged the same way
+    rq = min(64, B)
+    last = qsets[args.warmup + steps - 1]
+    gi, gs, gc = exact_topk_device_full(hx, torch, ix, last[:rq], rows, lo, k)
+    if world > 1:
+        lay = sh.block_layout(rq, k)
+        blk = np.zeros(lay["bytes"], dtype=np.uint8)
+        bi, bs, bc = sh.block_views(blk, rq, k)
+        bi[:], bs[:], bc[:] = gi, gs, gc.astype(np.uint32)
+        allb = torch.zeros((world, lay["bytes"]), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb.view(-1), torch.from_numpy(blk).to(dev))
+        truth = sh.merge_blocks_reference([allb[r].cpu().numpy() for r in range(world)], rq, k, k)[0]
+    else:
+        truth = gi
+    rec = recall_at_k(dev_ids[:rq], truth)
+    out = {"metric": "queries/sec, exhaustive top-10 through the tensor cores (config C4 shape)",
+           "value": round(steps * B / (ms_total / 1e3), 1), "unit": "queries/s", "n_gpus": world, "steps": steps,
+           "ms_per_step": round(ms_total / steps, 3), "scaling": "weak (rows per GPU fixed; 8 GPUs = C4's 10M rows)",
+           "dtype": "bf16 (fp32 accumulate in TMEM) + f32 exact re-rank", "recall_at_10_vs_exact_scan": round(rec, 4),
+           "config": {"workload": f"C4 shard shape: {B} queries x {rows} rows per GPU x d={dim} (total {rows * world} rows on "
+                                  f"{world} GPU(s)), k={k}", "setup": {"generate_s": round(gen_s, 2)}},
+           "e2e": {"value": round(steps * B / wall, 1), "unit": "queries/s", "ms_per_step": round(wall / steps * 1e3, 3),
+                   "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * (k * 12 + 4),
+                   "api": "hx_search_sharded(HX_SHARD_DENSE) (C ABI, pinned host buffers, blocking)",
+                   "identical_to_device_path": same},
+           "step_breakdown_ms": {"local_search": round(lms / steps, 3), "all_gather_and_merge": round(cms / steps, 3),
+                                 "k_dense_scores": round(kernel_ms, 4)},
+           "collective": (f"1 x ncclAllGather of {sh.block_layout(B, k)['bytes']} B per rank per step (issued by "
+                          f"libhelix_b200 through dlopen'ed NCCL) + merge kernel") if world > 1 else "none (single shard)",
+           "roofline": {"bound": "tensor", "kernel": "k_dense_scores", "achieved": round(flop / (kernel_ms * 1e-3) / 1e12, 1) if kernel_ms else None,
+                        "peak": tf_peak, "unit": "TFLOP/s", "frac": round(flop / (kernel_ms * 1e-3) / 1e12 / tf_peak, 4) if kernel_ms else None,
+                        "traffic": ncu_traffic("k_dense_scores", {"queries": B, "rows": rows, "dim": dim}),
+                        "flop_per_launch_per_gpu": flop, "kernel_ms_per_launch": round(kernel_ms, 4),
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); per GPU"},
+           "gpu_launches": steps * 8}
+    if world == 1 and rank == 0 and not args.no_cpu:
+        # the oracle's exact scan (search_exact = restricted_exact_scan over every id) on a bounded sample: parity + CPU rate
+        from oracle import hxo
+        om = hxo.COSINE if args.metric == "cosine" else hxo.EUCLIDEAN
+        ora = hxo.Index(om, dim)
+        for a0 in range(0, rows, 65536):
+            ids_, rows_ = ix.download_vectors(a0, min(65536, rows - a0))
+            ora.put_vectors(ids_, rows_)
+        ora.set_entry(lo, 0)
+        cores = available_cores()
+        ns = 2 * cores
+        t0 = time.perf_counter()
+        ci, cs, cc, _ = ora.search_exact_batch(last[:ns], k, threads=cores)
+        secs = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": round(ns / secs, 2), "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": f"{ns} queries of the last step, exact scan of all {rows} rows (oracle search_exact)",
+                               "bit_exact_vs_device": bool(ci.tolist() == dev_ids[:ns].tolist() and
+                                                           cs.tobytes() == o_sc.cpu().numpy()[:ns].tobytes())}
+    g.close()
+    ix.close()
+    return out
+
+
+def measure_d1536(hx, torch, args, local_rank, dev, stream):
+    """The reference's own million-row traversal fixture shape (index_lifecycle_scale.rs:1407-1430: d=1536, Euclidean,
+    m=16, m0=32, ef_construction=200) on synthetic vectors of that shape: HNSW top-10 + its four prefilter ranges."""
+    import argparse as _ap
+    a2 = _ap.Namespace(**vars(args))
+    a2.dim, a2.metric, a2.n = 1536, "euclidean", args.d1536_rows
+    n, dim, k = a2.n, a2.dim, K
+    Q = 16384
+    steps = max(2, min(args.steps, 5))
+    ix, setup = build_index(hx, a2, local_rank, 0, n)
+    hbm_peak, peak_src = measured_peaks()
+    qsets = [ix.generate_queries(SEED, Q, first_query=40_000_000 + s * Q, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
+             for s in range(steps + args.warmup)]
+    params = hx.SearchParams.strict(k, EF)
+    d_q = [torch.from_numpy(q).to(dev) for q in qsets]
+    o_ids = torch.zeros((Q, k), dtype=torch.int64, device=dev)
+    o_sc = torch.zeros((Q, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((Q,), dtype=torch.int32, device=dev)
+
+    def step_device(s):
+        ix.search_device(d_q[s].data_ptr(), Q, params, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+
+    rq = 256
+    truth = exact_topk_device(hx, torch, ix, qsets[0][:rq], n, 0, k)
+    step_device(0)
+    torch.cuda.synchronize(dev)
+    first_ids = o_ids.cpu().numpy().view(np.uint64).copy()
+    first_sc = o_sc.cpu().numpy().copy()
+    recall = recall_at_k(first_ids[:rq], truth)
+    ix.last_kernel_ms()
+    for s in range(args.warmup):
+        step_device(s)
+    torch.cuda.synchronize(dev)
+    ix.last_kernel_ms()
+    ms_total = _timed_device(torch, dev, steps, 0, lambda s: step_device(args.warmup + s))
+    kms, kl = ix.last_kernel_ms()
+    pst = hx.SearchParams.strict(k, EF)
+    pst.collect_stats = True
+    st = hx.SearchStats()
+    ix.search_device(d_q[0].data_ptr(), Q, pst, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream, st)
+    ix.last_kernel_ms()
+    kernel_ms = kms / max(kl, 1)
+    achieved = st.algorithmic_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms else 0.0
+    flags, fstatus = ix.device_flags(stream)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        ix.search_batch(qsets[args.warmup + s], params)
+    e2e = steps * Q / (time.perf_counter() - t0)
+    out = {"metric": "queries/sec @ recall@10, 1M x 1536 Euclidean HNSW top-10 (the reference's traversal fixture shape)",
+           "value": round(steps * Q / (ms_total / 1e3), 1), "unit": "queries/s", "steps": steps,
+           "ms_per_step": round(ms_total / steps, 3), "recall_at_10": round(recall, 4), "dtype": "f32",
+           "config": {"workload": f"{n}x{dim} f32 euclidean HNSW top-10 (m=16, m0=32, ef_construction=200, ef={EF}), {Q} "
+                                  f"independent single-query traversals per step", "setup": setup},
+           "e2e": {"value": round(e2e, 1), "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4,
+                   "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 8 + 4, "api": "hx_search (C ABI, host buffers, blocking)"},
+           "roofline": {"bound": "hbm", "kernel": "k_hnsw_search_ring", "achieved": round(achieved, 1), "peak": hbm_peak,
+                        "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": int(st.algorithmic_bytes), "kernel_ms_per_launch": round(kernel_ms, 4),
+                        "distance_computations_per_query": round(st.distance_computations / Q, 1)},
+           "device_flags": flags}
+    if not args.no_cpu:
+        from oracle import hxo
+        t0 = time.perf_counter()
+        ora = oracle_from_device(hxo, ix, a2)
+        mirror_s = time.perf_counter() - t0
+        cores = available_cores()
+        ns = 1024
+        ci, cs, cc, cst, secs = ora.search_batch(qsets[0][:ns], k, EF, threads=cores)
+        out["cpu_baseline"] = {"value": round(ns / secs, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": f"{ns} queries of the first step, one query per thread, identical graph and vectors",
+                               "ids_identical_to_device": bool(ci.tolist() == first_ids[:ns].tolist()),
+                               "scores_identical_to_device": bool(cs.tobytes() == first_sc[:ns].tobytes()),
+                               "mirror_s": round(mirror_s, 1)}
+        pf = measure_prefilter(hx, torch, ix, a2, dev, stream, n, dim, ora=ora, label_steps=2)
+        out["prefilter_reference_shapes"] = pf["reference_shapes"]
+        out["prefilter_label_sets"] = {"value": pf["value"], "roofline_frac": pf["roofline"]["frac"],
+                                       "bit_exact_vs_oracle": pf.get("cpu_baseline", {}).get("bit_exact_vs_device")}
+        del ora
+    ix.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -276,7 +738,10 @@ def run_ours(args):
     truth = exact_topk_device(hx, torch, ix, qsets[0][:rq], n, 0, k)
     step_device(0)
     torch.cuda.synchronize(dev)
-    recall = recall_at_k(o_ids[:rq].cpu().numpy().view(np.uint64), truth)
+    strict_ids0 = o_ids.cpu().numpy().view(np.uint64).copy()     # the device's strict answer for query set 0 (parity check)
+    strict_sc0 = o_sc.cpu().numpy().copy()
+    strict_cnt0 = o_cnt.cpu().numpy().copy()
+    recall = recall_at_k(strict_ids0[:rq], truth)
 
     # ---- value: W warm-up steps, then exactly K timed steps, barrier + synchronize on both sides ----------------------
     for s in range(args.warmup):
@@ -295,6 +760,9 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     kernel_ms_total, kernel_launches = ix.last_kernel_ms()
+    dev_flags, dev_flag_status = ix.device_flags(stream)   # error flags ORed over the timed launches: must be 0
+    if dev_flags != 0:
+        raise RuntimeError(f"device error flags {dev_flags:#x} raised inside the timed region (status {dev_flag_status})")
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -420,49 +888,95 @@ def run_ours(args):
         }
         default_planes = planes
 
-    # ---- sharded path (north_star): id-range shards of the SAME corpus, one all-gather, merge ----------------------------
+    # ---- sharded path (north_star): id-range shards of the SAME corpus behind the C ABI ------------------------------------
+    # hx_search_sharded_device: local search writes into the send block -> ONE ncclAllGather issued by the library -> merge.
     sharded = None
+    uid = None
+    if world > 1:
+        from helix_db_b200 import sharding as sh
+        uid = sh.exchange_unique_id(rank, device=dev)
     if world > 1 and not args.no_sharded:
         lo, hi = rank * n // world, (rank + 1) * n // world
         sx, s_setup = build_index(hx, args, local_rank, lo, hi - lo)
+        grp = sh.ShardGroup(sx, world, rank, uid)
         # every rank searches the SAME queries (rank 0's sets) against its shard
         sq = [ix.generate_queries(SEED, Q, first_query=s * Q, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND) for s in range(n_sets)]
         d_sq = [torch.from_numpy(q).to(dev) for q in sq]
-        from importlib import import_module
-        sharding = import_module("helix_db_b200.sharding")
-        searcher = sharding.ShardedSearcher(hx, sx, world, rank, Q, k, dev)
-
-        def step_sharded(s):
-            # local search -> ONE packed all-gather (12*k+4 bytes per query per shard) -> (score,id) merge kernel
-            ids_, sc_, cnt_ = searcher.step(d_sq[s], params, stream)
-            o_ids.copy_(ids_)
-
         truth_s = exact_topk_device(hx, torch, ix, sq[0][:rq], n, 0, k)
-        step_sharded(0)
+        step_device(0)   # the unsharded index on the same queries: the recall the shards have to match
+        ix.search_device(d_sq[0].data_ptr(), Q, params, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+        torch.cuda.synchronize(dev)
+        target = recall_at_k(o_ids[:rq].cpu().numpy().view(np.uint64), truth_s)
+
+        def run_sharded(s, p_local):
+            grp.search_device(sh.HNSW, d_sq[s].data_ptr(), Q, p_local, k, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
+
+        # iso-recall tuning of the per-shard beam: a shard is 1/world of the corpus, so the unsharded ef is over-provisioned
+        tuning, chosen = [], None
+        for ef_s in (10, 12, 16, 20, 24, 32, 48, 64, EF):
+            p_loc = hx.SearchParams.strict(k, ef_s)
+            run_sharded(0, p_loc)
+            torch.cuda.synchronize(dev)
+            r = recall_at_k(o_ids[:rq].cpu().numpy().view(np.uint64), truth_s)
+            tuning.append({"ef_per_shard": ef_s, "recall_at_10": round(r, 4)})
+            if chosen is None and r >= target:
+                chosen = ef_s
+                break
+        chosen = chosen or EF
+        p_loc = hx.SearchParams.strict(k, chosen)
+        run_sharded(0, p_loc)
         torch.cuda.synchronize(dev)
         s_recall = recall_at_k(o_ids[:rq].cpu().numpy().view(np.uint64), truth_s)
         for s in range(args.warmup):
-            step_sharded(s)
+            run_sharded(s, p_loc)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for s in range(args.steps):
-            step_sharded(args.warmup + s)
+            run_sharded(args.warmup + s, p_loc)
         g1.record()
         barrier()
         ts = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sflags, _ = sx.device_flags(stream)
+        # the same per-shard parameters at the unsharded beam width, for reference
+        p_full = hx.SearchParams.strict(k, EF)
+        for s in range(2):
+            run_sharded(s, p_full)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for s in range(min(args.steps, 4)):
+            run_sharded(args.warmup + s, p_full)
+        f1.record()
+        barrier()
+        tf_ = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
+        blk = sh.block_layout(Q, k)["bytes"]
         sharded = {"value": round(args.steps * Q / (float(ts.item()) / 1e3), 1), "unit": "queries/s",
-                   "recall_at_10": round(s_recall, 4), "shard_vectors": hi - lo, "collective": "1 x all_gather_into_tensor "
-                   f"of {(12 * k + 4) * Q} B per rank per step (NCCL) + hx_merge_topk_device",
-                   "ms_per_step": round(float(ts.item()) / args.steps, 3), "shard_build_s": s_setup["build_s"]}
+                   "recall_at_10": round(s_recall, 4), "unsharded_recall_at_10_same_queries": round(target, 4),
+                   "ef_per_shard": chosen, "k_per_shard": k, "iso_recall_tuning": tuning,
+                   "value_at_unsharded_ef": round(min(args.steps, 4) * Q / (float(tf_.item()) / 1e3), 1),
+                   "shard_vectors": hi - lo,
+                   "api": "hx_search_sharded_device (C ABI): local search into the send block, ncclAllGather, merge kernel",
+                   "collective": f"1 x ncclAllGather of {blk} B per rank per step (issued by libhelix_b200 via dlopen'ed NCCL)",
+                   "ms_per_step": round(float(ts.item()) / args.steps, 3), "shard_build_s": s_setup["build_s"],
+                   "device_flags": sflags}
+        grp.close()
         sx.close()
+
+    # ---- the other BASELINE configs as sub-results of the same line --------------------------------------------------------------
+    dense_c4 = None
+    if not args.no_subresults:
+        dense_c4 = measure_dense(hx, torch, args, world, rank, local_rank, dev, stream, uid)
 
     # ---- CPU baseline: the oracle on the box's host cores, same graph, bounded sample (rank 0, N = 1 only) -------------------
     cpu = None
+    ora = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args, ix, qsets[0], truth[:rq] if rq else None,
-                           default_planes if default_mode is not None else None)
+        cpu, ora = cpu_baseline(args, ix, qsets[0], truth[:rq] if rq else None,
+                                default_planes if default_mode is not None else None)
         if default_mode is not None and "default_mode_qps" in cpu:
             default_mode["cpu_port_qps"] = cpu.pop("default_mode_qps")
             default_mode["cpu_port_recall_at_10"] = cpu.pop("default_mode_recall")
@@ -470,9 +984,28 @@ def run_ours(args):
             cpu.pop("default_mode_sample", None)
             default_mode["cpu_port_identical_to_device"] = bool(d_ids_first is not None and
                                                                 pi.tolist() == d_ids_first[:len(pi)].tolist())
+        # id-level parity on the headline config: every CPU-sampled query, ids + score bytes + counts
+        ci, cs, cc = cpu.pop("_ids"), cpu.pop("_scores"), cpu.pop("_counts")
+        m = len(ci)
+        parity = {"queries_checked": int(m),
+                  "ids_identical_to_device": bool(ci.tolist() == strict_ids0[:m].tolist() and cc.tolist() == strict_cnt0[:m].tolist()),
+                  "scores_identical_to_device": bool(cs.tobytes() == strict_sc0[:m].tobytes()),
+                  "oracle": "C restatement of search.rs / restricted.rs traversing the identical graph and vectors"}
+        # and the recall ground truth itself: the device's exact scan against the oracle's exact scan
+        ng = min(2 * available_cores(), rq)
+        ei, es, ec, _ = ora.search_exact_batch(qsets[0][:ng], k, threads=available_cores())
+        parity["ground_truth_vs_oracle_exact_scan"] = {"queries": int(ng), "identical": bool(ei.tolist() == truth[:ng].tolist())}
+        cpu["parity"] = parity
+
+    prefilter = callers_res = d1536 = None
+    if rank == 0 and world == 1 and not args.no_subresults:
+        prefilter = measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=ora)
+        callers_res = measure_callers(hx, ix, qsets[0][:8192], k, EF, args.callers_seconds)
+    del ora
 
     impl = os.environ.get("HX_HNSW_IMPL", "ring")
     hnsw_kernel = {"ring": "k_hnsw_search_ring", "tma": "k_hnsw_search_tma", "ldg": "k_hnsw_search_warp"}.get(impl, impl)
+    line = None
     if rank == 0:
         line = {
             "metric": "queries/sec @ recall@10, DBpedia-1M d=768 top-10, 1/2/4/8 B200 vs CPU ref",
@@ -480,21 +1013,9 @@ def run_ours(args):
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "recall_at_10": round(recall, 4),
-            "config": {
-                "workload": f"C2: {n}x{dim} f32 {args.metric} HNSW top-10 (m=16, m0=32, ef_construction=200, ef={EF}), "
-                            f"independent single-query traversals (batch=1 semantics, no cross-query sharing), "
-                            f"{Q} queries per GPU per step",
-                "queries_per_step_per_gpu": Q, "parallelism": "single GPU" if world == 1 else
-                f"{world} full replicas, queries partitioned, no data-path collective",
-                "l2": "corpus 3.07 GB >> 126 MB L2; distinct queries every step and rank",
-                "graph": "built on the device (hx_index_build), identical adjacency mirrored into the CPU oracle",
-                "data_recipe": (f"{args.recipe}: unit-normalised {N_CENTROIDS}-component Gaussian mixture, sigma={SIGMA}, "
-                                + (f"rank-{KIND} latent space -> fixed random projection to {dim}-d + 2% noise"
-                                   if KIND else f"isolated isotropic clusters in {dim}-d") + ", seed=0x0DB9ED1A"),
-                "setup": setup,
-            },
+            "config": c2_config(args, world, setup),
             "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4,
-                    "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 4 + 4,
+                    "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 8 + 4,
                     "api": "hx_search (C ABI, pinned host buffers, blocking)"},
             "gpu_launches": args.steps * (1 if impl == "ring" else 2),
             "launches_per_step": ({hnsw_kernel: 1} if impl == "ring" else {"k_validate_and_header": 1, hnsw_kernel: 1}),
@@ -506,16 +1027,31 @@ def run_ours(args):
                          "distance_computations_per_query": round(st_sum["distance_computations"] / (args.steps * Q), 1)},
             "single_stream_batch1": {"latency_us": round(batch1_us, 1), "qps": round(1e6 / batch1_us, 1),
                                      "note": "one query per hx_search_device call, calls issued back to back"},
+            "device_flags_in_timed_region": dev_flags,
             "clocks": clocks,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity"] = parity
         if sharded is not None:
             line["sharded"] = sharded
         if default_mode is not None:
             line["default_mode"] = default_mode
-        print(json.dumps(line), flush=True)
+        if callers_res is not None:
+            line["concurrent_callers"] = callers_res
+        if prefilter is not None:
+            line["prefilter"] = prefilter
+        if dense_c4 is not None:
+            line["dense_c4"] = dense_c4
     ix.close()
+    if rank == 0 and world == 1 and not args.no_subresults and not args.no_d1536:
+        line["euclid_d1536"] = measure_d1536(hx, torch, args, local_rank, dev, stream)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+        if parity is not None and not (parity["ids_identical_to_device"] and parity["scores_identical_to_device"]):
+            print("PARITY FAILURE: device ids / scores differ from the oracle on the headline config", file=sys.stderr)
+            sys.exit(3)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -553,187 +1089,50 @@ def cpu_baseline(args, ix, queries, truth, planes=None):
                       f"identical graph and vectors",
             "single_thread_qps": round(min(sample, 256) / secs1, 1), "recall_at_10": None if rec is None else round(rec, 4),
             "distance_computations_per_query": round(st["distance_computations"] / sample, 1),
-            "mirror_s": round(mirror_s, 1)}
+            "mirror_s": round(mirror_s, 1),
+            "build_flags": "gcc -O2 -ffp-contract=off, AVX+FMA distance kernels via target attributes (oracle/Makefile); no -march=native: the traversal is DRAM-latency bound",
+            "_ids": ids, "_scores": sc, "_counts": cnt}
     out.update(extra)
-    return out
+    return out, ora
 
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_prefilter(args):
-    """Config C3: 1M x 768 prefiltered top-10 (graph-label filter), exact brute-force scan path, single B200.
-
-    A step = 100 queries, query b restricted to the label set {id : id mod 100 == b} (10 000 candidates = 1 % of the
-    corpus each), so one step reads every row of the 3.07 GB corpus exactly once (>> 126 MB L2)."""
-    import ctypes as C
-
+    """--workload prefilter: config C3 alone (the default line carries the same object as `prefilter`)."""
     import torch
 
     import helix_db_b200 as hx
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    n, dim, k, sel = args.n, args.dim, K, 100
-    B = sel
-    hbm_peak, peak_src = measured_peaks()
+    n, dim = args.n, args.dim
     metric = hx.Metric.Cosine if args.metric == "cosine" else hx.Metric.Euclidean
     ix = hx.VectorIndex(metric, hx.VectorIndexConfig("dbpedia_1m_synthetic", "embedding", dim), device=local_rank)
     ix.generate_vectors(0, n, SEED, N_CENTROIDS, SIGMA, KIND)
     ix.load_graph(0, np.array([0], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
     ix.set_entry(0, 0)
-    n_sets = args.steps + args.warmup
-    qsets = [ix.generate_queries(SEED, B, first_query=(rank * n_sets + s) * B, n_centroids=N_CENTROIDS, sigma=SIGMA,
-                                 kind=KIND) for s in range(n_sets)]
-    cand_lists = [np.arange(b, n, sel, dtype=np.uint64) for b in range(B)]
-    cand_ids = np.concatenate(cand_lists)
-    offs = np.zeros(B + 1, dtype=np.uint64)
-    offs[1:] = np.cumsum([len(c) for c in cand_lists])
-    per_q = int(max(len(c) for c in cand_lists))
-    total = int(offs[-1])
-    d_slots = torch.from_numpy(cand_ids.astype(np.uint32).view(np.int32)).to(dev)      # ids == slots here (first_id 0)
-    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
-    d_q = [torch.from_numpy(q).to(dev) for q in qsets]
-    o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
-    o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
-    o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-    params = hx.SearchParams.strict(k)
-
-    def step_device(s):
-        ix.search_restricted_device(d_q[s].data_ptr(), B, params, d_slots.data_ptr(), d_offs.data_ptr(), total, per_q,
-                                    o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), stream)
-
-    for s in range(args.warmup):
-        step_device(s)
-    torch.cuda.synchronize(dev)
-    ix.last_kernel_ms()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(args.steps):
-        step_device(args.warmup + s)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    kms, kl = ix.last_kernel_ms()
-    value = args.steps * B / (ms_total / 1e3)
-    bytes_per_launch = total * (4 * dim + (4 if args.metric == "cosine" else 0))
-    kernel_ms = kms / max(kl, 1)
-    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-    dev_ids = o_ids.cpu().numpy().view(np.uint64).copy()
-    dev_sc = o_sc.cpu().numpy().copy()
-
-    # e2e: candidate ids, offsets and queries in pinned host memory -> hx_search_restricted_multi -> host results
-    L = hx.load_library()
-    cp = params._c()
-    h_q = [torch.from_numpy(q).pin_memory() for q in qsets]
-    h_c = torch.from_numpy(cand_ids.view(np.int64)).pin_memory()
-    h_o = torch.from_numpy(offs.view(np.int64)).pin_memory()
-    h_ids = torch.zeros((B, k), dtype=torch.int64).pin_memory()
-    h_sc = torch.zeros((B, k), dtype=torch.float32).pin_memory()
-    h_cnt = torch.zeros((B,), dtype=torch.int32).pin_memory()
-
-    def step_host(s):
-        rc = L.hx_search_restricted_multi(ix.h, C.cast(h_q[s].data_ptr(), C.POINTER(C.c_float)), B, C.byref(cp),
-                                          C.cast(h_c.data_ptr(), C.POINTER(C.c_uint64)),
-                                          C.cast(h_o.data_ptr(), C.POINTER(C.c_uint64)),
-                                          C.cast(h_ids.data_ptr(), C.POINTER(C.c_uint64)),
-                                          C.cast(h_sc.data_ptr(), C.POINTER(C.c_float)),
-                                          C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None)
-        if rc != 0:
-            raise RuntimeError(L.hx_last_error().decode())
-
-    for s in range(args.warmup):
-        step_host(s)
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        step_host(args.warmup + s)
-    t1 = time.perf_counter()
-    e2e_value = args.steps * B / (t1 - t0)
-    same = bool(h_ids.numpy().view(np.uint64).tolist() == dev_ids.tolist() and h_sc.numpy().tobytes() == dev_sc.tobytes())
-
-    # e2e with the label sets resident on the device (hx_candidates: uploaded + mapped once, like a label bitmap cached per
-    # snapshot, SURVEY §8d): per step only the queries and 24 bytes per query cross PCIe
-    t0 = time.perf_counter()
-    dsets = [ix.cache_candidates(hx.RestrictedVectorCandidates(c)) for c in cand_lists]
-    cache_s = time.perf_counter() - t0
-    set_arr = (C.c_void_p * B)(*[d.h for d in dsets])
-
-    def step_host_sets(s):
-        rc = L.hx_search_restricted_sets(ix.h, C.cast(h_q[s].data_ptr(), C.POINTER(C.c_float)), B, C.byref(cp), set_arr, B,
-                                         C.cast(h_ids.data_ptr(), C.POINTER(C.c_uint64)),
-                                         C.cast(h_sc.data_ptr(), C.POINTER(C.c_float)),
-                                         C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None)
-        if rc != 0:
-            raise RuntimeError(L.hx_last_error().decode())
-
-    for s in range(args.warmup):
-        step_host_sets(s)
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        step_host_sets(args.warmup + s)
-    t1 = time.perf_counter()
-    e2e_sets = args.steps * B / (t1 - t0)
-    same_sets = bool(h_ids.numpy().view(np.uint64).tolist() == dev_ids.tolist() and h_sc.numpy().tobytes() == dev_sc.tobytes())
-
-    cpu = None
-    if not args.no_cpu and rank == 0:
+    ora = None
+    if not args.no_cpu:
         from oracle import hxo
-        om = hxo.COSINE if args.metric == "cosine" else hxo.EUCLIDEAN
-        ora = hxo.Index(om, dim)
+        ora = hxo.Index(hxo.COSINE if args.metric == "cosine" else hxo.EUCLIDEAN, dim)
         for lo in range(0, n, 65536):
             ids_, rows_ = ix.download_vectors(lo, min(65536, n - lo))
             ora.put_vectors(ids_, rows_)
         ora.set_entry(0, 0)
-        cores = available_cores()
-        qs = qsets[args.warmup + args.steps - 1]
-        ci, cs, cc, secs = ora.search_restricted_batch(qs, k, cand_ids, offs, threads=cores)
-        parity = bool(ci.tolist() == dev_ids.tolist() and cs.tobytes() == dev_sc.tobytes())
-        cpu = {"value": round(B / secs, 1), "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": f"the last step's {B} queries x {per_q} candidates, one query per thread, {cores} threads",
-               "bit_exact_vs_device": parity}
-    if rank == 0:
-        line = {
-            "metric": "queries/sec, DBpedia-1M d=768 prefiltered top-10 (graph-label filter), exact scan (config C3)",
-            "value": round(value, 1), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "recall_at_10": 1.0,
-            "config": {"workload": f"C3: {n}x{dim} f32 {args.metric}, {B} queries per step, query b restricted to "
-                                   f"{{id : id mod {sel} == b}} ({per_q} candidates each): every row read once per step",
-                       "l2": "3.07 GB streamed per step >> 126 MB L2", "recipe": args.recipe},
-            "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4 + total * 8 + (B + 1) * 8,
-                    "d2h_bytes_per_step": B * (k * 12 + 4) + B * 4 + 4, "api": "hx_search_restricted_multi (C ABI, pinned host)",
-                    "identical_to_device_path": same},
-            "e2e_device_resident_sets": {"value": round(e2e_sets, 1), "unit": "queries/s",
-                                         "h2d_bytes_per_step": B * dim * 4 + B * 24, "d2h_bytes_per_step": B * (k * 12 + 4) + B * 4 + 4,
-                                         "api": "hx_search_restricted_sets (label sets uploaded once with hx_candidates_create)",
-                                         "sets_upload_s": round(cache_s, 3), "identical_to_device_path": same_sets},
-            "gpu_launches": args.steps * 3,
-            "launches_per_step": {"k_validate_and_header": 1, "k_scan": 1, "k_select": 1},
-            "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_scan", {"queries": B, "candidates": per_q, "dim": dim}), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms_per_launch": round(kernel_ms, 4)},
-            "clocks": clocks,
-        }
-        if cpu:
-            line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    line = measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=ora)
+    line.update({"n_gpus": 1, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                 "data": "synthetic", "clocks": sampler.stop()})
+    print(json.dumps(line), flush=True)
     ix.close()
 
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_dense(args):
-    """Configs C4/C5 shape: exhaustive top-10 of a large query batch through the tensor cores (hx_search_dense: tcgen05
-    bf16 contraction -> per-run nominees -> exact fp32 re-rank).  With --gpus N the corpus (--n rows in total) is split by
-    id range, every rank scores every query against its shard, ONE NCCL all-gather moves the per-shard top-k and the
-    merge kernel selects the global top-k by (score, id)."""
+    """--workload dense: the C4 shape alone (the default line carries the same object as `dense_c4`)."""
     import torch
 
     import helix_db_b200 as hx
@@ -741,107 +1140,23 @@ def run_dense(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        from helix_db_b200 import sharding as sh
+        dist.init_process_group("nccl", device_id=dev)
+        uid = sh.exchange_unique_id(rank, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    n_total, dim, k = args.n, args.dim, K
-    B = args.queries_per_step if args.queries_per_step != 8192 else 1024
-    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
-    n = hi - lo
-    metric = hx.Metric.Cosine if args.metric == "cosine" else hx.Metric.Euclidean
-    ix = hx.VectorIndex(metric, hx.VectorIndexConfig("dense", "embedding", dim), device=local_rank, storage=1)
-    ix.generate_vectors(lo, n, SEED, N_CENTROIDS, SIGMA, KIND)
-    ix.load_graph(0, np.array([lo], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
-    ix.set_entry(lo, 0)
-    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
-    # every rank answers the SAME queries
-    qsets = [ix.generate_queries(SEED, B, first_query=s * B, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
-             for s in range(args.steps + args.warmup)]
-    params = hx.SearchParams.strict(k)
-    sharding = None
-    if world > 1:
-        from importlib import import_module
-        sharding = import_module("helix_db_b200.sharding")
-        pack = torch.zeros((B, 3 * k + 1), dtype=torch.int32, device=dev)
-        apack = torch.zeros((world, B, 3 * k + 1), dtype=torch.int32, device=dev)
-        o_ids = torch.zeros((B, k), dtype=torch.int64, device=dev)
-        o_sc = torch.zeros((B, k), dtype=torch.float32, device=dev)
-        o_cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-
-    def merge_across_ranks(ids, sc, cnt, nq, pk, apk, oi, osc, ocn):
-        sharding.pack_topk(torch.from_numpy(ids.view(np.int64).copy()).to(dev), torch.from_numpy(sc.copy()).to(dev),
-                           torch.from_numpy(cnt.astype(np.int32)).to(dev), pk)
-        sharding.all_gather_topk(pk, world, apk)
-        a_ids, a_sc, a_cnt = sharding.unpack_topk(apk, k)
-        hx.merge_topk_device(local_rank, a_ids.data_ptr(), a_sc.data_ptr(), a_cnt.data_ptr(), world, nq, k,
-                             oi.data_ptr(), osc.data_ptr(), ocn.data_ptr(), stream)
-        torch.cuda.synchronize(dev)
-        return oi.cpu().numpy().view(np.uint64)
-
-    def step(s):
-        ids, sc, cnt = ix.search_dense_batch(qsets[s], params)
-        kms = ix.last_kernel_ms()[0]
-        if world == 1:
-            return ids, kms
-        return merge_across_ranks(ids, sc, cnt, B, pack, apack, o_ids, o_sc, o_cnt), kms
-
-    for s in range(args.warmup):
-        step(s)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    kms, t0 = 0.0, time.perf_counter()
-    last = None
-    for s in range(args.steps):
-        last, km = step(args.warmup + s)
-        kms += km
-    torch.cuda.synchronize(dev)
-    wall = time.perf_counter() - t0
-    tw = torch.tensor([wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-    wall = float(tw.item())
-    clocks = sampler.stop() if rank == 0 else None
-    ldb = (dim + 63) // 64 * 64
-    flop = 2.0 * B * n * ldb
-    kernel_ms = kms / args.steps
-    # recall of the (merged) answer vs the exact scan of every shard, merged the same way
-    rq = min(64, B)
-    gi, gs, gc = exact_topk_device_full(hx, torch, ix, qsets[args.warmup + args.steps - 1][:rq], n, lo, k)
-    if world > 1:
-        p2 = torch.zeros((rq, 3 * k + 1), dtype=torch.int32, device=dev)
-        ap2 = torch.zeros((world, rq, 3 * k + 1), dtype=torch.int32, device=dev)
-        t_o = torch.zeros((rq, k), dtype=torch.int64, device=dev)
-        t_s = torch.zeros((rq, k), dtype=torch.float32, device=dev)
-        t_c = torch.zeros((rq,), dtype=torch.int32, device=dev)
-        truth = merge_across_ranks(gi, gs, gc, rq, p2, ap2, t_o, t_s, t_c)
-    else:
-        truth = gi
-    rec = recall_at_k(last[:rq], truth)
+    line = measure_dense(hx, torch, args, world, rank, local_rank, dev, stream, uid)
     if rank == 0:
-        line = {"metric": "queries/sec, exhaustive top-10 through the tensor cores (configs C4/C5 shape)",
-                "value": round(args.steps * B / wall, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(wall / args.steps * 1e3, 3), "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "bf16 (fp32 accumulate) + f32 exact re-rank",
-                "data": "synthetic", "recall_at_10": round(rec, 4),
-                "config": {"workload": f"dense: {B} queries x {n_total} rows x d={dim}, k={k}, host buffers (hx_search_dense)"
-                                       + (f", {world} id-range shards of {n} rows, 1 all-gather + merge" if world > 1 else ""),
-                           "recipe": args.recipe},
-                "roofline": {"bound": "tensor", "kernel": "k_dense_scores", "achieved": round(flop / (kernel_ms * 1e-3) / 1e12, 1),
-                             "peak": tf_peak, "unit": "TFLOP/s", "frac": round(flop / (kernel_ms * 1e-3) / 1e12 / tf_peak, 4),
-                             "traffic": ncu_traffic("k_dense_scores", {"queries": B, "rows": n, "dim": dim}), "flop_per_launch_per_gpu": flop,
-                             "kernel_ms_per_launch": round(kernel_ms, 4),
-                             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst); per GPU"},
-                "gpu_launches": args.steps * 7, "clocks": clocks}
+        line.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "data": "synthetic",
+                     "clocks": sampler.stop()})
         print(json.dumps(line), flush=True)
-    ix.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -889,9 +1204,9 @@ def run_reference(args):
         "value": round(value, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(total / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "recall_at_10": round(rec, 4),
-        "config": {"workload": f"C2: {n}x{dim} f32 {args.metric} HNSW top-10 (m=16, m0=32, ef_construction=200, ef={EF}), "
-                               f"one query per host thread, {per_step} queries per step (bounded sample of the {Q}-query step)",
-                   "graph": "built on the device (setup only), identical adjacency for both arms", "setup": setup},
+        "config": c2_config(args, 1, setup),
+        "sample": f"each step = {per_step} of the workload's {Q} queries per step (a bounded sample: throughput metric), one "
+                  f"query per host thread, {cores} threads; the graph both arms traverse is built on the device as untimed setup",
         "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} queries per step x {args.steps} steps, {cores} threads"},
         "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

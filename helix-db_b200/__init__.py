@@ -158,6 +158,8 @@ ABI_SYMBOLS = [
     "hx_candidates_destroy", "hx_candidates_len", "hx_search_restricted_sets",
     "hx_search_batch", "hx_device_flags", "hx_service_create", "hx_service_destroy", "hx_service_submit",
     "hx_service_poll", "hx_service_wait", "hx_service_search", "hx_service_get_stats",
+    "hx_shard_unique_id", "hx_shard_group_create", "hx_shard_group_destroy", "hx_search_sharded_device",
+    "hx_search_sharded", "hx_search_restricted_sharded", "hx_shard_group_last_ms",
 ]
 
 _lib = None
@@ -282,6 +284,20 @@ def load_library():
     L.hx_service_search.argtypes = [vp, fp, u64p, fp, u32p]
     L.hx_service_get_stats.restype = C.c_int32
     L.hx_service_get_stats.argtypes = [vp, C.POINTER(ServiceStats)]
+    L.hx_shard_unique_id.restype = C.c_int32
+    L.hx_shard_unique_id.argtypes = [u8p, sz]
+    L.hx_shard_group_create.restype = C.c_int32
+    L.hx_shard_group_create.argtypes = [vp, C.c_uint32, C.c_uint32, u8p, C.POINTER(vp)]
+    L.hx_shard_group_destroy.restype = None
+    L.hx_shard_group_destroy.argtypes = [vp]
+    L.hx_search_sharded_device.restype = C.c_int32
+    L.hx_search_sharded_device.argtypes = [vp, C.c_int32, vp, sz, C.POINTER(_Params), C.c_uint32, vp, vp, vp, vp]
+    L.hx_search_sharded.restype = C.c_int32
+    L.hx_search_sharded.argtypes = [vp, C.c_int32, fp, sz, C.POINTER(_Params), C.c_uint32, u64p, fp, u32p]
+    L.hx_search_restricted_sharded.restype = C.c_int32
+    L.hx_search_restricted_sharded.argtypes = [vp, fp, sz, C.POINTER(_Params), u64p, sz, u64p, fp, u32p]
+    L.hx_shard_group_last_ms.restype = C.c_int32
+    L.hx_shard_group_last_ms.argtypes = [vp, fp, fp]
     _lib = L
     return L
 

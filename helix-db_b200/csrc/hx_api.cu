@@ -2262,7 +2262,9 @@ extern "C" hx_status hx_merge_topk_device(int32_t device, const uint64_t* d_all_
   if (B == 0) return HX_OK;
   HX_CUDA(cudaSetDevice(device));
   k_merge_topk<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)cuda_stream>>>(
-      d_all_ids, d_all_scores, d_all_counts, n_shards, B, k, d_out_ids, d_out_scores, d_out_counts);
+      reinterpret_cast<const unsigned char*>(d_all_ids), reinterpret_cast<const unsigned char*>(d_all_scores),
+      reinterpret_cast<const unsigned char*>(d_all_counts), B * (size_t)k * 8, B * (size_t)k * 4, B * 4, n_shards, B, k, k,
+      d_out_ids, d_out_scores, d_out_counts);
   HX_CUDA(cudaGetLastError());
   return HX_OK;
 }

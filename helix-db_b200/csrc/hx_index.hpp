@@ -76,6 +76,16 @@ struct PinBuf {
   }
 };
 
+// dense path state cached across calls on one scratch set: encoded tensor maps, the shape they were built for
+struct HxDenseCache {
+  alignas(64) unsigned char map_q[128];
+  alignas(64) unsigned char map_x[128];
+  size_t B = 0;
+  uint32_t kprime = 0, ldb = 0;
+  const void* map_x_base = nullptr;
+  size_t map_x_rows = 0;
+};
+
 // One scratch set per in-flight host call (the handle is Send+Sync like the reference's index:
 // concurrent searches each take a private stream + buffers; SURVEY §8b "Threading").
 struct HxScratch {
@@ -99,6 +109,7 @@ struct HxScratch {
   DevBuf<uint64_t> d_qsim;             // query fingerprints
   bool prof_init = false;
   DevBuf<uint8_t> misc[16];   // dense path buffers (kept across calls)
+  HxDenseCache dense;
   DevBuf<uint8_t> d_block;    // small calls: results packed into one block -> one device-to-host copy
   PinBuf<uint8_t> h_block;
   size_t stamp_stride = 0;
@@ -206,3 +217,6 @@ bool hx_slot_of(const hx_index* ix, uint64_t id, uint32_t* slot);
 hx_status hx_build_impl(hx_index* ix, const uint16_t* levels, uint64_t seed);
 hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_search_params* p, uint64_t* out_ids,
                         float* out_scores, uint32_t* out_counts, hx_stats* stats);
+hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t B, const hx_search_params* p,
+                          uint64_t* d_out_ids, float* d_out_sc, uint32_t* d_out_cnt, cudaStream_t stream,
+                          cudaEvent_t e0, cudaEvent_t e1, uint32_t* launches_out);

@@ -396,8 +396,13 @@ static hx_status ensure_bf16(hx_index* ix, uint32_t ldb) {
   return HX_OK;
 }
 
-hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_search_params* p, uint64_t* out_ids,
-                        float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+// iota of the nominee CSR offsets (b * k')
+static __global__ void k_dense_offsets(uint64_t* __restrict__ offs, size_t B, uint32_t kprime) {
+  const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= B) offs[b] = b * (uint64_t)kprime;
+}
+
+static hx_status dense_check(hx_index* ix, const hx_search_params* p) {
   if (!p || p->k == 0) {
     hx_set_error("result count must be non-zero");
     return HX_ERR_INVALID_PARAMETER;
@@ -418,68 +423,76 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
     hx_set_error("invalid dimension: expected %u, got %u", ix->cfg.dimension, p->query_dimension);
     return HX_ERR_INVALID_DIMENSION;
   }
-  if (stats) memset(stats, 0, sizeof(*stats));
+  return HX_OK;
+}
+
+// Everything below is enqueued on `stream`; nothing synchronises with the host (buffers, tensor maps and the nominee
+// offsets are cached in the scratch set across calls).  d_queries: B x dim f32 on the device.  Per-query validation status
+// is left in s->d_qstatus (a query that fails validation yields count 0); error flags accumulate in s->d_err[0].
+hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t B, const hx_search_params* p,
+                          uint64_t* d_out_ids, float* d_out_sc, uint32_t* d_out_cnt, cudaStream_t stream,
+                          cudaEvent_t e0, cudaEvent_t e1, uint32_t* launches_out) {
+  hx_status rc = dense_check(ix, p);
+  if (rc) return rc;
   if (B == 0) return HX_OK;
-  if (!queries || !out_ids || !out_scores || !out_counts) return HX_ERR_INVALID_PARAMETER;
   if (ix->n == 0 || !ix->populated) {
-    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
+    HX_CUDA(cudaMemsetAsync(d_out_cnt, 0, B * sizeof(uint32_t), stream));
     return HX_OK;
   }
   const uint32_t dim = ix->cfg.dimension, k = p->k;
   const uint32_t ldb = (dim + HXD_BK - 1) / HXD_BK * HXD_BK;
-  hx_status rc = ensure_bf16(ix, ldb);
-  if (rc) return rc;
+  if ((rc = ensure_bf16(ix, ldb))) return rc;
   const size_t n = ix->n;
   const uint32_t m_tiles = (uint32_t)((B + HXD_BM - 1) / HXD_BM), n_tiles = (uint32_t)((n + HXD_BN - 1) / HXD_BN);
   const size_t B_pad = (size_t)m_tiles * HXD_BM, n_pad = (size_t)n_tiles * HXD_BN;
   const uint32_t kprime = (uint32_t)std::min<size_t>(std::max<uint32_t>(4 * k, 64), std::min<size_t>(800, n));
-
-  // ---- device buffers: kept in a pooled scratch set across calls ----
-  HxScratch* scr = nullptr;
-  if ((rc = hx_acquire_scratch(ix, &scr))) return rc;
-  struct Rel { hx_index* ix; HxScratch* s; ~Rel() { hx_release_scratch(ix, s); } } rel{ix, scr};
-  auto cleanup = [&]() {};
-#define HXD_CUDA(call)                                                                         \
-  do {                                                                                         \
-    cudaError_t _e = (call);                                                                   \
-    if (_e != cudaSuccess) {                                                                   \
-      hx_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
-      cleanup();                                                                               \
-      return _e == cudaErrorMemoryAllocation ? HX_ERR_OUT_OF_MEMORY : HX_ERR_CUDA;             \
-    }                                                                                          \
-  } while (0)
-  const size_t nkeys_calc_unused = 0;
-  (void)nkeys_calc_unused;
   // runs per m-tile: enough units to fill the SMs, and enough that one run's best-T comfortably covers its share of the
   // k' nominees even when the true neighbours cluster in id space (8x head-room)
   const uint32_t n_split = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_tiles,
       std::max<size_t>(std::max<size_t>(4, (size_t)ix->sm_count / m_tiles), (8 * (size_t)kprime + HXD_T - 1) / HXD_T)));
   const size_t nkeys = B * (size_t)n_split * 2 * HXD_T;
   int mi = 0;
+  bool grew = false;
   auto take = [&](size_t bytes, void** out) -> hx_status {
+    const unsigned char* before = scr->misc[mi].p;
     hx_status r = scr->misc[mi].reserve(bytes + 256);
+    if (scr->misc[mi].p != before) grew = true;
     *out = scr->misc[mi].p;
     ++mi;
     return r;
   };
-  float *d_q, *d_qaux, *d_sel_sc, *d_out_sc, *d_qhdr;
+  float *d_qaux, *d_sel_sc;
   __nv_bfloat16* d_qb;
-  uint64_t *d_keys, *d_sel_ids, *d_out_ids, *d_keys2, *d_coffs;
-  uint32_t *d_sel_cnt, *d_out_cnt, *d_status, *d_cslots, *d_err;
-  if ((rc = take(B * (size_t)dim * 4, (void**)&d_q)) || (rc = take(B * 4, (void**)&d_qhdr)) ||
-      (rc = take(B * 4, (void**)&d_status)) || (rc = take(B_pad * (size_t)ldb * 2, (void**)&d_qb)) ||
-      (rc = take(B_pad * 4, (void**)&d_qaux)) || (rc = take(nkeys * 8, (void**)&d_keys)) ||
-      (rc = take(B * (size_t)kprime * 8, (void**)&d_sel_ids)) || (rc = take(B * (size_t)kprime * 4, (void**)&d_sel_sc)) ||
-      (rc = take(B * 4, (void**)&d_sel_cnt)) || (rc = take(B * (size_t)kprime * 4, (void**)&d_cslots)) ||
-      (rc = take((B + 1) * 8, (void**)&d_coffs)) || (rc = take(B * (size_t)kprime * 8, (void**)&d_keys2)) ||
-      (rc = take(B * (size_t)k * 8, (void**)&d_out_ids)) || (rc = take(B * (size_t)k * 4, (void**)&d_out_sc)) ||
-      (rc = take(B * 4, (void**)&d_out_cnt)) || (rc = take(4, (void**)&d_err)))
+  uint64_t *d_keys, *d_sel_ids, *d_keys2, *d_coffs;
+  uint32_t *d_sel_cnt, *d_cslots;
+  if ((rc = take(B_pad * (size_t)ldb * 2, (void**)&d_qb)) || (rc = take(B_pad * 4, (void**)&d_qaux)) ||
+      (rc = take(nkeys * 8, (void**)&d_keys)) || (rc = take(B * (size_t)kprime * 8, (void**)&d_sel_ids)) ||
+      (rc = take(B * (size_t)kprime * 4, (void**)&d_sel_sc)) || (rc = take(B * 4, (void**)&d_sel_cnt)) ||
+      (rc = take(B * (size_t)kprime * 4, (void**)&d_cslots)) || (rc = take((B + 1) * 8, (void**)&d_coffs)) ||
+      (rc = take(B * (size_t)kprime * 8, (void**)&d_keys2)))
     return rc;
-  HXD_CUDA(cudaMemset(d_err, 0, 4));
-  HXD_CUDA(cudaMemset(d_sel_ids, 0xFF, B * (size_t)kprime * 8));   // unfilled nominee slots read as HX_ABSENT
-  HXD_CUDA(cudaMemset(d_qb, 0, B_pad * (size_t)ldb * 2));
-  HXD_CUDA(cudaMemset(d_qaux, 0, B_pad * 4));
-  HXD_CUDA(cudaMemcpy(d_q, queries, B * (size_t)dim * 4, cudaMemcpyHostToDevice));
+  if ((rc = scr->d_qhdr.reserve(B)) || (rc = scr->d_qstatus.reserve(B)) || (rc = scr->d_err.reserve(4))) return rc;
+  float* d_qhdr = scr->d_qhdr.p;
+  uint32_t* d_status = scr->d_qstatus.p;
+  uint32_t* d_err = scr->d_err.p;
+  HxDenseCache& dc = scr->dense;
+  const bool shape_changed = grew || dc.B != B || dc.kprime != kprime || dc.ldb != ldb;
+  HX_CUDA(cudaMemsetAsync(d_err, 0, 4, stream));
+  HX_CUDA(cudaMemsetAsync(d_sel_ids, 0xFF, B * (size_t)kprime * 8, stream));   // unfilled nominee slots read as HX_ABSENT
+  if (shape_changed) {   // pad rows / pad columns of the bf16 query tile and the nominee offsets: once per shape
+    HX_CUDA(cudaMemsetAsync(d_qb, 0, B_pad * (size_t)ldb * 2, stream));
+    HX_CUDA(cudaMemsetAsync(d_qaux, 0, B_pad * 4, stream));
+    k_dense_offsets<<<(unsigned)((B + 256) / 256), 256, 0, stream>>>(d_coffs, B, kprime);
+    if ((rc = make_map(reinterpret_cast<CUtensorMap*>(dc.map_q), d_qb, B_pad, ldb, HXD_BM))) return rc;
+    dc.B = B;
+    dc.kprime = kprime;
+    dc.ldb = ldb;
+  }
+  if (dc.map_x_base != ix->d_vec_bf16 || dc.map_x_rows != n_pad) {
+    if ((rc = make_map(reinterpret_cast<CUtensorMap*>(dc.map_x), ix->d_vec_bf16, n_pad, ldb, HXD_BN))) return rc;
+    dc.map_x_base = ix->d_vec_bf16;
+    dc.map_x_rows = n_pad;
+  }
   uint32_t launches = 0;
   // validation + exact headers (same order of checks as every other entry point)
   float limit = 0.f;
@@ -490,29 +503,12 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
     if ((double)limit > exact) limit = std::nextafter(limit, 0.0f);
     has_limit = true;
   }
-  k_validate_and_header<<<(unsigned)((B + 7) / 8), 256>>>(d_q, B, dim, dim, ix->cfg.metric, limit, has_limit ? 1 : 0, d_qhdr, d_status);
-  k_to_bf16<<<(unsigned)((B + 7) / 8), 256>>>(d_q, B, dim, dim, d_qb, ldb, d_qaux, ix->cfg.metric);
+  k_validate_and_header<<<(unsigned)((B + 7) / 8), 256, 0, stream>>>(d_q, B, dim, dim, ix->cfg.metric, limit, has_limit ? 1 : 0,
+                                                                    d_qhdr, d_status);
+  k_to_bf16<<<(unsigned)((B + 7) / 8), 256, 0, stream>>>(d_q, B, dim, dim, d_qb, ldb, d_qaux, ix->cfg.metric);
   launches += 2;
-  HXD_CUDA(cudaGetLastError());
-  {
-    std::vector<uint32_t> st(B);
-    HXD_CUDA(cudaMemcpy(st.data(), d_status, B * 4, cudaMemcpyDeviceToHost));
-    for (size_t b = 0; b < B; ++b)
-      if (st[b] != HX_ST_OK) {
-        cleanup();
-        const uint32_t code = st[b] >> 24;
-        hx_set_error_index(st[b] & 0xffffffu);
-        hx_set_error("query %zu failed validation (code %u)", b, code);
-        return code == HX_ST_COMPONENT ? HX_ERR_INVALID_VECTOR_COMPONENT
-                                       : (code == HX_ST_ZERO_NORM ? HX_ERR_ZERO_NORM_COSINE : HX_ERR_MAGNITUDE_EXCEEDED);
-      }
-  }
+  HX_CUDA(cudaGetLastError());
   // ---- tensor-core pass ----
-  CUtensorMap map_q, map_x;
-  if ((rc = make_map(&map_q, d_qb, B_pad, ldb, HXD_BM)) || (rc = make_map(&map_x, ix->d_vec_bf16, n_pad, ldb, HXD_BN))) {
-    cleanup();
-    return rc;
-  }
   HxDenseArgs a{};
   a.n_rows = (uint32_t)n;
   a.n_queries = (uint32_t)B;
@@ -524,24 +520,24 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   a.q_aux = d_qaux;
   a.keys = d_keys;
   a.metric = ix->cfg.metric;
-  a.debug = getenv("HX_DENSE_DEBUG") ? (uint32_t)atoi(getenv("HX_DENSE_DEBUG")) : 0u;
+  a.debug = 0u;
   const size_t smem = (size_t)HXD_STAGES * HXD_STAGE_BYTES + 16 * 8 + 16 + 2 * HXD_BN * 4 + (size_t)HXD_STAGE_CAP * HXD_EPI_THREADS * 8 + 1024;
-  HXD_CUDA(cudaFuncSetAttribute(k_dense_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::atomic<int> attr_set[64];
+  if (!attr_set[ix->device & 63].load()) {
+    HX_CUDA(cudaFuncSetAttribute(k_dense_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[ix->device & 63].store(1);
+  }
   const uint32_t grid = (uint32_t)std::min<size_t>((size_t)m_tiles * n_split, (size_t)ix->sm_count);
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  cudaEventRecord(e0, 0);
-  k_dense_scores<<<grid, HXD_THREADS, smem>>>(map_q, map_x, a);
-  cudaEventRecord(e1, 0);
+  if (e0) HX_CUDA(cudaEventRecord(e0, stream));
+  k_dense_scores<<<grid, HXD_THREADS, smem, stream>>>(*reinterpret_cast<CUtensorMap*>(dc.map_q),
+                                                      *reinterpret_cast<CUtensorMap*>(dc.map_x), a);
+  if (e1) HX_CUDA(cudaEventRecord(e1, stream));
   launches++;
-  HXD_CUDA(cudaGetLastError());
+  HX_CUDA(cudaGetLastError());
   // ---- k' nominees per query by approximate key, then the exact re-rank with the reference arithmetic ----
   HxDev dev = ix->dev();
   HxSelectArgs s1{};
   s1.keys = d_keys;
-  s1.cand_slots = nullptr;
-  s1.cand_offsets = nullptr;
   s1.q_status = d_status;
   s1.B = (uint32_t)B;
   s1.k = kprime;
@@ -550,14 +546,9 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   s1.out_ids = d_sel_ids;
   s1.out_scores = d_sel_sc;
   s1.out_counts = d_sel_cnt;
-  k_select<<<(unsigned)std::min<size_t>(B, 65535), HX_SEL_THREADS>>>(dev, s1);
-  k_keys_to_slots<<<(unsigned)((B * (size_t)kprime + 255) / 256), 256>>>(d_sel_ids, B * (size_t)kprime, d_cslots);
+  k_select<<<(unsigned)std::min<size_t>(B, 65535), HX_SEL_THREADS, 0, stream>>>(dev, s1);
+  k_keys_to_slots<<<(unsigned)((B * (size_t)kprime + 255) / 256), 256, 0, stream>>>(d_sel_ids, B * (size_t)kprime, d_cslots);
   launches += 2;
-  {
-    std::vector<uint64_t> offs(B + 1);
-    for (size_t b = 0; b <= B; ++b) offs[b] = b * (uint64_t)kprime;
-    HXD_CUDA(cudaMemcpy(d_coffs, offs.data(), (B + 1) * 8, cudaMemcpyHostToDevice));
-  }
   HxScanArgs sa{};
   sa.queries = d_q;
   sa.q_hdr = d_qhdr;
@@ -573,8 +564,8 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   {
     dim3 g(1, (unsigned)std::min<size_t>(B, 65535));
     const uint32_t sm = ix->ld * 4u;
-    if (ix->cfg.metric == HX_METRIC_COSINE) k_scan<HXM_COSINE><<<g, HX_SCAN_THREADS, sm>>>(dev, sa);
-    else k_scan<HXM_EUCLIDEAN><<<g, HX_SCAN_THREADS, sm>>>(dev, sa);
+    if (ix->cfg.metric == HX_METRIC_COSINE) k_scan<HXM_COSINE><<<g, HX_SCAN_THREADS, sm, stream>>>(dev, sa);
+    else k_scan<HXM_EUCLIDEAN><<<g, HX_SCAN_THREADS, sm, stream>>>(dev, sa);
   }
   HxSelectArgs s2{};
   s2.keys = d_keys2;
@@ -588,25 +579,69 @@ hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_s
   s2.out_ids = d_out_ids;
   s2.out_scores = d_out_sc;
   s2.out_counts = d_out_cnt;
-  k_select<<<(unsigned)std::min<size_t>(B, 65535), HX_SEL_THREADS>>>(dev, s2);
+  k_select<<<(unsigned)std::min<size_t>(B, 65535), HX_SEL_THREADS, 0, stream>>>(dev, s2);
   launches += 2;
-  HXD_CUDA(cudaGetLastError());
-  HXD_CUDA(cudaMemcpy(out_ids, d_out_ids, B * (size_t)k * 8, cudaMemcpyDeviceToHost));
-  HXD_CUDA(cudaMemcpy(out_scores, d_out_sc, B * (size_t)k * 4, cudaMemcpyDeviceToHost));
-  HXD_CUDA(cudaMemcpy(out_counts, d_out_cnt, B * 4, cudaMemcpyDeviceToHost));
+  HX_CUDA(cudaGetLastError());
+  if (launches_out) *launches_out = launches;
+  return HX_OK;
+}
+
+// Host-buffer entry point: a private stream + scratch set per call, the queries cross PCIe with one async copy, results
+// and per-query status come back with four, ONE stream synchronisation.
+hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_search_params* p, uint64_t* out_ids,
+                        float* out_scores, uint32_t* out_counts, hx_stats* stats) {
+  hx_status rc = dense_check(ix, p);
+  if (rc) return rc;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return HX_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts) return HX_ERR_INVALID_PARAMETER;
+  if (ix->n == 0 || !ix->populated) {
+    for (size_t b = 0; b < B; ++b) out_counts[b] = 0;
+    return HX_OK;
+  }
+  const uint32_t dim = ix->cfg.dimension, k = p->k;
+  HxScratch* scr = nullptr;
+  if ((rc = hx_acquire_scratch(ix, &scr))) return rc;
+  struct Rel { hx_index* ix; HxScratch* s; ~Rel() { hx_release_scratch(ix, s); } } rel{ix, scr};
+  if ((rc = scr->d_queries.reserve(B * (size_t)dim)) || (rc = scr->d_out_ids.reserve(B * (size_t)k)) ||
+      (rc = scr->d_out_scores.reserve(B * (size_t)k)) || (rc = scr->d_out_counts.reserve(B)) ||
+      (rc = scr->h_status.reserve(B)) || (rc = scr->h_err.reserve(1)))
+    return rc;
+  cudaStream_t st = scr->stream;
+  HX_CUDA(cudaMemcpyAsync(scr->d_queries.p, queries, B * (size_t)dim * 4, cudaMemcpyHostToDevice, st));
+  uint32_t launches = 0;
+  if ((rc = hx_dense_device(ix, scr, scr->d_queries.p, B, p, scr->d_out_ids.p, scr->d_out_scores.p, scr->d_out_counts.p, st,
+                            scr->ev0, scr->ev1, &launches)))
+    return rc;
+  HX_CUDA(cudaMemcpyAsync(out_ids, scr->d_out_ids.p, B * (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+  HX_CUDA(cudaMemcpyAsync(out_scores, scr->d_out_scores.p, B * (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+  HX_CUDA(cudaMemcpyAsync(out_counts, scr->d_out_counts.p, B * 4, cudaMemcpyDeviceToHost, st));
+  HX_CUDA(cudaMemcpyAsync(scr->h_status.p, scr->d_qstatus.p, B * 4, cudaMemcpyDeviceToHost, st));
+  HX_CUDA(cudaMemcpyAsync(scr->h_err.p, scr->d_err.p, 4, cudaMemcpyDeviceToHost, st));
+  HX_CUDA(cudaStreamSynchronize(st));
+  for (size_t b = 0; b < B; ++b)
+    if (scr->h_status.p[b] != HX_ST_OK) {
+      const uint32_t w = scr->h_status.p[b], code = w >> 24;
+      hx_set_error_index(w & 0xffffffu);
+      hx_set_error("query %zu failed validation (code %u)", b, code);
+      return code == HX_ST_COMPONENT ? HX_ERR_INVALID_VECTOR_COMPONENT
+                                     : (code == HX_ST_ZERO_NORM ? HX_ERR_ZERO_NORM_COSINE : HX_ERR_MAGNITUDE_EXCEEDED);
+    }
+  if (scr->h_err.p[0] & HXF_INVALID_SCORE) {
+    hx_set_error("vector distance kernel emitted an invalid score");
+    return HX_ERR_INVARIANT_VIOLATION;
+  }
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) {
+  if (cudaEventElapsedTime(&ms, scr->ev0, scr->ev1) == cudaSuccess) {
     ix->last_kernel_ms = ms;
     ix->last_kernel_launches = 1;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (stats) {
+    const uint32_t ldb = (dim + HXD_BK - 1) / HXD_BK * HXD_BK;
     stats->kernel_launches = launches;
-    stats->distance_computations = (uint64_t)B * n;
-    stats->algorithmic_bytes = (uint64_t)n * ldb * 2;   // corpus streamed once; the bound is the tensor pipe: 2*B*N*d flop
-    stats->reserved = (uint64_t)(2.0 * (double)B * (double)n * (double)ldb);   // flop of the contraction
+    stats->distance_computations = (uint64_t)B * ix->n;
+    stats->algorithmic_bytes = (uint64_t)ix->n * ldb * 2;   // corpus streamed once; the bound is the tensor pipe: 2*B*N*d flop
+    stats->reserved = (uint64_t)(2.0 * (double)B * (double)ix->n * (double)ldb);   // flop of the contraction
   }
-  cleanup();
   return HX_OK;
 }

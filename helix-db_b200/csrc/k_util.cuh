@@ -140,8 +140,11 @@ static __global__ void k_iota_ids(uint64_t* ids, size_t n, uint64_t first) {
 }
 
 // ---- merge of per-shard top-k lists: one warp per query, lane s walks shard s's sorted list -------
-static __global__ void k_merge_topk(const uint64_t* __restrict__ all_ids, const float* __restrict__ all_scores,
-                             const uint32_t* __restrict__ all_counts, uint32_t n_shards, size_t B, uint32_t k,
+// Per-shard lists live at base + s * stride (BYTE strides: the gathered blocks of the sharded path are one block per
+// shard, not one array per field); every list holds k_in entries per query, the merge emits k_out.
+static __global__ void k_merge_topk(const unsigned char* __restrict__ all_ids, const unsigned char* __restrict__ all_scores,
+                             const unsigned char* __restrict__ all_counts, size_t stride_ids, size_t stride_scores,
+                             size_t stride_counts, uint32_t n_shards, size_t B, uint32_t k_in, uint32_t k_out,
                              uint64_t* __restrict__ out_ids, float* __restrict__ out_scores,
                              uint32_t* __restrict__ out_counts) {
   const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -154,9 +157,12 @@ static __global__ void k_merge_topk(const uint64_t* __restrict__ all_ids, const 
   uint32_t cnt[4] = {0, 0, 0, 0};
   for (int j = 0; j < 4; ++j) {
     const uint32_t s = lane + 32u * (uint32_t)j;
-    if (s < n_shards) cnt[j] = all_counts[(size_t)s * B + q];
+    if (s < n_shards) {
+      const uint32_t c = reinterpret_cast<const uint32_t*>(all_counts + (size_t)s * stride_counts)[q];
+      cnt[j] = c < k_in ? c : k_in;
+    }
   }
-  while (out_n < k) {
+  while (out_n < k_out) {
     // best head among this lane's shards by (score, id)
     uint32_t bs = 0x7f800000u + 1u;   // larger than any finite score's bits
     uint64_t bid = ~0ull;
@@ -164,9 +170,9 @@ static __global__ void k_merge_topk(const uint64_t* __restrict__ all_ids, const 
     for (int j = 0; j < 4; ++j) {
       const uint32_t s = lane + 32u * (uint32_t)j;
       if (s < n_shards && cur[j] < cnt[j]) {
-        const size_t o = ((size_t)s * B + q) * k + cur[j];
-        const uint32_t sb = __float_as_uint(all_scores[o]);
-        const uint64_t id = all_ids[o];
+        const size_t o = q * k_in + cur[j];
+        const uint32_t sb = __float_as_uint(reinterpret_cast<const float*>(all_scores + (size_t)s * stride_scores)[o]);
+        const uint64_t id = reinterpret_cast<const uint64_t*>(all_ids + (size_t)s * stride_ids)[o];
         if (sb < bs || (sb == bs && id < bid)) { bs = sb; bid = id; bj = j; }
       }
     }
@@ -182,8 +188,8 @@ static __global__ void k_merge_topk(const uint64_t* __restrict__ all_ids, const 
     if (ms > 0x7f800000u) break;   // every list exhausted
     if (lane == ml && bj >= 0) cur[bj]++;
     if (lane == 0) {
-      out_ids[q * k + out_n] = mid;
-      out_scores[q * k + out_n] = __uint_as_float(ms);
+      out_ids[q * k_out + out_n] = mid;
+      out_scores[q * k_out + out_n] = __uint_as_float(ms);
     }
     out_n++;
   }

@@ -370,6 +370,40 @@ hx_status hx_merge_topk_device(int32_t device, const uint64_t* d_all_ids, const 
                                uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts,
                                void* cuda_stream);
 
+/* ---- sharded search: id-range shards, one rank per device, ONE all-gather -----------------
+ * Each rank holds an hx_index with a contiguous id range of the corpus (hx_index_generate_vectors / load_* with
+ * that range's ids, its own graph from hx_index_build or hx_index_load_graph).  A group binds the ranks with one NCCL
+ * communicator (NCCL is dlopen'ed on first use; a group of 1 never touches it).  A sharded search = local search on the
+ * shard, whose kernels write ids | scores | counts straight into this rank's send block -> ONE ncclAllGather of
+ * the blocks -> the (score, id) merge kernel on every rank.  Every rank passes the SAME queries and receives the same
+ * merged answer.  `local` holds the PER-SHARD parameters: local->k results are kept per shard (>= k_out is exact;
+ * smaller trades recall for traffic) and local->ef is the per-shard beam width — a shard is 1/n_shards of the corpus, so
+ * the beam that gives the unsharded index its recall is over-provisioned per shard; bench.py tunes it to iso-recall.
+ * Ranks may be processes (torchrun: rank 0 calls hx_shard_unique_id and ships the 128 bytes through the host's own
+ * channel) or threads of one process, one per device.  Collective: every rank must make the same sequence of calls. */
+typedef struct hx_shard_group hx_shard_group;
+enum { HX_SHARD_HNSW = 0 /* hx_search_device on the shard */, HX_SHARD_DENSE = 1 /* tensor-core exhaustive path */ };
+#define HX_SHARD_UNIQUE_ID_BYTES 128
+hx_status hx_shard_unique_id(uint8_t* out, size_t cap /* >= HX_SHARD_UNIQUE_ID_BYTES */);
+hx_status hx_shard_group_create(hx_index* shard, uint32_t n_shards, uint32_t rank, const uint8_t* unique_id,
+                                hx_shard_group** out);
+void      hx_shard_group_destroy(hx_shard_group* g);
+/* device buffers, everything enqueued on cuda_stream (no host synchronisation) */
+hx_status hx_search_sharded_device(hx_shard_group* g, int32_t path, const float* d_queries, size_t B,
+                                   const hx_search_params* local, uint32_t k_out, uint64_t* d_out_ids,
+                                   float* d_out_scores, uint32_t* d_out_counts, void* cuda_stream);
+/* host buffers (blocking) */
+hx_status hx_search_sharded(hx_shard_group* g, int32_t path, const float* queries, size_t B,
+                            const hx_search_params* local, uint32_t k_out, uint64_t* out_ids, float* out_scores,
+                            uint32_t* out_counts);
+/* restricted search across shards: every rank passes the same ascending candidate list; a shard scores the slice inside
+ * its id range (an empty slice = RestrictedVectorCandidates::Empty for that shard); exact for any number of shards */
+hx_status hx_search_restricted_sharded(hx_shard_group* g, const float* queries, size_t B, const hx_search_params* p,
+                                       const uint64_t* cand_ids, size_t n_cand, uint64_t* out_ids, float* out_scores,
+                                       uint32_t* out_counts);
+/* device time of the last host-buffer sharded call: local search, and all-gather + merge */
+hx_status hx_shard_group_last_ms(hx_shard_group* g, float* local_ms, float* collective_ms);
+
 /* ---- dense batched path (tensor cores; configs C4/C5) ---------------------------------- */
 /* Exhaustive top-k of B queries against all rows through the bf16 copy:
  * tcgen05 MMA for the B x N contraction, per-tile candidate filter, fp32 re-rank of

@@ -1,5 +1,6 @@
-"""N > 1 host logic on CPU: world_size = 2 over gloo (no GPU).  Checks the id-range split, the bit-preserving packing
-of the single all-gather, and that merging per-shard top-k by (score, id) reproduces the unsharded exact answer."""
+"""N > 1 host logic on CPU: world_size = 2 over gloo (no GPU).  Checks the id-range split, the byte-block wire format of
+the single all-gather, the unique-id exchange, and that merging per-shard top-k by (score, id) reproduces the unsharded
+exact answer."""
 import os
 import socket
 import sys
@@ -20,26 +21,6 @@ def _free_port():
     p = s.getsockname()[1]
     s.close()
     return p
-
-
-def _merge_reference(a_ids, a_sc, a_cnt, k):
-    """numpy statement of hx_merge_topk_device (test-side checker only)."""
-    S, Q, _ = a_ids.shape
-    out_ids = np.zeros((Q, k), dtype=np.uint64)
-    out_sc = np.zeros((Q, k), dtype=np.float32)
-    out_cnt = np.zeros(Q, dtype=np.int32)
-    for q in range(Q):
-        items = []
-        for s in range(S):
-            for j in range(int(a_cnt[s, q])):
-                items.append((np.float32(a_sc[s, q, j]).view(np.uint32).item(), int(a_ids[s, q, j])))
-        items.sort()
-        items = items[:k]
-        out_cnt[q] = len(items)
-        for j, (sb, i) in enumerate(items):
-            out_ids[q, j] = i
-            out_sc[q, j] = np.uint32(sb).view(np.float32)
-    return out_ids, out_sc, out_cnt
 
 
 def _worker(rank, world, port, ret):
@@ -69,23 +50,40 @@ def _worker(rank, world, port, ret):
     for q in range(Q):
         i, s = ora.search_exact(queries[q], k)
         l_ids[q, :len(i)], l_sc[q, :len(i)], l_cnt[q] = i, s, len(i)
-    l_ids[0, 0] = (1 << 63) + 12345 + rank                 # ids above 2^63 must survive the int32 packing
-    pack = sh.pack_topk(torch.from_numpy(l_ids.view(np.int64)), torch.from_numpy(l_sc), torch.from_numpy(l_cnt))
-    assert pack.shape == (Q, 3 * k + 1) and pack.dtype == torch.int32
-    apack = sh.all_gather_topk(pack, world)                 # the ONE collective
-    a_ids, a_sc, a_cnt = sh.unpack_topk(apack, k)
-    a_ids_n = a_ids.numpy().view(np.uint64)
-    assert a_ids_n[rank].tolist() == l_ids.tolist()         # round trip is bit exact
-    assert a_sc.numpy()[rank].tobytes() == l_sc.tobytes() and a_cnt.numpy()[rank].tolist() == l_cnt.tolist()
-    assert a_ids_n[0, 0, 0] == (1 << 63) + 12345 and a_ids_n[world - 1, 0, 0] == (1 << 63) + 12345 + world - 1
+    l_ids[0, 0] = (1 << 63) + 12345 + rank                 # ids above 2^63 must survive the byte blocks
+    # the wire format of the sharded path: one uint8 block per rank (ids | scores | counts), gathered by ONE collective
+    lay = sh.block_layout(Q, k)
+    block = np.zeros(lay["bytes"], dtype=np.uint8)
+    b_ids, b_sc, b_cnt = sh.block_views(block, Q, k)
+    b_ids[:], b_sc[:], b_cnt[:] = l_ids, l_sc, l_cnt.astype(np.uint32)
+    gathered = torch.zeros((world, lay["bytes"]), dtype=torch.uint8)
+    dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(block))          # the ONE collective
+    blocks = [gathered[r].numpy().copy() for r in range(world)]
+    r_ids, r_sc, r_cnt = sh.block_views(blocks[rank], Q, k)
+    assert r_ids.tolist() == l_ids.tolist() and r_sc.tobytes() == l_sc.tobytes() and r_cnt.tolist() == l_cnt.tolist()
+    assert sh.block_views(blocks[0], Q, k)[0][0, 0] == (1 << 63) + 12345
+    assert sh.block_views(blocks[world - 1], Q, k)[0][0, 0] == (1 << 63) + 12345 + world - 1
+    # the communicator's unique id travels from rank 0 to every rank through the host's channel (here: gloo broadcast)
+    uid = sh.exchange_unique_id(rank, make_id=lambda: bytes(range(128)))
+    assert uid == bytes(range(128))
     # restore the sentinel and compare the merge with the unsharded exact answer
     for r in range(world):
         rlo, rhi = sh.shard_range(n, world, r)
         o = hxo.Index(hxo.EUCLIDEAN, dim)
         o.put_vectors(ids[rlo:rhi], rows[rlo:rhi])
         o.set_entry(int(ids[rlo]), 0)
-        a_ids_n[r, 0, 0] = o.search_exact(queries[0], k)[0][0]
-    m_ids, m_sc, m_cnt = _merge_reference(a_ids_n, a_sc.numpy(), a_cnt.numpy(), k)
+        sh.block_views(blocks[r], Q, k)[0][0, 0] = o.search_exact(queries[0], k)[0][0]
+    m_ids, m_sc, m_cnt = sh.merge_blocks_reference(blocks, Q, k, k)
+    # a per-shard k smaller than k_out still merges (blocks built with 3 entries per query: fewer nominees per shard)
+    small = []
+    for r in range(world):
+        bi, bs, bc = sh.block_views(blocks[r], Q, k)
+        sb = np.zeros(sh.block_layout(Q, 3)["bytes"], dtype=np.uint8)
+        si, ss, scn = sh.block_views(sb, Q, 3)
+        si[:], ss[:], scn[:] = bi[:, :3], bs[:, :3], np.minimum(bc, 3)
+        small.append(sb)
+    t_ids, _, t_cnt = sh.merge_blocks_reference(small, Q, 3, k)
+    assert all(int(c) <= 3 * world for c in t_cnt) and t_ids[1, 0] == m_ids[1, 0]
     full = hxo.Index(hxo.EUCLIDEAN, dim)
     full.put_vectors(ids, rows)
     full.set_entry(int(ids[0]), 0)

@@ -160,6 +160,8 @@ ABI_SYMBOLS = [
     "hx_service_poll", "hx_service_wait", "hx_service_search", "hx_service_get_stats",
     "hx_shard_unique_id", "hx_shard_group_create", "hx_shard_group_destroy", "hx_search_sharded_device",
     "hx_search_sharded", "hx_search_restricted_sharded", "hx_shard_group_last_ms",
+    "hx_index_upsert_vectors", "hx_index_set_levels", "hx_index_upsert_neighbor_rows", "hx_index_delete_vectors",
+    "hx_index_load_upper_vector_rows", "hx_index_set_version", "hx_index_get_version",
 ]
 
 _lib = None
@@ -284,6 +286,20 @@ def load_library():
     L.hx_service_search.argtypes = [vp, fp, u64p, fp, u32p]
     L.hx_service_get_stats.restype = C.c_int32
     L.hx_service_get_stats.argtypes = [vp, C.POINTER(ServiceStats)]
+    L.hx_index_upsert_vectors.restype = C.c_int32
+    L.hx_index_upsert_vectors.argtypes = [vp, u64p, fp, sz]
+    L.hx_index_set_levels.restype = C.c_int32
+    L.hx_index_set_levels.argtypes = [vp, u64p, u16p, sz]
+    L.hx_index_upsert_neighbor_rows.restype = C.c_int32
+    L.hx_index_upsert_neighbor_rows.argtypes = [vp, C.c_uint16, u64p, u32p, u64p, sz]
+    L.hx_index_delete_vectors.restype = C.c_int32
+    L.hx_index_delete_vectors.argtypes = [vp, u64p, sz]
+    L.hx_index_load_upper_vector_rows.restype = C.c_int32
+    L.hx_index_load_upper_vector_rows.argtypes = [vp, u64p, u8p, sz]
+    L.hx_index_set_version.restype = C.c_int32
+    L.hx_index_set_version.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.hx_index_get_version.restype = C.c_int32
+    L.hx_index_get_version.argtypes = [vp, u64p, u64p, u64p]
     L.hx_shard_unique_id.restype = C.c_int32
     L.hx_shard_unique_id.argtypes = [u8p, sz]
     L.hx_shard_group_create.restype = C.c_int32
@@ -625,6 +641,45 @@ class VectorIndex:
         gi.update(levels=levels[:n], deg0=deg0[:n], nbr0=nbr0[:n * s0], upper_node=un[:rows], upper_layer=ul[:rows],
                   upper_deg=ud[:rows], upper_nbr=unb[:rows * su])
         return gi
+
+    # ---- incremental maintenance: a committed write arrives as row patches + a new version token ----
+    def upsert_vectors(self, ids, rows):
+        ia, ip = _u64(ids)
+        ra, rp = _f32(rows)
+        if ra.size != ia.size * self.dim:
+            raise HelixDbError(HX_ERR_INVALID_DIMENSION, f"expected {ia.size}x{self.dim} floats, got {ra.size}")
+        _ck(self.L.hx_index_upsert_vectors(self.h, ip, rp, ia.size))
+
+    def set_levels(self, ids, levels):
+        ia, ip = _u64(ids)
+        la = np.ascontiguousarray(levels, dtype=np.uint16)
+        _ck(self.L.hx_index_set_levels(self.h, ip, la.ctypes.data_as(C.POINTER(C.c_uint16)), ia.size))
+
+    def upsert_neighbor_rows(self, layer, node_ids, offsets, neighbors):
+        na, np_ = _u64(node_ids)
+        oa, op = _u32(offsets)
+        nb, nbp = _u64(neighbors)
+        _ck(self.L.hx_index_upsert_neighbor_rows(self.h, layer, np_, op, nbp, na.size))
+
+    def delete_vectors(self, ids):
+        ia, ip = _u64(ids)
+        _ck(self.L.hx_index_delete_vectors(self.h, ip, ia.size))
+
+    def load_upper_vector_rows(self, ids, rows: bytes):
+        """`[0x13]` hot-lane item rows (`[header f32][f32 x dim]` each)."""
+        ia, ip = _u64(ids)
+        if len(rows) != ia.size * (4 + 4 * self.dim):
+            raise HelixDbError(HX_ERR_INVARIANT_VIOLATION, "item rows must be 4+4*dimension bytes each")
+        buf = (C.c_uint8 * max(len(rows), 1)).from_buffer_copy(rows if rows else b"\0")
+        _ck(self.L.hx_index_load_upper_vector_rows(self.h, ip, buf, ia.size))
+
+    def set_version(self, generation: int, visible_seq: int):
+        _ck(self.L.hx_index_set_version(self.h, generation, visible_seq))
+
+    def version(self):
+        g, v, p = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _ck(self.L.hx_index_get_version(self.h, C.byref(g), C.byref(v), C.byref(p)))
+        return int(g.value), int(v.value), int(p.value)
 
     # ---- SimHash policy state (production-default mode) ----
     def set_simhash_config(self, threshold=43, sampling_ratio=0.8, adaptive_enabled=True, adaptive_failure_prob=0.1):

@@ -169,6 +169,11 @@ void hx_index::free_vectors() {
   if (d_has_simhash) cudaFree(d_has_simhash);
   d_simhash = nullptr; d_has_simhash = nullptr; simhash_count = 0;
   d_vec = nullptr; d_hdr = nullptr; d_ids = nullptr; d_vec_bf16 = nullptr; d_sqnorm = nullptr;
+  if (d_deleted) cudaFree(d_deleted);
+  d_deleted = nullptr;
+  host_deleted.clear();
+  n_deleted = 0;
+  cap_rows = 0;
   n = 0;
   ids_sorted.clear();
 }
@@ -184,6 +189,7 @@ void hx_index::free_graph() {
   d_nbr0 = nullptr; d_deg0 = nullptr; d_raw0 = nullptr; d_upper_off = nullptr;
   d_upper_nbr = nullptr; d_upper_deg = nullptr; d_level = nullptr;
   stride0 = 0; stride_u = 0; n_upper_rows = 0;
+  cap_upper = 0;
   staged.clear();
   graph_dirty = false;
   populated = false;
@@ -289,14 +295,17 @@ struct ScratchGuard {
 
 bool hx_slot_of(const hx_index* ix, uint64_t id, uint32_t* slot) {
   if (ix->n == 0) return false;
+  uint32_t s;
   if (ix->contiguous) {
     if (id < ix->first_id || id - ix->first_id >= ix->n) return false;
-    *slot = (uint32_t)(id - ix->first_id);
-    return true;
+    s = (uint32_t)(id - ix->first_id);
+  } else {
+    auto it = std::lower_bound(ix->ids_sorted.begin(), ix->ids_sorted.end(), id);
+    if (it == ix->ids_sorted.end() || *it != id) return false;
+    s = (uint32_t)(it - ix->ids_sorted.begin());
   }
-  auto it = std::lower_bound(ix->ids_sorted.begin(), ix->ids_sorted.end(), id);
-  if (it == ix->ids_sorted.end() || *it != id) return false;
-  *slot = (uint32_t)(it - ix->ids_sorted.begin());
+  if (!ix->host_deleted.empty() && ix->host_deleted[s]) return false;   // deleted by hx_index_delete_vectors
+  *slot = s;
   return true;
 }
 
@@ -931,13 +940,20 @@ hx_status hx_finalize_graph(hx_index* ix) {
       upper_deg[r] = (uint16_t)(e - b);
     }
   }
-  HX_CUDA(cudaMalloc((void**)&ix->d_nbr0, nbr0.size() * sizeof(uint32_t)));
-  HX_CUDA(cudaMalloc((void**)&ix->d_deg0, n * sizeof(uint16_t)));
-  HX_CUDA(cudaMalloc((void**)&ix->d_raw0, n * sizeof(uint16_t)));
-  HX_CUDA(cudaMalloc((void**)&ix->d_upper_off, n * sizeof(uint32_t)));
+  const size_t rcap = std::max(ix->cap_rows, n);   // per-row arrays follow the vector arrays' capacity (hx_mirror.inl)
+  HX_CUDA(cudaMalloc((void**)&ix->d_nbr0, rcap * (size_t)ix->stride0 * sizeof(uint32_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_deg0, rcap * sizeof(uint16_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_raw0, rcap * sizeof(uint16_t)));
+  HX_CUDA(cudaMalloc((void**)&ix->d_upper_off, rcap * sizeof(uint32_t)));
   HX_CUDA(cudaMalloc((void**)&ix->d_upper_nbr, upper_nbr.size() * sizeof(uint32_t)));
   HX_CUDA(cudaMalloc((void**)&ix->d_upper_deg, upper_deg.size() * sizeof(uint16_t)));
-  HX_CUDA(cudaMalloc((void**)&ix->d_level, n));
+  HX_CUDA(cudaMalloc((void**)&ix->d_level, rcap));
+  if (rcap > n) {
+    HX_CUDA(cudaMemset(ix->d_deg0, 0, rcap * sizeof(uint16_t)));
+    HX_CUDA(cudaMemset(ix->d_raw0, 0, rcap * sizeof(uint16_t)));
+    HX_CUDA(cudaMemset(ix->d_upper_off, 0xFF, rcap * sizeof(uint32_t)));
+    HX_CUDA(cudaMemset(ix->d_level, 0, rcap));
+  }
   HX_CUDA(cudaMemcpy(ix->d_nbr0, nbr0.data(), nbr0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   HX_CUDA(cudaMemcpy(ix->d_deg0, deg0.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
   HX_CUDA(cudaMemcpy(ix->d_raw0, raw0.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
@@ -1995,7 +2011,7 @@ static hx_status restricted_host(hx_index* ix, const float* queries, size_t B, c
                             cudaMemcpyHostToDevice, s->stream));
   }
   k_map_candidates<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(
-      ix->d_ids, (uint32_t)ix->n, s->d_cand_ids.p, total, s->d_cand_slots.p, ix->contiguous ? 1 : 0, ix->first_id);
+      ix->d_ids, (uint32_t)ix->n, s->d_cand_ids.p, total, s->d_cand_slots.p, ix->contiguous ? 1 : 0, ix->first_id, ix->d_deleted);
   HX_CUDA(cudaGetLastError());
   launches++;
   if ((rc = s->d_out_ids.reserve(B * (size_t)k))) return rc;
@@ -2081,7 +2097,7 @@ extern "C" hx_status hx_candidates_create(hx_index* ix, const uint64_t* cand_ids
     if (e == cudaSuccess) e = cudaMemcpy(d_ids, cand_ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
       k_map_candidates<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_ids, (uint32_t)ix->n, d_ids, n, c->d_slots,
-                                                             ix->contiguous ? 1 : 0, ix->first_id);
+                                                             ix->contiguous ? 1 : 0, ix->first_id, ix->d_deleted);
       e = cudaDeviceSynchronize();
     }
     if (d_ids) cudaFree(d_ids);
@@ -2203,7 +2219,7 @@ extern "C" hx_status hx_map_candidates_device(hx_index* ix, const uint64_t* d_ca
   if (n == 0) return HX_OK;
   HX_CUDA(cudaSetDevice(ix->device));
   k_map_candidates<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-      ix->d_ids, (uint32_t)ix->n, d_cand_ids, n, d_out_slots, ix->contiguous ? 1 : 0, ix->first_id);
+      ix->d_ids, (uint32_t)ix->n, d_cand_ids, n, d_out_slots, ix->contiguous ? 1 : 0, ix->first_id, ix->d_deleted);
   HX_CUDA(cudaGetLastError());
   (void)d_out_count;
   return HX_OK;
@@ -2319,10 +2335,11 @@ static hx_status ensure_simhash_arrays(hx_index* ix) {
     return HX_ERR_INVALID_PARAMETER;
   }
   if (!ix->d_simhash) {
-    HX_CUDA(cudaMalloc((void**)&ix->d_simhash, ix->n * sizeof(uint64_t)));
-    HX_CUDA(cudaMalloc((void**)&ix->d_has_simhash, ix->n));
-    HX_CUDA(cudaMemset(ix->d_simhash, 0, ix->n * sizeof(uint64_t)));
-    HX_CUDA(cudaMemset(ix->d_has_simhash, 0, ix->n));
+    const size_t rcap = std::max(ix->cap_rows, ix->n);
+    HX_CUDA(cudaMalloc((void**)&ix->d_simhash, rcap * sizeof(uint64_t)));
+    HX_CUDA(cudaMalloc((void**)&ix->d_has_simhash, rcap));
+    HX_CUDA(cudaMemset(ix->d_simhash, 0, rcap * sizeof(uint64_t)));
+    HX_CUDA(cudaMemset(ix->d_has_simhash, 0, rcap));
     ix->simhash_count = 0;
   }
   return HX_OK;
@@ -2723,3 +2740,4 @@ extern "C" hx_status hx_last_kernel_ms(hx_index* ix, float* ms, uint32_t* launch
 }
 
 #include "hx_service.inl"
+#include "hx_mirror.inl"

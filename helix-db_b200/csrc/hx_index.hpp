@@ -145,6 +145,13 @@ struct hx_index {
   bool contiguous = false;
   uint64_t first_id = 0;
   uint64_t vector_generation = 0;     // bumped whenever the slot numbering changes (hx_candidates are tied to it)
+  // incremental maintenance (hx_mirror.inl): allocated capacity of the per-row / upper-row arrays (0 = exactly n / rows),
+  // tombstones of deleted nodes
+  size_t cap_rows = 0, cap_upper = 0;
+  uint8_t* d_deleted = nullptr;
+  std::vector<uint8_t> host_deleted;
+  size_t n_deleted = 0;
+  std::atomic<uint64_t> mirror_patches{0};
   float* d_vec = nullptr;
   float* d_hdr = nullptr;
   uint64_t* d_ids = nullptr;

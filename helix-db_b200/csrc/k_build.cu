@@ -616,13 +616,20 @@ hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed) 
   ix->stride_u = (m + 15) / 16 * 16;
   ix->n_upper_rows = rows;
   hx_status rc;
-  if ((rc = dalloc(&ix->d_nbr0, n * (size_t)ix->stride0))) return rc;
-  if ((rc = dalloc(&ix->d_deg0, n))) return rc;
-  if ((rc = dalloc(&ix->d_raw0, n))) return rc;
-  if ((rc = dalloc(&ix->d_upper_off, n))) return rc;
+  const size_t rcap = std::max(ix->cap_rows, n);   // per-row arrays follow the vector arrays' capacity (hx_mirror.inl)
+  if ((rc = dalloc(&ix->d_nbr0, rcap * (size_t)ix->stride0))) return rc;
+  if ((rc = dalloc(&ix->d_deg0, rcap))) return rc;
+  if ((rc = dalloc(&ix->d_raw0, rcap))) return rc;
+  if ((rc = dalloc(&ix->d_upper_off, rcap))) return rc;
   if ((rc = dalloc(&ix->d_upper_nbr, rows * (size_t)ix->stride_u))) return rc;
   if ((rc = dalloc(&ix->d_upper_deg, rows))) return rc;
-  if ((rc = dalloc(&ix->d_level, n))) return rc;
+  if ((rc = dalloc(&ix->d_level, rcap))) return rc;
+  if (rcap > n) {
+    HX_CUDA(cudaMemset(ix->d_deg0, 0, rcap * sizeof(uint16_t)));
+    HX_CUDA(cudaMemset(ix->d_raw0, 0, rcap * sizeof(uint16_t)));
+    HX_CUDA(cudaMemset(ix->d_upper_off, 0xFF, rcap * sizeof(uint32_t)));
+    HX_CUDA(cudaMemset(ix->d_level, 0, rcap));
+  }
   HX_CUDA(cudaMemset(ix->d_nbr0, 0, n * (size_t)ix->stride0 * sizeof(uint32_t)));
   HX_CUDA(cudaMemset(ix->d_deg0, 0, n * sizeof(uint16_t)));
   HX_CUDA(cudaMemset(ix->d_upper_nbr, 0, std::max<size_t>(rows, 1) * ix->stride_u * sizeof(uint32_t)));

@@ -179,7 +179,8 @@ static __global__ void __launch_bounds__(HX_SEL_THREADS) k_select(HxDev ix, HxSe
 
 // ---- candidate id -> slot mapping (restricted.rs:615-659: ids without a vector row are skipped) ----------
 static __global__ void k_map_candidates(const uint64_t* __restrict__ ids_sorted, uint32_t n, const uint64_t* __restrict__ cand,
-                                 uint64_t n_cand, uint32_t* __restrict__ out_slots, int contiguous, uint64_t first_id) {
+                                 uint64_t n_cand, uint32_t* __restrict__ out_slots, int contiguous, uint64_t first_id,
+                                 const uint8_t* __restrict__ deleted) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cand) return;
   const uint64_t id = cand[i];
@@ -194,5 +195,6 @@ static __global__ void k_map_candidates(const uint64_t* __restrict__ ids_sorted,
     }
     if (lo < n && ids_sorted[lo] == id) slot = lo;
   }
+  if (deleted && slot != HX_ABSENT && deleted[slot]) slot = HX_ABSENT;   // hx_index_delete_vectors: the row is gone
   out_slots[i] = slot;
 }

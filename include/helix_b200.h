@@ -222,6 +222,34 @@ typedef struct {
 hx_status hx_parse_vector_key(const uint8_t* key, size_t len, hx_vector_key* out);
 hx_status hx_encode_vector_key(const hx_vector_key* key, uint8_t* out, size_t cap, size_t* out_len);
 
+/* ---- incremental mirror maintenance (memory_store.rs:105-130, read_index.rs:53-65) ------------
+ * A committed write reaches the mirror as ROW PATCHES — the rows the write made dirty on the Rust side
+ * (VectorMemoryDirtyRows: dirty_nodes + dirty_upper_neighbors) — followed by a new version token:
+ *   hx_index_upsert_vectors        vector rows: an existing id is overwritten in place, an id above the current
+ *                                  maximum is appended (ids come from a monotonic allocator); an absent id INSIDE the
+ *                                  mirrored range would renumber the slots -> HX_ERR_UNSUPPORTED, re-hydrate
+ *   hx_index_set_levels            the HNSW level of new nodes (allocates their empty upper rows, mutation.rs:706-739)
+ *   hx_index_upsert_neighbor_rows  replaces the layer's rows of the given nodes (decoded CSR as in hx_index_load_graph)
+ *   hx_index_load_simhash          (above) patches fingerprints by id
+ *   hx_index_delete_vectors        the node can no longer be scored or returned; its former neighbours' repaired rows
+ *                                  arrive as upserts; deleting the entry point needs a following hx_index_set_entry
+ *   hx_index_set_entry             (above) new entry point / max layer
+ *   hx_index_load_upper_vector_rows  `[0x13]` hot-lane item rows: inserted when the node is new, otherwise required to be
+ *                                  byte-identical to the canonical row (a stale hot-lane row is an InvariantViolation)
+ *   hx_index_set_version           the (generation identity, visible sequence) this image now corresponds to; the Rust
+ *                                  read guard compares it with the request's snapshot before dispatching a search here
+ * Patch calls must not overlap searches on the same handle (the Rust side holds its write lock, as it does around the
+ * resident cache's publish).  The rkyv metadata row is decoded on the Rust side: entry point and max layer cross the
+ * ABI as the two scalars of hx_index_set_entry. */
+hx_status hx_index_upsert_vectors(hx_index* idx, const uint64_t* ids, const float* rows, size_t n);
+hx_status hx_index_set_levels(hx_index* idx, const uint64_t* ids, const uint16_t* levels, size_t n);
+hx_status hx_index_upsert_neighbor_rows(hx_index* idx, uint16_t layer, const uint64_t* node_ids,
+                                        const uint32_t* offsets, const uint64_t* neighbors, size_t n_nodes);
+hx_status hx_index_delete_vectors(hx_index* idx, const uint64_t* ids, size_t n);
+hx_status hx_index_load_upper_vector_rows(hx_index* idx, const uint64_t* ids, const uint8_t* rows, size_t n);
+hx_status hx_index_set_version(hx_index* idx, uint64_t generation, uint64_t visible_seq);
+hx_status hx_index_get_version(hx_index* idx, uint64_t* generation, uint64_t* visible_seq, uint64_t* patches_applied);
+
 /* Build the HNSW graph on the device from the loaded vectors (SURVEY §8(f).1:
  * insert_hnsw / search_layer_beam / select_diverse / add_bidirectional_link,
  * mutation.rs:787-1005,1498-1591, restated as batched concurrent insertion).

@@ -448,8 +448,8 @@ def measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=None, label_
                                      "h2d_bytes_per_step": B * dim * 4 + B * 24, "d2h_bytes_per_step": B * (k * 12 + 4) + B * 4 + 4,
                                      "api": "hx_search_restricted_sets (label sets uploaded once with hx_candidates_create)",
                                      "sets_upload_s": round(cache_s, 3), "identical_to_device_path": same_sets},
-        "gpu_launches": steps * 3, "launches_per_step": {"k_validate_and_header": 1, "k_scan": 1, "k_select": 1},
-        "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+        "gpu_launches": steps * 2, "launches_per_step": {"k_validate_and_header": 1, "k_scan_topk": 1},
+        "roofline": {"bound": "hbm", "kernel": "k_scan_topk (bit-exact scan + warp-shuffle top-k, one launch)", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(achieved / hbm_peak, 4),
                      "traffic": ncu_traffic("k_scan", {"queries": B, "candidates": per_q, "dim": dim}), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms_per_launch": round(kernel_ms, 4)},

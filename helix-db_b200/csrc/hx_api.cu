@@ -229,7 +229,7 @@ void HxScratch::destroy() {
   d_qstatus.release(); d_out_counts.release(); d_qstats.release(); d_err.release(); d_epochs.release();
   d_cand_slots.release(); d_out_ids.release(); d_cand_ids.release(); d_cand_offsets.release(); d_keys.release();
   d_stamps.release();
-  d_tiepool.release(); d_tiebusy.release(); d_qerr.release(); h_qerr.release();
+  d_tiepool.release(); d_tiebusy.release(); d_qerr.release(); h_qerr.release(); d_partial.release(); d_tickets.release();
   d_vtab.release(); d_vpool.release(); d_vbusy.release(); d_prof.release(); d_pstats.release(); d_qsim.release();
   for (auto& m : misc) m.release();
   h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
@@ -1881,10 +1881,59 @@ static hx_status launch_scan_select(hx_index* ix, HxScratch* s, const float* d_q
                                     uint32_t* d_out_counts, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1,
                                     uint32_t* launches, const HxSetRefs* sets = nullptr) {
   hx_status rc;
-  if ((rc = s->d_keys.reserve(total_keys))) return rc;
   if ((rc = s->d_err.reserve(1))) return rc;
   HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, sizeof(uint32_t), stream));
   const HxDev dev = ix->dev();
+  // k <= 32 (the reference's default k = 10): ONE launch — scores reduced to the top k by warp shuffles inside the scan
+  // kernel, the last CTA of each query merges the per-CTA lists; no key array in HBM, no k_select launch
+  const uint32_t chunk_pick = pick_chunk(total_keys, ix->sm_count);
+  const uint32_t n_chunks = (uint32_t)((max_cands + chunk_pick - 1) / chunk_pick);
+  static const bool fused_off = getenv("HX_SCAN_FUSED") && atoi(getenv("HX_SCAN_FUSED")) == 0;
+  const bool fused_topk = !fused_off && k <= HX_TOPK && ix->cfg.metric != HX_METRIC_MANHATTAN && B <= 65535 &&
+                          (size_t)B * n_chunks * HX_TOPK * 8 <= (256ull << 20);
+  if (fused_topk) {
+    if ((rc = s->d_partial.reserve((size_t)B * n_chunks * HX_TOPK))) return rc;
+    if (s->tickets_zeroed < B || !s->d_tickets.p) {
+      if ((rc = s->d_tickets.reserve(B))) return rc;
+      HX_CUDA(cudaMemsetAsync(s->d_tickets.p, 0, s->d_tickets.cap * sizeof(uint32_t), stream));
+      s->tickets_zeroed = s->d_tickets.cap;
+    }
+    HxScanArgs a{};
+    a.queries = d_queries;
+    a.q_hdr = s->d_qhdr.p;
+    a.q_status = s->d_qstatus.p;
+    a.B = (uint32_t)B;
+    a.cand_slots = d_slots;
+    a.cand_offsets = d_offsets;
+    a.shared_set = shared ? 1u : 0u;
+    a.n_shared = n_shared;
+    a.chunk = chunk_pick;
+    a.err_flags = s->d_err.p;
+    if (sets) { a.q_slots = sets->q_slots; a.q_len = sets->q_len; a.q_keyoff = sets->q_keyoff; }
+    HxTopkArgs tk{};
+    tk.partial = s->d_partial.p;
+    tk.tickets = s->d_tickets.p;
+    tk.n_chunks = n_chunks;
+    tk.k = k;
+    tk.out_ids = d_out_ids;
+    tk.out_scores = d_out_scores;
+    tk.out_counts = d_out_counts;
+    dim3 grid(n_chunks, (unsigned)B);
+    const uint32_t smem = ix->ld * 4u;
+    HX_CUDA(cudaEventRecord(e0, stream));
+    if (ix->cfg.metric == HX_METRIC_EUCLIDEAN) {
+      if (smem > 48 * 1024) HX_CUDA(cudaFuncSetAttribute(k_scan_topk<HXM_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_scan_topk<HXM_EUCLIDEAN><<<grid, HX_SCAN_THREADS, smem, stream>>>(dev, a, tk);
+    } else {
+      if (smem > 48 * 1024) HX_CUDA(cudaFuncSetAttribute(k_scan_topk<HXM_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      k_scan_topk<HXM_COSINE><<<grid, HX_SCAN_THREADS, smem, stream>>>(dev, a, tk);
+    }
+    HX_CUDA(cudaGetLastError());
+    HX_CUDA(cudaEventRecord(e1, stream));
+    (*launches)++;
+    return HX_OK;
+  }
+  if ((rc = s->d_keys.reserve(total_keys))) return rc;
   HxScanArgs a{};
   a.queries = d_queries;
   a.q_hdr = s->d_qhdr.p;

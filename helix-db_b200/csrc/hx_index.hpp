@@ -102,6 +102,9 @@ struct HxScratch {
   DevBuf<uint64_t> d_tiepool;                  // overflow regions of the tie stack (HxRingArgs::tie_pool)
   DevBuf<uint32_t> d_tiebusy;
   bool tiepool_init = false;
+  DevBuf<uint64_t> d_partial;                  // fused scan + top-k: per-CTA lists
+  DevBuf<uint32_t> d_tickets;                  // ... and the per-query CTA tickets (self-resetting)
+  size_t tickets_zeroed = 0;
   DevBuf<uint32_t> d_qerr;                     // per-query error flags
   PinBuf<uint32_t> h_qerr;
   DevBuf<unsigned long long> d_prof;   // HX_PHASE_PROF diagnostics

@@ -82,6 +82,140 @@ static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan(HxDev ix, HxSca
   }
 }
 
+// ---- fused scan + top-k (k <= 32): ONE launch, no key array ---------------------------------------------------------------
+// north_star: "warp-shuffle top-k reduction".  Same grid and the same bit-exact octet scoring as k_scan, but a candidate's
+// key never goes to HBM: every warp keeps its HX_TOPK smallest keys sorted across its lanes (lane i = i-th smallest; an
+// insertion is one ballot for the rank and one shuffle-up for the shift), the 8 warps of the CTA merge through shared
+// memory, the CTA writes its HX_TOPK keys to a small partial array, and the LAST CTA of a query (atomic ticket) merges the
+// partials and writes ids / scores / count.  The ticket counter resets itself, so nothing is zeroed per launch.
+#define HX_TOPK 32
+
+struct HxTopkArgs {
+  uint64_t* partial;        // [B][n_chunks][HX_TOPK]
+  uint32_t* tickets;        // [B] zero before the first launch; self-resetting
+  uint32_t n_chunks;        // gridDim.x
+  uint32_t k;               // requested k (<= HX_TOPK); clamped to |C_q| per query (restricted.rs:200-213)
+  uint64_t* out_ids;        // [B][k]
+  float* out_scores;
+  uint32_t* out_counts;
+};
+
+// insert `key` into the warp's sorted list (lane i holds the i-th smallest, HX_KEY_MAX = empty); warp-uniform call
+__device__ __forceinline__ void hx_topk_insert(uint64_t& mine, uint64_t key, uint32_t lane) {
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t pos = __popc(__ballot_sync(FULL, mine < key));   // keys are distinct (rank in the low word)
+  if (pos >= HX_TOPK) return;
+  const uint64_t up = __shfl_up_sync(FULL, mine, 1);
+  if (lane > pos) mine = up;
+  else if (lane == pos) mine = key;
+}
+
+template <int METRIC>
+static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan_topk(HxDev ix, HxScanArgs a, HxTopkArgs tk) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* sq = reinterpret_cast<float*>(smem);
+  __shared__ uint64_t s_lists[HX_SCAN_THREADS / 32][HX_TOPK];
+  __shared__ uint32_t s_last;
+  const uint32_t tid = threadIdx.x, t = tid & 7u, oct = tid >> 3, lane = tid & 31u, warp = tid >> 5;
+  const unsigned FULL = 0xffffffffu;
+  for (uint32_t q = blockIdx.y; q < a.B; q += gridDim.y) {
+    const uint64_t base = a.q_slots ? 0ull : (a.shared_set ? 0ull : a.cand_offsets[q]);
+    const uint64_t n = a.q_slots ? a.q_len[q] : (a.shared_set ? a.n_shared : (a.cand_offsets[q + 1] - base));
+    const uint64_t start = (uint64_t)blockIdx.x * a.chunk;
+    const bool live = a.q_status[q] == 0u && start < n;            // uniform per CTA
+    uint64_t mine = HX_KEY_MAX;
+    if (live) {
+      const uint64_t end = (start + a.chunk < n) ? start + a.chunk : n;
+      const float q_hdr = a.q_hdr[q];
+      for (uint32_t i = tid; i < ix.ld; i += HX_SCAN_THREADS)
+        sq[i] = i < ix.dim ? a.queries[(size_t)q * ix.dim + i] : 0.0f;
+      __syncthreads();
+      const uint32_t* slots = a.q_slots ? a.q_slots[q] : a.cand_slots + base;
+      // every warp walks the chunk in steps of 32 rows (4 octets per warp: rows r, r+1, r+2, r+3 of its step)
+      for (uint64_t r0 = start; r0 < end; r0 += HX_SCAN_THREADS / 8) {
+        const uint64_t r = r0 + oct;
+        uint64_t key = HX_KEY_MAX;
+        if (r < end) {
+          const uint32_t slot = slots[r];
+          if (slot != HX_ABSENT) {
+            float s;
+            if (METRIC == HXM_MANHATTAN) s = hx_manhattan_seq(ix.vec + (size_t)slot * ix.ld, sq, ix.dim);
+            else s = hx_octet_score<METRIC>(ix, sq, q_hdr, slot, t);
+            if (!hx_score_ok(s)) atomicOr(a.err_flags, HXF_INVALID_SCORE);
+            key = hx_make_key(s, (uint32_t)r);
+          }
+        }
+        // the warp's four candidates of this step, tested against its current k-th before any insertion work
+        const uint64_t kth = __shfl_sync(FULL, mine, HX_TOPK - 1);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const uint64_t c = __shfl_sync(FULL, key, o * 8);
+          if (c < kth) hx_topk_insert(mine, c, lane);   // warp-uniform branch (c and kth are broadcasts)
+        }
+      }
+      s_lists[warp][lane] = mine;
+    }
+    __syncthreads();
+    if (live && warp == 0) {   // merge the 8 warp lists (warp 0's own list is already in `mine`)
+      for (uint32_t w = 1; w < HX_SCAN_THREADS / 32; ++w)
+        for (uint32_t i = 0; i < HX_TOPK; ++i) {
+          const uint64_t c = s_lists[w][i];
+          if (c == HX_KEY_MAX) break;                    // lists are sorted: the rest is empty
+          if (c < __shfl_sync(FULL, mine, HX_TOPK - 1)) hx_topk_insert(mine, c, lane);
+          else break;                                    // sorted: nothing further in this list can enter
+        }
+    }
+    if (warp == 0) {
+      // every CTA of the grid row reports (an empty list when it had nothing to scan) so that the ticket count is exact
+      tk.partial[((size_t)q * tk.n_chunks + blockIdx.x) * HX_TOPK + lane] = live ? mine : HX_KEY_MAX;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t tkt = atomicAdd(tk.tickets + q, 1u);
+        s_last = (tkt == tk.n_chunks - 1u) ? 1u : 0u;
+      }
+    }
+    __syncthreads();
+    if (s_last) {   // the last CTA of this query merges the partial lists: warp w takes chunks w, w+8, ...
+      __threadfence();
+      uint64_t best = HX_KEY_MAX;
+      const uint64_t* P = tk.partial + (size_t)q * tk.n_chunks * HX_TOPK;
+      for (uint32_t c = warp; c < tk.n_chunks; c += HX_SCAN_THREADS / 32) {
+        const uint64_t v = __ldcg(P + (size_t)c * HX_TOPK + lane);
+        for (uint32_t i = 0; i < HX_TOPK; ++i) {
+          const uint64_t x = __shfl_sync(FULL, v, i);
+          if (x >= __shfl_sync(FULL, best, HX_TOPK - 1)) break;   // sorted list: done with this chunk
+          hx_topk_insert(best, x, lane);
+        }
+      }
+      s_lists[warp][lane] = best;
+      __syncthreads();
+      if (warp == 0) {
+        for (uint32_t w = 1; w < HX_SCAN_THREADS / 32; ++w)
+          for (uint32_t i = 0; i < HX_TOPK; ++i) {
+            const uint64_t c = s_lists[w][i];
+            if (c >= __shfl_sync(FULL, best, HX_TOPK - 1)) break;
+            hx_topk_insert(best, c, lane);
+          }
+        const uint32_t kk = (uint64_t)tk.k < n ? tk.k : (uint32_t)n;   // k' = min(k, |C|)
+        const bool have = lane < kk && best != HX_KEY_MAX && a.q_status[q] == 0u;
+        if (have) {
+          const uint32_t rank = (uint32_t)(best & 0xffffffffu);
+          const uint32_t* slots = a.q_slots ? a.q_slots[q] : a.cand_slots + base;
+          tk.out_ids[(size_t)q * tk.k + lane] = ix.ids[slots[rank]];
+          tk.out_scores[(size_t)q * tk.k + lane] = hx_key_score(best);
+        }
+        const uint32_t cnt = __popc(__ballot_sync(FULL, have));
+        if (lane == 0) {
+          tk.out_counts[q] = cnt;
+          tk.tickets[q] = 0u;   // ready for the next launch
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- top-k selection -----------------------------------------------------------------------------------
 struct HxSelectArgs {
   const uint64_t* keys;

@@ -161,7 +161,7 @@ ABI_SYMBOLS = [
     "hx_shard_unique_id", "hx_shard_group_create", "hx_shard_group_destroy", "hx_search_sharded_device",
     "hx_search_sharded", "hx_search_restricted_sharded", "hx_shard_group_last_ms",
     "hx_index_upsert_vectors", "hx_index_set_levels", "hx_index_upsert_neighbor_rows", "hx_index_delete_vectors",
-    "hx_index_load_upper_vector_rows", "hx_index_set_version", "hx_index_get_version",
+    "hx_index_load_upper_vector_rows", "hx_index_set_version", "hx_index_get_version", "hx_index_build_ex",
 ]
 
 _lib = None
@@ -286,6 +286,8 @@ def load_library():
     L.hx_service_search.argtypes = [vp, fp, u64p, fp, u32p]
     L.hx_service_get_stats.restype = C.c_int32
     L.hx_service_get_stats.argtypes = [vp, C.POINTER(ServiceStats)]
+    L.hx_index_build_ex.restype = C.c_int32
+    L.hx_index_build_ex.argtypes = [vp, u16p, C.c_uint64, C.c_int32]
     L.hx_index_upsert_vectors.restype = C.c_int32
     L.hx_index_upsert_vectors.argtypes = [vp, u64p, fp, sz]
     L.hx_index_set_levels.restype = C.c_int32
@@ -607,12 +609,14 @@ class VectorIndex:
         _ck(self.L.hx_index_export_neighbor_row(self.h, layer, node_id, out, len(out), C.byref(n)))
         return bytes(out[:n.value])
 
-    def build(self, levels=None, seed=0):
-        if levels is None:
-            _ck(self.L.hx_index_build(self.h, None, seed))
-        else:
+    def build(self, levels=None, seed=0, sequential=False):
+        """hx_index_build_ex.  sequential=True: one insert_hnsw at a time — the reference's graph for the same insertion
+        order and levels (parity runs, small indexes); default: batched concurrent insertion."""
+        lp = None
+        if levels is not None:
             la = np.ascontiguousarray(levels, dtype=np.uint16)
-            _ck(self.L.hx_index_build(self.h, la.ctypes.data_as(C.POINTER(C.c_uint16)), seed))
+            lp = la.ctypes.data_as(C.POINTER(C.c_uint16))
+        _ck(self.L.hx_index_build_ex(self.h, lp, seed, 1 if sequential else 0))
 
     def graph_info(self):
         n, e, ml, s0, su = C.c_uint64(0), C.c_uint64(0), C.c_uint16(0), C.c_uint32(0), C.c_uint32(0)

@@ -969,7 +969,17 @@ hx_status hx_finalize_graph(hx_index* ix) {
 extern "C" hx_status hx_index_build(hx_index* ix, const uint16_t* levels, uint64_t seed) {
   if (!ix) return HX_ERR_INDEX_NOT_FOUND;
   HX_CUDA(cudaSetDevice(ix->device));
-  return hx_build_impl(ix, levels, seed);
+  return hx_build_impl(ix, levels, seed, 0);
+}
+
+extern "C" hx_status hx_index_build_ex(hx_index* ix, const uint16_t* levels, uint64_t seed, int32_t mode) {
+  if (!ix) return HX_ERR_INDEX_NOT_FOUND;
+  if (mode != HX_BUILD_BATCHED && mode != HX_BUILD_SEQUENTIAL) {
+    hx_set_error("unknown build mode %d", mode);
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  HX_CUDA(cudaSetDevice(ix->device));
+  return hx_build_impl(ix, levels, seed, mode == HX_BUILD_SEQUENTIAL ? 1 : 0);
 }
 
 extern "C" hx_status hx_index_graph_info(hx_index* ix, uint64_t* n_nodes, uint64_t* entry_point, uint16_t* max_layer,

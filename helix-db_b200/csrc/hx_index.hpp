@@ -224,7 +224,7 @@ hx_status hx_launch_cta_ring(hx_index* ix, const HxCtaRingCfg& c, const HxHnswAr
 bool hx_slot_of(const hx_index* ix, uint64_t id, uint32_t* slot);
 
 // implemented in k_build.cu / k_dense.cu
-hx_status hx_build_impl(hx_index* ix, const uint16_t* levels, uint64_t seed);
+hx_status hx_build_impl(hx_index* ix, const uint16_t* levels, uint64_t seed, int sequential);
 hx_status hx_dense_impl(hx_index* ix, const float* queries, size_t B, const hx_search_params* p, uint64_t* out_ids,
                         float* out_scores, uint32_t* out_counts, hx_stats* stats);
 hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t B, const hx_search_params* p,

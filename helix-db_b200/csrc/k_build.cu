@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(HXB_THREADS) k_build_search(HxDev ix, HxBuildA
   float* fdist = reinterpret_cast<float*>(frontier + fr_cap);
   uint32_t* sel = reinterpret_cast<uint32_t*>(fdist + fr_cap);        // [128]
   uint8_t* taken = reinterpret_cast<uint8_t*>(sel + 128);             // [256]
+  __shared__ uint64_t s_tie[HX_TIE_CAP];   // evicted-unexpanded entries whose score equals w.max (see k_hnsw.cuh)
   __shared__ uint32_t s_nf, s_cur, s_done, s_epoch, s_changed, s_nsel, s_reject, s_len;
   __shared__ float s_cur_dist;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, t = tid & 7u, oct = tid >> 3;
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(HXB_THREADS) k_build_search(HxDev ix, HxBuildA
       if (tid == 0) a.epochs[blockIdx.x] = epoch;
       const uint8_t ep8 = (uint8_t)epoch;
       HxBeam beam{beam_mem, 0u};
+      uint32_t tie_len = 0;
       if (warp == 0) {
         if (lane == 0) {
           beam_mem[0] = hx_make_key(cur_dist, cur << 1);
@@ -239,6 +241,9 @@ __global__ void __launch_bounds__(HXB_THREADS) k_build_search(HxDev ix, HxBuildA
             __syncwarp();
             if (lane == 0) beam_mem[first] = key | 1ull;
             cur_slot = (uint32_t)(key & 0xffffffffu) >> 1;
+          } else if (tie_len > 0) {   // `current.score > w.max` is strict: a candidate tied with w.max is still expanded
+            tie_len--;
+            cur_slot = (uint32_t)(s_tie[tie_len] & 0xffffffffu) >> 1;
           }
           uint32_t nf = 0;
           if (cur_slot != HX_ABSENT && (int)ix.level[cur_slot] >= layer) {
@@ -294,8 +299,22 @@ __global__ void __launch_bounds__(HXB_THREADS) k_build_search(HxDev ix, HxBuildA
               const uint32_t xslot = __shfl_sync(0xffffffffu, f < nf ? frontier[f] : 0u, src);
               const uint32_t wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
               if (!((xb < wmax) || (beam.len < ef))) continue;
+              const bool was_full = beam.len == ef;
               uint64_t ev;
               hx_beam_insert(beam, ef, ((uint64_t)xb << 32) | ((uint64_t)xslot << 1), &ev, lane);
+              if (was_full) {
+                const uint32_t new_wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
+                if (new_wmax < wmax) tie_len = 0;   // older ties are now above w.max: their pop would end the loop
+                if (!(ev & 1ull) && (uint32_t)(ev >> 32) == new_wmax) {
+                  if (tie_len < HX_TIE_CAP) {
+                    if (lane == 0) s_tie[tie_len] = ev;
+                    tie_len++;
+                  } else if (lane == 0) {
+                    atomicOr(a.counters + 3, HXF_TIE_OVERFLOW);
+                  }
+                }
+                __syncwarp();
+              }
             }
           }
         }
@@ -319,6 +338,100 @@ __global__ void __launch_bounds__(HXB_THREADS) k_build_search(HxDev ix, HxBuildA
       if (len) {
         cur = (uint32_t)(beam_mem[0] & 0xffffffffu);
         cur_dist = __uint_as_float((uint32_t)(beam_mem[0] >> 32));
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// write `vals[0..n)` (unique) into the row in ascending order (stage_neighbors_vec_for_mutation, mutation.rs:1291-1307)
+__device__ __forceinline__ void hxb_store_sorted(uint32_t* dst, uint16_t* deg, const uint32_t* vals, uint32_t n, uint32_t lane) {
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t x = vals[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) rank += (vals[j] < x) ? 1u : 0u;
+    dst[rank] = x;
+  }
+  if (lane == 0) *deg = (uint16_t)n;
+}
+
+// ---- sequential mode: add_bidirectional_link for ONE new node, targets in selection order --------------------------------
+// mutation.rs:1498-1591 one link at a time: append `u` to v's row; if the row overflows, rank ALL its neighbours by distance
+// to v, select_diverse to the limit, and remove the reciprocal edge from every rejected neighbour's own row — before the
+// next link of the same insert is processed (a later target sees the rows the earlier ones rewrote).  One CTA; with
+// k_build_search on a round of one node this reproduces insert_hnsw's graph exactly (tests/test_gpu_build_seq.py).
+__device__ __forceinline__ void hxb_remove_edge(const HxDev& ix, uint32_t r, uint32_t x) {   // one thread
+  uint32_t* row = hxb_row_nbr(ix, r);
+  uint16_t* degp = hxb_row_deg(ix, r);
+  const uint32_t deg = *degp;
+  uint32_t w = 0;
+  for (uint32_t j = 0; j < deg; ++j) {
+    const uint32_t y = row[j];
+    if (y != x) row[w++] = y;
+  }
+  *degp = (uint16_t)w;
+}
+
+__global__ void __launch_bounds__(HXB_THREADS) k_build_link_seq(HxDev ix, HxBuildArgs a) {
+  __shared__ uint64_t keys[HXB_MAX_CAND];
+  __shared__ uint64_t sorted[HXB_MAX_CAND];
+  __shared__ uint32_t cand[HXB_MAX_CAND];
+  __shared__ uint32_t sel[128];
+  __shared__ uint8_t taken[HXB_MAX_CAND];
+  __shared__ uint32_t s_nsel, s_reject;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, t = tid & 7u, oct = tid >> 3;
+  const uint32_t u = a.batch_start;
+  const int node_layer = ix.level[u];
+  const int top = node_layer < a.cur_max_layer ? node_layer : a.cur_max_layer;
+  for (int layer = top; layer >= 0; --layer) {
+    const uint32_t limit = layer == 0 ? a.lim0 : a.limu;
+    const uint32_t np = a.Pn[layer];
+    const uint32_t* prow = a.P + (layer == 0 ? 0u : a.lim0 + (uint32_t)(layer - 1) * a.limu);
+    const uint32_t ru = hxb_row_id(ix, layer, u);
+    if (warp == 0) hxb_store_sorted(hxb_row_nbr(ix, ru), hxb_row_deg(ix, ru), prow, np, lane);   // stage_new_neighbors
+    __syncthreads();
+    for (uint32_t pi = 0; pi < np; ++pi) {
+      const uint32_t v = prow[pi];
+      const uint32_t rv = hxb_row_id(ix, layer, v);
+      uint32_t* row = hxb_row_nbr(ix, rv);
+      uint16_t* degp = hxb_row_deg(ix, rv);
+      const uint32_t deg = *degp;
+      bool has = false;
+      for (uint32_t j = 0; j < deg; ++j) has |= (row[j] == u);
+      const uint32_t nc = deg + (has ? 0u : 1u);
+      for (uint32_t i = tid; i < nc; i += HXB_THREADS) cand[i] = i < deg ? row[i] : u;
+      __syncthreads();
+      if (nc <= limit) {
+        if (warp == 0) hxb_store_sorted(row, degp, cand, nc, lane);
+        __syncthreads();
+        continue;
+      }
+      for (uint32_t i = oct; i < nc; i += HXB_THREADS / 8) {
+        float d = hxb_pair(ix, v, cand[i], t);
+        if (t == 0) {
+          if (!hx_score_ok(d)) atomicOr(a.counters + 3, HXF_INVALID_SCORE);
+          keys[i] = hx_make_key(d, cand[i]);
+        }
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < nc; i += HXB_THREADS) {   // distances.sort(): rank sort by (score, id)
+        const uint64_t k = keys[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < nc; ++j) rank += (keys[j] < k) ? 1u : 0u;
+        sorted[rank] = k;
+      }
+      __syncthreads();
+      hxb_select_diverse(ix, sorted, nc, limit, sel, taken, &s_nsel, &s_reject);
+      const uint32_t nsel = s_nsel;
+      if (warp == 0) hxb_store_sorted(row, degp, sel, nsel, lane);
+      __syncthreads();
+      if (tid == 0) {   // remove the reciprocal edge of every rejected neighbour (u included, if v rejected it)
+        for (uint32_t i = 0; i < nc; ++i) {
+          const uint32_t c = cand[i];
+          bool kept = false;
+          for (uint32_t j = 0; j < nsel; ++j) kept |= (sel[j] == c);
+          if (!kept) hxb_remove_edge(ix, hxb_row_id(ix, layer, c), v);
+        }
       }
       __syncthreads();
     }
@@ -409,17 +522,6 @@ __device__ __forceinline__ bool hxb_in_R(const HxBuildArgs& a, uint32_t ti, uint
   for (uint32_t i = 0; i < n; ++i)
     if (Rrow[i] == x) return true;
   return false;
-}
-
-// write `vals[0..n)` (unique) into the row in ascending order (stage_neighbors_vec_for_mutation, mutation.rs:1291-1307)
-__device__ __forceinline__ void hxb_store_sorted(uint32_t* dst, uint16_t* deg, const uint32_t* vals, uint32_t n, uint32_t lane) {
-  for (uint32_t i = lane; i < n; i += 32) {
-    const uint32_t x = vals[i];
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; ++j) rank += (vals[j] < x) ? 1u : 0u;
-    dst[rank] = x;
-  }
-  if (lane == 0) *deg = (uint16_t)n;
 }
 
 // ---- kernel B2: mutual consent — an edge survives only if both endpoints keep it ------------------------------------------------
@@ -576,7 +678,7 @@ static hx_status dalloc(T** p, size_t count) {
   return HX_OK;
 }
 
-hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed) {
+hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed, int sequential) {
   const size_t n = ix->n;
   if (n == 0) return HX_OK;
   const uint32_t m = ix->cfg.m, lim0 = ix->lim0;
@@ -639,6 +741,7 @@ hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed) 
   // ---- build-only state ----------------------------------------------------------------------------------------------
   const size_t urows = n + rows;
   uint32_t max_batch = (uint32_t)std::min<size_t>(16384, std::max<size_t>(1, n / 64));
+  if (sequential) max_batch = 1;   // HX_BUILD_SEQUENTIAL: one insert at a time, links applied in selection order
   if (const char* env = getenv("HX_BUILD_MAX_BATCH")) {   // experiment knob: rounds never exceed this many nodes
     const long v = atol(env);
     if (v > 0) max_batch = (uint32_t)std::min<long>(v, 65536);
@@ -760,12 +863,15 @@ hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed) 
     const uint32_t gridA = (uint32_t)std::min<size_t>(batch, grid_cap);
     k_build_search<<<gridA, HXB_THREADS, smemA>>>(dev, a, ef_cap, fr_cap);
     HXB_CUDA(cudaGetLastError());
-    if (cur_max_layer >= 0) {
+    if (sequential) {
+      if (cur_max_layer >= 0) k_build_link_seq<<<1, HXB_THREADS>>>(dev, a);
+      // (an empty graph: the node only gets its empty rows, which the zero-initialised arrays already are)
+    } else if (cur_max_layer >= 0) {
       k_build_scatter<<<(unsigned)batch, 64>>>(dev, a);
       k_build_prune<<<(unsigned)std::min<size_t>(max_targets, (size_t)grid_cap * 2), HXB_THREADS>>>(dev, a);
     }
     // number of targets is only known on the device: size the consent grid by its upper bound for this round
-    {
+    if (!sequential) {
       const size_t tb = std::min<size_t>(max_targets, batch * (size_t)pstride);
       const size_t items = (cur_max_layer >= 0 ? tb : 0) + new_rows.size();
       k_build_finalize<<<(unsigned)((items + 7) / 8), 256>>>(dev, a, (uint32_t)new_rows.size(), d_new_rows);
@@ -790,6 +896,10 @@ hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed) 
   cleanup();
   if (counters[3] & HXF_INVALID_SCORE) {
     hx_set_error("vector distance kernel emitted an invalid score during build");
+    return HX_ERR_INVARIANT_VIOLATION;
+  }
+  if (counters[3] & HXF_TIE_OVERFLOW) {
+    hx_set_error("more than %d exact score ties at the insertion beam's boundary", HX_TIE_CAP);
     return HX_ERR_INVARIANT_VIOLATION;
   }
   ix->populated = true;

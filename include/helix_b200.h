@@ -256,6 +256,13 @@ hx_status hx_index_get_version(hx_index* idx, uint64_t* generation, uint64_t* vi
  * `levels` (n entries, slot order of ascending id) may be NULL => drawn from `seed`
  * with select_layer's law floor(-ln(U)*ml), ml = 1/ln(m) (mod.rs:769-796). */
 hx_status hx_index_build(hx_index* idx, const uint16_t* levels, uint64_t seed);
+/* Build modes.  HX_BUILD_BATCHED (hx_index_build): rounds of concurrent insertions — fast (1M x 768 in seconds), same
+ * structural invariants and recall class as the reference, but not the same graph (nodes of one round do not see each
+ * other).  HX_BUILD_SEQUENTIAL: one insert_hnsw at a time, the links of each insert applied in selection order
+ * (add_bidirectional_link, mutation.rs:1498-1591) — the graph is IDENTICAL to the reference's for the same insertion
+ * order (ascending id) and level assignment; two launches per node, meant for parity runs and small indexes (config C1). */
+enum { HX_BUILD_BATCHED = 0, HX_BUILD_SEQUENTIAL = 1 };
+hx_status hx_index_build_ex(hx_index* idx, const uint16_t* levels, uint64_t seed, int32_t mode);
 
 /* Download the graph (for the CPU oracle to traverse the identical adjacency). */
 hx_status hx_index_graph_info(hx_index* idx, uint64_t* n_nodes, uint64_t* entry_point,

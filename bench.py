@@ -872,8 +872,16 @@ def run_ours(args):
         for i in range(100):
             ix.search_ex(qsets[0][i:i + 1], pnew)
         single_us = (time.perf_counter() - t0) / 100 * 1e6
+        # recall of the production default against the beam width (the reference ships ef = max(k, 100); its own recall gate
+        # for this mode is 0.92, tests/production_support/vector/search.rs): where does 0.95 sit?
+        ef_study = []
+        for ef_d in (100, 150, 200, 300):
+            pe = hx.SearchParams.new(k).with_ef(ef_d)
+            e_ids, _, _ = ix.search_ex(qsets[0][:rq], pe)
+            ef_study.append({"ef": ef_d, "recall_at_10": round(recall_at_k(e_ids, truth), 4)})
         default_mode = {
             "params": "SearchParams::new(10): ef=100, SimHashMode::Adaptive, threshold 43, sampling 0.8, failure 0.1",
+            "recall_vs_ef": ef_study,
             "e2e_qps": round(args.steps * Q / td, 1), "kernel": "k_hnsw_search_policy",
             "kernel_ms_per_launch": round(kms_sum / args.steps, 4), "kernel_qps": round(args.steps * Q / (kms_sum / 1e3), 1),
             "recall_at_10": round(d_recall, 4),

@@ -130,7 +130,8 @@ class PolicyStats(C.Structure):
 class _ServiceConfig(C.Structure):
     _fields_ = [("k", C.c_uint32), ("ef", C.c_uint32), ("capacity", C.c_uint32), ("max_batch", C.c_uint32),
                 ("n_streams", C.c_uint32), ("ctas_per_sm", C.c_uint32), ("cta_warps", C.c_uint32),
-                ("rows_in_flight", C.c_uint32), ("visited_log2", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("rows_in_flight", C.c_uint32), ("visited_log2", C.c_uint32), ("min_batch", C.c_uint32),
+                ("batch_window_us", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class ServiceStats(C.Structure):
@@ -901,10 +902,11 @@ class SearchService:
     served by shared launches.  ``search`` blocks; ``submit`` / ``poll`` are the async pair."""
 
     def __init__(self, index: VectorIndex, k: int, ef: int = 0, capacity: int = 0, max_batch: int = 0, n_streams: int = 0,
-                 ctas_per_sm: int = 0, cta_warps: int = 0, rows_in_flight: int = 0, visited_log2: int = 0):
+                 ctas_per_sm: int = 0, cta_warps: int = 0, rows_in_flight: int = 0, visited_log2: int = 0,
+                 min_batch: int = 0, batch_window_us: int = 0, flags: int = 0):
         self.L, self.index, self.k = index.L, index, int(k)
         cfg = _ServiceConfig(int(k), int(ef), capacity, max_batch, n_streams, ctas_per_sm, cta_warps, rows_in_flight,
-                             visited_log2)
+                             visited_log2, min_batch, batch_window_us, flags)
         h = C.c_void_p()
         _ck(self.L.hx_service_create(index.h, C.byref(cfg), C.byref(h)))
         self.h = h

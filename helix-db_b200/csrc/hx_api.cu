@@ -1179,10 +1179,11 @@ bool hx_cta_ring_config(const hx_index* ix, uint32_t ef, uint32_t want_warps, ui
   return true;
 }
 
+// The dynamic-shared-memory attribute is per kernel INSTANTIATION and device: `set_for` must be one array per
+// instantiation (every k_hnsw_search_cta_ring<M,Q,NB> has the same function TYPE, so a static inside a function template
+// keyed by that type would be shared by all of them — the macro below declares it per expansion instead).
 template <typename F>
-static hx_status cta_ring_prepare(F* fn, int device, size_t smem) {
-  // the attribute is per function and device: set it once per (instantiation, device, size) instead of on every launch
-  static std::atomic<size_t> set_for[64];
+static hx_status cta_ring_prepare(F* fn, std::atomic<size_t>* set_for, int device, size_t smem) {
   const int d = device & 63;
   if (set_for[d].load(std::memory_order_relaxed) < smem) {
     HX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1197,7 +1198,8 @@ hx_status hx_launch_cta_ring(hx_index* ix, const HxCtaRingCfg& c, const HxHnswAr
   hx_status rc = HX_OK;
 #define HX_CTA_GO(M, Q, NBV)                                                                                          \
   do {                                                                                                                \
-    if ((rc = cta_ring_prepare(k_hnsw_search_cta_ring<M, Q, NBV>, ix->device, c.smem))) return rc;                     \
+    static std::atomic<size_t> set_for[64];                                                                           \
+    if ((rc = cta_ring_prepare(k_hnsw_search_cta_ring<M, Q, NBV>, set_for, ix->device, c.smem))) return rc;            \
     if (ctas_per_sm)                                                                                                  \
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_hnsw_search_cta_ring<M, Q, NBV>, (int)c.warps * 32, \
                                                     c.smem);                                                          \

@@ -44,6 +44,8 @@ struct HxSvcStream {
 struct hx_service {
   hx_index* ix = nullptr;
   uint32_t k = 0, ef = 0, cap = 0, mask = 0, max_batch = 0, dim = 0;
+  uint32_t min_batch = 16, busy_inflight = 64, window_ns = 30000;   // coalescing policy (see svc_dispatcher)
+  bool zero_copy = false;                                          // the kernel reads the queries straight from the pinned ring
   HxCtaRingCfg cta{};
   int ctas_per_sm = 0;
   bool cosine = false;
@@ -141,13 +143,20 @@ static hx_status svc_launch(hx_service* v, uint64_t first, uint32_t cnt) {
   }
   v->rr = (pick + 1) % v->streams.size();
   HxSvcStream& S = v->streams[pick];
-  HX_CUDA(cudaMemcpyAsync(v->d_q + (size_t)slot0 * v->dim, v->h_q + (size_t)slot0 * v->dim, (size_t)cnt * v->dim * sizeof(float),
-                          cudaMemcpyHostToDevice, S.st));
-  if (v->cosine)
-    HX_CUDA(cudaMemcpyAsync(v->d_qhdr + slot0, v->h_qhdr + slot0, cnt * sizeof(float), cudaMemcpyHostToDevice, S.st));
   HxHnswArgs a{};
-  a.queries = v->d_q + (size_t)slot0 * v->dim;
-  a.q_hdr = v->d_qhdr + slot0;
+  if (v->zero_copy) {
+    // dimension a multiple of 32: every warp loads the query into registers once and never touches it again, so it can
+    // come straight from the host-mapped ring (3 KB over PCIe per warp) — the launch is the only driver call of the batch
+    a.queries = v->h_q + (size_t)slot0 * v->dim;
+    a.q_hdr = v->h_qhdr + slot0;
+  } else {
+    HX_CUDA(cudaMemcpyAsync(v->d_q + (size_t)slot0 * v->dim, v->h_q + (size_t)slot0 * v->dim,
+                            (size_t)cnt * v->dim * sizeof(float), cudaMemcpyHostToDevice, S.st));
+    if (v->cosine)
+      HX_CUDA(cudaMemcpyAsync(v->d_qhdr + slot0, v->h_qhdr + slot0, cnt * sizeof(float), cudaMemcpyHostToDevice, S.st));
+    a.queries = v->d_q + (size_t)slot0 * v->dim;
+    a.q_hdr = v->d_qhdr + slot0;
+  }
   a.q_status = v->d_zero;
   a.B = cnt;
   a.k = v->k;
@@ -181,9 +190,21 @@ static hx_status svc_launch(hx_service* v, uint64_t first, uint32_t cnt) {
   return HX_OK;
 }
 
+static inline uint64_t svc_now_ns() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
+// Coalescing policy.  A launch costs the dispatcher a few microseconds whatever its size, so one launch per query caps
+// the service at the driver's launch rate (measured: ~70-100 k launches/s, profiles/r02_service_sweep_v1.jsonl).  When
+// the device is idle (few queries in flight) whatever is pending is launched at once — lowest latency; when it is busy
+// (>= busy_inflight queries in flight) a small batch is held back for at most window_ns so that the callers arriving in
+// that window share the launch: the wait is a few percent of a traversal and is hidden behind the queries already running.
 static void svc_dispatcher(hx_service* v) {
   cudaSetDevice(v->ix->device);
   uint32_t idle_spins = 0;
+  uint64_t first_seen = 0;
   while (!v->stop.load(std::memory_order_acquire)) {
     // contiguous run of published slots at head (ring order == ticket order; a run never wraps: the arrays are contiguous)
     uint32_t cnt = 0;
@@ -192,6 +213,7 @@ static void svc_dispatcher(hx_service* v) {
            v->seq[(slot0 + cnt)].load(std::memory_order_acquire) == v->head + cnt + 1)
       cnt++;
     if (cnt == 0) {
+      first_seen = 0;
       if (++idle_spins < 20000) { hx_cpu_relax(); continue; }
       // nothing for a while: sleep until a submitter wakes us (re-check after announcing, so no wake-up is lost)
       v->disp_sleep = 1;
@@ -206,6 +228,15 @@ static void svc_dispatcher(hx_service* v) {
       continue;
     }
     idle_spins = 0;
+    if (cnt < v->min_batch && cnt < v->max_batch && slot0 + cnt < v->cap) {
+      const uint64_t inflight = v->head - v->st_completed.load(std::memory_order_relaxed);
+      if (inflight >= v->busy_inflight) {
+        const uint64_t now = svc_now_ns();
+        if (!first_seen) first_seen = now;
+        if (now - first_seen < v->window_ns) { hx_cpu_relax(); continue; }
+      }
+    }
+    first_seen = 0;
     const hx_status rc = svc_launch(v, v->head, cnt);
     if (rc) {
       svc_fail_pending(v, rc);
@@ -282,6 +313,10 @@ extern "C" hx_status hx_service_create(hx_index* ix, const hx_service_config* cf
   v->mask = p2 - 1;
   v->max_batch = std::min(cfg->max_batch ? cfg->max_batch : 128u, v->cap);
   v->cosine = ix->cfg.metric == HX_METRIC_COSINE;
+  v->zero_copy = (v->dim % 32u) == 0u && !(cfg->flags & HX_SERVICE_STAGE_QUERIES);
+  if (cfg->min_batch) v->min_batch = cfg->min_batch;
+  if (cfg->batch_window_us) v->window_ns = cfg->batch_window_us * 1000u;
+  if (cfg->flags & HX_SERVICE_NO_COALESCING) v->window_ns = 0;
   v->has_limit = component_limit(ix->cfg.metric, v->dim, &v->limit);
   // launch shape: by default two CTAs resident per SM (half the shared memory each, 6 warps so two fit the register file)
   const uint32_t target = cfg->ctas_per_sm ? std::min(cfg->ctas_per_sm, 4u) : 2u;

@@ -351,8 +351,13 @@ typedef struct {
   uint32_t cta_warps;       /* warps per CTA of the traversal kernel; 0 => 12 / 6 / 4 for 1 / 2 / 3+ CTAs per SM */
   uint32_t rows_in_flight;  /* vector rows staged per CTA; 0 => as many as fit                        */
   uint32_t visited_log2;    /* log2 of the shared-memory visited-table size; 0 => auto               */
-  uint32_t reserved[3];
+  uint32_t min_batch;       /* while the device is busy a launch waits (<= batch_window_us) for this many queries; 0 => 16 */
+  uint32_t batch_window_us; /* 0 => 30                                                                */
+  uint32_t flags;           /* HX_SERVICE_*                                                           */
 } hx_service_config;
+enum { HX_SERVICE_NO_COALESCING = 1,   /* launch whatever is pending at once, always                              */
+       HX_SERVICE_STAGE_QUERIES = 2 }; /* copy queries to device memory first (default: the kernel reads the pinned
+                                          ring directly when the dimension is a multiple of 32)                     */
 typedef struct {
   uint64_t submitted, completed, launches, max_batch_seen, dispatcher_sleeps, completer_wakes;
   uint32_t cta_warps, rows_in_flight, visited_cap, smem_bytes, ctas_per_sm, reserved;

@@ -33,11 +33,12 @@ def main():
     q = ix.generate_queries(SEED, a.queries, first_query=10_000_000, n_centroids=1024, sigma=1.0, kind=32)
     k, ef = 10, 100
     ref_ids, ref_sc, ref_cnt = ix.search_batch(q, hx.SearchParams.strict(k, ef))
-    shapes = [dict(ctas_per_sm=2), dict(ctas_per_sm=1), dict(ctas_per_sm=3), dict(ctas_per_sm=2, cta_warps=4),
-              dict(ctas_per_sm=2, cta_warps=8), dict(ctas_per_sm=2, rows_in_flight=16), dict(ctas_per_sm=3, cta_warps=6),
-              dict(ctas_per_sm=4, cta_warps=4, visited_log2=12)]
+    shapes = [dict(ctas_per_sm=2), dict(ctas_per_sm=1), dict(ctas_per_sm=3), dict(ctas_per_sm=2, flags=1),
+              dict(ctas_per_sm=2, flags=2), dict(ctas_per_sm=2, min_batch=32, batch_window_us=60),
+              dict(ctas_per_sm=2, min_batch=8, batch_window_us=15), dict(ctas_per_sm=2, cta_warps=8),
+              dict(ctas_per_sm=3, cta_warps=6)]
     if a.quick:
-        shapes = shapes[:3]
+        shapes = shapes[:4]
     for shape in shapes:
         try:
             svc = ix.service(k, ef, capacity=2048, max_batch=128, **shape)
@@ -45,8 +46,8 @@ def main():
             print(json.dumps({"shape": shape, "error": str(e)}), flush=True)
             continue
         info = svc.stats()
-        for mode, ncall, nthr in (("tasks", 256, 8), ("tasks", 512, 8), ("tasks", 1024, 8), ("blocking", 256, 0),
-                                  ("blocking", 64, 0), ("blocking", 16, 0), ("blocking", 1, 0)):
+        for mode, ncall, nthr in (("tasks", 256, 8), ("tasks", 1024, 8), ("blocking", 256, 0), ("blocking", 64, 0),
+                                  ("blocking", 16, 0), ("blocking", 1, 0)):
             rep, ids, sc, cnt = callers.run(svc, ix, q, k, ef, ncall, mode=mode, n_threads=nthr, seconds=a.seconds)
             same = bool(ids.tolist() == ref_ids.tolist() and sc.tobytes() == ref_sc.tobytes() and cnt.tolist() == ref_cnt.tolist())
             st = svc.stats()

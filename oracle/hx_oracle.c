@@ -1059,6 +1059,320 @@ int hxo_search_exact(const hxo_index* ix, const float* query, uint32_t k, uint64
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Filter-aware (ACORN-style) restricted search  V/restricted.rs:837-1148
+ *   budgets :220-260, deterministic seeds :321-342, candidate keys :615-659, scoring :661-704,
+ *   bridges :706-751.  Restated for generations WITHOUT the SimHash routing directory
+ *   (simhash_directory_enabled() == false => no directory seeds, :866-925 skipped): seeds are the
+ *   evenly spaced sample of the candidate set plus the entry point when it is a candidate.
+ * Every heap / set is the reference's (BinaryHeap<Reverse<Candidate>>, BinaryHeap<Candidate>,
+ * BinaryHeap<Reverse<(u32, NodeId)>>, HashSet<NodeId>); only their iteration-independent behaviour is used.
+ * The scoring order inside one batch (physical key order) only permutes heap pushes and cannot change a result.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t* k; size_t cap, n; } idset;   /* open addressing, key + 1 stored (0 = empty) */
+static void idset_init(idset* s, size_t cap) {
+  size_t c = 64;
+  while (c < cap * 2) c <<= 1;
+  s->k = (uint64_t*)calloc(c, sizeof(uint64_t));
+  s->cap = c;
+  s->n = 0;
+}
+static void idset_grow(idset* s);
+static int idset_insert(idset* s, uint64_t id) { /* 1 if newly inserted */
+  if ((s->n + 1) * 2 > s->cap) idset_grow(s);
+  size_t h = (size_t)((id * 0x9E3779B97F4A7C15ULL) >> 17) & (s->cap - 1);
+  for (;;) {
+    if (s->k[h] == 0) { s->k[h] = id + 1; s->n++; return 1; }
+    if (s->k[h] == id + 1) return 0;
+    h = (h + 1) & (s->cap - 1);
+  }
+}
+static int idset_contains(const idset* s, uint64_t id) {
+  size_t h = (size_t)((id * 0x9E3779B97F4A7C15ULL) >> 17) & (s->cap - 1);
+  for (;;) {
+    if (s->k[h] == 0) return 0;
+    if (s->k[h] == id + 1) return 1;
+    h = (h + 1) & (s->cap - 1);
+  }
+}
+static void idset_grow(idset* s) {
+  idset o = *s;
+  s->cap = o.cap * 2;
+  s->k = (uint64_t*)calloc(s->cap, sizeof(uint64_t));
+  s->n = 0;
+  for (size_t i = 0; i < o.cap; ++i)
+    if (o.k[i]) idset_insert(s, o.k[i] - 1);
+  free(o.k);
+}
+
+typedef struct { uint32_t ham; uint64_t id; } bridge_key;
+typedef struct { bridge_key* a; size_t n, cap; } bridge_heap;   /* min-heap on (hamming, id) */
+static int bridge_less(bridge_key x, bridge_key y) { return x.ham < y.ham || (x.ham == y.ham && x.id < y.id); }
+static void bridge_push(bridge_heap* h, bridge_key c) {
+  if (h->n == h->cap) { h->cap = h->cap ? h->cap * 2 : 256; h->a = (bridge_key*)realloc(h->a, h->cap * sizeof(bridge_key)); }
+  size_t i = h->n++;
+  while (i > 0) {
+    size_t p = (i - 1) / 2;
+    if (!bridge_less(c, h->a[p])) break;
+    h->a[i] = h->a[p];
+    i = p;
+  }
+  h->a[i] = c;
+}
+static bridge_key bridge_pop(bridge_heap* h) {
+  bridge_key top = h->a[0], last = h->a[--h->n];
+  size_t i = 0;
+  for (;;) {
+    size_t l = 2 * i + 1, r = l + 1;
+    if (l >= h->n) break;
+    size_t c = (r < h->n && bridge_less(h->a[r], h->a[l])) ? r : l;
+    if (!bridge_less(h->a[c], last)) break;
+    h->a[i] = h->a[c];
+    i = c;
+  }
+  if (h->n) h->a[i] = last;
+  return top;
+}
+
+static int allowed_contains(const uint64_t* c, size_t n, uint64_t id) {
+  size_t lo = 0, hi = n;
+  while (lo < hi) {
+    size_t mid = lo + (hi - lo) / 2;
+    if (c[mid] < id) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && c[lo] == id;
+}
+
+typedef struct {
+  const hxo_index* ix;
+  const float* q;
+  float qh;
+  heap frontier, top;   /* min-heap / max-heap of cand (oracle slots) */
+  idset scored;
+  size_t beam_width;
+  hxo_filtered_stats* st;
+} fg_score;
+
+/* restricted_candidate_keys (:615-659) + restricted_score_keys (:661-704) for `ids` (already de-duplicated by the caller) */
+static int fg_score_ids(fg_score* f, const uint64_t* ids, size_t n) {
+  size_t nkeys = 0;
+  uint32_t* slots = (uint32_t*)malloc((n + 1) * sizeof(uint32_t));
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t s = slot_of(f->ix, ids[i]);
+    f->st->simhash_row_requests++;
+    if (s == UINT32_MAX || !f->ix->has_vec[s]) continue;                      /* absent candidate: skipped */
+    if (!f->ix->simhash || !f->ix->has_simhash[s]) { free(slots); return HXO_ERR_INVARIANT_VIOLATION; }   /* missing_simhash_error */
+    if (idset_contains(&f->scored, ids[i])) continue;                         /* keyed.retain(!scored) */
+    slots[nkeys++] = s;
+  }
+  if (nkeys) {
+    f->st->vector_payload_requests += nkeys;
+    for (size_t i = 0; i < nkeys; ++i) {
+      float d = dist_q(f->ix, f->q, f->qh, slots[i]);
+      int rc = hxo_score_validate(&d);
+      if (rc) { free(slots); return rc; }
+      f->st->distance_computations++;
+      cand c = {d, slots[i]};
+      idset_insert(&f->scored, f->ix->ids[slots[i]]);
+      heap_push(f->ix, &f->frontier, 0, c);
+      heap_push(f->ix, &f->top, 1, c);
+      if (f->top.n > f->beam_width) heap_pop(f->ix, &f->top, 1);
+    }
+  }
+  free(slots);
+  return HXO_OK;
+}
+
+/* restricted_enqueue_bridges (:706-751) */
+static int fg_enqueue_bridges(const hxo_index* ix, uint64_t qsim, const uint64_t* ids, size_t n, idset* queued,
+                              bridge_heap* bh, hxo_filtered_stats* st) {
+  for (size_t i = 0; i < n; ++i) {
+    if (!idset_insert(queued, ids[i])) continue;
+    const uint32_t s = slot_of(ix, ids[i]);
+    st->simhash_row_requests++;
+    if (s == UINT32_MAX || !ix->simhash || !ix->has_simhash[s]) return HXO_ERR_INVARIANT_VIOLATION;   /* mandatory companion */
+    bridge_key b = {(uint32_t)__builtin_popcountll(ix->simhash[s] ^ qsim), ids[i]};
+    bridge_push(bh, b);
+    st->bridge_frontier_pushes++;
+  }
+  return HXO_OK;
+}
+
+/* FilteredGraphBudgets::with_beam_percent (:232-260) */
+void hxo_filtered_budgets(uint32_t k_req, uint32_t ef, uint32_t beam_percent, size_t n_cand, hxo_filtered_budgets_t* b) {
+  const size_t k = k_req < n_cand ? k_req : n_cand;
+  if (beam_percent == 0) beam_percent = 150;                          /* FILTERED_BEAM_PERCENT */
+  if (ef == 0) ef = k_req > 100 ? k_req : 100;
+  size_t ef_filtered = (size_t)ef * beam_percent / 100;
+  if (ef_filtered < k * 4) ef_filtered = k * 4;
+  if (ef_filtered > n_cand) ef_filtered = n_cand;
+  b->ef_filtered = ef_filtered;
+  b->routing_rows = ef_filtered * 16;
+  b->bridge_rows = ef_filtered * 8;
+  b->vector_payloads = n_cand < 800 ? n_cand : 800;
+  b->sampled_seeds = n_cand < 64 ? n_cand : 64;
+}
+
+int hxo_search_filtered_graph(const hxo_index* ix, const float* query, uint32_t k_req, uint32_t ef, uint32_t beam_percent,
+                              const uint64_t* cand_ids, size_t n_cand, uint64_t query_simhash, uint64_t* out_ids,
+                              float* out_scores, uint32_t* out_count, hxo_filtered_stats* stats) {
+  hxo_filtered_budgets_t b;
+  hxo_filtered_budgets(k_req, ef, beam_percent, n_cand, &b);
+  return hxo_search_filtered_graph_budgets(ix, query, k_req, &b, cand_ids, n_cand, query_simhash, out_ids, out_scores,
+                                           out_count, stats);
+}
+
+int hxo_search_filtered_graph_budgets(const hxo_index* ix, const float* query, uint32_t k_req,
+                                      const hxo_filtered_budgets_t* budgets, const uint64_t* cand_ids, size_t n_cand,
+                                      uint64_t query_simhash, uint64_t* out_ids, float* out_scores, uint32_t* out_count,
+                                      hxo_filtered_stats* stats) {
+  hxo_filtered_stats local;
+  if (!stats) stats = &local;
+  memset(stats, 0, sizeof(*stats));
+  *out_count = 0;
+  if (k_req == 0 || n_cand == 0) return n_cand == 0 ? HXO_OK : HXO_ERR_INVALID_PARAMETER;
+  if (n_cand > 1000000) return HXO_ERR_QUERY;
+  const size_t k = k_req < n_cand ? k_req : n_cand;                   /* RestrictedResultCount (:200-213) */
+  if (k > 800) return HXO_ERR_QUERY;
+  if (!ix->populated) return HXO_OK;
+  const size_t ef_filtered = budgets->ef_filtered, routing_rows = budgets->routing_rows, bridge_rows = budgets->bridge_rows;
+  const size_t vector_payloads = budgets->vector_payloads, sampled_seeds = budgets->sampled_seeds;
+  const uint64_t entry = ix->entry_id;
+  const int entry_allowed = allowed_contains(cand_ids, n_cand, entry);
+
+  fg_score f;
+  memset(&f, 0, sizeof(f));
+  f.ix = ix;
+  f.q = query;
+  f.qh = hxo_header(ix->metric, query, ix->dim);
+  f.beam_width = ef_filtered;
+  f.st = stats;
+  idset_init(&f.scored, 1024);
+  idset attempted, expanded, queued, eligible_seen;
+  idset_init(&attempted, 1024);
+  idset_init(&expanded, 1024);
+  idset_init(&queued, 1024);
+  idset_init(&eligible_seen, 256);
+  bridge_heap bh = {0, 0, 0};
+  uint64_t* buf = (uint64_t*)malloc((sampled_seeds + 2) * sizeof(uint64_t));
+  uint64_t* routing = (uint64_t*)malloc(17 * sizeof(uint64_t));
+  uint64_t* bridges = (uint64_t*)malloc(257 * sizeof(uint64_t));
+  size_t elig_cap = 1024, rej_cap = 1024, n_elig = 0, n_rej = 0;
+  uint64_t* eligible = (uint64_t*)malloc(elig_cap * sizeof(uint64_t));
+  uint64_t* rejected = (uint64_t*)malloc(rej_cap * sizeof(uint64_t));
+  int rc = HXO_OK;
+
+  /* seeds: the evenly spaced sample, then the entry point when it is a candidate; truncated to the payload budget */
+  size_t n_init = hxo_deterministic_sample_ids(cand_ids, n_cand, sampled_seeds, buf);
+  for (size_t i = 0; i < n_init; ++i) idset_insert(&attempted, buf[i]);
+  if (entry_allowed && idset_insert(&attempted, entry)) buf[n_init++] = entry;
+  if (n_init > vector_payloads) n_init = vector_payloads;
+  /* (keys are resolved before the truncate in the reference; an id without a vector drops out of the key list, which
+   * only matters when the budget truncates — restated in the same order: resolve, then truncate) */
+  {
+    size_t w = 0;
+    for (size_t i = 0; i < n_init; ++i) {
+      const uint32_t s = slot_of(ix, buf[i]);
+      if (s == UINT32_MAX || !ix->has_vec[s]) { stats->simhash_row_requests++; continue; }
+      buf[w++] = buf[i];
+    }
+    n_init = w;
+  }
+  rc = fg_score_ids(&f, buf, n_init);
+  if (!rc && !entry_allowed) rc = fg_enqueue_bridges(ix, query_simhash, &entry, 1, &queued, &bh, stats);
+
+#define FG_CLASSIFY(node_slot)                                                                          \
+  do {                                                                                                  \
+    if (ix->has_row0[node_slot]) {                                                                      \
+      const uint32_t* row = ix->nbr0 + (size_t)(node_slot) * ix->stride0;                               \
+      for (uint32_t j = 0; j < ix->deg0[node_slot]; ++j) {                                              \
+        const uint64_t nid = ix->ids[row[j]];                                                           \
+        if (allowed_contains(cand_ids, n_cand, nid)) {                                                  \
+          if (!idset_contains(&attempted, nid) && idset_insert(&eligible_seen, nid)) {                  \
+            if (n_elig == elig_cap) { elig_cap *= 2; eligible = (uint64_t*)realloc(eligible, elig_cap * sizeof(uint64_t)); } \
+            eligible[n_elig++] = nid;                                                                   \
+          }                                                                                             \
+        } else {                                                                                        \
+          if (n_rej == rej_cap) { rej_cap *= 2; rejected = (uint64_t*)realloc(rejected, rej_cap * sizeof(uint64_t)); } \
+          rejected[n_rej++] = nid;                                                                      \
+        }                                                                                               \
+      }                                                                                                 \
+    }                                                                                                   \
+  } while (0)
+
+  while (!rc) {
+    if (stats->vector_payload_requests >= vector_payloads) { stats->termination = HXO_FG_VECTOR_BUDGET; break; }
+    if (bh.n == 0 && f.top.n >= ef_filtered && f.frontier.n && f.top.n &&
+        cand_less(ix, f.top.a[0], f.frontier.a[0])) {               /* next > worst */
+      stats->termination = HXO_FG_BEAM_COMPLETE;
+      break;
+    }
+    size_t n_routing = 0;
+    while (n_routing < 16 && f.frontier.n) {
+      cand c = heap_pop(ix, &f.frontier, 0);
+      if (idset_insert(&expanded, ix->ids[c.slot])) routing[n_routing++] = ix->ids[c.slot];
+    }
+    if (n_routing == 0 && bh.n == 0) { stats->termination = HXO_FG_EXHAUSTED; break; }
+    size_t routing_remaining = routing_rows > stats->routing_rows ? routing_rows - stats->routing_rows : 0;
+    if (routing_remaining == 0) { stats->termination = HXO_FG_ROUTING_BUDGET; break; }
+    if (n_routing > routing_remaining) n_routing = routing_remaining;
+    n_elig = 0;
+    n_rej = 0;
+    memset(eligible_seen.k, 0, eligible_seen.cap * sizeof(uint64_t));
+    eligible_seen.n = 0;
+    if (n_routing) {
+      stats->routing_rows += n_routing;
+      routing_remaining -= n_routing;
+      for (size_t i = 0; i < n_routing; ++i) {
+        const uint32_t s = slot_of(ix, routing[i]);
+        if (s != UINT32_MAX) FG_CLASSIFY(s);
+      }
+    }
+    rc = fg_enqueue_bridges(ix, query_simhash, rejected, n_rej, &queued, &bh, stats);
+    if (rc) break;
+    n_rej = 0;
+    const size_t bridge_remaining = bridge_rows > stats->bridge_rows ? bridge_rows - stats->bridge_rows : 0;
+    size_t bl = bridge_remaining < routing_remaining ? bridge_remaining : routing_remaining;
+    if (bl > 256) bl = 256;
+    if (bl > bh.n) bl = bh.n;
+    if (bl) {
+      for (size_t i = 0; i < bl; ++i) bridges[i] = bridge_pop(&bh).id;
+      stats->routing_rows += bl;
+      stats->bridge_rows += bl;
+      for (size_t i = 0; i < bl; ++i) {
+        const uint32_t s = slot_of(ix, bridges[i]);
+        if (s != UINT32_MAX) FG_CLASSIFY(s);
+      }
+      rc = fg_enqueue_bridges(ix, query_simhash, rejected, n_rej, &queued, &bh, stats);
+      if (rc) break;
+    } else if (n_routing == 0 && bh.n) {
+      stats->termination = HXO_FG_BRIDGE_BUDGET;
+      break;
+    }
+    const size_t vector_remaining = vector_payloads > stats->vector_payload_requests
+                                        ? vector_payloads - stats->vector_payload_requests : 0;
+    if (vector_remaining == 0) { stats->termination = HXO_FG_VECTOR_BUDGET; break; }
+    size_t take = vector_remaining < ef_filtered ? vector_remaining : ef_filtered;
+    if (n_elig > take) n_elig = take;
+    if (n_elig == 0) continue;
+    for (size_t i = 0; i < n_elig; ++i) idset_insert(&attempted, eligible[i]);
+    rc = fg_score_ids(&f, eligible, n_elig);
+  }
+#undef FG_CLASSIFY
+  if (!rc) {
+    qsort_r(f.top.a, f.top.n, sizeof(cand), cmp_cand_ctx, (void*)ix);
+    const size_t n = f.top.n < k ? f.top.n : k;
+    for (size_t i = 0; i < n; ++i) {
+      out_ids[i] = ix->ids[f.top.a[i].slot];
+      out_scores[i] = f.top.a[i].score;
+    }
+    *out_count = (uint32_t)n;
+  }
+  free(f.frontier.a); free(f.top.a); free(f.scored.k); free(attempted.k); free(expanded.k); free(queued.k);
+  free(eligible_seen.k); free(bh.a); free(buf); free(routing); free(bridges); free(eligible); free(rejected);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Build: V/mutation.rs:642-1005,1498-1591 + V/mod.rs:809-856
  * ------------------------------------------------------------------------------------------ */
 

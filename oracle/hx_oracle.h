@@ -127,6 +127,31 @@ int hxo_search(const hxo_index* idx, const float* query, uint32_t query_dim, uin
 int hxo_search_restricted(const hxo_index* idx, const float* query, uint32_t query_dim, uint32_t k,
                           const uint64_t* cand_ids, size_t n_cand, uint64_t* out_ids, float* out_scores,
                           uint32_t* out_count, uint64_t* distance_computations);
+
+/* Filter-aware (ACORN-style) restricted search, V/restricted.rs:837-1148, for generations without the SimHash routing
+ * directory: seeds = deterministic sample + entry point, bridges through non-members ranked by SimHash Hamming distance.
+ * Needs the node fingerprints (hxo_index_put_simhash) and the query's.  Approximate by design (the reference's recall
+ * gate for this branch is 0.92); restated so that the device walk can be compared with it step for step.
+ * Pinned by: the budgets' closed forms and deterministic_sample_ids literals (tests/production_support/vector/
+ * restricted.rs:532-551); SimHash VALUES are inputs (unpinned, see below). */
+enum { HXO_FG_NONE = 0, HXO_FG_VECTOR_BUDGET = 1, HXO_FG_BEAM_COMPLETE = 2, HXO_FG_EXHAUSTED = 3, HXO_FG_ROUTING_BUDGET = 4,
+       HXO_FG_BRIDGE_BUDGET = 5 };
+typedef struct {
+  uint64_t vector_payload_requests, distance_computations, routing_rows, bridge_rows, bridge_frontier_pushes,
+      simhash_row_requests;
+  uint32_t termination, reserved;
+} hxo_filtered_stats;
+typedef struct { size_t ef_filtered, routing_rows, bridge_rows, vector_payloads, sampled_seeds; } hxo_filtered_budgets_t;
+void hxo_filtered_budgets(uint32_t k, uint32_t ef, uint32_t beam_percent, size_t n_cand, hxo_filtered_budgets_t* out);
+int hxo_search_filtered_graph_budgets(const hxo_index* idx, const float* query, uint32_t k,
+                                      const hxo_filtered_budgets_t* budgets, const uint64_t* cand_ids, size_t n_cand,
+                                      uint64_t query_simhash, uint64_t* out_ids, float* out_scores, uint32_t* out_count,
+                                      hxo_filtered_stats* stats);
+int hxo_search_filtered_graph(const hxo_index* idx, const float* query, uint32_t k, uint32_t ef, uint32_t beam_percent,
+                              const uint64_t* cand_ids, size_t n_cand, uint64_t query_simhash, uint64_t* out_ids,
+                              float* out_scores, uint32_t* out_count, hxo_filtered_stats* stats);
+
+
 /* exact top-k over the whole index (ground truth for recall), same (score,id) rule. */
 int hxo_search_exact(const hxo_index* idx, const float* query, uint32_t k, uint64_t* out_ids,
                      float* out_scores, uint32_t* out_count);

@@ -40,6 +40,25 @@ def build(force: bool = False) -> Path:
     return _SO
 
 
+class FilteredBudgets(C.Structure):
+    """FilteredGraphBudgets (restricted.rs:220-260)."""
+    _fields_ = [(n, C.c_size_t) for n in ("ef_filtered", "routing_rows", "bridge_rows", "vector_payloads", "sampled_seeds")]
+
+
+class FilteredStats(C.Structure):
+    """The RestrictedSearchStats counters the filtered walk reports (restricted.rs)."""
+    _fields_ = [(n, C.c_uint64) for n in ("vector_payload_requests", "distance_computations", "routing_rows", "bridge_rows",
+                                          "bridge_frontier_pushes", "simhash_row_requests")] + \
+               [("termination", C.c_uint32), ("reserved", C.c_uint32)]
+
+    TERMINATION = {0: None, 1: "VectorBudget", 2: "BeamComplete", 3: "Exhausted", 4: "RoutingBudget", 5: "BridgeBudget"}
+
+    def as_dict(self):
+        d = {f: int(getattr(self, f)) for f, _ in self._fields_ if f != "reserved"}
+        d["termination"] = self.TERMINATION[d["termination"]]
+        return d
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("expansion_steps", C.c_uint64),
@@ -213,6 +232,11 @@ def lib():
     L.hxo_search_layer_greedy.argtypes = [C.c_void_p, fp, C.c_uint64, C.c_uint16, u64p]
     L.hxo_search.restype = C.c_int
     L.hxo_search.argtypes = [C.c_void_p, fp, C.c_uint32, C.c_uint32, C.c_uint32, u64p, fp, u32p, C.POINTER(Stats)]
+    L.hxo_filtered_budgets.restype = None
+    L.hxo_filtered_budgets.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, sz, C.POINTER(FilteredBudgets)]
+    L.hxo_search_filtered_graph_budgets.restype = C.c_int
+    L.hxo_search_filtered_graph_budgets.argtypes = [C.c_void_p, fp, C.c_uint32, C.POINTER(FilteredBudgets), u64p, sz, C.c_uint64,
+                                                    u64p, fp, C.POINTER(C.c_uint32), C.POINTER(FilteredStats)]
     L.hxo_search_restricted.restype = C.c_int
     L.hxo_search_restricted.argtypes = [C.c_void_p, fp, C.c_uint32, C.c_uint32, u64p, sz, u64p, fp, u32p, u64p]
     L.hxo_search_exact.restype = C.c_int
@@ -506,6 +530,25 @@ class Index:
         if secs < 0:
             raise OracleError(-1)
         return ids, sc, cnt, float(secs)
+
+    def search_filtered_graph(self, query, k, cand_ids, query_simhash, ef=0, beam_percent=150, budgets=None):
+        """restricted_filter_aware_search (restricted.rs:837-1148, directoryless).  Returns (ids, scores, stats dict)."""
+        qa, qp = _f32(query)
+        ca, cp = _u64(cand_ids)
+        b = FilteredBudgets()
+        if budgets is None:
+            self.L.hxo_filtered_budgets(k, ef, beam_percent, ca.size, C.byref(b))
+        else:
+            b.ef_filtered, b.routing_rows, b.bridge_rows, b.vector_payloads, b.sampled_seeds = budgets
+        ids = np.empty(max(k, 1), dtype=np.uint64)
+        sc = np.empty(max(k, 1), dtype=np.float32)
+        cnt = C.c_uint32(0)
+        st = FilteredStats()
+        self._ck(self.L.hxo_search_filtered_graph_budgets(self.h, qp, k, C.byref(b), cp, ca.size, int(query_simhash),
+                                                          ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                          sc.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt), C.byref(st)))
+        n = int(cnt.value)
+        return ids[:n].copy(), sc[:n].copy(), st.as_dict()
 
     def search_restricted(self, query, k, cand_ids):
         qa, qp = _f32(query)

@@ -487,3 +487,98 @@ def test_policy_path_with_neutral_parameters_reproduces_the_pinned_strict_search
                 for f in ("expansion_steps", "neighbors_examined", "distance_computations", "vectors_loaded"):
                     assert pst[f] == sst[f], (f, metric, mode)
                 assert pps["simhash_filtered"] == 0 and pps["rng_draws"] == 0
+
+
+# ---- filter-aware (ACORN) restricted search, directoryless generations (restricted.rs:837-1148) ------------------------------
+# Pinned by the reference's own directoryless tests (tests/production_support/vector/restricted.rs:313-423,964-1181):
+# the three-edge gulf, the SimHash-guided bridge, the missing-SimHash failure and the three budget terminations.
+def _fg_index(hxo, metric, nodes, entry, planes, drop_simhash=()):
+    ix = hxo.Index(metric, 2)
+    for node_id, vec, _ in nodes:
+        ix.put_vector(node_id, np.array(vec, np.float32))
+    for node_id, _, nbrs in nodes:
+        ix.put_neighbors(0, node_id, nbrs)
+    ix.set_entry(entry, 0)
+    keep = [n for n in nodes if n[0] not in drop_simhash]
+    ix.put_simhash(np.array([n[0] for n in keep], np.uint64),
+                   np.array([hxo.simhash_from_planes(planes, np.array(n[1], np.float32)) for n in keep], np.uint64))
+    return ix
+
+
+GULF = [(1, [0.0, 1.0], [2]), (2, [0.0, 1.0], [3]), (3, [0.0, 1.0], [1001]), (1001, [1.0, 0.0], [])]
+COMPETING = [(1, [0.0, 1.0], [2, 3]), (2, [1.0, 0.0], [1001]), (3, [-1.0, 0.0], [1002]), (1001, [1.0, 0.0], []),
+             (1002, [1.0, 0.0], [])]
+
+
+def test_filtered_graph_reference_kats(hxo):
+    planes = np.random.default_rng(42).standard_normal((64, 2)).astype(np.float32)   # any table: the KATs are sign-symmetric
+    q = np.array([1.0, 0.0], np.float32)
+    qs = hxo.simhash_from_planes(planes, q)
+    cand = np.arange(1000, 1257, dtype=np.uint64)                     # 257 ids: FilteredGraph plan (restricted.rs:426-453)
+    assert hxo.lib().hxo_restricted_plan(len(cand), 2) == 1
+    for metric in (hxo.COSINE, hxo.EUCLIDEAN, hxo.MANHATTAN):         # :964-990, :1022-1044
+        ix = _fg_index(hxo, metric, GULF, 1, planes)
+        ids, _, st = ix.search_filtered_graph(q, 10, cand, qs, ef=100)
+        assert ids.tolist() == [1001]
+        assert st["bridge_rows"] == 3 and st["bridge_frontier_pushes"] >= 3
+        assert st["vector_payload_requests"] == 1 and st["distance_computations"] == 1
+    # :1047-1100  budgets {ef_filtered 1, routing 2, bridge 2, payloads 1, seeds 0}: SimHash ranks node 2 before node 3
+    ix = _fg_index(hxo, hxo.COSINE, COMPETING, 1, planes)
+    ids, _, st = ix.search_filtered_graph(q, 1, np.arange(1001, 1258, dtype=np.uint64), qs, budgets=(1, 2, 2, 1, 0))
+    assert ids.tolist() == [1001] and st["bridge_rows"] == 2 and st["vector_payload_requests"] == 1
+    assert st["distance_computations"] == 1 and st["bridge_frontier_pushes"] >= 3
+    # :995-1020  a bridge neighbour without its SimHash fails closed
+    ix = _fg_index(hxo, hxo.COSINE, GULF, 1, planes, drop_simhash=(2,))
+    with pytest.raises(hxo.OracleError):
+        ix.search_filtered_graph(q, 10, cand, qs, ef=100)
+    # :1103-1181  explicit budgets record the exact termination reason
+    ix = _fg_index(hxo, hxo.COSINE, GULF, 1, planes)
+    for budgets, expected in (((1, 0, 1, 1, 0), "RoutingBudget"), ((1, 4, 0, 1, 0), "BridgeBudget"),
+                              ((1, 4, 2, 0, 0), "VectorBudget")):
+        ids, _, st = ix.search_filtered_graph(q, 1, cand, qs, budgets=budgets)
+        assert ids.tolist() == [] and st["termination"] == expected
+        assert st["routing_rows"] <= budgets[1] and st["bridge_rows"] <= budgets[2]
+    # FilteredGraphBudgets::with_beam_percent (:486-530): ef 100 -> ef_filtered 150, 64 seeds, 800 payloads
+    b = hxo.FilteredBudgets()
+    hxo.lib().hxo_filtered_budgets(10, 100, 150, 100_000, b)
+    assert (b.ef_filtered, b.routing_rows, b.bridge_rows, b.vector_payloads, b.sampled_seeds) == (150, 2400, 1200, 800, 64)
+
+
+def test_filtered_graph_recall_contract(hxo):
+    """exact_and_filter_aware_paths_enforce_membership_and_recall_budgets (restricted.rs:1224-1284): 512 x 8 circle with
+    skip links, allowed = ids not divisible by 3, ef = 64, k = 10 -> recall@10 >= 0.95 over the reference's eight queries."""
+    n, dim, k = 512, 8, 10
+    ix = hxo.Index(hxo.COSINE, dim, m=32, m0=64)
+    ids = np.arange(1, n + 1, dtype=np.uint64)
+
+    def vec(e):
+        a = 2.0 * math.pi * e / n
+        v = np.zeros(dim, np.float32)
+        v[0], v[1] = np.float32(math.cos(a)), np.float32(math.sin(a))
+        return v
+
+    rows = np.stack([vec(int(e)) for e in ids])
+    ix.put_vectors(ids, rows)
+    for e in ids:
+        e = int(e)
+        nb, off = set(), 1
+        while off < n:
+            nb.add((e - 1 + off) % n + 1)
+            nb.add((e - 1 + n - off % n) % n + 1)
+            off *= 2
+        nb.discard(e)
+        ix.put_neighbors(0, e, sorted(nb))
+    ix.set_entry(1, 0)
+    planes = np.random.default_rng(42).standard_normal((64, dim)).astype(np.float32)
+    ix.put_simhash(ids, np.array([hxo.simhash_from_planes(planes, r) for r in rows], np.uint64))
+    allowed = np.array([e for e in range(1, n + 1) if e % 3 != 0], dtype=np.uint64)
+    matched = 0
+    for qid in (1, 43, 87, 129, 211, 307, 401, 509):
+        q = vec(qid)
+        got, _, st = ix.search_filtered_graph(q, k, allowed, hxo.simhash_from_planes(planes, q), ef=64)
+        want, _ = ix.search_restricted(q, k, allowed)
+        assert all(int(g) % 3 != 0 for g in got)
+        assert st["routing_rows"] <= 96 * 16 and st["bridge_rows"] <= 96 * 8
+        assert st["distance_computations"] == st["vector_payload_requests"]
+        matched += len(set(got.tolist()) & set(want.tolist()))
+    assert matched / 80.0 >= 0.95

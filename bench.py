@@ -414,6 +414,7 @@ def measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=None, label_
                "kernel_ms_per_launch": round(kms2 / max(kl2, 1), 4),
                "scan_GBps": round(SB * count * (4 * dim + hdr) / (kms2 / max(kl2, 1) * 1e-3) / 1e9, 1) if kms2 else None,
                "reference_plan": hx.restricted_plan(count, dim),
+               "note": "one candidate range shared by the 64 queries of a step: rows are re-read from L2, so scan_GBps can exceed the HBM peak",
                "host_path_identical_to_device_path": bool(hi.tolist() == g_ids.tolist() and hs.tobytes() == g_sc.tobytes())}
         if ora is not None:
             nchk = 8 if count <= 10_000 else 2

@@ -1129,8 +1129,8 @@ static hx_status prepare_device_queries(hx_index* ix, HxScratch* s, const float*
 }
 
 // ---- HNSW launch ---------------------------------------------------------------------------------
-#define HX_TIE_POOL_N 8u
-#define HX_TIE_POOL_CAP 65536u
+#define HX_TIE_POOL_N 256u     // overflow regions shared by the queries of a launch (claimed on a query's 33rd tie)
+#define HX_TIE_POOL_CAP 4096u  // entries per region: a query can hold 32 + 4096 exact ties at its beam boundary
 // overflow regions of the tie stack + per-query error words on one scratch set
 static hx_status setup_tie_pool(HxScratch* s, HxRingArgs* rg, cudaStream_t stream) {
   hx_status rc;

@@ -44,7 +44,7 @@ struct HxSvcStream {
 struct hx_service {
   hx_index* ix = nullptr;
   uint32_t k = 0, ef = 0, cap = 0, mask = 0, max_batch = 0, dim = 0;
-  uint32_t min_batch = 16, busy_inflight = 64, window_ns = 30000;   // coalescing policy (see svc_dispatcher)
+  uint32_t min_batch = 16, busy_inflight = 24, window_ns = 30000;   // coalescing policy (see svc_dispatcher)
   bool zero_copy = false;                                          // the kernel reads the queries straight from the pinned ring
   HxCtaRingCfg cta{};
   int ctas_per_sm = 0;

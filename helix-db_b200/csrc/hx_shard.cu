@@ -78,7 +78,8 @@ struct hx_shard_group {
   DevBuf<float> o_sc;
   DevBuf<uint32_t> o_cnt;
   cudaStream_t stream = nullptr; // host-buffer entry points
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  bool kernel_timed = false;
   std::mutex mu;                 // one sharded call at a time per group (a collective is an ordered operation)
   float last_local_ms = 0.f, last_collective_ms = 0.f;
 };
@@ -119,6 +120,8 @@ extern "C" hx_status hx_shard_group_create(hx_index* shard, uint32_t n_shards, u
   if (e == cudaSuccess) e = cudaEventCreate(&g->ev1);
   if (e == cudaSuccess) e = cudaEventCreate(&g->evc0);
   if (e == cudaSuccess) e = cudaEventCreate(&g->evc1);
+  if (e == cudaSuccess) e = cudaEventCreate(&g->evk0);
+  if (e == cudaSuccess) e = cudaEventCreate(&g->evk1);
   if (e != cudaSuccess) {
     hx_set_error("shard group creation failed: %s", cudaGetErrorString(e));
     delete g;
@@ -155,7 +158,7 @@ extern "C" void hx_shard_group_destroy(hx_shard_group* g) {
   g->o_ids.release(); g->o_sc.release(); g->o_cnt.release();
   g->scr.destroy();
   if (g->stream) cudaStreamDestroy(g->stream);
-  for (cudaEvent_t ev : {g->ev0, g->ev1, g->evc0, g->evc1})
+  for (cudaEvent_t ev : {g->ev0, g->ev1, g->evc0, g->evc1, g->evk0, g->evk1})
     if (ev) cudaEventDestroy(ev);
   delete g;
 }
@@ -219,8 +222,9 @@ static hx_status sharded_device_locked(hx_shard_group* g, int32_t path, const fl
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(g->send.p + bl.off_cnt);
   HX_CUDA(cudaEventRecord(g->ev0, stream));
   if (path == HX_SHARD_DENSE) {
-    if ((rc = hx_dense_device(g->ix, &g->scr, d_queries, B, local, s_ids, s_sc, s_cnt, stream, nullptr, nullptr, nullptr)))
+    if ((rc = hx_dense_device(g->ix, &g->scr, d_queries, B, local, s_ids, s_sc, s_cnt, stream, g->evk0, g->evk1, nullptr)))
       return rc;
+    g->kernel_timed = true;
   } else if (path == HX_SHARD_HNSW) {
     if ((rc = hx_search_device(g->ix, d_queries, B, local, s_ids, s_sc, s_cnt, stream, nullptr))) return rc;
   } else {
@@ -252,6 +256,11 @@ static hx_status download(hx_shard_group* g, size_t B, uint32_t k_out, uint64_t*
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) == cudaSuccess) g->last_local_ms = ms;
   if (cudaEventElapsedTime(&ms, g->evc0, g->evc1) == cudaSuccess) g->last_collective_ms = ms;
+  if (g->kernel_timed && cudaEventElapsedTime(&ms, g->evk0, g->evk1) == cudaSuccess) {   // k_dense_scores alone
+    g->ix->last_kernel_ms = ms;
+    g->ix->last_kernel_launches = 1;
+  }
+  g->kernel_timed = false;
   return HX_OK;
 }
 

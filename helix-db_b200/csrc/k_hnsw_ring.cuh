@@ -66,9 +66,19 @@ __device__ __forceinline__ bool hx_tie_push(HxTie& t, uint64_t e, const HxRingAr
   }
   if (t.ovf_idx < 0) {
     int got = -1;
-    if (lane == 0)
-      for (uint32_t i = 0; i < rg.tie_pool_n; ++i)
-        if (atomicCAS(rg.tie_busy + i, 0u, 1u) == 0u) { got = (int)i; break; }   // never waits: no deadlock with the visited pool
+    if (lane == 0) {
+      // BOUNDED wait (about a millisecond): holders release their region at the end of their query, but an unbounded wait
+      // could deadlock against the visited-table pool (one query holding a region and waiting for a table, another the
+      // reverse).  When the wait runs out only THIS query fails.
+      for (uint32_t tries = 0; tries < 512u && got < 0; ++tries) {
+        const uint32_t start = (uint32_t)(clock64() >> 4) % (rg.tie_pool_n ? rg.tie_pool_n : 1u);
+        for (uint32_t j = 0; j < rg.tie_pool_n; ++j) {
+          const uint32_t i = (start + j) % rg.tie_pool_n;
+          if (atomicCAS(rg.tie_busy + i, 0u, 1u) == 0u) { got = (int)i; break; }
+        }
+        if (got < 0) __nanosleep(2000);
+      }
+    }
     got = __shfl_sync(0xffffffffu, got, 0);
     if (got < 0) return false;
     t.ovf_idx = got;

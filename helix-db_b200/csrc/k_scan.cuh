@@ -110,6 +110,22 @@ __device__ __forceinline__ void hx_topk_insert(uint64_t& mine, uint64_t key, uin
   else if (lane == pos) mine = key;
 }
 
+// top-32 of the union of two ascending 32-lists (lane i holds the i-th smallest of each): min(A[i], B[31-i]) is a
+// bitonic sequence made of exactly the 32 smallest keys; five compare-exchange stages sort it.  ~12 shuffles instead of
+// up to 32 insertions.
+__device__ __forceinline__ uint64_t hx_topk_merge32(uint64_t mine, uint64_t other, uint32_t lane) {
+  const unsigned FULL = 0xffffffffu;
+  const uint64_t rev = __shfl_sync(FULL, other, 31u - lane);
+  uint64_t v = mine < rev ? mine : rev;
+#pragma unroll
+  for (uint32_t s = 16; s > 0; s >>= 1) {
+    const uint64_t p = __shfl_xor_sync(FULL, v, s);
+    const bool lower = (lane & s) == 0u;
+    v = (lower == (v < p)) ? v : p;   // lower half keeps the min, upper half the max
+  }
+  return v;
+}
+
 template <int METRIC>
 static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan_topk(HxDev ix, HxScanArgs a, HxTopkArgs tk) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -157,13 +173,8 @@ static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan_topk(HxDev ix, 
     }
     __syncthreads();
     if (live && warp == 0) {   // merge the 8 warp lists (warp 0's own list is already in `mine`)
-      for (uint32_t w = 1; w < HX_SCAN_THREADS / 32; ++w)
-        for (uint32_t i = 0; i < HX_TOPK; ++i) {
-          const uint64_t c = s_lists[w][i];
-          if (c == HX_KEY_MAX) break;                    // lists are sorted: the rest is empty
-          if (c < __shfl_sync(FULL, mine, HX_TOPK - 1)) hx_topk_insert(mine, c, lane);
-          else break;                                    // sorted: nothing further in this list can enter
-        }
+#pragma unroll
+      for (uint32_t w = 1; w < HX_SCAN_THREADS / 32; ++w) mine = hx_topk_merge32(mine, s_lists[w][lane], lane);
     }
     if (warp == 0) {
       // every CTA of the grid row reports (an empty list when it had nothing to scan) so that the ticket count is exact
@@ -180,23 +191,13 @@ static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan_topk(HxDev ix, 
       __threadfence();
       uint64_t best = HX_KEY_MAX;
       const uint64_t* P = tk.partial + (size_t)q * tk.n_chunks * HX_TOPK;
-      for (uint32_t c = warp; c < tk.n_chunks; c += HX_SCAN_THREADS / 32) {
-        const uint64_t v = __ldcg(P + (size_t)c * HX_TOPK + lane);
-        for (uint32_t i = 0; i < HX_TOPK; ++i) {
-          const uint64_t x = __shfl_sync(FULL, v, i);
-          if (x >= __shfl_sync(FULL, best, HX_TOPK - 1)) break;   // sorted list: done with this chunk
-          hx_topk_insert(best, x, lane);
-        }
-      }
+      for (uint32_t c = warp; c < tk.n_chunks; c += HX_SCAN_THREADS / 32)
+        best = hx_topk_merge32(best, __ldcg(P + (size_t)c * HX_TOPK + lane), lane);
       s_lists[warp][lane] = best;
       __syncthreads();
       if (warp == 0) {
-        for (uint32_t w = 1; w < HX_SCAN_THREADS / 32; ++w)
-          for (uint32_t i = 0; i < HX_TOPK; ++i) {
-            const uint64_t c = s_lists[w][i];
-            if (c >= __shfl_sync(FULL, best, HX_TOPK - 1)) break;
-            hx_topk_insert(best, c, lane);
-          }
+#pragma unroll
+        for (uint32_t w = 1; w < HX_SCAN_THREADS / 32; ++w) best = hx_topk_merge32(best, s_lists[w][lane], lane);
         const uint32_t kk = (uint64_t)tk.k < n ? tk.k : (uint32_t)n;   // k' = min(k, |C|)
         const bool have = lane < kk && best != HX_KEY_MAX && a.q_status[q] == 0u;
         if (have) {

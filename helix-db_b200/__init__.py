@@ -144,6 +144,19 @@ class ServiceStats(C.Structure):
         return {f: int(getattr(self, f)) for f, _ in self._fields_ if f != "reserved"}
 
 
+class FilteredBudgets(C.Structure):
+    """FilteredGraphBudgets (restricted.rs:220-260)."""
+    _fields_ = [(n, C.c_uint32) for n in ("ef_filtered", "routing_rows", "bridge_rows", "vector_payloads", "sampled_seeds")]
+
+
+class FilteredStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("vector_payload_requests", "distance_computations", "routing_rows", "bridge_rows",
+                                          "bridge_frontier_pushes", "iterations", "kernel_launches", "reserved")]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_ if f != "reserved"}
+
+
 # every symbol include/helix_b200.h declares (checked by tests/test_abi_surface.py)
 ABI_SYMBOLS = [
     "hx_index_create", "hx_index_destroy", "hx_index_load_vectors", "hx_index_generate_vectors",
@@ -163,6 +176,7 @@ ABI_SYMBOLS = [
     "hx_search_sharded", "hx_search_restricted_sharded", "hx_shard_group_last_ms",
     "hx_index_upsert_vectors", "hx_index_set_levels", "hx_index_upsert_neighbor_rows", "hx_index_delete_vectors",
     "hx_index_load_upper_vector_rows", "hx_index_set_version", "hx_index_get_version", "hx_index_build_ex",
+    "hx_filtered_budgets", "hx_search_filtered_graph",
 ]
 
 _lib = None
@@ -287,6 +301,11 @@ def load_library():
     L.hx_service_search.argtypes = [vp, fp, u64p, fp, u32p]
     L.hx_service_get_stats.restype = C.c_int32
     L.hx_service_get_stats.argtypes = [vp, C.POINTER(ServiceStats)]
+    L.hx_filtered_budgets.restype = None
+    L.hx_filtered_budgets.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(FilteredBudgets)]
+    L.hx_search_filtered_graph.restype = C.c_int32
+    L.hx_search_filtered_graph.argtypes = [vp, fp, sz, C.POINTER(_Params), C.POINTER(FilteredBudgets), u64p, sz, u64p, u64p,
+                                           fp, u32p, C.POINTER(FilteredStats)]
     L.hx_index_build_ex.restype = C.c_int32
     L.hx_index_build_ex.argtypes = [vp, u16p, C.c_uint64, C.c_int32]
     L.hx_index_upsert_vectors.restype = C.c_int32
@@ -815,6 +834,30 @@ class VectorIndex:
                                         ids.ctypes.data_as(C.POINTER(C.c_uint64)),
                                         sc.ctypes.data_as(C.POINTER(C.c_float)),
                                         cnt.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(st)))
+        return ids, sc, cnt
+
+    def search_filtered_graph(self, queries, params: SearchParams, allowed: RestrictedVectorCandidates, query_simhash=None,
+                              budgets=None, stats=None):
+        """hx_search_filtered_graph: the reference's filter-aware (ACORN) walk, restricted.rs:837-1148 (approximate)."""
+        qa, qp = _f32(queries)
+        B = qa.size // self.dim
+        cp = params._c()
+        k = cp.k
+        ca, cpnt = _u64(allowed.ids)
+        ids = np.zeros((B, k), dtype=np.uint64)
+        sc = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        bp = None
+        if budgets is not None:
+            bb = FilteredBudgets(*[int(x) for x in budgets])
+            bp = C.byref(bb)
+        sp = None
+        if query_simhash is not None:
+            sa, sp = _u64(query_simhash)
+        st = stats if stats is not None else FilteredStats()
+        _ck(self.L.hx_search_filtered_graph(self.h, qp, B, C.byref(cp), bp, cpnt, ca.size, sp,
+                                            ids.ctypes.data_as(C.POINTER(C.c_uint64)), sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                            cnt.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(st)))
         return ids, sc, cnt
 
     def cache_candidates(self, allowed: "RestrictedVectorCandidates") -> "DeviceCandidates":

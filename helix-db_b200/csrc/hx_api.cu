@@ -16,6 +16,7 @@
 #include "k_hnsw_ring.cuh"
 #include "k_hnsw_policy.cuh"
 #include "k_scan.cuh"
+#include "k_filtered.cuh"
 #include "k_util.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -230,6 +231,7 @@ void HxScratch::destroy() {
   d_cand_slots.release(); d_out_ids.release(); d_cand_ids.release(); d_cand_offsets.release(); d_keys.release();
   d_stamps.release();
   d_tiepool.release(); d_tiebusy.release(); d_qerr.release(); h_qerr.release(); d_partial.release(); d_tickets.release();
+  d_fg_stamps.release(); d_fg_epochs.release(); d_fg_bridge.release(); d_fg_elig.release(); d_fg_bits.release(); d_fg_seed.release();
   d_vtab.release(); d_vpool.release(); d_vbusy.release(); d_prof.release(); d_pstats.release(); d_qsim.release();
   for (auto& m : misc) m.release();
   h_ids.release(); h_cand_offsets.release(); h_scores.release(); h_queries.release(); h_qhdr.release();
@@ -2802,3 +2804,4 @@ extern "C" hx_status hx_last_kernel_ms(hx_index* ix, float* ms, uint32_t* launch
 
 #include "hx_service.inl"
 #include "hx_mirror.inl"
+#include "hx_filtered.inl"

@@ -105,6 +105,11 @@ struct HxScratch {
   DevBuf<uint64_t> d_partial;                  // fused scan + top-k: per-CTA lists
   DevBuf<uint32_t> d_tickets;                  // ... and the per-query CTA tickets (self-resetting)
   size_t tickets_zeroed = 0;
+  // filtered (ACORN) walk: per-CTA stamp arrays [grid][n] + epochs, bridge frontiers, eligible lists, candidate bitmap, seeds
+  DevBuf<uint32_t> d_fg_stamps, d_fg_epochs, d_fg_elig, d_fg_bits, d_fg_seed;
+  DevBuf<uint64_t> d_fg_bridge;
+  size_t fg_stamp_rows = 0;
+  uint32_t fg_stamp_grid = 0;
   DevBuf<uint32_t> d_qerr;                     // per-query error flags
   PinBuf<uint32_t> h_qerr;
   DevBuf<unsigned long long> d_prof;   // HX_PHASE_PROF diagnostics

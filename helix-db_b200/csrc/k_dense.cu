@@ -90,6 +90,20 @@ __device__ __forceinline__ void hxd_tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load without the wait: the caller overlaps it with work on the previous chunk, then hxd_tmem_wait_ld()
+__device__ __forceinline__ void hxd_tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void hxd_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // 32 lanes x 8 consecutive fp32 columns
 __device__ __forceinline__ void hxd_tmem_ld8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -257,10 +271,29 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // column (10k SASS instructions, instruction-cache bound: tensor pipe 9 %).  Columns that beat the running
         // threshold are only STAGED (two predicated shared-memory stores); the single insertion-network instance below
         // drains the staging area.
+        // round 2: the accumulator is read 32 columns at a time and DOUBLE BUFFERED — the tcgen05.ld of chunk i+1 is in
+        // flight while chunk i is tested — instead of sixteen serialised x8 loads per half tile: with two epilogue warps
+        // per scheduler the TMEM round trip (not the instruction count) was what kept the tensor pipe at 54 % (ncu,
+        // profiles/r02_ncu_dense_v1_raw.txt)
+        auto drain = [&]() {   // the insertion network (one instance per call site: eight in all)
 #pragma unroll 1
-        for (uint32_t c0 = 0; c0 < HXD_BN / 2 && !(a.debug & 1u); c0 += 8) {
-          uint32_t rr[8];
-          hxd_tmem_ld8(taddr + c0, rr);
+          for (uint32_t i = 0; i < cnt; ++i) {
+            const float tvi = stg_t[i * HXD_EPI_THREADS + et];
+            if (tvi > bt[HXD_T - 1]) {
+              bt[HXD_T - 1] = tvi;
+              bs[HXD_T - 1] = stg_s[i * HXD_EPI_THREADS + et];
+#pragma unroll
+              for (int j = HXD_T - 1; j > 0; --j)
+                if (bt[j] > bt[j - 1]) {
+                  const float tf = bt[j]; bt[j] = bt[j - 1]; bt[j - 1] = tf;
+                  const uint32_t tsl = bs[j]; bs[j] = bs[j - 1]; bs[j - 1] = tsl;
+                }
+            }
+          }
+          cnt = 0;
+          thr = bt[HXD_T - 1];
+        };
+        auto test8 = [&](const uint32_t* rr, uint32_t c0, bool last) {   // eight columns against the running threshold
           const float4 x0 = ax4[(c0 >> 2)], x1 = ax4[(c0 >> 2) + 1];
           float tv[8];
           if (a.metric == HXM_COSINE) {
@@ -281,23 +314,21 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               stg_s[cnt * HXD_EPI_THREADS + et] = slot0 + c0 + e;
               ++cnt;
             }
-          if (cnt > HXD_STAGE_CAP - 8 || c0 + 8 >= HXD_BN / 2) {   // drain: the only instance of the insertion network
+          if (cnt > HXD_STAGE_CAP - 8 || last) drain();
+        };
+        if (!(a.debug & 1u)) {
+          uint32_t ra[32], rb[32];
+          hxd_tmem_ld32_nowait(taddr, ra);
+          hxd_tmem_wait_ld();
 #pragma unroll 1
-            for (uint32_t i = 0; i < cnt; ++i) {
-              const float tvi = stg_t[i * HXD_EPI_THREADS + et];
-              if (tvi > bt[HXD_T - 1]) {
-                bt[HXD_T - 1] = tvi;
-                bs[HXD_T - 1] = stg_s[i * HXD_EPI_THREADS + et];
-#pragma unroll
-                for (int j = HXD_T - 1; j > 0; --j)
-                  if (bt[j] > bt[j - 1]) {
-                    const float tf = bt[j]; bt[j] = bt[j - 1]; bt[j - 1] = tf;
-                    const uint32_t tsl = bs[j]; bs[j] = bs[j - 1]; bs[j - 1] = tsl;
-                  }
-              }
-            }
-            cnt = 0;
-            thr = bt[HXD_T - 1];
+          for (uint32_t c0 = 0; c0 < HXD_BN / 2; c0 += 64) {
+            hxd_tmem_ld32_nowait(taddr + c0 + 32, rb);            // in flight while chunk `ra` is tested
+            test8(ra, c0, false); test8(ra + 8, c0 + 8, false); test8(ra + 16, c0 + 16, false); test8(ra + 24, c0 + 24, false);
+            hxd_tmem_wait_ld();
+            if (c0 + 64 < HXD_BN / 2) hxd_tmem_ld32_nowait(taddr + c0 + 64, ra);
+            test8(rb, c0 + 32, false); test8(rb + 8, c0 + 40, false); test8(rb + 16, c0 + 48, false);
+            test8(rb + 24, c0 + 56, c0 + 64 >= HXD_BN / 2);
+            hxd_tmem_wait_ld();
           }
         }
         hxd_fence_before();
@@ -448,8 +479,14 @@ hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t
   const uint32_t kprime = (uint32_t)std::min<size_t>(std::max<uint32_t>(4 * k, 64), std::min<size_t>(800, n));
   // runs per m-tile: enough units to fill the SMs, and enough that one run's best-T comfortably covers its share of the
   // k' nominees even when the true neighbours cluster in id space (8x head-room)
-  const uint32_t n_split = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_tiles,
+  uint32_t n_split = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_tiles,
       std::max<size_t>(std::max<size_t>(4, (size_t)ix->sm_count / m_tiles), (8 * (size_t)kprime + HXD_T - 1) / HXD_T)));
+  // the grid is one persistent CTA per SM: make the number of work units a multiple of it so that the last wave is full
+  // (1024 queries = 8 m-tiles: 32 runs = 256 units = 1.73 waves of 148 CTAs, the tensor pipe idles 13 % of the launch;
+  // 37 runs = 296 units = exactly 2 waves)
+  if ((size_t)m_tiles * n_split > (size_t)ix->sm_count)
+    for (uint32_t cand = n_split; cand <= std::min<uint32_t>(n_tiles, 2 * n_split); ++cand)
+      if (((size_t)m_tiles * cand) % (size_t)ix->sm_count == 0) { n_split = cand; break; }
   const size_t nkeys = B * (size_t)n_split * 2 * HXD_T;
   int mi = 0;
   bool grew = false;

@@ -716,6 +716,7 @@ __device__ __forceinline__ uint32_t hx_rbeam_admit_batch(HxRegBeam<NB>& b, uint3
   const bool was_full = old_len == ef;
   const uint32_t old_wmax = wmax;
   uint32_t q[NB];
+  __syncwarp();   // every lane has finished its binary searches over `stage` before any lane rewrites it (racecheck)
 #pragma unroll
   for (int r = 0; r < NB; ++r) {
     const uint32_t p = (uint32_t)r * 32u + lane;
@@ -1120,7 +1121,8 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
         }
       }
       if (prof) { pt5 = clock64(); pa[4] += pt5 - pt4; }
-      // no barrier here: only warp 0 touches the beam; the next barrier orders the reuse of frontier / fdist
+      if (warp == 0) __syncwarp();   // admission's reads of frontier[] before the next expansion rewrites it (racecheck)
+      // no CTA barrier here: only warp 0 touches the beam; the next barrier orders the reuse of frontier / fdist
     }
     if (prof) {
       for (int i = 0; i < 6; ++i) atomicAdd(rg.prof + i, pa[i]);

@@ -127,7 +127,7 @@ __device__ __forceinline__ uint64_t hx_topk_merge32(uint64_t mine, uint64_t othe
 }
 
 template <int METRIC>
-static __global__ void __launch_bounds__(HX_SCAN_THREADS) k_scan_topk(HxDev ix, HxScanArgs a, HxTopkArgs tk) {
+static __global__ void __launch_bounds__(HX_SCAN_THREADS, 4) k_scan_topk(HxDev ix, HxScanArgs a, HxTopkArgs tk) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* sq = reinterpret_cast<float*>(smem);
   __shared__ uint64_t s_lists[HX_SCAN_THREADS / 32][HX_TOPK];

@@ -297,6 +297,28 @@ hx_status hx_search_restricted_multi(hx_index* idx, const float* queries, size_t
                                      const uint64_t* cand_offsets, uint64_t* out_ids,
                                      float* out_scores, uint32_t* out_counts, hx_stats* stats);
 
+/* ---- filter-aware (ACORN-style) restricted search (restricted.rs:837-1148) -------------------------------------
+ * The walk the reference plans for |C| > 256 (restricted.rs:426-453), for generations without the SimHash routing
+ * directory: seeds = the evenly spaced sample of the candidate set + the entry point when it is a candidate; the best
+ * scored candidates' layer-0 rows are routed 16 at a time; neighbours outside the candidate set become bridges ranked by
+ * SimHash Hamming distance to the query and are expanded (never scored) up to 256 at a time; at most 800 candidate vectors
+ * are scored.  Approximate by design (the reference gates it at recall 0.92); hx_search_restricted answers the same
+ * question exactly and is the better choice until |C| x row bytes dominates (bench.py reports the cross-over).
+ * Needs the node fingerprints (hx_index_load_simhash / hx_index_compute_simhash) and the queries' (given, or projected
+ * from the planes).  budgets == NULL: FilteredGraphBudgets::with_beam_percent(params, k, |C|, 150).  One candidate set for
+ * the B queries.  A neighbour without its SimHash row fails the call (InvariantViolation, "missing simhash"). */
+typedef struct { uint32_t ef_filtered, routing_rows, bridge_rows, vector_payloads, sampled_seeds; } hx_filtered_budgets_t;
+typedef struct {   /* RestrictedSearchStats counters, summed over the B queries */
+  uint64_t vector_payload_requests, distance_computations, routing_rows, bridge_rows, bridge_frontier_pushes, iterations,
+      kernel_launches, reserved;
+} hx_filtered_stats;
+void      hx_filtered_budgets(uint32_t k, uint32_t ef, uint32_t beam_percent /*0 => 150*/, uint64_t n_cand,
+                              hx_filtered_budgets_t* out);
+hx_status hx_search_filtered_graph(hx_index* idx, const float* queries, size_t B, const hx_search_params* p,
+                                   const hx_filtered_budgets_t* budgets, const uint64_t* cand_ids, size_t n_cand,
+                                   const uint64_t* query_simhash, uint64_t* out_ids, float* out_scores,
+                                   uint32_t* out_counts, hx_filtered_stats* stats);
+
 /* ---- device-resident candidate sets (prefilter reuse) ------------------------------------------------------
  * The reference's label / equality indexes are RoaringTreemap values tied to a snapshot
  * (encoding/v1/indexes/label.rs:10-14; SURVEY §8d: "allow label bitmaps to be cached device-side keyed by the same

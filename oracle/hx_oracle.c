@@ -1264,11 +1264,7 @@ int hxo_search_filtered_graph_budgets(const hxo_index* ix, const float* query, u
   /* seeds: the evenly spaced sample, then the entry point when it is a candidate; truncated to the payload budget */
   size_t n_init = hxo_deterministic_sample_ids(cand_ids, n_cand, sampled_seeds, buf);
   for (size_t i = 0; i < n_init; ++i) idset_insert(&attempted, buf[i]);
-  if (entry_allowed && idset_insert(&attempted, entry)) buf[n_init++] = entry;
-  if (n_init > vector_payloads) n_init = vector_payloads;
-  /* (keys are resolved before the truncate in the reference; an id without a vector drops out of the key list, which
-   * only matters when the budget truncates — restated in the same order: resolve, then truncate) */
-  {
+  {   /* restricted_candidate_keys: an id without a vector row has no key (:629-640) */
     size_t w = 0;
     for (size_t i = 0; i < n_init; ++i) {
       const uint32_t s = slot_of(ix, buf[i]);
@@ -1277,6 +1273,8 @@ int hxo_search_filtered_graph_budgets(const hxo_index* ix, const float* query, u
     }
     n_init = w;
   }
+  if (entry_allowed && idset_insert(&attempted, entry)) buf[n_init++] = entry;   /* :948-960 */
+  if (n_init > vector_payloads) n_init = vector_payloads;                        /* initial_keys.truncate (:961) */
   rc = fg_score_ids(&f, buf, n_init);
   if (!rc && !entry_allowed) rc = fg_enqueue_bridges(ix, query_simhash, &entry, 1, &queued, &bh, stats);
 

@@ -1,0 +1,99 @@
+"""The filter-aware (ACORN-style) restricted walk on the device (hx_search_filtered_graph, restricted.rs:837-1148) against
+the oracle's restatement — which is itself pinned by the reference's directoryless KATs (tests/test_oracle_kat.py).
+ids, order, score bits and the RestrictedSearchStats counters must be identical."""
+import math
+
+import numpy as np
+import pytest
+
+import helix_db_b200 as hx
+from oracle import hxo
+from hx_testutil import mirror_from_oracle
+from test_gpu_parity import build_pair
+from test_oracle_kat import COMPETING, GULF, _fg_index
+
+pytestmark = pytest.mark.gpu
+
+
+def _mirror_with_simhash(ora, gm, dim, planes, ids, rows, drop=()):
+    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("fg", "embedding", dim))
+    mirror_from_oracle(gpu, ora)
+    keep = [i for i in range(len(ids)) if int(ids[i]) not in drop]
+    bits = np.array([hxo.simhash_from_planes(planes, rows[i]) for i in keep], dtype=np.uint64)
+    gpu.load_simhash(ids[keep], bits)
+    return gpu
+
+
+def test_reference_kats_through_the_c_abi():
+    planes = np.random.default_rng(42).standard_normal((64, 2)).astype(np.float32)
+    q = np.array([[1.0, 0.0]], np.float32)
+    qs = np.array([hxo.simhash_from_planes(planes, q[0])], dtype=np.uint64)
+    cand = hx.RestrictedVectorCandidates(np.arange(1000, 1257, dtype=np.uint64))
+    for gm, om in ((hx.Metric.Cosine, hxo.COSINE), (hx.Metric.Euclidean, hxo.EUCLIDEAN), (hx.Metric.Manhattan, hxo.MANHATTAN)):
+        ora = _fg_index(hxo, om, GULF, 1, planes)
+        ids = np.array([n[0] for n in GULF], np.uint64)
+        rows = np.array([n[1] for n in GULF], np.float32)
+        gpu = _mirror_with_simhash(ora, gm, 2, planes, ids, rows)
+        st = hx.FilteredStats()
+        gi, gs, gc = gpu.search_filtered_graph(q, hx.SearchParams.new(10), cand, qs, stats=st)
+        assert gc[0] == 1 and gi[0, 0] == 1001                               # restricted.rs tests :964-990
+        assert st.bridge_rows == 3 and st.vector_payload_requests == 1 and st.distance_computations == 1
+        assert st.bridge_frontier_pushes >= 3
+        gpu.close()
+    ora = _fg_index(hxo, hxo.COSINE, COMPETING, 1, planes)
+    ids = np.array([n[0] for n in COMPETING], np.uint64)
+    rows = np.array([n[1] for n in COMPETING], np.float32)
+    gpu = _mirror_with_simhash(ora, hx.Metric.Cosine, 2, planes, ids, rows)
+    st = hx.FilteredStats()
+    gi, gs, gc = gpu.search_filtered_graph(q, hx.SearchParams.new(1), hx.RestrictedVectorCandidates(np.arange(1001, 1258, dtype=np.uint64)),
+                                           qs, budgets=(1, 2, 2, 1, 0), stats=st)
+    assert gc[0] == 1 and gi[0, 0] == 1001 and st.bridge_rows == 2 and st.vector_payload_requests == 1   # :1047-1100
+    gpu.close()
+    # a bridge neighbour without its SimHash fails closed (:995-1020)
+    ora = _fg_index(hxo, hxo.COSINE, GULF, 1, planes)
+    ids = np.array([n[0] for n in GULF], np.uint64)
+    rows = np.array([n[1] for n in GULF], np.float32)
+    gpu = _mirror_with_simhash(ora, hx.Metric.Cosine, 2, planes, ids, rows, drop=(2,))
+    with pytest.raises(hx.HelixDbError) as e:
+        gpu.search_filtered_graph(q, hx.SearchParams.new(10), cand, qs)
+    assert e.value.variant == "InvariantViolation" and "missing simhash" in str(e.value)
+    gpu.close()
+
+
+@pytest.mark.parametrize("gm,om,n,dim,sel", [(hx.Metric.Cosine, hxo.COSINE, 4000, 48, 3), (hx.Metric.Euclidean, hxo.EUCLIDEAN, 3000, 96, 10),
+                                             (hx.Metric.Cosine, hxo.COSINE, 2500, 768, 2)])
+def test_walk_equals_the_oracle_on_hnsw_graphs(gm, om, n, dim, sel):
+    rng = np.random.default_rng(61)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    gpu, ora = build_pair(gm, om, rows, m=8, m0=16, efc=60)
+    ids = np.arange(n, dtype=np.uint64)
+    planes = rng.standard_normal((64, dim)).astype(np.float32)
+    bits = np.array([hxo.simhash_from_planes(planes, r) for r in rows], dtype=np.uint64)
+    ora.put_simhash(ids, bits)
+    gpu.load_simhash(ids, bits)
+    cand_ids = ids[ids % sel == 1].copy()                                  # 1/sel of the corpus: plenty of bridging
+    cand = hx.RestrictedVectorCandidates(cand_ids)
+    B, k, ef = 40, 10, 64
+    q = rng.standard_normal((B, dim)).astype(np.float32)
+    qs = np.array([hxo.simhash_from_planes(planes, x) for x in q], dtype=np.uint64)
+    st = hx.FilteredStats()
+    gi, gs, gc = gpu.search_filtered_graph(q, hx.SearchParams.new(k).with_ef(ef), cand, qs, stats=st)
+    tot = dict(vector_payload_requests=0, distance_computations=0, routing_rows=0, bridge_rows=0, bridge_frontier_pushes=0)
+    hits = 0
+    for b in range(B):
+        oi, os_, ost = ora.search_filtered_graph(q[b], k, cand_ids, int(qs[b]), ef=ef)
+        assert gc[b] == len(oi) and gi[b, :gc[b]].tolist() == oi.tolist(), f"query {b}: ids differ"
+        assert gs[b, :gc[b]].tobytes() == os_.tobytes(), f"query {b}: score bits differ"
+        for f in tot:
+            tot[f] += ost[f]
+        ei, _ = ora.search_restricted(q[b], k, cand_ids)
+        hits += len(set(oi.tolist()) & set(ei.tolist()))
+    for f in tot:
+        assert getattr(st, f) == tot[f], f
+    assert hits / (B * k) >= 0.8                                             # approximate by design; membership is exact
+    assert all(int(x) % sel == 1 for x in gi[gc > 0][:, 0])
+    # projected query fingerprints (planes on the device) give the same answer
+    gpu.set_simhash_planes(planes)
+    gi2, gs2, gc2 = gpu.search_filtered_graph(q, hx.SearchParams.new(k).with_ef(ef), cand)
+    assert gi2.tolist() == gi.tolist() and gs2.tobytes() == gs.tobytes()
+    gpu.close()

@@ -114,6 +114,7 @@ __device__ void hxb_select_diverse(const HxDev& ix, const uint64_t* cand_key, ui
     }
     __syncthreads();
   }
+  __syncthreads();   // every thread has read *s_nsel at the loop's exit test before thread 0 rewrites it (racecheck)
   if (tid == 0) {   // back-fill with the closest remaining (mod.rs:842-853)
     uint32_t nsel = *s_nsel;
     for (uint32_t i = 0; i < ncand && nsel < m; ++i)

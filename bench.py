@@ -383,8 +383,27 @@ def measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=None, label_
         d.close()
 
     # ---- the reference's contiguous shapes: one candidate range shared by 64 queries ----
+    # each shape is answered twice: exactly (scan) and by the reference's own plan for |C| > 256, the filter-aware (ACORN)
+    # walk (restricted.rs:837-1148; needs node fingerprints: a stand-in hyperplane table when none is loaded)
     shapes = []
     SB = 64
+    acorn_ready = False
+    try:
+        ix.download_simhash(0, 1)
+        acorn_ready = True
+    except Exception:
+        try:
+            ix._bench_planes = np.random.default_rng(42).standard_normal((64, dim)).astype(np.float32)
+            ix.set_simhash_planes(ix._bench_planes)
+            ix.compute_simhash()
+            acorn_ready = True
+        except Exception:
+            acorn_ready = False
+    ora_sim = False
+
+    def hxo_simhash(planes, v):
+        from oracle import hxo as _h
+        return _h.simhash_from_planes(planes, v)
     sq = ix.generate_queries(SEED, SB, first_query=21_000_000, n_centroids=N_CENTROIDS, sigma=SIGMA, kind=KIND)
     d_sq = torch.from_numpy(sq).to(dev)
     s_ids = torch.zeros((SB, k), dtype=torch.int64, device=dev)
@@ -425,6 +444,39 @@ def measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=None, label_
                 ok = ok and g_ids[b, :len(ei)].tolist() == ei.tolist() and g_sc[b, :len(ei)].tobytes() == es.tobytes()
             ent["oracle_bit_exact"] = bool(ok)
             ent["cpu_port_qps_1thread"] = round(nchk / (time.perf_counter() - t0), 1)
+        if acorn_ready and count > 256:
+            pa = hx.SearchParams.new(k)                              # ef = 100 -> ef_filtered 150, <= 800 vectors scored
+            cset = hx.RestrictedVectorCandidates(cids)
+            fst = hx.FilteredStats()
+            try:
+                a_ids, a_sc, a_cnt = ix.search_filtered_graph(sq, pa, cset, stats=fst)
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    ix.search_filtered_graph(sq, pa, cset)
+                a_qps = steps * SB / (time.perf_counter() - t0)
+                hit = sum(len(set(a_ids[b, :a_cnt[b]].tolist()) & set(g_ids[b].tolist())) for b in range(SB))
+                ac = {"qps": round(a_qps, 1), "recall_at_10_vs_exact": round(hit / float(SB * k), 4),
+                      "vectors_scored_per_query": round(fst.vector_payload_requests / SB, 1),
+                      "bridge_rows_per_query": round(fst.bridge_rows / SB, 1),
+                      "kernel": "k_filtered_walk (one CTA per query)", "faster_than_exact_scan": bool(a_qps > ent["e2e"])}
+                if ora is not None:
+                    if not ora_sim:
+                        nn = n
+                        ora.put_simhash(np.arange(nn, dtype=np.uint64), ix.download_simhash(0, nn))
+                        ora_sim = True
+                    okw = True
+                    for b in range(2):
+                        # the device projected the query fingerprints from the planes; project the same way on the host
+                        pl = getattr(ix, "_bench_planes", None)
+                        if pl is None:
+                            break
+                        oi, osc, _ = ora.search_filtered_graph(sq[b], k, cids, hxo_simhash(pl, sq[b]), ef=100)
+                        okw = okw and a_ids[b, :a_cnt[b]].tolist() == oi.tolist() and a_sc[b, :a_cnt[b]].tobytes() == osc.tobytes()
+                    else:
+                        ac["oracle_bit_exact"] = bool(okw)
+                ent["acorn_walk"] = ac
+            except hx.HelixDbError as e:
+                ent["acorn_walk"] = {"error": str(e)}
         shapes.append(ent)
 
     cpu = None
@@ -837,6 +889,7 @@ def run_ours(args):
     d_ids_first = None
     if not args.no_default_mode and args.metric == "cosine":
         planes = np.random.default_rng(42).standard_normal((64, dim)).astype(np.float32)
+        ix._bench_planes = planes
         ix.set_simhash_planes(planes)
         t0 = time.perf_counter()
         ix.compute_simhash()

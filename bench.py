@@ -504,7 +504,7 @@ def measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=None, label_
         "gpu_launches": steps * 2, "launches_per_step": {"k_validate_and_header": 1, "k_scan_topk": 1},
         "roofline": {"bound": "hbm", "kernel": "k_scan_topk (bit-exact scan + warp-shuffle top-k, one launch)", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(achieved / hbm_peak, 4),
-                     "traffic": ncu_traffic("k_scan", {"queries": B, "candidates": per_q, "dim": dim}), "peak_source": peak_src,
+                     "traffic": ncu_traffic("k_scan_topk", {"queries": B, "candidates": per_q, "dim": dim}), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms_per_launch": round(kernel_ms, 4)},
         "reference_shapes": shapes,
     }
@@ -563,6 +563,8 @@ def measure_dense(hx, torch, args, world, rank, local_rank, dev, stream, uid):
     ix.load_graph(0, np.array([lo], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
     ix.set_entry(lo, 0)
     gen_s = time.perf_counter() - t0
+    if world > 1:   # one NCCL unique id per communicator: never reuse the id of another group
+        uid = sh.exchange_unique_id(rank, device=dev)
     g = sh.ShardGroup(ix, world, rank, uid)
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     tf_peak = float(peaks.get("bf16_tflops", 1590.0))

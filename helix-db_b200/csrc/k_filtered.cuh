@@ -190,55 +190,91 @@ __global__ void __launch_bounds__(HXG_THREADS) k_filtered_walk(HxDev ix, HxFilte
 
     // classify the layer-0 rows of `nodes[0..cnt)` in order (:1028-1041, :1072-1083): candidates not yet attempted join
     // the eligible list once (discovery order), everything else becomes a bridge once.  One warp, ballot compaction.
+    // Rows are independent to FETCH but ordered to COMMIT (eligible order is part of the answer): the eight warps take the
+    // rows round-robin, each prefetches its row's first 32 neighbours — the row itself, their candidate bits, their flags
+    // (to warm L2) and fingerprints: the ~1.5 us of dependent latency — and then commits in row order behind a turn
+    // counter in shared memory; the commit re-reads the flags (an earlier row of the same batch may have claimed the slot).
     uint32_t nEL = 0;
     auto classify = [&](const uint32_t* nodes, bool keys64, const uint64_t* nodes64, uint32_t cnt) {
-      if (warp == 0) {
-        uint32_t el = nEL, br = nBR, pushes = 0, err = 0;
-        for (uint32_t r = 0; r < cnt; ++r) {
-          const uint32_t node = keys64 ? (uint32_t)(nodes64[r] & 0xffffffffu) : nodes[r];
-          const uint32_t deg = ix.deg0[node];
-          const uint32_t* row = ix.nbr0 + (size_t)node * ix.stride0;
-          for (uint32_t base = 0; base < deg; base += 32) {
-            const uint32_t j = base + lane;
-            uint32_t nb = 0, fl = 0;
-            bool ok = false, is_el = false, is_br = false;
-            if (j < deg) {
-              nb = row[j];
-              ok = true;
-              fl = flags_of(nb);
-              const bool allowed = (a.allowed_bits[nb >> 5] >> (nb & 31u)) & 1u;
-              if (allowed) is_el = !(fl & (HXG_F_ATT | HXG_F_ELIG));
-              else is_br = !(fl & HXG_F_QUEUED);
-            }
-            (void)ok;
-            // a row is ascending and unique, so lanes of one chunk never name the same slot: flags can be set in parallel
-            if (is_el) stamp[nb] = ebits | (fl | HXG_F_ELIG);
-            if (is_br) stamp[nb] = ebits | (fl | HXG_F_QUEUED);
-            const uint32_t me = __ballot_sync(FULL, is_el), mb = __ballot_sync(FULL, is_br);
-            if (is_el) {
-              const uint32_t p = el + __popc(me & ((1u << lane) - 1u));
-              if (p < a.elig_cap) EL[p] = nb; else err |= HXG_ERR_CAPACITY;
-            }
-            if (is_br) {
-              const uint32_t p = br + __popc(mb & ((1u << lane) - 1u));
-              const bool has = a.has_simhash ? a.has_simhash[nb] != 0 : true;
-              if (!has) err |= HXG_ERR_MISSING_SIMHASH;
-              const uint32_t ham = (uint32_t)__popcll(a.simhash[nb] ^ qsim);
-              if (p < a.bridge_cap) BR[p] = ((uint64_t)ham << 32) | nb; else err |= HXG_ERR_CAPACITY;
-            }
-            el += __popc(me);
-            br += __popc(mb);
-            pushes += __popc(mb);
-            __syncwarp();
+      __shared__ volatile uint32_t s_turn, s_el, s_br, s_push;
+      if (tid == 0) { s_turn = 0; s_el = nEL; s_br = nBR; s_push = 0; }
+      __syncthreads();
+      uint32_t err = 0;
+      for (uint32_t r = warp; r < cnt; r += HXG_THREADS / 32) {
+        const uint32_t node = keys64 ? (uint32_t)(nodes64[r] & 0xffffffffu) : nodes[r];
+        const uint32_t deg = ix.deg0[node];
+        const uint32_t* row = ix.nbr0 + (size_t)node * ix.stride0;
+        // ---- prefetch phase (runs concurrently in all warps)
+        uint32_t nb0 = 0;
+        bool allowed0 = false;
+        uint64_t sim0 = 0;
+        bool has0 = true;
+        if (lane < deg) {
+          nb0 = row[lane];
+          allowed0 = (a.allowed_bits[nb0 >> 5] >> (nb0 & 31u)) & 1u;
+          (void)stamp[nb0];
+          if (!allowed0) {
+            sim0 = a.simhash[nb0];
+            has0 = a.has_simhash ? a.has_simhash[nb0] != 0 : true;
           }
         }
-        err = __reduce_or_sync(FULL, err);
-        if (lane == 0) { s_cnt = el; s_cnt2 = br; s_take = pushes; if (err) atomicOr(&s_flag, err); }
+        // ---- commit phase, in row order
+        if (lane == 0)
+          while (s_turn != r) __nanosleep(40);
+        __syncwarp();
+        uint32_t el = s_el, br = s_br, pushes = 0;
+        for (uint32_t base = 0; base < deg; base += 32) {
+          const uint32_t j = base + lane;
+          uint32_t nb = nb0, fl = 0;
+          bool allowed = allowed0, has = has0, is_el = false, is_br = false;
+          uint64_t sim = sim0;
+          if (j < deg) {
+            if (base) {
+              nb = row[j];
+              allowed = (a.allowed_bits[nb >> 5] >> (nb & 31u)) & 1u;
+              if (!allowed) {
+                sim = a.simhash[nb];
+                has = a.has_simhash ? a.has_simhash[nb] != 0 : true;
+              }
+            }
+            fl = flags_of(nb);
+            if (allowed) is_el = !(fl & (HXG_F_ATT | HXG_F_ELIG));
+            else is_br = !(fl & HXG_F_QUEUED);
+          }
+          // a row is ascending and unique, so lanes of one chunk never name the same slot: flags can be set in parallel
+          if (is_el) stamp[nb] = ebits | (fl | HXG_F_ELIG);
+          if (is_br) stamp[nb] = ebits | (fl | HXG_F_QUEUED);
+          const uint32_t me = __ballot_sync(FULL, is_el), mb = __ballot_sync(FULL, is_br);
+          if (is_el) {
+            const uint32_t p = el + __popc(me & ((1u << lane) - 1u));
+            if (p < a.elig_cap) EL[p] = nb; else err |= HXG_ERR_CAPACITY;
+          }
+          if (is_br) {
+            const uint32_t p = br + __popc(mb & ((1u << lane) - 1u));
+            if (!has) err |= HXG_ERR_MISSING_SIMHASH;
+            if (p < a.bridge_cap) BR[p] = ((uint64_t)__popcll(sim ^ qsim) << 32) | nb; else err |= HXG_ERR_CAPACITY;
+          }
+          el += __popc(me);
+          br += __popc(mb);
+          pushes += __popc(mb);
+          __syncwarp();
+        }
+        __threadfence_block();
+        if (lane == 0) {
+          s_el = el;
+          s_br = br;
+          s_push = s_push + pushes;
+          __threadfence_block();
+          s_turn = r + 1u;
+        }
+        __syncwarp();
       }
+      err = __reduce_or_sync(FULL, err);
+      if (lane == 0 && err) atomicOr(&s_flag, err);
       __syncthreads();
-      nEL = min(s_cnt, a.elig_cap);
-      nBR = min(s_cnt2, a.bridge_cap);
-      st_pushes += s_take;
+      nEL = min((uint32_t)s_el, a.elig_cap);
+      nBR = min((uint32_t)s_br, a.bridge_cap);
+      st_pushes += s_push;
       __syncthreads();
     };
 

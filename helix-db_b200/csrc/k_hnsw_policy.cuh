@@ -232,6 +232,11 @@ __device__ __forceinline__ uint32_t hxp_choose_index(HxSession& s, uint32_t coun
   return result;
 }
 
+// CTA build: warp 0 (the query) and the helper warps rendezvous from DIFFERENT call sites.  `__syncthreads()` works there
+// (bar.sync 0 only counts arrivals) but is outside the programming model and is what compute-sanitizer's synccheck flags
+// as "divergent threads in block"; a named barrier with an explicit thread count says what is meant.
+__device__ __forceinline__ void hxp_cta_sync() { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x) : "memory"); }
+
 // read-only membership probe of the visited set
 __device__ __forceinline__ bool hx_vt_contains(const HxVisited& v, uint32_t key) {
   uint32_t h = (key * 2654435761u) >> v.shift;
@@ -327,14 +332,14 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
   };
   if (CTA && warp != 0) {   // helpers: score on command until warp 0 says done
     for (;;) {
-      __syncthreads();
+      hxp_cta_sync();
       if (s_cmd == 2u) return;
       const uint32_t cnt = s_cnt;
       q_hdr = s_qhdr;
       qg = s_qg;
       for (uint32_t base = 0; base < cnt; base += R) {
         score_share(frontier, base, min(R, cnt - base));
-        __syncthreads();
+        hxp_cta_sync();
       }
     }
   }
@@ -342,10 +347,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     if (CTA) {   // list == frontier (always, in this kernel)
       if (cnt == 0) return;
       if (lane == 0) { s_cmd = 1u; s_cnt = cnt; s_qhdr = q_hdr; s_qg = qg; }
-      __syncthreads();
+      hxp_cta_sync();
       for (uint32_t base = 0; base < cnt; base += R) {
         score_share(list, base, min(R, cnt - base));
-        __syncthreads();
+        hxp_cta_sync();
       }
       return;
     }
@@ -734,7 +739,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
   }
   if (CTA) {   // warp 0: release the helpers
     if (lane == 0) s_cmd = 2u;
-    __syncthreads();
+    hxp_cta_sync();
   }
   if (pa.pstats && lane == 0)
     for (int i = 0; i < 12; ++i)

@@ -444,7 +444,7 @@ def measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=None, label_
                 ok = ok and g_ids[b, :len(ei)].tolist() == ei.tolist() and g_sc[b, :len(ei)].tobytes() == es.tobytes()
             ent["oracle_bit_exact"] = bool(ok)
             ent["cpu_port_qps_1thread"] = round(nchk / (time.perf_counter() - t0), 1)
-        if acorn_ready and count > 256:
+        if acorn_ready and count > 256 and ix.graph_info()["max_layer"] > 0:   # the walk needs a real graph
             pa = hx.SearchParams.new(k)                              # ef = 100 -> ef_filtered 150, <= 800 vectors scored
             cset = hx.RestrictedVectorCandidates(cids)
             fst = hx.FilteredStats()
@@ -1067,8 +1067,7 @@ def run_ours(args):
         callers_res = measure_callers(hx, ix, qsets[0][:8192], k, EF, args.callers_seconds)
     del ora
 
-    impl = os.environ.get("HX_HNSW_IMPL", "ring")
-    hnsw_kernel = {"ring": "k_hnsw_search_ring", "tma": "k_hnsw_search_tma", "ldg": "k_hnsw_search_warp"}.get(impl, impl)
+    hnsw_kernel = "k_hnsw_search_ring"
     line = None
     if rank == 0:
         line = {
@@ -1081,8 +1080,8 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4,
                     "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 8 + 4,
                     "api": "hx_search (C ABI, pinned host buffers, blocking)"},
-            "gpu_launches": args.steps * (1 if impl == "ring" else 2),
-            "launches_per_step": ({hnsw_kernel: 1} if impl == "ring" else {"k_validate_and_header": 1, hnsw_kernel: 1}),
+            "gpu_launches": args.steps,
+            "launches_per_step": {hnsw_kernel: 1},
             "roofline": {"bound": "hbm", "kernel": hnsw_kernel, "achieved": round(achieved, 1), "peak": hbm_peak,
                          "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic("k_hnsw_search", {"queries": Q, "rows": n, "dim": dim, "ef": EF}),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_per_launch),
@@ -1172,19 +1171,12 @@ def run_prefilter(args):
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream(dev).cuda_stream
     n, dim = args.n, args.dim
-    metric = hx.Metric.Cosine if args.metric == "cosine" else hx.Metric.Euclidean
-    ix = hx.VectorIndex(metric, hx.VectorIndexConfig("dbpedia_1m_synthetic", "embedding", dim), device=local_rank)
-    ix.generate_vectors(0, n, SEED, N_CENTROIDS, SIGMA, KIND)
-    ix.load_graph(0, np.array([0], np.uint64), np.array([0, 0], np.uint32), np.zeros(0, np.uint64))
-    ix.set_entry(0, 0)
+    # the exact scan needs no graph; the filter-aware walk reported next to the reference's shapes does: build it
+    ix, _setup = build_index(hx, args, local_rank, 0, n)
     ora = None
     if not args.no_cpu:
         from oracle import hxo
-        ora = hxo.Index(hxo.COSINE if args.metric == "cosine" else hxo.EUCLIDEAN, dim)
-        for lo in range(0, n, 65536):
-            ids_, rows_ = ix.download_vectors(lo, min(65536, n - lo))
-            ora.put_vectors(ids_, rows_)
-        ora.set_entry(0, 0)
+        ora = oracle_from_device(hxo, ix, args)
     sampler = ClockSampler(local_rank)
     sampler.start()
     line = measure_prefilter(hx, torch, ix, args, dev, stream, n, dim, ora=ora)

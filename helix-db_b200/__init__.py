@@ -127,6 +127,14 @@ class PolicyStats(C.Structure):
         return {f: int(getattr(self, f)) for f, _ in self._fields_}
 
 
+class _Tuning(C.Structure):
+    # hx_tuning (include/helix_b200.h): launch-shape knobs, -1 = built-in default
+    _fields_ = [(f, C.c_int32) for f in (
+        "ring_warps", "ring_rows", "visited_log2", "visited_pool", "l2_hint", "prefetch_below", "lat_warps", "lat_admit_seq",
+        "lat_spec", "phase_prof", "pipeline", "scan_fused", "pol_warps", "pol_min_rows", "pol_cta", "pol_early_sim",
+        "build_max_batch")]
+
+
 class _ServiceConfig(C.Structure):
     _fields_ = [("k", C.c_uint32), ("ef", C.c_uint32), ("capacity", C.c_uint32), ("max_batch", C.c_uint32),
                 ("n_streams", C.c_uint32), ("ctas_per_sm", C.c_uint32), ("cta_warps", C.c_uint32),
@@ -176,7 +184,7 @@ ABI_SYMBOLS = [
     "hx_search_sharded", "hx_search_restricted_sharded", "hx_shard_group_last_ms",
     "hx_index_upsert_vectors", "hx_index_set_levels", "hx_index_upsert_neighbor_rows", "hx_index_delete_vectors",
     "hx_index_load_upper_vector_rows", "hx_index_set_version", "hx_index_get_version", "hx_index_build_ex",
-    "hx_filtered_budgets", "hx_search_filtered_graph",
+    "hx_filtered_budgets", "hx_search_filtered_graph", "hx_index_get_tuning", "hx_index_set_tuning",
 ]
 
 _lib = None
@@ -197,6 +205,10 @@ def load_library():
     L.hx_index_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
     L.hx_index_destroy.restype = None
     L.hx_index_destroy.argtypes = [vp]
+    L.hx_index_get_tuning.restype = C.c_int32
+    L.hx_index_get_tuning.argtypes = [vp, C.POINTER(_Tuning)]
+    L.hx_index_set_tuning.restype = C.c_int32
+    L.hx_index_set_tuning.argtypes = [vp, C.POINTER(_Tuning)]
     L.hx_index_load_vectors.restype = C.c_int32
     L.hx_index_load_vectors.argtypes = [vp, u64p, fp, sz]
     L.hx_index_generate_vectors.restype = C.c_int32
@@ -696,6 +708,25 @@ class VectorIndex:
             raise HelixDbError(HX_ERR_INVARIANT_VIOLATION, "item rows must be 4+4*dimension bytes each")
         buf = (C.c_uint8 * max(len(rows), 1)).from_buffer_copy(rows if rows else b"\0")
         _ck(self.L.hx_index_load_upper_vector_rows(self.h, ip, buf, ia.size))
+
+    def tune(self, **knobs):
+        """hx_index_set_tuning: launch-shape knobs for experiments / A-B tests (fields of hx_tuning).  The handle starts from
+        the environment's values (HX_RING_WARPS, ...); ``tune(x=..)`` overrides fields on top of those, ``tune()`` alone
+        returns to them.  Results are bit-identical for every setting."""
+        _ck(self.L.hx_index_set_tuning(self.h, None))
+        if knobs:
+            t = _Tuning()
+            _ck(self.L.hx_index_get_tuning(self.h, C.byref(t)))
+            for key, val in knobs.items():
+                if not hasattr(t, key):
+                    raise TypeError(f"unknown tuning knob {key!r}")
+                setattr(t, key, int(val))
+            _ck(self.L.hx_index_set_tuning(self.h, C.byref(t)))
+
+    def tuning(self) -> dict:
+        t = _Tuning()
+        _ck(self.L.hx_index_get_tuning(self.h, C.byref(t)))
+        return {f: int(getattr(t, f)) for f, _ in _Tuning._fields_}
 
     def set_version(self, generation: int, visible_seq: int):
         _ck(self.L.hx_index_set_version(self.h, generation, visible_seq))

@@ -227,9 +227,8 @@ void HxScratch::destroy() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   d_queries.release(); d_qhdr.release(); d_out_scores.release();
-  d_qstatus.release(); d_out_counts.release(); d_qstats.release(); d_err.release(); d_epochs.release();
+  d_qstatus.release(); d_out_counts.release(); d_qstats.release(); d_err.release();
   d_cand_slots.release(); d_out_ids.release(); d_cand_ids.release(); d_cand_offsets.release(); d_keys.release();
-  d_stamps.release();
   d_tiepool.release(); d_tiebusy.release(); d_qerr.release(); h_qerr.release(); d_partial.release(); d_tickets.release();
   d_fg_stamps.release(); d_fg_epochs.release(); d_fg_bridge.release(); d_fg_elig.release(); d_fg_bits.release(); d_fg_seed.release();
   d_vtab.release(); d_vpool.release(); d_vbusy.release(); d_prof.release(); d_pstats.release(); d_qsim.release();
@@ -312,6 +311,55 @@ bool hx_slot_of(const hx_index* ix, uint64_t id, uint32_t* slot) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// launch-shape knobs (hx_tuning): seeded from the environment ONCE per handle, never read on the search path
+// ------------------------------------------------------------------------------------------------
+static int32_t env_knob(const char* name, long lo, long hi) {
+  const char* e = getenv(name);
+  if (!e || !*e) return -1;
+  const long v = atol(e);
+  return v >= lo && v <= hi ? (int32_t)v : -1;
+}
+static void tuning_from_env(hx_tuning* t) {
+  t->ring_warps = env_knob("HX_RING_WARPS", 1, 16);
+  t->ring_rows = env_knob("HX_RING_R", 1, 32);
+  t->visited_log2 = env_knob("HX_VT_CAP_LOG2", 6, 24);
+  t->visited_pool = env_knob("HX_VT_POOL", 0, 1024);
+  t->l2_hint = env_knob("HX_L2_HINT", 0, 1);
+  t->prefetch_below = env_knob("HX_PREFETCH_BELOW", 0, 1 << 20);
+  t->lat_warps = env_knob("HX_LAT_WARPS", 1, 12);
+  const char* adm = getenv("HX_LAT_ADMIT");
+  t->lat_admit_seq = adm ? (strcmp(adm, "seq") == 0 ? 1 : 0) : -1;
+  t->lat_spec = env_knob("HX_LAT_SPEC", 0, 1);
+  t->phase_prof = env_knob("HX_PHASE_PROF", 0, 1);
+  t->pipeline = env_knob("HX_PIPELINE", 0, 1);
+  t->scan_fused = env_knob("HX_SCAN_FUSED", 0, 1);
+  t->pol_warps = env_knob("HX_POL_WARPS", 1, 16);
+  t->pol_min_rows = env_knob("HX_POL_MINR", 1, 32);
+  t->pol_cta = env_knob("HX_POL_CTA", 0, 1);
+  t->pol_early_sim = env_knob("HX_POL_EARLY_SIM", 0, 1);
+  t->build_max_batch = env_knob("HX_BUILD_MAX_BATCH", 1, 65536);
+}
+static inline uint32_t knob(int32_t v, uint32_t dflt) { return v < 0 ? dflt : (uint32_t)v; }
+
+extern "C" hx_status hx_index_get_tuning(const hx_index* ix, hx_tuning* out) {
+  if (!ix || !out) {
+    hx_set_error("hx_index_get_tuning: null argument");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  *out = ix->tune;
+  return HX_OK;
+}
+extern "C" hx_status hx_index_set_tuning(hx_index* ix, const hx_tuning* t) {
+  if (!ix) {
+    hx_set_error("hx_index_set_tuning: null handle");
+    return HX_ERR_INVALID_PARAMETER;
+  }
+  if (t) ix->tune = *t;
+  else tuning_from_env(&ix->tune);   // NULL: back to the environment's values
+  return HX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // lifecycle
 // ------------------------------------------------------------------------------------------------
 extern "C" hx_status hx_index_create(const hx_index_config* cfg, hx_index** out) {
@@ -342,6 +390,7 @@ extern "C" hx_status hx_index_create(const hx_index_config* cfg, hx_index** out)
   hx_index* ix = new hx_index();
   ix->cfg = *cfg;
   ix->device = cfg->device;
+  tuning_from_env(&ix->tune);
   ix->lim0 = std::max(cfg->m0, 2 * cfg->m);
   ix->ld = round_up(cfg->dimension, 32);
   cudaDeviceProp prop;
@@ -1149,10 +1198,6 @@ static hx_status setup_tie_pool(HxScratch* s, HxRingArgs* rg, cudaStream_t strea
   return HX_OK;
 }
 
-static uint32_t hnsw_smem_bytes(const hx_index* ix, uint32_t ef, uint32_t fr_cap) {
-  return ix->ld * 4u + ef * 8u + HX_TIE_CAP * 8u + fr_cap * 8u;
-}
-
 // ---- CTA-per-query ring build: configuration + launch (shared by hx_search's small-batch path and the query service) ----
 // Shared memory per CTA: [query (QCH == 0)] | RC row slots | beam / merge stage [ef] | tie stack | RC mbarriers | frontier |
 // scores | visited table.  `budget` = dynamic shared memory the CTA may take (227 KB: one CTA per SM; ~113 KB: two).
@@ -1160,7 +1205,7 @@ bool hx_cta_ring_config(const hx_index* ix, uint32_t ef, uint32_t want_warps, ui
                         size_t budget, HxCtaRingCfg* c) {
   const uint32_t chunks = ix->ld / 32;
   const size_t rowbytes = (size_t)ix->ld * 4;
-  c->qch = chunks <= 8 ? 8 : chunks <= 24 ? 24 : chunks <= 48 ? 48 : 0;
+  c->qch = ix->cfg.metric == HX_METRIC_MANHATTAN ? 0 : chunks <= 8 ? 8 : chunks <= 24 ? 24 : chunks <= 48 ? 48 : 0;
   c->fr_cap = round_up(std::max(std::max(ix->stride0, ix->stride_u), 32u), 32);
   uint32_t lg = 12;
   while ((1u << lg) < 64u * ef && lg < 24) lg++;
@@ -1222,10 +1267,7 @@ hx_status hx_launch_cta_ring(hx_index* ix, const HxCtaRingCfg& c, const HxHnswAr
   } while (0)
   if (ix->cfg.metric == HX_METRIC_EUCLIDEAN) HX_CTA_Q(HXM_EUCLIDEAN);
   else if (ix->cfg.metric == HX_METRIC_COSINE) HX_CTA_Q(HXM_COSINE);
-  else {
-    hx_set_error("the CTA ring build serves the Euclidean and cosine metrics");
-    return HX_ERR_UNSUPPORTED;
-  }
+  else HX_CTA_NB(HXM_MANHATTAN, 0);   // one thread per row, sequential chain: the query stays in shared memory
 #undef HX_CTA_Q
 #undef HX_CTA_NB
 #undef HX_CTA_GO
@@ -1239,14 +1281,15 @@ struct HxFusedArgs {   // pipelined host-buffer search: validation inside the ri
   int has_limit = 0;
 };
 
-// true when launch_hnsw will take the warp-per-query ring build for this call
-static bool hnsw_uses_ring(const hx_index* ix, size_t B) {
-  if (B < (size_t)ix->sm_count || ix->cfg.metric == HX_METRIC_MANHATTAN) return false;
-  if ((size_t)ix->ld * 8 > 160 * 1024) return false;   // a warp's query + one row slot must fit (launch_hnsw re-checks)
-  if (const char* env = getenv("HX_HNSW_IMPL")) return strcmp(env, "ring") == 0;
-  return true;
-}
+// true when launch_hnsw takes the warp-per-query build for this call (the host-buffer path pipelines only that one)
+static bool hnsw_uses_ring(const hx_index* ix, size_t B) { return B >= (size_t)ix->sm_count; }
 
+// Two builds of the same algorithm (bit-identical results, every metric):
+//  * B <  #SMs : one CTA per query (k_hnsw_search_cta_ring: rows spread over the CTA's warps, register beam, visited set in
+//                shared memory) — lowest latency per query;
+//  * B >= #SMs : one WARP per query (k_hnsw_search_ring), up to 16 queries in flight per SM — highest throughput.
+// Shapes the CTA build cannot hold (a row does not fit next to the visited table) take the warp build; rows that do not fit
+// a warp's share either are reduced straight from global memory (R = 0).
 static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries, size_t B, uint32_t k, uint32_t ef,
                              uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts, uint32_t* d_qstats,
                              cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1, bool* timed, uint32_t* launches,
@@ -1261,107 +1304,61 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     if (d_qstats) HX_CUDA(cudaMemsetAsync(d_qstats, 0, B * 4 * sizeof(uint32_t), stream));
     return HX_OK;
   }
-  const uint32_t fr_cap = round_up(std::max(ix->stride0, ix->stride_u), 32);
-  const uint32_t smem = hnsw_smem_bytes(ix, ef, fr_cap);
-  if (smem > 200 * 1024) {
-    hx_set_error("query working set %u bytes exceeds shared memory", smem);
-    return HX_ERR_INVALID_PARAMETER;
-  }
-  // Two builds of the same algorithm (bit-identical results):
-  //  * B <  #SMs : one CTA per query (32 octets score a whole neighbour row at once) — lowest latency per query;
-  //  * B >= #SMs : one WARP per query, 8 warps per CTA, up to 32 queries in flight per SM — highest throughput.
-  // resident CTAs per SM of the warp-per-query build (register cap 65536/(256*minb)); HX_WARP_MINB overrides for experiments
-  uint32_t minb = 4;
-  if (const char* env = getenv("HX_WARP_MINB")) { const int v = atoi(env); if (v >= 4 && v <= 6) minb = (uint32_t)v; }
-  const uint32_t wpc = HX_HNSW_THREADS / 32;
-  const uint32_t wstride = round_up(smem, 128);
-  const bool latency = B < (size_t)ix->sm_count || (size_t)wpc * wstride > 200 * 1024;
-  uint32_t grid, slots;
-  size_t smem_launch;
-  const size_t stride = ((ix->n + 15) / 16) * 16;
-  // TMA-staged build (default for throughput): R rows per warp and round live in shared memory
-  bool use_tma = !latency;
-  if (const char* env = getenv("HX_HNSW_IMPL")) use_tma = use_tma && strcmp(env, "ldg") != 0;
-  uint32_t tma_R = 0, tma_wstride = 0, tma_wpc = 12, cta_RC = 0;   // 12 warps/SM measured best (8: 0.65, 12: 0.70, 16: 0.70 of HBM peak)
-  if (const char* env = getenv("HX_TMA_WARPS")) { const int v = atoi(env); if (v >= 4 && v <= 16) tma_wpc = (uint32_t)v; }
-  if (use_tma) {
-    const size_t fixed = (size_t)ix->ld * 4 + (size_t)ef * 8 + HX_TIE_CAP * 8 + 8 + (size_t)fr_cap * 12;
-    const size_t per_warp_budget = (216 * 1024) / tma_wpc;
-    if (per_warp_budget > fixed + (size_t)ix->ld * 4) tma_R = (uint32_t)std::min<size_t>(32, (per_warp_budget - fixed) / ((size_t)ix->ld * 4));
-    if (tma_R == 0) use_tma = false;
-    else tma_wstride = round_up((uint32_t)(fixed + (size_t)tma_R * ix->ld * 4), 128);
-  }
-  // Ring builds (k_hnsw_ring.cuh): visited hash sets, per-slot mbarrier ring, warp-per-row reduction.  Default for
-  // Euclidean / cosine: warp-per-query when the batch fills the GPU, CTA-per-query (visited set in shared memory) below
-  // that.  HX_HNSW_IMPL=tma|ldg (throughput) and HX_LAT_IMPL=tma|ldg (latency) select the first generation for A/B runs.
-  const bool small_batch = B < (size_t)ix->sm_count;
-  const bool ring_metric = ix->cfg.metric != HX_METRIC_MANHATTAN;
-  bool use_ring = !small_batch && ring_metric;
-  if (const char* env = getenv("HX_HNSW_IMPL")) use_ring = use_ring && strcmp(env, "ring") == 0;
-  bool use_cta_ring = small_batch && ring_metric;
-  if (const char* env = getenv("HX_LAT_IMPL")) use_cta_ring = use_cta_ring && strcmp(env, "ring") == 0;
-  uint32_t ring_R = 0, ring_wstride = 0, ring_wpc = 0, ring_qch = 0, vt_cap = 0, cta_vt_cap = 0, cta_warps = 8;
+  const hx_tuning& t = ix->tune;
+  const bool manhattan = ix->cfg.metric == HX_METRIC_MANHATTAN;
+  const uint32_t fr_cap = round_up(std::max(std::max(ix->stride0, ix->stride_u), 32u), 32);
   const size_t rowbytes = (size_t)ix->ld * 4;
   const size_t ring_budget = 227 * 1024;
-  if (use_ring || use_cta_ring) {
-    const uint32_t chunks = ix->ld / 32;
-    ring_qch = chunks <= 8 ? 8 : chunks <= 24 ? 24 : chunks <= 48 ? 48 : 0;
-    uint32_t lg = 12;
-    while ((1u << lg) < 64u * ef && lg < 24) lg++;
-    if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) lg = (uint32_t)v; }
-    vt_cap = 1u << lg;
-  }
-  if (use_ring) {
+  const uint32_t chunks = ix->ld / 32;
+  // the query lives in registers (QCH chunks of 32) when it fits; Manhattan walks it sequentially: shared memory
+  const uint32_t ring_qch = manhattan ? 0u : chunks <= 8 ? 8u : chunks <= 24 ? 24u : chunks <= 48 ? 48u : 0u;
+  uint32_t lg = 12;
+  while ((1u << lg) < 64u * ef && lg < 24) lg++;
+  const uint32_t vt_cap = 1u << knob(t.visited_log2, lg);
+  HxCtaRingCfg cta_cfg{};
+  bool use_cta_ring = B < (size_t)ix->sm_count &&
+                      hx_cta_ring_config(ix, ef, knob(t.lat_warps, 0), knob(t.ring_rows, 0), knob(t.visited_log2, 0), ring_budget,
+                                         &cta_cfg) &&
+                      cta_cfg.fr_cap == fr_cap;
+  uint32_t ring_R = 0, ring_wstride = 0, ring_wpc = 0;
+  if (!use_cta_ring) {
     const size_t fixed0 = (ring_qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 12;
-    uint32_t want_wpc = 16, want_R = 0;
-    if (const char* env = getenv("HX_RING_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 16) want_wpc = (uint32_t)v; }
-    if (const char* env = getenv("HX_RING_R")) { const int v = atoi(env); if (v >= 1 && v <= 32) want_R = (uint32_t)v; }
+    uint32_t want_wpc = knob(t.ring_warps, 16);
+    const uint32_t want_R = knob(t.ring_rows, 0);
     // few queries: fewer warps per CTA so that the batch spreads over all SMs (and each warp gets a deeper ring)
     const uint32_t spread = (uint32_t)std::max<size_t>(1, (B + ix->sm_count - 1) / (size_t)ix->sm_count);
     want_wpc = std::min(want_wpc, spread);
-    for (uint32_t w = want_wpc; w >= 1; --w) {
+    for (uint32_t w = want_wpc; w >= 1 && !manhattan; --w) {
       const size_t per_warp = (ring_budget / w) & ~(size_t)127;
       if (per_warp <= fixed0 + 8 + rowbytes) continue;
       uint32_t r = (uint32_t)std::min<size_t>(32, (per_warp - fixed0) / (rowbytes + 8));
       if (want_R) r = std::min(r, want_R);
       if (r >= 4 || w == 1 || (want_R && r == want_R)) { ring_wpc = w; ring_R = r; break; }
     }
-    if (ring_R == 0) use_ring = false;
-    else ring_wstride = round_up((uint32_t)(fixed0 + (size_t)ring_R * (rowbytes + 8)), 128);
-  }
-  size_t cta_ring_smem = 0;
-  HxCtaRingCfg cta_cfg{};
-  if (use_cta_ring) {
-    // rows in flight first (up to 32), then the largest visited table that still fits (at least 1024 entries)
-    uint32_t want_rc = 0, want_warps = 0;
-    if (const char* env = getenv("HX_RING_R")) { const int v = atoi(env); if (v >= 1 && v <= 32) want_rc = (uint32_t)v; }
-    if (const char* env = getenv("HX_LAT_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 12) want_warps = (uint32_t)v; }
-    uint32_t want_lg = 0;
-    if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) want_lg = (uint32_t)v; }
-    if (!hx_cta_ring_config(ix, ef, want_warps, want_rc, want_lg, ring_budget, &cta_cfg) || cta_cfg.fr_cap != fr_cap) {
-      use_cta_ring = false;
-    } else {
-      cta_vt_cap = cta_cfg.vt_cap;
-      ring_R = cta_cfg.RC;
-      cta_ring_smem = cta_cfg.smem;
-      cta_warps = cta_cfg.warps;
+    if (ring_wpc == 0) {   // no row slots: Manhattan (one lane per row, from global memory) or rows too large to stage
+      const size_t need = round_up((uint32_t)std::min<size_t>(fixed0, 1u << 30), 128);
+      if (need > ring_budget) {
+        hx_set_error("query working set %zu bytes exceeds shared memory (dimension %u, ef %u)", fixed0, ix->cfg.dimension, ef);
+        return HX_ERR_INVALID_PARAMETER;
+      }
+      ring_wpc = (uint32_t)std::max<size_t>(1, std::min<size_t>(want_wpc, ring_budget / need));
     }
+    ring_wstride = round_up((uint32_t)(fixed0 + (size_t)ring_R * (rowbytes + 8)), 128);
+  }
+  const bool use_ring = !use_cta_ring;
+  uint32_t grid;
+  size_t smem_launch, vslots = 0;
+  if (use_ring) {
+    grid = (uint32_t)std::min<size_t>((B + ring_wpc - 1) / ring_wpc, (size_t)ix->sm_count);
+    smem_launch = (size_t)ring_wpc * ring_wstride;
+    vslots = (size_t)grid * ring_wpc;
+  } else {
+    grid = (uint32_t)B;   // B < #SMs
+    smem_launch = cta_cfg.smem;
   }
   HxRingArgs rg{};
-  if (use_ring || use_cta_ring) {
-    use_tma = false;
-    slots = 0;
-    size_t vslots = 0;
-    if (use_ring) {
-      grid = (uint32_t)std::min<size_t>((B + ring_wpc - 1) / ring_wpc, (size_t)ix->sm_count);
-      smem_launch = (size_t)ring_wpc * ring_wstride;
-      vslots = (size_t)grid * ring_wpc;
-    } else {
-      grid = (uint32_t)B;   // B < #SMs
-      smem_launch = cta_ring_smem;
-    }
-    uint32_t pool_n = 32;
-    if (const char* env = getenv("HX_VT_POOL")) { const int v = atoi(env); if (v >= 0 && v <= 1024) pool_n = (uint32_t)v; }
+  {
+    const uint32_t pool_n = knob(t.visited_pool, 32);
     const uint32_t pool_cap = std::max<uint32_t>(vt_cap * 16u, 65536u);
     if (vslots && (rc = s->d_vtab.reserve(vslots * vt_cap))) return rc;
     if (s->vpool_n != pool_n || s->vpool_cap != pool_cap || !s->d_vbusy.p) {
@@ -1377,58 +1374,16 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
     rg.pool_busy = s->d_vbusy.p;
     rg.pool_n = pool_n;
     rg.pool_cap = pool_cap;
-    rg.l2_hint = 1;
-    if (const char* env = getenv("HX_L2_HINT")) rg.l2_hint = atoi(env) ? 1u : 0u;
-    rg.prefetch_below = ef / 2 + 1;
-    if (const char* env = getenv("HX_PREFETCH_BELOW")) { const int v = atoi(env); if (v >= 0) rg.prefetch_below = (uint32_t)v; }
+    rg.l2_hint = knob(t.l2_hint, 1);
+    rg.prefetch_below = knob(t.prefetch_below, ef / 2 + 1);
     if ((rc = setup_tie_pool(s, &rg, stream))) return rc;
-    rg.batch_admit = 1;
-    if (const char* env = getenv("HX_LAT_ADMIT")) rg.batch_admit = strcmp(env, "seq") == 0 ? 0u : 1u;
-    rg.l2_spec = 0;   // measured: the speculative row prefetch costs more than it hides (profiles/r01_latency_*); opt-in
-    if (const char* env = getenv("HX_LAT_SPEC")) rg.l2_spec = atoi(env) ? 1u : 0u;
-    if (const char* env = getenv("HX_PHASE_PROF")) {   // diagnostics: cycle sums per phase of the latency build
-      if (atoi(env)) {
-        if ((rc = s->d_prof.reserve(8))) return rc;
-        if (!s->prof_init) { HX_CUDA(cudaMemsetAsync(s->d_prof.p, 0, 8 * sizeof(unsigned long long), stream)); s->prof_init = true; }
-        rg.prof = s->d_prof.p;
-      }
+    rg.batch_admit = knob(t.lat_admit_seq, 0) ? 0u : 1u;
+    rg.l2_spec = knob(t.lat_spec, 0);   // measured: the speculative row prefetch costs more than it hides (profiles/r01_latency_*)
+    if (knob(t.phase_prof, 0)) {        // diagnostics: cycle sums per phase of the latency build
+      if ((rc = s->d_prof.reserve(8))) return rc;
+      if (!s->prof_init) { HX_CUDA(cudaMemsetAsync(s->d_prof.p, 0, 8 * sizeof(unsigned long long), stream)); s->prof_init = true; }
+      rg.prof = s->d_prof.p;
     }
-  } else if (use_tma) {
-    grid = (uint32_t)std::min<size_t>((B + tma_wpc - 1) / tma_wpc, (size_t)ix->sm_count);
-    slots = (uint32_t)ix->sm_count * 16;
-    smem_launch = (size_t)tma_wpc * tma_wstride;
-  } else if (latency) {
-    grid = (uint32_t)std::min<size_t>(B, (size_t)ix->sm_count * 4);
-    slots = (uint32_t)ix->sm_count * 4;
-    smem_launch = smem;
-    // TMA-staged latency build when at least 8 rows fit next to the query state
-    const char* env = getenv("HX_LAT_IMPL");
-    const size_t fixed = (size_t)ix->ld * 4 + (size_t)ef * 8 + HX_TIE_CAP * 8 + 8 + (size_t)fr_cap * 12;
-    if (!(env && strcmp(env, "ldg") == 0) && 200 * 1024 > fixed + 8 * (size_t)ix->ld * 4) {
-      cta_RC = (uint32_t)std::min<size_t>(32, (200 * 1024 - fixed) / ((size_t)ix->ld * 4));
-      smem_launch = fixed + (size_t)cta_RC * ix->ld * 4;
-      grid = (uint32_t)std::min<size_t>(B, (size_t)ix->sm_count);
-    }
-  } else {
-    uint32_t ctas_per_sm = minb;
-    while (ctas_per_sm > 1 && (size_t)ctas_per_sm * wpc * wstride > 200 * 1024) ctas_per_sm--;
-    uint32_t max_ctas = (uint32_t)ix->sm_count * ctas_per_sm;
-    // visited stamps cost n bytes per resident query: keep them under ~8 GB
-    const size_t budget = 8ull << 30;
-    while (max_ctas > (uint32_t)ix->sm_count && (size_t)max_ctas * wpc * stride > budget) max_ctas -= (uint32_t)ix->sm_count;
-    grid = (uint32_t)std::min<size_t>((B + wpc - 1) / wpc, max_ctas);
-    slots = (uint32_t)ix->sm_count * ctas_per_sm * wpc;
-    if ((size_t)slots * stride > budget) slots = max_ctas * wpc;
-    smem_launch = (size_t)wpc * wstride;
-  }
-  if (slots && (s->stamp_grid < slots || s->stamp_n != ix->n || !s->d_stamps.p)) {
-    if ((rc = s->d_stamps.reserve((size_t)slots * stride))) return rc;
-    if ((rc = s->d_epochs.reserve(slots))) return rc;
-    HX_CUDA(cudaMemsetAsync(s->d_stamps.p, 0, (size_t)slots * stride, stream));
-    HX_CUDA(cudaMemsetAsync(s->d_epochs.p, 0, slots * sizeof(uint32_t), stream));
-    s->stamp_grid = slots;
-    s->stamp_stride = stride;
-    s->stamp_n = ix->n;
   }
   const bool had_err = s->d_err.p != nullptr;
   if ((rc = s->d_err.reserve(4))) return rc;   // [0] error flags, [1] query counter of the ring build, [2] queries landed
@@ -1436,7 +1391,6 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   if (sticky_flags && had_err) HX_CUDA(cudaMemsetAsync(s->d_err.p + 1, 0, sizeof(uint32_t), stream));
   else HX_CUDA(cudaMemsetAsync(s->d_err.p, 0, 2 * sizeof(uint32_t), stream));
   rg.counter = s->d_err.p + 1;
-  if (!(use_ring || use_cta_ring)) HX_CUDA(cudaMemsetAsync(s->d_qerr.p, 0, B * sizeof(uint32_t), stream));   // first-generation kernels report batch flags only
   HxHnswArgs a{};
   a.queries = d_queries;
   a.q_hdr = s->d_qhdr.p;
@@ -1448,15 +1402,12 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   a.out_scores = d_out_scores;
   a.out_counts = d_out_counts;
   a.q_stats = d_qstats;
-  a.stamps = s->d_stamps.p;
-  a.epochs = s->d_epochs.p;
-  a.stamp_stride = s->stamp_stride;
   a.err_flags = s->d_err.p;
   a.q_err = s->d_qerr.p;
   a.fr_cap = fr_cap;
   if (fused) {
     if (!use_ring) {
-      hx_set_error("internal: fused validation needs the ring build");
+      hx_set_error("internal: fused validation needs the warp-per-query build");
       return HX_ERR_INVARIANT_VIOLATION;
     }
     a.fused_validate = 1;
@@ -1468,59 +1419,30 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   }
   const HxDev dev = ix->dev();
   HX_CUDA(cudaEventRecord(e0, stream));
-#define HX_LAUNCH_WARP(M, MB)                                                                                      \
-  do {                                                                                                             \
-    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 8, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                 (int)smem_launch));                                                               \
-    HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_warp<M, 8, MB>, cudaFuncAttributePreferredSharedMemoryCarveout,     \
-                                 cudaSharedmemCarveoutMaxShared));                                                 \
-    k_hnsw_search_warp<M, 8, MB><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, wstride);                 \
-  } while (0)
 #define HX_LAUNCH_RING(M, Q)                                                                                       \
   do {                                                                                                             \
     HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_ring<M, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                  (int)smem_launch));                                                               \
     k_hnsw_search_ring<M, Q><<<grid, ring_wpc * 32, smem_launch, stream>>>(dev, a, rg, ring_wstride, ring_R);      \
   } while (0)
-#define HX_LAUNCH_HNSW(M)                                                                                          \
+#define HX_LAUNCH_RING_Q(M)                                                                                        \
   do {                                                                                                             \
-    if (use_cta_ring && M != HXM_MANHATTAN) {                                                                      \
-      if ((rc = hx_launch_cta_ring(ix, cta_cfg, a, rg, grid, stream, nullptr))) return rc;                          \
-    } else if (use_ring && M != HXM_MANHATTAN) {                                                                   \
-      constexpr int MR = M == HXM_MANHATTAN ? HXM_EUCLIDEAN : M;                                                   \
-      if (ring_qch == 8) HX_LAUNCH_RING(MR, 8);                                                                    \
-      else if (ring_qch == 24) HX_LAUNCH_RING(MR, 24);                                                             \
-      else if (ring_qch == 48) HX_LAUNCH_RING(MR, 48);                                                             \
-      else HX_LAUNCH_RING(MR, 0);                                                                                  \
-    } else if (use_tma) {                                                                                                 \
-      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_tma<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                   (int)smem_launch));                                                             \
-      k_hnsw_search_tma<M><<<grid, tma_wpc * 32, smem_launch, stream>>>(dev, a, tma_wstride, tma_R);               \
-    } else if (latency && cta_RC) {                                                                                \
-      HX_CUDA(cudaFuncSetAttribute(k_hnsw_search_cta_tma<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                   (int)smem_launch));                                                             \
-      k_hnsw_search_cta_tma<M><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a, cta_RC);                    \
-    } else if (latency) {                                                                                          \
-      if (smem_launch > 48 * 1024)                                                                                 \
-        HX_CUDA(cudaFuncSetAttribute(k_hnsw_search<M, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                     (int)smem_launch));                                                           \
-      k_hnsw_search<M, 8><<<grid, HX_HNSW_THREADS, smem_launch, stream>>>(dev, a);                                 \
-    } else if (minb == 6) {                                                                                        \
-      HX_LAUNCH_WARP(M, 6);                                                                                        \
-    } else if (minb == 5) {                                                                                        \
-      HX_LAUNCH_WARP(M, 5);                                                                                        \
-    } else {                                                                                                       \
-      HX_LAUNCH_WARP(M, 4);                                                                                        \
-    }                                                                                                              \
+    if (ring_qch == 8) HX_LAUNCH_RING(M, 8);                                                                       \
+    else if (ring_qch == 24) HX_LAUNCH_RING(M, 24);                                                                \
+    else if (ring_qch == 48) HX_LAUNCH_RING(M, 48);                                                                \
+    else HX_LAUNCH_RING(M, 0);                                                                                     \
   } while (0)
-  switch (ix->cfg.metric) {
-    case HX_METRIC_EUCLIDEAN: HX_LAUNCH_HNSW(HXM_EUCLIDEAN); break;
-    case HX_METRIC_COSINE: HX_LAUNCH_HNSW(HXM_COSINE); break;
-    default: HX_LAUNCH_HNSW(HXM_MANHATTAN); break;
+  if (use_cta_ring) {
+    if ((rc = hx_launch_cta_ring(ix, cta_cfg, a, rg, grid, stream, nullptr))) return rc;
+  } else {
+    switch (ix->cfg.metric) {
+      case HX_METRIC_EUCLIDEAN: HX_LAUNCH_RING_Q(HXM_EUCLIDEAN); break;
+      case HX_METRIC_COSINE: HX_LAUNCH_RING_Q(HXM_COSINE); break;
+      default: HX_LAUNCH_RING(HXM_MANHATTAN, 0); break;
+    }
   }
-#undef HX_LAUNCH_HNSW
+#undef HX_LAUNCH_RING_Q
 #undef HX_LAUNCH_RING
-#undef HX_LAUNCH_WARP
   HX_CUDA(cudaGetLastError());
   HX_CUDA(cudaEventRecord(e1, stream));
   *timed = true;
@@ -1633,7 +1555,7 @@ static hx_status report_batch(HxScratch* s, size_t B, uint32_t* out_counts, hx_s
     }
     if (st && !first) first = st;
   }
-  if (!out_status && batch_flags) {   // a flag no query owns (copy time-out, first-generation kernels)
+  if (!out_status && batch_flags) {   // a flag no query owns (copy time-out)
     hx_status rc = check_device_flags(batch_flags);
     if (rc) return rc;
   }
@@ -1700,7 +1622,7 @@ static hx_status hx_search_strict(hx_index* ix, const float* queries, size_t B, 
   // by a 4-byte copy that publishes how many queries have landed; the search kernel is already running, validates every
   // query itself (no separate k_validate_and_header launch) and only waits for the chunk a query belongs to.
   bool pipelined = B >= 1024 && hnsw_uses_ring(ix, B) && ix->n != 0 && ix->populated;
-  if (const char* env = getenv("HX_PIPELINE")) pipelined = pipelined && atoi(env) != 0;
+  pipelined = pipelined && knob(ix->tune.pipeline, 1) != 0;
   HxFusedArgs fz;
   if (pipelined) {
     const uint32_t dim = ix->cfg.dimension;
@@ -1902,7 +1824,7 @@ static hx_status launch_scan_select(hx_index* ix, HxScratch* s, const float* d_q
   // kernel, the last CTA of each query merges the per-CTA lists; no key array in HBM, no k_select launch
   const uint32_t chunk_pick = pick_chunk(total_keys, ix->sm_count);
   const uint32_t n_chunks = (uint32_t)((max_cands + chunk_pick - 1) / chunk_pick);
-  static const bool fused_off = getenv("HX_SCAN_FUSED") && atoi(getenv("HX_SCAN_FUSED")) == 0;
+  const bool fused_off = knob(ix->tune.scan_fused, 1) == 0;
   const bool fused_topk = !fused_off && k <= HX_TOPK && ix->cfg.metric != HX_METRIC_MANHATTAN && B <= 65535 &&
                           (size_t)B * n_chunks * HX_TOPK * 8 <= (256ull << 20);
   if (fused_topk) {
@@ -2517,12 +2439,10 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   const size_t budget = 227 * 1024;
   uint32_t wpc = 0, R = 0;
   const uint32_t spread = (uint32_t)std::max<size_t>(1, (B + ix->sm_count - 1) / (size_t)ix->sm_count);
-  uint32_t pol_warps = 16, pol_minR = 3;   // fewer rows per expansion survive the gate: 3 slots suffice
-  if (const char* env = getenv("HX_POL_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 16) pol_warps = (uint32_t)v; }
-  if (const char* env = getenv("HX_POL_MINR")) { const int v = atoi(env); if (v >= 1 && v <= 32) pol_minR = (uint32_t)v; }
+  const hx_tuning& t = ix->tune;
+  const uint32_t pol_warps = knob(t.pol_warps, 16), pol_minR = knob(t.pol_min_rows, 3);   // fewer rows per expansion survive the gate: 3 slots suffice
   // B < #SMs: one CTA per query (warp 0 runs the query, 7 more warps reduce rows with it)
-  bool pol_cta = B < (size_t)ix->sm_count;
-  if (const char* env = getenv("HX_POL_CTA")) pol_cta = pol_cta && atoi(env) != 0;
+  const bool pol_cta = B < (size_t)ix->sm_count && knob(t.pol_cta, 1) != 0;
   for (uint32_t w = pol_cta ? 1u : std::min(pol_warps, spread); w >= 1; --w) {
     const size_t per_warp = (budget / w) & ~(size_t)127;
     if (per_warp <= fixed0 + 8 + rowbytes) continue;
@@ -2536,8 +2456,7 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   uint32_t wstride = round_up((uint32_t)(fixed0 + (size_t)R * (rowbytes + 8)), 128);
   uint32_t lg = 12;
   while ((1u << lg) < 64u * ef && lg < 24) lg++;
-  if (const char* env = getenv("HX_VT_CAP_LOG2")) { const int v = atoi(env); if (v >= 6 && v <= 24) lg = (uint32_t)v; }
-  uint32_t vt_cap = 1u << lg;
+  uint32_t vt_cap = 1u << knob(t.visited_log2, lg);
   size_t cta_vt_bytes = 0;
   if (pol_cta) {   // the visited set sits in shared memory behind the query's region: shrink rows / table until it fits
     while (vt_cap > 1024 && (size_t)vt_cap * 4 > budget / 4) vt_cap >>= 1;
@@ -2551,8 +2470,7 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   }
   const uint32_t grid = (uint32_t)std::min<size_t>((B + wpc - 1) / wpc, (size_t)ix->sm_count);
   const size_t vslots = (size_t)grid * wpc;
-  uint32_t pool_n = 32;
-  if (const char* env = getenv("HX_VT_POOL")) { const int v = atoi(env); if (v >= 0 && v <= 1024) pool_n = (uint32_t)v; }
+  const uint32_t pool_n = knob(t.visited_pool, 32);
   const uint32_t pool_cap = std::max<uint32_t>(vt_cap * 16u, 65536u);
   if ((rc = s->d_vtab.reserve(vslots * vt_cap))) return rc;
   if (s->vpool_n != pool_n || s->vpool_cap != pool_cap || !s->d_vbusy.p) {
@@ -2577,8 +2495,7 @@ static hx_status launch_policy(hx_index* ix, HxScratch* s, const float* d_querie
   rg.l2_hint = 1;
   if ((rc = setup_tie_pool(s, &rg, stream))) return rc;
   if ((rc = s->d_qerr.reserve(B))) return rc;
-  rg.l2_spec = 1;   // policy kernel: fingerprints requested together with the visited probe (HX_POL_EARLY_SIM=0: after it)
-  if (const char* env = getenv("HX_POL_EARLY_SIM")) rg.l2_spec = atoi(env) ? 1u : 0u;
+  rg.l2_spec = knob(t.pol_early_sim, 1);   // policy kernel: fingerprints requested together with the visited probe (0: after it)
   HxHnswArgs a{};
   a.queries = d_queries;
   a.q_hdr = s->d_qhdr.p;

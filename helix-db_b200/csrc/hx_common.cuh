@@ -64,6 +64,9 @@ __device__ __forceinline__ void hx_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hx_smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void hx_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void hx_mbar_arrive(uint64_t* bar) {   // release at CTA scope: earlier shared-memory writes are visible to the waiters
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hx_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void hx_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hx_smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -94,9 +94,8 @@ struct HxScratch {
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_queries, d_qhdr, d_out_scores;
-  DevBuf<uint32_t> d_qstatus, d_out_counts, d_qstats, d_err, d_epochs, d_cand_slots;
+  DevBuf<uint32_t> d_qstatus, d_out_counts, d_qstats, d_err, d_cand_slots;
   DevBuf<uint64_t> d_out_ids, d_cand_ids, d_cand_offsets, d_keys;
-  DevBuf<uint8_t> d_stamps;
   DevBuf<uint32_t> d_vtab, d_vpool, d_vbusy;   // ring build: visited hash sets, overflow pool, pool busy flags
   uint32_t vpool_n = 0xffffffffu, vpool_cap = 0;
   DevBuf<uint64_t> d_tiepool;                  // overflow regions of the tie stack (HxRingArgs::tie_pool)
@@ -120,9 +119,6 @@ struct HxScratch {
   HxDenseCache dense;
   DevBuf<uint8_t> d_block;    // small calls: results packed into one block -> one device-to-host copy
   PinBuf<uint8_t> h_block;
-  size_t stamp_stride = 0;
-  uint32_t stamp_grid = 0;
-  size_t stamp_n = 0;
   PinBuf<uint64_t> h_ids, h_cand_offsets;
   PinBuf<float> h_scores, h_queries, h_qhdr;
   PinBuf<uint32_t> h_counts, h_qstats, h_status, h_err, h_avail;
@@ -143,6 +139,7 @@ struct HxLayerRows {   // host staging of one mirrored HNSW layer (slot space)
 
 struct hx_index {
   hx_index_config cfg{};
+  hx_tuning tune{};   // launch-shape knobs: environment at hx_index_create, hx_index_set_tuning afterwards
   int device = 0;
   int sm_count = 148;
   uint32_t lim0 = 32;   // MutationDegreeLimits.layer0 = max(m0, 2m)  (mutation.rs:179-199)

@@ -290,10 +290,6 @@ extern "C" hx_status hx_service_create(hx_index* ix, const hx_service_config* cf
     hx_set_error("search beam width must be in [k, 4096], got %u", ef);
     return HX_ERR_INVALID_PARAMETER;
   }
-  if (ix->cfg.metric == HX_METRIC_MANHATTAN) {
-    hx_set_error("the query service serves the Euclidean and cosine metrics");
-    return HX_ERR_UNSUPPORTED;
-  }
   HX_CUDA(cudaSetDevice(ix->device));
   hx_status rc = hx_finalize_graph(ix);
   if (rc) return rc;

@@ -743,10 +743,8 @@ hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed, 
   const size_t urows = n + rows;
   uint32_t max_batch = (uint32_t)std::min<size_t>(16384, std::max<size_t>(1, n / 64));
   if (sequential) max_batch = 1;   // HX_BUILD_SEQUENTIAL: one insert at a time, links applied in selection order
-  if (const char* env = getenv("HX_BUILD_MAX_BATCH")) {   // experiment knob: rounds never exceed this many nodes
-    const long v = atol(env);
-    if (v > 0) max_batch = (uint32_t)std::min<long>(v, 65536);
-  }
+  if (ix->tune.build_max_batch > 0 && !sequential)   // experiment knob: rounds never exceed this many nodes
+    max_batch = (uint32_t)std::min<int32_t>(ix->tune.build_max_batch, 65536);
   const uint32_t maxL_all = (uint32_t)top;
   const uint32_t pstride = lim0 + maxL_all * m;
   const uint32_t rstride = std::max(lim0, m);

@@ -232,11 +232,6 @@ __device__ __forceinline__ uint32_t hxp_choose_index(HxSession& s, uint32_t coun
   return result;
 }
 
-// CTA build: warp 0 (the query) and the helper warps rendezvous from DIFFERENT call sites.  `__syncthreads()` works there
-// (bar.sync 0 only counts arrivals) but is outside the programming model and is what compute-sanitizer's synccheck flags
-// as "divergent threads in block"; a named barrier with an explicit thread count says what is meant.
-__device__ __forceinline__ void hxp_cta_sync() { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x) : "memory"); }
-
 // read-only membership probe of the visited set
 __device__ __forceinline__ bool hx_vt_contains(const HxVisited& v, uint32_t key) {
   uint32_t h = (key * 2654435761u) >> v.shift;
@@ -258,7 +253,11 @@ template <int METRIC, int QCH, bool CTA>
 __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy(HxDev ix, HxHnswArgs a, HxRingArgs rg,
                                                                                 HxPolicyArgs pa, uint32_t wstride, uint32_t R) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint32_t s_cmd, s_cnt;      // CTA mode: warp 0 -> helpers (1 = score s_cnt rows of `frontier`, 2 = done)
+  // CTA mode: warp 0 (the query) and the helper warps meet from different places in the code, so the rendezvous is a pair
+  // of mbarriers, not __syncthreads(): s_bar_cmd (1 arrival: warp 0 posts a command) and s_bar_done (one arrival per helper
+  // warp: its share of the rows is scored and visible)
+  __shared__ uint32_t s_cmd, s_cnt;      // warp 0 -> helpers (1 = score s_cnt rows of `frontier`, 2 = done)
+  __shared__ __align__(8) uint64_t s_bar_cmd, s_bar_done;
   __shared__ float s_qhdr;
   __shared__ const float* s_qg;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -283,8 +282,13 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
   const uint32_t rowbytes = ix.ld * 4u;
   const uint64_t policy = hx_policy_evict_first();
   uint32_t ph = 0;
+  uint32_t pc = 0, pd = 0;   // phase parity of the command / done barriers
   if (CTA) {
     if (threadIdx.x < R) hx_mbar_init(bars + threadIdx.x, 1);
+    if (threadIdx.x == 0) {
+      hx_mbar_init(&s_bar_cmd, 1);
+      hx_mbar_init(&s_bar_done, W > 1 ? W - 1 : 1);
+    }
     hx_fence_mbar_init();
     __syncthreads();
   } else {
@@ -307,6 +311,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
   // CTA mode: every warp's share of one pass of `rows` rows starting at list[base] (slot = row index within the pass)
   auto score_share = [&](const uint32_t* list, uint32_t base, uint32_t rows) {
     const uint32_t mine = lane * W + warp;
+    if (METRIC == HXM_MANHATTAN) {   // one strictly sequential chain per row (simple.rs:186-202): one thread per row, from global memory
+      if (mine < rows) fdist[base + mine] = hx_manhattan_seq(ix.vec + (size_t)list[base + mine] * ix.ld, sq, ix.dim);
+      return;
+    }
     float rh = 0.f;
     if (mine < rows) {
       const uint32_t slot = list[base + mine];
@@ -317,41 +325,45 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     for (uint32_t r = warp; r < rows; r += W, ++j) {
       const float row_hdr = __shfl_sync(FULL, rh, j);
       hx_mbar_wait(bars + r, (ph >> r) & 1u);
-      float sc;
-      if (METRIC == HXM_MANHATTAN) {
-        sc = 0.0f;
-        const float* row = ring + (size_t)r * ix.ld;
-        for (uint32_t i = 0; i < ix.dim; ++i) sc = __fadd_rn(sc, fabsf(__fsub_rn(sq[i], row[i])));
-      } else {
-        sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
-            ring + (size_t)r * ix.ld, qr, sq, qg, q_hdr, row_hdr, ix.dim, lane);
-      }
+      const float sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
+          ring + (size_t)r * ix.ld, qr, sq, qg, q_hdr, row_hdr, ix.dim, lane);
       if (lane == 0) fdist[base + r] = sc;
     }
     ph ^= rows >= 32u ? FULL : ((1u << rows) - 1u);
   };
   if (CTA && warp != 0) {   // helpers: score on command until warp 0 says done
     for (;;) {
-      hxp_cta_sync();
+      hx_mbar_wait(&s_bar_cmd, pc);
+      pc ^= 1u;
       if (s_cmd == 2u) return;
       const uint32_t cnt = s_cnt;
       q_hdr = s_qhdr;
       qg = s_qg;
-      for (uint32_t base = 0; base < cnt; base += R) {
-        score_share(frontier, base, min(R, cnt - base));
-        hxp_cta_sync();
-      }
+      // a row slot is only ever touched by the warp that owns it (slot r -> warp r mod W): passes need no rendezvous
+      for (uint32_t base = 0; base < cnt; base += R) score_share(frontier, base, min(R, cnt - base));
+      __syncwarp();
+      if (lane == 0) hx_mbar_arrive(&s_bar_done);
     }
   }
   auto score_list = [&](const uint32_t* list, uint32_t cnt) {
     if (CTA) {   // list == frontier (always, in this kernel)
       if (cnt == 0) return;
-      if (lane == 0) { s_cmd = 1u; s_cnt = cnt; s_qhdr = q_hdr; s_qg = qg; }
-      hxp_cta_sync();
-      for (uint32_t base = 0; base < cnt; base += R) {
-        score_share(list, base, min(R, cnt - base));
-        hxp_cta_sync();
+      if (lane == 0) {
+        s_cmd = 1u; s_cnt = cnt; s_qhdr = q_hdr; s_qg = qg;
+        hx_mbar_arrive(&s_bar_cmd);
       }
+      __syncwarp();
+      for (uint32_t base = 0; base < cnt; base += R) score_share(list, base, min(R, cnt - base));
+      if (W > 1) {   // every helper's scores are in fdist (and `list` may be rewritten)
+        hx_mbar_wait(&s_bar_done, pd);
+        pd ^= 1u;
+      }
+      __syncwarp();
+      return;
+    }
+    if (METRIC == HXM_MANHATTAN) {   // lane f walks row f's sequential chain, straight from global memory
+      for (uint32_t f = lane; f < cnt; f += 32) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)list[f] * ix.ld, sq, ix.dim);
+      __syncwarp();
       return;
     }
     if (lane < min(R, cnt)) issue(lane, list[lane]);
@@ -362,15 +374,8 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     for (uint32_t j = 0; j < cnt; ++j) {
       hx_mbar_wait(bars + s, (ph >> s) & 1u);
       ph ^= 1u << s;
-      float sc;
-      if (METRIC == HXM_MANHATTAN) {
-        sc = 0.0f;   // one sequential chain (simple.rs:186-202); every lane walks it, reads are broadcasts
-        const float* row = ring + (size_t)s * ix.ld;
-        for (uint32_t i = 0; i < ix.dim; ++i) sc = __fadd_rn(sc, fabsf(__fsub_rn(sq[i], row[i])));
-      } else {
-        sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
-            ring + (size_t)s * ix.ld, qr, sq, qg, q_hdr, METRIC == HXM_COSINE ? fhdr[j] : 0.f, ix.dim, lane);
-      }
+      const float sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
+          ring + (size_t)s * ix.ld, qr, sq, qg, q_hdr, METRIC == HXM_COSINE ? fhdr[j] : 0.f, ix.dim, lane);
       if (lane == 0) fdist[j] = sc;
       __syncwarp();
       if (j + R < cnt && lane == 0) issue(s, list[j + R]);
@@ -738,8 +743,10 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     __syncwarp();
   }
   if (CTA) {   // warp 0: release the helpers
-    if (lane == 0) s_cmd = 2u;
-    hxp_cta_sync();
+    if (lane == 0) {
+      s_cmd = 2u;
+      hx_mbar_arrive(&s_bar_cmd);
+    }
   }
   if (pa.pstats && lane == 0)
     for (int i = 0; i < 12; ++i)

@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
   float qr[QCH > 0 ? QCH : 1];
   const float* qg = nullptr;
   float q_hdr = 0.f;
+  constexpr int MS = METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC;   // the warp reduction is never run for Manhattan
 
   auto issue = [&](uint32_t s, uint32_t slot) {   // one lane
     hx_mbar_expect_tx(bars + s, rowbytes);
@@ -348,6 +349,22 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
   };
   // score the rows whose slots are list[0..cnt) into fdist[0..cnt)
   auto score_list = [&](const uint32_t* list, uint32_t cnt) {
+    if (METRIC == HXM_MANHATTAN) {
+      // one strictly sequential chain per row (simple.rs:186-202): lane f walks row f, straight from global memory
+      for (uint32_t f = lane; f < cnt; f += 32) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)list[f] * ix.ld, sq, ix.dim);
+      __syncwarp();
+      return;
+    }
+    if (R == 0) {   // a row does not fit next to the query state (dim in the tens of thousands): reduce it from global memory
+      for (uint32_t j = 0; j < cnt; ++j) {
+        const uint32_t slot = list[j];
+        const float sc = hx_warp_score<MS, QCH>(ix.vec + (size_t)slot * ix.ld, qr, sq, qg, q_hdr,
+                                                METRIC == HXM_COSINE ? __ldg(ix.hdr + slot) : 0.f, ix.dim, lane);
+        if (lane == 0) fdist[j] = sc;
+      }
+      __syncwarp();
+      return;
+    }
     if (lane < min(R, cnt)) issue(lane, list[lane]);
     if (METRIC == HXM_COSINE)
       for (uint32_t f = lane; f < cnt; f += 32) fhdr[f] = __ldg(ix.hdr + list[f]);
@@ -356,8 +373,8 @@ __global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxD
     for (uint32_t j = 0; j < cnt; ++j) {
       hx_mbar_wait(bars + s, (ph >> s) & 1u);
       ph ^= 1u << s;
-      const float sc = hx_warp_score<METRIC, QCH>(ring + (size_t)s * ix.ld, qr, sq, qg, q_hdr,
-                                                  METRIC == HXM_COSINE ? fhdr[j] : 0.f, ix.dim, lane);
+      const float sc = hx_warp_score<MS, QCH>(ring + (size_t)s * ix.ld, qr, sq, qg, q_hdr,
+                                              METRIC == HXM_COSINE ? fhdr[j] : 0.f, ix.dim, lane);
       if (lane == 0) fdist[j] = sc;
       __syncwarp();   // every lane is done with slot s
       if (j + R < cnt && lane == 0) issue(s, list[j + R]);
@@ -815,6 +832,13 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
   // all threads: reduce list[0..cnt) (shared memory, visible to every warp) into fdist.  Warp w owns slots and rows
   // w, w+W, ...: it issues their copies itself (lane j -> its j-th row), so a slot is only ever touched by one warp.
   auto score_list = [&](const uint32_t* list, uint32_t cnt, auto&& after_issue) {
+    if (METRIC == HXM_MANHATTAN) {
+      // one strictly sequential chain per row (simple.rs:186-202): thread f walks row f, straight from global memory
+      for (uint32_t f = tid; f < cnt; f += blockDim.x) fdist[f] = hx_manhattan_seq(ix.vec + (size_t)list[f] * ix.ld, sq, ix.dim);
+      if (cnt) after_issue();
+      __syncthreads();
+      return;
+    }
     for (uint32_t base = 0; base < cnt; base += RC) {
       const uint32_t rows = min(RC, cnt - base);
       const uint32_t mine = lane * W + warp;   // the row this lane issues
@@ -831,7 +855,8 @@ __global__ void __launch_bounds__(QCH >= 48 ? 256 : HX_CTA_RING_MAX_THREADS, 1)
       for (uint32_t r = warp; r < rows; r += W, ++j) {
         const float row_hdr = __shfl_sync(FULL, rh, j);
         hx_mbar_wait(bars + r, (ph >> r) & 1u);
-        const float sc = hx_warp_score<METRIC, QCH>(ring + (size_t)r * ix.ld, qr, sq, qg, q_hdr, row_hdr, ix.dim, lane);
+        const float sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), QCH>(
+            ring + (size_t)r * ix.ld, qr, sq, qg, q_hdr, row_hdr, ix.dim, lane);
         if (lane == 0) fdist[base + r] = sc;
       }
       ph ^= rows >= 32u ? FULL : ((1u << rows) - 1u);

@@ -536,10 +536,37 @@ const char* hx_last_error(void);          /* thread-local, valid until the next 
 uint32_t    hx_last_error_index(void);    /* component index for HX_ERR_INVALID_VECTOR_COMPONENT */
 const char* hx_version(void);
 /* Device time (ms, CUDA events recorded on the launch stream around the dominant kernel:
- * k_hnsw_search or k_scan) and launch count.  After host-buffer calls: the most recent call.
+ * the traversal kernel or the scan) and launch count.  After host-buffer calls: the most recent call.
  * After device-buffer calls: the SUM over every launch since the previous hx_last_kernel_ms
  * (the call synchronises on the recorded events). */
 hx_status hx_last_kernel_ms(hx_index* idx, float* ms, uint32_t* launches);
+
+/* Launch-shape knobs of the traversal kernels, for experiments and A/B tests (every default is the measured best; results
+ * are bit-identical for every setting — tests/test_gpu_parity.py::test_traversal_builds_agree).  A handle takes its values
+ * from the environment ONCE, in hx_index_create (the variable named next to each field); nothing on the search path reads
+ * the environment.  -1 in any field = the built-in default.  hx_index_set_tuning(idx, NULL) re-reads the environment.
+ * Not synchronised with searches in flight on the same handle. */
+typedef struct hx_tuning {
+  int32_t ring_warps;      /* HX_RING_WARPS      warp-per-query build: warps per SM, 1..16 (16)                    */
+  int32_t ring_rows;       /* HX_RING_R          row slots per warp / rows in flight per CTA, 1..32 (what fits)     */
+  int32_t visited_log2;    /* HX_VT_CAP_LOG2     log2 entries of a query's visited hash set, 6..24 (64 ef rounded)  */
+  int32_t visited_pool;    /* HX_VT_POOL         overflow tables, 0..1024 (32)                                     */
+  int32_t l2_hint;         /* HX_L2_HINT         evict-first hint on row copies (1)                                 */
+  int32_t prefetch_below;  /* HX_PREFETCH_BELOW  beam position below which an admitted row is L2-prefetched (ef/2+1)*/
+  int32_t lat_warps;       /* HX_LAT_WARPS       CTA-per-query build: warps per CTA, 1..12 (12; 8 above d = 1024)   */
+  int32_t lat_admit_seq;   /* HX_LAT_ADMIT=seq   CTA build: sequential instead of one-pass admission (0)           */
+  int32_t lat_spec;        /* HX_LAT_SPEC        CTA build: speculative L2 prefetch of the next expansion (0)       */
+  int32_t phase_prof;      /* HX_PHASE_PROF      CTA build: per-phase cycle sums, printed by hx_last_kernel_ms (0)  */
+  int32_t pipeline;        /* HX_PIPELINE        chunked query upload overlapped with the search (1)               */
+  int32_t scan_fused;      /* HX_SCAN_FUSED      prefilter scan: in-kernel top-k for k <= 32 (1)                    */
+  int32_t pol_warps;       /* HX_POL_WARPS       default-mode kernel: warps per SM, 1..16 (16)                      */
+  int32_t pol_min_rows;    /* HX_POL_MINR        default-mode kernel: least row slots per warp (3)                  */
+  int32_t pol_cta;         /* HX_POL_CTA         default-mode kernel: CTA-per-query build below #SMs queries (1)    */
+  int32_t pol_early_sim;   /* HX_POL_EARLY_SIM   fingerprints requested together with the visited probe (1)         */
+  int32_t build_max_batch; /* HX_BUILD_MAX_BATCH device build: cap on the nodes inserted per round (n/64, <= 16384) */
+} hx_tuning;
+hx_status hx_index_get_tuning(const hx_index* idx, hx_tuning* out);
+hx_status hx_index_set_tuning(hx_index* idx, const hx_tuning* tuning);
 
 #ifdef __cplusplus
 }

@@ -345,11 +345,13 @@ def test_many_queries_and_epoch_wrap():
         assert a[0].tolist() == oi[it % 7].tolist() and b[0].tobytes() == os_[it % 7].tobytes()
 
 
-# ---- every build of the traversal kernel answers with the same bits: ring (default), first-generation TMA / LDG builds,
-# ---- and the ring build with visited tables so small that every query re-hashes into the overflow pool ------------------
+# ---- every launch shape of the traversal kernels answers with the same bits: default, tiny visited tables (every query
+# ---- re-hashes into the overflow pool), few warps / shallow rings, every admission strategy of the CTA build, and the
+# ---- dimension whose row does not fit a warp's share (d = 1600: the warp build reduces rows of 6.4 KB through 1-2 slots)
 @pytest.mark.parametrize("gm,om,dim", [(hx.Metric.Euclidean, hxo.EUCLIDEAN, 70), (hx.Metric.Cosine, hxo.COSINE, 768),
-                                       (hx.Metric.Cosine, hxo.COSINE, 40), (hx.Metric.Euclidean, hxo.EUCLIDEAN, 1600)])
-def test_traversal_builds_agree(gm, om, dim, monkeypatch):
+                                       (hx.Metric.Cosine, hxo.COSINE, 40), (hx.Metric.Euclidean, hxo.EUCLIDEAN, 1600),
+                                       (hx.Metric.Manhattan, hxo.MANHATTAN, 96)])
+def test_traversal_builds_agree(gm, om, dim):
     n, nq = (1200, 320) if dim < 1000 else (500, 300)
     rng = np.random.default_rng(dim + 7)
     rows = rng.standard_normal((n, dim)).astype(np.float32)
@@ -359,40 +361,32 @@ def test_traversal_builds_agree(gm, om, dim, monkeypatch):
     oi, os_, oc, ost, _ = ora.search_batch(queries, k, ef, threads=4)
     params = hx.SearchParams.strict(k, ef)
     params.collect_stats = True
-    variants = [{}, {"HX_HNSW_IMPL": "tma"}, {"HX_HNSW_IMPL": "ldg"}, {"HX_VT_CAP_LOG2": "6"},
-                {"HX_RING_WARPS": "5", "HX_RING_R": "2", "HX_L2_HINT": "0"}, {"HX_RING_R": "1"}]
-    for env in variants:
-        for key in ("HX_HNSW_IMPL", "HX_VT_CAP_LOG2", "HX_RING_WARPS", "HX_RING_R", "HX_L2_HINT"):
-            monkeypatch.delenv(key, raising=False)
-        for key, val in env.items():
-            monkeypatch.setenv(key, val)
+    variants = [{}, {"visited_log2": 6}, {"ring_warps": 5, "ring_rows": 2, "l2_hint": 0}, {"ring_rows": 1},
+                {"ring_warps": 1, "prefetch_below": 0}, {"pipeline": 0}]
+    for knobs in variants:
+        gpu.tune(**knobs)
         st = hx.SearchStats()
         gi, gs, gc = gpu.search_batch(queries, params, st)
-        assert gc.tolist() == oc.tolist(), env
-        assert gi.tolist() == oi.tolist(), env
-        assert gs.tobytes() == os_.tobytes(), env
+        assert gc.tolist() == oc.tolist(), knobs
+        assert gi.tolist() == oi.tolist(), knobs
+        assert gs.tobytes() == os_.tobytes(), knobs
         for f in ("expansion_steps", "neighbors_examined", "distance_computations"):
-            assert getattr(st, f) == ost[f], (f, env)
-    # small batches (B < #SMs) take the CTA-per-query builds: ring (visited set in shared memory) vs first generation
+            assert getattr(st, f) == ost[f], (f, knobs)
+    # small batches (B < #SMs) take the CTA-per-query build (visited set in shared memory, register beam up to ef = 128)
     nsmall = 40
     _, _, _, sst, _ = ora.search_batch(queries[:nsmall], k, ef, threads=4)
     small_stats = (sst["expansion_steps"], sst["neighbors_examined"], sst["distance_computations"])
-    for env in [{}, {"HX_LAT_IMPL": "tma"}, {"HX_LAT_IMPL": "ldg"}, {"HX_VT_CAP_LOG2": "6"}, {"HX_RING_R": "3"},
-                {"HX_LAT_WARPS": "3", "HX_L2_HINT": "0"}, {"HX_LAT_SPEC": "1"}, {"HX_LAT_WARPS": "1"},
-                {"HX_LAT_ADMIT": "seq", "HX_VT_CAP_LOG2": "7"}]:
-        for key in ("HX_HNSW_IMPL", "HX_LAT_IMPL", "HX_VT_CAP_LOG2", "HX_RING_WARPS", "HX_RING_R", "HX_L2_HINT", "HX_LAT_WARPS",
-                    "HX_LAT_SPEC", "HX_LAT_ADMIT"):
-            monkeypatch.delenv(key, raising=False)
-        for key, val in env.items():
-            monkeypatch.setenv(key, val)
+    for knobs in [{}, {"visited_log2": 6}, {"ring_rows": 3}, {"lat_warps": 3, "l2_hint": 0}, {"lat_spec": 1}, {"lat_warps": 1},
+                  {"lat_admit_seq": 1, "visited_log2": 7}]:
+        gpu.tune(**knobs)
         st = hx.SearchStats()
         gi, gs, gc = gpu.search_batch(queries[:nsmall], params, st)
-        assert gc.tolist() == oc[:nsmall].tolist(), env
-        assert gi.tolist() == oi[:nsmall].tolist(), env
-        assert gs.tobytes() == os_[:nsmall].tobytes(), env
-        assert (st.expansion_steps, st.neighbors_examined, st.distance_computations) == small_stats, env
-    for key in ("HX_LAT_WARPS", "HX_L2_HINT", "HX_LAT_SPEC", "HX_LAT_ADMIT", "HX_VT_CAP_LOG2"):
-        monkeypatch.delenv(key, raising=False)
+        assert gc.tolist() == oc[:nsmall].tolist(), knobs
+        assert gi.tolist() == oi[:nsmall].tolist(), knobs
+        assert gs.tobytes() == os_[:nsmall].tobytes(), knobs
+        assert (st.expansion_steps, st.neighbors_examined, st.distance_computations) == small_stats, knobs
+    gpu.tune()
+    assert gpu.tuning()["visited_log2"] == -1
     # beams wider than 128 entries take the shared-memory beam of the latency build (the register beam holds 4 x 32)
     wi, ws, wc, _, _ = ora.search_batch(queries[:nsmall], k, 200, threads=4)
     gi, gs, gc = gpu.search_batch(queries[:nsmall], hx.SearchParams.strict(k, 200))
@@ -401,17 +395,35 @@ def test_traversal_builds_agree(gm, om, dim, monkeypatch):
     wi, ws, wc, _, _ = ora.search_batch(queries[:nsmall], k, 128, threads=4)
     assert gc.tolist() == wc.tolist() and gi.tolist() == wi.tolist() and gs.tobytes() == ws.tobytes()
     # a pool of zero overflow tables: the overflow is reported, never silently truncated
-    monkeypatch.setenv("HX_VT_CAP_LOG2", "6")
-    monkeypatch.setenv("HX_VT_POOL", "0")
+    gpu.tune(visited_log2=6, visited_pool=0)
     with pytest.raises(hx.HelixDbError) as e:
         gpu.search_batch(queries, params)
     assert e.value.variant == "InvariantViolation"
+    gpu.tune()
+    with pytest.raises(TypeError):
+        gpu.tune(no_such_knob=1)
+
+
+# ---- rows too large to stage (d = 12 288: 48 KB per row): the CTA build cannot hold a row next to its visited table and a
+# ---- warp's share holds at most a few, down to none (ring_rows is capped by what fits) — results still bit-exact
+@pytest.mark.parametrize("dim", [12288, 30016])      # 30016: not even one 120 KB row fits next to the 120 KB query -> R = 0
+def test_very_large_dimension(dim):
+    n, nq = 300, 160
+    rng = np.random.default_rng(5)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    gpu, ora = build_pair(hx.Metric.Cosine, hxo.COSINE, rows, m=6, m0=12, efc=30)
+    oi, os_, oc, _, _ = ora.search_batch(queries, 5, 24, threads=4)
+    params = hx.SearchParams.strict(5, 24)
+    for b in (nq, 9, 1):
+        gi, gs, gc = gpu.search_batch(queries[:b], params)
+        assert gc.tolist() == oc[:b].tolist() and gi.tolist() == oi[:b].tolist() and gs.tobytes() == os_[:b].tobytes(), b
 
 
 # ---- exact score ties at the beam boundary (duplicate vectors): the tie stack / `dropped` bookkeeping decides
 # ---- expansion_steps, so ids, scores AND counters must match for every admission strategy ----------------------------------
 @pytest.mark.parametrize("gm,om", METRICS[:2])
-def test_exact_ties_at_beam_boundary(gm, om, monkeypatch):
+def test_exact_ties_at_beam_boundary(gm, om):
     rng = np.random.default_rng(99)
     n, dim, nq = 1000, 4, 200
     rows = rng.integers(0, 5, size=(n, dim)).astype(np.float32) + 1.0      # 625 grid positions: many identical vectors
@@ -421,11 +433,8 @@ def test_exact_ties_at_beam_boundary(gm, om, monkeypatch):
         oi, os_, oc, _, _ = ora.search_batch(queries, k, ef, threads=4)
         per_q = [ora.search(queries[q], k, ef=ef, with_stats=True)[2] for q in range(24)]
         params = hx.SearchParams.strict(k, ef)
-        for env in ({}, {"HX_LAT_ADMIT": "seq"}, {"HX_LAT_IMPL": "tma"}):
-            for key in ("HX_LAT_ADMIT", "HX_LAT_IMPL"):
-                monkeypatch.delenv(key, raising=False)
-            for key, val in env.items():
-                monkeypatch.setenv(key, val)
+        for env in ({}, {"lat_admit_seq": 1}, {"ring_rows": 2, "lat_warps": 2}):
+            gpu.tune(**env)
             gi, gs, gc = gpu.search_batch(queries, params)                     # warp-per-query builds
             assert gc.tolist() == oc.tolist() and gi.tolist() == oi.tolist() and gs.tobytes() == os_.tobytes(), (ef, env)
             gi, gs, gc = gpu.search_batch(queries[:100], params)               # CTA-per-query builds
@@ -442,7 +451,7 @@ def test_exact_ties_at_beam_boundary(gm, om, monkeypatch):
 
 # ---- large host batches are pipelined: chunked H2D on a second stream, validation fused into the search kernel ----------
 @pytest.mark.parametrize("gm,om", METRICS[:2])
-def test_pipelined_host_search(gm, om, monkeypatch):
+def test_pipelined_host_search(gm, om):
     n, dim, nq = 1500, 40, 3000
     rng = np.random.default_rng(8)
     rows = rng.standard_normal((n, dim)).astype(np.float32)
@@ -451,7 +460,7 @@ def test_pipelined_host_search(gm, om, monkeypatch):
     params = hx.SearchParams.strict(5, 24)
     oi, os_, oc, ost, _ = ora.search_batch(queries, 5, 24, threads=4)
     for pipe in ("1", "0"):
-        monkeypatch.setenv("HX_PIPELINE", pipe)
+        gpu.tune(pipeline=int(pipe))
         st = hx.SearchStats()
         params.collect_stats = True
         gi, gs, gc = gpu.search_batch(queries, params, st)

@@ -59,12 +59,11 @@ def compare(gpu, ora, queries, qsim, params, cfg, what):
     si, ss, scnt = gpu.search_ex(queries[:40], params, query_simhash=qsim[:40], stats=st2, policy_stats=ps2)
     assert si.tolist() == gi[:40].tolist() and ss.tobytes() == gs[:40].tobytes() and scnt.tolist() == gc[:40].tolist(), what
     st3, ps3 = hx.SearchStats(), hx.PolicyStats()
-    import os
-    os.environ["HX_POL_CTA"] = "0"
+    gpu.tune(pol_cta=0)                                   # the warp-per-query build for the same 40 queries
     try:
         gpu.search_ex(queries[:40], params, query_simhash=qsim[:40], stats=st3, policy_stats=ps3)
     finally:
-        del os.environ["HX_POL_CTA"]
+        gpu.tune()
     assert ps2.as_dict() == ps3.as_dict() and st2.expansion_steps == st3.expansion_steps, what
     return ptot
 

@@ -21,7 +21,8 @@ def _pairs(results):
 
 
 @pytest.mark.parametrize("gm,om,n,dim", [(hx.Metric.Euclidean, hxo.EUCLIDEAN, 3000, 64),
-                                         (hx.Metric.Cosine, hxo.COSINE, 1500, 768)])
+                                         (hx.Metric.Cosine, hxo.COSINE, 1500, 768),
+                                         (hx.Metric.Manhattan, hxo.MANHATTAN, 1200, 40)])
 @pytest.mark.parametrize("ctas_per_sm", [1, 2, 3])
 def test_service_bit_exact_blocking_and_async(gm, om, n, dim, ctas_per_sm):
     rng = np.random.default_rng(7)

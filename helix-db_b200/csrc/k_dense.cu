@@ -4,8 +4,15 @@
 // queries against the whole shard is a (B x d) x (d x N) GEMM with arithmetic intensity ~B flop/byte, far beyond the
 // HBM ridge.  It runs on the 5th-generation tensor cores:
 //   * operands in bf16 (a bf16 copy of the corpus is kept when hx_index_config.storage == 1), fp32 accumulation in TMEM;
-//   * tiles 128 queries x 256 rows x 64 (K), 4-stage TMA ring (cp.async.bulk.tensor, 128-byte swizzle) feeding
-//     tcgen05.mma.cta_group::1.kind::f16 issued by one elected thread; accumulators double-buffered in TMEM (2 x 256 cols);
+//   * CTA PAIRS (thread-block clusters of 2 = the two SMs of a TPC): one tcgen05.mma.cta_group::2 covers 256 queries x 256
+//     corpus rows x 16 (K) — each CTA holds its own 128 queries (A, and the 128 TMEM lanes of their accumulators) and
+//     stages only HALF of the corpus tile (B); the tensor cores of both SMs read both halves.  With cta_group::1 every SM
+//     staged the whole 48 KB k-block itself: 94 B/clk of TMA writes + 94 B/clk of operand reads against 128 B/clk of shared
+//     memory bandwidth — ncu: tensor pipe 65 % of active (profiles/r02_ncu_dense_v2_details.txt).  Pairing cuts both to
+//     64 + 64 KB per 2 SMs;
+//   * 6-stage TMA ring of (16 KB A | 16 KB half-B) per CTA (cp.async.bulk.tensor.cta_group::2, 128-byte swizzle, completion
+//     counted on the LEADER CTA's mbarrier), MMAs issued by one elected thread of the leader, ring slots and accumulator
+//     stages released in both CTAs by multicast tcgen05.commit; accumulators double-buffered in TMEM (2 x 256 columns);
 //   * fused epilogue: 4 warps read the accumulator with tcgen05.ld, turn it into the metric's score with the stored
 //     row norms, and keep the HX_DENSE_T best rows of the tile per query (register insertion), emitting
 //     score_bits<<32|slot keys — the B x N score matrix is never written.
@@ -27,53 +34,71 @@
 #include "k_scan.cuh"
 #include "k_util.cuh"
 
-#define HXD_BM 128          // queries per tile (UMMA M)
-#define HXD_BN 256          // corpus rows per tile (UMMA N)
+#define HXD_BM 128          // queries per CTA tile (UMMA M = 256 over the CTA pair)
+#define HXD_BN 256          // corpus rows per tile (UMMA N); each CTA of the pair stages HXD_BN / 2 of them
 #define HXD_BK 64           // bf16 elements per k-block = 128 bytes = one swizzle atom
-#define HXD_STAGES 4
+#define HXD_STAGES 6
 #define HXD_T 16            // best rows kept per (query, work unit = one m-tile x a contiguous run of n-tiles)
 #define HXD_THREADS 384     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-11: epilogue (2 per TMEM lane quarter)
 #define HXD_EPI_THREADS 256
 #define HXD_STAGE_CAP 12    // per-thread staging entries (shared memory) between the column test and the top-T insertion
 #define HXD_A_BYTES (HXD_BM * HXD_BK * 2)
-#define HXD_B_BYTES (HXD_BN * HXD_BK * 2)
+#define HXD_B_BYTES ((HXD_BN / 2) * HXD_BK * 2)   // this CTA's half of the corpus tile
 #define HXD_STAGE_BYTES (HXD_A_BYTES + HXD_B_BYTES)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hxd_tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ uint32_t hxd_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t hxd_mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void hxd_cluster_sync() {   // all threads of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// tile -> this CTA's shared memory; the bytes are counted on the mbarrier at cluster address `bar_cluster` (the leader's)
+__device__ __forceinline__ void hxd_tma_load_2d(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           hx_smem_u32(smem_dst)),
-      "l"(map), "r"(hx_smem_u32(bar)), "r"(c0), "r"(c1)
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void hxd_prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
-__device__ __forceinline__ void hxd_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hx_smem_u32(bar)) : "memory");
+__device__ __forceinline__ void hxd_mbar_arrive_cluster(uint32_t bar_cluster) {   // arrive on a barrier of any CTA of the cluster
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
-__device__ __forceinline__ void hxd_tmem_alloc(uint32_t* smem_out, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hx_smem_u32(smem_out)), "r"(cols)
+__device__ __forceinline__ void hxd_tmem_alloc(uint32_t* smem_out, uint32_t cols) {   // the same warp id in both CTAs of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hx_smem_u32(smem_out)), "r"(cols)
                : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void hxd_tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void hxd_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void hxd_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem] * B[smem]^T, M=128, N=256, K=16 (bf16), fp32 accumulate
+// D[tmem of both CTAs] (+)= A[smem of both CTAs] * B[smem halves of both CTAs]^T, M=256, N=256, K=16 (bf16), fp32 accumulate.
+// Issued by one thread of the leader CTA; the descriptors are shared-memory offsets valid in both CTAs.
 __device__ __forceinline__ void hxd_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// all previously issued MMAs of this thread arrive on `bar` when they have completed
-__device__ __forceinline__ void hxd_umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hx_smem_u32(bar))
+// all previously issued MMAs of this thread arrive on the barrier at the same offset in BOTH CTAs when they have completed
+__device__ __forceinline__ void hxd_umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   hx_smem_u32(bar)),
+               "h"((uint16_t)3)
                : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = TMEM lane base+i)
@@ -130,100 +155,99 @@ struct HxDenseArgs {
   uint32_t n_rows;            // corpus rows (unpadded)
   uint32_t n_queries;         // B (unpadded)
   uint32_t k_blocks;          // ldb / 64
-  uint32_t m_tiles, n_tiles;
-  uint32_t n_split;           // work unit u: m-tile u % m_tiles, n-tiles [r*n_tiles/n_split, (r+1)*n_tiles/n_split), r = u / m_tiles
+  uint32_t m_pairs, n_tiles;  // m_pairs = pairs of 128-query tiles (one pair = one CTA pair)
+  uint32_t n_split;           // work unit u of a CTA pair: query pair u % m_pairs, n-tiles [r*n_tiles/n_split, (r+1)*n_tiles/n_split), r = u / m_pairs
   const float* row_aux;       // cosine: 1/|x_i|   ; euclidean: |x_i|^2            (from the bf16-rounded rows)
   const float* q_aux;         // cosine: 1/|q_b|   ; euclidean: |q_b|^2
   uint64_t* keys;             // [B][n_split][2][HXD_T]  (two column halves per query row)
   int32_t metric;
-  uint32_t debug;             // experiments: bit0 = epilogue drains without reading TMEM, bit1 = no TMA after the first ring fill
 };
 
-__global__ void __launch_bounds__(HXD_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HXD_THREADS, 1)
 k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, HxDenseArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // HXD_STAGES x (A 16 KB | B 32 KB); the 128-byte swizzle needs 1024-byte aligned tiles: align inside the window
+  // HXD_STAGES x (A 16 KB | half-B 16 KB); the 128-byte swizzle needs 1024-byte aligned tiles: align inside the window
+  // (the window starts at the same offset in both CTAs of the pair, so every object below has the same offset in both)
   unsigned char* smem = smem_raw + ((1024u - (hx_smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* tiles = smem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + HXD_STAGES * HXD_STAGE_BYTES);
-  uint64_t* empty = full + HXD_STAGES;
-  uint64_t* tfull = empty + HXD_STAGES;     // [2] accumulator stage ready for the epilogue
-  uint64_t* tempty = tfull + 2;             // [2] accumulator stage drained
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + HXD_STAGES * HXD_STAGE_BYTES);   // leader's copy is the live one
+  uint64_t* empty = full + HXD_STAGES;      // per CTA: ring slot free (multicast commit of the MMAs that read it)
+  uint64_t* tfull = empty + HXD_STAGES;     // [2] per CTA: accumulator stage ready for the epilogue (multicast commit)
+  uint64_t* tempty = tfull + 2;             // [2] leader's copy: accumulator stage drained by the epilogues of BOTH CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* aux = reinterpret_cast<float*>(tmem_slot + 4);   // [2][HXD_BN] row aux of the tile being drained
   float* stg_t = aux + 2 * HXD_BN;                          // [HXD_STAGE_CAP][256] staged t values   (entry-major: conflict-free)
   uint32_t* stg_s = reinterpret_cast<uint32_t*>(stg_t + HXD_STAGE_CAP * HXD_EPI_THREADS);   // [HXD_STAGE_CAP][256] staged slots
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t rank = hxd_cta_rank();                     // 0 = leader (issues the MMAs of the pair)
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   if (threadIdx.x == 0) {
     hxd_prefetch_tmap(&map_q);
     hxd_prefetch_tmap(&map_x);
     for (int s = 0; s < HXD_STAGES; ++s) {
-      hx_mbar_init(full + s, 1);
+      hx_mbar_init(full + s, 1);                             // the leader's producer: one arrive.expect_tx for both CTAs' bytes
       hx_mbar_init(empty + s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       hx_mbar_init(tfull + s, 1);
-      hx_mbar_init(tempty + s, HXD_EPI_THREADS);
+      hx_mbar_init(tempty + s, 2 * HXD_EPI_THREADS);
     }
     hx_fence_mbar_init();
   }
   if (warp == 2) hxd_tmem_alloc(tmem_slot, 512);
   hxd_fence_before();
-  __syncthreads();
+  hxd_cluster_sync();       // barriers of both CTAs initialised before any remote arrive / complete_tx; TMEM allocated
   hxd_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t total_units = a.m_tiles * a.n_split;
+  const uint32_t total_units = a.m_pairs * a.n_split;
 
   if (warp == 0) {
-    // ===== TMA producer (one lane) =====
+    // ===== TMA producer (one lane, in BOTH CTAs: own 128 queries + own half of the corpus tile) =====
     if (lane == 0) {
       uint32_t stage = 0, ph = 0;
-      for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
-        // units with the same n-range and different m-tiles run on neighbouring CTAs in step: the corpus tile is read
-        // from HBM once and served to the others by L2
-        const uint32_t mt = u % a.m_tiles, r = u / a.m_tiles;
+      for (uint32_t u = pair; u < total_units; u += n_pairs) {
+        // units with the same n-range and different query pairs run on neighbouring CTA pairs in step: the corpus tile is
+        // read from HBM once and served to the others by L2
+        const uint32_t mt = 2u * (u % a.m_pairs) + rank, r = u / a.m_pairs;
         const uint32_t nt0 = (uint32_t)((uint64_t)r * a.n_tiles / a.n_split), nt1 = (uint32_t)((uint64_t)(r + 1) * a.n_tiles / a.n_split);
         for (uint32_t nt = nt0; nt < nt1; ++nt)
           for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-            hx_mbar_wait(empty + stage, ph ^ 1u);
+            hx_mbar_wait(empty + stage, ph ^ 1u);           // own slot free (the multicast commit arrives in both CTAs)
             unsigned char* sa = tiles + (size_t)stage * HXD_STAGE_BYTES;
-            if ((a.debug & 2u) && (ph || nt != nt0 || u != blockIdx.x)) {
-              hxd_mbar_arrive(full + stage);              // experiment: operands stay whatever the first fill left
-            } else {
-              hx_mbar_expect_tx(full + stage, HXD_STAGE_BYTES);
-              hxd_tma_load_2d(sa, &map_q, full + stage, (int)(kb * HXD_BK), (int)(mt * HXD_BM));
-              hxd_tma_load_2d(sa + HXD_A_BYTES, &map_x, full + stage, (int)(kb * HXD_BK), (int)(nt * HXD_BN));
-            }
+            const uint32_t lead_full = hxd_mapa(hx_smem_u32(full + stage), 0u);
+            if (rank == 0) hx_mbar_expect_tx(full + stage, 2u * HXD_STAGE_BYTES);
+            hxd_tma_load_2d(sa, &map_q, lead_full, (int)(kb * HXD_BK), (int)(mt * HXD_BM));
+            hxd_tma_load_2d(sa + HXD_A_BYTES, &map_x, lead_full, (int)(kb * HXD_BK), (int)(nt * HXD_BN + rank * (HXD_BN / 2)));
             if (++stage == HXD_STAGES) { stage = 0; ph ^= 1u; }
           }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one lane) =====
-    if (lane == 0) {
+    // ===== MMA issuer (one lane of the LEADER CTA, for the pair) =====
+    if (lane == 0 && rank == 0) {
       // InstrDescriptor: c_format F32 (1<<4) | a_format BF16 (1<<7) | b_format BF16 (1<<10) | K-major A,B | N>>3 at 17 | M>>4 at 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HXD_BN >> 3) << 17) | ((uint32_t)(HXD_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HXD_BN >> 3) << 17) | ((uint32_t)((2 * HXD_BM) >> 4) << 24);
       uint32_t stage = 0, ph = 0, acc = 0, acc_ph = 0;
-      for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
-       const uint32_t r = u / a.m_tiles;
+      for (uint32_t u = pair; u < total_units; u += n_pairs) {
+       const uint32_t r = u / a.m_pairs;
        const uint32_t nt0 = (uint32_t)((uint64_t)r * a.n_tiles / a.n_split), nt1 = (uint32_t)((uint64_t)(r + 1) * a.n_tiles / a.n_split);
        for (uint32_t nt = nt0; nt < nt1; ++nt) {
-        hx_mbar_wait(tempty + acc, acc_ph ^ 1u);   // epilogue has drained this accumulator stage
+        hx_mbar_wait(tempty + acc, acc_ph ^ 1u);   // both epilogues have drained this accumulator stage
         hxd_fence_after();
         const uint32_t tmem_d = tmem_base + acc * HXD_BN;
         for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
-          hx_mbar_wait(full + stage, ph);
+          hx_mbar_wait(full + stage, ph);          // both CTAs' tiles have landed
           hxd_fence_after();
           const uint32_t sa = hx_smem_u32(tiles + (size_t)stage * HXD_STAGE_BYTES);
           const uint64_t adesc = hxd_make_desc(sa), bdesc = hxd_make_desc(sa + HXD_A_BYTES);
 #pragma unroll
           for (uint32_t k = 0; k < HXD_BK / 16; ++k)   // 16 bf16 = 32 bytes along K inside the swizzle atom: start address += 2
             hxd_umma(tmem_d, adesc + 2ull * k, bdesc + 2ull * k, idesc, (kb | k) ? 1u : 0u);
-          hxd_umma_commit(empty + stage);             // smem slot reusable once these MMAs have read it
+          hxd_umma_commit_pair(empty + stage);        // slot reusable in both CTAs once these MMAs have read it
           if (++stage == HXD_STAGES) { stage = 0; ph ^= 1u; }
         }
-        hxd_umma_commit(tfull + acc);                 // accumulator complete
+        hxd_umma_commit_pair(tfull + acc);            // accumulator complete (each CTA drains its own 128 lanes)
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
        }
       }
@@ -240,8 +264,9 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const uint32_t row_in_tile = q4 * 32 + lane;
     const uint32_t et = threadIdx.x - 128;            // 0..255
     uint32_t acc = 0, acc_ph = 0;
-    for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const uint32_t mt = u % a.m_tiles, r = u / a.m_tiles;
+    const uint32_t lead_tempty0 = hxd_mapa(hx_smem_u32(tempty), 0u);
+    for (uint32_t u = pair; u < total_units; u += n_pairs) {
+      const uint32_t mt = 2u * (u % a.m_pairs) + rank, r = u / a.m_pairs;
       const uint32_t nt0 = (uint32_t)((uint64_t)r * a.n_tiles / a.n_split), nt1 = (uint32_t)((uint64_t)(r + 1) * a.n_tiles / a.n_split);
       const uint32_t qrow = mt * HXD_BM + row_in_tile;
       const float qa = qrow < a.n_queries ? a.q_aux[qrow] : 0.f;
@@ -316,7 +341,7 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
           if (cnt > HXD_STAGE_CAP - 8 || last) drain();
         };
-        if (!(a.debug & 1u)) {
+        {
           uint32_t ra[32], rb[32];
           hxd_tmem_ld32_nowait(taddr, ra);
           hxd_tmem_wait_ld();
@@ -332,7 +357,7 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
         }
         hxd_fence_before();
-        hxd_mbar_arrive(tempty + acc);   // 256 arrivals free the accumulator stage
+        hxd_mbar_arrive_cluster(lead_tempty0 + acc * 8u);   // 2 x 256 arrivals (both CTAs) free the accumulator stage
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
       if (qrow < a.n_queries) {
@@ -351,7 +376,7 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
   }
   hxd_fence_before();
-  __syncthreads();
+  hxd_cluster_sync();       // the leader's MMAs wrote BOTH CTAs' TMEM: nobody frees before both are done
   if (warp == 2) hxd_tmem_dealloc(tmem_base, 512);
 }
 
@@ -474,19 +499,20 @@ hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t
   const uint32_t ldb = (dim + HXD_BK - 1) / HXD_BK * HXD_BK;
   if ((rc = ensure_bf16(ix, ldb))) return rc;
   const size_t n = ix->n;
-  const uint32_t m_tiles = (uint32_t)((B + HXD_BM - 1) / HXD_BM), n_tiles = (uint32_t)((n + HXD_BN - 1) / HXD_BN);
-  const size_t B_pad = (size_t)m_tiles * HXD_BM, n_pad = (size_t)n_tiles * HXD_BN;
+  const uint32_t m_pairs = (uint32_t)((B + 2 * HXD_BM - 1) / (2 * HXD_BM)), n_tiles = (uint32_t)((n + HXD_BN - 1) / HXD_BN);
+  const size_t B_pad = (size_t)m_pairs * 2 * HXD_BM, n_pad = (size_t)n_tiles * HXD_BN;
+  const size_t n_cta_pairs = (size_t)std::max(1, ix->sm_count / 2);   // one persistent CTA pair per TPC
   const uint32_t kprime = (uint32_t)std::min<size_t>(std::max<uint32_t>(4 * k, 64), std::min<size_t>(800, n));
-  // runs per m-tile: enough units to fill the SMs, and enough that one run's best-T comfortably covers its share of the
-  // k' nominees even when the true neighbours cluster in id space (8x head-room)
+  // runs per query pair: enough units to fill the CTA pairs, and enough that one run's best-T comfortably covers its share
+  // of the k' nominees even when the true neighbours cluster in id space (8x head-room)
   uint32_t n_split = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_tiles,
-      std::max<size_t>(std::max<size_t>(4, (size_t)ix->sm_count / m_tiles), (8 * (size_t)kprime + HXD_T - 1) / HXD_T)));
-  // the grid is one persistent CTA per SM: make the number of work units a multiple of it so that the last wave is full
-  // (1024 queries = 8 m-tiles: 32 runs = 256 units = 1.73 waves of 148 CTAs, the tensor pipe idles 13 % of the launch;
-  // 37 runs = 296 units = exactly 2 waves)
-  if ((size_t)m_tiles * n_split > (size_t)ix->sm_count)
+      std::max<size_t>(std::max<size_t>(4, n_cta_pairs / m_pairs), (8 * (size_t)kprime + HXD_T - 1) / HXD_T)));
+  // the grid is one persistent CTA pair per TPC: make the number of work units a multiple of it so that the last wave is
+  // full (1024 queries = 4 query pairs: 32 runs = 128 units = 1.73 waves of 74 pairs, the tensor pipe idles 13 % of the
+  // launch; 37 runs = 148 units = exactly 2 waves)
+  if ((size_t)m_pairs * n_split > n_cta_pairs)
     for (uint32_t cand = n_split; cand <= std::min<uint32_t>(n_tiles, 2 * n_split); ++cand)
-      if (((size_t)m_tiles * cand) % (size_t)ix->sm_count == 0) { n_split = cand; break; }
+      if (((size_t)m_pairs * cand) % n_cta_pairs == 0) { n_split = cand; break; }
   const size_t nkeys = B * (size_t)n_split * 2 * HXD_T;
   int mi = 0;
   bool grew = false;
@@ -526,7 +552,7 @@ hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t
     dc.ldb = ldb;
   }
   if (dc.map_x_base != ix->d_vec_bf16 || dc.map_x_rows != n_pad) {
-    if ((rc = make_map(reinterpret_cast<CUtensorMap*>(dc.map_x), ix->d_vec_bf16, n_pad, ldb, HXD_BN))) return rc;
+    if ((rc = make_map(reinterpret_cast<CUtensorMap*>(dc.map_x), ix->d_vec_bf16, n_pad, ldb, HXD_BN / 2))) return rc;   // a CTA stages half a corpus tile
     dc.map_x_base = ix->d_vec_bf16;
     dc.map_x_rows = n_pad;
   }
@@ -550,21 +576,20 @@ hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t
   a.n_rows = (uint32_t)n;
   a.n_queries = (uint32_t)B;
   a.k_blocks = ldb / HXD_BK;
-  a.m_tiles = m_tiles;
+  a.m_pairs = m_pairs;
   a.n_tiles = n_tiles;
   a.n_split = n_split;
   a.row_aux = ix->d_sqnorm;
   a.q_aux = d_qaux;
   a.keys = d_keys;
   a.metric = ix->cfg.metric;
-  a.debug = 0u;
   const size_t smem = (size_t)HXD_STAGES * HXD_STAGE_BYTES + 16 * 8 + 16 + 2 * HXD_BN * 4 + (size_t)HXD_STAGE_CAP * HXD_EPI_THREADS * 8 + 1024;
   static std::atomic<int> attr_set[64];
   if (!attr_set[ix->device & 63].load()) {
     HX_CUDA(cudaFuncSetAttribute(k_dense_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[ix->device & 63].store(1);
   }
-  const uint32_t grid = (uint32_t)std::min<size_t>((size_t)m_tiles * n_split, (size_t)ix->sm_count);
+  const uint32_t grid = 2u * (uint32_t)std::min<size_t>((size_t)m_pairs * n_split, n_cta_pairs);   // clusters of 2 (__cluster_dims__)
   if (e0) HX_CUDA(cudaEventRecord(e0, stream));
   k_dense_scores<<<grid, HXD_THREADS, smem, stream>>>(*reinterpret_cast<CUtensorMap*>(dc.map_q),
                                                       *reinterpret_cast<CUtensorMap*>(dc.map_x), a);

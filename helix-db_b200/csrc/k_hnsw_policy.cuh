@@ -370,8 +370,28 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     if (METRIC == HXM_COSINE)
       for (uint32_t f = lane; f < cnt; f += 32) fhdr[f] = __ldg(ix.hdr + list[f]);
     __syncwarp();
-    uint32_t s = 0;
-    for (uint32_t j = 0; j < cnt; ++j) {
+    uint32_t s = 0, j = 0;
+    // rows two at a time: both reductions are dependent chains (24 FMAs + 5 shuffles at d = 768), interleaving two of them
+    // halves the time the warp spends waiting on its own arithmetic (the kernel is bound by per-warp issue latency, not by
+    // DRAM: ncu, profiles/r01_ncu_policy_r01_details.txt — 8.9 cycles per issued instruction at 41 % DRAM throughput)
+    for (; R >= 2u && j + 1 < cnt; j += 2) {
+      const uint32_t s1 = (s + 1 == R) ? 0u : s + 1;
+      hx_mbar_wait(bars + s, (ph >> s) & 1u);
+      hx_mbar_wait(bars + s1, (ph >> s1) & 1u);
+      ph ^= (1u << s) | (1u << s1);
+      float sa, sb;
+      hx_warp_score2<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
+          ring + (size_t)s * ix.ld, ring + (size_t)s1 * ix.ld, qr, sq, qg, q_hdr, METRIC == HXM_COSINE ? fhdr[j] : 0.f,
+          METRIC == HXM_COSINE ? fhdr[j + 1] : 0.f, ix.dim, lane, sa, sb);
+      if (lane == 0) { fdist[j] = sa; fdist[j + 1] = sb; }
+      __syncwarp();   // every lane is done with both slots
+      if (lane == 0) {
+        if (j + R < cnt) issue(s, list[j + R]);
+        if (j + 1 + R < cnt) issue(s1, list[j + 1 + R]);
+      }
+      s = (s1 + 1 == R) ? 0u : s1 + 1;
+    }
+    for (; j < cnt; ++j) {
       hx_mbar_wait(bars + s, (ph >> s) & 1u);
       ph ^= 1u << s;
       const float sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
@@ -671,13 +691,28 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
       if (ns == 0) continue;
       // -- score and admit (search.rs:909-953)
       score_list(frontier, ns);
-      for (uint32_t f = 0; f < ns; ++f) {
-        float s = fdist[f];
-        if (!hx_score_ok(s)) qflags |= HXF_INVALID_SCORE;
-        const uint32_t sbits = __float_as_uint(s);
+      // One pass decides which scores can be admitted at all: once the effective beam (entries + fill slots) is full it stays
+      // full and w.max only decreases, so a score that fails `dist < w.max || len + fill < ef` now fails it at its turn too;
+      // the survivors are admitted one by one in neighbour order with the test repeated on the live state (search.rs:909-953)
+      for (uint32_t base = 0; base < ns; base += 32) {
+       const uint32_t fl = base + lane;
+       float sl = fl < ns ? fdist[fl] : 0.f;
+       uint32_t sbl = 0;
+       bool pass = false;
+       if (fl < ns) {
+         if (!hx_score_ok(sl)) qflags |= HXF_INVALID_SCORE;
+         sbl = __float_as_uint(sl);
+         pass = sbl < (uint32_t)(beam_mem[beam.len - 1] >> 32) || beam.len + fill < a.ef;
+       }
+       const uint32_t slot_l = fl < ns ? frontier[fl] : 0u;
+       uint32_t pmask = __ballot_sync(FULL, pass);
+       while (pmask) {
+        const int src = __ffs(pmask) - 1;
+        pmask &= pmask - 1;
+        const uint32_t sbits = __shfl_sync(FULL, sbl, src);
+        const uint32_t xslot = __shfl_sync(FULL, slot_l, src);
         const uint32_t wmax = (uint32_t)(beam_mem[beam.len - 1] >> 32);
         if (!(sbits < wmax || beam.len + fill < a.ef)) continue;
-        const uint32_t xslot = frontier[f];
         const uint64_t nkey = ((uint64_t)sbits << 32) | ((uint64_t)xslot << 1);
         const bool was_full = beam.len == a.ef;
         const uint32_t old_wmax = wmax;
@@ -707,6 +742,7 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
           }
           __syncwarp();
         }
+       }
       }
       __syncwarp();
       if (failed) break;

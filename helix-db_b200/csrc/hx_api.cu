@@ -192,8 +192,10 @@ void hx_index::free_graph() {
   stride0 = 0; stride_u = 0; n_upper_rows = 0;
   cap_upper = 0;
   staged.clear();
-  graph_dirty = false;
   populated = false;
+  // graph_dirty is NOT touched here: hx_finalize_graph calls this while it holds fin_mu with the flag still set — clearing
+  // it would let a concurrent search skip the lock and launch on a half-uploaded graph.  Callers that really reset the
+  // graph clear the flag themselves.
 }
 
 hx_status HxScratch::ring_next(cudaEvent_t* e0, cudaEvent_t* e1) {
@@ -420,6 +422,7 @@ extern "C" void hx_index_destroy(hx_index* ix) {
 
 static hx_status alloc_vectors(hx_index* ix, size_t n) {
   ix->free_graph();
+  ix->graph_dirty.store(false, std::memory_order_release);   // no staged rows, no device graph: nothing to finalise
   ix->free_vectors();
   if (n >= (1ull << 31)) {
     hx_set_error("a shard holds at most 2^31-1 rows (got %zu)", n);

@@ -688,6 +688,7 @@ hx_status hx_build_impl(hx_index* ix, const uint16_t* levels_in, uint64_t seed, 
     return HX_ERR_INVALID_VECTOR_CONFIG;
   }
   ix->free_graph();
+  ix->graph_dirty.store(false, std::memory_order_release);   // the build writes the device graph itself
   // ---- levels -----------------------------------------------------------------------------------------------------
   std::vector<uint8_t> level(n);
   const float ml = 1.0f / std::log((float)std::max(m, 2u));   // default_ml_for_m (mod.rs:705-709)

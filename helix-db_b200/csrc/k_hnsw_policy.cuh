@@ -370,28 +370,8 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     if (METRIC == HXM_COSINE)
       for (uint32_t f = lane; f < cnt; f += 32) fhdr[f] = __ldg(ix.hdr + list[f]);
     __syncwarp();
-    uint32_t s = 0, j = 0;
-    // rows two at a time: both reductions are dependent chains (24 FMAs + 5 shuffles at d = 768), interleaving two of them
-    // halves the time the warp spends waiting on its own arithmetic (the kernel is bound by per-warp issue latency, not by
-    // DRAM: ncu, profiles/r01_ncu_policy_r01_details.txt — 8.9 cycles per issued instruction at 41 % DRAM throughput)
-    for (; R >= 2u && j + 1 < cnt; j += 2) {
-      const uint32_t s1 = (s + 1 == R) ? 0u : s + 1;
-      hx_mbar_wait(bars + s, (ph >> s) & 1u);
-      hx_mbar_wait(bars + s1, (ph >> s1) & 1u);
-      ph ^= (1u << s) | (1u << s1);
-      float sa, sb;
-      hx_warp_score2<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(
-          ring + (size_t)s * ix.ld, ring + (size_t)s1 * ix.ld, qr, sq, qg, q_hdr, METRIC == HXM_COSINE ? fhdr[j] : 0.f,
-          METRIC == HXM_COSINE ? fhdr[j + 1] : 0.f, ix.dim, lane, sa, sb);
-      if (lane == 0) { fdist[j] = sa; fdist[j + 1] = sb; }
-      __syncwarp();   // every lane is done with both slots
-      if (lane == 0) {
-        if (j + R < cnt) issue(s, list[j + R]);
-        if (j + 1 + R < cnt) issue(s1, list[j + 1 + R]);
-      }
-      s = (s1 + 1 == R) ? 0u : s1 + 1;
-    }
-    for (; j < cnt; ++j) {
+    uint32_t s = 0;
+    for (uint32_t j = 0; j < cnt; ++j) {
       hx_mbar_wait(bars + s, (ph >> s) & 1u);
       ph ^= 1u << s;
       const float sc = hx_warp_score<(METRIC == HXM_MANHATTAN ? HXM_EUCLIDEAN : METRIC), (Q_SMEM ? 0 : QCH)>(

@@ -301,82 +301,6 @@ __device__ __forceinline__ float hx_warp_row(const float* __restrict__ row_s, co
   return result;
 }
 
-// Two rows at once: the same two chains per lane, interleaved, so that one row's FMA / shuffle latency hides behind the
-// other's (each row's arithmetic and order are exactly hx_warp_row's).
-template <bool IS_DOT, int QCH>
-__device__ __forceinline__ void hx_warp_row2(const float* __restrict__ row_a, const float* __restrict__ row_b, const float* qr,
-                                             const float* __restrict__ sq, const float* __restrict__ qg, uint32_t dim,
-                                             uint32_t lane, float& out_a, float& out_b) {
-  const unsigned FULL = 0xffffffffu;
-  const uint32_t chunks = dim >> 5;
-  float acc_a = 0.f, acc_b = 0.f;
-  if (QCH > 0) {
-#pragma unroll
-    for (int c = 0; c < (QCH > 0 ? QCH : 1); ++c) {
-      if ((uint32_t)c < chunks) {
-        const float xa = row_a[c * 32 + lane], xb = row_b[c * 32 + lane];
-        const float q = qr[c];
-        if (IS_DOT) {
-          acc_a = __fmaf_rn(q, xa, acc_a);
-          acc_b = __fmaf_rn(q, xb, acc_b);
-        } else {
-          const float da = __fsub_rn(q, xa), db = __fsub_rn(q, xb);
-          acc_a = __fmaf_rn(da, da, acc_a);
-          acc_b = __fmaf_rn(db, db, acc_b);
-        }
-      }
-    }
-  } else {
-#pragma unroll 8
-    for (uint32_t c = 0; c < chunks; ++c) {
-      const float xa = row_a[c * 32 + lane], xb = row_b[c * 32 + lane];
-      const float q = sq[c * 32 + lane];
-      if (IS_DOT) {
-        acc_a = __fmaf_rn(q, xa, acc_a);
-        acc_b = __fmaf_rn(q, xb, acc_b);
-      } else {
-        const float da = __fsub_rn(q, xa), db = __fsub_rn(q, xb);
-        acc_a = __fmaf_rn(da, da, acc_a);
-        acc_b = __fmaf_rn(db, db, acc_b);
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < 5; ++o) {   // hsum order of hx_warp_row: 8, 16, 4, 2, 1
-    const int m = o == 0 ? 8 : o == 1 ? 16 : o == 2 ? 4 : o == 3 ? 2 : 1;
-    const float ta = __shfl_xor_sync(FULL, acc_a, m), tb = __shfl_xor_sync(FULL, acc_b, m);
-    acc_a = __fadd_rn(acc_a, ta);
-    acc_b = __fadd_rn(acc_b, tb);
-  }
-  float ra = acc_a, rb = acc_b;
-  for (uint32_t i = chunks << 5; i < dim; ++i) {   // scalar tail: separately rounded mul + add
-    const float a = __ldg(qg + i), ba = row_a[i], bb = row_b[i];
-    if (IS_DOT) {
-      ra = __fadd_rn(ra, __fmul_rn(a, ba));
-      rb = __fadd_rn(rb, __fmul_rn(a, bb));
-    } else {
-      const float da = __fsub_rn(a, ba), db = __fsub_rn(a, bb);
-      ra = __fadd_rn(ra, __fmul_rn(da, da));
-      rb = __fadd_rn(rb, __fmul_rn(db, db));
-    }
-  }
-  out_a = ra;
-  out_b = rb;
-}
-template <int METRIC, int QCH>
-__device__ __forceinline__ void hx_warp_score2(const float* __restrict__ row_a, const float* __restrict__ row_b, const float* qr,
-                                               const float* __restrict__ sq, const float* __restrict__ qg, float q_hdr,
-                                               float hdr_a, float hdr_b, uint32_t dim, uint32_t lane, float& out_a, float& out_b) {
-  if (METRIC == HXM_EUCLIDEAN) {
-    hx_warp_row2<false, QCH>(row_a, row_b, qr, sq, qg, dim, lane, out_a, out_b);
-    return;
-  }
-  float pa, pb;
-  hx_warp_row2<true, QCH>(row_a, row_b, qr, sq, qg, dim, lane, pa, pb);
-  out_a = hx_cosine_finish(pa, q_hdr, hdr_a, qg, row_a, dim);
-  out_b = hx_cosine_finish(pb, q_hdr, hdr_b, qg, row_b, dim);
-}
-
 template <int METRIC, int QCH>
 __device__ __forceinline__ float hx_warp_score(const float* __restrict__ row_s, const float* qr, const float* __restrict__ sq,
                                                const float* __restrict__ qg, float q_hdr, float row_hdr, uint32_t dim,

@@ -663,7 +663,8 @@ def test_device_build(gm, om, n, dim, m):
 # ---- dense tensor-core path (tcgen05 bf16 contraction nominates, exact fp32 re-rank decides) -------------------------------------
 @pytest.mark.parametrize("gm,om,n,dim,B", [(hx.Metric.Cosine, hxo.COSINE, 5000, 768, 300),
                                           (hx.Metric.Euclidean, hxo.EUCLIDEAN, 3000, 100, 130),
-                                          (hx.Metric.Cosine, hxo.COSINE, 700, 64, 5)])
+                                          (hx.Metric.Cosine, hxo.COSINE, 700, 64, 5),
+                                          (hx.Metric.Cosine, hxo.COSINE, 60000, 128, 260)])
 def test_dense_tensor_core_path(gm, om, n, dim, B):
     rng = np.random.default_rng(n + dim)
     lat = rng.standard_normal((n, 16)).astype(np.float32)

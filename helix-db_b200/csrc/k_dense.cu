@@ -10,12 +10,15 @@
 //     staged the whole 48 KB k-block itself: 94 B/clk of TMA writes + 94 B/clk of operand reads against 128 B/clk of shared
 //     memory bandwidth — ncu: tensor pipe 65 % of active (profiles/r02_ncu_dense_v2_details.txt).  Pairing cuts both to
 //     64 + 64 KB per 2 SMs;
-//   * 6-stage TMA ring of (16 KB A | 16 KB half-B) per CTA (cp.async.bulk.tensor.cta_group::2, 128-byte swizzle, completion
+//   * 5-stage TMA ring of (16 KB A | 16 KB half-B) per CTA (cp.async.bulk.tensor.cta_group::2, 128-byte swizzle, completion
 //     counted on the LEADER CTA's mbarrier), MMAs issued by one elected thread of the leader, ring slots and accumulator
 //     stages released in both CTAs by multicast tcgen05.commit; accumulators double-buffered in TMEM (2 x 256 columns);
-//   * fused epilogue: 4 warps read the accumulator with tcgen05.ld, turn it into the metric's score with the stored
-//     row norms, and keep the HX_DENSE_T best rows of the tile per query (register insertion), emitting
-//     score_bits<<32|slot keys — the B x N score matrix is never written.
+//   * fused epilogue: 16 warps per CTA (one per TMEM lane quarter x column quarter) read the accumulator with tcgen05.ld,
+//     turn it into the metric's score order with the stored row norms, and keep the HX_DENSE_T best rows per (query, run of
+//     tiles, column quarter) by register insertion, emitting score_bits<<32|slot keys — the B x N score matrix is never
+//     written.  The epilogue is what bounds the kernel at K = 768: a warp's column work is one dependent instruction
+//     stream, and with 8 warps it took longer per tile than the tile's MMAs (1.60 ms, 0.78 of the burst peak); with 16
+//     warps 1.45 ms, 0.86 (profiles/r02_dense_limiter_experiments.json).
 // The approximate (bf16) keys only NOMINATE candidates: k_select keeps the k' best keys per query and the exact fp32
 // scan kernel (bit-exact reference arithmetic) re-ranks them, so returned scores are exact and ordering follows the
 // reference's (score, id) rule; recall vs the exhaustive exact scan is measured, not assumed.
@@ -37,10 +40,11 @@
 #define HXD_BM 128          // queries per CTA tile (UMMA M = 256 over the CTA pair)
 #define HXD_BN 256          // corpus rows per tile (UMMA N); each CTA of the pair stages HXD_BN / 2 of them
 #define HXD_BK 64           // bf16 elements per k-block = 128 bytes = one swizzle atom
-#define HXD_STAGES 6
-#define HXD_T 16            // best rows kept per (query, work unit = one m-tile x a contiguous run of n-tiles)
-#define HXD_THREADS 384     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-11: epilogue (2 per TMEM lane quarter)
-#define HXD_EPI_THREADS 256
+#define HXD_STAGES 5
+#define HXD_PARTS 4         // column quarters of a tile: one epilogue warp per (TMEM lane quarter, column quarter)
+#define HXD_T 8             // best rows kept per (query, run of n-tiles, column quarter): 32 per (query, run)
+#define HXD_THREADS 640     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-19: epilogue
+#define HXD_EPI_THREADS 512
 #define HXD_STAGE_CAP 12    // per-thread staging entries (shared memory) between the column test and the top-T insertion
 #define HXD_A_BYTES (HXD_BM * HXD_BK * 2)
 #define HXD_B_BYTES ((HXD_BN / 2) * HXD_BK * 2)   // this CTA's half of the corpus tile
@@ -159,7 +163,7 @@ struct HxDenseArgs {
   uint32_t n_split;           // work unit u of a CTA pair: query pair u % m_pairs, n-tiles [r*n_tiles/n_split, (r+1)*n_tiles/n_split), r = u / m_pairs
   const float* row_aux;       // cosine: 1/|x_i|   ; euclidean: |x_i|^2            (from the bf16-rounded rows)
   const float* q_aux;         // cosine: 1/|q_b|   ; euclidean: |q_b|^2
-  uint64_t* keys;             // [B][n_split][2][HXD_T]  (two column halves per query row)
+  uint64_t* keys;             // [B][n_split][HXD_PARTS][HXD_T]
   int32_t metric;
 };
 
@@ -253,16 +257,20 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: 8 warps; thread = one query row x one half (128 columns) of the tile =====
+    // ===== epilogue: 16 warps; thread = one query row x one quarter (64 columns) of the tile =====
+    // A warp's column work is ONE dependent instruction stream (a lane is a query; whenever any of the 32 admits a column the
+    // warp walks the staging path).  With 8 warps x 128 columns that stream took longer per tile than the tile's 12 k-blocks
+    // of MMAs (profiles/r02_dense_limiter_experiments.json: the epilogue's column work cost 0.36 ms of a 1.6 ms kernel and
+    // 4 extra instructions per 8 columns cost another 0.28 ms): 16 warps x 64 columns halve it.
     // ncu on the first version (profiles/): the tensor pipe sat at 10 % because 4 warps x 256 columns x ~30 instructions
     // per column could not drain an accumulator as fast as the MMAs filled it.  Now the test is done in the dot-product
     // domain (one FMUL/FFMA + one compare per column: the score is monotone in it), padded rows carry a sentinel that
     // can never pass, row terms are read as float4, and two warps share each TMEM lane quarter.
-    const uint32_t ew = warp - 4;                     // 0..7
+    const uint32_t ew = warp - 4;                     // 0..15
     const uint32_t q4 = ew & 3u;                      // TMEM lane quarter this warp may access (warp id % 4)
-    const uint32_t half = ew >> 2;                    // column half
+    const uint32_t half = ew >> 2;                    // column quarter 0..3
     const uint32_t row_in_tile = q4 * 32 + lane;
-    const uint32_t et = threadIdx.x - 128;            // 0..255
+    const uint32_t et = threadIdx.x - 128;            // 0..511
     uint32_t acc = 0, acc_ph = 0;
     const uint32_t lead_tempty0 = hxd_mapa(hx_smem_u32(tempty), 0u);
     for (uint32_t u = pair; u < total_units; u += n_pairs) {
@@ -281,17 +289,19 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const uint32_t n0 = nt * HXD_BN;
         float* ax = aux + acc * HXD_BN;
         {
-          const uint32_t c = et;                        // 256 threads stage the 256 row terms of the tile
-          float v = (n0 + c < a.n_rows) ? a.row_aux[n0 + c] : 0.f;
-          if (n0 + c >= a.n_rows) v = a.metric == HXM_COSINE ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
-          ax[c] = v;                                    // padded rows: t = NaN / -inf never beats the threshold
+          const uint32_t c = et;                        // the first 256 threads stage the 256 row terms of the tile
+          if (c < HXD_BN) {
+            float v = (n0 + c < a.n_rows) ? a.row_aux[n0 + c] : 0.f;
+            if (n0 + c >= a.n_rows) v = a.metric == HXM_COSINE ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
+            ax[c] = v;                                  // padded rows: t = NaN / -inf never beats the threshold
+          }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         hx_mbar_wait(tfull + acc, acc_ph);
         hxd_fence_after();
-        const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + acc * HXD_BN + half * (HXD_BN / 2);
-        const float4* ax4 = reinterpret_cast<const float4*>(ax + half * (HXD_BN / 2));
-        const uint32_t slot0 = n0 + half * (HXD_BN / 2);
+        const uint32_t taddr = tmem_base + ((q4 * 32u) << 16) + acc * HXD_BN + half * (HXD_BN / HXD_PARTS);
+        const float4* ax4 = reinterpret_cast<const float4*>(ax + half * (HXD_BN / HXD_PARTS));
+        const uint32_t slot0 = n0 + half * (HXD_BN / HXD_PARTS);
         // The loop body is deliberately small and NOT unrolled: the first version inlined the insertion network at every
         // column (10k SASS instructions, instruction-cache bound: tensor pipe 9 %).  Columns that beat the running
         // threshold are only STAGED (two predicated shared-memory stores); the single insertion-network instance below
@@ -341,27 +351,22 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
           if (cnt > HXD_STAGE_CAP - 8 || last) drain();
         };
-        {
+        {   // 64 columns: two 32-column loads, the second in flight while the first is tested (16-column halves of `rb`
+            // would save registers, but 640 threads leave 96 each and this fits)
           uint32_t ra[32], rb[32];
           hxd_tmem_ld32_nowait(taddr, ra);
           hxd_tmem_wait_ld();
-#pragma unroll 1
-          for (uint32_t c0 = 0; c0 < HXD_BN / 2; c0 += 64) {
-            hxd_tmem_ld32_nowait(taddr + c0 + 32, rb);            // in flight while chunk `ra` is tested
-            test8(ra, c0, false); test8(ra + 8, c0 + 8, false); test8(ra + 16, c0 + 16, false); test8(ra + 24, c0 + 24, false);
-            hxd_tmem_wait_ld();
-            if (c0 + 64 < HXD_BN / 2) hxd_tmem_ld32_nowait(taddr + c0 + 64, ra);
-            test8(rb, c0 + 32, false); test8(rb + 8, c0 + 40, false); test8(rb + 16, c0 + 48, false);
-            test8(rb + 24, c0 + 56, c0 + 64 >= HXD_BN / 2);
-            hxd_tmem_wait_ld();
-          }
+          hxd_tmem_ld32_nowait(taddr + 32, rb);
+          test8(ra, 0, false); test8(ra + 8, 8, false); test8(ra + 16, 16, false); test8(ra + 24, 24, false);
+          hxd_tmem_wait_ld();
+          test8(rb, 32, false); test8(rb + 8, 40, false); test8(rb + 16, 48, false); test8(rb + 24, 56, true);
         }
         hxd_fence_before();
         hxd_mbar_arrive_cluster(lead_tempty0 + acc * 8u);   // 2 x 256 arrivals (both CTAs) free the accumulator stage
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
       if (qrow < a.n_queries) {
-        uint64_t* out = a.keys + (((size_t)qrow * a.n_split + r) * 2 + half) * HXD_T;
+        uint64_t* out = a.keys + (((size_t)qrow * a.n_split + r) * HXD_PARTS + half) * HXD_T;
 #pragma unroll
         for (int i = 0; i < HXD_T; ++i) {
           uint64_t key = HX_KEY_MAX;
@@ -506,14 +511,14 @@ hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t
   // runs per query pair: enough units to fill the CTA pairs, and enough that one run's best-T comfortably covers its share
   // of the k' nominees even when the true neighbours cluster in id space (8x head-room)
   uint32_t n_split = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_tiles,
-      std::max<size_t>(std::max<size_t>(4, n_cta_pairs / m_pairs), (8 * (size_t)kprime + HXD_T - 1) / HXD_T)));
+      std::max<size_t>(std::max<size_t>(4, n_cta_pairs / m_pairs), (8 * (size_t)kprime + HXD_PARTS * HXD_T - 1) / (HXD_PARTS * HXD_T))));
   // the grid is one persistent CTA pair per TPC: make the number of work units a multiple of it so that the last wave is
   // full (1024 queries = 4 query pairs: 32 runs = 128 units = 1.73 waves of 74 pairs, the tensor pipe idles 13 % of the
   // launch; 37 runs = 148 units = exactly 2 waves)
   if ((size_t)m_pairs * n_split > n_cta_pairs)
     for (uint32_t cand = n_split; cand <= std::min<uint32_t>(n_tiles, 2 * n_split); ++cand)
       if (((size_t)m_pairs * cand) % n_cta_pairs == 0) { n_split = cand; break; }
-  const size_t nkeys = B * (size_t)n_split * 2 * HXD_T;
+  const size_t nkeys = B * (size_t)n_split * HXD_PARTS * HXD_T;
   int mi = 0;
   bool grew = false;
   auto take = [&](size_t bytes, void** out) -> hx_status {
@@ -604,7 +609,7 @@ hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t
   s1.B = (uint32_t)B;
   s1.k = kprime;
   s1.shared_set = 2;   // keys carry global slots in their low word (no candidate indirection)
-  s1.n_shared = (uint64_t)n_split * 2 * HXD_T;
+  s1.n_shared = (uint64_t)n_split * HXD_PARTS * HXD_T;
   s1.out_ids = d_sel_ids;
   s1.out_scores = d_sel_sc;
   s1.out_counts = d_sel_cnt;

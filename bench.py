@@ -977,7 +977,7 @@ def run_ours(args):
 
         # iso-recall tuning of the per-shard beam: a shard is 1/world of the corpus, so the unsharded ef is over-provisioned
         tuning, chosen = [], None
-        for ef_s in (10, 12, 16, 20, 24, 32, 48, 64, EF):
+        for ef_s in (10, 12, 16, 20, 24, 32, 40, 48, 56, 64, 72, 80, 90, EF):
             p_loc = hx.SearchParams.strict(k, ef_s)
             run_sharded(0, p_loc)
             torch.cuda.synchronize(dev)

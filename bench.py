@@ -722,9 +722,26 @@ def measure_d1536(hx, torch, args, local_rank, dev, stream):
     kernel_ms = kms / max(kl, 1)
     achieved = st.algorithmic_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms else 0.0
     flags, fstatus = ix.device_flags(stream)
+    # e2e: hx_search through the C ABI with pinned host buffers (the same call as the C2 line's e2e)
+    import ctypes as C
+    L = hx.load_library()
+    cp = params._c()
+    h_q = [torch.from_numpy(qsets[args.warmup + s]).pin_memory() for s in range(steps)]
+    h_ids = torch.zeros((Q, k), dtype=torch.int64).pin_memory()
+    h_sc = torch.zeros((Q, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.zeros((Q,), dtype=torch.int32).pin_memory()
+
+    def step_host(s):
+        rc = L.hx_search(ix.h, C.cast(h_q[s].data_ptr(), C.POINTER(C.c_float)), Q, C.byref(cp),
+                         C.cast(h_ids.data_ptr(), C.POINTER(C.c_uint64)), C.cast(h_sc.data_ptr(), C.POINTER(C.c_float)),
+                         C.cast(h_cnt.data_ptr(), C.POINTER(C.c_uint32)), None)
+        if rc != 0:
+            raise RuntimeError(f"hx_search failed: {L.hx_last_error().decode()}")
+
+    step_host(0)
     t0 = time.perf_counter()
     for s in range(steps):
-        ix.search_batch(qsets[args.warmup + s], params)
+        step_host(s)
     e2e = steps * Q / (time.perf_counter() - t0)
     out = {"metric": "queries/sec @ recall@10, 1M x 1536 Euclidean HNSW top-10 (the reference's traversal fixture shape)",
            "value": round(steps * Q / (ms_total / 1e3), 1), "unit": "queries/s", "steps": steps,
@@ -732,7 +749,7 @@ def measure_d1536(hx, torch, args, local_rank, dev, stream):
            "config": {"workload": f"{n}x{dim} f32 euclidean HNSW top-10 (m=16, m0=32, ef_construction=200, ef={EF}), {Q} "
                                   f"independent single-query traversals per step", "setup": setup},
            "e2e": {"value": round(e2e, 1), "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4,
-                   "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 8 + 4, "api": "hx_search (C ABI, host buffers, blocking)"},
+                   "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 8 + 4, "api": "hx_search (C ABI, pinned host buffers, blocking)"},
            "roofline": {"bound": "hbm", "kernel": "k_hnsw_search_ring", "achieved": round(achieved, 1), "peak": hbm_peak,
                         "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": int(st.algorithmic_bytes), "kernel_ms_per_launch": round(kernel_ms, 4),

@@ -462,7 +462,9 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
 
     // ---- layer 0 with the policy (search.rs:500-992)
     HxBeam beam{beam_mem, 1u};
-    HxBeam topk{topk_mem, 1u};
+    // The reference's top-k tracker (a max-heap of the k best admitted candidates, search.rs:933-938) needs no storage of its
+    // own here: every admitted candidate enters the beam, the beam keeps the ef >= k best of them sorted, so the tracker IS
+    // the beam's first min(k, len) entries and its maximum is beam[min(k, len) - 1].
     const uint32_t topk_target = a.k > 1u ? a.k : 1u;   // == a.k (k >= 1)
     HxTie tq = hx_tie_make(tie);
     uint32_t dropped = 0;
@@ -477,7 +479,6 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
     if (lane == 0) {
       const uint64_t k0 = hx_make_key(cur_dist, cur << 1);
       beam_mem[0] = k0;
-      topk_mem[0] = k0;
       sess_mem[25] = 0;
       hx_vt_test_and_set(vt, cur);
     }
@@ -545,8 +546,8 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
       __syncwarp();
       if (nf == 0) continue;
       // -- decision (search.rs:603-649)
-      const bool topk_ready = topk.len >= topk_target;
-      const float delta = topk.len ? hx_key_score(topk_mem[topk.len - 1]) : __uint_as_float(cur_bits);
+      const bool topk_ready = beam.len >= topk_target;
+      const float delta = hx_key_score(beam_mem[min(beam.len, topk_target) - 1u]);   // beam.len >= 1: the entry point
       const HxDecision dec = hxp_decide(METRIC, pa.cfg, topk_ready, a.ef, beam.len, nf, __uint_as_float(cur_bits), delta, bstate,
                                         bremaining, 0ull, w_examined, w_filtered, w_expansions, memo_key, memo_thr);
       bstate = dec.next_state;
@@ -699,13 +700,6 @@ __global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy
         uint64_t ev;
         hx_beam_insert2(beam, a.ef, nkey, &ev, lane);
         if (!was_full && beam.len + fill > a.ef) fill--;   // a real candidate replaced a virtual fill slot (:940-944)
-        {   // top-k tracker: BinaryHeap push, pop the maximum when above k (:933-938)
-          const bool tfull = topk.len == topk_target;
-          if (!tfull || nkey < topk_mem[topk.len - 1]) {
-            uint64_t tev;
-            hx_beam_insert2(topk, topk_target, nkey, &tev, lane);
-          }
-        }
         if (lane == 0) {
           hx_prefetch_l2(ix.nbr0 + (size_t)xslot * ix.stride0);
           hx_prefetch_l2(ix.deg0 + xslot);

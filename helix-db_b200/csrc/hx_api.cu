@@ -1327,6 +1327,7 @@ static hx_status launch_hnsw(hx_index* ix, HxScratch* s, const float* d_queries,
   if (!use_cta_ring) {
     const size_t fixed0 = (ring_qch == 0 ? rowbytes : 0) + (size_t)ef * 8 + HX_TIE_CAP * 8 + (size_t)fr_cap * 12;
     uint32_t want_wpc = knob(t.ring_warps, 16);
+    if (ring_qch == 48) want_wpc = std::min(want_wpc, (uint32_t)HX_RING_QCH48_THREADS / 32u);   // launch bound of that build
     const uint32_t want_R = knob(t.ring_rows, 0);
     // few queries: fewer warps per CTA so that the batch spreads over all SMs (and each warp gets a deeper ring)
     const uint32_t spread = (uint32_t)std::max<size_t>(1, (B + ix->sm_count - 1) / (size_t)ix->sm_count);

@@ -245,12 +245,12 @@ __device__ __forceinline__ bool hx_vt_contains(const HxVisited& v, uint32_t key)
 
 // shared memory per warp: query | R row slots | beam[ef] | topk[k] | tie | R mbarriers | frontier | fdist | fhdr(aliases fsim) |
 //                         fstate (bytes) | session (28 words)
-#define HX_POLICY_MAX_THREADS 512
+#define HX_POLICY_MAX_THREADS 512   // warp-per-query build; the CTA-per-query build launches 8 warps (256 threads: up to 255 registers, no spills)
 // CTA = false: one warp per query (throughput).  CTA = true (B < #SMs): one CTA per query — warp 0 runs the very same
 // per-query code, and whenever it has rows to score it wakes the other warps, which issue and reduce their share of the
 // rows (row r -> warp r mod W), exactly like the latency build of the exhaustive kernel.
 template <int METRIC, int QCH, bool CTA>
-__global__ void __launch_bounds__(HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy(HxDev ix, HxHnswArgs a, HxRingArgs rg,
+__global__ void __launch_bounds__(CTA ? 256 : HX_POLICY_MAX_THREADS, 1) k_hnsw_search_policy(HxDev ix, HxHnswArgs a, HxRingArgs rg,
                                                                                 HxPolicyArgs pa, uint32_t wstride, uint32_t R) {
   extern __shared__ __align__(128) unsigned char smem[];
   // CTA mode: warp 0 (the query) and the helper warps meet from different places in the code, so the rendezvous is a pair

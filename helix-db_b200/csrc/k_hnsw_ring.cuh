@@ -313,8 +313,9 @@ __device__ __forceinline__ float hx_warp_score(const float* __restrict__ row_s, 
 // ---- warp-per-query, ring-staged rows (throughput build) -------------------------------------------------------------------
 // shared memory per warp: [query (QCH == 0 only)] | R row slots | beam | tie stack | R mbarriers | frontier | scores | headers
 #define HX_RING_MAX_THREADS 512
+#define HX_RING_QCH48_THREADS 320   // 1024 < d <= 1536: 48 query registers per lane; 6 KB rows leave room for at most 9 warps anyway
 template <int METRIC, int QCH>
-__global__ void __launch_bounds__(HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxDev ix, HxHnswArgs a, HxRingArgs rg,
+__global__ void __launch_bounds__(QCH >= 48 ? HX_RING_QCH48_THREADS : HX_RING_MAX_THREADS, 1) k_hnsw_search_ring(HxDev ix, HxHnswArgs a, HxRingArgs rg,
                                                                             uint32_t wstride, uint32_t R) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;

@@ -692,6 +692,21 @@ def test_dense_tensor_core_path(gm, om, n, dim, B):
         keys = [(float(ds[q, j]), int(di[q, j])) for j in range(k)]
         assert keys == sorted(keys)                        # (score, id) order
     assert hit / float(B * k) >= 0.99
+    # ... and against the ORACLE's exact scan (not only this repository's own scan kernel): same ids except where a true
+    # neighbour was not nominated by its bf16 score, and every returned score is the oracle's score for that id, bit for bit
+    ora = hxo.Index(om, dim)
+    ora.put_vectors(ids, rows)
+    nchk, ohit = min(B, 24), 0
+    for q in range(nchk):
+        oi, os_ = ora.search_exact(queries[q], k)
+        exact = {int(i): os_[j].tobytes() for j, i in enumerate(oi)}
+        ohit += len(set(di[q].tolist()) & set(exact))
+        for j, i in enumerate(di[q]):
+            if int(i) in exact:
+                assert ds[q, j].tobytes() == exact[int(i)], (q, j)
+        if len(set(di[q].tolist()) & set(exact)) == k:
+            assert di[q].tolist() == oi.tolist(), q                      # complete answers come in the oracle's order
+    assert ohit / float(nchk * k) >= 0.99
     storage0 = hx.VectorIndex(gm, hx.VectorIndexConfig("d0", "embedding", dim))
     storage0.load_vectors(ids[:10], rows[:10])
     with pytest.raises(hx.HelixDbError):

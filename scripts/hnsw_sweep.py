@@ -1,6 +1,6 @@
 """On-GPU A/B of the HNSW traversal builds and their knobs on the C2 corpus (1M x 768, embedding recipe).
 
-One index build, then for every variant (environment knobs read by launch_hnsw at call time): warm-up, timed launches
+One index build, then for every variant (launch knobs of hx_tuning, given as their HX_* environment names and re-read with VectorIndex.tune()): warm-up, timed launches
 through hx_search_device, kernel time from the library's own CUDA events, algorithmic GB/s from the SearchStats counters,
 and a bit-for-bit comparison of ids/scores with the first variant.  Not the bench — writes gpurun_out/hnsw_sweep.json.
 
@@ -20,10 +20,9 @@ sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
 import helix_db_b200 as hx  # noqa: E402
 
-KNOBS = ("HX_HNSW_IMPL", "HX_RING_WARPS", "HX_RING_R", "HX_VT_CAP_LOG2", "HX_L2_HINT", "HX_TMA_WARPS", "HX_VT_POOL",
-         "HX_LAT_IMPL", "HX_LAT_WARPS", "HX_PHASE_PROF", "HX_LAT_SPEC", "HX_LAT_ADMIT", "HX_POL_QCH", "HX_POL_WARPS", "HX_POL_MINR", "HX_POL_EARLY_SIM", "HX_PREFETCH_BELOW", "HX_PIPELINE")
+KNOBS = ("HX_RING_WARPS", "HX_RING_R", "HX_VT_CAP_LOG2", "HX_L2_HINT", "HX_VT_POOL", "HX_LAT_WARPS", "HX_PHASE_PROF", "HX_LAT_SPEC",
+         "HX_LAT_ADMIT", "HX_POL_WARPS", "HX_POL_MINR", "HX_POL_EARLY_SIM", "HX_POL_CTA", "HX_PREFETCH_BELOW", "HX_PIPELINE")
 DEFAULT_VARIANTS = [
-    ("tma12", {"HX_HNSW_IMPL": "tma"}),
     ("ring16", {}),
     ("ring16_nohint", {"HX_L2_HINT": "0"}),
     ("ring16_vt12", {"HX_VT_CAP_LOG2": "12"}),
@@ -71,6 +70,7 @@ def main():
             for key in KNOBS:
                 os.environ.pop(key, None)
             os.environ.update(env)
+            ix.tune()   # the handle reads the environment at creation: re-read it (hx_index_set_tuning(NULL))
             p = hx.SearchParams.new(k)
             ids0, sc0, cnt0 = ix.search_ex(qs[0], p)
             got = (ids0.tobytes(), sc0.tobytes())
@@ -101,6 +101,7 @@ def main():
             for key in KNOBS:
                 os.environ.pop(key, None)
             os.environ.update(env)
+            ix.tune()   # the handle reads the environment at creation: re-read it (hx_index_set_tuning(NULL))
             p = hx.SearchParams.strict(k, bench.EF)
             p.collect_stats = True
             st = hx.SearchStats()

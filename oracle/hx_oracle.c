@@ -1824,13 +1824,19 @@ void hxo_session_seeded(hxo_session* s, uint64_t seed) { /* randomness.rs:122-13
 uint64_t hxo_session_seed_for(uint64_t query_simhash, uint64_t entry_point, uint64_t ef) { /* randomness.rs:109-114 */
   return query_simhash ^ rotl64(entry_point, 17) ^ rotl64(ef, 7);
 }
+/* PCG32's output permutation XSH-RR (xorshift high bits, random rotate) of a 64-bit LCG state; the LCG multiplier is PCG's
+ * 6364136223846793005.  Pinned by the PCG reference implementation's demo stream (tests/test_oracle_kat.py). */
+uint32_t hxo_pcg32_xsh_rr(uint64_t state) {
+  const uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+  const uint32_t rot = (uint32_t)(state >> 59);
+  return (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31)); /* rotate_right */
+}
+uint64_t hxo_pcg32_step(uint64_t state, uint64_t increment) { return state * 6364136223846793005ull + increment; }
 static void session_start(hxo_session* s) { /* SeedableRng::seed_from_u64: PCG32 fills the 32-byte key */
   uint64_t state = s->seed;
   for (int i = 0; i < 8; ++i) {
-    state = state * 6364136223846793005ull + 11634580027462260723ull;
-    const uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
-    const uint32_t rot = (uint32_t)(state >> 59);
-    s->key[i] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31)); /* rotate_right; little-endian words */
+    state = hxo_pcg32_step(state, 11634580027462260723ull); /* advance FIRST (away from a low-weight seed), then output */
+    s->key[i] = hxo_pcg32_xsh_rr(state);                    /* little-endian words of the 32-byte seed */
   }
   s->block = 0;
   s->pos = 16;

@@ -10,8 +10,9 @@
  * tests/test_oracle_kat.py).  Strict-exhaustive search and the layer-0 policy functions are
  * pinned by values the reference's tests assert.  NOT pinned (the section at the end of this
  * header says exactly what): the stream of the query session RNG (rand 0.10.2 / chacha20 0.10.1
- * are absent from the tree; restated from their published algorithm) and SimHash hyperplane
- * values (never generated here: fingerprints and planes are inputs).
+ * are absent from the tree; restated from their published algorithm; the ChaCha12 generator and
+ * PCG32 pieces are checked against those crates' published value-stability vectors) and SimHash
+ * hyperplane values (never generated here: fingerprints and planes are inputs).
  */
 #ifndef HX_ORACLE_H
 #define HX_ORACLE_H
@@ -181,11 +182,17 @@ int hxo_index_import_graph(hxo_index* idx, const uint16_t* levels, const uint32_
  *
  * Pinning: the policy functions are pinned by the literals of the reference's own policy tests
  * (policy.rs:641-1010: thresholds, probabilities, bypass window transitions; tests/test_oracle_kat.py).
- * PARITY UNPINNED: (1) the values drawn from the query session RNG — rand 0.10.2 `StdRng` = ChaCha12 seeded through
- * rand_core's `seed_from_u64` (PCG32 expansion), `random::<f32>()` = (next_u32 >> 8) * 2^-24, `random_range(0..n)` =
- * widening-multiply with one bias-correction draw — are restated from the published algorithms of those crates
- * (absent from /root/reference; no committed value pins them; the reference's own tests only compare two instances
- * of the generator); (2) SimHash hyperplanes (StdRng(42) Gaussian draws) are never generated here: node and query
+ * PARITY UNPINNED BY THE TREE: (1) the values drawn from the query session RNG — rand 0.10.2 `StdRng` = ChaCha12 seeded
+ * through rand_core's `seed_from_u64` (PCG32 expansion), `random::<f32>()` = (next_u32 >> 8) * 2^-24,
+ * `random_range(0..n)` = widening-multiply with one bias-correction draw — are restated from the published algorithms
+ * of those crates (absent from /root/reference; no committed value pins them; the reference's own tests only compare
+ * two instances of the generator).  What narrows that gap (tests/test_oracle_kat.py, vectors quoted from the published
+ * crates' own value-stability tests, not from a file in the tree): the ChaCha12 stream — round count, counter / stream
+ * start, word order, `from_rng` re-seeding — reproduces rand's `test_stdrng_construction` (10719222850664546238,
+ * 14064965282130556830) and rand_chacha's `test_chacha_construction` (137206642, 1325750369); PCG32's LCG step and
+ * XSH-RR permutation reproduce the PCG reference demo stream (0xa15c02b7, 0x7b47f409, ...).  Still resting on the
+ * restatement alone: seed_from_u64's increment constant and advance-then-output order, the f32 conversion, and the
+ * range reduction of `random_range`; (2) SimHash hyperplanes (StdRng(42) Gaussian draws) are never generated here: node and query
  * fingerprints are INPUTS (the reference persists them as [0x12] rows), or are projected from caller-supplied planes.
  * The RNG is consulted only for frontiers larger than max(ef/4, 8) (policy.rs:526-556), i.e. rarely at ef=100, m0=32.
  * SimHash "filter reads" follow the resident-store case (memory_store.rs:331-337: no KV read, so the read budget of
@@ -240,6 +247,9 @@ typedef struct { uint64_t seed; int32_t started; uint32_t key[8]; uint64_t block
 void     hxo_session_seeded(hxo_session* s, uint64_t seed);
 uint64_t hxo_session_seed_for(uint64_t query_simhash, uint64_t entry_point, uint64_t ef);  /* randomness.rs:109-114 */
 uint32_t hxo_session_next_u32(hxo_session* s);
+/* the two halves of rand_core's seed_from_u64 expansion: PCG's LCG step and its XSH-RR output permutation */
+uint32_t hxo_pcg32_xsh_rr(uint64_t state);
+uint64_t hxo_pcg32_step(uint64_t state, uint64_t increment);
 /* the ChaCha block function itself (words 12-13 = counter, 14-15 = stream); pinned by RFC 7539 2.3.2 at 20 rounds */
 void     hxo_chacha_block(const uint32_t key[8], uint64_t counter, uint64_t stream, int rounds, uint32_t out[16]);
 int      hxo_session_should_sample(hxo_session* s, float ratio);           /* :141-153 */

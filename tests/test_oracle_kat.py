@@ -460,6 +460,72 @@ def test_session_rng_structure(hxo):
     assert out[:4].tolist() == [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3] and out[15] == 0x4e3c50a2
 
 
+def test_chacha12_stream_matches_the_rand_crates_value_stability_vectors(hxo):
+    """The session RNG is `rand::rngs::StdRng` (randomness.rs:96-165) = ChaCha12 over a 32-byte seed, output consumed as
+    little-endian words in block order.  The rand / rand_chacha crates are NOT in the tree, so these known
+    answers are quoted from the published crates' own value-stability tests, not from a file under /root/reference:
+      * rand `rngs/std.rs::test_stdrng_construction`: seed [1,0,0,0, 23,0,0,0, 200,1,0,0, 210,30,0,0, 0 x 16],
+        `next_u64()` = 10719222850664546238, and a second StdRng seeded with the NEXT 32 bytes of that stream
+        (`from_rng` = `fill_bytes(seed)`) gives `next_u64()` = 14064965282130556830;
+      * rand_chacha `chacha.rs::test_chacha_construction` (ChaCha20Rng): seed = u64 LE words [0, 1, 2, 3],
+        `next_u32()` = 137206642, then `from_rng` -> `next_u32()` = 1325750369.
+    They pin what the RFC 7539 vector alone does not: the round count StdRng uses (8 and 20 rounds both fail the first
+    vector), the zero 64-bit block counter / zero stream id start, and the word order in which a block is consumed."""
+    L = hxo.lib()
+    u32p = _C.POINTER(_C.c_uint32)
+
+    def block(key_words, rounds):
+        key = np.ascontiguousarray(key_words, dtype=np.uint32)
+        out = np.zeros(16, dtype=np.uint32)
+        L.hxo_chacha_block(key.ctypes.data_as(u32p), 0, 0, rounds, out.ctypes.data_as(u32p))
+        return out
+
+    seed = np.frombuffer(bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16), dtype="<u4")
+    b0 = block(seed, 12)
+    assert (int(b0[0]) | (int(b0[1]) << 32)) == 10719222850664546238
+    for wrong in (8, 20):
+        w = block(seed, wrong)
+        assert (int(w[0]) | (int(w[1]) << 32)) != 10719222850664546238
+    b1 = block(b0[2:10], 12)                                   # from_rng: the next 8 words of the stream are the new key
+    assert (int(b1[0]) | (int(b1[1]) << 32)) == 14064965282130556830
+    seed20 = np.array([0, 0, 1, 0, 2, 0, 3, 0], dtype=np.uint32)
+    c0 = block(seed20, 20)
+    assert int(c0[0]) == 137206642
+    assert int(block(c0[1:9], 20)[0]) == 1325750369
+    # ... and the oracle's session walks exactly that stream: a session whose PCG32-expanded key is K returns the words of
+    # block(K, counter 0), block(K, counter 1), ... in order (pos / block bookkeeping of hxo_session_next_u32)
+    s = hxo.Session()
+    L.hxo_session_seeded(_C.byref(s), 42)
+    first = [L.hxo_session_next_u32(_C.byref(s)) for _ in range(40)]
+    key = np.array(list(s.key), dtype=np.uint32)
+    want = []
+    for counter in range(3):
+        out = np.zeros(16, dtype=np.uint32)
+        L.hxo_chacha_block(key.ctypes.data_as(u32p), counter, 0, 12, out.ctypes.data_as(u32p))
+        want += out.tolist()
+    assert first == want[:40]
+    # seed_from_u64 expands the u64 through PCG32 (LCG step, XSH-RR output).  The PCG reference implementation's demo
+    # stream (pcg32_srandom(42, 54): 0xa15c02b7 0x7b47f409 0xba1d3330 0x83d2f293 0xbfa4784b 0xcbed606e) pins the multiplier
+    # and the permutation the oracle uses; the session key is those two functions applied advance-first with rand_core's
+    # increment (restated, unpinned)
+    L.hxo_pcg32_xsh_rr.restype, L.hxo_pcg32_xsh_rr.argtypes = _C.c_uint32, [_C.c_uint64]
+    L.hxo_pcg32_step.restype, L.hxo_pcg32_step.argtypes = _C.c_uint64, [_C.c_uint64, _C.c_uint64]
+    inc = (54 << 1) | 1
+    st = L.hxo_pcg32_step((L.hxo_pcg32_step(0, inc) + 42) & (2**64 - 1), inc)
+    demo = []
+    for _ in range(6):
+        demo.append(L.hxo_pcg32_xsh_rr(st))
+        st = L.hxo_pcg32_step(st, inc)
+    assert demo == [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
+    st, want_key = 42, []
+    for _ in range(8):
+        st = L.hxo_pcg32_step(st, 11634580027462260723)
+        want_key.append(L.hxo_pcg32_xsh_rr(st))
+    assert list(s.key) == want_key
+    # f32 draw = (u32 >> 8) * 2^-24 (rand's StandardUniform for f32: 24 mantissa bits, [0, 1)): the extremes
+    assert np.float32((0xFFFFFFFF >> 8)) * np.float32(1.0 / 16777216.0) == np.float32(1.0) - np.float32(2.0 ** -24)
+
+
 def test_policy_path_with_neutral_parameters_reproduces_the_pinned_strict_search(hxo):
     """Consistency of the non-exhaustive restatement with the value-pinned strict one: with a zero threshold and sampling
     ratio 1.0 no neighbour is filtered, deferred or drawn for, so layer0_policy must walk exactly like layer0_strict

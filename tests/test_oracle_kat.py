@@ -648,3 +648,61 @@ def test_filtered_graph_recall_contract(hxo):
         assert st["distance_computations"] == st["vector_payload_requests"]
         matched += len(set(got.tolist()) & set(want.tolist()))
     assert matched / 80.0 >= 0.95
+
+
+def test_layer0_search_modes_contracts_of_the_reference(hxo):
+    """V/index.rs:2414-2557 `test_layer0_search_modes_cover_sampling_filtering_and_adaptive_bypass` and :2559-2601
+    `non_angular_metric_disables_filter_phase_without_disabling_sampling_policy`, replayed on the oracle's restatement of
+    the non-exhaustive layer 0.  The reference draws insertion layers from `rand::rng()`, so its own assertions are
+    relations, not values; the same relations must hold here for any layer sequence (three seeds are tried).  The index
+    is the test's: Cosine d=2, m=8, m0=16, ef_construction=32, simhash_threshold 0, sampling_ratio 0.5, 32 points on the
+    unit circle (ids 1..=32)."""
+    planes = np.random.default_rng(42).standard_normal((64, 2)).astype(np.float32)
+    ml = hxo.lib().hxo_default_ml_for_m(8)
+    for seed in (1, 2, 3):
+        ora = hxo.Index(hxo.COSINE, 2, m=8, m0=16, ef_construction=32)
+        lr = np.random.default_rng(seed)
+        pts = []
+        for off in range(32):
+            ang = np.float32(off) * np.float32(2.0 * math.pi) / np.float32(32.0)
+            v = np.array([np.cos(ang, dtype=np.float32), np.sin(ang, dtype=np.float32)], dtype=np.float32)
+            pts.append(v)
+            ora.insert(off + 1, v, int(hxo.lib().hxo_select_layer_from_uniform(ml, float(lr.random(dtype=np.float32)))))
+        ora.put_simhash(np.arange(1, 33, dtype=np.uint64),
+                        np.array([hxo.simhash_from_planes(planes, v) for v in pts], dtype=np.uint64))
+        q10, q01 = np.array([1.0, 0.0], np.float32), np.array([0.0, 1.0], np.float32)
+        base = dict(threshold=0, sampling_ratio=0.5)
+
+        def run(q, **kw):
+            cfg = hxo.policy_defaults(**{**base, **kw})
+            return ora.search_policy(q, 5, 16, cfg, hxo.simhash_from_planes(planes, q))
+
+        # SimHashMode::Off, pre-sampling 1.0: no fingerprint is ever looked at
+        off_ids, _, off_st, off_ps = run(q10, mode=hxo.SIMHASH_OFF, has_pre_override=1, pre_override=1.0)
+        assert len(off_ids) > 0 and off_st["expansion_steps"] > 0
+        assert off_ps["simhash_examined"] == 0 and off_ps["simhash_filtered"] == 0
+        # ... which is the strict-exhaustive specialisation (search.rs:344,595-596): identical to the pinned strict walk
+        s_ids, s_sc = ora.search(q10, 5, ef=16)
+        assert off_ids.tolist() == s_ids.tolist()
+        # Always, sampling ratio 0.0: fingerprints examined, candidates pass the (zero) threshold before sampling
+        al_ids, _, _, al_ps = run(q10, mode=hxo.SIMHASH_ALWAYS, has_pre_override=1, pre_override=1.0, sampling_ratio=0.0)
+        assert len(al_ids) > 0 and al_ps["simhash_examined"] > 0 and al_ps["simhash_passed_before_sampling"] > 0
+        # Always, sampling ratio 1.0, threshold 0: nothing is filtered or dropped => the ids of the Off search
+        fx_ids, _, _, fx_ps = run(q10, mode=hxo.SIMHASH_ALWAYS, has_pre_override=1, pre_override=1.0, sampling_ratio=1.0)
+        assert fx_ids.tolist() == off_ids.tolist() and fx_ps["simhash_filtered"] == 0
+        # Adaptive, pre-sampling 0.25, sampling 0.5, failure 0.5, bypass tuning (1, 1, 1.0, 1): bypass windows open
+        ad_ids, _, ad_st, ad_ps = run(q01, mode=hxo.SIMHASH_ADAPTIVE, has_pre_override=1, pre_override=0.25,
+                                      sampling_ratio=0.5, failure_prob=0.5, bypass_min_frontier=1,
+                                      bypass_window_expansions=1, bypass_min_filter_rate=1.0, read_budget_multiplier=1)
+        assert len(ad_ids) > 0 and ad_st["expansion_steps"] > 0 and ad_ps["simhash_bypass_expansions"] > 0
+    # Euclidean index, threshold 64, sampling 0.5, mode Always, pre-sampling 1.0: the filter phase is off for a
+    # non-angular metric (no fingerprint examined or filtered), the sampling policy stays on (ratio 0.5)
+    euc = hxo.Index(hxo.EUCLIDEAN, 2)
+    for node_id in range(1, 25):
+        euc.insert(node_id, np.array([float(node_id), 1.0], np.float32), 0)
+    cfg = hxo.policy_defaults(mode=hxo.SIMHASH_ALWAYS, threshold=64, sampling_ratio=0.5, has_pre_override=1, pre_override=1.0)
+    ids, _, _, ps = euc.search_policy(np.array([1.0, 1.0], np.float32), 5, 16, cfg, 0)
+    assert len(ids) > 0 and ps["simhash_examined"] == 0 and ps["simhash_filtered"] == 0
+    d = hxo.policy_decide(hxo.EUCLIDEAN, cfg, topk_ready=1, ef=16, search_frontier_len=16, candidate_frontier_len=16,
+                          current=0.2, delta=0.4)
+    assert not d.filter_cached and abs(d.sampling_probability() - 0.5) < 1e-7      # avg_active_sampling_ratio == 0.5

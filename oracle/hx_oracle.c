@@ -1594,6 +1594,214 @@ int hxo_index_insert(hxo_index* ix, uint64_t id, const float* v, uint16_t node_l
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Delete: stage_delete_with_metadata (mutation.rs:1658-1773), delete_from_layer (:1819-1888),
+ * remove_edge_from_neighbor (:1890-1908), relink_neighbor (:1916-2050), find_best_entry_candidate (:340-394).
+ * The reference finds the rows that name the node through its reverse-locator rows (one prefix scan); this in-memory
+ * restatement recomputes that set by scanning the rows.  Items resolve at every layer through the canonical row
+ * (index.rs:1544-1557 falls back to get_item), i.e. has_vec.  Entry candidates are every live node keyed
+ * (u16::MAX - layer, node id): the scan yields the highest layer first, ascending id within it.
+ * ------------------------------------------------------------------------------------------ */
+static uint32_t* row_copy(const hxo_index* ix, uint16_t layer, uint32_t slot, uint32_t extra, uint32_t* n) {
+  uint32_t deg;
+  const uint32_t* r = row_get(ix, layer, slot, &deg);
+  uint32_t* out = (uint32_t*)malloc(((size_t)deg + extra + 1) * sizeof(uint32_t));
+  if (deg) memcpy(out, r, deg * sizeof(uint32_t));
+  *n = deg;
+  return out;
+}
+
+/* distances from `owner` to every member of `members` that has an item, sorted by (score, id) */
+static int ranked_from(const hxo_index* ix, uint32_t owner, const uint32_t* members, uint32_t n, uint32_t skip, cand** out,
+                       uint32_t* out_n) {
+  cand* d = (cand*)malloc(((size_t)n + 1) * sizeof(cand));
+  uint32_t nd = 0;
+  const float* ov = ix->vecs + (size_t)owner * ix->dim;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t c = members[i];
+    if (c == skip || !ix->has_vec[c]) continue;
+    float sc = hxo_distance(ix->metric, ov, ix->hdr[owner], ix->vecs + (size_t)c * ix->dim, ix->hdr[c], ix->dim);
+    const int rc = hxo_score_validate(&sc); /* Candidate::try_new */
+    if (rc) {
+      free(d);
+      return rc;
+    }
+    d[nd].score = sc;
+    d[nd].slot = c;
+    nd++;
+  }
+  qsort_r(d, nd, sizeof(cand), cmp_cand_ctx, (void*)ix);
+  *out = d;
+  *out_n = nd;
+  return HXO_OK;
+}
+
+static int prune_to_limit(const hxo_index* ix, uint32_t owner, uint32_t* members, uint32_t* n, uint32_t max_nbrs) {
+  cand* d;
+  uint32_t nd;
+  int rc = ranked_from(ix, owner, members, *n, UINT32_MAX, &d, &nd);
+  if (rc) return rc;
+  uint8_t* resolvable = (uint8_t*)malloc((size_t)nd + 1);
+  memset(resolvable, 1, (size_t)nd + 1);
+  rc = select_diverse(ix, d, nd, resolvable, max_nbrs, members, n);
+  free(resolvable);
+  free(d);
+  return rc;
+}
+
+static int relink_neighbor(hxo_index* ix, uint16_t layer, uint32_t nb, const uint32_t* cands, uint32_t ncands,
+                           uint32_t max_nbrs) {
+  if (!ix->has_vec[nb]) return HXO_OK; /* :1925-1930 */
+  uint32_t n_old, n_cur;
+  uint32_t* old = row_copy(ix, layer, nb, 0, &n_old);
+  uint32_t* cur = row_copy(ix, layer, nb, max_nbrs + 1, &n_cur);
+  cand* ranked;
+  uint32_t nr;
+  int rc = ranked_from(ix, nb, cands, ncands, nb, &ranked, &nr); /* :1935-1953: HashSet order is erased by the sort */
+  if (!rc) {
+    for (uint32_t i = 0; i < nr && i < max_nbrs; ++i) /* :1954-1958 */
+      if (!row_contains(cur, n_cur, ranked[i].slot)) cur[n_cur++] = ranked[i].slot;
+    free(ranked);
+    if (n_cur > max_nbrs) rc = prune_to_limit(ix, nb, cur, &n_cur, max_nbrs); /* :1960-1983 */
+  }
+  if (!rc) {
+    row_set(ix, layer, nb, cur, n_cur); /* :1985-1993 (row_set sorts its own copy; `cur` keeps the selection order) */
+    for (uint32_t i = 0; i < n_cur && !rc; ++i) { /* :1994-2047: every NEW connection gets its reciprocal edge */
+      const uint32_t nn = cur[i];
+      if (row_contains(old, n_old, nn)) continue;
+      uint32_t n_rev;
+      uint32_t* rev = row_copy(ix, layer, nn, 1, &n_rev);
+      if (!row_contains(rev, n_rev, nb)) {
+        rev[n_rev++] = nb;
+        if (n_rev > max_nbrs && ix->has_vec[nn]) rc = prune_to_limit(ix, nn, rev, &n_rev, max_nbrs);
+        /* no item for the reverse owner: the over-long row is staged as it is (:2006-2017) */
+        if (!rc) row_set(ix, layer, nn, rev, n_rev);
+      }
+      free(rev);
+    }
+  }
+  free(old);
+  free(cur);
+  return rc;
+}
+
+static int delete_from_layer(hxo_index* ix, uint16_t layer, uint32_t node, uint32_t max_nbrs, const uint32_t* extra,
+                             uint32_t n_extra) {
+  uint32_t n_out;
+  uint32_t* outgoing = row_copy(ix, layer, node, 0, &n_out);
+  /* affected = (outgoing \ {node}) U (extra \ {node}), ascending id (BTreeSet) */
+  uint32_t* affected = (uint32_t*)malloc(((size_t)n_out + n_extra + 1) * sizeof(uint32_t));
+  uint8_t* mandatory = (uint8_t*)calloc((size_t)n_out + n_extra + 1, 1);
+  uint32_t na = 0;
+  for (uint32_t i = 0; i < n_out; ++i)
+    if (outgoing[i] != node && !row_contains(affected, na, outgoing[i])) affected[na++] = outgoing[i];
+  const uint32_t n_mand = na;
+  for (uint32_t i = 0; i < n_extra; ++i)
+    if (extra[i] != node && !row_contains(affected, na, extra[i])) affected[na++] = extra[i];
+  int rc = HXO_OK;
+  if (na) {
+    /* sort by id, carrying the "came from the outgoing row" flag */
+    uint32_t* order = (uint32_t*)malloc((size_t)na * sizeof(uint32_t));
+    memcpy(order, affected, (size_t)na * sizeof(uint32_t));
+    qsort_r(order, na, sizeof(uint32_t), cmp_slot_by_id_ctx, ix);
+    for (uint32_t i = 0; i < na; ++i) mandatory[i] = row_contains(affected, n_mand, order[i]) ? 1 : 0;
+    uint32_t* relink = (uint32_t*)malloc((size_t)na * sizeof(uint32_t));
+    uint32_t nrl = 0;
+    for (uint32_t i = 0; i < na; ++i) { /* :1848-1856 */
+      uint32_t deg;
+      const uint32_t* r = row_get(ix, layer, order[i], &deg);
+      const int had_edge = row_contains(r, deg, node);
+      if (had_edge) remove_edge(ix, layer, order[i], node);
+      if (mandatory[i] || had_edge) relink[nrl++] = order[i]; /* ascending id: `order` is */
+    }
+    if (nrl) {
+      /* candidates (:1861-1876): the relink sources and their remaining neighbours, minus the node */
+      size_t cap = nrl;
+      for (uint32_t i = 0; i < nrl; ++i) {
+        uint32_t deg;
+        row_get(ix, layer, relink[i], &deg);
+        cap += deg;
+      }
+      uint32_t* cands = (uint32_t*)malloc((cap + 1) * sizeof(uint32_t));
+      uint32_t nc = 0;
+      for (uint32_t i = 0; i < nrl; ++i)
+        if (relink[i] != node && !row_contains(cands, nc, relink[i])) cands[nc++] = relink[i];
+      for (uint32_t i = 0; i < nrl; ++i) {
+        uint32_t deg;
+        const uint32_t* r = row_get(ix, layer, relink[i], &deg);
+        for (uint32_t j = 0; j < deg; ++j)
+          if (r[j] != node && r[j] != relink[i] && !row_contains(cands, nc, r[j])) cands[nc++] = r[j];
+      }
+      for (uint32_t i = 0; i < nrl && !rc; ++i) rc = relink_neighbor(ix, layer, relink[i], cands, nc, max_nbrs);
+      free(cands);
+    }
+    free(relink);
+    free(order);
+  }
+  free(mandatory);
+  free(affected);
+  free(outgoing);
+  return rc;
+}
+
+int hxo_index_delete(hxo_index* ix, uint64_t id, int* existed) {
+  if (existed) *existed = 0;
+  const uint32_t node = slot_of(ix, id);
+  if (node == UINT32_MAX) return HXO_OK; /* nothing names an id this index never saw */
+  const int item_existed = ix->has_vec[node] ? 1 : 0;
+  const int node_max_layer = ix->level[node] > 0 ? ix->level[node] : 0; /* get_node_max_layer_cached :1788-1811 */
+  int top = node_max_layer;
+  if ((int)ix->max_layer > top) top = ix->max_layer;
+  for (size_t s = 0; s < ix->n; ++s)
+    if (ix->level[s] > top) top = ix->level[s];
+  int rc = HXO_OK;
+  uint32_t* src = (uint32_t*)malloc((ix->n + 1) * sizeof(uint32_t));
+  for (int layer = top; layer >= 0 && !rc; --layer) { /* layers_to_process, highest first (:1681-1702) */
+    uint32_t ns = 0;
+    for (size_t s = 0; s < ix->n; ++s) { /* the reverse locators of (layer, node) */
+      if ((uint32_t)s == node) continue;
+      uint32_t deg;
+      const uint32_t* r = row_get(ix, (uint16_t)layer, (uint32_t)s, &deg);
+      if (deg && row_contains(r, deg, node)) src[ns++] = (uint32_t)s;
+    }
+    if (layer > node_max_layer && ns == 0) continue;
+    rc = delete_from_layer(ix, (uint16_t)layer, node, layer == 0 ? ix->lim0 : ix->lim_upper, src, ns);
+  }
+  free(src);
+  if (rc) return rc;
+  /* the node's own rows, vector and fingerprint (:1711-1737) */
+  if (item_existed) {
+    ix->has_vec[node] = 0;
+    ix->count--;
+  }
+  ix->has_row0[node] = 0;
+  ix->deg0[node] = 0;
+  if (ix->up[node]) memset(ix->up[node]->present, 0, ix->up[node]->nlayers);
+  ix->level[node] = -1;
+  if (ix->has_simhash && node < ix->sim_cap) ix->has_simhash[node] = 0;
+  if (ix->populated && ix->entry_id == id) { /* :1751-1763 */
+    int best_level = -1;
+    uint64_t best_id = 0;
+    for (size_t s = 0; s < ix->n; ++s) {
+      if (!ix->has_vec[s] || ix->level[s] < 0) continue;
+      if (ix->level[s] > best_level || (ix->level[s] == best_level && ix->ids[s] < best_id)) {
+        best_level = ix->level[s];
+        best_id = ix->ids[s];
+      }
+    }
+    if (best_level < 0) {
+      ix->populated = 0; /* entry_point = None, max_layer = 0 */
+      ix->entry_id = 0;
+      ix->max_layer = 0;
+    } else {
+      ix->entry_id = best_id;
+      ix->max_layer = (uint16_t)best_level;
+    }
+  }
+  if (existed) *existed = item_existed;
+  return HXO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Bulk graph import (slot space = rank of ascending id), as downloaded from the device
  * ------------------------------------------------------------------------------------------ */
 int hxo_index_import_graph(hxo_index* ix, const uint16_t* levels, const uint32_t* deg0, const uint32_t* nbr0,

@@ -111,6 +111,10 @@ int hxo_index_put_vectors(hxo_index* idx, const uint64_t* ids, const float* rows
 
 /* insert_with_mutation_cache + insert_hnsw (mutation.rs:642-895) with the layer given by the caller. */
 int hxo_index_insert(hxo_index* idx, uint64_t id, const float* v, uint16_t layer);
+/* VectorIndex::delete (mutation.rs:1606-1773): removes the node from every layer, re-links every row that named it
+ * (delete_from_layer :1819, relink_neighbor :1916), drops its rows / vector / fingerprint and, when it was the entry
+ * point, promotes the best live entry candidate (highest layer, then smallest id).  *existed = the item was present. */
+int hxo_index_delete(hxo_index* idx, uint64_t id, int* existed);
 
 /* Row export (for mirroring into the device index). */
 size_t hxo_index_node_ids(const hxo_index* idx, uint64_t* out, size_t cap);            /* ascending */

@@ -220,6 +220,8 @@ def lib():
     L.hxo_index_set_entry.argtypes = [C.c_void_p, C.c_uint64, C.c_uint16]
     L.hxo_index_insert.restype = C.c_int
     L.hxo_index_insert.argtypes = [C.c_void_p, C.c_uint64, fp, C.c_uint16]
+    L.hxo_index_delete.restype = C.c_int
+    L.hxo_index_delete.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
     L.hxo_index_node_ids.restype = sz
     L.hxo_index_node_ids.argtypes = [C.c_void_p, u64p, sz]
     L.hxo_index_node_level.restype = C.c_int
@@ -437,6 +439,12 @@ class Index:
         va, vp = _f32(v)
         assert va.size == self.dim
         self._ck(self.L.hxo_index_insert(self.h, node_id, vp, layer))
+
+    def delete(self, node_id) -> bool:
+        """VectorIndex::delete (mutation.rs:1606-1773); True when the item existed."""
+        existed = C.c_int(0)
+        self._ck(self.L.hxo_index_delete(self.h, node_id, C.byref(existed)))
+        return bool(existed.value)
 
     def node_ids(self):
         n = len(self)

@@ -706,3 +706,93 @@ def test_layer0_search_modes_contracts_of_the_reference(hxo):
     d = hxo.policy_decide(hxo.EUCLIDEAN, cfg, topk_ready=1, ef=16, search_frontier_len=16, candidate_frontier_len=16,
                           current=0.2, delta=0.4)
     assert not d.filter_cached and abs(d.sampling_probability() - 0.5) < 1e-7      # avg_active_sampling_ratio == 0.5
+
+
+# --- delete: stage_delete_with_metadata / delete_from_layer / relink_neighbor (V/mutation.rs:1658-2050) -------
+def test_delete_relinks_by_the_reference_algorithm_hand_derived(hxo):
+    """A chain 1-2-3-4 on a line (Euclidean, x = id), limits m=2 / m0=4, delete 3.  Worked by hand from the reference:
+    outgoing(3) = [2,4]; the edge to 3 is removed from rows 2 and 4 (-> [1] and []); relink sources [2,4];
+    candidates = {2,4} U nbrs(2)\\{3,2} U nbrs(4)\\{3,4} = {1,2,4};
+    relink(2): ranked [1 (1.0), 4 (4.0)] -> row [1,4]; new edge 4 gets the reciprocal -> row(4) = [2];
+    relink(4): ranked [2 (4.0), 1 (9.0)] -> row [2,1] -> canonical [1,2]; new edge 1 gets the reciprocal -> row(1) = [2,4]."""
+    ix = hxo.Index(hxo.EUCLIDEAN, 2, m=2, m0=4, ef_construction=8)
+    for i in (1, 2, 3, 4):
+        ix.put_vector(i, [float(i), 0.0])
+    for node, nb in ((1, [2]), (2, [1, 3]), (3, [2, 4]), (4, [3])):
+        ix.put_neighbors(0, node, nb)
+    ix.set_entry(1, 0)
+    assert ix.delete(3) is True
+    assert {i: ix.neighbors(0, i).tolist() for i in (1, 2, 4)} == {1: [2, 4], 2: [1, 4], 4: [1, 2]}
+    assert ix.neighbors(0, 3).tolist() == [] and ix.node_ids().tolist() == [1, 2, 4] and ix.state() == (1, 0)
+    assert ix.delete(3) is False and ix.delete(99) is False     # idempotent; an unknown id is Ok(false)
+    ids, _ = ix.search([3.0, 0.0], 4)
+    assert ids.tolist() == [2, 4, 1]                            # d = 1, 1, 4: the (score, id) order; 3 is gone
+
+
+def test_delete_contract_fixture_of_the_reference(hxo):
+    """T/vector/mutation.rs:705-750,843-871 (`run_graph_delete_contracts`: Cosine d=3, m=2, m0=4, ef_construction=8, six
+    scripted inserts) and V/index.rs:3540-3600: a deleted node is never returned, the entry point stays live
+    (the highest remaining layer, smallest id), node layers read back (1 -> 2, 2 -> 1, unknown -> none), deleting the
+    last node leaves `Empty`, and the next insert takes the first-insert path again."""
+    ix = hxo.Index(hxo.COSINE, 3, m=2, m0=4, ef_construction=8)
+    for nid, v, layer in [(1, [1.0, 0.0, 0.0], 2), (2, [0.9, 0.1, 0.0], 1), (3, [0.8, 0.2, 0.0], 0),
+                          (4, [0.7, 0.3, 0.0], 0), (5, [0.6, 0.4, 0.0], 0), (6, [0.0, 1.0, 0.0], 0)]:
+        ix.insert(nid, v, layer)
+    assert (ix.node_level(1), ix.node_level(2), ix.node_level(999)) == (2, 1, -1) and ix.state() == (1, 2)
+    assert ix.delete(3) is True
+    for layer in (0, 1, 2):
+        for node in (1, 2, 4, 5, 6):
+            assert 3 not in ix.neighbors(layer, node).tolist()
+    assert 3 not in ix.search([0.8, 0.2, 0.0], 6)[0].tolist() and len(ix) == 5
+    assert ix.delete(1) is True                                 # the entry point
+    assert ix.state() == (2, 1) and ix.neighbors(1, 2).tolist() == []
+    assert sorted(ix.search([1.0, 0.0, 0.0], 6)[0].tolist()) == [2, 4, 5, 6]
+    for nid in (2, 4, 5, 6):
+        assert ix.delete(nid) is True
+    assert ix.state() is None and len(ix) == 0 and ix.search([1.0, 0.0, 0.0], 3)[0].tolist() == []
+    ix.insert(7, [1.0, 0.0, 0.0], 1)
+    assert ix.state() == (7, 1) and ix.search([1.0, 0.0, 0.0], 3)[0].tolist() == [7]
+
+
+@pytest.mark.parametrize("metric_name", ["EUCLIDEAN", "COSINE"])
+def test_delete_keeps_the_graph_invariants_and_recall(hxo, metric_name):
+    """The reference's structural invariants (V/index.rs:3617-3701: degree <= limit, no self link, strictly ascending
+    rows) must survive deletions, no row may name a deleted node on any layer, the entry point must be a live node of
+    the highest remaining layer, and the repaired graph must still search well (recall@10 vs the exact scan)."""
+    metric = getattr(hxo, metric_name)
+    rng = np.random.default_rng(31)
+    n, dim = 600, 12
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    ix = hxo.Index(metric, dim, m=8, m0=16, ef_construction=64)
+    ml = hxo.lib().hxo_default_ml_for_m(8)
+    lv = [int(hxo.lib().hxo_select_layer_from_uniform(ml, float(u))) for u in rng.random(n, dtype=np.float32)]
+    for i in range(n):
+        ix.insert(i + 1, rows[i], lv[i])
+    entry0, top0 = ix.state()
+    victims = [entry0] + [int(x) for x in rng.permutation(np.arange(1, n + 1))[:200] if int(x) != entry0]
+    alive = set(range(1, n + 1))
+    for step, v in enumerate(victims):
+        assert ix.delete(v) is True
+        alive.discard(v)
+        if step % 40 == 0 or step == len(victims) - 1:
+            entry, top = ix.state()
+            levels = {i: ix.node_level(i) for i in alive}
+            assert entry in alive and top == max(levels.values()) == levels[entry]
+            assert entry == min(i for i in alive if levels[i] == top)
+            for layer in range(0, top0 + 1):
+                limit = ix.layer0_limit if layer == 0 else 8
+                for i in alive:
+                    r = ix.neighbors(layer, i).tolist()
+                    assert len(r) <= limit and i not in r and all(a < b for a, b in zip(r, r[1:]))
+                    assert alive.issuperset(r), (layer, i)
+            for v2 in victims[:step + 1]:
+                assert all(len(ix.neighbors(layer, v2)) == 0 for layer in range(0, top0 + 1))
+    assert len(ix) == n - len(victims)
+    queries = rng.standard_normal((60, dim)).astype(np.float32)
+    hit = 0
+    for q in queries:
+        got, _ = ix.search(q, 10, ef=64)
+        want, _ = ix.search_exact(q, 10)
+        assert alive.issuperset(got.tolist())
+        hit += len(set(got.tolist()) & set(want.tolist()))
+    assert hit / 600.0 >= 0.95

@@ -796,3 +796,40 @@ def test_delete_keeps_the_graph_invariants_and_recall(hxo, metric_name):
         assert alive.issuperset(got.tolist())
         hit += len(set(got.tolist()) & set(want.tolist()))
     assert hit / 600.0 >= 0.95
+
+
+def test_restricted_admission_literals_of_the_reference(hxo):
+    """T/vector/restricted.rs:459-591 literal for literal: the exact / filtered-graph plan boundary, the filtered budgets
+    for 1 000 candidates at k = 10 / ef = 100 (beam percent 100 / 150 / 200 and the x2 / x4 multipliers of the 150 % default),
+    deterministic seeds, and the result-count clamp (MAX_RESTRICTED_RESULT_COUNT = 800 = the vector-payload budget)."""
+    L = hxo.lib()
+    assert L.hxo_restricted_plan(256, 1536) == 0               # Exact: 256 ids, 1.5 MiB of vectors
+    assert L.hxo_restricted_plan(256, 5000) == 1               # FilteredGraph: 256 * 5000 * 4 B > 4 MiB
+    assert L.hxo_restricted_plan(257, 2) == 1                  # FilteredGraph: cardinality alone
+    assert L.hxo_restricted_plan(1000, 1536) == 1
+
+    def budgets(k, ef, percent, n):
+        b = hxo.FilteredBudgets()
+        L.hxo_filtered_budgets(k, ef, percent, n, _C.byref(b))
+        return b
+
+    # beam percent 100 / 150 (the default) / 200, and the x2 / x4 beam multipliers (= percent 200 / 400)
+    for percent, want in ((100, 100), (150, 150), (200, 200), (400, 400)):
+        b = budgets(10, 100, percent, 1000)
+        assert b.ef_filtered == want
+        assert (b.sampled_seeds, b.vector_payloads) == (64, 800)              # FILTERED_SAMPLED_SEEDS, ..._PAYLOAD_LIMIT
+        assert (b.routing_rows, b.bridge_rows) == (want * 16, want * 8)
+    assert budgets(10, 0, 0, 1000).ef_filtered == 150          # SearchParams::new(10): ef = 100, FILTERED_BEAM_PERCENT
+    assert budgets(10, 100, 150, 40).ef_filtered == 40         # min(candidate_count)
+    assert budgets(30, 100, 100, 1000).ef_filtered == 120      # max(k * 4)
+    ids = np.arange(1, 100_001, dtype=np.uint64)
+    s = hxo.deterministic_sample_ids(ids, 256)
+    assert len(s) == 256 and all(a < b for a, b in zip(s, s[1:]))
+    assert hxo.deterministic_sample_ids([7], 1).tolist() == [7]
+    assert hxo.deterministic_sample_ids([3, 7], 1).tolist() == [3]
+    assert hxo.deterministic_sample_ids([3, 7], 8).tolist() == [3, 7]
+    assert hxo.restricted_result_count(800, 1000) == (hxo.OK, 800)
+    assert hxo.restricted_result_count(800 + 200, 800) == (hxo.OK, 800)      # clamps to |C| before the limit check
+    assert hxo.restricted_result_count(800 + 1, 1000)[0] == hxo.ERR_QUERY
+    b = budgets(800, 800, 150, 1000)
+    assert b.vector_payloads == 800 and b.vector_payloads >= 800

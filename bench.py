@@ -239,7 +239,7 @@ def exact_topk_device(hx, torch, ix, queries, n, first_id, k):
     return exact_topk_device_full(hx, torch, ix, queries, n, first_id, k)[0]
 
 
-def c2_config(args, world, setup=None):
+def c2_config(args, world):
     """The `config` object of the C2 line — shared verbatim by our arm and the --impl reference arm."""
     n, dim, Q = args.n, args.dim, args.queries_per_step
     cfg = {
@@ -255,8 +255,6 @@ def c2_config(args, world, setup=None):
                         + (f"rank-{KIND} latent space -> fixed random projection to {dim}-d + 2% noise"
                            if KIND else f"isolated isotropic clusters in {dim}-d") + ", seed=0x0DB9ED1A"),
     }
-    if setup is not None:
-        cfg["setup"] = setup
     return cfg
 
 
@@ -1103,7 +1101,8 @@ def run_ours(args):
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "recall_at_10": round(recall, 4),
-            "config": c2_config(args, world, setup),
+            "config": c2_config(args, world),
+            "setup": setup,                                    # timings of the untimed setup: outside `config`, which both arms share verbatim
             "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4,
                     "d2h_bytes_per_step": Q * (k * 12 + 4) + Q * 8 + 4,
                     "api": "hx_search (C ABI, pinned host buffers, blocking)"},
@@ -1287,7 +1286,8 @@ def run_reference(args):
         "value": round(value, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(total / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "recall_at_10": round(rec, 4),
-        "config": c2_config(args, 1, setup),
+        "config": c2_config(args, args.gpus),              # the config of OUR arm at this N, verbatim (rank 0 alone runs the CPU arm)
+        "setup": setup,
         "sample": f"each step = {per_step} of the workload's {Q} queries per step (a bounded sample: throughput metric), one "
                   f"query per host thread, {cores} threads; the graph both arms traverse is built on the device as untimed setup",
         "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cores, "kind": "port",

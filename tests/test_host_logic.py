@@ -58,3 +58,19 @@ def test_policy_builder_methods_validate_like_the_reference():
         hx.SearchParams.new(10).with_pre_simhash_sampling_ratio(-0.5)
     t = hx.SearchParams.throughput_profile_floor_92(100)  # mod.rs:615-621: ef = max(k, 48)
     assert t.ef() == 100 and t.requires_query_simhash()
+
+
+def test_bench_config_is_shared_verbatim_by_both_arms(monkeypatch):
+    """bench.py: the driver compares the `config` objects of our arm and of `--impl reference`; nothing that varies from run
+    to run (setup timings) may live inside it, and the reference arm quotes OUR arm's config at the same N."""
+    import sys as _sys
+    import bench
+    for n_gpus in (1, 8):
+        monkeypatch.setattr(_sys, "argv", ["bench.py", "--gpus", str(n_gpus)])
+        ours = bench.c2_config(bench.parse(), n_gpus)
+        monkeypatch.setattr(_sys, "argv", ["bench.py", "--gpus", str(n_gpus), "--impl", "reference", "--steps", "3"])
+        ref_args = bench.parse()
+        theirs = bench.c2_config(ref_args, ref_args.gpus)
+        assert ours == theirs and "setup" not in ours
+        assert ours["workload"].startswith("C2: 1000000x768 f32 cosine HNSW top-10")
+        assert ours["queries_per_step_per_gpu"] == 32768

@@ -92,3 +92,19 @@ def test_cpp_host_mirror_compiles_against_the_header(tmp_path):
                    '.requires_query_simhash() ? 0 : 1; }\n' % (ROOT / "helix-db_b200" / "host" / "vector_index.hpp"))
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_cpp_host_mirror_links_and_runs(tmp_path):
+    """The C++ host mirror is not only parsed: tests/cpp/host_mirror_selftest.cpp is linked against libhelix_b200.so and
+    executed.  Without a GPU its device-free half runs (SearchParams / candidate-set contracts of the reference, the pure
+    ABI entry points) and the constructor must refuse with "no CPU fallback"; tests/test_gpu_parity.py runs the same
+    binary on the device."""
+    import shutil
+    import torch
+    from hx_testutil import build_and_run_cpp_selftest
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    rc, out = build_and_run_cpp_selftest(tmp_path)
+    assert rc == 0, out
+    if not torch.cuda.is_available():
+        assert "device-free checks passed" in out, out

@@ -138,61 +138,3 @@ def test_delete_and_hot_lane_rows():
     gpu.load_upper_vector_rows([n + 5], item(fresh_vec))
     assert np.array_equal(gpu.download_vectors(n, 1)[1][0], fresh_vec)
     gpu.close()
-
-
-@pytest.mark.parametrize("gm,om", [(hx.Metric.Euclidean, hxo.EUCLIDEAN), (hx.Metric.Cosine, hxo.COSINE)])
-def test_reference_delete_as_row_patches(gm, om):
-    """VectorIndex::delete (mutation.rs:1606-1773: delete_from_layer + relink_neighbor + entry-candidate promotion) runs on
-    the oracle; the rows it dirtied reach the device as patches (hx_index_delete_vectors, hx_index_upsert_neighbor_rows,
-    hx_index_set_entry).  After every committed write the mirror must answer exactly like the oracle — the first write
-    deletes the entry point and every other node of the top layer, so the graph loses a layer."""
-    rng = np.random.default_rng(23)
-    n, dim, k, ef = 1200, 32, 10, 50
-    rows = rng.standard_normal((n, dim)).astype(np.float32)
-    ids = np.arange(100, 100 + n, dtype=np.uint64)
-    lv = levels_for(n, 8, 11)
-    ora = hxo.Index(om, dim, m=8, m0=16, ef_construction=60)
-    for i in range(n):
-        ora.insert(int(ids[i]), rows[i], lv[i])
-    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("del", "embedding", dim).with_m(8).with_m0(16).with_ef_construction(60))
-    mirror_from_oracle(gpu, ora)
-    entry0, top0 = ora.export_graph()[1]
-    top_nodes = [int(ids[i]) for i in range(n) if lv[i] == top0]
-    assert entry0 in top_nodes and top0 >= 2
-    order = [int(x) for x in rng.permutation(ids) if int(x) not in top_nodes]
-    writes = [top_nodes + order[:20], order[20:60], order[60:100], order[100:140]]
-    q_small = rng.standard_normal((120, dim)).astype(np.float32)   # B < #SMs: the CTA-per-query build
-    q_big = rng.standard_normal((400, dim)).astype(np.float32)     # the warp-per-query build
-    p = hx.SearchParams.strict(k, ef)
-    gone = set()
-    for w, victims in enumerate(writes):
-        before, _ = _graph_rows(ora)
-        for v in victims:
-            assert ora.delete(v) is True
-        gone.update(victims)
-        after, state = _graph_rows(ora)
-        assert not (set(node for _, node in after) & gone)
-        gpu.delete_vectors(victims)
-        assert _apply_diff(gpu, before, after, state) > 0
-        gpu.set_version(3, 10 + w)
-        if w == 0:
-            assert state[1] < top0                             # the top layer is gone, the entry moved down
-        for q in (q_small, q_big):
-            gi, gs, gc = gpu.search_batch(q, p)
-            oi, os_, oc, _, _ = ora.search_batch(q, k, ef, threads=4)
-            assert gc.tolist() == oc.tolist() and gi.tolist() == oi.tolist() and gs.tobytes() == os_.tobytes(), w
-            assert not (set(gi.flatten().tolist()) & gone)
-    # the exact restricted scan skips deleted ids like absent ones
-    cand = np.array(sorted(set(int(x) for x in ids[::5]) | set(list(gone)[:40])), dtype=np.uint64)
-    ri, rs, rc = gpu.search_restricted_batch(q_small[:8], hx.SearchParams.strict(6), hx.RestrictedVectorCandidates(cand))
-    live = np.array([c for c in cand.tolist() if c not in gone], dtype=np.uint64)
-    for b in range(8):
-        ei, es = ora.search_restricted(q_small[b], 6, live)
-        assert ri[b, :rc[b]].tolist() == ei.tolist() and rs[b, :rc[b]].tobytes() == es.tobytes()
-    # a fresh hydration of the final oracle state answers identically
-    fresh = hx.VectorIndex(gm, hx.VectorIndexConfig("fresh", "embedding", dim).with_m(8).with_m0(16).with_ef_construction(60))
-    mirror_from_oracle(fresh, ora)
-    a, b = gpu.search_batch(q_big, p), fresh.search_batch(q_big, p)
-    assert a[0].tolist() == b[0].tolist() and a[1].tobytes() == b[1].tobytes() and a[2].tolist() == b[2].tolist()
-    gpu.close()
-    fresh.close()

@@ -779,15 +779,3 @@ def test_concurrent_host_threads():
         (ai, as_, ac), (bi, bs, bc) = results[t]
         assert ai.tolist() == expected[t][0].tolist() and as_.tobytes() == expected[t][1].tobytes()
         assert bi.tolist() == expected_r[t][0].tolist() and bs.tobytes() == expected_r[t][1].tobytes()
-
-
-def test_cpp_host_mirror_runs_the_phase0_kat_on_the_device(tmp_path):
-    """helix-db_b200/host/vector_index.hpp as a TESTED host binding: a C++ program linked against libhelix_b200.so runs the
-    reference's phase-0 known-answer test (index.rs:2318-2411), the validation-order KAT and a prefiltered scan through
-    helix::VectorIndex on the device (tests/cpp/host_mirror_selftest.cpp)."""
-    import shutil
-    from hx_testutil import build_and_run_cpp_selftest
-    if shutil.which("g++") is None:
-        pytest.skip("g++ not available")
-    rc, out = build_and_run_cpp_selftest(tmp_path)
-    assert rc == 0 and "passed on the device" in out, out

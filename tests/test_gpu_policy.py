@@ -154,52 +154,3 @@ def test_policy_mode_requirements_and_strict_forwarding():
     with pytest.raises(hx.HelixDbError):
         gpu.load_simhash([10**9], [1])                    # a fingerprint for a node without a vector row
     assert hx.load_library().hx_order_code_from_simhash_bits(1 << 47) == 1 << 62
-
-
-def test_reference_layer0_search_mode_contracts_on_the_device():
-    """V/index.rs:2414-2557 (`test_layer0_search_modes_cover_sampling_filtering_and_adaptive_bypass`) through the C ABI:
-    Cosine d=2, m=8, m0=16, ef_construction=32, index threshold 0 / sampling ratio 0.5, 32 points on the unit circle with
-    ids 1..=32.  The reference asserts relations between the four searches (its insertion layers come from `rand::rng()`);
-    here the same relations are asserted on the DEVICE's answers and counters, and every answer is also compared with the
-    oracle bit for bit (tests/test_oracle_kat.py replays the same contract on the oracle alone)."""
-    import math
-    planes = np.random.default_rng(42).standard_normal((64, 2)).astype(np.float32)
-    ang = (np.arange(32, dtype=np.float32) * np.float32(2.0 * math.pi) / np.float32(32.0)).astype(np.float32)
-    rows = np.stack([np.cos(ang, dtype=np.float32), np.sin(ang, dtype=np.float32)], axis=1).astype(np.float32)
-    ids = np.arange(1, 33, dtype=np.uint64)
-    gpu, ora = build_pair(hx.Metric.Cosine, hxo.COSINE, rows, ids=ids, m=8, m0=16, efc=32, seed=4)
-    bits = np.array([hxo.simhash_from_planes(planes, r) for r in rows], dtype=np.uint64)
-    gpu.set_simhash_planes(planes)
-    gpu.compute_simhash()
-    assert gpu.download_simhash(0, 32).tolist() == bits.tolist()
-    ora.put_simhash(ids, bits)
-    qang = (np.arange(48, dtype=np.float32) * np.float32(2.0 * math.pi) / np.float32(48.0) + np.float32(0.01))
-    queries = np.stack([np.cos(qang), np.sin(qang)], axis=1).astype(np.float32)
-    queries[0], queries[1] = (1.0, 0.0), (0.0, 1.0)            # the reference's two queries
-    qsim = np.array([hxo.simhash_from_planes(planes, q) for q in queries], dtype=np.uint64)
-    gpu.set_simhash_config(threshold=0, sampling_ratio=0.5)
-
-    def run(params):
-        st, ps = hx.SearchStats(), hx.PolicyStats()
-        params.collect_stats = True
-        gi, gs, gc = gpu.search_ex(queries[:2], params, query_simhash=qsim[:2], stats=st, policy_stats=ps)
-        compare(gpu, ora, queries, qsim, params, oracle_cfg(params, threshold=0, sampling_ratio=0.5), "circle contract")
-        return gi, gc, st, ps.as_dict()
-
-    def base():                                                # the builders mutate in place: a fresh object per search
-        return hx.SearchParams.new(5).with_ef(16)
-
-    off_i, off_c, off_st, off_ps = run(base().with_simhash_mode(hx.SimHashMode.Off).with_pre_simhash_sampling_ratio(1.0))
-    assert off_c[0] > 0 and off_st.expansion_steps > 0
-    assert off_ps["simhash_examined"] == 0 and off_ps["simhash_filtered"] == 0
-    al_i, al_c, _, al_ps = run(base().with_simhash_mode(hx.SimHashMode.Always).with_pre_simhash_sampling_ratio(1.0)
-                               .with_simhash_sampling_ratio(0.0))
-    assert al_c[0] > 0 and al_ps["simhash_examined"] > 0 and al_ps["simhash_passed_before_sampling"] > 0
-    fx_i, fx_c, _, fx_ps = run(base().with_simhash_mode(hx.SimHashMode.Always).with_pre_simhash_sampling_ratio(1.0)
-                               .with_simhash_sampling_ratio(1.0))
-    assert fx_i[0, :fx_c[0]].tolist() == off_i[0, :off_c[0]].tolist() and fx_ps["simhash_filtered"] == 0
-    ad_i, ad_c, ad_st, ad_ps = run(base().with_simhash_mode(hx.SimHashMode.Adaptive).with_pre_simhash_sampling_ratio(0.25)
-                                   .with_simhash_sampling_ratio(0.5).with_simhash_failure_prob(0.5)
-                                   .with_simhash_bypass_tuning(1, 1, 1.0, 1))
-    assert ad_c[1] > 0 and ad_st.expansion_steps > 0 and ad_ps["simhash_bypass_expansions"] > 0
-    gpu.close()

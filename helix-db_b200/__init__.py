@@ -24,6 +24,8 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libhelix_b200.so"
+if os.environ.get("HELIX_B200_LIB"):            # an alternate BUILD of the same library (A/B of a compile-time option)
+    LIB_PATH = Path(os.environ["HELIX_B200_LIB"]).resolve()
 
 # ---- status codes (include/helix_b200.h) ------------------------------------------------------------------
 HX_OK = 0

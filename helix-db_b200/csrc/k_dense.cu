@@ -43,6 +43,30 @@
 #define HXD_STAGES 5
 #define HXD_PARTS 4         // column quarters of a tile: one epilogue warp per (TMEM lane quarter, column quarter)
 #define HXD_T 8             // best rows kept per (query, run of n-tiles, column quarter): 32 per (query, run)
+// Row placement inside a 256-row corpus tile.  A bucket of the fused top-T is (query, run of tiles, 64-COLUMN quarter) and keeps
+// HXD_T rows.  With rows placed in id order a quarter is 64 CONSECUTIVE ids, so a query whose true neighbours are consecutive
+// ids (near-duplicate rows inserted back to back: chunks of one document) could have more than HXD_T of them in one bucket and
+// lose the rest.  HXD_INTERLEAVE = 1 stores row j of a tile at position (j % 4) * 64 + j / 4: consecutive ids land in different
+// quarters (a run of 32 consecutive ids puts at most 8 into any bucket), at no cost to the kernel (same loads, same MMAs; only
+// the slot a column stands for changes).
+#ifndef HXD_INTERLEAVE
+#define HXD_INTERLEAVE 0
+#endif
+// position of tile row j / tile row held at position c (inverse of each other)
+__host__ __device__ __forceinline__ uint32_t hxd_pos_of_row(uint32_t j) {
+#if HXD_INTERLEAVE
+  return (j & 3u) * (HXD_BN / HXD_PARTS) + (j >> 2);
+#else
+  return j;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t hxd_row_at_pos(uint32_t c) {
+#if HXD_INTERLEAVE
+  return (c & (HXD_BN / HXD_PARTS - 1u)) * HXD_PARTS + c / (HXD_BN / HXD_PARTS);
+#else
+  return c;
+#endif
+}
 #define HXD_THREADS 640     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-19: epilogue
 #define HXD_EPI_THREADS 512
 #define HXD_STAGE_CAP 12    // per-thread staging entries (shared memory) between the column test and the top-T insertion
@@ -291,8 +315,9 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         {
           const uint32_t c = et;                        // the first 256 threads stage the 256 row terms of the tile
           if (c < HXD_BN) {
-            float v = (n0 + c < a.n_rows) ? a.row_aux[n0 + c] : 0.f;
-            if (n0 + c >= a.n_rows) v = a.metric == HXM_COSINE ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
+            const bool live = n0 + hxd_row_at_pos(c) < a.n_rows;   // row_aux is indexed by POSITION, the bound is on the row there
+            float v = live ? a.row_aux[n0 + c] : 0.f;
+            if (!live) v = a.metric == HXM_COSINE ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
             ax[c] = v;                                  // padded rows: t = NaN / -inf never beats the threshold
           }
         }
@@ -346,7 +371,11 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           for (int e = 0; e < 8; ++e)
             if (tv[e] > thr) {
               stg_t[cnt * HXD_EPI_THREADS + et] = tv[e];
+#if HXD_INTERLEAVE
+              stg_s[cnt * HXD_EPI_THREADS + et] = n0 + (c0 + e) * HXD_PARTS + half;   // hxd_row_at_pos(half * 64 + c0 + e)
+#else
               stg_s[cnt * HXD_EPI_THREADS + et] = slot0 + c0 + e;
+#endif
               ++cnt;
             }
           if (cnt > HXD_STAGE_CAP - 8 || last) drain();
@@ -387,13 +416,15 @@ k_dense_scores(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
 // f32 rows -> bf16 rows (round to nearest even) with zero padding to ldb, plus the per-row aux term computed from the
 // ROUNDED values (so that approximate scores are self-consistent)
+// `tiled`: the corpus copy — row w goes to its tile position (hxd_pos_of_row); queries keep their order
 __global__ void k_to_bf16(const float* __restrict__ src, size_t rows, uint32_t dim, size_t ld_src, __nv_bfloat16* __restrict__ dst,
-                          uint32_t ldb, float* __restrict__ aux, int metric) {
+                          uint32_t ldb, float* __restrict__ aux, int metric, int tiled) {
   const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (w >= rows) return;
+  const size_t pos = tiled ? (w / HXD_BN) * HXD_BN + hxd_pos_of_row((uint32_t)(w % HXD_BN)) : w;
   const float* s = src + w * ld_src;
-  __nv_bfloat16* d = dst + w * (size_t)ldb;
+  __nv_bfloat16* d = dst + pos * (size_t)ldb;
   float ss = 0.f;
   for (uint32_t j = lane; j < ldb; j += 32) {
     const float x = j < dim ? s[j] : 0.f;
@@ -405,7 +436,7 @@ __global__ void k_to_bf16(const float* __restrict__ src, size_t rows, uint32_t d
   ss += __shfl_xor_sync(0xffffffffu, ss, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 8);
   ss += __shfl_xor_sync(0xffffffffu, ss, 4);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
   ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-  if (lane == 0) aux[w] = metric == HXM_COSINE ? (ss > 0.f ? rsqrtf(ss) : 0.f) : ss;
+  if (lane == 0) aux[pos] = metric == HXM_COSINE ? (ss > 0.f ? rsqrtf(ss) : 0.f) : ss;
 }
 
 // keys[q][j] hold GLOBAL slots in their low word; turn the selected ones into a per-query candidate slot list
@@ -452,7 +483,7 @@ static hx_status ensure_bf16(hx_index* ix, uint32_t ldb) {
   HX_CUDA(cudaMalloc((void**)&ix->d_sqnorm, n_pad * sizeof(float)));
   HX_CUDA(cudaMemset(ix->d_sqnorm, 0, n_pad * sizeof(float)));
   k_to_bf16<<<(unsigned)((ix->n + 7) / 8), 256>>>(ix->d_vec, ix->n, ix->cfg.dimension, ix->ld, (__nv_bfloat16*)ix->d_vec_bf16, ldb,
-                                                  ix->d_sqnorm, ix->cfg.metric);
+                                                  ix->d_sqnorm, ix->cfg.metric, 1);
   HX_CUDA(cudaGetLastError());
   return HX_OK;
 }
@@ -573,7 +604,7 @@ hx_status hx_dense_device(hx_index* ix, HxScratch* scr, const float* d_q, size_t
   }
   k_validate_and_header<<<(unsigned)((B + 7) / 8), 256, 0, stream>>>(d_q, B, dim, dim, ix->cfg.metric, limit, has_limit ? 1 : 0,
                                                                     d_qhdr, d_status);
-  k_to_bf16<<<(unsigned)((B + 7) / 8), 256, 0, stream>>>(d_q, B, dim, dim, d_qb, ldb, d_qaux, ix->cfg.metric);
+  k_to_bf16<<<(unsigned)((B + 7) / 8), 256, 0, stream>>>(d_q, B, dim, dim, d_qb, ldb, d_qaux, ix->cfg.metric, 0);
   launches += 2;
   HX_CUDA(cudaGetLastError());
   // ---- tensor-core pass ----

@@ -1801,6 +1801,20 @@ int hxo_index_delete(hxo_index* ix, uint64_t id, int* existed) {
   return HXO_OK;
 }
 
+/* VectorInsertContract::Upsert (mutation.rs:653-661): an existing item is deleted through the full delete path first,
+ * then the vector is inserted like a fresh one (new layer draw, new links). */
+int hxo_index_upsert(hxo_index* ix, uint64_t id, const float* v, uint16_t node_layer) {
+  const uint32_t s = slot_of(ix, id);
+  if (s != UINT32_MAX && ix->has_vec[s]) {
+    uint32_t bad;
+    int rc = hxo_validate_vector(ix->metric, ix->dim, v, ix->dim, &bad); /* validation precedes every write */
+    if (rc) return rc;
+    rc = hxo_index_delete(ix, id, NULL);
+    if (rc) return rc;
+  }
+  return hxo_index_insert(ix, id, v, node_layer);
+}
+
 /* ------------------------------------------------------------------------------------------
  * Bulk graph import (slot space = rank of ascending id), as downloaded from the device
  * ------------------------------------------------------------------------------------------ */

@@ -115,6 +115,8 @@ int hxo_index_insert(hxo_index* idx, uint64_t id, const float* v, uint16_t layer
  * (delete_from_layer :1819, relink_neighbor :1916), drops its rows / vector / fingerprint and, when it was the entry
  * point, promotes the best live entry candidate (highest layer, then smallest id).  *existed = the item was present. */
 int hxo_index_delete(hxo_index* idx, uint64_t id, int* existed);
+/* VectorInsertContract::Upsert (mutation.rs:653-661): delete an existing item, then insert */
+int hxo_index_upsert(hxo_index* idx, uint64_t id, const float* v, uint16_t layer);
 
 /* Row export (for mirroring into the device index). */
 size_t hxo_index_node_ids(const hxo_index* idx, uint64_t* out, size_t cap);            /* ascending */

@@ -220,6 +220,8 @@ def lib():
     L.hxo_index_set_entry.argtypes = [C.c_void_p, C.c_uint64, C.c_uint16]
     L.hxo_index_insert.restype = C.c_int
     L.hxo_index_insert.argtypes = [C.c_void_p, C.c_uint64, fp, C.c_uint16]
+    L.hxo_index_upsert.restype = C.c_int
+    L.hxo_index_upsert.argtypes = [C.c_void_p, C.c_uint64, fp, C.c_uint16]
     L.hxo_index_delete.restype = C.c_int
     L.hxo_index_delete.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
     L.hxo_index_node_ids.restype = sz
@@ -439,6 +441,12 @@ class Index:
         va, vp = _f32(v)
         assert va.size == self.dim
         self._ck(self.L.hxo_index_insert(self.h, node_id, vp, layer))
+
+    def upsert(self, node_id, v, layer):
+        """insert with VectorInsertContract::Upsert (mutation.rs:653-661): an existing item is deleted first."""
+        va, vp = _f32(v)
+        assert va.size == self.dim
+        self._ck(self.L.hxo_index_upsert(self.h, node_id, vp, layer))
 
     def delete(self, node_id) -> bool:
         """VectorIndex::delete (mutation.rs:1606-1773); True when the item existed."""

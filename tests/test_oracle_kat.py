@@ -833,3 +833,28 @@ def test_restricted_admission_literals_of_the_reference(hxo):
     assert hxo.restricted_result_count(800 + 1, 1000)[0] == hxo.ERR_QUERY
     b = budgets(800, 800, 150, 1000)
     assert b.vector_payloads == 800 and b.vector_payloads >= 800
+
+
+def test_upsert_contracts_of_the_reference(hxo):
+    """V/index.rs:3033-3050 (`test_upsert_insert_replaces_existing_vector`): the replacement vector is the one kept and the
+    count stays 1; V/index.rs:3053-3100 (`test_upsert_entry_reconnects_layer0_for_every_layer_assignment`): for every
+    scripted assignment of {first, fallback, replacement} layers in 0..=2, deleting the entry node 0 and re-inserting it with
+    another vector restores the bidirectional layer-0 link with node 1, and the closer node answers the query."""
+    ix = hxo.Index(hxo.COSINE, 2)
+    ix.upsert(1, [1.0, 0.0], 0)
+    ix.upsert(1, [0.0, 1.0], 0)
+    assert ix.vector(1).tolist() == [0.0, 1.0] and len(ix) == 1 and ix.state() == (1, 0)
+    for first in range(3):
+        for fallback in range(3):
+            for replacement in range(3):
+                ix = hxo.Index(hxo.COSINE, 2)
+                ix.insert(0, [1.0, 0.0], first)
+                ix.insert(1, [0.0, 1.0], fallback)
+                assert ix.delete(0) is True
+                assert ix.state() == (1, fallback)             # the fallback is promoted with its own layer
+                ix.insert(0, [-1.0, 0.0], replacement)
+                what = (first, fallback, replacement)
+                assert 1 in ix.neighbors(0, 0).tolist() and 0 in ix.neighbors(0, 1).tolist(), what
+                assert ix.state() == ((0, replacement) if replacement > fallback else (1, fallback)), what
+                ids, _ = ix.search([1.0, 0.0], 1)              # strict walk; two nodes leave the default mode nothing to sample
+                assert ids.tolist() == [1], what

@@ -374,6 +374,12 @@ extern "C" hx_status hx_index_create(const hx_index_config* cfg, hx_index** out)
     hx_set_error("invalid vector index config: dimension=%u m=%u metric=%d", cfg->dimension, cfg->m, cfg->metric);
     return HX_ERR_INVALID_VECTOR_CONFIG;
   }
+  // Layer0Connections / ConstructionBeamWidth (parameters.rs:54-100, config/indexes.rs:413-417): both must cover m
+  if (cfg->m0 < cfg->m || cfg->ef_construction < cfg->m) {
+    hx_set_error("invalid vector index config: m0=%u and ef_construction=%u must be at least m=%u", cfg->m0,
+                 cfg->ef_construction, cfg->m);
+    return HX_ERR_INVALID_VECTOR_CONFIG;
+  }
   if (cfg->dimension > 65536) {
     hx_set_error("dimension %u above the supported maximum 65536", cfg->dimension);
     return HX_ERR_INVALID_VECTOR_CONFIG;

@@ -108,3 +108,16 @@ def test_cpp_host_mirror_links_and_runs(tmp_path):
     assert rc == 0, out
     if not torch.cuda.is_available():
         assert "device-free checks passed" in out, out
+
+
+def test_index_config_is_validated_before_the_device_is_touched():
+    """Connections / Layer0Connections / ConstructionBeamWidth (parameters.rs:25-100, config/indexes.rs:411-466): m is
+    non-zero and both m0 and ef_construction must cover it -> InvalidVectorConfig, with or without a GPU."""
+    def make(**kw):
+        cfg = hx.VectorIndexConfig("t", "embedding", kw.pop("dimension", 8))
+        cfg.m, cfg.m0, cfg.ef_construction = kw.get("m", 16), kw.get("m0", 32), kw.get("efc", 200)
+        return hx.VectorIndex(hx.Metric.Cosine, cfg)
+    for bad in (dict(m=0), dict(m=16, m0=15), dict(m=16, efc=15), dict(dimension=0), dict(m=64)):   # m=64 > default m0=32
+        with pytest.raises(hx.HelixDbError) as e:
+            make(**bad)
+        assert e.value.variant == "InvalidVectorConfig", bad

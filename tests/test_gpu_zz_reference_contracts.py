@@ -135,3 +135,33 @@ def test_cpp_host_mirror_runs_the_phase0_kat_on_the_device(tmp_path):
         pytest.skip("g++ not available")
     rc, out = build_and_run_cpp_selftest(tmp_path)
     assert rc == 0 and "passed on the device" in out, out
+
+
+@pytest.mark.parametrize("gm,om", [(hx.Metric.Cosine, hxo.COSINE), (hx.Metric.Euclidean, hxo.EUCLIDEAN)])
+def test_dense_path_keeps_id_clustered_neighbours(gm, om):
+    """hx_search_dense nominates by bucket — (query, run of tiles, 64-column quarter), best HXD_T = 8 rows each.  With rows
+    placed in id order a bucket holds 64 CONSECUTIVE ids per tile, so a query whose 11 nearest rows are consecutive ids (chunks
+    of one document inserted back to back) would keep only 8 of them (measured: recall 0.8 on exactly this fixture,
+    profiles/r02_dense_row_placement_ab.json).  The interleaved placement (HXD_INTERLEAVE, csrc/k_dense.cu) spreads consecutive
+    ids over the four quarters: every true neighbour must come back, with the oracle's exact scan as the ground truth."""
+    rng = np.random.default_rng(77)
+    n, dim, k, nh = 40_000, 64, 10, 16
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    hq = rng.standard_normal((nh, dim)).astype(np.float32)
+    for h in range(nh):
+        base = 2048 * h + 192                                  # tile rows 192..202: inside the fourth 64-row stripe of a tile
+        for i in range(11):
+            rows[base + i] = hq[h] + np.float32(0.01 * (i + 1)) * rng.standard_normal(dim).astype(np.float32)
+    ids = np.arange(n, dtype=np.uint64)
+    gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("hz", "embedding", dim), storage=1)
+    gpu.load_vectors(ids, rows)
+    gpu.load_graph(0, ids[:1], [0, 0], [])
+    gpu.set_entry(int(ids[0]), 0)
+    ora = hxo.Index(om, dim)
+    ora.put_vectors(ids, rows)
+    di, ds, dc = gpu.search_dense_batch(hq, hx.SearchParams.strict(k))
+    for h in range(nh):
+        oi, os_ = ora.search_exact(hq[h], k)
+        assert set(oi.tolist()) <= set(range(2048 * h + 192, 2048 * h + 203))      # the fixture is what it claims to be
+        assert di[h, :dc[h]].tolist() == oi.tolist() and ds[h, :dc[h]].tobytes() == os_.tobytes(), h
+    gpu.close()

@@ -42,7 +42,9 @@
 #define HXD_BK 64           // bf16 elements per k-block = 128 bytes = one swizzle atom
 #define HXD_STAGES 5
 #define HXD_PARTS 4         // column quarters of a tile: one epilogue warp per (TMEM lane quarter, column quarter)
+#ifndef HXD_T
 #define HXD_T 8             // best rows kept per (query, run of n-tiles, column quarter): 32 per (query, run)
+#endif
 // Row placement inside a 256-row corpus tile.  A bucket of the fused top-T is (query, run of tiles, 64-COLUMN quarter) and keeps
 // HXD_T rows.  With rows placed in id order a quarter is 64 CONSECUTIVE ids, so a query whose true neighbours are consecutive
 // ids (near-duplicate rows inserted back to back: chunks of one document) could have more than HXD_T of them in one bucket and

@@ -17,17 +17,26 @@ from oracle import hxo  # noqa: E402
 
 
 def main():
+    out = {"lib": os.environ.get("HELIX_B200_LIB", "default"), "version": hx.version()}
+    # stride 1: consecutive ids (what real corpora do); stride 4: ids congruent mod 4 inside one tile — the adversarial layout
+    # for the interleaved placement (every near-duplicate lands in the same column quarter again)
+    for stride in (1, 4):
+        out[f"stride_{stride}"] = fixture(stride)
+    print(json.dumps(out))
+
+
+def fixture(stride):
     rng = np.random.default_rng(77)
     n, dim, k, nh, nr = 40_000, 64, 10, 16, 240
     rows = rng.standard_normal((n, dim)).astype(np.float32)
     hq = rng.standard_normal((nh, dim)).astype(np.float32)
     for h in range(nh):
-        base = 2048 * h + 192                                  # tile row 192..202: the fourth 64-row stripe of its tile
+        base = 2048 * h + 192                                  # tile row 192 + stride * i, i < 11: inside one 256-row tile
         for i in range(11):
-            rows[base + i] = hq[h] + np.float32(0.01 * (i + 1)) * rng.standard_normal(dim).astype(np.float32)
+            rows[base + stride * i] = hq[h] + np.float32(0.01 * (i + 1)) * rng.standard_normal(dim).astype(np.float32)
     queries = np.concatenate([hq, rng.standard_normal((nr, dim)).astype(np.float32)])
     ids = np.arange(n, dtype=np.uint64)
-    out = {"lib": os.environ.get("HELIX_B200_LIB", "default"), "version": hx.version()}
+    out = {}
     for gm, om, name in ((hx.Metric.Cosine, hxo.COSINE, "cosine"), (hx.Metric.Euclidean, hxo.EUCLIDEAN, "euclidean")):
         gpu = hx.VectorIndex(gm, hx.VectorIndexConfig("hz", "embedding", dim), storage=1)
         gpu.load_vectors(ids, rows)
@@ -50,7 +59,7 @@ def main():
         out[name] = {"hazard_recall": hit_h / float(nh * k), "random_recall": hit_r / float(nr * k),
                      "returned_scores_bit_exact": exact_scores == hit_h + hit_r}
         gpu.close()
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":

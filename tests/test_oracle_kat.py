@@ -421,6 +421,17 @@ def test_simhash_primitives_and_order_code(hxo):
         assert L.hxo_order_code_from_simhash_bits(1 << band_shift) == 1 << code_bit
     assert L.hxo_simhash_collision_count(0, 0) == 64 and L.hxo_simhash_collision_count(0, 2**64 - 1) == 0
     assert L.hxo_simhash_collision_count(0b1010, 0b0110) == 62                           # unaligned_vector/simhash.rs:37-40
+    # the reference's own literals (unaligned_vector/simhash.rs:326-376): collision counts, Hamming distance, the threshold gate
+    A, B5 = 0xAAAA_AAAA_AAAA_AAAA, 0x5555_5555_5555_5555
+    assert L.hxo_simhash_collision_count(A, A) == 64 and L.hxo_simhash_collision_count(A, B5) == 0
+    assert L.hxo_simhash_collision_count(A, 0xAAAA_AAAA_0000_0000) == 48
+    F = 2**64 - 1
+    assert 64 - L.hxo_simhash_collision_count(F, F) == 0 and 64 - L.hxo_simhash_collision_count(F, 0) == 64
+    assert 64 - L.hxo_simhash_collision_count(F, F - 1) == 1
+    near = 0xFFFF_FFFF_FFFF_FFF0                                                         # 60 matching bits
+    assert L.hxo_simhash_collision_count(F, near) >= 60 and not L.hxo_simhash_collision_count(F, near) >= 61
+    # a zero vector has no positive projection: fingerprint 0 (`dot_product > 0.0`, :283-286), deterministically
+    assert hxo.simhash_from_planes(np.random.default_rng(3).standard_normal((64, 16)).astype(np.float32), np.zeros(16, np.float32)) == 0
     rng = np.random.default_rng(1)
     planes = rng.standard_normal((64, 9)).astype(np.float32)
     v = rng.standard_normal(9).astype(np.float32)

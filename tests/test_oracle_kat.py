@@ -869,3 +869,23 @@ def test_upsert_contracts_of_the_reference(hxo):
                 assert ix.state() == ((0, replacement) if replacement > fallback else (1, fallback)), what
                 ids, _ = ix.search([1.0, 0.0], 1)              # strict walk; two nodes leave the default mode nothing to sample
                 assert ids.tolist() == [1], what
+
+
+def test_distance_score_and_candidate_contracts(hxo):
+    """V/parameters.rs tests (`distance_score_is_finite_nonnegative_and_totally_ordered`), V/model.rs tests
+    (`candidate_rejects_invalid_scores_and_orders_ties_by_node`) and V/index.rs:2115-2124: NaN / +-inf / negative scores are
+    InvariantViolation, -0.0 is stored as +0.0, and candidates order by (score, then node id)."""
+    L = hxo.lib()
+    for bad in (float("nan"), float("inf"), float("-inf"), -1.0):
+        v = _C.c_float(bad)
+        assert L.hxo_score_validate(_C.byref(v)) == hxo.ERR_INVARIANT_VIOLATION
+    z = _C.c_float(-0.0)
+    assert L.hxo_score_validate(_C.byref(z)) == hxo.OK and bits(z.value) == bits(0.0)
+    one = _C.c_float(1.0)
+    assert L.hxo_score_validate(_C.byref(one)) == hxo.OK and one.value == 1.0
+    # ordering through the public result: equal scores come back in ascending id order, smaller scores first
+    ix = hxo.Index(hxo.EUCLIDEAN, 2)
+    for nid, v in ((3, [1.0, 0.0]), (1, [1.0, 0.0]), (2, [2.0, 0.0]), (7, [0.5, 0.0])):
+        ix.put_vector(nid, v)
+    ids, sc = ix.search_exact([0.0, 0.0], 4)
+    assert ids.tolist() == [7, 1, 3, 2] and sc.tolist() == [0.25, 1.0, 1.0, 4.0]

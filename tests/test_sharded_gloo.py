@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, n):
     sys.path.insert(0, str(ROOT))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -33,7 +33,7 @@ def _worker(rank, world, port, ret):
     sh = import_module("helix_db_b200.sharding")
     from oracle import hxo
 
-    n, dim, Q, k = 600, 16, 9, 5
+    dim, Q, k = 16, 9, 5
     rng = np.random.default_rng(99)                       # same data on every rank
     rows = rng.integers(-2, 3, size=(n, dim)).astype(np.float32)
     queries = rng.integers(-2, 3, size=(Q, dim)).astype(np.float32)
@@ -102,10 +102,10 @@ def _worker(rank, world, port, ret):
     ret[rank] = True
 
 
-def test_sharded_host_logic_world2_gloo():
-    world = 2
+@pytest.mark.parametrize("world,n", [(2, 600), (4, 601)])          # 601: shards of unequal size
+def test_sharded_host_logic_gloo(world, n):
     port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, ret, n), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world))

@@ -121,3 +121,22 @@ def test_index_config_is_validated_before_the_device_is_touched():
         with pytest.raises(hx.HelixDbError) as e:
             make(**bad)
         assert e.value.variant == "InvalidVectorConfig", bad
+
+
+def test_product_plan_and_budget_functions_match_the_reference_literals():
+    """The PRODUCT's device-free planning entry points (not the oracle's): hx_restricted_plan and hx_filtered_budgets against
+    the literals of the reference's admission test (tests/production_support/vector/restricted.rs:459-530)."""
+    import ctypes as C
+    lib = hx.load_library()
+    assert hx.restricted_plan(256, 1536) == "Exact" and hx.restricted_plan(256, 5000) == "FilteredGraph"
+    assert hx.restricted_plan(257, 2) == "FilteredGraph" and hx.restricted_plan(1000, 1536) == "FilteredGraph"
+    for percent, want in ((100, 100), (150, 150), (200, 200), (400, 400), (0, 150)):   # 0 = FILTERED_BEAM_PERCENT
+        b = hx.FilteredBudgets()
+        lib.hx_filtered_budgets(10, 100, percent, 1000, C.byref(b))
+        assert b.ef_filtered == want and (b.sampled_seeds, b.vector_payloads) == (64, 800)
+        assert (b.routing_rows, b.bridge_rows) == (want * 16, want * 8)
+    b = hx.FilteredBudgets()
+    lib.hx_filtered_budgets(800, 800, 150, 1000, C.byref(b))
+    assert b.vector_payloads == 800                             # MAX_RESTRICTED_RESULT_COUNT == the payload budget
+    lib.hx_filtered_budgets(10, 100, 150, 40, C.byref(b))
+    assert (b.ef_filtered, b.sampled_seeds, b.vector_payloads) == (40, 40, 40)   # everything clamps to |C|

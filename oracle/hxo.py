@@ -15,6 +15,8 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 _SO = _HERE / "_build" / "libhx_oracle.so"
+if os.environ.get("HXO_ORACLE_SO"):                # another build of the same checker (oracle/Makefile: `make asan`)
+    _SO = Path(os.environ["HXO_ORACLE_SO"]).resolve()
 
 EUCLIDEAN, COSINE, MANHATTAN = 0, 1, 2
 METRICS = {"euclidean": EUCLIDEAN, "cosine": COSINE, "manhattan": MANHATTAN}

@@ -100,7 +100,44 @@ def compute(levels=None):
     return out
 
 
+MUT_OUT = Path(__file__).with_name("mutation_golden.json")
+N_DELETE, N_UPSERT = 150, 30
+
+
+def compute_mutations(levels):
+    """The write path after the build: VectorIndex::delete (mutation.rs:1606-2050: delete_from_layer, relink_neighbor,
+    entry-candidate promotion) for a scripted list of ids that starts with the entry point, then Upsert (mutation.rs:653-661)
+    of scripted ids with new vectors and layers.  Frozen per metric: the adjacency digest, the entry point and the strict
+    top-k of the fixture's queries after each phase."""
+    ids, rows, queries, _ = inputs()
+    newrows = hxo.xorshift_vectors(3_000_003, N_UPSERT, DIM)
+    out = {"_generator": "tests/golden/make_golden.py", "n_delete": N_DELETE, "n_upsert": N_UPSERT, "metrics": {}}
+    for name, metric in (("euclidean", hxo.EUCLIDEAN), ("cosine", hxo.COSINE), ("manhattan", hxo.MANHATTAN)):
+        ix = build(metric, ids, rows, levels)
+        entry0 = ix.state()[0]
+        victims = [entry0] + [int(i) for i in ids[3::8] if int(i) != entry0][:N_DELETE - 1]
+        for v in victims:
+            assert ix.delete(v)
+        ent = {"deleted": victims[:4] + ["..."], "after_delete": {"graph_sha256": graph_digest(ix), "state": list(ix.state()),
+                                                                "count": len(ix), "strict": []}}
+        for q in queries:
+            oi, os_ = ix.search(q, K, ef=EF)
+            ent["after_delete"]["strict"].append({"ids": oi.tolist(), "score_bits": hexbits(os_)})
+        targets = [int(i) for i in ids[5::40]][:N_UPSERT]              # some deleted before, some alive: both Upsert arms
+        for j, t in enumerate(targets):
+            ix.upsert(t, newrows[j], int(levels[(7 * j) % len(levels)]))
+        ent["after_upsert"] = {"graph_sha256": graph_digest(ix), "state": list(ix.state()), "count": len(ix), "strict": []}
+        for q in queries:
+            oi, os_ = ix.search(q, K, ef=EF)
+            ent["after_upsert"]["strict"].append({"ids": oi.tolist(), "score_bits": hexbits(os_)})
+        out["metrics"][name] = ent
+    return out
+
+
 if __name__ == "__main__":
     data = compute()
     OUT.write_text(json.dumps(data, separators=(",", ":")) + "\n")
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes)")
+    mut = compute_mutations(data["levels"])
+    MUT_OUT.write_text(json.dumps(mut, separators=(",", ":")) + "\n")
+    print(f"wrote {MUT_OUT} ({MUT_OUT.stat().st_size} bytes)")

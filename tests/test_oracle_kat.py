@@ -889,3 +889,20 @@ def test_distance_score_and_candidate_contracts(hxo):
         ix.put_vector(nid, v)
     ids, sc = ix.search_exact([0.0, 0.0], 4)
     assert ids.tolist() == [7, 1, 3, 2] and sc.tolist() == [0.25, 1.0, 1.0, 4.0]
+
+
+def test_short_and_ramp_vector_literals(hxo):
+    """T/vector/distance_neighbors.rs:148-185: the three kernels on (1,2,3) x (3,2,1), norms, and the 33-element ramps on which
+    the vectorised and the scalar order must agree within 1e-5 relative (here: the AVX-FMA order vs the scalar order)."""
+    a, b = [1.0, 2.0, 3.0], [3.0, 2.0, 1.0]
+    assert hxo.pair("hxo_dot_product", a, b) == 10.0 and hxo.pair("hxo_dot_scalar", a, b) == 10.0
+    assert hxo.pair("hxo_euclidean_distance", a, b) == 8.0 and hxo.pair("hxo_euclid_scalar", a, b) == 8.0
+    assert hxo.pair("hxo_manhattan", a, b) == 4.0
+    assert np.float32(math.sqrt(hxo.pair("hxo_dot_product", [4.0, 6.0], [4.0, 6.0]))) == np.float32(52.0) ** np.float32(0.5)
+    assert np.float32(math.sqrt(hxo.pair("hxo_dot_product", [1.0, -2.0, 3.0], [1.0, -2.0, 3.0]))) == np.sqrt(np.float32(14.0))
+    left = np.arange(33, dtype=np.float32)
+    right = left[::-1].copy()
+    for fast, slow in (("hxo_dot_avx_fma", "hxo_dot_scalar"), ("hxo_euclid_avx_fma", "hxo_euclid_scalar")):
+        f, s = hxo.pair(fast, left, right), hxo.pair(slow, left, right)
+        assert abs(f - s) <= abs(s) * 1e-5
+    assert hxo.pair("hxo_dot_scalar", left, right) == float(sum(i * (32 - i) for i in range(33)))      # exact in f32
